@@ -1,0 +1,421 @@
+"""MultiResolutionGaussianProcess: drop-in for the reference's src/MRGP.py API (constructor, fit, predict,
+public state) with the variational-inference sweep running on one B200 through libcimrgp.so.
+
+Same constructor arguments, same exceptions for the same misuse (MRGP.py:37-126), same meaning of every
+method.  What is NOT carried over (raises NotImplementedError with the reason): the GPy input-warp model
+(`adaptive_inputs=True` without an `input_model`; third-party GP), per-sweep
+interval optimisation (`basis_interval_obj`, next scope row), shared (non region-specific) noise or bias,
+dx > 1 and dy > 2 on the device.
+"""
+import numpy as np
+
+from . import _lib
+from .BasisInterval import BasisInterval
+from .IndexSetGenerator import offsets_of
+from .KernelClass import LaplacianEigenpairs, MaternKernel
+from .engine import Engine
+
+
+class _View(object):
+    """Read-only, lazily materialised mirror of a reference state object."""
+
+    def __init__(self, model, getters, consts):
+        self.__dict__['_model'] = model
+        self.__dict__['_getters'] = getters
+        self.__dict__.update(consts)
+
+    def __getattr__(self, name):
+        g = self.__dict__['_getters'].get(name)
+        if g is None:
+            raise AttributeError(name)
+        return g()
+
+
+class MultiResolutionGaussianProcess(object):
+    def __init__(self, train_xy,
+                 n_basis,
+                 index_set_obj,
+                 basis_function_obj,
+                 spectral_density_obj=None,
+                 basis_interval_obj=None,
+                 interval_factor=1,
+                 adaptive_inputs=False,
+                 standard_normalized_inputs=True,
+                 axis_resolution_specific=False,
+                 ard_resolution_specific=False,
+                 noise_region_specific=True,
+                 bias_region_specific=True,
+                 noninformative_initialization=True,
+                 snr_ratio=None,
+                 full_x=None,
+                 input_model=None,
+                 forced_independence=False,
+                 verbose=False,
+                 device=0,
+                 n_ctas=0):
+        self.verbose = verbose
+        self.forced_independence = forced_independence
+        # MRGP.py:38-50
+        if forced_independence is True:
+            self.axis_resolution_specific = True
+            self.ard_resolution_specific = True
+            if self.verbose is True:
+                print("*** All GPs are forced to be independent *** ")
+        else:
+            if (axis_resolution_specific is False) and (ard_resolution_specific is False):
+                self.axis_resolution_specific = False
+                self.ard_resolution_specific = False
+                if self.verbose is True:
+                    print(" \n *** GPs are conditionally independent given the basis axes *** \n ")
+            else:
+                raise TypeError("not yet supported")
+        self.adaptive_inputs = adaptive_inputs
+        self.standard_normalized_inputs = standard_normalized_inputs
+        self.noise_region_specific = noise_region_specific
+        self.bias_region_specific = bias_region_specific
+        self.n_layers = index_set_obj.get_n_resolutions() + 1
+        self.index_set_obj = index_set_obj
+        self.n_basis = n_basis
+        x_train = np.asarray(train_xy[0], dtype=np.float64)
+        y_train = np.asarray(train_xy[1], dtype=np.float64)
+        self.observations = y_train
+        self.dy = y_train.shape[1]
+        if self.dy < 2:
+            raise ValueError('output dimension must be greater than 1')   # MRGP.py:65-66
+        if noninformative_initialization is not True:
+            raise ValueError('not yet implemented...')                       # Priors.py:27, 49, 80
+        x_train, self.full_x, self.mean_x_train, self.std_x_train = self._normalize_inputs(x_train, full_x)
+
+        def per_layer(value, what):
+            # MRGP.py:71-106
+            if isinstance(value, list) is False:
+                return [value] * self.n_layers
+            if len(value) != self.n_layers:
+                raise ValueError(what + ' must be a list of the same length as the number of resolutions + 1')
+            return value
+        self.spectral_density_obj = per_layer(spectral_density_obj, 'spectral_density_obj')
+        self.basis_function_obj = per_layer(basis_function_obj, 'basis_function_obj')
+        self.use_prior = [s is not None for s in self.spectral_density_obj]
+        self.interval_factor = per_layer(interval_factor, 'interval_factor')
+        if forced_independence is True:
+            basis_interval_obj = None                                        # MRGP.py:108-109
+        if basis_interval_obj is None:
+            self.adaptive_basis_intervals = False
+            self.basis_interval_obj = [BasisInterval() for _ in range(self.n_layers)]
+        else:
+            per_layer(basis_interval_obj, 'basis_interval_obj')
+            raise NotImplementedError('adaptive basis intervals (BasisInterval.learn, BasisInterval.py:18-134) are '
+                                      'not on the device yet; pass basis_interval_obj=None')
+        for b in self.basis_function_obj:
+            if getattr(b, 'name', None) != 'Laplacian':
+                raise TypeError('the device path implements the Laplacian eigenfunction basis only')
+        # Inputs.py:8-55
+        if self.adaptive_inputs is True:
+            if input_model is None:
+                raise NotImplementedError('adaptive_inputs=True needs an input_model: the GPy warp model of the '
+                                          'reference (Inputs.py:22-49) is a third-party GP and out of scope')
+            z = np.atleast_2d(np.linspace(start=np.min(x_train), stop=np.max(x_train), num=x_train.shape[0])).T
+            self.input_model = input_model
+            self.input_z = z if self.full_x is None else np.atleast_2d(
+                np.linspace(start=np.min(self.full_x), stop=np.max(self.full_x), num=self.full_x.shape[0])).T
+            x_used = z
+        else:
+            self.input_model = None
+            x_used = x_train
+        self._x_used = x_used
+        self.dx = x_used.shape[1]
+        self._offsets = offsets_of(index_set_obj)
+        if int(self._offsets[0][-1]) != x_used.shape[0]:
+            raise ValueError('index set does not cover the training samples')
+        self.n_regions = [len(o) - 1 for o in self._offsets]
+        self.n_samps = [list(np.diff(o).astype(int)) for o in self._offsets]
+        sf = [1. if s is None else s.sf for s in self.spectral_density_obj]          # MRGP.py:174-179
+        noise_var0 = 1.0
+        if snr_ratio is not None:
+            noise_var0 = self._compute_initial_noise_var_from_snr(y=y_train, snr_ratio=snr_ratio)
+        spectral, host_spectral = [], []
+        for s in self.spectral_density_obj:
+            if s is None:
+                spectral.append(None)
+                host_spectral.append(None)
+            elif isinstance(s, MaternKernel) or all(hasattr(s, a) for a in ('nu', 'l', 'sf')) and \
+                    getattr(s, 'name', '') == 'Matern':
+                spectral.append((s.nu, s.l, s.sf))
+                host_spectral.append(None)
+            else:
+                spectral.append((1., 1., 1.))
+                host_spectral.append(s)       # any object with .spectral(s): evaluated on the host, uploaded
+        self._engine = Engine(x_used, y_train, self._offsets, n_basis, mode='fi' if forced_independence else 'ci',
+                              spectral=spectral, interval_factor=[float(f) for f in self.interval_factor],
+                              noise_var0=noise_var0, ard_prior_influence=float(np.mean(sf)),
+                              noise_region_specific=noise_region_specific, bias_region_specific=bias_region_specific,
+                              device=device, n_ctas=n_ctas)
+        if any(s is not None for s in host_spectral):
+            eng = self._engine
+            for j, s in enumerate(host_spectral):
+                if s is not None:
+                    lam = eng.get(j, _lib.F_LAMBDA, (self.n_regions[j], n_basis))
+                    eng.put(j, _lib.F_SPECTRAL, np.vectorize(lambda v: s.spectral(np.sqrt(v)))(lam))
+            eng._ck(eng.lib.mrgp_init_state(eng.handle, float(noise_var0), float(np.mean(sf))))
+        self.lower_bound_layer = [[] for _ in range(self.n_layers)]
+        self.lower_bound = []
+        self.lower_bound_terms = []
+
+    # ------------------------------------------------------------------------------------------
+    def _normalize_inputs(self, x_train, full_x):
+        # MRGP.py:278-295
+        x = x_train if full_x is None else np.asarray(full_x, dtype=np.float64)
+        if self.standard_normalized_inputs is True:
+            std_x_train = np.std(x, 0)
+            std_x_train[std_x_train == 0] = 1
+            mean_x_train = np.mean(x, 0)
+            x_train = (x_train - np.full(x_train.shape, mean_x_train)) / np.full(x_train.shape, std_x_train)
+            if full_x is not None:
+                full_x = (x - np.full(x.shape, mean_x_train)) / np.full(x.shape, std_x_train)
+        else:
+            mean_x_train = None
+            std_x_train = None
+        return x_train, full_x, mean_x_train, std_x_train
+
+    @staticmethod
+    def _compute_initial_noise_var_from_snr(y, snr_ratio):
+        # MRGP.py:966-971
+        n_samps = y.shape[0]
+        y_var = (np.linalg.norm(y) ** 2) / n_samps - np.dot(np.mean(y, axis=0), np.mean(y, axis=0))
+        return y_var / snr_ratio
+
+    # ------------------------------------------------------------------------------------------
+    def fit(self, n_iter=1, tol=1e-3, min_iter=10):
+        # MRGP.py:367-412
+        if tol is None:
+            self._engine.sweep(n_iter)
+            self._engine.synchronize()
+            return
+        if self.forced_independence:
+            self._engine.sweep(n_iter)      # MRGP.py:400-401: no bound, no early stop in fi mode
+            self._engine.synchronize()
+            return
+        if n_iter < min_iter:
+            min_iter = n_iter
+        for iter_ in range(1, n_iter + 1):
+            self._engine.sweep(1)
+            lower_bound, lower_bound_layer = self._compute_lower_bound()
+            self.lower_bound.append(lower_bound)
+            for j in range(self.n_layers):
+                self.lower_bound_layer[j].append(lower_bound_layer[j])
+            if iter_ > min_iter:
+                delta_elbo_layer = [self.lower_bound_layer[j][-1] - self.lower_bound_layer[j][-2]
+                                    for j in range(self.n_layers)]
+                if self.verbose is True:
+                    print("\nTotal ELBO: %.4f ... dELBO %.4f" % (self.lower_bound[-1],
+                                                                 self.lower_bound[-1] - self.lower_bound[-2]))
+                if abs(delta_elbo_layer[0]) < abs(tol):
+                    if self.verbose is True:
+                        print("converged: dELBO is smaller than %s" % str(tol))
+                    break
+
+    def _fit(self):
+        self._engine.sweep(1)
+
+    def _independent_fit(self):
+        self._engine.sweep(1)
+
+    def _compute_lower_bound(self, prime_shared_posterior=None):
+        # MRGP.py:414-424; the six terms per layer are kept in lower_bound_terms
+        terms = self._engine.elbo()
+        self.lower_bound_terms.append(terms)
+        ll = [float(v) for v in np.sum(terms, axis=1)]
+        return float(np.sum(ll)), ll
+
+    # ------------------------------------------------------------------------------------------
+    def _warp(self, test_x):
+        # MRGP.py:731-741
+        if self.adaptive_inputs is True:
+            if self.full_x is None:
+                if isinstance(self.input_model, list) is True:
+                    test_x = np.mean([m.predict(test_x) for m in self.input_model], axis=0)
+                else:
+                    test_x = self.input_model.predict(test_x)
+            else:
+                test_x = self.input_z
+        return test_x
+
+    def _norm(self, test_x):
+        test_x = np.asarray(test_x, dtype=np.float64)
+        if self.standard_normalized_inputs is True:
+            test_x = (test_x - np.full(test_x.shape, self.mean_x_train)) / np.full(test_x.shape, self.std_x_train)
+        return test_x
+
+    def get_predicted_mean(self, test_x, index_set_obj=None, number_of_regions=None):
+        # MRGP.py:805-814
+        test_x = self._norm(test_x)
+        if index_set_obj is None:
+            return self._engine.predict_mean(self._warp(test_x))
+        # MRGP.py:757-767
+        if index_set_obj.get_n_resolutions() > self.index_set_obj.get_n_resolutions():
+            raise ValueError('resolution in the test index set must be smaller or equal to that in the '
+                             'train set.')
+        if number_of_regions is None:
+            if self.index_set_obj.divider != index_set_obj.divider:
+                raise ValueError('divider on the training index_set must be'
+                                 ' the same as in the test index_set.')
+        if number_of_regions is not None:
+            if (self.n_regions == number_of_regions) is False:
+                raise ValueError('number of regions in the training must be the same as test.')
+        test_offsets = offsets_of(index_set_obj)
+        for j, off in enumerate(test_offsets):
+            if len(off) - 1 != self.n_regions[j]:
+                raise ValueError('number of regions in the training must be the same as test.')
+        return self._engine.predict_mean(self._warp(test_x), test_offsets)
+
+    def get_central_moment2(self, test_x, index_set_obj=None, number_of_regions=None):
+        # MRGP.py:816-823
+        test_x = self._norm(test_x)
+        if index_set_obj is None:
+            return self._engine.predict_var(self._warp(test_x))
+        raise NotImplementedError('get_central_moment2 with an index set (MRGP.py:863-932) overwrites the latent '
+                                  'functions of the model in the reference; not offered on the device yet')
+
+    def get_test_likelihood(self, test, index_set_obj=None, number_of_regions=None):
+        # MRGP.py:825-831
+        test_x, test_y = test[0], test[1]
+        mf = self.get_predicted_mean(test_x, index_set_obj, number_of_regions)
+        vf = self.get_central_moment2(test_x, index_set_obj=index_set_obj)
+        ll = -0.5 * np.log(2 * np.pi * vf) - 0.5 * (np.linalg.norm((test_y - mf), axis=1) ** 2) / vf
+        return np.mean(ll)
+
+    def get_basis_contributions(self):
+        # MRGP.py:973-982
+        out = []
+        for j in range(self.n_layers):
+            m2 = self._engine.get(j, _lib.F_M2, (self.n_regions[j], self.n_basis))
+            out.append([m2[l] / sum(m2[l]) for l in range(self.n_regions[j])])
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # public state, materialised from the device on access
+    # ------------------------------------------------------------------------------------------
+    def _split(self, j, arr):
+        off = self._offsets[j]
+        return [arr[off[l]:off[l + 1]] for l in range(self.n_regions[j])]
+
+    @property
+    def x(self):
+        return [self._split(j, self._x_used) for j in range(self.n_layers)]
+
+    @property
+    def train_basis_intervals(self):
+        return [list(self._engine.get(j, _lib.F_L, (self.n_regions[j], 1))) for j in range(self.n_layers)]
+
+    @property
+    def lambda_(self):
+        return [list(self._engine.get(j, _lib.F_LAMBDA, (self.n_regions[j], self.n_basis))) for j in range(self.n_layers)]
+
+    @property
+    def spectral_density_prior(self):
+        return [list(self._engine.get(j, _lib.F_SPECTRAL, (self.n_regions[j], self.n_basis))) for j in range(self.n_layers)]
+
+    @property
+    def phi_x(self):
+        """Feature matrices (n_jl, M) per region, rebuilt on the host on demand (KernelClass.py:21-37)."""
+        out = []
+        ids = np.arange(1, self.n_basis + 1, dtype=np.float64)[None, :]
+        for j in range(self.n_layers):
+            L = self._engine.get(j, _lib.F_L, (self.n_regions[j],))
+            row = []
+            for l, xs in enumerate(self._split(j, self._x_used)):
+                row.append((1. / np.sqrt(L[l])) * np.sin((np.pi * ids * (xs + L[l])) / (2 * L[l])))
+            out.append(row)
+        return out
+
+    def _posterior_view(self, j):
+        e, R, M, dy = self._engine, self.n_regions[j], self.n_basis, self.dy
+        F = _lib
+        g = {
+            'scale_precision': lambda: e.get(j, F.F_SCALE_PRECISION, (R, M)),
+            'scale_mean_zeta': lambda: list(e.get(j, F.F_ZETA, (R, M))),
+            'scale_mean_y_tilde': lambda: list(np.swapaxes(e.get(j, F.F_YTILDE, (R, M, dy)), 1, 2)),
+            'noise_gamma_shape': lambda: e.get(j, F.F_NOISE_SHAPE, (R,)),
+            'noise_gamma_scale': lambda: e.get(j, F.F_NOISE_SCALE, (R,)),
+            'bias_normal_precision': lambda: e.get(j, F.F_BIAS_PRECISION, (R,)),
+            'bias_normal_mean': lambda: e.get(j, F.F_BIAS_MEAN, (R, dy)),
+        }
+        if self.forced_independence:
+            g.update({
+                'axis_bingham_b': lambda: list(e.get(j, F.F_AXIS_B, (R, M, dy, dy))),
+                'axis_bingham_kappa': lambda: list(e.get(j, F.F_AXIS_KAPPA, (R, M, dy))),
+                'axis_bingham_rho': lambda: list(e.get(j, F.F_AXIS_RHO, (R, M, dy))),
+                'axis_bingham_log_const': lambda: list(e.get(j, F.F_AXIS_LOGC, (R, M))),
+                'ard_gamma_shape': lambda: list(e.get(j, F.F_ARD_SHAPE, (R, M))),
+                'ard_gamma_scale': lambda: list(e.get(j, F.F_ARD_SCALE, (R, M))),
+            })
+        return _View(self, g, dict(dy=dy, n_basis=M, n_regions=R, noise_region_specific=True, bias_region_specific=True))
+
+    def _stats_view(self, j):
+        e, R, M, dy = self._engine, self.n_regions[j], self.n_basis, self.dy
+        F = _lib
+        g = {
+            'scale_axis_mean': lambda: list(np.swapaxes(e.get(j, F.F_A, (R, M, dy)), 1, 2)),
+            'scale_moment2': lambda: list(e.get(j, F.F_M2, (R, M))),
+            'scale_axis_central_moment2': lambda: list(e.get(j, F.F_CM2, (R, M))),
+            'noise_mean': lambda: list(e.get(j, F.F_NOISE_MEAN, (R,))),
+            'noise_log_mean': lambda: list(e.get(j, F.F_NOISE_LOG_MEAN, (R,))),
+            'bias_mean': lambda: list(e.get(j, F.F_BIAS_MEAN, (R, dy))),
+            'bias_var': lambda: list(e.get(j, F.F_BIAS_VAR, (R,))),
+            'latent_f_mean': lambda: self._split(j, e.latent(j)[0]),
+            'latent_f_var': lambda: self._split(j, e.latent(j)[1][:, None]),
+        }
+        if self.forced_independence:
+            g.update({
+                'axis_cov': lambda: list(e.get(j, F.F_AXIS_COV, (R, M, dy, dy))),
+                'ard_mean': lambda: list(e.get(j, F.F_ARD_MEAN, (R, M))),
+                'ard_log_mean': lambda: list(e.get(j, F.F_ARD_LOG_MEAN, (R, M))),
+                'omega': lambda: [np.ones((M, M)) / M for _ in range(R)],
+            })
+        return _View(self, g, dict(dy=dy, n_basis=M, n_regions=R, noise_region_specific=True, bias_region_specific=True))
+
+    @property
+    def posterior_obj(self):
+        return [self._posterior_view(j) for j in range(self.n_layers)]
+
+    @property
+    def stats_obj(self):
+        return [self._stats_view(j) for j in range(self.n_layers)]
+
+    @property
+    def get_posterior(self):
+        return self.posterior_obj
+
+    @property
+    def get_stats(self):
+        return self.stats_obj
+
+    def _require_ci(self):
+        if self.forced_independence:
+            raise AttributeError('shared posterior / stats exist in ci mode only (MRGP.py:229-246)')
+
+    @property
+    def shared_posterior(self):
+        self._require_ci()
+        e, M, dy = self._engine, self.n_basis, self.dy
+        F = _lib
+        return _View(self, {
+            'axis_bingham_b': lambda: e.get(-1, F.F_AXIS_B, (M, dy, dy)),
+            'axis_bingham_kappa': lambda: e.get(-1, F.F_AXIS_KAPPA, (M, dy)),
+            'axis_bingham_rho': lambda: e.get(-1, F.F_AXIS_RHO, (M, dy)),
+            'axis_bingham_log_const': lambda: e.get(-1, F.F_AXIS_LOGC, (M,)),
+            'ard_gamma_shape': lambda: e.get(-1, F.F_ARD_SHAPE, (M,)),
+            'ard_gamma_scale': lambda: e.get(-1, F.F_ARD_SCALE, (M,)),
+        }, dict(dy=dy, n_basis=M))
+
+    @property
+    def shared_stats(self):
+        self._require_ci()
+        e, M, dy = self._engine, self.n_basis, self.dy
+        F = _lib
+        return _View(self, {
+            'axis_cov': lambda: e.get(-1, F.F_AXIS_COV, (M, dy, dy)),
+            'ard_mean': lambda: e.get(-1, F.F_ARD_MEAN, (M,)),
+            'ard_log_mean': lambda: e.get(-1, F.F_ARD_LOG_MEAN, (M,)),
+            'omega': lambda: e.get(-1, F.F_OMEGA, (M, M)),
+        }, dict(dy=dy, n_basis=M))

@@ -1,0 +1,1230 @@
+// C ABI (include/cimrgp.h) over the sm_100a kernels of mrgp_kernels.cuh: host-side plan, workspace
+// carving, kernel dispatch, the per-layer composition of a sweep and its CUDA-graph replay.
+#include "../../include/cimrgp.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mrgp_kernels.cuh"
+
+using namespace mrgp;
+
+namespace {
+
+std::string g_create_error;
+
+struct LayerPlan {
+    std::vector<int64_t> offsets;     // R + 1
+    std::vector<Segment> segs;
+    std::vector<int32_t> cta_seg;     // n_ctas + 1
+    std::vector<int32_t> seg_cta;     // per segment (host only)
+    std::vector<int32_t> region_run;  // R + 1
+    int32_t R = 0, n_runs = 0;
+};
+
+struct LayerDev {
+    // plan
+    Segment *segs = nullptr;
+    int32_t *cta_seg = nullptr, *region_run = nullptr;
+    int64_t *offsets = nullptr;
+    // static
+    double *L = nullptr, *inv2L = nullptr, *rsqrtL = nullptr, *lam = nullptr, *S = nullptr, *d = nullptr;
+    // posterior / stats
+    double *prec = nullptr, *zeta = nullptr, *ytil = nullptr, *A = nullptr, *A_prev = nullptr, *m2 = nullptr, *cm2 = nullptr;
+    double *noise_shape = nullptr, *noise_scale = nullptr, *noise_shape0 = nullptr, *noise_scale0 = nullptr;
+    double *noise_mean = nullptr, *noise_log_mean = nullptr;
+    double *bias_prec = nullptr, *bias_prec0 = nullptr, *bias_mean = nullptr, *bias_mean0 = nullptr, *bias_var = nullptr;
+    double *yvar = nullptr, *sumsB = nullptr, *bcontrib = nullptr;
+    // fi: per-region axis / ARD
+    double *axB = nullptr, *axKappa = nullptr, *axRho = nullptr, *axLogC = nullptr, *axCov = nullptr;
+    double *ardShape = nullptr, *ardScale = nullptr, *ardMean = nullptr, *ardLogMean = nullptr;
+    // spectral settings
+    int32_t use_prior = 1;
+    double nu = 1.0, ell = 1.0, sf = 1.0;
+    bool basis_built = false;
+};
+
+struct SharedDev {
+    double *axB = nullptr, *axKappa = nullptr, *axRho = nullptr, *axLogC = nullptr, *axCov = nullptr;
+    double *ardShape = nullptr, *ardScale = nullptr, *ardMean = nullptr, *ardLogMean = nullptr;
+    double *omega = nullptr, *logOmegaHat = nullptr;
+    double *primeB = nullptr, *primeLogC = nullptr, *primeShape = nullptr, *primeScale = nullptr;
+    double *priorB = nullptr, *priorLogC = nullptr, *priorShape = nullptr, *priorScale = nullptr;
+};
+
+}  // namespace
+
+struct mrgp_handle {
+    mrgp_config cfg{};
+    int32_t n_ctas = 0;
+    int64_t cta_quantum = 0;
+    int32_t sm_count = 0;
+    std::vector<LayerPlan> plan;
+    std::vector<LayerDev> dev;
+    SharedDev sh;
+    size_t ws_bytes = 0;
+    char *ws = nullptr;
+    bool bound = false, have_data = false, state_init = false;
+    const double *x = nullptr, *y = nullptr;
+    double *x_ws = nullptr, *y_ws = nullptr, *g = nullptr, *hvar = nullptr, *tmp_mean = nullptr, *tmp_var = nullptr;
+    double *part = nullptr, *elbo_out = nullptr;
+    RegionArgs *elbo_args = nullptr;
+    int32_t part_stride = 0, max_runs = 0;
+    unsigned long long *chol_count = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr;
+    bool own_stream = false;
+    std::vector<cudaEvent_t> ev_fork, ev_join;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t launches = 0, launches_per_sweep = 0;
+    bool capturing = false;
+    double fi_shape0_mix = 0.0, fi_scale0_mix = 0.0;
+    std::string err;
+};
+
+namespace {
+
+int fail(mrgp_handle *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h)
+        h->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(h, MRGP_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+bool basis_supported(int m) { return m == 8 || m == 20 || m == 30 || m == 40; }
+
+// ---- plan -------------------------------------------------------------------------------------
+void build_plan(mrgp_handle *h) {
+    const int64_t N = h->cfg.n_samples;
+    const int J = h->cfg.n_layers;
+    const int64_t Q = h->cta_quantum;
+    const int G = h->n_ctas;
+    for (int j = 0; j < J; ++j) {
+        LayerPlan &lp = h->plan[j];
+        std::vector<int64_t> cuts;
+        cuts.insert(cuts.end(), lp.offsets.begin(), lp.offsets.end());
+        if (j > 0) cuts.insert(cuts.end(), h->plan[j - 1].offsets.begin(), h->plan[j - 1].offsets.end());
+        for (int c = 0; c < G; ++c) cuts.push_back(std::min<int64_t>(N, (int64_t)c * Q));
+        cuts.push_back(N);
+        std::sort(cuts.begin(), cuts.end());
+        cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+        lp.segs.clear();
+        lp.seg_cta.clear();
+        lp.cta_seg.assign(G + 1, 0);
+        lp.region_run.assign(lp.R + 1, 0);
+        int region = 0, parent = 0, run = -1, prev_cta = -1, prev_region = -1;
+        const std::vector<int64_t> *poff = (j > 0) ? &h->plan[j - 1].offsets : nullptr;
+        for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+            const int64_t s = cuts[k], e = cuts[k + 1];
+            while (lp.offsets[region + 1] <= s) ++region;
+            if (poff)
+                while ((*poff)[parent + 1] <= s) ++parent;
+            const int cta = (int)(s / Q);
+            if (cta != prev_cta || region != prev_region) {
+                ++run;
+                if (region != prev_region)
+                    for (int r = prev_region + 1; r <= region; ++r) lp.region_run[r] = run;
+            }
+            Segment sg;
+            sg.start = s;
+            sg.len = (int32_t)(e - s);
+            sg.region = region;
+            sg.parent = parent;
+            sg.run = run;
+            sg.flush = 0;
+            sg.pad = 0;
+            lp.segs.push_back(sg);
+            lp.seg_cta.push_back(cta);
+            prev_cta = cta;
+            prev_region = region;
+        }
+        lp.n_runs = run + 1;
+        lp.region_run[lp.R] = lp.n_runs;
+        for (size_t k = 0; k < lp.segs.size(); ++k)
+            lp.segs[k].flush = (k + 1 == lp.segs.size() || lp.segs[k + 1].run != lp.segs[k].run) ? 1 : 0;
+        // first segment of each CTA (CTAs past the data get an empty range)
+        size_t k = 0;
+        for (int c = 0; c <= G; ++c) {
+            while (k < lp.segs.size() && lp.seg_cta[k] < c) ++k;
+            lp.cta_seg[c] = (int32_t)k;
+        }
+    }
+}
+
+// ---- workspace --------------------------------------------------------------------------------
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(char *b) : base(b) {}
+    template <typename T>
+    T *take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+size_t carve(mrgp_handle *h, char *base) {
+    Carver c(base);
+    const int64_t N = h->cfg.n_samples;
+    const int DY = h->cfg.dy, M = h->cfg.n_basis, J = h->cfg.n_layers;
+    const bool fi = h->cfg.mode == MRGP_MODE_FI;
+    h->x_ws = c.take<double>(N * h->cfg.dx);
+    h->y_ws = c.take<double>(N * DY);
+    h->g = c.take<double>(N * DY);
+    h->hvar = c.take<double>(N);
+    h->tmp_mean = c.take<double>(N * DY);
+    h->tmp_var = c.take<double>(N);
+    h->max_runs = 0;
+    for (int j = 0; j < J; ++j) h->max_runs = std::max(h->max_runs, h->plan[j].n_runs);
+    h->part_stride = std::max(M * DY, kPartBStride);
+    h->part = c.take<double>((size_t)h->max_runs * h->part_stride);
+    h->elbo_out = c.take<double>((size_t)J * 6);
+    h->elbo_args = c.take<RegionArgs>(J);
+    h->chol_count = c.take<unsigned long long>(1);
+    for (int j = 0; j < J; ++j) {
+        const LayerPlan &lp = h->plan[j];
+        LayerDev &d = h->dev[j];
+        const size_t R = lp.R, RM = R * M;
+        d.segs = c.take<Segment>(lp.segs.size());
+        d.cta_seg = c.take<int32_t>(lp.cta_seg.size());
+        d.region_run = c.take<int32_t>(lp.region_run.size());
+        d.offsets = c.take<int64_t>(lp.offsets.size());
+        d.L = c.take<double>(R);
+        d.inv2L = c.take<double>(R);
+        d.rsqrtL = c.take<double>(R);
+        d.lam = c.take<double>(RM);
+        d.S = c.take<double>(RM);
+        d.d = c.take<double>(RM);
+        d.prec = c.take<double>(RM);
+        d.zeta = c.take<double>(RM);
+        d.ytil = c.take<double>(RM * DY);
+        d.A = c.take<double>(RM * DY);
+        d.A_prev = c.take<double>(RM * DY);
+        d.m2 = c.take<double>(RM);
+        d.cm2 = c.take<double>(RM);
+        d.noise_shape = c.take<double>(R);
+        d.noise_scale = c.take<double>(R);
+        d.noise_shape0 = c.take<double>(R);
+        d.noise_scale0 = c.take<double>(R);
+        d.noise_mean = c.take<double>(R);
+        d.noise_log_mean = c.take<double>(R);
+        d.bias_prec = c.take<double>(R);
+        d.bias_prec0 = c.take<double>(R);
+        d.bias_mean = c.take<double>(R * DY);
+        d.bias_mean0 = c.take<double>(R * DY);
+        d.bias_var = c.take<double>(R);
+        d.yvar = c.take<double>(R);
+        d.sumsB = c.take<double>(R * (DY + 3));
+        d.bcontrib = c.take<double>(RM * 3);
+        if (fi) {
+            d.axB = c.take<double>(RM * DY * DY);
+            d.axKappa = c.take<double>(RM * DY);
+            d.axRho = c.take<double>(RM * DY);
+            d.axLogC = c.take<double>(RM);
+            d.axCov = c.take<double>(RM * DY * DY);
+            d.ardShape = c.take<double>(RM);
+            d.ardScale = c.take<double>(RM);
+            d.ardMean = c.take<double>(RM);
+            d.ardLogMean = c.take<double>(RM);
+        }
+    }
+    SharedDev &s = h->sh;
+    s.axB = c.take<double>((size_t)M * DY * DY);
+    s.axKappa = c.take<double>((size_t)M * DY);
+    s.axRho = c.take<double>((size_t)M * DY);
+    s.axLogC = c.take<double>(M);
+    s.axCov = c.take<double>((size_t)M * DY * DY);
+    s.ardShape = c.take<double>(M);
+    s.ardScale = c.take<double>(M);
+    s.ardMean = c.take<double>(M);
+    s.ardLogMean = c.take<double>(M);
+    s.omega = c.take<double>((size_t)M * M);
+    s.logOmegaHat = c.take<double>((size_t)M * M);
+    s.primeB = c.take<double>((size_t)M * DY * DY);
+    s.primeLogC = c.take<double>(M);
+    s.primeShape = c.take<double>(M);
+    s.primeScale = c.take<double>(M);
+    s.priorB = c.take<double>((size_t)M * DY * DY);
+    s.priorLogC = c.take<double>(M);
+    s.priorShape = c.take<double>(M);
+    s.priorScale = c.take<double>(M);
+    return (c.off + 255) & ~(size_t)255;
+}
+
+// ---- argument packs -----------------------------------------------------------------------------
+StreamArgs stream_args(mrgp_handle *h, int j) {
+    const LayerDev &d = h->dev[j];
+    StreamArgs a{};
+    a.segs = d.segs;
+    a.cta_seg = d.cta_seg;
+    a.x = h->x;
+    a.y = h->y;
+    a.g = h->g;
+    a.h = h->hvar;
+    a.inv2L = d.inv2L;
+    a.rsqrtL = d.rsqrtL;
+    a.A = d.A;
+    a.A_prev = d.A_prev;
+    a.cm2 = d.cm2;
+    a.bias = d.bias_mean;
+    a.pbias = j > 0 ? h->dev[j - 1].bias_mean : nullptr;
+    a.pbias_var = j > 0 ? h->dev[j - 1].bias_var : nullptr;
+    a.part = h->part;
+    a.part_stride = h->part_stride;
+    return a;
+}
+
+RegionArgs region_args(mrgp_handle *h, int j) {
+    const LayerDev &d = h->dev[j];
+    const SharedDev &s = h->sh;
+    const bool fi = h->cfg.mode == MRGP_MODE_FI;
+    RegionArgs a{};
+    a.R = h->plan[j].R;
+    a.M = h->cfg.n_basis;
+    a.DY = h->cfg.dy;
+    a.layer = j;
+    a.mode = h->cfg.mode;
+    a.infer = (!fi && j > 0) ? 1 : 0;
+    a.region_run = d.region_run;
+    a.offsets = d.offsets;
+    a.part = h->part;
+    a.part_stride = h->part_stride;
+    a.L = d.L;
+    a.inv2L = d.inv2L;
+    a.rsqrtL = d.rsqrtL;
+    a.lam = d.lam;
+    a.S = d.S;
+    a.d = d.d;
+    a.prec = d.prec;
+    a.zeta = d.zeta;
+    a.ytil = d.ytil;
+    a.A = d.A;
+    a.A_prev = d.A_prev;
+    a.m2 = d.m2;
+    a.cm2 = d.cm2;
+    a.noise_shape = d.noise_shape;
+    a.noise_scale = d.noise_scale;
+    a.noise_shape0 = d.noise_shape0;
+    a.noise_scale0 = d.noise_scale0;
+    a.noise_mean = d.noise_mean;
+    a.noise_log_mean = d.noise_log_mean;
+    a.bias_prec = d.bias_prec;
+    a.bias_prec0 = d.bias_prec0;
+    a.bias_mean = d.bias_mean;
+    a.bias_mean0 = d.bias_mean0;
+    a.bias_var = d.bias_var;
+    a.yvar = d.yvar;
+    a.sumsB = d.sumsB;
+    a.bcontrib = d.bcontrib;
+    if (fi) {
+        a.axB = d.axB;
+        a.axKappa = d.axKappa;
+        a.axRho = d.axRho;
+        a.axLogC = d.axLogC;
+        a.axCov = d.axCov;
+        a.ardShape = d.ardShape;
+        a.ardScale = d.ardScale;
+        a.ardMean = d.ardMean;
+        a.ardLogMean = d.ardLogMean;
+    } else {
+        a.axB = s.axB;
+        a.axKappa = s.axKappa;
+        a.axRho = s.axRho;
+        a.axLogC = s.axLogC;
+        a.axCov = s.axCov;
+        a.ardShape = s.ardShape;
+        a.ardScale = s.ardScale;
+        a.ardMean = s.ardMean;
+        a.ardLogMean = s.ardLogMean;
+    }
+    a.omega = s.omega;
+    a.logOmegaHat = s.logOmegaHat;
+    a.primeB = s.primeB;
+    a.primeLogC = s.primeLogC;
+    a.primeShape = s.primeShape;
+    a.primeScale = s.primeScale;
+    a.priorB = s.priorB;
+    a.priorLogC = s.priorLogC;
+    a.priorShape = s.priorShape;
+    a.priorScale = s.priorScale;
+    a.chol_count = h->chol_count;
+    a.fi_shape0_mix = h->fi_shape0_mix;
+    a.fi_scale0_mix = h->fi_scale0_mix;
+    a.use_prior = d.use_prior;
+    a.nu = d.nu;
+    a.ell = d.ell;
+    a.sf = d.sf;
+    a.interval_factor = 1.0;
+    a.L_given = 0;
+    return a;
+}
+
+// ---- kernel dispatch ----------------------------------------------------------------------------
+constexpr size_t kRedSmemBytes = kRedSmemDoubles * sizeof(double);
+
+template <typename K>
+cudaError_t set_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+template <int M>
+cudaError_t launch_phase_a(mrgp_handle *h, const StreamArgs &a, bool infer, bool latent) {
+    constexpr int DY = 2;
+    dim3 grid(h->n_ctas), block(kThreads);
+#define LA(I, L)                                                                \
+    {                                                                           \
+        cudaError_t e = set_smem(k_phase_a<DY, M, I, L>, kRedSmemBytes);        \
+        if (e != cudaSuccess) return e;                                         \
+        k_phase_a<DY, M, I, L><<<grid, block, kRedSmemBytes, h->stream>>>(a);   \
+    }
+    if (infer)
+        LA(true, true)
+    else if (latent)
+        LA(false, true)
+    else
+        LA(false, false)
+#undef LA
+    return cudaGetLastError();
+}
+
+template <int M>
+cudaError_t launch_phase_b(mrgp_handle *h, const StreamArgs &a, bool infer, bool latent, bool prop) {
+    constexpr int DY = 2;
+    dim3 grid(h->n_ctas), block(kThreads);
+#define LB(I, L, P) k_phase_b<DY, M, I, L, P><<<grid, block, 0, h->stream>>>(a)
+    if (infer) {
+        if (prop)
+            LB(true, true, true);
+        else
+            LB(true, true, false);
+    } else if (latent) {
+        if (prop)
+            LB(false, true, true);
+        else
+            LB(false, true, false);
+    } else {
+        if (prop)
+            LB(false, false, true);
+        else
+            LB(false, false, false);
+    }
+#undef LB
+    return cudaGetLastError();
+}
+
+template <int M>
+cudaError_t launch_phi2sum(mrgp_handle *h, const StreamArgs &a) {
+    cudaError_t e = set_smem(k_phi2sum<M>, kRedSmemBytes);
+    if (e != cudaSuccess) return e;
+    k_phi2sum<M><<<h->n_ctas, kThreads, kRedSmemBytes, h->stream>>>(a);
+    return cudaGetLastError();
+}
+
+#define DISPATCH_M(m, expr)                     \
+    switch (m) {                                \
+        case 8: { constexpr int MM = 8; expr; } break;   \
+        case 20: { constexpr int MM = 20; expr; } break; \
+        case 30: { constexpr int MM = 30; expr; } break; \
+        case 40: { constexpr int MM = 40; expr; } break; \
+        default: break;                         \
+    }
+
+int check_ready(mrgp_handle *h, int layer, bool need_state) {
+    if (!h) return MRGP_EINVAL;
+    if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
+    if (!h->have_data) return fail(h, MRGP_ESTATE, "no data set");
+    if (layer < 0 || layer >= h->cfg.n_layers) return fail(h, MRGP_EINVAL, "layer %d out of range", layer);
+    if (need_state && !h->state_init) return fail(h, MRGP_ESTATE, "state not initialised");
+    return MRGP_OK;
+}
+
+void count(mrgp_handle *h, int n = 1) {
+    if (h->capturing)
+        h->launches_per_sweep += n;
+    else
+        h->launches += n;
+}
+
+// ---- the phases ---------------------------------------------------------------------------------
+int do_phase_a(mrgp_handle *h, int j) {
+    const bool fi = h->cfg.mode == MRGP_MODE_FI;
+    const bool infer = !fi && j > 0, latent = j > 0;
+    StreamArgs a = stream_args(h, j);
+    cudaError_t e = cudaErrorInvalidValue;
+    DISPATCH_M(h->cfg.n_basis, e = launch_phase_a<MM>(h, a, infer, latent));
+    CK(e);
+    count(h);
+    return MRGP_OK;
+}
+
+int reduce_threads(int nv, int max_runs_per_region, int cap) {
+    const int nval = (nv + 31) & ~31;
+    int slices = std::max(1, std::min(cap / nval, max_runs_per_region));
+    return nval * slices;
+}
+
+int max_region_runs(const LayerPlan &lp) {
+    int m = 1;
+    for (int r = 0; r < lp.R; ++r) m = std::max(m, lp.region_run[r + 1] - lp.region_run[r]);
+    return m;
+}
+
+int do_axis_update(mrgp_handle *h, int j, bool fork_omega) {
+    const bool fi = h->cfg.mode == MRGP_MODE_FI;
+    const int M = h->cfg.n_basis, DY = h->cfg.dy;
+    RegionArgs a = region_args(h, j);
+    const LayerPlan &lp = h->plan[j];
+    {
+        const int nv = M * DY, nval = (nv + 31) & ~31;
+        const int threads = std::max(reduce_threads(nv, max_region_runs(lp), 1024), ((M + 31) & ~31));
+        const int slices = threads / nval;
+        const size_t smem = (size_t)(slices * nval + nv) * sizeof(double);
+        k_reduce_scale<2><<<lp.R, threads, smem, h->stream>>>(a);
+        CK(cudaGetLastError());
+        count(h);
+    }
+    if (fi) return MRGP_OK;
+    if (fork_omega && j > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_join[j - 1], 0));
+    {
+        const int nv = M * 3, nval = (nv + 31) & ~31;
+        const int slices = 1024 / nval;
+        const size_t smem = (size_t)(slices * nval + nv) * sizeof(double);
+        k_axis_shared<2><<<1, 1024, smem, h->stream>>>(a);
+        CK(cudaGetLastError());
+        count(h);
+    }
+    {
+        const int total = lp.R * M;
+        k_scale_stats<2><<<(total + 127) / 128, 128, 0, h->stream>>>(a);
+        CK(cudaGetLastError());
+        count(h);
+    }
+    {
+        const int nval = (M + 31) & ~31;
+        const int slices = 1024 / nval;
+        const size_t smem = (size_t)(slices * nval + 2 * M) * sizeof(double);
+        k_ard<2><<<1, 1024, smem, h->stream>>>(a);
+        CK(cudaGetLastError());
+        count(h);
+    }
+    {
+        cudaStream_t st = h->stream;
+        if (fork_omega) {
+            CK(cudaEventRecord(h->ev_fork[j], h->stream));
+            CK(cudaStreamWaitEvent(h->side, h->ev_fork[j], 0));
+            st = h->side;
+        }
+        const size_t smem = (size_t)(M * M + 2 * M + 1) * sizeof(double);
+        k_omega<<<1, 1024, smem, st>>>(a, 5000, 1e-13);
+        CK(cudaGetLastError());
+        count(h);
+        if (fork_omega) CK(cudaEventRecord(h->ev_join[j], h->side));
+    }
+    return MRGP_OK;
+}
+
+int do_phase_b(mrgp_handle *h, int j) {
+    const bool fi = h->cfg.mode == MRGP_MODE_FI;
+    const bool infer = !fi && j > 0, latent = j > 0, prop = j + 1 < h->cfg.n_layers;
+    StreamArgs a = stream_args(h, j);
+    cudaError_t e = cudaErrorInvalidValue;
+    DISPATCH_M(h->cfg.n_basis, e = launch_phase_b<MM>(h, a, infer, latent, prop));
+    CK(e);
+    count(h);
+    return MRGP_OK;
+}
+
+int do_bias_noise(mrgp_handle *h, int j) {
+    RegionArgs a = region_args(h, j);
+    k_bias_noise<2><<<h->plan[j].R, 128, 0, h->stream>>>(a);
+    CK(cudaGetLastError());
+    count(h);
+    return MRGP_OK;
+}
+
+int sweep_once(mrgp_handle *h, bool fork_omega) {
+    const int J = h->cfg.n_layers;
+    const bool ci = h->cfg.mode == MRGP_MODE_CI;
+    int rc;
+    for (int j = 0; j < J; ++j) {
+        if ((rc = do_phase_a(h, j))) return rc;
+        if ((rc = do_axis_update(h, j, fork_omega && ci))) return rc;
+        if ((rc = do_phase_b(h, j))) return rc;
+        if ((rc = do_bias_noise(h, j))) return rc;
+    }
+    if (fork_omega && ci) CK(cudaStreamWaitEvent(h->stream, h->ev_join[J - 1], 0));
+    return MRGP_OK;
+}
+
+struct FieldRef {
+    void *ptr = nullptr;
+    int64_t n = 0;
+};
+
+FieldRef field_ref(mrgp_handle *h, int layer, int field) {
+    FieldRef f;
+    const int M = h->cfg.n_basis, DY = h->cfg.dy;
+    const bool fi = h->cfg.mode == MRGP_MODE_FI;
+    if (field >= MRGP_F_AXIS_B && !fi) {
+        if (layer != -1) return f;
+        SharedDev &s = h->sh;
+        switch (field) {
+            case MRGP_F_AXIS_B: f = {s.axB, (int64_t)M * DY * DY}; break;
+            case MRGP_F_AXIS_KAPPA: f = {s.axKappa, (int64_t)M * DY}; break;
+            case MRGP_F_AXIS_RHO: f = {s.axRho, (int64_t)M * DY}; break;
+            case MRGP_F_AXIS_LOGC: f = {s.axLogC, M}; break;
+            case MRGP_F_AXIS_COV: f = {s.axCov, (int64_t)M * DY * DY}; break;
+            case MRGP_F_ARD_SHAPE: f = {s.ardShape, M}; break;
+            case MRGP_F_ARD_SCALE: f = {s.ardScale, M}; break;
+            case MRGP_F_ARD_MEAN: f = {s.ardMean, M}; break;
+            case MRGP_F_ARD_LOG_MEAN: f = {s.ardLogMean, M}; break;
+            case MRGP_F_OMEGA: f = {s.omega, (int64_t)M * M}; break;
+            case MRGP_F_LOG_OMEGA_HAT: f = {s.logOmegaHat, (int64_t)M * M}; break;
+            default: break;
+        }
+        return f;
+    }
+    if (layer < 0 || layer >= h->cfg.n_layers) return f;
+    LayerDev &d = h->dev[layer];
+    const int64_t R = h->plan[layer].R, RM = R * M;
+    switch (field) {
+        case MRGP_F_L: f = {d.L, R}; break;
+        case MRGP_F_LAMBDA: f = {d.lam, RM}; break;
+        case MRGP_F_SPECTRAL: f = {d.S, RM}; break;
+        case MRGP_F_PHI2SUM: f = {d.d, RM}; break;
+        case MRGP_F_SCALE_PRECISION: f = {d.prec, RM}; break;
+        case MRGP_F_ZETA: f = {d.zeta, RM}; break;
+        case MRGP_F_YTILDE: f = {d.ytil, RM * DY}; break;
+        case MRGP_F_NOISE_SHAPE: f = {d.noise_shape, R}; break;
+        case MRGP_F_NOISE_SCALE: f = {d.noise_scale, R}; break;
+        case MRGP_F_BIAS_PRECISION: f = {d.bias_prec, R}; break;
+        case MRGP_F_A: f = {d.A, RM * DY}; break;
+        case MRGP_F_M2: f = {d.m2, RM}; break;
+        case MRGP_F_CM2: f = {d.cm2, RM}; break;
+        case MRGP_F_NOISE_MEAN: f = {d.noise_mean, R}; break;
+        case MRGP_F_NOISE_LOG_MEAN: f = {d.noise_log_mean, R}; break;
+        case MRGP_F_BIAS_MEAN: f = {d.bias_mean, R * DY}; break;
+        case MRGP_F_BIAS_VAR: f = {d.bias_var, R}; break;
+        case MRGP_F_FBAR: f = {h->tmp_mean, h->cfg.n_samples * DY}; break;
+        case MRGP_F_FVAR: f = {h->tmp_var, h->cfg.n_samples}; break;
+        case MRGP_F_YVAR: f = {d.yvar, R}; break;
+        case MRGP_F_PHASE_B_SUMS: f = {d.sumsB, R * (DY + 3)}; break;
+        default: break;
+    }
+    if (fi) {
+        switch (field) {
+            case MRGP_F_AXIS_B: f = {d.axB, RM * DY * DY}; break;
+            case MRGP_F_AXIS_KAPPA: f = {d.axKappa, RM * DY}; break;
+            case MRGP_F_AXIS_RHO: f = {d.axRho, RM * DY}; break;
+            case MRGP_F_AXIS_LOGC: f = {d.axLogC, RM}; break;
+            case MRGP_F_AXIS_COV: f = {d.axCov, RM * DY * DY}; break;
+            case MRGP_F_ARD_SHAPE: f = {d.ardShape, RM}; break;
+            case MRGP_F_ARD_SCALE: f = {d.ardScale, RM}; break;
+            case MRGP_F_ARD_MEAN: f = {d.ardMean, RM}; break;
+            case MRGP_F_ARD_LOG_MEAN: f = {d.ardLogMean, RM}; break;
+            default: break;
+        }
+    }
+    return f;
+}
+
+int fill_eval_layers(mrgp_handle *h, EvalArgs &ea, int n_layers, const int64_t *const *dev_offsets) {
+    if (n_layers > kMaxLayers) return fail(h, MRGP_EINVAL, "too many layers");
+    ea.n_layers = n_layers;
+    ea.M = h->cfg.n_basis;
+    for (int j = 0; j < n_layers; ++j) {
+        const LayerDev &d = h->dev[j];
+        EvalLayer &l = ea.layer[j];
+        l.offsets = dev_offsets ? dev_offsets[j] : d.offsets;
+        l.inv2L = d.inv2L;
+        l.rsqrtL = d.rsqrtL;
+        l.A = d.A;
+        l.cm2 = d.cm2;
+        l.bias = d.bias_mean;
+        l.bias_var = d.bias_var;
+        l.R = h->plan[j].R;
+    }
+    return MRGP_OK;
+}
+
+void drop_graph(mrgp_handle *h) {
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    h->graph_exec = nullptr;
+    h->graph = nullptr;
+    h->launches_per_sweep = 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int mrgp_abi_version(void) { return MRGP_ABI_VERSION; }
+
+const char *mrgp_last_error(const mrgp_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, const int32_t *n_regions, mrgp_handle **out) {
+    mrgp_handle *h = nullptr;
+    if (!cfg || !region_offsets || !n_regions || !out) return fail(h, MRGP_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != MRGP_ABI_VERSION) return fail(h, MRGP_EINVAL, "abi version %d != %d", cfg->abi_version, MRGP_ABI_VERSION);
+    if (cfg->mode != MRGP_MODE_CI && cfg->mode != MRGP_MODE_FI) return fail(h, MRGP_EINVAL, "unknown mode");
+    if (cfg->dy < 2) return fail(h, MRGP_EINVAL, "output dimension must be greater than 1");
+    if (cfg->dy != 2) return fail(h, MRGP_EINVAL, "dy = %d: only dy == 2 is implemented on the device", cfg->dy);
+    if (cfg->dx != 1) return fail(h, MRGP_EINVAL, "dx = %d: only dx == 1 is implemented on the device", cfg->dx);
+    if (!basis_supported(cfg->n_basis)) return fail(h, MRGP_EINVAL, "n_basis = %d: compiled for 8, 20, 30, 40", cfg->n_basis);
+    if (cfg->n_layers < 1 || cfg->n_layers > kMaxLayers) return fail(h, MRGP_EINVAL, "n_layers out of range");
+    if (cfg->n_samples < 1) return fail(h, MRGP_EINVAL, "n_samples < 1");
+    if (!cfg->noise_region_specific || !cfg->bias_region_specific)
+        return fail(h, MRGP_EINVAL, "only region-specific noise and bias are implemented on the device");
+    h = new mrgp_handle();
+    h->cfg = *cfg;
+    h->plan.resize(cfg->n_layers);
+    h->dev.resize(cfg->n_layers);
+    for (int j = 0; j < cfg->n_layers; ++j) {
+        LayerPlan &lp = h->plan[j];
+        lp.R = n_regions[j];
+        if (lp.R < 1) {
+            delete h;
+            return fail(nullptr, MRGP_EINVAL, "layer %d has no regions", j);
+        }
+        lp.offsets.assign(region_offsets[j], region_offsets[j] + lp.R + 1);
+        bool ok = lp.offsets.front() == 0 && lp.offsets.back() == cfg->n_samples;
+        for (int r = 0; r < lp.R && ok; ++r) ok = lp.offsets[r + 1] > lp.offsets[r];
+        if (!ok) {
+            delete h;
+            return fail(nullptr, MRGP_EINVAL, "layer %d: offsets must be strictly increasing from 0 to n_samples", j);
+        }
+    }
+    // streaming geometry: one persistent CTA per SM unless told otherwise; small problems use fewer CTAs
+    int sms = 148;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) sms = prop.multiProcessorCount;
+    } else {
+        cudaGetLastError();
+    }
+    h->sm_count = sms;
+    int want = cfg->n_ctas > 0 ? cfg->n_ctas : sms;
+    const int64_t min_per_cta = 4 * kThreads;
+    const int64_t cap = std::max<int64_t>(1, (cfg->n_samples + min_per_cta - 1) / min_per_cta);
+    want = (int)std::min<int64_t>(want, cap);
+    int64_t q = (cfg->n_samples + want - 1) / want;
+    q = ((q + 31) / 32) * 32;
+    h->cta_quantum = q;
+    h->n_ctas = (int)((cfg->n_samples + q - 1) / q);
+    build_plan(h);
+    h->ws_bytes = carve(h, nullptr);
+    *out = h;
+    return MRGP_OK;
+}
+
+void mrgp_destroy(mrgp_handle *h) {
+    if (!h) return;
+    drop_graph(h);
+    for (auto e : h->ev_fork) cudaEventDestroy(e);
+    for (auto e : h->ev_join) cudaEventDestroy(e);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+size_t mrgp_workspace_bytes(const mrgp_handle *h) { return h ? h->ws_bytes : 0; }
+
+int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
+    if (!h || !dev_ptr) return fail(h, MRGP_EINVAL, "null argument");
+    if (bytes < h->ws_bytes) return fail(h, MRGP_ENOMEM, "workspace %zu < %zu bytes", bytes, h->ws_bytes);
+    if (((uintptr_t)dev_ptr & 255) != 0) return fail(h, MRGP_EINVAL, "workspace must be 256-byte aligned");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(h, MRGP_ENODEVICE, "no CUDA device");
+    }
+    CK(cudaSetDevice(h->cfg.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->cfg.device));
+    if (prop.major != 10) return fail(h, MRGP_ENODEVICE, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+    if (!h->stream) {
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    if (!h->side) CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    if (h->ev_fork.empty()) {
+        h->ev_fork.resize(h->cfg.n_layers);
+        h->ev_join.resize(h->cfg.n_layers);
+        for (int j = 0; j < h->cfg.n_layers; ++j) {
+            CK(cudaEventCreateWithFlags(&h->ev_fork[j], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_join[j], cudaEventDisableTiming));
+        }
+    }
+    h->ws = static_cast<char *>(dev_ptr);
+    carve(h, h->ws);
+    drop_graph(h);
+    // upload the plan
+    for (int j = 0; j < h->cfg.n_layers; ++j) {
+        const LayerPlan &lp = h->plan[j];
+        LayerDev &d = h->dev[j];
+        CK(cudaMemcpyAsync(d.segs, lp.segs.data(), lp.segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d.cta_seg, lp.cta_seg.data(), lp.cta_seg.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d.region_run, lp.region_run.data(), lp.region_run.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d.offsets, lp.offsets.data(), lp.offsets.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaMemsetAsync(h->chol_count, 0, sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(h->g, 0, (size_t)h->cfg.n_samples * h->cfg.dy * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->hvar, 0, (size_t)h->cfg.n_samples * sizeof(double), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->bound = true;
+    return MRGP_OK;
+}
+
+int mrgp_set_stream(mrgp_handle *h, void *cuda_stream) {
+    if (!h) return MRGP_EINVAL;
+    if (!cuda_stream) return fail(h, MRGP_EINVAL, "a non-default stream is required (graph capture)");
+    drop_graph(h);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->own_stream = false;
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return MRGP_OK;
+}
+
+int mrgp_set_data(mrgp_handle *h, const double *x_dev, const double *y_dev) {
+    if (!h || !x_dev || !y_dev) return fail(h, MRGP_EINVAL, "null argument");
+    if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
+    if (((uintptr_t)y_dev & 15) != 0 || ((uintptr_t)x_dev & 7) != 0) return fail(h, MRGP_EINVAL, "x must be 8-byte and y 16-byte aligned");
+    if (h->x != x_dev || h->y != y_dev) drop_graph(h);
+    h->x = x_dev;
+    h->y = y_dev;
+    h->have_data = true;
+    return MRGP_OK;
+}
+
+int mrgp_set_data_host(mrgp_handle *h, const double *x_host, const double *y_host) {
+    if (!h || !x_host || !y_host) return fail(h, MRGP_EINVAL, "null argument");
+    if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
+    const size_t N = (size_t)h->cfg.n_samples;
+    CK(cudaMemcpyAsync(h->x_ws, x_host, N * h->cfg.dx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->y_ws, y_host, N * h->cfg.dy * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->x != h->x_ws || h->y != h->y_ws) drop_graph(h);
+    h->x = h->x_ws;
+    h->y = h->y_ws;
+    h->have_data = true;
+    return MRGP_OK;
+}
+
+int mrgp_set_spectral(mrgp_handle *h, int32_t layer, int32_t use_prior, double nu, double l, double sf) {
+    if (!h || layer < 0 || layer >= h->cfg.n_layers) return fail(h, MRGP_EINVAL, "bad layer");
+    LayerDev &d = h->dev[layer];
+    d.use_prior = use_prior;
+    d.nu = nu;
+    d.ell = l;
+    d.sf = sf;
+    return MRGP_OK;
+}
+
+int mrgp_build_basis(mrgp_handle *h, int32_t layer, double interval_factor, const double *L_host) {
+    int rc = check_ready(h, layer, false);
+    if (rc) return rc;
+    LayerDev &d = h->dev[layer];
+    const LayerPlan &lp = h->plan[layer];
+    StreamArgs sa = stream_args(h, layer);
+    RegionArgs ra = region_args(h, layer);
+    ra.interval_factor = interval_factor;
+    if (L_host) {
+        CK(cudaMemcpyAsync(d.L, L_host, lp.R * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        ra.L_given = 1;
+    } else {
+        k_absmax<<<h->n_ctas, kThreads, 0, h->stream>>>(sa);
+        CK(cudaGetLastError());
+        count(h);
+    }
+    k_region_setup<<<(lp.R + 7) / 8, 256, 0, h->stream>>>(ra);
+    CK(cudaGetLastError());
+    count(h);
+    cudaError_t e = cudaErrorInvalidValue;
+    DISPATCH_M(h->cfg.n_basis, e = launch_phi2sum<MM>(h, sa));
+    CK(e);
+    count(h);
+    k_reduce_d<<<lp.R, 64, 0, h->stream>>>(ra);
+    CK(cudaGetLastError());
+    count(h);
+    d.basis_built = true;
+    return MRGP_OK;
+}
+
+int mrgp_init_state(mrgp_handle *h, double noise_var0, double ard_prior_influence) {
+    int rc = check_ready(h, 0, false);
+    if (rc) return rc;
+    for (int j = 0; j < h->cfg.n_layers; ++j)
+        if (!h->dev[j].basis_built) return fail(h, MRGP_ESTATE, "basis of layer %d not built", j);
+    const int M = h->cfg.n_basis;
+    const double zero2[2] = {0.0, 0.0};
+    double logc0, rho0[2];
+    saddle_point<2>(zero2, logc0, rho0);
+    // fi ARD mixing of the (never updated) prior: sum_k (1/M) shape0_k in index order (Posteriors.py:293-295)
+    double sh = 0.0, sc = 0.0;
+    const double w = 1.0 / (double)M;
+    for (int k = 0; k < M; ++k) {
+        sh += w * kEps;
+        sc += w * (kEps / ard_prior_influence);
+    }
+    h->fi_shape0_mix = sh;
+    h->fi_scale0_mix = sc;
+    for (int j = 0; j < h->cfg.n_layers; ++j) {
+        RegionArgs a = region_args(h, j);
+        const int total = h->plan[j].R * M;
+        k_init_layer<2><<<(total + 127) / 128, 128, 0, h->stream>>>(a, j == 0 ? noise_var0 : 1.0, ard_prior_influence, logc0, rho0[0]);
+        CK(cudaGetLastError());
+        count(h);
+    }
+    {
+        RegionArgs a = region_args(h, 0);
+        SharedDev &s = h->sh;
+        // region_args points the axis/ARD fields at per-layer arrays in fi mode; the shared block is
+        // initialised in both modes so that every buffer is defined
+        a.axB = s.axB; a.axKappa = s.axKappa; a.axRho = s.axRho; a.axLogC = s.axLogC; a.axCov = s.axCov;
+        a.ardShape = s.ardShape; a.ardScale = s.ardScale; a.ardMean = s.ardMean; a.ardLogMean = s.ardLogMean;
+        k_init_shared<2><<<1, 256, 0, h->stream>>>(a, s.priorB, s.priorLogC, s.priorShape, s.priorScale, ard_prior_influence, logc0, rho0[0]);
+        CK(cudaGetLastError());
+        count(h);
+    }
+    CK(cudaMemsetAsync(h->g, 0, (size_t)h->cfg.n_samples * h->cfg.dy * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->hvar, 0, (size_t)h->cfg.n_samples * sizeof(double), h->stream));
+    drop_graph(h);
+    h->state_init = true;
+    return MRGP_OK;
+}
+
+int64_t mrgp_state_elems(const mrgp_handle *h, int32_t layer, int32_t field) {
+    if (!h) return -1;
+    FieldRef f = field_ref(const_cast<mrgp_handle *>(h), layer, field);
+    return f.n > 0 ? f.n : -1;
+}
+
+int mrgp_get_state(mrgp_handle *h, int32_t layer, int32_t field, double *dst_host, size_t n_elems) {
+    if (!h || !dst_host) return fail(h, MRGP_EINVAL, "null argument");
+    if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
+    FieldRef f = field_ref(h, layer, field);
+    if (!f.ptr || f.n <= 0) return fail(h, MRGP_EINVAL, "unknown field %d for layer %d", field, layer);
+    if ((int64_t)n_elems != f.n) return fail(h, MRGP_EINVAL, "field %d has %lld elements, caller passed %zu", field, (long long)f.n, n_elems);
+    if (field == MRGP_F_FBAR || field == MRGP_F_FVAR) {
+        // latent functions of `layer`: sum over coarser layers (Stats.py:126-157), recomputed on demand
+        int rc = check_ready(h, layer, true);
+        if (rc) return rc;
+        const int64_t N = h->cfg.n_samples;
+        if (layer == 0) {
+            CK(cudaMemsetAsync(h->tmp_mean, 0, (size_t)N * h->cfg.dy * sizeof(double), h->stream));
+            CK(cudaMemsetAsync(h->tmp_var, 0, (size_t)N * sizeof(double), h->stream));
+        } else {
+            EvalArgs ea{};
+            if ((rc = fill_eval_layers(h, ea, layer, nullptr))) return rc;
+            ea.n = N;
+            ea.x = h->x;
+            ea.out_mean = h->tmp_mean;
+            ea.out_var = h->tmp_var;
+            ea.single_region = 0;
+            k_eval_layers<2><<<(unsigned)((N + 127) / 128), 128, 0, h->stream>>>(ea);
+            CK(cudaGetLastError());
+            count(h);
+        }
+    }
+    CK(cudaMemcpyAsync(dst_host, f.ptr, (size_t)f.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MRGP_OK;
+}
+
+int mrgp_set_state(mrgp_handle *h, int32_t layer, int32_t field, const double *src_host, size_t n_elems) {
+    if (!h || !src_host) return fail(h, MRGP_EINVAL, "null argument");
+    if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
+    if (field == MRGP_F_FBAR || field == MRGP_F_FVAR) return fail(h, MRGP_EINVAL, "latent functions are derived, not settable");
+    FieldRef f = field_ref(h, layer, field);
+    if (!f.ptr || f.n <= 0) return fail(h, MRGP_EINVAL, "unknown field %d for layer %d", field, layer);
+    if ((int64_t)n_elems != f.n) return fail(h, MRGP_EINVAL, "field %d has %lld elements, caller passed %zu", field, (long long)f.n, n_elems);
+    CK(cudaMemcpyAsync(f.ptr, src_host, (size_t)f.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MRGP_OK;
+}
+
+int mrgp_phase_a(mrgp_handle *h, int32_t layer) {
+    int rc = check_ready(h, layer, true);
+    return rc ? rc : do_phase_a(h, layer);
+}
+
+int mrgp_axis_update(mrgp_handle *h, int32_t layer) {
+    int rc = check_ready(h, layer, true);
+    return rc ? rc : do_axis_update(h, layer, false);
+}
+
+int mrgp_phase_b(mrgp_handle *h, int32_t layer) {
+    int rc = check_ready(h, layer, true);
+    return rc ? rc : do_phase_b(h, layer);
+}
+
+int mrgp_bias_noise(mrgp_handle *h, int32_t layer) {
+    int rc = check_ready(h, layer, true);
+    return rc ? rc : do_bias_noise(h, layer);
+}
+
+int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
+    int rc = check_ready(h, 0, true);
+    if (rc) return rc;
+    if (n_iter < 0) return fail(h, MRGP_EINVAL, "n_iter < 0");
+    if (!h->graph_exec) {
+        h->launches_per_sweep = 0;
+        h->capturing = true;
+        cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) {
+            h->capturing = false;
+            return fail(h, MRGP_ECUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+        }
+        rc = sweep_once(h, true);
+        cudaGraph_t graph = nullptr;
+        e = cudaStreamEndCapture(h->stream, &graph);
+        h->capturing = false;
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) return fail(h, MRGP_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        h->graph = graph;
+        CK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+    }
+    for (int it = 0; it < n_iter; ++it) CK(cudaGraphLaunch(h->graph_exec, h->stream));
+    h->launches += h->launches_per_sweep * n_iter;
+    return MRGP_OK;
+}
+
+int mrgp_synchronize(mrgp_handle *h) {
+    if (!h || !h->stream) return fail(h, MRGP_ESTATE, "no stream");
+    CK(cudaStreamSynchronize(h->stream));
+    return MRGP_OK;
+}
+
+int mrgp_elbo(mrgp_handle *h, double *out_host) {
+    int rc = check_ready(h, 0, true);
+    if (rc) return rc;
+    if (!out_host) return fail(h, MRGP_EINVAL, "null argument");
+    if (h->cfg.mode != MRGP_MODE_CI) return fail(h, MRGP_EINVAL, "the lower bound is defined for ci mode only (MRGP.py:378-401)");
+    std::vector<RegionArgs> args(h->cfg.n_layers);
+    for (int j = 0; j < h->cfg.n_layers; ++j) args[j] = region_args(h, j);
+    CK(cudaMemcpyAsync(h->elbo_args, args.data(), args.size() * sizeof(RegionArgs), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // args is a local
+    k_elbo<2><<<h->cfg.n_layers, 256, 0, h->stream>>>(h->elbo_args, h->elbo_out);
+    CK(cudaGetLastError());
+    count(h);
+    CK(cudaMemcpyAsync(out_host, h->elbo_out, (size_t)h->cfg.n_layers * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MRGP_OK;
+}
+
+int mrgp_predict_mean(mrgp_handle *h, const double *x_test_dev, int64_t n_test, const int64_t *const *test_offsets,
+                      int32_t n_test_layers, double *out_dev) {
+    int rc = check_ready(h, 0, true);
+    if (rc) return rc;
+    if (!x_test_dev || !out_dev || n_test < 1) return fail(h, MRGP_EINVAL, "bad argument");
+    EvalArgs ea{};
+    std::vector<const int64_t *> dev_off;
+    int64_t *staging = nullptr;
+    if (test_offsets) {
+        if (n_test_layers < 1 || n_test_layers > h->cfg.n_layers)
+            return fail(h, MRGP_EINVAL, "resolution in the test index set must be smaller or equal to that in the train set");
+        size_t total = 0;
+        for (int j = 0; j < n_test_layers; ++j) total += h->plan[j].R + 1;
+        if (total * sizeof(int64_t) > (size_t)h->cfg.n_samples * sizeof(double)) return fail(h, MRGP_ENOMEM, "test offsets do not fit the staging buffer");
+        staging = reinterpret_cast<int64_t *>(h->tmp_var);
+        size_t o = 0;
+        for (int j = 0; j < n_test_layers; ++j) {
+            const size_t cnt = h->plan[j].R + 1;
+            if (test_offsets[j][0] != 0 || test_offsets[j][cnt - 1] != n_test) return fail(h, MRGP_EINVAL, "test offsets of layer %d do not cover the test points", j);
+            CK(cudaMemcpyAsync(staging + o, test_offsets[j], cnt * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+            dev_off.push_back(staging + o);
+            o += cnt;
+        }
+        if ((rc = fill_eval_layers(h, ea, n_test_layers, dev_off.data()))) return rc;
+        ea.single_region = 0;
+    } else {
+        if ((rc = fill_eval_layers(h, ea, 1, nullptr))) return rc;
+        ea.single_region = 1;
+    }
+    ea.n = n_test;
+    ea.x = x_test_dev;
+    ea.out_mean = out_dev;
+    ea.out_var = nullptr;
+    k_eval_layers<2><<<(unsigned)((n_test + 127) / 128), 128, 0, h->stream>>>(ea);
+    CK(cudaGetLastError());
+    count(h);
+    CK(cudaStreamSynchronize(h->stream));
+    return MRGP_OK;
+}
+
+int mrgp_predict_var(mrgp_handle *h, const double *x_test_dev, int64_t n_test, double *out_dev) {
+    int rc = check_ready(h, 0, true);
+    if (rc) return rc;
+    if (!x_test_dev || !out_dev || n_test < 1) return fail(h, MRGP_EINVAL, "bad argument");
+    EvalArgs ea{};
+    if ((rc = fill_eval_layers(h, ea, 1, nullptr))) return rc;
+    ea.single_region = 1;
+    ea.n = n_test;
+    ea.x = x_test_dev;
+    ea.out_mean = nullptr;
+    ea.out_var = out_dev;
+    k_eval_layers<2><<<(unsigned)((n_test + 127) / 128), 128, 0, h->stream>>>(ea);
+    CK(cudaGetLastError());
+    count(h);
+    CK(cudaStreamSynchronize(h->stream));
+    return MRGP_OK;
+}
+
+int64_t mrgp_launch_count(const mrgp_handle *h) { return h ? h->launches : -1; }
+
+int64_t mrgp_cholesky_count(mrgp_handle *h) {
+    if (!h || !h->bound) return -1;
+    unsigned long long v = 0;
+    if (cudaMemcpyAsync(&v, h->chol_count, sizeof v, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    return (int64_t)v;
+}
+
+int mrgp_batched_cholesky(void *cuda_stream, double *a_dev, int32_t n, int64_t batch, int32_t *info_dev) {
+    mrgp_handle *h = nullptr;
+    if (!a_dev || !info_dev || n < 1 || n > 32 || batch < 1) return fail(h, MRGP_EINVAL, "bad argument");
+    const int64_t threads = batch * 32;
+    k_batched_cholesky<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a_dev, n, batch, info_dev);
+    CK(cudaGetLastError());
+    return MRGP_OK;
+}
+
+int mrgp_fp64_probe(void *cuda_stream, int64_t iters, double *sink_dev, float *ms_out) {
+    mrgp_handle *h = nullptr;
+    if (!sink_dev || !ms_out || iters < 1) return fail(h, MRGP_EINVAL, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    k_fp64_probe<<<sms * 4, 256, 0, st>>>(iters / 8 + 1, sink_dev);   // warm-up
+    CK(cudaEventRecord(e0, st));
+    k_fp64_probe<<<sms * 4, 256, 0, st>>>(iters, sink_dev);
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(ms_out, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return MRGP_OK;
+}
+
+// ---- host-only hooks ----------------------------------------------------------------------------
+int mrgp_plan_info(const mrgp_handle *h, int32_t layer, int32_t *n_ctas, int32_t *n_segments, int32_t *n_runs) {
+    if (!h || layer < 0 || layer >= h->cfg.n_layers) return MRGP_EINVAL;
+    if (n_ctas) *n_ctas = h->n_ctas;
+    if (n_segments) *n_segments = (int32_t)h->plan[layer].segs.size();
+    if (n_runs) *n_runs = h->plan[layer].n_runs;
+    return MRGP_OK;
+}
+
+int mrgp_plan_segments(const mrgp_handle *h, int32_t layer, int64_t *seg_out) {
+    if (!h || !seg_out || layer < 0 || layer >= h->cfg.n_layers) return MRGP_EINVAL;
+    const LayerPlan &lp = h->plan[layer];
+    for (size_t k = 0; k < lp.segs.size(); ++k) {
+        seg_out[k * 6 + 0] = lp.segs[k].start;
+        seg_out[k * 6 + 1] = lp.segs[k].start + lp.segs[k].len;
+        seg_out[k * 6 + 2] = lp.segs[k].region;
+        seg_out[k * 6 + 3] = lp.segs[k].parent;
+        seg_out[k * 6 + 4] = lp.segs[k].run;
+        seg_out[k * 6 + 5] = lp.seg_cta[k];
+    }
+    return MRGP_OK;
+}
+
+double mrgp_host_digamma(double x) { return digamma(x); }
+
+double mrgp_host_matern_spectral(double lambda, double nu, double l, double sf) { return matern_spectral(lambda, nu, l, sf); }
+
+void mrgp_host_bingham2(const double *b_in, double *b_out, double *kappa, double *rho, double *logc, double *axis_cov, int32_t *n_chol) {
+    Bingham2 bg;
+    bingham2(b_in[0], 0.5 * (b_in[1] + b_in[2]), b_in[3], bg);
+    b_out[0] = bg.b[0];
+    b_out[1] = b_out[2] = bg.b[1];
+    b_out[3] = bg.b[2];
+    kappa[0] = bg.kappa[0];
+    kappa[1] = bg.kappa[1];
+    rho[0] = bg.rho[0];
+    rho[1] = bg.rho[1];
+    *logc = bg.logc;
+    axis_cov[0] = bg.cov[0];
+    axis_cov[1] = axis_cov[2] = bg.cov[1];
+    axis_cov[3] = bg.cov[2];
+    if (n_chol) *n_chol = bg.n_chol;
+}
+
+void mrgp_host_basis(double x, double L, int32_t n_basis, double *phi_out) {
+    double f1, c2;
+    basis_seed(x, 0.5 / L, 1.0 / std::sqrt(L), f1, c2);
+    double fm = 0.0, f = f1;
+    for (int i = 0; i < n_basis; ++i) {
+        phi_out[i] = f;
+        const double fn = std::fma(c2, f, -fm);
+        fm = f;
+        f = fn;
+    }
+}
+
+int mrgp_host_omega(const double *lw, int32_t m, double *omega_out, int32_t *iters_out) {
+    // serial statement of k_omega (same iteration, same stopping rule)
+    std::vector<double> K((size_t)m * m), u(m, 1.0), v(m, 1.0);
+    for (int i = 0; i < m; ++i) {
+        double mx = -INFINITY;
+        for (int k = 0; k < m; ++k) mx = std::max(mx, lw[i * m + k]);
+        for (int k = 0; k < m; ++k) K[i * m + k] = std::exp(lw[i * m + k] - mx);
+    }
+    int it = 0;
+    for (; it < 5000; ++it) {
+        bool bad = false;
+        for (int i = 0; i < m; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < m; ++k) s += K[i * m + k] * v[k];
+            if (std::fabs(u[i] * s - 1.0) > 1e-13) bad = true;
+            u[i] = 1.0 / s;
+        }
+        const bool done = it > 0 && !bad;
+        for (int k = 0; k < m; ++k) {
+            double s = 0.0;
+            for (int i = 0; i < m; ++i) s += K[i * m + k] * u[i];
+            v[k] = 1.0 / s;
+        }
+        if (done) break;
+    }
+    for (int i = 0; i < m; ++i)
+        for (int k = 0; k < m; ++k) omega_out[i * m + k] = u[i] * K[i * m + k] * v[k];
+    if (iters_out) *iters_out = it + 1;
+    return MRGP_OK;
+}
+
+}  // extern "C"
+

@@ -1,0 +1,1061 @@
+// Device kernels of the ciMRGP / fiMRGP sweep for sm_100a.
+//
+// Layout of the streaming kernels (phase A, phase B, basis build): the sample axis [0, N) is cut into
+// one contiguous range per persistent CTA; each range is cut further at the region boundaries of the
+// layer and of its parent layer into SEGMENTS (host-built table).  Inside a segment all 256 threads
+// stride over the samples (coalesced 8/16-byte loads per lane, one sample ahead prefetched), the basis
+// functions of a sample are produced by the three-term sine recurrence from one sincospi, and per-thread
+// FP64 register accumulators hold the region statistics.  At the end of a RUN (last segment of a region
+// inside the CTA range) the block reduces the accumulators through shared memory in a fixed order and
+// writes one partial per run: no atomics, results are reproducible for a given launch geometry.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mrgp_math.cuh"
+
+namespace mrgp {
+
+constexpr int kThreads = 256;      // streaming CTA size (8 warps)
+constexpr int kPartBStride = 8;    // doubles per phase-B partial (dy + 3 <= 8)
+constexpr int kRedChunk = 32;      // values reduced per block_reduce round
+constexpr int kRedSmemDoubles = kRedChunk * kThreads + 8 * 32;
+
+struct Segment {
+    int64_t start;
+    int32_t len;
+    int32_t region;
+    int32_t parent;
+    int32_t run;
+    int32_t flush;   // 1: last segment of its run
+    int32_t pad;
+};
+
+// Arguments of the streaming kernels for one layer.
+struct StreamArgs {
+    const Segment *segs;
+    const int32_t *cta_seg;      // (n_ctas + 1) first segment of each CTA
+    const double *x;             // (N)
+    const double *y;             // (N, DY)
+    double *g;                   // (N, DY) latent mean of the layer minus the parent's bias (in place)
+    double *h;                   // (N)     latent variance minus the parent's bias variance (in place)
+    const double *inv2L;         // (R)
+    const double *rsqrtL;        // (R)
+    const double *A;             // (R, M, DY) current coefficients
+    const double *A_prev;        // (R, M, DY) coefficients before this layer's update (phase B, inferred)
+    const double *cm2;           // (R, M)
+    const double *bias;          // (R, DY) current (old) bias of the layer
+    const double *pbias;         // (Rp, DY) parent-layer bias (new)
+    const double *pbias_var;     // (Rp)
+    double *part;                // partial sums per run
+    int32_t part_stride;
+};
+
+// ------------------------------------------------------------------------------------------------
+// block reductions
+// ------------------------------------------------------------------------------------------------
+
+// Sum NV per-thread values over the 256 threads of the block, fixed order; out[v] written by warp 0.
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *red, double *out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *part = red + kRedChunk * kThreads;
+#pragma unroll
+    for (int c = 0; c < (NV + kRedChunk - 1) / kRedChunk; ++c) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kRedChunk; ++k)
+            if (c * kRedChunk + k < NV) red[k * kThreads + tid] = v[c * kRedChunk + k];
+        __syncthreads();
+        double s = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) s += red[lane * kThreads + warp * 32 + ((k + lane) & 31)];
+        part[warp * 32 + lane] = s;
+        __syncthreads();
+        if (tid < 32 && c * kRedChunk + tid < NV) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < kThreads / 32; ++q) t += part[q * 32 + tid];
+            out[c * kRedChunk + tid] = t;
+        }
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Few values (NV <= 8): shuffle inside the warp, then across the 8 warps through shared memory.
+template <int NV, bool MAX>
+__device__ __forceinline__ void block_reduce_small(double (&v)[NV], double *sm /* >= 8*8 */, double *out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const double s = MAX ? warp_max(v[k]) : warp_sum(v[k]);
+        if (lane == 0) sm[warp * 8 + k] = s;
+    }
+    __syncthreads();
+    if (tid < NV) {
+        double t = sm[tid];
+#pragma unroll
+        for (int q = 1; q < kThreads / 32; ++q) t = MAX ? fmax(t, sm[q * 8 + tid]) : t + sm[q * 8 + tid];
+        out[tid] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 / K1: max|x| per run, then sum phi^2 per run
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_absmax(StreamArgs p) {
+    __shared__ double sm[64];
+    const int tid = threadIdx.x;
+    double acc[1] = {0.0};
+    const int s0 = p.cta_seg[blockIdx.x], s1 = p.cta_seg[blockIdx.x + 1];
+    for (int s = s0; s < s1; ++s) {
+        const Segment sg = p.segs[s];
+        const int64_t end = sg.start + sg.len;
+        for (int64_t n = sg.start + tid; n < end; n += kThreads) acc[0] = fmax(acc[0], fabs(p.x[n]));
+        if (sg.flush) {
+            block_reduce_small<1, true>(acc, sm, p.part + (size_t)sg.run * p.part_stride);
+            acc[0] = 0.0;
+        }
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(kThreads, 1) k_phi2sum(StreamArgs p) {
+    extern __shared__ double red[];
+    __shared__ double sScal[2];
+    const int tid = threadIdx.x;
+    double acc[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) acc[i] = 0.0;
+    const int s0 = p.cta_seg[blockIdx.x], s1 = p.cta_seg[blockIdx.x + 1];
+    for (int s = s0; s < s1; ++s) {
+        const Segment sg = p.segs[s];
+        __syncthreads();
+        if (tid == 0) {
+            sScal[0] = p.inv2L[sg.region];
+            sScal[1] = p.rsqrtL[sg.region];
+        }
+        __syncthreads();
+        const double inv2L = sScal[0], rs = sScal[1];
+        const int64_t end = sg.start + sg.len;
+        for (int64_t n = sg.start + tid; n < end; n += kThreads) {
+            double f1, c2;
+            basis_seed(p.x[n], inv2L, rs, f1, c2);
+            double fm = 0.0, f = f1;
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                acc[i] = fma(f, f, acc[i]);
+                const double fn = fma(c2, f, -fm);
+                fm = f;
+                f = fn;
+            }
+        }
+        if (sg.flush) {
+            block_reduce_store<M>(acc, red, p.part + (size_t)sg.run * p.part_stride);
+#pragma unroll
+            for (int i = 0; i < M; ++i) acc[i] = 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase A: T[i][d] = sum_n phi_i(n) r_d(n),  r = y - (fbar + b + Phi A_old^T)
+//   INFER  : targets are the layer's own prediction Phi A_old^T + (b_old + fbar)   (ci, j > 0;
+//            LatentOutputs.py:25-40 via MRGP.py:577) instead of the observations (LatentOutputs.py:6-18)
+//   LATENT : the layer has coarser layers below it (fbar = g + parent bias); layer 0 has fbar == 0.
+// y_tilde_i = T_i + (sum_n phi_i^2) a_i reproduces Posteriors.py:61-78 (the penalty over k != i) with
+// one pass instead of M.
+// ------------------------------------------------------------------------------------------------
+template <int DY, int M, bool INFER, bool LATENT>
+__global__ void __launch_bounds__(kThreads, 1) k_phase_a(StreamArgs p) {
+    extern __shared__ double red[];
+    __shared__ double sA[M * DY];
+    __shared__ double sScal[2 + 2 * DY];
+    const int tid = threadIdx.x;
+    double T[M * DY];
+#pragma unroll
+    for (int i = 0; i < M * DY; ++i) T[i] = 0.0;
+    const int s0 = p.cta_seg[blockIdx.x], s1 = p.cta_seg[blockIdx.x + 1];
+    for (int s = s0; s < s1; ++s) {
+        const Segment sg = p.segs[s];
+        __syncthreads();
+        if (tid < M * DY) sA[tid] = p.A[(size_t)sg.region * (M * DY) + tid];
+        if (tid == 0) {
+            sScal[0] = p.inv2L[sg.region];
+            sScal[1] = p.rsqrtL[sg.region];
+        }
+        if (tid < DY) {
+            sScal[2 + tid] = p.bias[(size_t)sg.region * DY + tid];
+            sScal[2 + DY + tid] = LATENT ? p.pbias[(size_t)sg.parent * DY + tid] : 0.0;
+        }
+        __syncthreads();
+        const double inv2L = sScal[0], rs = sScal[1];
+        double b[DY], pb[DY];
+#pragma unroll
+        for (int d = 0; d < DY; ++d) {
+            b[d] = sScal[2 + d];
+            pb[d] = sScal[2 + DY + d];
+        }
+        const int64_t end = sg.start + sg.len;
+        int64_t n = sg.start + tid;
+        double xn = 0.0, yn[DY], gn[DY];
+#pragma unroll
+        for (int d = 0; d < DY; ++d) yn[d] = gn[d] = 0.0;
+        if (n < end) {
+            xn = p.x[n];
+#pragma unroll
+            for (int d = 0; d < DY; ++d) {
+                if (!INFER) yn[d] = p.y[n * DY + d];
+                if (LATENT) gn[d] = p.g[n * DY + d];
+            }
+        }
+        while (n < end) {
+            asm volatile("" ::: "memory");   // keep the region coefficients in shared memory, not registers
+            const double xc = xn;
+            double yc[DY], gc[DY];
+#pragma unroll
+            for (int d = 0; d < DY; ++d) {
+                yc[d] = yn[d];
+                gc[d] = gn[d];
+            }
+            n += kThreads;
+            if (n < end) {
+                xn = p.x[n];
+#pragma unroll
+                for (int d = 0; d < DY; ++d) {
+                    if (!INFER) yn[d] = p.y[n * DY + d];
+                    if (LATENT) gn[d] = p.g[n * DY + d];
+                }
+            }
+            double phi[M];
+            double c2;
+            basis_seed(xc, inv2L, rs, phi[0], c2);
+            if (M > 1) phi[1] = c2 * phi[0];
+#pragma unroll
+            for (int i = 2; i < M; ++i) phi[i] = fma(c2, phi[i - 1], -phi[i - 2]);
+            double e[DY];
+#pragma unroll
+            for (int d = 0; d < DY; ++d) e[d] = 0.0;
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+#pragma unroll
+                for (int d = 0; d < DY; ++d) e[d] = fma(phi[i], sA[i * DY + d], e[d]);
+            double r[DY];
+#pragma unroll
+            for (int d = 0; d < DY; ++d) {
+                const double fb = LATENT ? gc[d] + pb[d] : 0.0;
+                const double target = INFER ? e[d] + (b[d] + fb) : yc[d];
+                r[d] = target - ((fb + b[d]) + e[d]);
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+#pragma unroll
+                for (int d = 0; d < DY; ++d) T[i * DY + d] = fma(phi[i], r[d], T[i * DY + d]);
+        }
+        if (sg.flush) {
+            block_reduce_store<M * DY>(T, red, p.part + (size_t)sg.run * p.part_stride);
+#pragma unroll
+            for (int i = 0; i < M * DY; ++i) T[i] = 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase B: residual statistics with the NEW coefficients, fused with the propagation of the latent
+// mean / variance to the next layer (Posteriors.py:81-148, Stats.py:126-157):
+//   r = target - Phi A_new^T - fbar;   partial = [sum r_d, sum |r|^2, sum fvar, sum_n sum_i phi_i^2 cm2_i]
+//   g <- fbar + Phi A_new^T,  h <- fvar + sum_i phi_i^2 cm2_i      (PROPAGATE; the layer's own bias and
+//   bias variance are added by the next layer when it reads g, h, because they are not known yet).
+// ------------------------------------------------------------------------------------------------
+template <int DY, int M, bool INFER, bool LATENT, bool PROPAGATE>
+__global__ void __launch_bounds__(kThreads, 2) k_phase_b(StreamArgs p) {
+    __shared__ double sAn[M * DY];
+    __shared__ double sAo[INFER ? M * DY : 1];
+    __shared__ double sC[M];
+    __shared__ double sScal[4 + 2 * DY];
+    __shared__ double sRed[64];
+    const int tid = threadIdx.x;
+    double acc[DY + 3];
+#pragma unroll
+    for (int i = 0; i < DY + 3; ++i) acc[i] = 0.0;
+    const int s0 = p.cta_seg[blockIdx.x], s1 = p.cta_seg[blockIdx.x + 1];
+    for (int s = s0; s < s1; ++s) {
+        const Segment sg = p.segs[s];
+        __syncthreads();
+        if (tid < M * DY) {
+            sAn[tid] = p.A[(size_t)sg.region * (M * DY) + tid];
+            if (INFER) sAo[tid] = p.A_prev[(size_t)sg.region * (M * DY) + tid];
+        }
+        if (tid < M) sC[tid] = p.cm2[(size_t)sg.region * M + tid];
+        if (tid == 0) {
+            sScal[0] = p.inv2L[sg.region];
+            sScal[1] = p.rsqrtL[sg.region];
+            sScal[2] = LATENT ? p.pbias_var[sg.parent] : 0.0;
+        }
+        if (tid < DY) {
+            sScal[4 + tid] = p.bias[(size_t)sg.region * DY + tid];
+            sScal[4 + DY + tid] = LATENT ? p.pbias[(size_t)sg.parent * DY + tid] : 0.0;
+        }
+        __syncthreads();
+        const double inv2L = sScal[0], rs = sScal[1], pbv = sScal[2];
+        double b[DY], pb[DY];
+#pragma unroll
+        for (int d = 0; d < DY; ++d) {
+            b[d] = sScal[4 + d];
+            pb[d] = sScal[4 + DY + d];
+        }
+        const int64_t end = sg.start + sg.len;
+        int64_t n = sg.start + tid;
+        double xn = 0.0, hn = 0.0, yn[DY], gn[DY];
+#pragma unroll
+        for (int d = 0; d < DY; ++d) yn[d] = gn[d] = 0.0;
+        if (n < end) {
+            xn = p.x[n];
+            if (LATENT) hn = p.h[n];
+#pragma unroll
+            for (int d = 0; d < DY; ++d) {
+                if (!INFER) yn[d] = p.y[n * DY + d];
+                if (LATENT) gn[d] = p.g[n * DY + d];
+            }
+        }
+        while (n < end) {
+            asm volatile("" ::: "memory");   // keep the region coefficients in shared memory, not registers
+            const int64_t nc = n;
+            const double xc = xn, hc = hn;
+            double yc[DY], gc[DY];
+#pragma unroll
+            for (int d = 0; d < DY; ++d) {
+                yc[d] = yn[d];
+                gc[d] = gn[d];
+            }
+            n += kThreads;
+            if (n < end) {
+                xn = p.x[n];
+                if (LATENT) hn = p.h[n];
+#pragma unroll
+                for (int d = 0; d < DY; ++d) {
+                    if (!INFER) yn[d] = p.y[n * DY + d];
+                    if (LATENT) gn[d] = p.g[n * DY + d];
+                }
+            }
+            double f1, c2;
+            basis_seed(xc, inv2L, rs, f1, c2);
+            double fm = 0.0, f = f1;
+            double en[DY], eo[DY], v = 0.0;
+#pragma unroll
+            for (int d = 0; d < DY; ++d) en[d] = eo[d] = 0.0;
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+#pragma unroll
+                for (int d = 0; d < DY; ++d) {
+                    en[d] = fma(f, sAn[i * DY + d], en[d]);
+                    if (INFER) eo[d] = fma(f, sAo[i * DY + d], eo[d]);
+                }
+                v = fma(f * sC[i], f, v);
+                const double fn = fma(c2, f, -fm);
+                fm = f;
+                f = fn;
+            }
+            const double fv = LATENT ? hc + pbv : 0.0;
+            double rr = 0.0;
+#pragma unroll
+            for (int d = 0; d < DY; ++d) {
+                const double fb = LATENT ? gc[d] + pb[d] : 0.0;
+                const double target = INFER ? eo[d] + (b[d] + fb) : yc[d];
+                const double r = (target - en[d]) - fb;
+                acc[d] += r;
+                rr = fma(r, r, rr);
+                if (PROPAGATE) p.g[nc * DY + d] = fb + en[d];
+            }
+            acc[DY] += rr;
+            acc[DY + 1] += fv;
+            acc[DY + 2] += v;
+            if (PROPAGATE) p.h[nc] = fv + v;
+        }
+        if (sg.flush) {
+            block_reduce_small<DY + 3, false>(acc, sRed, p.part + (size_t)sg.run * p.part_stride);
+#pragma unroll
+            for (int i = 0; i < DY + 3; ++i) acc[i] = 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-region small kernels
+// ------------------------------------------------------------------------------------------------
+struct RegionArgs {
+    int32_t R, M, DY, layer;
+    int32_t mode;              // 0 ci, 1 fi
+    int32_t infer;             // ci, layer > 0
+    const int32_t *region_run; // (R + 1) run range of each region
+    const int64_t *offsets;    // (R + 1)
+    const double *part;        // partials of the preceding streaming kernel
+    int32_t part_stride;
+    // static
+    double *L, *inv2L, *rsqrtL, *lam, *S, *d;
+    // posterior / stats
+    double *prec, *zeta, *ytil, *A, *A_prev, *m2, *cm2;
+    double *noise_shape, *noise_scale, *noise_shape0, *noise_scale0, *noise_mean, *noise_log_mean;
+    double *bias_prec, *bias_prec0, *bias_mean, *bias_mean0, *bias_var, *yvar, *sumsB;
+    // shared (ci) or per-region (fi) axis / ARD
+    double *axB, *axKappa, *axRho, *axLogC, *axCov, *ardShape, *ardScale, *ardMean, *ardLogMean;
+    double *omega, *logOmegaHat;
+    double *primeB, *primeLogC, *primeShape, *primeScale;   // snapshot read by ARD / omega (ci)
+    const double *priorB, *priorLogC, *priorShape, *priorScale;
+    double *bcontrib;          // (R, M, 3) ci: 0.5 noise zeta ytil ytil^T
+    unsigned long long *chol_count;
+    double fi_shape0_mix, fi_scale0_mix;   // sum_k (1/M) shape0_k, sum_k (1/M) scale0_k (Posteriors.py:293-295)
+    // spectral density
+    int32_t use_prior;
+    double nu, ell, sf, interval_factor;
+    int32_t L_given;
+};
+
+// K3 + K2: L = factor max|x| (BasisInterval.py:15-16), 1/(2L), L^-1/2, lambda (KernelClass.py:36),
+// S (KernelClass.py:80-90).  One warp per region.
+__global__ void k_region_setup(RegionArgs a) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= a.R) return;
+    double L;
+    if (a.L_given) {
+        L = a.L[r];
+    } else {
+        double m = 0.0;
+        for (int q = a.region_run[r] + lane; q < a.region_run[r + 1]; q += 32) m = fmax(m, a.part[(size_t)q * a.part_stride]);
+        m = warp_max(m);
+        L = a.interval_factor * m;
+    }
+    if (lane == 0) {
+        a.L[r] = L;
+        a.inv2L[r] = 0.5 / L;
+        a.rsqrtL[r] = 1.0 / sqrt(L);
+    }
+    for (int i = lane; i < a.M; i += 32) {
+        const double w = (kPi * (double)(i + 1)) / (2.0 * L);
+        const double lam = w * w;
+        a.lam[(size_t)r * a.M + i] = lam;
+        a.S[(size_t)r * a.M + i] = a.use_prior ? matern_spectral(lam, a.nu, a.ell, a.sf) : 1.0;
+    }
+}
+
+// d[r][i] = sum over the region's runs of the phi^2 partials (Posteriors.py:41).
+__global__ void k_reduce_d(RegionArgs a) {
+    const int r = blockIdx.x;
+    for (int i = threadIdx.x; i < a.M; i += blockDim.x) {
+        double s = 0.0;
+        for (int q = a.region_run[r]; q < a.region_run[r + 1]; ++q) s += a.part[(size_t)q * a.part_stride + i];
+        a.d[(size_t)r * a.M + i] = s;
+    }
+}
+
+// Sum the phase-A partials of region r for value t (= i*DY + d), `slices` threads per value.
+// Block of 128 threads laid out as (slice, value) with value fastest; NVAL = M*DY <= 96 -> up to 1 slice
+// per 128 threads; for regions with many runs (coarse layers) the kernel is launched with 1024 threads
+// so that 8+ slices share the run loop.
+template <int DY>
+__global__ void k_reduce_scale(RegionArgs a) {
+    extern __shared__ double sm[];   // [slices][NV] + ytil[NV]
+    const int r = blockIdx.x;
+    const int M = a.M, NV = M * DY;
+    const int nval = (NV + 31) & ~31;
+    const int slices = blockDim.x / nval;
+    const int v = threadIdx.x % nval, sl = threadIdx.x / nval;
+    double acc = 0.0;
+    if (v < NV && sl < slices)
+        for (int q = a.region_run[r] + sl; q < a.region_run[r + 1]; q += slices) acc += a.part[(size_t)q * a.part_stride + v];
+    if (sl < slices) sm[sl * nval + v] = acc;
+    __syncthreads();
+    double *ytil_s = sm + slices * nval;
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+        for (int q = 0; q < slices; ++q) t += sm[q * nval + threadIdx.x];
+        const int i = threadIdx.x / DY;
+        // y_tilde_i = Phi_i^T r + (sum phi_i^2) a_i   (Posteriors.py:61-78)
+        const double yt = t + a.d[(size_t)r * M + i] * a.A[(size_t)r * NV + threadIdx.x];
+        ytil_s[threadIdx.x] = yt;
+        a.ytil[(size_t)r * NV + threadIdx.x] = yt;
+    }
+    __syncthreads();
+    if (threadIdx.x < M) {
+        const int i = threadIdx.x;
+        const size_t ri = (size_t)r * M + i;
+        const double noise = a.noise_mean[r];
+        const double ard = (a.mode == 0) ? a.ardMean[i] : a.ardMean[ri];
+        // Posteriors.py:40-42 / :304-306
+        const double prec = ard / a.S[ri] + noise * a.d[ri];
+        const double zeta = noise / prec;
+        a.prec[ri] = prec;
+        a.zeta[ri] = zeta;
+        const double w = 0.5 * noise * zeta;
+        static_assert(DY == 2, "dy == 2 only");
+        const double y0 = ytil_s[i * DY], y1 = ytil_s[i * DY + 1];
+        if (a.mode == 0) {
+            // contribution to B_i, summed over regions by k_axis_shared (Posteriors.py:507-517)
+            a.bcontrib[ri * 3 + 0] = w * (y0 * y0);
+            a.bcontrib[ri * 3 + 1] = w * (y0 * y1);
+            a.bcontrib[ri * 3 + 2] = w * (y1 * y1);
+        } else {
+            // fi: the prior B is the untouched zero prior, omega == 1/M (Posteriors.py:253-285)
+            Bingham2 bg;
+            bingham2(0.0 + w * (y0 * y0), 0.0 + w * (y0 * y1), 0.0 + w * (y1 * y1), bg);
+            atomicAdd(a.chol_count, (unsigned long long)bg.n_chol);
+            a.axB[ri * 4 + 0] = bg.b[0];
+            a.axB[ri * 4 + 1] = bg.b[1];
+            a.axB[ri * 4 + 2] = bg.b[1];
+            a.axB[ri * 4 + 3] = bg.b[2];
+            a.axKappa[ri * 2 + 0] = bg.kappa[0];
+            a.axKappa[ri * 2 + 1] = bg.kappa[1];
+            a.axRho[ri * 2 + 0] = bg.rho[0];
+            a.axRho[ri * 2 + 1] = bg.rho[1];
+            a.axLogC[ri] = bg.logc;
+            a.axCov[ri * 4 + 0] = bg.cov[0];
+            a.axCov[ri * 4 + 1] = bg.cov[1];
+            a.axCov[ri * 4 + 2] = bg.cov[1];
+            a.axCov[ri * 4 + 3] = bg.cov[2];
+            // Stats.py:257-290
+            const double cy0 = bg.cov[0] * y0 + bg.cov[1] * y1, cy1 = bg.cov[1] * y0 + bg.cov[2] * y1;
+            a.A_prev[ri * DY + 0] = a.A[ri * DY + 0];
+            a.A_prev[ri * DY + 1] = a.A[ri * DY + 1];
+            a.A[ri * DY + 0] = zeta * cy0;
+            a.A[ri * DY + 1] = zeta * cy1;
+            const double z2 = zeta * zeta;
+            const double m2 = 1.0 / prec + z2 * (y0 * cy0 + y1 * cy1);
+            const double ccy0 = bg.cov[0] * cy0 + bg.cov[1] * cy1, ccy1 = bg.cov[1] * cy0 + bg.cov[2] * cy1;
+            const double cm2 = 1.0 / prec + z2 * (y0 * (cy0 - ccy0) + y1 * (cy1 - ccy1));
+            a.m2[ri] = m2;
+            a.cm2[ri] = cm2;
+            // Posteriors.py:288-295, Stats.py:251-255
+            const double shape = a.fi_shape0_mix + 0.5 * (double)a.R;
+            const double scale = a.fi_scale0_mix + 0.5 * (m2 / a.S[ri]);
+            a.ardShape[ri] = shape;
+            a.ardScale[ri] = scale;
+            a.ardMean[ri] = shape / scale;
+            a.ardLogMean[ri] = digamma(shape) - log(scale);
+        }
+    }
+}
+
+// ci: B_i = sum_k omega_ik B'_k + sum_l contrib_li, PD guard, Bingham parameters, axis covariance
+// (Posteriors.py:497-530, Stats.py:375-382).  Also takes the snapshot of the "previous posterior"
+// (MRGP.py:575 / :581) that ARD and omega read.  One block of 1024 threads.
+template <int DY>
+__global__ void __launch_bounds__(1024) k_axis_shared(RegionArgs a) {
+    static_assert(DY == 2, "dy == 2 only");
+    extern __shared__ double sm[];   // [slices][M*3]
+    const int M = a.M, NV = M * 3;
+    const int nval = (NV + 31) & ~31;
+    const int slices = blockDim.x / nval;
+    const int v = threadIdx.x % nval, sl = threadIdx.x / nval;
+    const bool first = (a.layer == 0);
+    // snapshot prime <- prior (layer 0) or current shared posterior
+    for (int t = threadIdx.x; t < M * 4; t += blockDim.x) a.primeB[t] = first ? a.priorB[t] : a.axB[t];
+    for (int t = threadIdx.x; t < M; t += blockDim.x) {
+        a.primeLogC[t] = first ? a.priorLogC[t] : a.axLogC[t];
+        a.primeShape[t] = first ? a.priorShape[t] : a.ardShape[t];
+        a.primeScale[t] = first ? a.priorScale[t] : a.ardScale[t];
+    }
+    double acc = 0.0;
+    if (v < NV && sl < slices)
+        for (int l = sl; l < a.R; l += slices) acc += a.bcontrib[(size_t)l * NV + v];
+    if (sl < slices) sm[sl * nval + v] = acc;
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+        for (int q = 0; q < slices; ++q) t += sm[q * nval + threadIdx.x];
+        sm[slices * nval + threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < M) {
+        const int i = threadIdx.x;
+        const double *data = sm + slices * nval + i * 3;
+        double b00 = 0.0, b01 = 0.0, b11 = 0.0;
+        for (int k = 0; k < M; ++k) {
+            const double w = a.omega[i * M + k];
+            b00 += w * a.primeB[k * 4 + 0];
+            b01 += w * a.primeB[k * 4 + 1];
+            b11 += w * a.primeB[k * 4 + 3];
+        }
+        Bingham2 bg;
+        bingham2(b00 + data[0], b01 + data[1], b11 + data[2], bg);
+        atomicAdd(a.chol_count, (unsigned long long)bg.n_chol);
+        a.axB[i * 4 + 0] = bg.b[0];
+        a.axB[i * 4 + 1] = bg.b[1];
+        a.axB[i * 4 + 2] = bg.b[1];
+        a.axB[i * 4 + 3] = bg.b[2];
+        a.axKappa[i * 2 + 0] = bg.kappa[0];
+        a.axKappa[i * 2 + 1] = bg.kappa[1];
+        a.axRho[i * 2 + 0] = bg.rho[0];
+        a.axRho[i * 2 + 1] = bg.rho[1];
+        a.axLogC[i] = bg.logc;
+        a.axCov[i * 4 + 0] = bg.cov[0];
+        a.axCov[i * 4 + 1] = bg.cov[1];
+        a.axCov[i * 4 + 2] = bg.cov[1];
+        a.axCov[i * 4 + 3] = bg.cov[2];
+    }
+}
+
+// ci: a, m2, cm2 per (region, basis) from the shared axis covariance (Stats.py:67-100).
+template <int DY>
+__global__ void k_scale_stats(RegionArgs a) {
+    static_assert(DY == 2, "dy == 2 only");
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.R * a.M) return;
+    const int i = t % a.M;
+    const size_t ri = t;
+    const double c00 = a.axCov[i * 4 + 0], c01 = a.axCov[i * 4 + 1], c11 = a.axCov[i * 4 + 3];
+    const double y0 = a.ytil[ri * DY], y1 = a.ytil[ri * DY + 1];
+    const double zeta = a.zeta[ri], prec = a.prec[ri];
+    const double cy0 = c00 * y0 + c01 * y1, cy1 = c01 * y0 + c11 * y1;
+    a.A_prev[ri * DY + 0] = a.A[ri * DY + 0];
+    a.A_prev[ri * DY + 1] = a.A[ri * DY + 1];
+    a.A[ri * DY + 0] = zeta * cy0;
+    a.A[ri * DY + 1] = zeta * cy1;
+    const double z2 = zeta * zeta;
+    a.m2[ri] = 1.0 / prec + z2 * (y0 * cy0 + y1 * cy1);
+    const double ccy0 = c00 * cy0 + c01 * cy1, ccy1 = c01 * cy0 + c11 * cy1;
+    a.cm2[ri] = 1.0 / prec + z2 * (y0 * (cy0 - ccy0) + y1 * (cy1 - ccy1));
+}
+
+// ci: ARD posterior and moments (Posteriors.py:533-541, Stats.py:385-388), then log omega_hat
+// (Stats.py:405-412).  One block of 1024 threads.
+template <int DY>
+__global__ void __launch_bounds__(1024) k_ard(RegionArgs a) {
+    static_assert(DY == 2, "dy == 2 only");
+    extern __shared__ double sm[];   // [slices][M] + ard_mean[M] + ard_log_mean[M]
+    const int M = a.M;
+    const int nval = (M + 31) & ~31;
+    const int slices = blockDim.x / nval;
+    const int v = threadIdx.x % nval, sl = threadIdx.x / nval;
+    double acc = 0.0;
+    if (v < M && sl < slices)
+        for (int l = sl; l < a.R; l += slices) acc += a.m2[(size_t)l * M + v] / a.S[(size_t)l * M + v];
+    if (sl < slices) sm[sl * nval + v] = acc;
+    __syncthreads();
+    double *s_mean = sm + slices * nval, *s_lmean = s_mean + M;
+    if (threadIdx.x < M) {
+        const int i = threadIdx.x;
+        double beta2 = 0.0;
+        for (int q = 0; q < slices; ++q) beta2 += sm[q * nval + i];
+        double sh = 0.0, sc = 0.0;
+        for (int k = 0; k < M; ++k) {
+            const double w = a.omega[i * M + k];
+            sh += w * a.primeShape[k];
+            sc += w * a.primeScale[k];
+        }
+        const double shape = sh + 0.5 * (double)a.R;
+        const double scale = sc + 0.5 * beta2;
+        a.ardShape[i] = shape;
+        a.ardScale[i] = scale;
+        const double mean = shape / scale, lmean = digamma(shape) - log(scale);
+        a.ardMean[i] = mean;
+        a.ardLogMean[i] = lmean;
+        s_mean[i] = mean;
+        s_lmean[i] = lmean;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < M * M; t += blockDim.x) {
+        const int i = t / M, k = t % M;
+        const double *C = a.axCov + i * 4, *B = a.primeB + k * 4;
+        const double tr = C[0] * B[0] + C[1] * B[2] + C[2] * B[1] + C[3] * B[3];   // trace(C_i B'_k)
+        const double shp = a.primeShape[k], scp = a.primeScale[k];
+        a.logOmegaHat[t] = tr - a.primeLogC[k] + shp * log(scp) - lgamma(shp) + (shp - 1.0) * s_lmean[i] - scp * s_mean[i];
+    }
+}
+
+// ci: omega = diag(alpha) exp(log_omega_hat) diag(beta) with unit row and column sums (Stats.py:413-420;
+// the reference solves the 2M log-scalings with MINPACK hybrd to xtol 1.5e-8, this is the fixed point
+// it approximates, by Sinkhorn iteration on the row-max-shifted kernel).  One block of 1024 threads =
+// 32 warps, warp w owns rows/columns w and w + 32 (M <= 64).
+__global__ void __launch_bounds__(1024) k_omega(RegionArgs a, int max_iter, double tol) {
+    extern __shared__ double sm[];   // K[M*M], u[M], v[M], err
+    const int M = a.M;
+    double *K = sm, *u = K + M * M, *vv = u + M, *flag = vv + M;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = warp; i < M; i += 32) {
+        double mx = -INFINITY;
+        for (int k = lane; k < M; k += 32) mx = fmax(mx, a.logOmegaHat[i * M + k]);
+        mx = warp_max(mx);
+        for (int k = lane; k < M; k += 32) K[i * M + k] = exp(a.logOmegaHat[i * M + k] - mx);
+    }
+    for (int t = threadIdx.x; t < M; t += blockDim.x) {
+        u[t] = 1.0;
+        vv[t] = 1.0;
+    }
+    __syncthreads();
+    for (int it = 0; it < max_iter; ++it) {
+        if (threadIdx.x == 0) *flag = 0.0;
+        __syncthreads();
+        // rows: u_i = 1 / sum_k K_ik v_k ; the deviation of the current row sums from 1 is the error
+        for (int i = warp; i < M; i += 32) {
+            double s = 0.0;
+            for (int k = lane; k < M; k += 32) s = fma(K[i * M + k], vv[k], s);
+            s = warp_sum(s);
+            if (lane == 0) {
+                const double e = fabs(u[i] * s - 1.0);
+                if (e > tol) *flag = 1.0;   // benign race: any writer sets the same value
+                u[i] = 1.0 / s;
+            }
+        }
+        __syncthreads();
+        const bool done = (it > 0) && (*flag == 0.0);
+        // columns: v_k = 1 / sum_i K_ik u_i
+        for (int k = warp; k < M; k += 32) {
+            double s = 0.0;
+            for (int i = lane; i < M; i += 32) s = fma(K[i * M + k], u[i], s);
+            s = warp_sum(s);
+            if (lane == 0) vv[k] = 1.0 / s;
+        }
+        __syncthreads();
+        if (done) break;
+    }
+    for (int t = threadIdx.x; t < M * M; t += blockDim.x) a.omega[t] = u[t / M] * K[t] * vv[t % M];
+}
+
+// P4, P5, S5 for region-specific noise and bias (Posteriors.py:81-93, 132-148 (ci) / 396-412 (fi);
+// Stats.py:102-124).  One block of 128 threads per region: 16 slices x 8 values over the run partials.
+template <int DY>
+__global__ void k_bias_noise(RegionArgs a) {
+    __shared__ double sm[16 * 8];
+    const int r = blockIdx.x;
+    const int v = threadIdx.x & 7, sl = threadIdx.x >> 3;
+    double acc = 0.0;
+    if (v < DY + 3)
+        for (int q = a.region_run[r] + sl; q < a.region_run[r + 1]; q += 16) acc += a.part[(size_t)q * a.part_stride + v];
+    sm[sl * 8 + v] = acc;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double t = 0.0;
+        for (int q = 0; q < 16; ++q) t += sm[q * 8 + threadIdx.x];
+        sm[threadIdx.x] = t;
+        if (threadIdx.x < DY + 3) a.sumsB[(size_t)r * (DY + 3) + threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double n = (double)(a.offsets[r + 1] - a.offsets[r]);
+        const double bp0 = a.bias_prec0[r];
+        const double bp = bp0 + n;
+        double t3 = 0.0, t4 = 0.0;
+        for (int d = 0; d < DY; ++d) {
+            const double m0 = a.bias_mean0[(size_t)r * DY + d];
+            const double m = (1.0 / bp) * (m0 * bp0 + sm[d]);
+            a.bias_mean[(size_t)r * DY + d] = m;
+            t3 += m0 * m0;
+            t4 += m * m;
+        }
+        t3 *= bp0;
+        t4 *= bp;
+        // y_var: 1/noise_mean(old) for inferred targets, not multiplied by n in the ci regional/regional
+        // variant (Posteriors.py:138); fi targets are observations with y_var == 0 (LatentOutputs.py:11-18)
+        const double yvar = a.infer ? 1.0 / a.noise_mean[r] : 0.0;
+        const double shape = a.noise_shape0[r] + 0.5 * (double)DY * n;
+        const double scale = a.noise_scale0[r] + 0.5 * (t3 - t4 + sm[DY] + sm[DY + 1] + sm[DY + 2] + yvar);
+        a.yvar[r] = yvar;
+        a.bias_prec[r] = bp;
+        a.bias_var[r] = 1.0 / bp;
+        a.noise_shape[r] = shape;
+        a.noise_scale[r] = scale;
+        a.noise_mean[r] = shape / scale;
+        a.noise_log_mean[r] = digamma(shape) - log(scale);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prediction and latent export (not on the sweep path): region found by binary search on offsets
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_region(const int64_t *off, int R, int64_t n) {
+    int lo = 0, hi = R;   // off[lo] <= n < off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= n)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+struct EvalLayer {
+    const int64_t *offsets;   // region offsets used to assign sample positions to regions
+    const double *inv2L, *rsqrtL, *A, *cm2, *bias, *bias_var;
+    int32_t R;
+};
+
+constexpr int kMaxLayers = 24;
+struct EvalArgs {
+    EvalLayer layer[kMaxLayers];
+    int32_t n_layers;
+    int32_t M;
+    int64_t n;
+    const double *x;
+    double *out_mean;   // (n, DY) or null
+    double *out_var;    // (n) or null
+    int32_t single_region;   // 1: every point uses region 0 of layer 0 (MRGP.py:726-755, 833-861)
+};
+
+// out_mean = sum_j (Phi_j A_j^T + b_j), out_var = sum_j (bias_var_j + sum_i phi_i^2 cm2_ji) over the
+// given layers (MRGP.py:782-803; Stats.py:126-157 when used to export the latent functions).
+template <int DY>
+__global__ void k_eval_layers(EvalArgs a) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= a.n) return;
+    const double x = a.x[n];
+    double mean[DY], var = 0.0;
+#pragma unroll
+    for (int d = 0; d < DY; ++d) mean[d] = 0.0;
+    for (int j = 0; j < a.n_layers; ++j) {
+        const EvalLayer &ly = a.layer[j];
+        const int r = a.single_region ? 0 : find_region(ly.offsets, ly.R, n);
+        double f1, c2;
+        basis_seed(x, ly.inv2L[r], ly.rsqrtL[r], f1, c2);
+        double fm = 0.0, f = f1, e[DY], v = 0.0;
+#pragma unroll
+        for (int d = 0; d < DY; ++d) e[d] = 0.0;
+        const double *A = ly.A + (size_t)r * a.M * DY;
+        const double *C = ly.cm2 + (size_t)r * a.M;
+        for (int i = 0; i < a.M; ++i) {
+#pragma unroll
+            for (int d = 0; d < DY; ++d) e[d] = fma(f, A[i * DY + d], e[d]);
+            v = fma(f * C[i], f, v);
+            const double fn = fma(c2, f, -fm);
+            fm = f;
+            f = fn;
+        }
+#pragma unroll
+        for (int d = 0; d < DY; ++d) mean[d] += ly.bias[(size_t)r * DY + d] + e[d];
+        var += ly.bias_var[r] + v;
+    }
+    if (a.out_mean)
+#pragma unroll
+        for (int d = 0; d < DY; ++d) a.out_mean[n * DY + d] = mean[d];
+    if (a.out_var) a.out_var[n] = var;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ELBO (MRGP.py:414-569), one block per layer.  prime == the shared prior for layer 0 and the CURRENT
+// shared posterior for layers > 0 (alias at MRGP.py:379).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_1024(double v, double *sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    v = warp_sum(v);
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (warp == 0) {
+        t = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;   // valid in warp 0
+}
+
+template <int DY>
+__global__ void __launch_bounds__(256) k_elbo(const RegionArgs *layers, double *out /* (J, 6) */) {
+    static_assert(DY == 2, "dy == 2 only");
+    __shared__ double sm[32];
+    const RegionArgs a = layers[blockIdx.x];
+    const int j = blockIdx.x, M = a.M, R = a.R;
+    const bool first = (j == 0);
+    const double *pB = first ? a.priorB : a.axB;
+    const double *pLogC = first ? a.priorLogC : a.axLogC;
+    const double *pShape = first ? a.priorShape : a.ardShape;
+    const double *pScale = first ? a.priorScale : a.ardScale;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const double n = (double)(a.offsets[r + 1] - a.offsets[r]);
+        const double *sb = a.sumsB + (size_t)r * (DY + 3);
+        double bb = 0.0, bs = 0.0, w0w0 = 0.0, ww0 = 0.0;
+        for (int d = 0; d < DY; ++d) {
+            const double b = a.bias_mean[(size_t)r * DY + d], b0 = a.bias_mean0[(size_t)r * DY + d];
+            bb += b * b;
+            bs += b * sb[d];
+            w0w0 += b0 * b0;
+            ww0 += b * b0;
+        }
+        // :535-569  sum |r - b|^2 = sum |r|^2 - 2 b . sum r + n |b|^2
+        const double mean_term = sb[DY] - 2.0 * bs + n * bb;
+        const double nlm = a.noise_log_mean[r], nm = a.noise_mean[r];
+        t0 += mean_term + sb[DY + 1] + sb[DY + 2] + a.bias_var[r] + a.yvar[r] * n + 0.5 * DY * (nlm - kLog2Pi) * n;
+        // :449-475
+        const double tau = a.bias_prec[r], tau0 = a.bias_prec0[r];
+        const double term1 = 1.0 / (tau * nm) + bb - 2.0 * ww0 + w0w0;
+        t4 += (0.5 * DY * (log(tau0) + nlm - kLog2Pi) + 0.5 * tau0 * nm * term1) - (0.5 * DY * (log(tau) + nlm - kLog2Pi) - 0.5);
+        // :426-447
+        const double c0 = a.noise_shape0[r], d0 = a.noise_scale0[r], c = a.noise_shape[r], d = a.noise_scale[r];
+        t5 += (c0 * log(d0) - lgamma(c0) + (c0 - 1.0) * nlm - d0 * nm) - (c * log(d) - lgamma(c) + (c - 1.0) * nlm - d * nm);
+    }
+    // :520-533
+    for (int t = threadIdx.x; t < R * M; t += blockDim.x) {
+        const int i = t % M;
+        t1 += (0.5 * a.ardLogMean[i] / a.S[t] - 0.5 * a.ardMean[i] * a.m2[t] / a.S[t]) - (0.5 * log(a.prec[t]) - 0.5);
+    }
+    // :499-518 (element-wise product inside the trace -> diagonal entries only), :477-497
+    for (int t = threadIdx.x; t < M * M; t += blockDim.x) {
+        const int i = t / M, k = t % M;
+        const double w = a.omega[t];
+        t2 += w * (-pLogC[k] + a.axCov[i * 4 + 0] * pB[k * 4 + 0] + a.axCov[i * 4 + 3] * pB[k * 4 + 3]);
+        t3 += w * (pShape[k] * log(pScale[k]) - lgamma(pShape[k]) + (pShape[k] - 1.0) * a.ardLogMean[i] - pScale[k] * a.ardMean[i]);
+    }
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        t2 -= -a.axLogC[i] + a.axCov[i * 4 + 0] * a.axB[i * 4 + 0] + a.axCov[i * 4 + 3] * a.axB[i * 4 + 3];
+        t3 -= a.ardShape[i] * log(a.ardScale[i]) - lgamma(a.ardShape[i]) + (a.ardShape[i] - 1.0) * a.ardLogMean[i] - a.ardScale[i] * a.ardMean[i];
+    }
+    double vals[6] = {t0, t1, t2, t3, t4, t5};
+    for (int q = 0; q < 6; ++q) {
+        const double s = block_sum_1024(vals[q], sm);
+        if (threadIdx.x == 0) out[j * 6 + q] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// initialisation (Priors.py non-informative; Posteriors.py:10-30; Stats.py:8-62, 355-369)
+// ------------------------------------------------------------------------------------------------
+template <int DY>
+__global__ void k_init_layer(RegionArgs a, double noise_var0, double ard_influence, double logc0, double rho0) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int M = a.M;
+    if (t < a.R) {
+        const int r = t;
+        a.noise_shape0[r] = kEps;
+        a.noise_scale0[r] = (kEps + 1.0) * noise_var0;
+        a.noise_shape[r] = kEps;
+        a.noise_scale[r] = (kEps + 1.0) * noise_var0;
+        a.noise_mean[r] = kEps / ((kEps + 1.0) * noise_var0);
+        a.noise_log_mean[r] = digamma(kEps) - log((kEps + 1.0) * noise_var0);
+        a.bias_prec0[r] = kEps;
+        a.bias_prec[r] = kEps;
+        a.bias_var[r] = 1.0 / kEps;
+        a.yvar[r] = 0.0;
+        for (int d = 0; d < DY; ++d) {
+            a.bias_mean0[(size_t)r * DY + d] = 0.0;
+            a.bias_mean[(size_t)r * DY + d] = 0.0;
+        }
+        for (int d = 0; d < DY + 3; ++d) a.sumsB[(size_t)r * (DY + 3) + d] = 0.0;
+    }
+    if (t < a.R * M) {
+        a.prec[t] = 1.0 / a.S[t];
+        a.zeta[t] = 0.0;
+        a.m2[t] = 0.0;
+        a.cm2[t] = 0.0;
+        for (int d = 0; d < DY; ++d) {
+            a.ytil[(size_t)t * DY + d] = 0.0;
+            a.A[(size_t)t * DY + d] = 0.0;
+            a.A_prev[(size_t)t * DY + d] = 0.0;
+        }
+        if (a.mode == 1) {
+            for (int q = 0; q < DY * DY; ++q) {
+                a.axB[(size_t)t * DY * DY + q] = 0.0;
+                a.axCov[(size_t)t * DY * DY + q] = 0.0;
+            }
+            for (int d = 0; d < DY; ++d) {
+                a.axKappa[(size_t)t * DY + d] = 0.0;
+                a.axRho[(size_t)t * DY + d] = rho0;
+            }
+            a.axLogC[t] = logc0;
+            a.ardShape[t] = kEps;
+            a.ardScale[t] = kEps / ard_influence;
+            a.ardMean[t] = kEps / (kEps / ard_influence);
+            a.ardLogMean[t] = digamma(kEps) - log(kEps / ard_influence);
+        }
+    }
+}
+
+template <int DY>
+__global__ void k_init_shared(RegionArgs a, double *priorB, double *priorLogC, double *priorShape, double *priorScale,
+                              double ard_influence, double logc0, double rho0) {
+    const int M = a.M;
+    for (int t = threadIdx.x; t < M; t += blockDim.x) {
+        for (int q = 0; q < DY * DY; ++q) {
+            priorB[t * DY * DY + q] = 0.0;
+            a.axB[t * DY * DY + q] = 0.0;
+            a.axCov[t * DY * DY + q] = 0.0;
+            a.primeB[t * DY * DY + q] = 0.0;
+        }
+        for (int d = 0; d < DY; ++d) {
+            a.axKappa[t * DY + d] = 0.0;
+            a.axRho[t * DY + d] = rho0;
+        }
+        priorLogC[t] = logc0;
+        a.axLogC[t] = logc0;
+        a.primeLogC[t] = logc0;
+        priorShape[t] = kEps;
+        priorScale[t] = kEps / ard_influence;
+        a.ardShape[t] = kEps;
+        a.ardScale[t] = kEps / ard_influence;
+        a.primeShape[t] = kEps;
+        a.primeScale[t] = kEps / ard_influence;
+        a.ardMean[t] = kEps / (kEps / ard_influence);
+        a.ardLogMean[t] = digamma(kEps) - log(kEps / ard_influence);
+    }
+    for (int t = threadIdx.x; t < M * M; t += blockDim.x) {
+        a.omega[t] = 1.0 / (double)M;
+        a.logOmegaHat[t] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// micro-benchmarks
+// ------------------------------------------------------------------------------------------------
+
+// Batched Cholesky (lower), one warp per n x n matrix (n <= 32): lane r owns row r; the pivot and the
+// scaled column are broadcast with warp shuffles.  Mirrors LAPACK potrf's info convention.
+__global__ void k_batched_cholesky(double *a, int n, int64_t batch, int32_t *info) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= batch) return;
+    double *A = a + w * (int64_t)n * n;
+    double row[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) row[c] = (lane < n && c < n && c <= lane) ? A[lane * n + c] : 0.0;
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        if (k < n) {
+            double piv = __shfl_sync(0xffffffffu, row[k], k);
+            if (!(piv > 0.0) && bad == 0) bad = k + 1;
+            const double rp = (bad == 0) ? 1.0 / sqrt(piv) : 0.0;
+            if (lane >= k) row[k] *= rp;   // column k of L
+#pragma unroll
+            for (int c = k + 1; c < 32; ++c) {
+                const double lck = __shfl_sync(0xffffffffu, row[k], c);   // L[c][k]
+                if (c < n && lane >= c) row[c] = fma(-row[k], lck, row[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+        if (lane < n && c < n && c <= lane) A[lane * n + c] = row[c];
+    if (lane == 0) info[w] = bad;
+}
+
+__global__ void k_fp64_probe(int64_t iters, double *sink) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double m = 0.999999999, c = 1e-9;
+    for (int64_t i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c);
+        a1 = fma(a1, m, c);
+        a2 = fma(a2, m, c);
+        a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c);
+        a5 = fma(a5, m, c);
+        a6 = fma(a6, m, c);
+        a7 = fma(a7, m, c);
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) sink[0] = s;
+}
+
+}  // namespace mrgp

@@ -1,0 +1,209 @@
+// Scalar math shared by the device kernels and the host test hooks (same source, compiled twice).
+// Every routine cites the reference code it replaces (paths under the reference's src/).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MRGP_HD __host__ __device__ __forceinline__
+#else
+#define MRGP_HD inline
+#endif
+
+namespace mrgp {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kLog2Pi = 1.8378770664093454835606594728112;
+constexpr double kEps = 1e-45;  // Priors.py:5
+
+// psi(x) for x > 0 (scipy.special.psi at Stats.py:36, 107, 366, 388): upward recurrence to x >= 10,
+// then the asymptotic series.  |rel err| ~ 1e-16 on the arguments the model produces (1e-45 ... ~N).
+MRGP_HD double digamma(double x) {
+    double acc = 0.0;
+    while (x < 10.0) {
+        acc -= 1.0 / x;
+        x += 1.0;
+    }
+    const double inv = 1.0 / x;
+    const double i2 = inv * inv;
+    const double series =
+        i2 * (1.0 / 12.0 -
+              i2 * (1.0 / 120.0 -
+                    i2 * (1.0 / 252.0 - i2 * (1.0 / 240.0 - i2 * (1.0 / 132.0 - i2 * (691.0 / 32760.0 - i2 * (1.0 / 12.0)))))));
+    return acc + (log(x) - 0.5 * inv - series);
+}
+
+// Matern spectral density S(sqrt(lambda)), KernelClass.py:80-90 exponentiated as :57-58, called from
+// MRGP.py:297-303 with s = sqrt(lambda).
+MRGP_HD double matern_spectral(double lambda, double nu, double l, double sf) {
+    const double s = sqrt(lambda);
+    const double log_arg = log(2.0 * nu) - 2.0 * log(l);
+    const double arg = exp(log_arg);
+    const double log_const = 0.5 * kLog2Pi + nu * log_arg;
+    const double log_gamma_term = lgamma(nu + 0.5) - lgamma(nu);
+    const double log_power_term = -(nu + 0.5) * log(arg + s * s);
+    return exp(log(sf) + log_const + log_gamma_term + log_power_term);
+}
+
+// np.spacing(x) for x >= 0 (SanityCheck.py:40).
+MRGP_HD double spacing(double x) {
+    union {
+        double d;
+        uint64_t u;
+    } v;
+    v.d = x;
+    v.u += 1;
+    return v.d - x;
+}
+
+// LAPACK potrf on a symmetric 2x2 [[a, b], [b, c]]: success iff both pivots are > 0
+// (numpy.linalg.cholesky at SanityCheck.py:59-65).
+MRGP_HD bool chol2_ok(double a, double b, double c) {
+    if (!(a > 0.0)) return false;
+    const double l21 = b / sqrt(a);
+    const double piv = c - l21 * l21;
+    return piv > 0.0;
+}
+
+// Symmetric 2x2 eigen-solve: l1 >= l2 and the projector P1 = v1 v1^T (p00, p01, p11).
+// Replaces numpy.linalg.eig on a symmetric input (CommonDensities.py:73-76); eigenvector signs are
+// irrelevant because only v v^T is used downstream (Stats.py:375-382).
+MRGP_HD void eig2(double a, double b, double c, double &l1, double &l2, double &p00, double &p01, double &p11) {
+    const double m = 0.5 * (a + c);
+    const double d = 0.5 * (a - c);
+    const double h = sqrt(d * d + b * b);
+    l1 = m + h;
+    l2 = m - h;
+    if (h > 0.0) {
+        const double ih = 0.5 / h;
+        p00 = 0.5 + d * ih;
+        p11 = 0.5 - d * ih;
+        p01 = b * ih;
+    } else {
+        p00 = 1.0;
+        p01 = 0.0;
+        p11 = 0.0;
+    }
+}
+
+// First-order Kume-Wood saddle-point approximation of log C(kappa) and its gradient for a real Bingham
+// distribution of dimension P (computeRealBinghamConstant.py:42-147).  The root of
+// 1/2 sum 1/(Lam_k - t) = 1 on [0.1 - P, 0.1 - 0.5] (:72-95, brentq in the reference) is found by Newton
+// from the right end of the bracket: the function is increasing and convex left of min(Lam) = 0.1 and
+// non-negative at 0.1 - 0.5, so the iterates decrease monotonically to the root.
+template <int P>
+MRGP_HD void saddle_point(const double *kappa, double &logc, double *rho) {
+    double lam[P];
+    double mn = -kappa[0];
+    for (int k = 1; k < P; ++k) mn = fmin(mn, -kappa[k]);
+    const double adjust = 0.1 - mn;
+    for (int k = 0; k < P; ++k) lam[k] = -kappa[k] + adjust;
+    double t = 0.1 - 0.5;
+    for (int it = 0; it < 60; ++it) {
+        double f = -1.0, fp = 0.0;
+        for (int k = 0; k < P; ++k) {
+            const double r = 1.0 / (lam[k] - t);
+            f += 0.5 * r;
+            fp += 0.5 * r * r;
+        }
+        const double step = f / fp;
+        const double tn = t - step;
+        if (!(fabs(step) > 1e-17 * fabs(t)) || tn >= t) {
+            t = (tn < t) ? tn : t;
+            break;
+        }
+        t = tn;
+    }
+    double k2 = 0.0, k3 = 0.0, sumlog = 0.0;
+    double r1[P];
+    for (int k = 0; k < P; ++k) {
+        r1[k] = 1.0 / (lam[k] - t);
+        k2 += r1[k] * r1[k];
+        k3 += r1[k] * r1[k] * r1[k];
+        sumlog += log(lam[k] - t);
+    }
+    k2 *= 0.5;
+    logc = 0.5 * (log(2.0) + (P - 1) * log(kPi) - log(k2) - sumlog) - t + adjust;
+    // gradient (:125-143)
+    double dk1dt = 0.0;
+    for (int k = 0; k < P; ++k) dk1dt += 0.5 * r1[k] * r1[k];
+    double dsumlogdt = 0.0;
+    for (int k = 0; k < P; ++k) dsumlogdt -= r1[k];
+    for (int k = 0; k < P; ++k) {
+        const double dk1dlam = -0.5 * r1[k] * r1[k];
+        const double dtdlam = -dk1dlam / dk1dt;
+        const double dk2dlam = -(r1[k] * r1[k] * r1[k]) + k3 * dtdlam;
+        const double dlogk2 = dk2dlam / k2;
+        const double dsl = r1[k] + dsumlogdt * dtdlam;
+        rho[k] = 0.5 * dlogk2 + 0.5 * dsl + dtdlam;
+    }
+}
+
+struct Bingham2 {
+    double b[3];      // guarded B: b00, b01, b11
+    double kappa[2];  // clamped at 0 (Posteriors.py:525-526)
+    double rho[2];
+    double logc;
+    double cov[3];    // axis_cov: c00, c01, c11
+    int n_chol;       // Cholesky factorisations attempted by the guard
+};
+
+// One Bingham axis update for dy == 2: PD guard (Posteriors.py:519-523 -> SanityCheck.py:16-65), eigen-
+// solve sorted descending (CommonDensities.py:73-76), saddle-point constant from the unclamped
+// eigenvalues (:77), axis covariance (Stats.py:375-382).
+MRGP_HD void bingham2(double a, double b, double c, Bingham2 &out) {
+    int n_chol = 1;
+    if (!chol2_ok(a, b, c)) {
+        // nearestPD: B = (A + A^T)/2 is A itself; H = V |Lambda| V^T; A2 = (B + H)/2 = V max(Lambda,0) V^T
+        const double fro = sqrt(a * a + 2.0 * b * b + c * c);
+        double l1, l2, p00, p01, p11;
+        eig2(a, b, c, l1, l2, p00, p01, p11);
+        const double m1 = l1 > 0.0 ? l1 : 0.0, m2 = l2 > 0.0 ? l2 : 0.0;
+        a = m1 * p00 + m2 * (1.0 - p00);
+        b = m1 * p01 - m2 * p01;
+        c = m1 * p11 + m2 * (1.0 - p11);
+        ++n_chol;
+        if (!chol2_ok(a, b, c)) {
+            const double sp = spacing(fro);
+            for (int k = 1; k <= 64; ++k) {
+                eig2(a, b, c, l1, l2, p00, p01, p11);
+                const double shift = -l2 * (double)(k * k) + sp;
+                a += shift;
+                c += shift;
+                ++n_chol;
+                if (chol2_ok(a, b, c)) break;
+            }
+        }
+    }
+    double l1, l2, p00, p01, p11;
+    eig2(a, b, c, l1, l2, p00, p01, p11);
+    const double kap[2] = {l1, l2};
+    saddle_point<2>(kap, out.logc, out.rho);
+    out.b[0] = a;
+    out.b[1] = b;
+    out.b[2] = c;
+    out.kappa[0] = l1 < 0.0 ? 0.0 : l1;
+    out.kappa[1] = l2 < 0.0 ? 0.0 : l2;
+    out.cov[0] = out.rho[0] * p00 + out.rho[1] * (1.0 - p00);
+    out.cov[1] = out.rho[0] * p01 - out.rho[1] * p01;
+    out.cov[2] = out.rho[0] * p11 + out.rho[1] * (1.0 - p11);
+    out.n_chol = n_chol;
+}
+
+// Basis angle: theta = pi (x + L)/(2L) = pi (u + 1/2), u = x / (2L)  (KernelClass.py:31-35), so
+// sin(theta) = cos(pi u) and cos(theta) = -sin(pi u).  Returns phi_1 = L^-1/2 sin(theta) and
+// c2 = 2 cos(theta); higher orders follow phi_{i+1} = c2 phi_i - phi_{i-1} with phi_0 = 0.
+MRGP_HD void basis_seed(double x, double inv2L, double rsqrtL, double &phi1, double &c2) {
+    double sp, cp;
+#if defined(__CUDA_ARCH__)
+    sincospi(x * inv2L, &sp, &cp);
+#else
+    const double u = x * inv2L;
+    sp = sin(kPi * u);
+    cp = cos(kPi * u);
+#endif
+    phi1 = rsqrtL * cp;
+    c2 = -2.0 * sp;
+}
+
+}  // namespace mrgp

@@ -1,0 +1,239 @@
+"""Parity of the CUDA path (through the drop-in API and the C ABI) with the golden fixtures produced by
+the unmodified reference and with the CPU oracle.  Tolerance (BASELINE.json north_star): relative 1e-6 in
+fp64, plus 1e-12 * max|ref| per array for exact zeros; index sets bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mrgp_oracle as O
+from parity import assert_state_close, mismatch
+import workloads
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+RTOL = 1e-6
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + '.npz'))
+
+
+def split(g, prefix):
+    return {k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)}
+
+
+def build(x, y, m, resolution, fi, **kw):
+    from cimrgp_b200 import IndexSetUniform, LaplacianEigenpairs, MaternKernel
+    from cimrgp_b200.MRGP import MultiResolutionGaussianProcess
+    return MultiResolutionGaussianProcess(
+        train_xy=[x, y], n_basis=m, index_set_obj=IndexSetUniform(x.shape[0], resolution, 2),
+        basis_function_obj=LaplacianEigenpairs(), spectral_density_obj=MaternKernel(nu=1, l=1, sf=1),
+        adaptive_inputs=False, standard_normalized_inputs=True, basis_interval_obj=None, interval_factor=1,
+        forced_independence=fi, **kw)
+
+
+def compare(state, ref, rtol=RTOL):
+    assert_state_close(state, ref, rtol, skip=('kappa',))
+    for key in ref:
+        if key.endswith('kappa'):
+            assert mismatch(state[key], ref[key], rtol, atol_scale=1e-12) is None, key
+
+
+CASES = [('c1_ci', False, {}), ('c1_fi', True, {}), ('n2000_ci', False, {}), ('n2000_fi', True, {}),
+         ('c2_ci', False, {}), ('c2_fi', True, {}), ('n600_ci_snr', False, dict(snr_ratio=10.))]
+
+
+@pytest.mark.parametrize('name,fi,kw', CASES)
+def test_sweeps_match_reference_goldens(name, fi, kw):
+    g = load(name)
+    x, y = g['x'], g['y']
+    m = build(x, y, int(g['meta.M']), int(g['meta.resolution']), fi, **kw)
+    compare(m._engine.state(), split(g, 'k0.'))
+    done = 0
+    for k in g['meta.checkpoints']:
+        m.fit(int(k) - done, None)
+        done = int(k)
+        compare(m._engine.state(), split(g, 'k%d.' % k))
+    if 'pred.x' in g.files:
+        from cimrgp_b200 import IndexSetUniform
+        xt = g['pred.x']
+        assert mismatch(m.get_predicted_mean(xt), g['pred.mean_global'], RTOL) is None
+        idx_t = IndexSetUniform(xt.shape[0], int(g['meta.resolution']), 2)
+        assert mismatch(m.get_predicted_mean(xt, index_set_obj=idx_t), g['pred.mean_indexed'], RTOL) is None
+        assert mismatch(m.get_central_moment2(xt), g['pred.var_global'], RTOL) is None
+
+
+def test_ci_upper_layers_are_exactly_inert():
+    """SURVEY.md §8c behavioural KAT: exact zeros, and indexed prediction == layer-0 prediction."""
+    from cimrgp_b200 import IndexSetUniform
+    x, y = workloads.workload1(4096)
+    m = build(x, y, 30, 5, False)
+    m.fit(4, None)
+    for j in range(1, 6):
+        st = m._engine.layer_state(j)
+        assert not np.any(st['A']) and not np.any(st['bias_mean']) and not np.any(st['ytil'])
+    xt = np.atleast_2d(np.linspace(1, 3, 5000)).T
+    a = m.get_predicted_mean(xt)
+    b = m.get_predicted_mean(xt, index_set_obj=IndexSetUniform(5000, 5, 2))
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('fi', [False, True])
+def test_elbo_and_oracle_mid_size(fi):
+    """N = 20000, 8 layers: three sweeps against the CPU oracle (fsolve vs the exact scaling: 1e-6)."""
+    x, y = workloads.workload1(20000)
+    offsets = O.uniform_offsets(20000, 7, 2)
+    ora = O.OracleMRGP(x, y, 30, offsets, mode='fi' if fi else 'ci')
+    m = build(x, y, 30, 7, fi)
+    for _ in range(3):
+        ora.sweep()
+    m.fit(3, None)
+    compare(m._engine.state(), ora.state())
+    if not fi:
+        total, per_layer, terms = ora.elbo()
+        got = m._engine.elbo()
+        assert mismatch(got, terms, RTOL) is None
+
+
+def test_elbo_matches_reference_golden():
+    g = load('c1_ci_elbo')
+    x, y = g['x'], g['y']
+    n_iter = g['lower_bound'].shape[0]
+    m = build(x, y, int(g['meta.M']), int(g['meta.resolution']), False)
+    m.fit(n_iter=n_iter, tol=1e-300, min_iter=n_iter)
+    assert mismatch(np.array(m.lower_bound_terms), g['terms'], RTOL) is None
+    assert mismatch(np.array(m.lower_bound_layer), g['lower_bound_layer'], RTOL) is None
+    assert mismatch(np.array(m.lower_bound), g['lower_bound'], RTOL) is None
+
+
+def test_graph_replay_equals_stepwise_phases_and_is_deterministic():
+    x, y = workloads.workload1(50000)
+    a = build(x, y, 30, 6, False)
+    b = build(x, y, 30, 6, False)
+    c = build(x, y, 30, 6, False)
+    a.fit(3, None)
+    c.fit(3, None)
+    for _ in range(3):
+        b._engine.sweep_stepwise()
+    b._engine.synchronize()
+    sa, sb, sc = a._engine.state(), b._engine.state(), c._engine.state()
+    for k in sa:
+        assert np.array_equal(sa[k], sc[k]), k          # same launch geometry -> bitwise reproducible
+        assert np.array_equal(sa[k], sb[k]), k          # graph replay == per-phase ABI calls
+
+
+def test_results_do_not_depend_on_grid_size():
+    x, y = workloads.workload1(30000)
+    a = build(x, y, 30, 6, True, n_ctas=148)
+    b = build(x, y, 30, 6, True, n_ctas=7)
+    a.fit(2, None)
+    b.fit(2, None)
+    compare(b._engine.state(), a._engine.state(), rtol=1e-9)
+
+
+def test_ragged_random_regions_against_oracle():
+    """IndexSetUniform(n_regions=...) random boundaries (IndexSetGenerator.py:67-92): ragged regions whose
+    boundaries do not nest across layers."""
+    from cimrgp_b200 import IndexSetUniform, LaplacianEigenpairs, MaternKernel
+    from cimrgp_b200.MRGP import MultiResolutionGaussianProcess
+    x, y = workloads.workload1(3000)
+    np.random.seed(5)
+    idx = IndexSetUniform(3000, 3, 2, n_regions=[1, 3, 4, 7], min_percentage_of_samples_per_region=0.1)
+    for fi in (False, True):
+        m = MultiResolutionGaussianProcess([x, y], 20, idx, LaplacianEigenpairs(), MaternKernel(2.5, 0.7, 1.3),
+                                           forced_independence=fi, interval_factor=[1.0, 1.1, 1.2, 1.3])
+        ora = O.OracleMRGP(x, y, 20, idx.offsets, mode='fi' if fi else 'ci', spectral=(2.5, 0.7, 1.3),
+                           interval_factor=[1.0, 1.1, 1.2, 1.3])
+        m.fit(2, None)
+        ora.sweep()
+        ora.sweep()
+        compare(m._engine.state(), ora.state())
+
+
+def test_full_size_properties():
+    """BASELINE config 4 (N = 1e6, 10 layers, 1023 regions): size-independent properties."""
+    from cimrgp_b200 import IndexSetUniform
+    n = 1000000
+    x, y = workloads.workload1(n)
+    m = build(x, y, 30, 9, False)
+    m.fit(3, None)
+    eng = m._engine
+    sh = eng.shared_state()
+    assert np.max(np.abs(sh['omega'].sum(0) - 1)) < 1e-11 and np.max(np.abs(sh['omega'].sum(1) - 1)) < 1e-11
+    tot = 0
+    for j in range(10):
+        st = eng.layer_state(j)
+        assert all(np.all(np.isfinite(v)) for v in st.values())
+        # noise shape counts the samples of the region: c = c0 + dy/2 * n  (Posteriors.py:136)
+        assert np.array_equal(st['noise_shape'], 1e-45 + 0.5 * 2 * np.diff(eng.offsets[j]).astype(np.float64))
+        assert np.allclose(st['bias_prec'], np.diff(eng.offsets[j]))
+        tot += st['A'].shape[0]
+        if j > 0:
+            assert not np.any(st['A']) and not np.any(st['bias_mean'])
+    assert tot == 1023
+    # layer 0 explains the signal: residual variance ~ noise level of the generator (0.1 * U(1,2))^2
+    st0 = eng.layer_state(0)
+    assert 50. < st0['noise_mean'][0] < 200.
+    xt = np.atleast_2d(np.linspace(1, 3, 100000)).T
+    pm = m.get_predicted_mean(xt)
+    truth = workloads.signal1(xt)[:, :, 0].T
+    assert np.sqrt(np.mean((pm - truth) ** 2)) < 0.2
+    assert np.array_equal(pm, m.get_predicted_mean(xt, index_set_obj=IndexSetUniform(100000, 9, 2)))
+    # fi at full size: every layer is active; phase-B sums are consistent with the bias posterior
+    f = build(x, y, 30, 9, True)
+    f.fit(2, None)
+    for j in (0, 5, 9):
+        st = f._engine.layer_state(j)
+        assert all(np.all(np.isfinite(v)) for v in st.values())
+        assert np.any(st['A'])
+    assert f._engine.cholesky_count() >= 2 * 1023 * 30
+
+
+def test_batched_cholesky_matches_lapack():
+    import ctypes as C
+    import torch
+    from cimrgp_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(0)
+    for n in (2, 5, 16, 32):
+        batch = 1000
+        a = rng.randn(batch, n, n + 3)
+        a = a @ np.swapaxes(a, 1, 2)
+        a[7] = -a[7]                                  # not PD: potrf info = 1
+        ref = np.linalg.cholesky(np.delete(a, 7, axis=0))
+        t = torch.as_tensor(a, device='cuda').contiguous()
+        info = torch.zeros(batch, dtype=torch.int32, device='cuda')
+        torch.cuda.synchronize()
+        assert lib.mrgp_batched_cholesky(None, C.c_void_p(t.data_ptr()), n, batch, C.c_void_p(info.data_ptr())) == 0
+        torch.cuda.synchronize()
+        got = np.tril(np.delete(t.cpu().numpy(), 7, axis=0))
+        info = info.cpu().numpy()
+        assert info[7] == 1 and not np.any(np.delete(info, 7))
+        assert np.max(np.abs(got - ref)) < 1e-11 * np.max(np.abs(ref))
+
+
+def test_constructor_errors_match_reference():
+    from cimrgp_b200 import IndexSetUniform, LaplacianEigenpairs, MaternKernel, BasisInterval
+    from cimrgp_b200.MRGP import MultiResolutionGaussianProcess as M
+    x, y = workloads.workload1(64)
+    idx = IndexSetUniform(64, 2, 2)
+    le, mk = LaplacianEigenpairs(), MaternKernel()
+    with pytest.raises(TypeError):
+        M([x, y], 30, idx, le, mk, axis_resolution_specific=True)                       # MRGP.py:50
+    with pytest.raises(ValueError):
+        M([x, y[:, :1]], 30, idx, le, mk)                                               # MRGP.py:66
+    with pytest.raises(ValueError):
+        M([x, y], 30, idx, le, [mk, mk])                                                # MRGP.py:75
+    with pytest.raises(ValueError):
+        M([x, y], 30, idx, le, mk, interval_factor=[1, 1])                              # MRGP.py:102
+    with pytest.raises(NotImplementedError):
+        M([x, y], 30, idx, le, mk, basis_interval_obj=BasisInterval())
+    m = M([x, y], 30, idx, le, mk)
+    with pytest.raises(ValueError):
+        m.get_predicted_mean(x, index_set_obj=IndexSetUniform(64, 3, 2))               # MRGP.py:758-760
+    with pytest.raises(ValueError):
+        m.get_predicted_mean(x, index_set_obj=IndexSetUniform(64, 2, 3))               # MRGP.py:762-764
+    assert len(m.posterior_obj) == 3 and m.stats_obj[2].scale_axis_mean[3].shape == (2, 30)
+    assert m.phi_x[1][1].shape == (32, 30) and m.stats_obj[1].latent_f_var[0].shape == (32, 1)
