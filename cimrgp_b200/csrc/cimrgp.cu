@@ -76,6 +76,8 @@ struct mrgp_handle {
     double *x_ws = nullptr, *y_ws = nullptr, *g = nullptr, *hvar = nullptr, *tmp_mean = nullptr, *tmp_var = nullptr;
     double *part = nullptr, *elbo_out = nullptr;
     RegionArgs *elbo_args = nullptr;
+    int64_t *off_staging = nullptr;
+    size_t off_total = 0;
     int32_t part_stride = 0, max_runs = 0;
     unsigned long long *chol_count = nullptr;
     cudaStream_t stream = nullptr, side = nullptr;
@@ -83,7 +85,7 @@ struct mrgp_handle {
     std::vector<cudaEvent_t> ev_fork, ev_join;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
-    int64_t launches = 0, launches_per_sweep = 0;
+    int64_t launches = 0, launches_per_sweep = 0, sweeps_done = 0;
     bool capturing = false;
     double fi_shape0_mix = 0.0, fi_scale0_mix = 0.0;
     std::string err;
@@ -107,6 +109,7 @@ int fail(mrgp_handle *h, int code, const char *fmt, ...) {
 #define CK(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) cudaGetLastError();                                                       \
         if (e_ != cudaSuccess) return fail(h, MRGP_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
@@ -201,6 +204,9 @@ size_t carve(mrgp_handle *h, char *base) {
     h->part = c.take<double>((size_t)h->max_runs * h->part_stride);
     h->elbo_out = c.take<double>((size_t)J * 6);
     h->elbo_args = c.take<RegionArgs>(J);
+    h->off_total = 0;
+    for (int j = 0; j < J; ++j) h->off_total += h->plan[j].R + 1;
+    h->off_staging = c.take<int64_t>(h->off_total);
     h->chol_count = c.take<unsigned long long>(1);
     for (int j = 0; j < J; ++j) {
         const LayerPlan &lp = h->plan[j];
@@ -497,7 +503,7 @@ int do_axis_update(mrgp_handle *h, int j, bool fork_omega) {
     const LayerPlan &lp = h->plan[j];
     {
         const int nv = M * DY, nval = (nv + 31) & ~31;
-        const int threads = std::max(reduce_threads(nv, max_region_runs(lp), 1024), ((M + 31) & ~31));
+        const int threads = std::max(reduce_threads(nv, max_region_runs(lp), 512), ((M + 31) & ~31));
         const int slices = threads / nval;
         const size_t smem = (size_t)(slices * nval + nv) * sizeof(double);
         k_reduce_scale<2><<<lp.R, threads, smem, h->stream>>>(a);
@@ -915,6 +921,7 @@ int mrgp_init_state(mrgp_handle *h, double noise_var0, double ard_prior_influenc
     CK(cudaMemsetAsync(h->g, 0, (size_t)h->cfg.n_samples * h->cfg.dy * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->hvar, 0, (size_t)h->cfg.n_samples * sizeof(double), h->stream));
     drop_graph(h);
+    h->sweeps_done = 0;
     h->state_init = true;
     return MRGP_OK;
 }
@@ -936,7 +943,7 @@ int mrgp_get_state(mrgp_handle *h, int32_t layer, int32_t field, double *dst_hos
         int rc = check_ready(h, layer, true);
         if (rc) return rc;
         const int64_t N = h->cfg.n_samples;
-        if (layer == 0) {
+        if (layer == 0 || h->sweeps_done == 0) {   // Stats.py:57-62: zeros until the first sweep
             CK(cudaMemsetAsync(h->tmp_mean, 0, (size_t)N * h->cfg.dy * sizeof(double), h->stream));
             CK(cudaMemsetAsync(h->tmp_var, 0, (size_t)N * sizeof(double), h->stream));
         } else {
@@ -986,6 +993,7 @@ int mrgp_phase_b(mrgp_handle *h, int32_t layer) {
 
 int mrgp_bias_noise(mrgp_handle *h, int32_t layer) {
     int rc = check_ready(h, layer, true);
+    if (!rc && layer == h->cfg.n_layers - 1) h->sweeps_done += 1;
     return rc ? rc : do_bias_noise(h, layer);
 }
 
@@ -1015,6 +1023,7 @@ int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
     }
     for (int it = 0; it < n_iter; ++it) CK(cudaGraphLaunch(h->graph_exec, h->stream));
     h->launches += h->launches_per_sweep * n_iter;
+    h->sweeps_done += n_iter;
     return MRGP_OK;
 }
 
@@ -1052,10 +1061,7 @@ int mrgp_predict_mean(mrgp_handle *h, const double *x_test_dev, int64_t n_test, 
     if (test_offsets) {
         if (n_test_layers < 1 || n_test_layers > h->cfg.n_layers)
             return fail(h, MRGP_EINVAL, "resolution in the test index set must be smaller or equal to that in the train set");
-        size_t total = 0;
-        for (int j = 0; j < n_test_layers; ++j) total += h->plan[j].R + 1;
-        if (total * sizeof(int64_t) > (size_t)h->cfg.n_samples * sizeof(double)) return fail(h, MRGP_ENOMEM, "test offsets do not fit the staging buffer");
-        staging = reinterpret_cast<int64_t *>(h->tmp_var);
+        staging = h->off_staging;
         size_t o = 0;
         for (int j = 0; j < n_test_layers; ++j) {
             const size_t cnt = h->plan[j].R + 1;
@@ -1201,7 +1207,12 @@ int mrgp_host_omega(const double *lw, int32_t m, double *omega_out, int32_t *ite
     for (int i = 0; i < m; ++i) {
         double mx = -INFINITY;
         for (int k = 0; k < m; ++k) mx = std::max(mx, lw[i * m + k]);
-        for (int k = 0; k < m; ++k) K[i * m + k] = std::exp(lw[i * m + k] - mx);
+        for (int k = 0; k < m; ++k) K[i * m + k] = lw[i * m + k] - mx;
+    }
+    for (int k = 0; k < m; ++k) {
+        double mx = -INFINITY;
+        for (int i = 0; i < m; ++i) mx = std::max(mx, K[i * m + k]);
+        for (int i = 0; i < m; ++i) K[i * m + k] = std::exp(K[i * m + k] - mx);
     }
     int it = 0;
     for (; it < 5000; ++it) {

@@ -466,7 +466,7 @@ __global__ void k_reduce_d(RegionArgs a) {
 // per 128 threads; for regions with many runs (coarse layers) the kernel is launched with 1024 threads
 // so that 8+ slices share the run loop.
 template <int DY>
-__global__ void k_reduce_scale(RegionArgs a) {
+__global__ void __launch_bounds__(512) k_reduce_scale(RegionArgs a) {
     extern __shared__ double sm[];   // [slices][NV] + ytil[NV]
     const int r = blockIdx.x;
     const int M = a.M, NV = M * DY;
@@ -684,11 +684,20 @@ __global__ void __launch_bounds__(1024) k_omega(RegionArgs a, int max_iter, doub
     const int M = a.M;
     double *K = sm, *u = K + M * M, *vv = u + M, *flag = vv + M;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // shift by the row maxima, then by the column maxima of the result: every row and every column
+    // of K then holds an entry equal to 1 and nothing overflows or underflows to an empty line
     for (int i = warp; i < M; i += 32) {
         double mx = -INFINITY;
         for (int k = lane; k < M; k += 32) mx = fmax(mx, a.logOmegaHat[i * M + k]);
         mx = warp_max(mx);
-        for (int k = lane; k < M; k += 32) K[i * M + k] = exp(a.logOmegaHat[i * M + k] - mx);
+        for (int k = lane; k < M; k += 32) K[i * M + k] = a.logOmegaHat[i * M + k] - mx;
+    }
+    __syncthreads();
+    for (int k = warp; k < M; k += 32) {
+        double mx = -INFINITY;
+        for (int i = lane; i < M; i += 32) mx = fmax(mx, K[i * M + k]);
+        mx = warp_max(mx);
+        for (int i = lane; i < M; i += 32) K[i * M + k] = exp(K[i * M + k] - mx);
     }
     for (int t = threadIdx.x; t < M; t += blockDim.x) {
         u[t] = 1.0;
