@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Benchmark of the ciMRGP VI hot path (BASELINE.json: VI iterations/sec at N = 1e6, 10 resolutions).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" is one full variational sweep (`_fit()`, MRGP.py:571-652) over all 10 layers of the config-4
+workload (N = 1e6 samples, dx = 1, dy = 2, M = 30, 1023 regions, ci mode, fp64, static basis intervals).
+Prints ONE JSON line (see the keys below).  Timing: CUDA events on the engine's stream around every step,
+L2 flushed (256 MB write) between steps, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+
+N_SAMPLES = 1000000
+N_LAYERS = 10
+N_BASIS = 30
+DY = 2
+WORKLOAD = 'config4: synthetic 1-D nonstationary signal (script-1 f, seed 10), N=1e6, dx=1, dy=2, M=30, ' \
+           '10 resolutions (1023 regions), ciMRGP, fp64, static basis intervals'
+# algorithmic HBM bytes per sample-layer: phase A 8(dx+2dy) = 40, phase B 8(dx+2dy+1) + 8(dy+1) = 72
+BYTES_SWEEP_PER_SAMPLE_LAYER = 112
+
+
+def peak_hbm():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 8 and r[4 + k] == 'Active' for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def make_model(n, device, n_ctas=0):
+    import workloads
+    from cimrgp_b200 import IndexSetUniform, LaplacianEigenpairs, MaternKernel
+    from cimrgp_b200.MRGP import MultiResolutionGaussianProcess
+    x, y = workloads.workload1(n)
+    m = MultiResolutionGaussianProcess([x, y], N_BASIS, IndexSetUniform(n, N_LAYERS - 1, 2), LaplacianEigenpairs(),
+                                       MaternKernel(nu=1, l=1, sf=1), forced_independence=False, device=device,
+                                       n_ctas=n_ctas)
+    return m
+
+
+def oracle_sample(n_sample, sweeps):
+    """CPU oracle (NumPy port of the reference) on a bounded sample of the workload: the same signal,
+    layers and basis at n_sample samples.  Returns seconds per sweep and the fixed (N-independent) part
+    spent in the permutation-weight solver."""
+    import workloads
+    from oracle import mrgp_oracle as O
+    x, y = workloads.workload1(n_sample)
+    m = O.OracleMRGP(x, y, N_BASIS, O.uniform_offsets(n_sample, N_LAYERS - 1, 2), mode='ci')
+    times = []
+    for _ in range(sweeps):
+        t0 = time.perf_counter()
+        m.sweep()
+        times.append(time.perf_counter() - t0)
+    return times, m.t_omega / sweeps
+
+
+def scaled_rate(t_step, t_fixed, n_sample):
+    """it/s on the full N from a step on n_sample samples: streaming part scales linearly in N, the
+    permutation-weight solve does not depend on N."""
+    return 1.0 / (t_fixed + (t_step - t_fixed) * (float(N_SAMPLES) / n_sample))
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (its NumPy port, oracle/; the
+    reference itself is Python and does not exist on the GPU box) on the host cores."""
+    if rank != 0:
+        return
+    budget = 150.0
+    per_step = budget / max(1, args.steps + args.warmup)
+    n_sample = int(min(N_SAMPLES, max(20000, (per_step - 1.5) / 41.5e-6)))
+    n_sample = (n_sample // 1024) * 1024
+    times, t_fixed = oracle_sample(n_sample, args.steps + args.warmup)
+    t_step = float(np.mean(times[args.warmup:]))
+    value = scaled_rate(t_step, t_fixed, n_sample)
+    sample = '%d steps of one oracle sweep on N=%d samples (same 10 layers, M=30); scaled to N=1e6 as ' \
+             '1/(t_omega + (t_step - t_omega) * 1e6/N), t_step=%.2fs, t_omega=%.2fs' % (args.steps, n_sample, t_step, t_fixed)
+    line = {
+        'impl': 'reference', 'metric': 'ciMRGP VI iters/sec at N=1e6, R=10', 'value': value, 'unit': 'it/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / value,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD},
+        'cpu_baseline': {'value': value, 'unit': 'it/s', 'cores': 1, 'kind': 'port', 'sample': sample,
+                         'host_cores': os.cpu_count()},
+        'e2e': {'value': value, 'unit': 'it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def time_phase(eng, fn, j, torch, reps):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = []
+    for _ in range(reps):
+        ev0.record(eng.stream)
+        fn(j)
+        ev1.record(eng.stream)
+        ev1.synchronize()
+        out.append(ev0.elapsed_time(ev1))
+    return out
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        raise SystemExit('multi-GPU sharding is not wired into bench.py yet')
+    torch.cuda.set_device(local_rank)
+    m = make_model(N_SAMPLES, local_rank, args.ctas)
+    eng = m._engine
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+    peak, peak_src = peak_hbm()
+
+    for _ in range(max(args.warmup, 3)):
+        eng.sweep(1)
+    eng.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- device-resident timing: K sweeps, L2 flushed between steps ------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = eng.launch_count()
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ev[k][0].record(eng.stream)
+        eng.sweep(1)
+        ev[k][1].record(eng.stream)
+    torch.cuda.synchronize()
+    launches = eng.launch_count() - l0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_s = sum(step_ms) / 1e3
+    value = args.steps / total_s
+
+    # ---- end to end through the public API: pinned host -> device, sweep, ELBO terms back ----------
+    e2e = None
+    if not args.no_e2e:
+        e2e_ms = []
+        for k in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(eng.stream)
+            eng.copy_in_from_pinned()          # H2D of x (N,1) and y (N,2) from pinned memory
+            m.fit(n_iter=1, tol=1e-300, min_iter=1)    # one sweep + the six ELBO terms per layer, read back
+            b.record(eng.stream)
+            b.synchronize()
+            e2e_ms.append(a.elapsed_time(b))
+        e2e = {'value': args.steps / (sum(e2e_ms) / 1e3), 'unit': 'it/s',
+               'h2d_bytes_per_step': N_SAMPLES * (1 + DY) * 8, 'd2h_bytes_per_step': N_LAYERS * 6 * 8,
+               'ms_per_step': float(np.mean(e2e_ms)), 'lower_bound_layer0': m.lower_bound_layer[0][-1]}
+    clocks = sampler.stop()
+
+    # ---- per-kernel timing for the roofline (CUDA events around single launches on the engine stream) --
+    reps = 3
+    t_a = [time_phase(eng, eng.phase_a, j, torch, reps) for j in range(N_LAYERS)]
+    t_mid = [time_phase(eng, eng.axis_update, j, torch, reps) for j in range(N_LAYERS)]
+    t_b = [time_phase(eng, eng.phase_b, j, torch, reps) for j in range(N_LAYERS)]
+    t_post = [time_phase(eng, eng.bias_noise, j, torch, reps) for j in range(N_LAYERS)]
+    med = lambda rows: [float(np.median(r)) for r in rows]
+    ta, tm, tb, tp = med(t_a), med(t_mid), med(t_b), med(t_post)
+    # dominant kernel: phase B with inferred targets, latent input and propagation (layers 1 .. J-2)
+    dom = tb[1:N_LAYERS - 1]
+    dom_ms = float(np.mean(dom))
+    # bytes one launch has to move: x (8) + latent mean (16) + latent var (8) read, latent mean/var (24)
+    # written per sample; y is not read when the targets are inferred (SURVEY.md counts 72 with y)
+    dom_bytes = 56 * N_SAMPLES
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'k_phase_b<2,30,infer,latent,propagate>', 'achieved': achieved,
+                'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'bytes_per_launch': dom_bytes, 'ms_per_launch': dom_ms,
+                'sweep_algorithmic_gbs': BYTES_SWEEP_PER_SAMPLE_LAYER * N_SAMPLES * N_LAYERS / (total_s / args.steps) / 1e9,
+                'kernel_ms': {'phase_a': ta, 'axis_update': tm, 'phase_b': tb, 'bias_noise': tp}}
+    # FP64 pipe: measured DFMA peak next to the FMA count of the dominant kernel (7 per basis function
+    # and sample: recurrence 1, Phi A_new 2, Phi A_old 2, phi^2 cm2 2; + ~40 for sincospi and the tail)
+    import ctypes as C
+    sink = torch.zeros(8, dtype=torch.float64, device='cuda')
+    ms = C.c_float()
+    iters = 200000
+    torch.cuda.synchronize()
+    eng.lib.mrgp_fp64_probe(None, iters, C.c_void_p(sink.data_ptr()), C.byref(ms))
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    fp64_peak = sms * 4 * 256 * iters * 8 * 2 / (ms.value * 1e-3) / 1e12
+    dom_flops = (7 * N_BASIS + 40) * 2 * N_SAMPLES
+    roofline['fp64'] = {'peak_tflops_measured': fp64_peak, 'achieved_tflops': dom_flops / (dom_ms * 1e-3) / 1e12,
+                        'frac': dom_flops / (dom_ms * 1e-3) / 1e12 / fp64_peak}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        n_sample = 200000
+        times, t_fixed = oracle_sample(n_sample, 1)
+        cpu_value = scaled_rate(times[0], t_fixed, n_sample)
+        cpu = {'value': cpu_value, 'unit': 'it/s', 'cores': 1, 'kind': 'port', 'host_cores': os.cpu_count(),
+               'sample': 'one oracle sweep (NumPy port of MRGP._fit) on N=%d of the same signal, 10 layers, M=30: '
+                         '%.1fs, of which %.1fs in the N-independent fsolve; scaled to N=1e6 as '
+                         '1/(t_omega + (t - t_omega) * 5)' % (n_sample, times[0], t_fixed)}
+
+    line = {
+        'metric': 'ciMRGP VI iters/sec at N=1e6, R=10', 'value': value, 'unit': 'it/s', 'n_gpus': 1,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * total_s / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'l2': 'flushed between timed steps (256 MB write)',
+                   'n_ctas': eng.lib and args.ctas or 'one persistent CTA per SM'},
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
+        'omega_iters_last_sweep': [int(v) for v in eng.get(-1, 51, (N_LAYERS,))],
+        'batched_cholesky': {'count_total': eng.cholesky_count(), 'n': DY,
+                             'note': 'dy x dy PD guard inside k_axis_shared; < 1% of a sweep'},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--ctas', type=int, default=0)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -54,7 +54,7 @@ struct LayerDev {
 struct SharedDev {
     double *axB = nullptr, *axKappa = nullptr, *axRho = nullptr, *axLogC = nullptr, *axCov = nullptr;
     double *ardShape = nullptr, *ardScale = nullptr, *ardMean = nullptr, *ardLogMean = nullptr;
-    double *omega = nullptr, *logOmegaHat = nullptr;
+    double *omega = nullptr, *logOmegaHat = nullptr, *omegaIters = nullptr, *ardPartial = nullptr;
     double *primeB = nullptr, *primeLogC = nullptr, *primeShape = nullptr, *primeScale = nullptr;
     double *priorB = nullptr, *priorLogC = nullptr, *priorShape = nullptr, *priorScale = nullptr;
 };
@@ -80,6 +80,7 @@ struct mrgp_handle {
     size_t off_total = 0;
     int32_t part_stride = 0, max_runs = 0;
     unsigned long long *chol_count = nullptr;
+    unsigned int *done_counter = nullptr;
     cudaStream_t stream = nullptr, side = nullptr;
     bool own_stream = false;
     std::vector<cudaEvent_t> ev_fork, ev_join;
@@ -208,6 +209,7 @@ size_t carve(mrgp_handle *h, char *base) {
     for (int j = 0; j < J; ++j) h->off_total += h->plan[j].R + 1;
     h->off_staging = c.take<int64_t>(h->off_total);
     h->chol_count = c.take<unsigned long long>(1);
+    h->done_counter = c.take<unsigned int>(1);
     for (int j = 0; j < J; ++j) {
         const LayerPlan &lp = h->plan[j];
         LayerDev &d = h->dev[j];
@@ -267,6 +269,8 @@ size_t carve(mrgp_handle *h, char *base) {
     s.ardLogMean = c.take<double>(M);
     s.omega = c.take<double>((size_t)M * M);
     s.logOmegaHat = c.take<double>((size_t)M * M);
+    s.omegaIters = c.take<double>(kMaxLayers);
+    s.ardPartial = c.take<double>((size_t)8 * M);
     s.primeB = c.take<double>((size_t)M * DY * DY);
     s.primeLogC = c.take<double>(M);
     s.primeShape = c.take<double>(M);
@@ -298,6 +302,27 @@ StreamArgs stream_args(mrgp_handle *h, int j) {
     a.pbias_var = j > 0 ? h->dev[j - 1].bias_var : nullptr;
     a.part = h->part;
     a.part_stride = h->part_stride;
+    a.n_samples = h->cfg.n_samples;
+    a.cta_quantum = h->cta_quantum;
+    a.done_counter = h->done_counter;
+    a.region_run = d.region_run;
+    a.offsets = d.offsets;
+    a.R = h->plan[j].R;
+    a.infer = (h->cfg.mode == MRGP_MODE_CI && j > 0) ? 1 : 0;
+    a.fuse_tail = 0;
+    a.bias_prec0 = d.bias_prec0;
+    a.bias_mean0 = d.bias_mean0;
+    a.noise_shape0 = d.noise_shape0;
+    a.noise_scale0 = d.noise_scale0;
+    a.bias_mean_out = d.bias_mean;
+    a.bias_prec = d.bias_prec;
+    a.bias_var = d.bias_var;
+    a.noise_shape = d.noise_shape;
+    a.noise_scale = d.noise_scale;
+    a.noise_mean = d.noise_mean;
+    a.noise_log_mean = d.noise_log_mean;
+    a.yvar = d.yvar;
+    a.sumsB = d.sumsB;
     return a;
 }
 
@@ -366,6 +391,8 @@ RegionArgs region_args(mrgp_handle *h, int j) {
     }
     a.omega = s.omega;
     a.logOmegaHat = s.logOmegaHat;
+    a.omegaIters = s.omegaIters;
+    a.ardPartial = s.ardPartial;
     a.primeB = s.primeB;
     a.primeLogC = s.primeLogC;
     a.primeShape = s.primeShape;
@@ -398,11 +425,12 @@ template <int M>
 cudaError_t launch_phase_a(mrgp_handle *h, const StreamArgs &a, bool infer, bool latent) {
     constexpr int DY = 2;
     dim3 grid(h->n_ctas), block(kThreads);
-#define LA(I, L)                                                                \
-    {                                                                           \
-        cudaError_t e = set_smem(k_phase_a<DY, M, I, L>, kRedSmemBytes);        \
-        if (e != cudaSuccess) return e;                                         \
-        k_phase_a<DY, M, I, L><<<grid, block, kRedSmemBytes, h->stream>>>(a);   \
+#define LA(I, L)                                                                                               \
+    {                                                                                                          \
+        const size_t smem = (size_t)(kStages * TileLayout<DY, !(I), (L), false>::kDoubles + kRedSmemDoubles) * sizeof(double); \
+        cudaError_t e = set_smem(k_phase_a<DY, M, I, L>, smem);                                                \
+        if (e != cudaSuccess) return e;                                                                        \
+        k_phase_a<DY, M, I, L><<<grid, block, smem, h->stream>>>(a);                                           \
     }
     if (infer)
         LA(true, true)
@@ -417,23 +445,29 @@ cudaError_t launch_phase_a(mrgp_handle *h, const StreamArgs &a, bool infer, bool
 template <int M>
 cudaError_t launch_phase_b(mrgp_handle *h, const StreamArgs &a, bool infer, bool latent, bool prop) {
     constexpr int DY = 2;
-    dim3 grid(h->n_ctas), block(kThreads);
-#define LB(I, L, P) k_phase_b<DY, M, I, L, P><<<grid, block, 0, h->stream>>>(a)
+    dim3 grid(h->n_ctas), block(kThreadsB);
+#define LB(I, L, P)                                                                                         \
+    {                                                                                                       \
+        const size_t smem = (size_t)(kStages * TileLayout<DY, !(I), (L), (L)>::kDoubles) * sizeof(double);  \
+        cudaError_t e = set_smem(k_phase_b<DY, M, I, L, P>, smem);                                          \
+        if (e != cudaSuccess) return e;                                                                     \
+        k_phase_b<DY, M, I, L, P><<<grid, block, smem, h->stream>>>(a);                                     \
+    }
     if (infer) {
         if (prop)
-            LB(true, true, true);
+            LB(true, true, true)
         else
-            LB(true, true, false);
+            LB(true, true, false)
     } else if (latent) {
         if (prop)
-            LB(false, true, true);
+            LB(false, true, true)
         else
-            LB(false, true, false);
+            LB(false, true, false)
     } else {
         if (prop)
-            LB(false, false, true);
+            LB(false, false, true)
         else
-            LB(false, false, false);
+            LB(false, false, false)
     }
 #undef LB
     return cudaGetLastError();
@@ -496,9 +530,12 @@ int max_region_runs(const LayerPlan &lp) {
     return m;
 }
 
+int do_mid_ci(mrgp_handle *h, int j, bool fork_omega);
+
 int do_axis_update(mrgp_handle *h, int j, bool fork_omega) {
     const bool fi = h->cfg.mode == MRGP_MODE_FI;
     const int M = h->cfg.n_basis, DY = h->cfg.dy;
+    if (!fi) return do_mid_ci(h, j, fork_omega);
     RegionArgs a = region_args(h, j);
     const LayerPlan &lp = h->plan[j];
     {
@@ -510,29 +547,41 @@ int do_axis_update(mrgp_handle *h, int j, bool fork_omega) {
         CK(cudaGetLastError());
         count(h);
     }
-    if (fi) return MRGP_OK;
+    return MRGP_OK;
+}
+
+int do_mid_ci(mrgp_handle *h, int j, bool fork_omega) {
+    const int M = h->cfg.n_basis;
+    RegionArgs a = region_args(h, j);
+    const LayerPlan &lp = h->plan[j];
     if (fork_omega && j > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_join[j - 1], 0));
+    int n_partials = 1;
     {
-        const int nv = M * 3, nval = (nv + 31) & ~31;
-        const int slices = 1024 / nval;
-        const size_t smem = (size_t)(slices * nval + nv) * sizeof(double);
-        k_axis_shared<2><<<1, 1024, smem, h->stream>>>(a);
-        CK(cudaGetLastError());
+        const int items = lp.R * M;
+        int nc = std::min(8, std::max(1, (items + kMidThreads - 1) / kMidThreads));
+        nc = std::min(nc, lp.R);
+        int lpi = 1;
+        const int mr = max_region_runs(lp);
+        while (lpi < 32 && lpi * 2 * items <= nc * kMidThreads && lpi < mr) lpi *= 2;
+        const int rpc = (lp.R + nc - 1) / nc;
+        nc = (lp.R + rpc - 1) / rpc;
+        const size_t smem = mid_smem_doubles(M) * sizeof(double);
+        CK(set_smem(k_mid_ci<2>, smem));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(nc);
+        cfg.blockDim = dim3(kMidThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = nc;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_mid_ci<2>, a, lpi, rpc));
         count(h);
-    }
-    {
-        const int total = lp.R * M;
-        k_scale_stats<2><<<(total + 127) / 128, 128, 0, h->stream>>>(a);
-        CK(cudaGetLastError());
-        count(h);
-    }
-    {
-        const int nval = (M + 31) & ~31;
-        const int slices = 1024 / nval;
-        const size_t smem = (size_t)(slices * nval + 2 * M) * sizeof(double);
-        k_ard<2><<<1, 1024, smem, h->stream>>>(a);
-        CK(cudaGetLastError());
-        count(h);
+        n_partials = nc;
     }
     {
         cudaStream_t st = h->stream;
@@ -541,8 +590,8 @@ int do_axis_update(mrgp_handle *h, int j, bool fork_omega) {
             CK(cudaStreamWaitEvent(h->side, h->ev_fork[j], 0));
             st = h->side;
         }
-        const size_t smem = (size_t)(M * M + 2 * M + 1) * sizeof(double);
-        k_omega<<<1, 1024, smem, st>>>(a, 5000, 1e-13);
+        const size_t smem = omega_smem_doubles(M) * sizeof(double);
+        k_omega<<<1, kOmegaThreads, smem, st>>>(a, n_partials);
         CK(cudaGetLastError());
         count(h);
         if (fork_omega) CK(cudaEventRecord(h->ev_join[j], h->side));
@@ -550,10 +599,11 @@ int do_axis_update(mrgp_handle *h, int j, bool fork_omega) {
     return MRGP_OK;
 }
 
-int do_phase_b(mrgp_handle *h, int j) {
+int do_phase_b(mrgp_handle *h, int j, bool fuse_tail) {
     const bool fi = h->cfg.mode == MRGP_MODE_FI;
     const bool infer = !fi && j > 0, latent = j > 0, prop = j + 1 < h->cfg.n_layers;
     StreamArgs a = stream_args(h, j);
+    a.fuse_tail = fuse_tail ? 1 : 0;
     cudaError_t e = cudaErrorInvalidValue;
     DISPATCH_M(h->cfg.n_basis, e = launch_phase_b<MM>(h, a, infer, latent, prop));
     CK(e);
@@ -562,8 +612,8 @@ int do_phase_b(mrgp_handle *h, int j) {
 }
 
 int do_bias_noise(mrgp_handle *h, int j) {
-    RegionArgs a = region_args(h, j);
-    k_bias_noise<2><<<h->plan[j].R, 128, 0, h->stream>>>(a);
+    StreamArgs a = stream_args(h, j);
+    k_bias_noise<2><<<1, kThreadsB, 0, h->stream>>>(a);
     CK(cudaGetLastError());
     count(h);
     return MRGP_OK;
@@ -576,8 +626,7 @@ int sweep_once(mrgp_handle *h, bool fork_omega) {
     for (int j = 0; j < J; ++j) {
         if ((rc = do_phase_a(h, j))) return rc;
         if ((rc = do_axis_update(h, j, fork_omega && ci))) return rc;
-        if ((rc = do_phase_b(h, j))) return rc;
-        if ((rc = do_bias_noise(h, j))) return rc;
+        if ((rc = do_phase_b(h, j, true))) return rc;   // bias / noise update fused into the kernel tail
     }
     if (fork_omega && ci) CK(cudaStreamWaitEvent(h->stream, h->ev_join[J - 1], 0));
     return MRGP_OK;
@@ -607,6 +656,7 @@ FieldRef field_ref(mrgp_handle *h, int layer, int field) {
             case MRGP_F_ARD_LOG_MEAN: f = {s.ardLogMean, M}; break;
             case MRGP_F_OMEGA: f = {s.omega, (int64_t)M * M}; break;
             case MRGP_F_LOG_OMEGA_HAT: f = {s.logOmegaHat, (int64_t)M * M}; break;
+            case MRGP_F_OMEGA_ITERS: f = {s.omegaIters, h->cfg.n_layers}; break;
             default: break;
         }
         return f;
@@ -801,6 +851,7 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
         CK(cudaMemcpyAsync(d.offsets, lp.offsets.data(), lp.offsets.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     }
     CK(cudaMemsetAsync(h->chol_count, 0, sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(h->done_counter, 0, sizeof(unsigned int), h->stream));
     CK(cudaMemsetAsync(h->g, 0, (size_t)h->cfg.n_samples * h->cfg.dy * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->hvar, 0, (size_t)h->cfg.n_samples * sizeof(double), h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -821,7 +872,7 @@ int mrgp_set_stream(mrgp_handle *h, void *cuda_stream) {
 int mrgp_set_data(mrgp_handle *h, const double *x_dev, const double *y_dev) {
     if (!h || !x_dev || !y_dev) return fail(h, MRGP_EINVAL, "null argument");
     if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
-    if (((uintptr_t)y_dev & 15) != 0 || ((uintptr_t)x_dev & 7) != 0) return fail(h, MRGP_EINVAL, "x must be 8-byte and y 16-byte aligned");
+    if (((uintptr_t)y_dev & 15) != 0 || ((uintptr_t)x_dev & 15) != 0) return fail(h, MRGP_EINVAL, "x and y must be 16-byte aligned (bulk copies)");
     if (h->x != x_dev || h->y != y_dev) drop_graph(h);
     h->x = x_dev;
     h->y = y_dev;
@@ -988,7 +1039,7 @@ int mrgp_axis_update(mrgp_handle *h, int32_t layer) {
 
 int mrgp_phase_b(mrgp_handle *h, int32_t layer) {
     int rc = check_ready(h, layer, true);
-    return rc ? rc : do_phase_b(h, layer);
+    return rc ? rc : do_phase_b(h, layer, false);
 }
 
 int mrgp_bias_noise(mrgp_handle *h, int32_t layer) {
@@ -1202,38 +1253,10 @@ void mrgp_host_basis(double x, double L, int32_t n_basis, double *phi_out) {
 }
 
 int mrgp_host_omega(const double *lw, int32_t m, double *omega_out, int32_t *iters_out) {
-    // serial statement of k_omega (same iteration, same stopping rule)
-    std::vector<double> K((size_t)m * m), u(m, 1.0), v(m, 1.0);
-    for (int i = 0; i < m; ++i) {
-        double mx = -INFINITY;
-        for (int k = 0; k < m; ++k) mx = std::max(mx, lw[i * m + k]);
-        for (int k = 0; k < m; ++k) K[i * m + k] = lw[i * m + k] - mx;
-    }
-    for (int k = 0; k < m; ++k) {
-        double mx = -INFINITY;
-        for (int i = 0; i < m; ++i) mx = std::max(mx, K[i * m + k]);
-        for (int i = 0; i < m; ++i) K[i * m + k] = std::exp(K[i * m + k] - mx);
-    }
-    int it = 0;
-    for (; it < 5000; ++it) {
-        bool bad = false;
-        for (int i = 0; i < m; ++i) {
-            double s = 0.0;
-            for (int k = 0; k < m; ++k) s += K[i * m + k] * v[k];
-            if (std::fabs(u[i] * s - 1.0) > 1e-13) bad = true;
-            u[i] = 1.0 / s;
-        }
-        const bool done = it > 0 && !bad;
-        for (int k = 0; k < m; ++k) {
-            double s = 0.0;
-            for (int i = 0; i < m; ++i) s += K[i * m + k] * u[i];
-            v[k] = 1.0 / s;
-        }
-        if (done) break;
-    }
-    for (int i = 0; i < m; ++i)
-        for (int k = 0; k < m; ++k) omega_out[i * m + k] = u[i] * K[i * m + k] * v[k];
-    if (iters_out) *iters_out = it + 1;
+    std::vector<double> w((size_t)3 * m * m + 4 * m);
+    double *K = w.data(), *P = K + m * m, *S = P + m * m, *v = S + m * m, *c = v + m, *rhs = c + m, *dinv = rhs + m;
+    const int it = omega_solve_serial(lw, m, omega_out, K, P, S, v, c, rhs, dinv);
+    if (iters_out) *iters_out = it;
     return MRGP_OK;
 }
 

@@ -9,10 +9,12 @@
 // inside the CTA range) the block reduces the accumulators through shared memory in a fixed order and
 // writes one partial per run: no atomics, results are reproducible for a given launch geometry.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "mrgp_math.cuh"
+#include "mrgp_tma.cuh"
 
 namespace mrgp {
 
@@ -49,6 +51,15 @@ struct StreamArgs {
     const double *pbias_var;     // (Rp)
     double *part;                // partial sums per run
     int32_t part_stride;
+    int64_t n_samples;
+    int64_t cta_quantum;         // samples per CTA range (multiple of 32)
+    // bias / noise update fused into the tail of phase B (run by the last CTA to finish)
+    unsigned int *done_counter;
+    const int32_t *region_run;   // (R + 1)
+    const int64_t *offsets;      // (R + 1)
+    int32_t R, infer, fuse_tail;
+    const double *bias_prec0, *bias_mean0, *noise_shape0, *noise_scale0;
+    double *bias_mean_out, *bias_prec, *bias_var, *noise_shape, *noise_scale, *noise_mean, *noise_log_mean, *yvar, *sumsB;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -94,8 +105,8 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 // Few values (NV <= 8): shuffle inside the warp, then across the 8 warps through shared memory.
-template <int NV, bool MAX>
-__device__ __forceinline__ void block_reduce_small(double (&v)[NV], double *sm /* >= 8*8 */, double *out) {
+template <int NV, bool MAX, int NT = kThreads>
+__device__ __forceinline__ void block_reduce_small(double (&v)[NV], double *sm /* >= (NT/32)*8 */, double *out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __syncthreads();
 #pragma unroll
@@ -107,7 +118,7 @@ __device__ __forceinline__ void block_reduce_small(double (&v)[NV], double *sm /
     if (tid < NV) {
         double t = sm[tid];
 #pragma unroll
-        for (int q = 1; q < kThreads / 32; ++q) t = MAX ? fmax(t, sm[q * 8 + tid]) : t + sm[q * 8 + tid];
+        for (int q = 1; q < NT / 32; ++q) t = MAX ? fmax(t, sm[q * 8 + tid]) : t + sm[q * 8 + tid];
         out[tid] = t;
     }
 }
@@ -171,103 +182,280 @@ __global__ void __launch_bounds__(kThreads, 1) k_phi2sum(StreamArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// P4, P5, S5 for one region from the summed phase-B statistics sm[0..DY+2] = [sum r_d, sum |r|^2, sum fvar,
+// sum phi^2 cm2] (region-specific noise and bias: Posteriors.py:81-93, 132-148 (ci) / 396-412 (fi);
+// Stats.py:102-124).  y_var is 1/noise_mean(old) for inferred targets and is NOT multiplied by n in the ci
+// regional/regional variant (Posteriors.py:138); fi targets are observations with y_var == 0.
+// ------------------------------------------------------------------------------------------------
+template <int DY>
+__device__ __forceinline__ void bias_noise_region(const StreamArgs &p, int r, const double *sums) {
+    const double n = (double)(p.offsets[r + 1] - p.offsets[r]);
+    const double bp0 = p.bias_prec0[r];
+    const double bp = bp0 + n;
+    double t3 = 0.0, t4 = 0.0;
+#pragma unroll
+    for (int d = 0; d < DY; ++d) {
+        const double m0 = p.bias_mean0[(size_t)r * DY + d];
+        const double m = (1.0 / bp) * (m0 * bp0 + sums[d]);
+        p.bias_mean_out[(size_t)r * DY + d] = m;
+        t3 += m0 * m0;
+        t4 += m * m;
+    }
+    t3 *= bp0;
+    t4 *= bp;
+    const double yvar = p.infer ? 1.0 / p.noise_mean[r] : 0.0;
+    const double shape = p.noise_shape0[r] + 0.5 * (double)DY * n;
+    const double scale = p.noise_scale0[r] + 0.5 * (t3 - t4 + sums[DY] + sums[DY + 1] + sums[DY + 2] + yvar);
+    p.yvar[r] = yvar;
+    p.bias_prec[r] = bp;
+    p.bias_var[r] = 1.0 / bp;
+    p.noise_shape[r] = shape;
+    p.noise_scale[r] = scale;
+    p.noise_mean[r] = shape / scale;
+    p.noise_log_mean[r] = digamma(shape) - log(scale);
+#pragma unroll
+    for (int d = 0; d < DY + 3; ++d) p.sumsB[(size_t)r * (DY + 3) + d] = sums[d];
+}
+
+// All regions of the layer by one block: `lpr` lanes (power of two <= 32) share the run loop of a region,
+// the lane sums are combined by shuffles in a fixed order.
+template <int DY>
+__device__ __forceinline__ void bias_noise_all(const StreamArgs &p, int lpr) {
+    const int groups = blockDim.x / lpr;
+    const int grp = threadIdx.x / lpr, sl = threadIdx.x % lpr;
+    for (int base = 0; base < p.R; base += groups) {
+        const int r = base + grp;
+        double acc[DY + 3];
+#pragma unroll
+        for (int d = 0; d < DY + 3; ++d) acc[d] = 0.0;
+        if (r < p.R)
+            for (int q = p.region_run[r] + sl; q < p.region_run[r + 1]; q += lpr) {
+                const double *src = p.part + (size_t)q * p.part_stride;
+#pragma unroll
+                for (int d = 0; d < DY + 3; ++d) acc[d] += __ldcg(src + d);
+            }
+        for (int o = lpr >> 1; o > 0; o >>= 1)
+#pragma unroll
+            for (int d = 0; d < DY + 3; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o);
+        if (r < p.R && sl == 0) bias_noise_region<DY>(p, r, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile pipeline of the streaming kernels.  A CTA walks its contiguous sample range in tiles of
+// kTile = 256 threads x kS samples; the inputs of a tile (x, y, latent mean g, latent variance h) are
+// brought to shared memory by bulk asynchronous copies (TMA, cp.async.bulk) that complete on an mbarrier,
+// kStages tiles ahead of the arithmetic, so no thread ever waits on a global load and no registers are
+// spent on prefetching.  Inside a tile every thread works on kS samples at once: the region coefficients
+// are read from shared memory once per basis function for all kS samples and the kS sine recurrences
+// are independent dependency chains for the FP64 pipe.
+// ------------------------------------------------------------------------------------------------
+constexpr int kS = 4;
+constexpr int kTile = kThreads * kS;
+constexpr int kStages = 3;
+constexpr int kThreadsB = 512;              // phase B: 16 warps, kSB samples per thread (same tile)
+constexpr int kSB = kTile / kThreadsB;
+
+template <int DY, bool NEED_Y, bool NEED_G, bool NEED_H>
+struct TileLayout {
+    static constexpr int kX = 0;
+    static constexpr int kH = kTile;
+    static constexpr int kY = kH + (NEED_H ? kTile : 0);
+    static constexpr int kG = kY + (NEED_Y ? kTile * DY : 0);
+    static constexpr int kDoubles = kG + (NEED_G ? kTile * DY : 0);
+    static_assert((DY * 8) % 16 == 0, "rows of y / g must be multiples of 16 bytes for the bulk copies");
+};
+
+// One thread arms the barrier of a stage and issues the copies of `cnt` samples starting at `start`.
+template <int DY, bool NEED_Y, bool NEED_G, bool NEED_H>
+__device__ __forceinline__ void issue_tile(const StreamArgs &p, double *stage, uint64_t *bar, int64_t start, int cnt) {
+    using L = TileLayout<DY, NEED_Y, NEED_G, NEED_H>;
+    const int even = cnt & ~1;   // 8-byte rows: bulk copies move multiples of 16 bytes, an odd tail goes by hand
+    uint32_t bytes = (uint32_t)even * 8u * (NEED_H ? 2u : 1u) + (uint32_t)cnt * DY * 8u * ((NEED_Y ? 1u : 0u) + (NEED_G ? 1u : 0u));
+    if (cnt & 1) {
+        stage[L::kX + cnt - 1] = p.x[start + cnt - 1];
+        if (NEED_H) stage[L::kH + cnt - 1] = p.h[start + cnt - 1];
+    }
+    mbar_arrive_expect_tx(bar, bytes);
+    if (even) {
+        bulk_g2s(stage + L::kX, p.x + start, (uint32_t)even * 8u, bar);
+        if (NEED_H) bulk_g2s(stage + L::kH, p.h + start, (uint32_t)even * 8u, bar);
+    }
+    if (NEED_Y) bulk_g2s(stage + L::kY, p.y + start * DY, (uint32_t)cnt * DY * 8u, bar);
+    if (NEED_G) bulk_g2s(stage + L::kG, p.g + start * DY, (uint32_t)cnt * DY * 8u, bar);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Phase A: T[i][d] = sum_n phi_i(n) r_d(n),  r = y - (fbar + b + Phi A_old^T)
 //   INFER  : targets are the layer's own prediction Phi A_old^T + (b_old + fbar)   (ci, j > 0;
 //            LatentOutputs.py:25-40 via MRGP.py:577) instead of the observations (LatentOutputs.py:6-18)
 //   LATENT : the layer has coarser layers below it (fbar = g + parent bias); layer 0 has fbar == 0.
 // y_tilde_i = T_i + (sum_n phi_i^2) a_i reproduces Posteriors.py:61-78 (the penalty over k != i) with
-// one pass instead of M.
+// one pass over the samples instead of M.  The basis is generated twice per sample (once for Phi A^T,
+// once for Phi^T r) instead of being kept in registers: 30 extra FMAs buy kS samples in flight.
 // ------------------------------------------------------------------------------------------------
+template <int DY, int M, int SB, bool INFER, bool LATENT>
+__device__ __forceinline__ void phase_a_block(double (&T)[M * DY], const double *st, int k0, int64_t tile_lo, int64_t pos,
+                                              int64_t hi, const double *sA, double inv2L, double rs, const double (&b)[DY],
+                                              const double (&pb)[DY]) {
+    using L = TileLayout<DY, !INFER, LATENT, false>;
+    asm volatile("" ::: "memory");   // keep the region coefficients in shared memory, not in registers
+    double f1[SB], c2[SB], f[SB], fm[SB], e[SB][DY], r[SB][DY];
+    bool act[SB];
+#pragma unroll
+    for (int q = 0; q < SB; ++q) {
+        const int idx = (k0 + q) * kThreads + threadIdx.x;
+        const int64_t n = tile_lo + idx;
+        act[q] = n >= pos && n < hi;
+        const double x = act[q] ? st[L::kX + idx] : 0.0;
+        basis_seed(x, inv2L, act[q] ? rs : 0.0, f1[q], c2[q]);
+        f[q] = f1[q];
+        fm[q] = 0.0;
+#pragma unroll
+        for (int d = 0; d < DY; ++d) e[q][d] = 0.0;
+    }
+#pragma unroll 5
+    for (int i = 0; i < M; ++i) {
+        double a[DY];
+#pragma unroll
+        for (int d = 0; d < DY; ++d) a[d] = sA[i * DY + d];
+#pragma unroll
+        for (int q = 0; q < SB; ++q) {
+#pragma unroll
+            for (int d = 0; d < DY; ++d) e[q][d] = fma(f[q], a[d], e[q][d]);
+            const double fn = fma(c2[q], f[q], -fm[q]);
+            fm[q] = f[q];
+            f[q] = fn;
+        }
+    }
+    asm volatile("" ::: "memory");   // read the targets / latent mean only now (register pressure)
+#pragma unroll
+    for (int q = 0; q < SB; ++q) {
+        const int idx = (k0 + q) * kThreads + threadIdx.x;
+#pragma unroll
+        for (int d = 0; d < DY; ++d) {
+            const double g = (LATENT && act[q]) ? st[L::kG + idx * DY + d] : 0.0;
+            const double yv = (!INFER && act[q]) ? st[L::kY + idx * DY + d] : 0.0;
+            const double fb = LATENT ? g + pb[d] : 0.0;   // fbar
+            const double target = INFER ? e[q][d] + (b[d] + fb) : yv;
+            r[q][d] = target - ((fb + b[d]) + e[q][d]);
+        }
+        f[q] = f1[q];
+        fm[q] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+#pragma unroll
+        for (int q = 0; q < SB; ++q) {
+#pragma unroll
+            for (int d = 0; d < DY; ++d) T[i * DY + d] = fma(f[q], r[q][d], T[i * DY + d]);
+            const double fn = fma(c2[q], f[q], -fm[q]);
+            fm[q] = f[q];
+            f[q] = fn;
+        }
+    }
+}
+
 template <int DY, int M, bool INFER, bool LATENT>
 __global__ void __launch_bounds__(kThreads, 1) k_phase_a(StreamArgs p) {
-    extern __shared__ double red[];
+    using L = TileLayout<DY, !INFER, LATENT, false>;
+    extern __shared__ __align__(128) double dsm[];
+    double *stages = dsm;
+    double *red = dsm + kStages * L::kDoubles;
     __shared__ double sA[M * DY];
     __shared__ double sScal[2 + 2 * DY];
+    __shared__ __align__(8) uint64_t bars[kStages];
     const int tid = threadIdx.x;
+    const int64_t c0 = (int64_t)blockIdx.x * p.cta_quantum;
+    const int64_t c1 = (c0 + p.cta_quantum < p.n_samples) ? c0 + p.cta_quantum : p.n_samples;
+    const int n_tiles = (c1 > c0) ? (int)((c1 - c0 + kTile - 1) / kTile) : 0;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int t = 0; t < kStages && t < n_tiles; ++t) {
+            const int64_t start = c0 + (int64_t)t * kTile;
+            const int cnt = (int)((c1 - start < kTile) ? c1 - start : kTile);
+            issue_tile<DY, !INFER, LATENT, false>(p, stages + t * L::kDoubles, &bars[t], start, cnt);
+        }
+    }
     double T[M * DY];
 #pragma unroll
     for (int i = 0; i < M * DY; ++i) T[i] = 0.0;
-    const int s0 = p.cta_seg[blockIdx.x], s1 = p.cta_seg[blockIdx.x + 1];
-    for (int s = s0; s < s1; ++s) {
-        const Segment sg = p.segs[s];
-        __syncthreads();
-        if (tid < M * DY) sA[tid] = p.A[(size_t)sg.region * (M * DY) + tid];
-        if (tid == 0) {
-            sScal[0] = p.inv2L[sg.region];
-            sScal[1] = p.rsqrtL[sg.region];
-        }
-        if (tid < DY) {
-            sScal[2 + tid] = p.bias[(size_t)sg.region * DY + tid];
-            sScal[2 + DY + tid] = LATENT ? p.pbias[(size_t)sg.parent * DY + tid] : 0.0;
-        }
-        __syncthreads();
-        const double inv2L = sScal[0], rs = sScal[1];
-        double b[DY], pb[DY];
+    int s = p.cta_seg[blockIdx.x];
+    const int s_end = p.cta_seg[blockIdx.x + 1];
+    int loaded = -1;
+    double inv2L = 0.0, rs = 0.0, b[DY], pb[DY];
 #pragma unroll
-        for (int d = 0; d < DY; ++d) {
-            b[d] = sScal[2 + d];
-            pb[d] = sScal[2 + DY + d];
-        }
-        const int64_t end = sg.start + sg.len;
-        int64_t n = sg.start + tid;
-        double xn = 0.0, yn[DY], gn[DY];
-#pragma unroll
-        for (int d = 0; d < DY; ++d) yn[d] = gn[d] = 0.0;
-        if (n < end) {
-            xn = p.x[n];
-#pragma unroll
-            for (int d = 0; d < DY; ++d) {
-                if (!INFER) yn[d] = p.y[n * DY + d];
-                if (LATENT) gn[d] = p.g[n * DY + d];
-            }
-        }
-        while (n < end) {
-            asm volatile("" ::: "memory");   // keep the region coefficients in shared memory, not registers
-            const double xc = xn;
-            double yc[DY], gc[DY];
-#pragma unroll
-            for (int d = 0; d < DY; ++d) {
-                yc[d] = yn[d];
-                gc[d] = gn[d];
-            }
-            n += kThreads;
-            if (n < end) {
-                xn = p.x[n];
+    for (int d = 0; d < DY; ++d) b[d] = pb[d] = 0.0;
+    Segment sg;
+    if (s < s_end) sg = p.segs[s];
+    for (int t = 0; t < n_tiles; ++t) {
+        const int stage = t % kStages;
+        const double *st = stages + stage * L::kDoubles;
+        mbar_wait(&bars[stage], (uint32_t)((t / kStages) & 1));
+        const int64_t tile_lo = c0 + (int64_t)t * kTile;
+        const int64_t tile_hi = (tile_lo + kTile < c1) ? tile_lo + kTile : c1;
+        int64_t pos = tile_lo;
+        while (pos < tile_hi) {
+            if (loaded != s) {
+                __syncthreads();
+                if (tid < M * DY) sA[tid] = p.A[(size_t)sg.region * (M * DY) + tid];
+                if (tid == 0) {
+                    sScal[0] = p.inv2L[sg.region];
+                    sScal[1] = p.rsqrtL[sg.region];
+                }
+                if (tid < DY) {
+                    sScal[2 + tid] = p.bias[(size_t)sg.region * DY + tid];
+                    sScal[2 + DY + tid] = LATENT ? p.pbias[(size_t)sg.parent * DY + tid] : 0.0;
+                }
+                __syncthreads();
+                inv2L = sScal[0];
+                rs = sScal[1];
 #pragma unroll
                 for (int d = 0; d < DY; ++d) {
-                    if (!INFER) yn[d] = p.y[n * DY + d];
-                    if (LATENT) gn[d] = p.g[n * DY + d];
+                    b[d] = sScal[2 + d];
+                    pb[d] = sScal[2 + DY + d];
+                }
+                loaded = s;
+            }
+            const int64_t seg_end = sg.start + sg.len;
+            const int64_t hi = (seg_end < tile_hi) ? seg_end : tile_hi;
+            // 256-sample sub-blocks of the tile that intersect [pos, hi)
+            int ka = (int)((pos - tile_lo) / kThreads);
+            const int kb = (int)((hi - 1 - tile_lo) / kThreads);
+            while (ka <= kb) {
+                const int left = kb - ka + 1;
+                if (left >= 4) {
+                    phase_a_block<DY, M, 4, INFER, LATENT>(T, st, ka, tile_lo, pos, hi, sA, inv2L, rs, b, pb);
+                    ka += 4;
+                } else if (left >= 2) {
+                    phase_a_block<DY, M, 2, INFER, LATENT>(T, st, ka, tile_lo, pos, hi, sA, inv2L, rs, b, pb);
+                    ka += 2;
+                } else {
+                    phase_a_block<DY, M, 1, INFER, LATENT>(T, st, ka, tile_lo, pos, hi, sA, inv2L, rs, b, pb);
+                    ka += 1;
                 }
             }
-            double phi[M];
-            double c2;
-            basis_seed(xc, inv2L, rs, phi[0], c2);
-            if (M > 1) phi[1] = c2 * phi[0];
+            pos = hi;
+            if (hi == seg_end) {
+                if (sg.flush) {
+                    block_reduce_store<M * DY>(T, red, p.part + (size_t)sg.run * p.part_stride);
 #pragma unroll
-            for (int i = 2; i < M; ++i) phi[i] = fma(c2, phi[i - 1], -phi[i - 2]);
-            double e[DY];
-#pragma unroll
-            for (int d = 0; d < DY; ++d) e[d] = 0.0;
-#pragma unroll
-            for (int i = 0; i < M; ++i)
-#pragma unroll
-                for (int d = 0; d < DY; ++d) e[d] = fma(phi[i], sA[i * DY + d], e[d]);
-            double r[DY];
-#pragma unroll
-            for (int d = 0; d < DY; ++d) {
-                const double fb = LATENT ? gc[d] + pb[d] : 0.0;
-                const double target = INFER ? e[d] + (b[d] + fb) : yc[d];
-                r[d] = target - ((fb + b[d]) + e[d]);
+                    for (int i = 0; i < M * DY; ++i) T[i] = 0.0;
+                }
+                ++s;
+                if (s < s_end) sg = p.segs[s];
             }
-#pragma unroll
-            for (int i = 0; i < M; ++i)
-#pragma unroll
-                for (int d = 0; d < DY; ++d) T[i * DY + d] = fma(phi[i], r[d], T[i * DY + d]);
         }
-        if (sg.flush) {
-            block_reduce_store<M * DY>(T, red, p.part + (size_t)sg.run * p.part_stride);
-#pragma unroll
-            for (int i = 0; i < M * DY; ++i) T[i] = 0.0;
+        __syncthreads();   // every thread is done reading this stage
+        if (tid == 0 && t + kStages < n_tiles) {
+            const int64_t start = c0 + (int64_t)(t + kStages) * kTile;
+            const int cnt = (int)((c1 - start < kTile) ? c1 - start : kTile);
+            issue_tile<DY, !INFER, LATENT, false>(p, stages + stage * L::kDoubles, &bars[stage], start, cnt);
         }
     }
 }
@@ -279,116 +467,195 @@ __global__ void __launch_bounds__(kThreads, 1) k_phase_a(StreamArgs p) {
 //   g <- fbar + Phi A_new^T,  h <- fvar + sum_i phi_i^2 cm2_i      (PROPAGATE; the layer's own bias and
 //   bias variance are added by the next layer when it reads g, h, because they are not known yet).
 // ------------------------------------------------------------------------------------------------
+template <int DY, int M, int SB, int NT, bool INFER, bool LATENT, bool PROPAGATE>
+__device__ __forceinline__ void phase_b_block(double (&acc)[DY + 3], const StreamArgs &p, const double *st, int k0, int64_t tile_lo,
+                                              int64_t pos, int64_t hi, const double *sAn, const double *sAo, const double *sC,
+                                              double inv2L, double rs, double pbv, const double (&b)[DY], const double (&pb)[DY]) {
+    using L = TileLayout<DY, !INFER, LATENT, LATENT>;
+    asm volatile("" ::: "memory");
+    double c2[SB], f[SB], fm[SB], en[SB][DY], eo[SB][DY], v[SB];
+    bool act[SB];
+#pragma unroll
+    for (int q = 0; q < SB; ++q) {
+        const int idx = (k0 + q) * NT + threadIdx.x;
+        const int64_t n = tile_lo + idx;
+        act[q] = n >= pos && n < hi;
+        const double x = act[q] ? st[L::kX + idx] : 0.0;
+        basis_seed(x, inv2L, act[q] ? rs : 0.0, f[q], c2[q]);
+        fm[q] = 0.0;
+        v[q] = 0.0;
+#pragma unroll
+        for (int d = 0; d < DY; ++d) en[q][d] = eo[q][d] = 0.0;
+    }
+#pragma unroll 5
+    for (int i = 0; i < M; ++i) {
+        double an[DY], ao[DY];
+#pragma unroll
+        for (int d = 0; d < DY; ++d) {
+            an[d] = sAn[i * DY + d];
+            ao[d] = INFER ? sAo[i * DY + d] : 0.0;
+        }
+        const double c = sC[i];
+#pragma unroll
+        for (int q = 0; q < SB; ++q) {
+#pragma unroll
+            for (int d = 0; d < DY; ++d) {
+                en[q][d] = fma(f[q], an[d], en[q][d]);
+                if (INFER) eo[q][d] = fma(f[q], ao[d], eo[q][d]);
+            }
+            v[q] = fma(f[q] * c, f[q], v[q]);
+            const double fn = fma(c2[q], f[q], -fm[q]);
+            fm[q] = f[q];
+            f[q] = fn;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < SB; ++q) {
+        if (act[q]) {
+            const int idx = (k0 + q) * NT + threadIdx.x;
+            const int64_t n = tile_lo + idx;
+            const double fv = LATENT ? st[L::kH + idx] + pbv : 0.0;
+            double rr = 0.0;
+#pragma unroll
+            for (int d = 0; d < DY; ++d) {
+                const double fb = LATENT ? st[L::kG + idx * DY + d] + pb[d] : 0.0;
+                const double target = INFER ? eo[q][d] + (b[d] + fb) : st[L::kY + idx * DY + d];
+                const double r = (target - en[q][d]) - fb;
+                acc[d] += r;
+                rr = fma(r, r, rr);
+                if (PROPAGATE) p.g[n * DY + d] = fb + en[q][d];
+            }
+            acc[DY] += rr;
+            acc[DY + 1] += fv;
+            acc[DY + 2] += v[q];
+            if (PROPAGATE) p.h[n] = fv + v[q];
+        }
+    }
+}
+
 template <int DY, int M, bool INFER, bool LATENT, bool PROPAGATE>
-__global__ void __launch_bounds__(kThreads, 2) k_phase_b(StreamArgs p) {
+__global__ void __launch_bounds__(kThreadsB, 1) k_phase_b(StreamArgs p) {
+    constexpr int NT = kThreadsB;
+    using L = TileLayout<DY, !INFER, LATENT, LATENT>;
+    extern __shared__ __align__(128) double dsm[];
+    double *stages = dsm;
     __shared__ double sAn[M * DY];
     __shared__ double sAo[INFER ? M * DY : 1];
     __shared__ double sC[M];
     __shared__ double sScal[4 + 2 * DY];
-    __shared__ double sRed[64];
+    __shared__ double sRed[(kThreadsB / 32) * 8];
+    __shared__ __align__(8) uint64_t bars[kStages];
     const int tid = threadIdx.x;
+    const int64_t c0 = (int64_t)blockIdx.x * p.cta_quantum;
+    const int64_t c1 = (c0 + p.cta_quantum < p.n_samples) ? c0 + p.cta_quantum : p.n_samples;
+    const int n_tiles = (c1 > c0) ? (int)((c1 - c0 + kTile - 1) / kTile) : 0;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int t = 0; t < kStages && t < n_tiles; ++t) {
+            const int64_t start = c0 + (int64_t)t * kTile;
+            const int cnt = (int)((c1 - start < kTile) ? c1 - start : kTile);
+            issue_tile<DY, !INFER, LATENT, LATENT>(p, stages + t * L::kDoubles, &bars[t], start, cnt);
+        }
+    }
     double acc[DY + 3];
 #pragma unroll
     for (int i = 0; i < DY + 3; ++i) acc[i] = 0.0;
-    const int s0 = p.cta_seg[blockIdx.x], s1 = p.cta_seg[blockIdx.x + 1];
-    for (int s = s0; s < s1; ++s) {
-        const Segment sg = p.segs[s];
-        __syncthreads();
-        if (tid < M * DY) {
-            sAn[tid] = p.A[(size_t)sg.region * (M * DY) + tid];
-            if (INFER) sAo[tid] = p.A_prev[(size_t)sg.region * (M * DY) + tid];
-        }
-        if (tid < M) sC[tid] = p.cm2[(size_t)sg.region * M + tid];
-        if (tid == 0) {
-            sScal[0] = p.inv2L[sg.region];
-            sScal[1] = p.rsqrtL[sg.region];
-            sScal[2] = LATENT ? p.pbias_var[sg.parent] : 0.0;
-        }
-        if (tid < DY) {
-            sScal[4 + tid] = p.bias[(size_t)sg.region * DY + tid];
-            sScal[4 + DY + tid] = LATENT ? p.pbias[(size_t)sg.parent * DY + tid] : 0.0;
-        }
-        __syncthreads();
-        const double inv2L = sScal[0], rs = sScal[1], pbv = sScal[2];
-        double b[DY], pb[DY];
+    int s = p.cta_seg[blockIdx.x];
+    const int s_end = p.cta_seg[blockIdx.x + 1];
+    int loaded = -1;
+    double inv2L = 0.0, rs = 0.0, pbv = 0.0, b[DY], pb[DY];
 #pragma unroll
-        for (int d = 0; d < DY; ++d) {
-            b[d] = sScal[4 + d];
-            pb[d] = sScal[4 + DY + d];
-        }
-        const int64_t end = sg.start + sg.len;
-        int64_t n = sg.start + tid;
-        double xn = 0.0, hn = 0.0, yn[DY], gn[DY];
-#pragma unroll
-        for (int d = 0; d < DY; ++d) yn[d] = gn[d] = 0.0;
-        if (n < end) {
-            xn = p.x[n];
-            if (LATENT) hn = p.h[n];
-#pragma unroll
-            for (int d = 0; d < DY; ++d) {
-                if (!INFER) yn[d] = p.y[n * DY + d];
-                if (LATENT) gn[d] = p.g[n * DY + d];
-            }
-        }
-        while (n < end) {
-            asm volatile("" ::: "memory");   // keep the region coefficients in shared memory, not registers
-            const int64_t nc = n;
-            const double xc = xn, hc = hn;
-            double yc[DY], gc[DY];
-#pragma unroll
-            for (int d = 0; d < DY; ++d) {
-                yc[d] = yn[d];
-                gc[d] = gn[d];
-            }
-            n += kThreads;
-            if (n < end) {
-                xn = p.x[n];
-                if (LATENT) hn = p.h[n];
+    for (int d = 0; d < DY; ++d) b[d] = pb[d] = 0.0;
+    Segment sg;
+    if (s < s_end) sg = p.segs[s];
+    for (int t = 0; t < n_tiles; ++t) {
+        const int stage = t % kStages;
+        const double *st = stages + stage * L::kDoubles;
+        mbar_wait(&bars[stage], (uint32_t)((t / kStages) & 1));
+        const int64_t tile_lo = c0 + (int64_t)t * kTile;
+        const int64_t tile_hi = (tile_lo + kTile < c1) ? tile_lo + kTile : c1;
+        int64_t pos = tile_lo;
+        while (pos < tile_hi) {
+            if (loaded != s) {
+                __syncthreads();
+                if (tid < M * DY) {
+                    sAn[tid] = p.A[(size_t)sg.region * (M * DY) + tid];
+                    if (INFER) sAo[tid] = p.A_prev[(size_t)sg.region * (M * DY) + tid];
+                }
+                if (tid < M) sC[tid] = p.cm2[(size_t)sg.region * M + tid];
+                if (tid == 0) {
+                    sScal[0] = p.inv2L[sg.region];
+                    sScal[1] = p.rsqrtL[sg.region];
+                    sScal[2] = LATENT ? p.pbias_var[sg.parent] : 0.0;
+                }
+                if (tid < DY) {
+                    sScal[4 + tid] = p.bias[(size_t)sg.region * DY + tid];
+                    sScal[4 + DY + tid] = LATENT ? p.pbias[(size_t)sg.parent * DY + tid] : 0.0;
+                }
+                __syncthreads();
+                inv2L = sScal[0];
+                rs = sScal[1];
+                pbv = sScal[2];
 #pragma unroll
                 for (int d = 0; d < DY; ++d) {
-                    if (!INFER) yn[d] = p.y[n * DY + d];
-                    if (LATENT) gn[d] = p.g[n * DY + d];
+                    b[d] = sScal[4 + d];
+                    pb[d] = sScal[4 + DY + d];
+                }
+                loaded = s;
+            }
+            const int64_t seg_end = sg.start + sg.len;
+            const int64_t hi = (seg_end < tile_hi) ? seg_end : tile_hi;
+            int ka = (int)((pos - tile_lo) / NT);
+            const int kb = (int)((hi - 1 - tile_lo) / NT);
+            while (ka <= kb) {
+                const int left = kb - ka + 1;
+                if (kSB >= 4 && left >= 4) {
+                    phase_b_block<DY, M, 4, NT, INFER, LATENT, PROPAGATE>(acc, p, st, ka, tile_lo, pos, hi, sAn, sAo, sC, inv2L, rs, pbv, b, pb);
+                    ka += 4;
+                } else if (left >= 2) {
+                    phase_b_block<DY, M, 2, NT, INFER, LATENT, PROPAGATE>(acc, p, st, ka, tile_lo, pos, hi, sAn, sAo, sC, inv2L, rs, pbv, b, pb);
+                    ka += 2;
+                } else {
+                    phase_b_block<DY, M, 1, NT, INFER, LATENT, PROPAGATE>(acc, p, st, ka, tile_lo, pos, hi, sAn, sAo, sC, inv2L, rs, pbv, b, pb);
+                    ka += 1;
                 }
             }
-            double f1, c2;
-            basis_seed(xc, inv2L, rs, f1, c2);
-            double fm = 0.0, f = f1;
-            double en[DY], eo[DY], v = 0.0;
+            pos = hi;
+            if (hi == seg_end) {
+                if (sg.flush) {
+                    block_reduce_small<DY + 3, false, NT>(acc, sRed, p.part + (size_t)sg.run * p.part_stride);
 #pragma unroll
-            for (int d = 0; d < DY; ++d) en[d] = eo[d] = 0.0;
-#pragma unroll
-            for (int i = 0; i < M; ++i) {
-#pragma unroll
-                for (int d = 0; d < DY; ++d) {
-                    en[d] = fma(f, sAn[i * DY + d], en[d]);
-                    if (INFER) eo[d] = fma(f, sAo[i * DY + d], eo[d]);
+                    for (int i = 0; i < DY + 3; ++i) acc[i] = 0.0;
                 }
-                v = fma(f * sC[i], f, v);
-                const double fn = fma(c2, f, -fm);
-                fm = f;
-                f = fn;
+                ++s;
+                if (s < s_end) sg = p.segs[s];
             }
-            const double fv = LATENT ? hc + pbv : 0.0;
-            double rr = 0.0;
-#pragma unroll
-            for (int d = 0; d < DY; ++d) {
-                const double fb = LATENT ? gc[d] + pb[d] : 0.0;
-                const double target = INFER ? eo[d] + (b[d] + fb) : yc[d];
-                const double r = (target - en[d]) - fb;
-                acc[d] += r;
-                rr = fma(r, r, rr);
-                if (PROPAGATE) p.g[nc * DY + d] = fb + en[d];
-            }
-            acc[DY] += rr;
-            acc[DY + 1] += fv;
-            acc[DY + 2] += v;
-            if (PROPAGATE) p.h[nc] = fv + v;
         }
-        if (sg.flush) {
-            block_reduce_small<DY + 3, false>(acc, sRed, p.part + (size_t)sg.run * p.part_stride);
-#pragma unroll
-            for (int i = 0; i < DY + 3; ++i) acc[i] = 0.0;
+        __syncthreads();
+        if (tid == 0 && t + kStages < n_tiles) {
+            const int64_t start = c0 + (int64_t)(t + kStages) * kTile;
+            const int cnt = (int)((c1 - start < kTile) ? c1 - start : kTile);
+            issue_tile<DY, !INFER, LATENT, LATENT>(p, stages + stage * L::kDoubles, &bars[stage], start, cnt);
         }
+    }
+    // ---- tail: the last CTA to finish turns the run partials into the bias / noise posteriors --------
+    if (!p.fuse_tail) return;
+    __shared__ int sLast;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sLast = (atomicAdd(p.done_counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (sLast) {
+        __threadfence();
+        int lpr = 32;
+        while (lpr > 1 && (NT / lpr) < p.R) lpr >>= 1;
+        bias_noise_all<DY>(p, lpr);
+        if (tid == 0) *p.done_counter = 0u;
     }
 }
 
@@ -411,7 +678,7 @@ struct RegionArgs {
     double *bias_prec, *bias_prec0, *bias_mean, *bias_mean0, *bias_var, *yvar, *sumsB;
     // shared (ci) or per-region (fi) axis / ARD
     double *axB, *axKappa, *axRho, *axLogC, *axCov, *ardShape, *ardScale, *ardMean, *ardLogMean;
-    double *omega, *logOmegaHat;
+    double *omega, *logOmegaHat, *omegaIters, *ardPartial;
     double *primeB, *primeLogC, *primeShape, *primeScale;   // snapshot read by ARD / omega (ci)
     const double *priorB, *priorLogC, *priorShape, *priorScale;
     double *bcontrib;          // (R, M, 3) ci: 0.5 noise zeta ytil ytil^T
@@ -548,110 +815,197 @@ __global__ void __launch_bounds__(512) k_reduce_scale(RegionArgs a) {
     }
 }
 
-// ci: B_i = sum_k omega_ik B'_k + sum_l contrib_li, PD guard, Bingham parameters, axis covariance
-// (Posteriors.py:497-530, Stats.py:375-382).  Also takes the snapshot of the "previous posterior"
-// (MRGP.py:575 / :581) that ARD and omega read.  One block of 1024 threads.
+// ------------------------------------------------------------------------------------------------
+// ci mid-step in ONE launch: a thread-block cluster of up to 8 CTAs does P1-finish, P2 (+ guard, Bingham),
+// S1, S2, P3, S3 and the log omega_hat table; the two cross-region sums (B_i over regions, ARD scale over
+// regions) go through distributed shared memory with cluster barriers instead of separate kernels.
+//   regions are split contiguously over the CTAs; `lpi` lanes (power of two) share the run loop of one
+//   (region, basis) item on coarse layers where a region has many run partials.
+// Same arithmetic and summation order as k_reduce_scale / k_axis_shared / k_scale_stats / k_ard.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMidThreads = 512;
+constexpr int kMidChunk = 32;   // regions per shared-memory reduction chunk
+
+__host__ __device__ inline size_t mid_smem_doubles(int M) { return (size_t)M * M + 4 * M + 3 * M + 4 * M + 3 * 128 + (size_t)kMidChunk * M * 4; }
+
 template <int DY>
-__global__ void __launch_bounds__(1024) k_axis_shared(RegionArgs a) {
+__global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, int regions_per_cta) {
     static_assert(DY == 2, "dy == 2 only");
-    extern __shared__ double sm[];   // [slices][M*3]
-    const int M = a.M, NV = M * 3;
-    const int nval = (NV + 31) & ~31;
-    const int slices = blockDim.x / nval;
-    const int v = threadIdx.x % nval, sl = threadIdx.x / nval;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int NC = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int M = a.M, tid = threadIdx.x;
+    extern __shared__ double sm[];
+    double *sOmega = sm;                  // M*M
+    double *sPB = sOmega + M * M;         // M*4  previous posterior B ("prime")
+    double *sPLogC = sPB + 4 * M;         // M
+    double *sPShape = sPLogC + M;         // M
+    double *sPScale = sPShape + M;        // M
+    double *sCov = sPScale + M;           // M*4
+    double *sPubB = sCov + 4 * M;         // 128  this CTA's sums of the B contributions (read by peers)
+    double *sPubA = sPubB + 128;          // 128  this CTA's sums of m2/S
+    double *sTot = sPubA + 128;           // 128
+    double *sContrib = sTot + 128;        // kMidChunk * M * 4
     const bool first = (a.layer == 0);
-    // snapshot prime <- prior (layer 0) or current shared posterior
-    for (int t = threadIdx.x; t < M * 4; t += blockDim.x) a.primeB[t] = first ? a.priorB[t] : a.axB[t];
-    for (int t = threadIdx.x; t < M; t += blockDim.x) {
-        a.primeLogC[t] = first ? a.priorLogC[t] : a.axLogC[t];
-        a.primeShape[t] = first ? a.priorShape[t] : a.ardShape[t];
-        a.primeScale[t] = first ? a.priorScale[t] : a.ardScale[t];
+    for (int t = tid; t < M * M; t += kMidThreads) sOmega[t] = a.omega[t];
+    for (int t = tid; t < M * 4; t += kMidThreads) sPB[t] = first ? a.priorB[t] : a.axB[t];
+    for (int t = tid; t < M; t += kMidThreads) {
+        sPLogC[t] = first ? a.priorLogC[t] : a.axLogC[t];
+        sPShape[t] = first ? a.priorShape[t] : a.ardShape[t];
+        sPScale[t] = first ? a.priorScale[t] : a.ardScale[t];
     }
-    double acc = 0.0;
-    if (v < NV && sl < slices)
-        for (int l = sl; l < a.R; l += slices) acc += a.bcontrib[(size_t)l * NV + v];
-    if (sl < slices) sm[sl * nval + v] = acc;
-    __syncthreads();
-    if (threadIdx.x < NV) {
+    const int r0 = rank * regions_per_cta;
+    const int r1 = (r0 + regions_per_cta < a.R) ? r0 + regions_per_cta : a.R;
+    const int groups = kMidThreads / lpi, grp = tid / lpi, sl = tid % lpi;
+    // ---- step 1: y_tilde, precision, zeta per (region, basis); B contributions summed over my regions ----
+    double accB = 0.0;
+    for (int cb = r0; cb < r1; cb += kMidChunk) {
+        const int nreg = (cb + kMidChunk < r1) ? kMidChunk : r1 - cb;
+        const int nitems = nreg * M;
+        for (int base = 0; base < nitems; base += groups) {
+            const int it = base + grp;
+            const bool valid = it < nitems;
+            const int l = cb + (valid ? it / M : 0), i = valid ? it % M : 0;
+            double t0 = 0.0, t1 = 0.0;
+            if (valid)
+                for (int q = a.region_run[l] + sl; q < a.region_run[l + 1]; q += lpi) {
+                    const double2 v = *reinterpret_cast<const double2 *>(a.part + (size_t)q * a.part_stride + i * 2);
+                    t0 += v.x;
+                    t1 += v.y;
+                }
+            for (int o = lpi >> 1; o > 0; o >>= 1) {
+                t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+                t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+            }
+            if (valid && sl == 0) {
+                const size_t ri = (size_t)l * M + i;
+                const double dsum = a.d[ri];
+                const double y0 = t0 + dsum * a.A[ri * 2 + 0], y1 = t1 + dsum * a.A[ri * 2 + 1];   // Posteriors.py:61-78
+                const double noise = a.noise_mean[l];
+                const double prec = a.ardMean[i] / a.S[ri] + noise * dsum;                       // Posteriors.py:40-42
+                const double zeta = noise / prec;
+                a.ytil[ri * 2 + 0] = y0;
+                a.ytil[ri * 2 + 1] = y1;
+                a.prec[ri] = prec;
+                a.zeta[ri] = zeta;
+                const double w = 0.5 * noise * zeta;                                             // Posteriors.py:507-517
+                sContrib[it * 4 + 0] = w * (y0 * y0);
+                sContrib[it * 4 + 1] = w * (y0 * y1);
+                sContrib[it * 4 + 2] = w * (y1 * y1);
+            }
+        }
+        __syncthreads();
+        if (tid < M * 3) {
+            const int i = tid / 3, c = tid % 3;
+            for (int k = 0; k < nreg; ++k) accB += sContrib[(k * M + i) * 4 + c];
+        }
+        __syncthreads();
+    }
+    if (tid < M * 3) sPubB[tid] = accB;
+    cluster.sync();
+    if (tid < M * 3) {
         double t = 0.0;
-        for (int q = 0; q < slices; ++q) t += sm[q * nval + threadIdx.x];
-        sm[slices * nval + threadIdx.x] = t;
+        for (int c = 0; c < NC; ++c) t += cluster.map_shared_rank(sPubB, c)[tid];
+        sTot[tid] = t;
     }
     __syncthreads();
-    if (threadIdx.x < M) {
-        const int i = threadIdx.x;
-        const double *data = sm + slices * nval + i * 3;
+    // ---- step 2: B_i, PD guard, Bingham parameters, axis covariance (every CTA, identical results) --------
+    if (tid < M) {
+        const int i = tid;
         double b00 = 0.0, b01 = 0.0, b11 = 0.0;
         for (int k = 0; k < M; ++k) {
-            const double w = a.omega[i * M + k];
-            b00 += w * a.primeB[k * 4 + 0];
-            b01 += w * a.primeB[k * 4 + 1];
-            b11 += w * a.primeB[k * 4 + 3];
+            const double w = sOmega[i * M + k];
+            b00 += w * sPB[k * 4 + 0];
+            b01 += w * sPB[k * 4 + 1];
+            b11 += w * sPB[k * 4 + 3];
         }
         Bingham2 bg;
-        bingham2(b00 + data[0], b01 + data[1], b11 + data[2], bg);
-        atomicAdd(a.chol_count, (unsigned long long)bg.n_chol);
-        a.axB[i * 4 + 0] = bg.b[0];
-        a.axB[i * 4 + 1] = bg.b[1];
-        a.axB[i * 4 + 2] = bg.b[1];
-        a.axB[i * 4 + 3] = bg.b[2];
-        a.axKappa[i * 2 + 0] = bg.kappa[0];
-        a.axKappa[i * 2 + 1] = bg.kappa[1];
-        a.axRho[i * 2 + 0] = bg.rho[0];
-        a.axRho[i * 2 + 1] = bg.rho[1];
-        a.axLogC[i] = bg.logc;
-        a.axCov[i * 4 + 0] = bg.cov[0];
-        a.axCov[i * 4 + 1] = bg.cov[1];
-        a.axCov[i * 4 + 2] = bg.cov[1];
-        a.axCov[i * 4 + 3] = bg.cov[2];
+        bingham2(b00 + sTot[i * 3 + 0], b01 + sTot[i * 3 + 1], b11 + sTot[i * 3 + 2], bg);
+        sCov[i * 4 + 0] = bg.cov[0];
+        sCov[i * 4 + 1] = bg.cov[1];
+        sCov[i * 4 + 2] = bg.cov[2];
+        if (rank == 0) {
+            atomicAdd(a.chol_count, (unsigned long long)bg.n_chol);
+            a.axB[i * 4 + 0] = bg.b[0];
+            a.axB[i * 4 + 1] = bg.b[1];
+            a.axB[i * 4 + 2] = bg.b[1];
+            a.axB[i * 4 + 3] = bg.b[2];
+            a.axKappa[i * 2 + 0] = bg.kappa[0];
+            a.axKappa[i * 2 + 1] = bg.kappa[1];
+            a.axRho[i * 2 + 0] = bg.rho[0];
+            a.axRho[i * 2 + 1] = bg.rho[1];
+            a.axLogC[i] = bg.logc;
+            a.axCov[i * 4 + 0] = bg.cov[0];
+            a.axCov[i * 4 + 1] = bg.cov[1];
+            a.axCov[i * 4 + 2] = bg.cov[1];
+            a.axCov[i * 4 + 3] = bg.cov[2];
+        }
     }
-}
-
-// ci: a, m2, cm2 per (region, basis) from the shared axis covariance (Stats.py:67-100).
-template <int DY>
-__global__ void k_scale_stats(RegionArgs a) {
-    static_assert(DY == 2, "dy == 2 only");
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.R * a.M) return;
-    const int i = t % a.M;
-    const size_t ri = t;
-    const double c00 = a.axCov[i * 4 + 0], c01 = a.axCov[i * 4 + 1], c11 = a.axCov[i * 4 + 3];
-    const double y0 = a.ytil[ri * DY], y1 = a.ytil[ri * DY + 1];
-    const double zeta = a.zeta[ri], prec = a.prec[ri];
-    const double cy0 = c00 * y0 + c01 * y1, cy1 = c01 * y0 + c11 * y1;
-    a.A_prev[ri * DY + 0] = a.A[ri * DY + 0];
-    a.A_prev[ri * DY + 1] = a.A[ri * DY + 1];
-    a.A[ri * DY + 0] = zeta * cy0;
-    a.A[ri * DY + 1] = zeta * cy1;
-    const double z2 = zeta * zeta;
-    a.m2[ri] = 1.0 / prec + z2 * (y0 * cy0 + y1 * cy1);
-    const double ccy0 = c00 * cy0 + c01 * cy1, ccy1 = c01 * cy0 + c11 * cy1;
-    a.cm2[ri] = 1.0 / prec + z2 * (y0 * (cy0 - ccy0) + y1 * (cy1 - ccy1));
-}
-
-// ci: ARD posterior and moments (Posteriors.py:533-541, Stats.py:385-388), then log omega_hat
-// (Stats.py:405-412).  One block of 1024 threads.
-template <int DY>
-__global__ void __launch_bounds__(1024) k_ard(RegionArgs a) {
-    static_assert(DY == 2, "dy == 2 only");
-    extern __shared__ double sm[];   // [slices][M] + ard_mean[M] + ard_log_mean[M]
-    const int M = a.M;
-    const int nval = (M + 31) & ~31;
-    const int slices = blockDim.x / nval;
-    const int v = threadIdx.x % nval, sl = threadIdx.x / nval;
-    double acc = 0.0;
-    if (v < M && sl < slices)
-        for (int l = sl; l < a.R; l += slices) acc += a.m2[(size_t)l * M + v] / a.S[(size_t)l * M + v];
-    if (sl < slices) sm[sl * nval + v] = acc;
+    if (rank == 0) {   // snapshot of the previous posterior, read by the ELBO / kept for inspection
+        for (int t = tid; t < M * 4; t += kMidThreads) a.primeB[t] = sPB[t];
+        for (int t = tid; t < M; t += kMidThreads) {
+            a.primeLogC[t] = sPLogC[t];
+            a.primeShape[t] = sPShape[t];
+            a.primeScale[t] = sPScale[t];
+        }
+    }
     __syncthreads();
-    double *s_mean = sm + slices * nval, *s_lmean = s_mean + M;
-    if (threadIdx.x < M) {
-        const int i = threadIdx.x;
+    // ---- step 3: a, m2, cm2 per (region, basis) (Stats.py:67-100); m2/S summed over my regions --------------
+    double accA = 0.0;
+    for (int cb = r0; cb < r1; cb += kMidChunk) {
+        const int nreg = (cb + kMidChunk < r1) ? kMidChunk : r1 - cb;
+        const int nitems = nreg * M;
+        for (int it = tid; it < nitems; it += kMidThreads) {
+            const int l = cb + it / M, i = it % M;
+            const size_t ri = (size_t)l * M + i;
+            const double c00 = sCov[i * 4 + 0], c01 = sCov[i * 4 + 1], c11 = sCov[i * 4 + 2];
+            const double y0 = a.ytil[ri * 2], y1 = a.ytil[ri * 2 + 1];
+            const double zeta = a.zeta[ri], prec = a.prec[ri];
+            const double cy0 = c00 * y0 + c01 * y1, cy1 = c01 * y0 + c11 * y1;
+            a.A_prev[ri * 2 + 0] = a.A[ri * 2 + 0];
+            a.A_prev[ri * 2 + 1] = a.A[ri * 2 + 1];
+            a.A[ri * 2 + 0] = zeta * cy0;
+            a.A[ri * 2 + 1] = zeta * cy1;
+            const double z2 = zeta * zeta;
+            const double m2 = 1.0 / prec + z2 * (y0 * cy0 + y1 * cy1);
+            const double ccy0 = c00 * cy0 + c01 * cy1, ccy1 = c01 * cy0 + c11 * cy1;
+            a.m2[ri] = m2;
+            a.cm2[ri] = 1.0 / prec + z2 * (y0 * (cy0 - ccy0) + y1 * (cy1 - ccy1));
+            sContrib[it] = m2 / a.S[ri];
+        }
+        __syncthreads();
+        if (tid < M)
+            for (int k = 0; k < nreg; ++k) accA += sContrib[k * M + tid];
+        __syncthreads();
+    }
+    // m2/S sums of my regions: finished (ARD, log omega_hat, omega) by k_omega off the critical path
+    if (tid < M) a.ardPartial[rank * M + tid] = accA;
+    cluster.sync();   // peers keep their shared memory alive until everybody has read the B sums
+}
+
+// ci, off the critical path (side stream): ARD posterior and moments from the per-CTA m2/S sums of
+// k_mid_ci (Posteriors.py:533-541, Stats.py:385-388), the log omega_hat table (Stats.py:405-412) and the
+// doubly-stochastic scaling omega (Stats.py:413-420) by the warm-up + Newton scheme of omega_solve_serial
+// (mrgp_math.cuh), one block of 256 threads, warp per matrix row / column.
+constexpr int kOmegaThreads = 256;
+
+__host__ __device__ inline size_t omega_smem_doubles(int M) { return (size_t)3 * M * M + 10 * M + 8; }
+
+__global__ void __launch_bounds__(kOmegaThreads) k_omega(RegionArgs a, int n_partials) {
+    extern __shared__ double sm[];
+    const int M = a.M, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kOmegaThreads / 32;
+    double *K = sm, *P = K + M * M, *S = P + M * M, *v = S + M * M, *c = v + M, *rhs = c + M, *dinv = rhs + M;
+    double *yv = dinv + M, *xv = yv + M, *s_mean = xv + M, *s_lmean = s_mean + M, *s_k = s_lmean + M, *red = s_k + M;
+    for (int t = tid; t < M * M; t += kOmegaThreads) P[t] = a.omega[t];   // the OLD omega mixes the ARD prior
+    __syncthreads();
+    if (tid < M) {
+        const int i = tid;
         double beta2 = 0.0;
-        for (int q = 0; q < slices; ++q) beta2 += sm[q * nval + i];
+        for (int q = 0; q < n_partials; ++q) beta2 += a.ardPartial[q * M + i];
         double sh = 0.0, sc = 0.0;
         for (int k = 0; k < M; ++k) {
-            const double w = a.omega[i * M + k];
+            const double w = P[i * M + k];
             sh += w * a.primeShape[k];
             sc += w * a.primeScale[k];
         }
@@ -664,121 +1018,116 @@ __global__ void __launch_bounds__(1024) k_ard(RegionArgs a) {
         a.ardLogMean[i] = lmean;
         s_mean[i] = mean;
         s_lmean[i] = lmean;
+        const double shp = a.primeShape[i], scp = a.primeScale[i];
+        s_k[i] = -a.primeLogC[i] + shp * log(scp) - lgamma(shp);   // the terms of log omega_hat that depend on k only
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < M * M; t += blockDim.x) {
+    for (int t = tid; t < M * M; t += kOmegaThreads) {
         const int i = t / M, k = t % M;
         const double *C = a.axCov + i * 4, *B = a.primeB + k * 4;
         const double tr = C[0] * B[0] + C[1] * B[2] + C[2] * B[1] + C[3] * B[3];   // trace(C_i B'_k)
-        const double shp = a.primeShape[k], scp = a.primeScale[k];
-        a.logOmegaHat[t] = tr - a.primeLogC[k] + shp * log(scp) - lgamma(shp) + (shp - 1.0) * s_lmean[i] - scp * s_mean[i];
-    }
-}
-
-// ci: omega = diag(alpha) exp(log_omega_hat) diag(beta) with unit row and column sums (Stats.py:413-420;
-// the reference solves the 2M log-scalings with MINPACK hybrd to xtol 1.5e-8, this is the fixed point
-// it approximates, by Sinkhorn iteration on the row-max-shifted kernel).  One block of 1024 threads =
-// 32 warps, warp w owns rows/columns w and w + 32 (M <= 64).
-__global__ void __launch_bounds__(1024) k_omega(RegionArgs a, int max_iter, double tol) {
-    extern __shared__ double sm[];   // K[M*M], u[M], v[M], err
-    const int M = a.M;
-    double *K = sm, *u = K + M * M, *vv = u + M, *flag = vv + M;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // shift by the row maxima, then by the column maxima of the result: every row and every column
-    // of K then holds an entry equal to 1 and nothing overflows or underflows to an empty line
-    for (int i = warp; i < M; i += 32) {
-        double mx = -INFINITY;
-        for (int k = lane; k < M; k += 32) mx = fmax(mx, a.logOmegaHat[i * M + k]);
-        mx = warp_max(mx);
-        for (int k = lane; k < M; k += 32) K[i * M + k] = a.logOmegaHat[i * M + k] - mx;
+        const double lw = tr + s_k[k] + (a.primeShape[k] - 1.0) * s_lmean[i] - a.primeScale[k] * s_mean[i];
+        a.logOmegaHat[t] = lw;
+        K[t] = lw;
     }
     __syncthreads();
-    for (int k = warp; k < M; k += 32) {
+    for (int i = warp; i < M; i += NW) {
+        double mx = -INFINITY;
+        for (int k = lane; k < M; k += 32) mx = fmax(mx, K[i * M + k]);
+        mx = warp_max(mx);
+        for (int k = lane; k < M; k += 32) K[i * M + k] -= mx;
+    }
+    __syncthreads();
+    for (int k = warp; k < M; k += NW) {
         double mx = -INFINITY;
         for (int i = lane; i < M; i += 32) mx = fmax(mx, K[i * M + k]);
         mx = warp_max(mx);
         for (int i = lane; i < M; i += 32) K[i * M + k] = exp(K[i * M + k] - mx);
     }
-    for (int t = threadIdx.x; t < M; t += blockDim.x) {
-        u[t] = 1.0;
-        vv[t] = 1.0;
-    }
+    if (tid < M) v[tid] = 1.0;
     __syncthreads();
-    for (int it = 0; it < max_iter; ++it) {
-        if (threadIdx.x == 0) *flag = 0.0;
-        __syncthreads();
-        // rows: u_i = 1 / sum_k K_ik v_k ; the deviation of the current row sums from 1 is the error
-        for (int i = warp; i < M; i += 32) {
+    int iters = 0;
+    double err_prev = INFINITY;
+    for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
+        ++iters;
+        for (int i = warp; i < M; i += NW) {
             double s = 0.0;
-            for (int k = lane; k < M; k += 32) s = fma(K[i * M + k], vv[k], s);
+            for (int k = lane; k < M; k += 32) s = fma(K[i * M + k], v[k], s);
             s = warp_sum(s);
-            if (lane == 0) {
-                const double e = fabs(u[i] * s - 1.0);
-                if (e > tol) *flag = 1.0;   // benign race: any writer sets the same value
-                u[i] = 1.0 / s;
+            const double u = 1.0 / s;
+            for (int k = lane; k < M; k += 32) P[i * M + k] = K[i * M + k] * v[k] * u;
+        }
+        __syncthreads();
+        for (int k = warp; k < M; k += NW) {
+            double s = 0.0;
+            for (int i = lane; i < M; i += 32) s += P[i * M + k];
+            s = warp_sum(s);
+            if (lane == 0) c[k] = s;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double e = 0.0;
+            for (int k = lane; k < M; k += 32) e = fmax(e, fabs(c[k] - 1.0));
+            e = warp_max(e);
+            if (lane == 0) red[0] = e;
+        }
+        __syncthreads();
+        const double err = red[0];
+        if (err < kOmegaTol) break;
+        if (it < kOmegaWarmup || !(err < err_prev)) {
+            if (tid < M) v[tid] /= c[tid];   // Sinkhorn column step
+            err_prev = (it < kOmegaWarmup) ? INFINITY : err;
+            __syncthreads();
+            continue;
+        }
+        err_prev = err;
+        for (int e = tid; e < M * M; e += kOmegaThreads) {
+            const int k = e / M, m = e % M;
+            if (m <= k) {
+                double s = 0.0;
+                for (int i = 0; i < M; ++i) s = fma(P[i * M + k], P[i * M + m], s);
+                S[e] = ((k == m) ? c[k] : 0.0) - s + 1.0 / (double)M;
             }
         }
+        if (tid < M) rhs[tid] = 1.0 - c[tid];
         __syncthreads();
-        const bool done = (it > 0) && (*flag == 0.0);
-        // columns: v_k = 1 / sum_i K_ik u_i
-        for (int k = warp; k < M; k += 32) {
-            double s = 0.0;
-            for (int i = lane; i < M; i += 32) s = fma(K[i * M + k], u[i], s);
-            s = warp_sum(s);
-            if (lane == 0) vv[k] = 1.0 / s;
+        for (int j = 0; j < M; ++j) {   // Cholesky, lower triangle in place, diagonal untouched, 1/l_jj aside
+            const double di = 1.0 / sqrt(S[j * M + j]);
+            if (tid > j && tid < M) S[tid * M + j] *= di;
+            if (tid == 0) dinv[j] = di;
+            __syncthreads();
+            const int w = M - j - 1;
+            for (int e = tid; e < w * w; e += kOmegaThreads) {
+                const int r = j + 1 + e / w, q = j + 1 + e % w;
+                if (q <= r) S[r * M + q] -= S[r * M + j] * S[q * M + j];
+            }
+            __syncthreads();
         }
+        for (int j = 0; j < M; ++j) {   // L y = rhs
+            const double yj = rhs[j] * dinv[j];
+            if (tid > j && tid < M) rhs[tid] -= S[tid * M + j] * yj;
+            if (tid == j) yv[j] = yj;
+            __syncthreads();
+        }
+        for (int j = M - 1; j >= 0; --j) {   // L^T x = y
+            const double xj = yv[j] * dinv[j];
+            if (tid < j) yv[tid] -= S[j * M + tid] * xj;
+            if (tid == j) xv[j] = xj;
+            __syncthreads();
+        }
+        if (tid < M) v[tid] *= exp(fmax(-30.0, fmin(30.0, xv[tid])));
         __syncthreads();
-        if (done) break;
     }
-    for (int t = threadIdx.x; t < M * M; t += blockDim.x) a.omega[t] = u[t / M] * K[t] * vv[t % M];
+    for (int t = tid; t < M * M; t += kOmegaThreads) a.omega[t] = P[t];
+    if (tid == 0) a.omegaIters[a.layer] = (double)iters;
 }
 
-// P4, P5, S5 for region-specific noise and bias (Posteriors.py:81-93, 132-148 (ci) / 396-412 (fi);
-// Stats.py:102-124).  One block of 128 threads per region: 16 slices x 8 values over the run partials.
+// Standalone bias / noise update (per-phase ABI entry; the sweep uses the fused tail of phase B).
 template <int DY>
-__global__ void k_bias_noise(RegionArgs a) {
-    __shared__ double sm[16 * 8];
-    const int r = blockIdx.x;
-    const int v = threadIdx.x & 7, sl = threadIdx.x >> 3;
-    double acc = 0.0;
-    if (v < DY + 3)
-        for (int q = a.region_run[r] + sl; q < a.region_run[r + 1]; q += 16) acc += a.part[(size_t)q * a.part_stride + v];
-    sm[sl * 8 + v] = acc;
-    __syncthreads();
-    if (threadIdx.x < 8) {
-        double t = 0.0;
-        for (int q = 0; q < 16; ++q) t += sm[q * 8 + threadIdx.x];
-        sm[threadIdx.x] = t;
-        if (threadIdx.x < DY + 3) a.sumsB[(size_t)r * (DY + 3) + threadIdx.x] = t;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const double n = (double)(a.offsets[r + 1] - a.offsets[r]);
-        const double bp0 = a.bias_prec0[r];
-        const double bp = bp0 + n;
-        double t3 = 0.0, t4 = 0.0;
-        for (int d = 0; d < DY; ++d) {
-            const double m0 = a.bias_mean0[(size_t)r * DY + d];
-            const double m = (1.0 / bp) * (m0 * bp0 + sm[d]);
-            a.bias_mean[(size_t)r * DY + d] = m;
-            t3 += m0 * m0;
-            t4 += m * m;
-        }
-        t3 *= bp0;
-        t4 *= bp;
-        // y_var: 1/noise_mean(old) for inferred targets, not multiplied by n in the ci regional/regional
-        // variant (Posteriors.py:138); fi targets are observations with y_var == 0 (LatentOutputs.py:11-18)
-        const double yvar = a.infer ? 1.0 / a.noise_mean[r] : 0.0;
-        const double shape = a.noise_shape0[r] + 0.5 * (double)DY * n;
-        const double scale = a.noise_scale0[r] + 0.5 * (t3 - t4 + sm[DY] + sm[DY + 1] + sm[DY + 2] + yvar);
-        a.yvar[r] = yvar;
-        a.bias_prec[r] = bp;
-        a.bias_var[r] = 1.0 / bp;
-        a.noise_shape[r] = shape;
-        a.noise_scale[r] = scale;
-        a.noise_mean[r] = shape / scale;
-        a.noise_log_mean[r] = digamma(shape) - log(scale);
-    }
+__global__ void __launch_bounds__(kThreadsB) k_bias_noise(StreamArgs p) {
+    int lpr = 32;
+    while (lpr > 1 && (kThreadsB / lpr) < p.R) lpr >>= 1;
+    bias_noise_all<DY>(p, lpr);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -98,21 +98,31 @@ MRGP_HD void saddle_point(const double *kappa, double &logc, double *rho) {
     for (int k = 1; k < P; ++k) mn = fmin(mn, -kappa[k]);
     const double adjust = 0.1 - mn;
     for (int k = 0; k < P; ++k) lam[k] = -kappa[k] + adjust;
-    double t = 0.1 - 0.5;
-    for (int it = 0; it < 60; ++it) {
-        double f = -1.0, fp = 0.0;
-        for (int k = 0; k < P; ++k) {
-            const double r = 1.0 / (lam[k] - t);
-            f += 0.5 * r;
-            fp += 0.5 * r * r;
+    double t;
+    if (P == 2) {
+        // closed form of 1/2 (1/(u + a0) + 1/(u + a1)) = 1 with u = 0.1 - t, a_k = lam_k - 0.1 >= 0:
+        // u = 1/2 [1 - (a0 + a1) + sqrt(1 + (a0 - a1)^2)], written without cancellation for a large gap
+        const double a0 = lam[0] - 0.1, a1 = lam[P - 1] - 0.1;
+        const double amin = fmin(a0, a1), gap = fabs(a0 - a1);
+        const double u = 0.5 * (1.0 - 2.0 * amin + 1.0 / (sqrt(1.0 + gap * gap) + gap));
+        t = 0.1 - u;
+    } else {
+        t = 0.1 - 0.5;
+        for (int it = 0; it < 60; ++it) {
+            double f = -1.0, fp = 0.0;
+            for (int k = 0; k < P; ++k) {
+                const double r = 1.0 / (lam[k] - t);
+                f += 0.5 * r;
+                fp += 0.5 * r * r;
+            }
+            const double step = f / fp;
+            const double tn = t - step;
+            if (!(fabs(step) > 1e-17 * fabs(t)) || tn >= t) {
+                t = (tn < t) ? tn : t;
+                break;
+            }
+            t = tn;
         }
-        const double step = f / fp;
-        const double tn = t - step;
-        if (!(fabs(step) > 1e-17 * fabs(t)) || tn >= t) {
-            t = (tn < t) ? tn : t;
-            break;
-        }
-        t = tn;
     }
     double k2 = 0.0, k3 = 0.0, sumlog = 0.0;
     double r1[P];
@@ -188,6 +198,90 @@ MRGP_HD void bingham2(double a, double b, double c, Bingham2 &out) {
     out.cov[1] = out.rho[0] * p01 - out.rho[1] * p01;
     out.cov[2] = out.rho[0] * p11 + out.rho[1] * (1.0 - p11);
     out.n_chol = n_chol;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Permutation-alignment weights (Stats.py:390-445): omega = diag(alpha) exp(lw) diag(beta) with unit row and
+// column sums.  The reference finds the 2M log-scalings with MINPACK hybrd (xtol 1.5e-8); this is the
+// fixed point that call approximates.  Serial statement of the algorithm that k_omega runs with one block:
+//   1. shift lw by its row maxima, then by the column maxima of the result (every row and column of K
+//      holds an entry 1: no overflow, no empty line), K = exp(shifted);
+//   2. a few Sinkhorn sweeps (rows, columns) as a warm-up;
+//   3. Newton on the column scalings v with the rows normalised exactly:
+//        P_ik = K_ik v_k / sum_k' K_ik' v_k',  c = P^T 1,  (diag(c) - P^T P + 11^T/M) delta = 1 - c,
+//        v_k <- v_k exp(delta_k)
+//      (the Hessian of the convex dual, singular only along 1, fixed by the rank-one term); a Sinkhorn
+//      column step replaces the Newton step whenever the residual did not decrease.
+// Sinkhorn alone needs hundreds of sweeps on the peaked matrices of the fine layers; Newton needs < 10.
+// work: K[M*M], P[M*M], S[M*M], v[M], c[M], rhs[M], dinv[M]
+// ------------------------------------------------------------------------------------------------
+constexpr int kOmegaWarmup = 6;
+constexpr int kOmegaMaxNewton = 40;
+constexpr double kOmegaTol = 1e-13;
+
+inline int omega_solve_serial(const double *lw, int M, double *omega, double *K, double *P, double *S, double *v,
+                              double *c, double *rhs, double *dinv) {
+    for (int i = 0; i < M; ++i) {
+        double mx = -INFINITY;
+        for (int k = 0; k < M; ++k) mx = fmax(mx, lw[i * M + k]);
+        for (int k = 0; k < M; ++k) K[i * M + k] = lw[i * M + k] - mx;
+    }
+    for (int k = 0; k < M; ++k) {
+        double mx = -INFINITY;
+        for (int i = 0; i < M; ++i) mx = fmax(mx, K[i * M + k]);
+        for (int i = 0; i < M; ++i) K[i * M + k] = exp(K[i * M + k] - mx);
+        v[k] = 1.0;
+    }
+    int iters = 0;
+    double err_prev = INFINITY;
+    for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
+        ++iters;
+        for (int i = 0; i < M; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < M; ++k) s = fma(K[i * M + k], v[k], s);
+            const double u = 1.0 / s;
+            for (int k = 0; k < M; ++k) P[i * M + k] = K[i * M + k] * v[k] * u;
+        }
+        double err = 0.0;
+        for (int k = 0; k < M; ++k) {
+            double s = 0.0;
+            for (int i = 0; i < M; ++i) s += P[i * M + k];
+            c[k] = s;
+            err = fmax(err, fabs(s - 1.0));
+        }
+        if (err < kOmegaTol) break;
+        if (it < kOmegaWarmup || !(err < err_prev)) {
+            for (int k = 0; k < M; ++k) v[k] /= c[k];   // Sinkhorn column step
+            err_prev = (it < kOmegaWarmup) ? INFINITY : err;
+            continue;
+        }
+        err_prev = err;
+        for (int k = 0; k < M; ++k)
+            for (int m = 0; m <= k; ++m) {
+                double s = 0.0;
+                for (int i = 0; i < M; ++i) s = fma(P[i * M + k], P[i * M + m], s);
+                S[k * M + m] = ((k == m) ? c[k] : 0.0) - s + 1.0 / (double)M;
+            }
+        for (int k = 0; k < M; ++k) rhs[k] = 1.0 - c[k];
+        for (int j = 0; j < M; ++j) {   // Cholesky, lower triangle in place (diagonal kept, 1/l_jj aside)
+            const double d = sqrt(S[j * M + j]);
+            dinv[j] = 1.0 / d;
+            for (int i = j + 1; i < M; ++i) S[i * M + j] *= dinv[j];
+            for (int r = j + 1; r < M; ++r)
+                for (int q = j + 1; q <= r; ++q) S[r * M + q] -= S[r * M + j] * S[q * M + j];
+        }
+        for (int j = 0; j < M; ++j) {
+            rhs[j] *= dinv[j];
+            for (int i = j + 1; i < M; ++i) rhs[i] -= S[i * M + j] * rhs[j];
+        }
+        for (int j = M - 1; j >= 0; --j) {
+            rhs[j] *= dinv[j];
+            for (int i = 0; i < j; ++i) rhs[i] -= S[j * M + i] * rhs[j];
+        }
+        for (int k = 0; k < M; ++k) v[k] *= exp(fmax(-30.0, fmin(30.0, rhs[k])));
+    }
+    for (int t = 0; t < M * M; ++t) omega[t] = P[t];
+    return iters;
 }
 
 // Basis angle: theta = pi (x + L)/(2L) = pi (u + 1/2), u = x / (2L)  (KernelClass.py:31-35), so

@@ -86,7 +86,8 @@ enum {
     MRGP_F_ARD_MEAN = 47,       /* ([R,] M)                                                          */
     MRGP_F_ARD_LOG_MEAN = 48,   /* ([R,] M)                                                          */
     MRGP_F_OMEGA = 49,          /* (M, M)    ci only, Stats.py:369, 390-420                          */
-    MRGP_F_LOG_OMEGA_HAT = 50   /* (M, M)    ci only, Stats.py:405-412 (last evaluation)             */
+    MRGP_F_LOG_OMEGA_HAT = 50,  /* (M, M)    ci only, Stats.py:405-412 (last evaluation)             */
+    MRGP_F_OMEGA_ITERS = 51     /* (J,)      ci only: scaling iterations of the last omega solve per layer */
 };
 
 typedef struct mrgp_handle mrgp_handle;

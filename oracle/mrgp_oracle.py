@@ -17,6 +17,8 @@ Every function cites the reference file:line it follows.  Regions of a layer are
 ranges (IndexSetGenerator.py:51-92 only ever builds `list(range(a, b))`), so a layer is described by an
 int64 offsets array of length R+1 and per-region sums are `np.add.reduceat`.
 """
+import time
+
 import numpy as np
 from numpy import linalg as la
 from scipy.optimize import brentq, fminbound, fsolve
@@ -275,6 +277,7 @@ class OracleMRGP(object):
         self.omega_solver = omega_solver
         self.adaptive = None if mode == 'fi' else adaptive  # MRGP.py:108-109
         self.n_chol = 0
+        self.t_omega = 0.0   # seconds spent in the permutation-weight solver (bench.py reports it)
         # MRGP.py:278-295
         ref = x if full_x is None else np.asarray(full_x, dtype=np.float64)
         if standard_normalized_inputs:
@@ -525,7 +528,9 @@ class OracleMRGP(object):
             # Stats.py:390-420
             lw = log_omega_hat(pB, pLogC, pShape, pScale, sh.axis_cov, sh.ard_log_mean, sh.ard_mean)
             sh.log_omega_hat = lw
+            _t0 = time.perf_counter()
             sh.omega = omega_fsolve(lw) if self.omega_solver == 'fsolve' else omega_sinkhorn(lw)
+            self.t_omega += time.perf_counter() - _t0
             self._bias_noise(ly, y, y_var)
             if self.adaptive is not None:
                 self._learn_intervals(ly, j, y, sh.ard_mean)  # MRGP.py:632-641
