@@ -69,6 +69,8 @@ SIGNATURES = {
     'mrgp_cholesky_count': (C.c_int64, [_P]),
     'mrgp_batched_cholesky': (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P]),
     'mrgp_fp64_probe': (C.c_int, [_P, C.c_int64, _P, C.POINTER(C.c_float)]),
+    'mrgp_timeline_enable': (C.c_int, [_P, C.c_int32]),
+    'mrgp_timeline_read': (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_int32]),
     'mrgp_plan_info': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'mrgp_plan_segments': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64)]),
     'mrgp_host_digamma': (C.c_double, [C.c_double]),

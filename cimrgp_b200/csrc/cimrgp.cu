@@ -54,7 +54,7 @@ struct LayerDev {
 struct SharedDev {
     double *axB = nullptr, *axKappa = nullptr, *axRho = nullptr, *axLogC = nullptr, *axCov = nullptr;
     double *ardShape = nullptr, *ardScale = nullptr, *ardMean = nullptr, *ardLogMean = nullptr;
-    double *omega = nullptr, *logOmegaHat = nullptr, *omegaIters = nullptr, *ardPartial = nullptr;
+    double *omega = nullptr, *logOmegaHat = nullptr, *omegaIters = nullptr, *ardPartial = nullptr, *omegaEta = nullptr, *omegaWarm = nullptr;
     double *primeB = nullptr, *primeLogC = nullptr, *primeShape = nullptr, *primeScale = nullptr;
     double *priorB = nullptr, *priorLogC = nullptr, *priorShape = nullptr, *priorScale = nullptr;
 };
@@ -80,7 +80,7 @@ struct mrgp_handle {
     size_t off_total = 0;
     int32_t part_stride = 0, max_runs = 0;
     unsigned long long *chol_count = nullptr;
-    unsigned int *done_counter = nullptr;
+    unsigned int *done_counter = nullptr, *mid_sync = nullptr;
     cudaStream_t stream = nullptr, side = nullptr;
     bool own_stream = false;
     std::vector<cudaEvent_t> ev_fork, ev_join;
@@ -88,6 +88,8 @@ struct mrgp_handle {
     cudaGraphExec_t graph_exec = nullptr;
     int64_t launches = 0, launches_per_sweep = 0, sweeps_done = 0;
     bool capturing = false;
+    bool timeline = false;
+    unsigned long long *ts = nullptr;   // (kMaxLayers * 4) x {begin, end} global-timer stamps
     double fi_shape0_mix = 0.0, fi_scale0_mix = 0.0;
     std::string err;
 };
@@ -210,6 +212,8 @@ size_t carve(mrgp_handle *h, char *base) {
     h->off_staging = c.take<int64_t>(h->off_total);
     h->chol_count = c.take<unsigned long long>(1);
     h->done_counter = c.take<unsigned int>(1);
+    h->mid_sync = c.take<unsigned int>(2 * kMaxLayers);
+    h->ts = c.take<unsigned long long>(kMaxLayers * 8);
     for (int j = 0; j < J; ++j) {
         const LayerPlan &lp = h->plan[j];
         LayerDev &d = h->dev[j];
@@ -244,7 +248,7 @@ size_t carve(mrgp_handle *h, char *base) {
         d.bias_var = c.take<double>(R);
         d.yvar = c.take<double>(R);
         d.sumsB = c.take<double>(R * (DY + 3));
-        d.bcontrib = c.take<double>(RM * 3);
+        d.bcontrib = c.take<double>(std::max<size_t>(RM * 3, 32 * 96));
         if (fi) {
             d.axB = c.take<double>(RM * DY * DY);
             d.axKappa = c.take<double>(RM * DY);
@@ -270,7 +274,9 @@ size_t carve(mrgp_handle *h, char *base) {
     s.omega = c.take<double>((size_t)M * M);
     s.logOmegaHat = c.take<double>((size_t)M * M);
     s.omegaIters = c.take<double>(kMaxLayers);
-    s.ardPartial = c.take<double>((size_t)8 * M);
+    s.ardPartial = c.take<double>((size_t)256 * M);
+    s.omegaEta = c.take<double>((size_t)kMaxLayers * 64);
+    s.omegaWarm = c.take<double>(kMaxLayers);
     s.primeB = c.take<double>((size_t)M * DY * DY);
     s.primeLogC = c.take<double>(M);
     s.primeShape = c.take<double>(M);
@@ -310,6 +316,8 @@ StreamArgs stream_args(mrgp_handle *h, int j) {
     a.R = h->plan[j].R;
     a.infer = (h->cfg.mode == MRGP_MODE_CI && j > 0) ? 1 : 0;
     a.fuse_tail = 0;
+    a.layer = j;
+    a.ts = h->timeline ? h->ts : nullptr;
     a.bias_prec0 = d.bias_prec0;
     a.bias_mean0 = d.bias_mean0;
     a.noise_shape0 = d.noise_shape0;
@@ -393,6 +401,8 @@ RegionArgs region_args(mrgp_handle *h, int j) {
     a.logOmegaHat = s.logOmegaHat;
     a.omegaIters = s.omegaIters;
     a.ardPartial = s.ardPartial;
+    a.omegaEta = s.omegaEta;
+    a.omegaWarm = s.omegaWarm;
     a.primeB = s.primeB;
     a.primeLogC = s.primeLogC;
     a.primeShape = s.primeShape;
@@ -402,6 +412,7 @@ RegionArgs region_args(mrgp_handle *h, int j) {
     a.priorShape = s.priorShape;
     a.priorScale = s.priorScale;
     a.chol_count = h->chol_count;
+    a.ts = h->timeline ? h->ts : nullptr;
     a.fi_shape0_mix = h->fi_shape0_mix;
     a.fi_scale0_mix = h->fi_scale0_mix;
     a.use_prior = d.use_prior;
@@ -416,9 +427,13 @@ RegionArgs region_args(mrgp_handle *h, int j) {
 // ---- kernel dispatch ----------------------------------------------------------------------------
 constexpr size_t kRedSmemBytes = kRedSmemDoubles * sizeof(double);
 
+// Every kernel of the sweep asks for the same (maximum) shared-memory carveout: switching the L1 / shared split
+// between consecutive kernels drains and reconfigures the SMs, which costs more than the small kernels run.
 template <typename K>
 cudaError_t set_smem(K kernel, size_t bytes) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 1));
 }
 
 template <int M>
@@ -543,6 +558,7 @@ int do_axis_update(mrgp_handle *h, int j, bool fork_omega) {
         const int threads = std::max(reduce_threads(nv, max_region_runs(lp), 512), ((M + 31) & ~31));
         const int slices = threads / nval;
         const size_t smem = (size_t)(slices * nval + nv) * sizeof(double);
+        CK(set_smem(k_reduce_scale<2>, smem));
         k_reduce_scale<2><<<lp.R, threads, smem, h->stream>>>(a);
         CK(cudaGetLastError());
         count(h);
@@ -557,31 +573,21 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega) {
     if (fork_omega && j > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_join[j - 1], 0));
     int n_partials = 1;
     {
-        const int items = lp.R * M;
-        int nc = std::min(8, std::max(1, (items + kMidThreads - 1) / kMidThreads));
-        nc = std::min(nc, lp.R);
-        int lpi = 1;
         const int mr = max_region_runs(lp);
-        while (lpi < 32 && lpi * 2 * items <= nc * kMidThreads && lpi < mr) lpi *= 2;
-        const int rpc = (lp.R + nc - 1) / nc;
-        nc = (lp.R + rpc - 1) / rpc;
-        const size_t smem = mid_smem_doubles(M) * sizeof(double);
+        int nb = std::min(48, lp.R);
+        const int rpc = (lp.R + nb - 1) / nb;
+        nb = (lp.R + rpc - 1) / rpc;
+        const int items_cta = std::min(rpc, 32) * M;
+        int lpi = 1;
+        while (lpi < 32 && lpi * 2 <= mr && lpi * 2 * items_cta <= kMidThreads) lpi *= 2;
+        const size_t smem = (size_t)(std::max(std::max(32 * M * 4 + 96, M * M + 4 * M + 3 * 96), 37 * M)) * sizeof(double);
         CK(set_smem(k_mid_ci<2>, smem));
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(nc);
-        cfg.blockDim = dim3(kMidThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = h->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = nc;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&cfg, k_mid_ci<2>, a, lpi, rpc));
+        int rpc_arg = rpc;
+        unsigned int *sync_words = h->mid_sync + 2 * j;
+        void *args[] = {&a, &lpi, &rpc_arg, &sync_words};
+        CK(cudaLaunchCooperativeKernel((const void *)k_mid_ci<2>, dim3(nb), dim3(kMidThreads), args, smem, h->stream));
         count(h);
-        n_partials = nc;
+        n_partials = nb;
     }
     {
         cudaStream_t st = h->stream;
@@ -591,6 +597,7 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega) {
             st = h->side;
         }
         const size_t smem = omega_smem_doubles(M) * sizeof(double);
+        CK(set_smem(k_omega, smem));
         k_omega<<<1, kOmegaThreads, smem, st>>>(a, n_partials);
         CK(cudaGetLastError());
         count(h);
@@ -852,6 +859,7 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
     }
     CK(cudaMemsetAsync(h->chol_count, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->done_counter, 0, sizeof(unsigned int), h->stream));
+    CK(cudaMemsetAsync(h->mid_sync, 0, 2 * kMaxLayers * sizeof(unsigned int), h->stream));
     CK(cudaMemsetAsync(h->g, 0, (size_t)h->cfg.n_samples * h->cfg.dy * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->hvar, 0, (size_t)h->cfg.n_samples * sizeof(double), h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -971,6 +979,7 @@ int mrgp_init_state(mrgp_handle *h, double noise_var0, double ard_prior_influenc
     }
     CK(cudaMemsetAsync(h->g, 0, (size_t)h->cfg.n_samples * h->cfg.dy * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->hvar, 0, (size_t)h->cfg.n_samples * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->sh.omegaWarm, 0, kMaxLayers * sizeof(double), h->stream));
     drop_graph(h);
     h->sweeps_done = 0;
     h->state_init = true;
@@ -1194,6 +1203,44 @@ int mrgp_fp64_probe(void *cuda_stream, int64_t iters, double *sink_dev, float *m
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return MRGP_OK;
+}
+
+// Debug aid (not part of the reference-facing surface): per-kernel completion times of one sweep.
+// mrgp_timeline_enable(h, 1) before the first mrgp_sweep() makes the captured graph carry timing events;
+// mrgp_timeline_read() returns (tag, ms since sweep start) pairs: tag 1 phase A, 2 mid-step, 3 phase B, 4 omega.
+int mrgp_timeline_enable(mrgp_handle *h, int32_t on) {
+    if (!h) return MRGP_EINVAL;
+    h->timeline = on != 0;
+    drop_graph(h);
+    return MRGP_OK;
+}
+
+int mrgp_timeline_read(mrgp_handle *h, int32_t *tags, float *ms, int32_t cap) {
+    // Runs one sweep with fresh stamps and returns, per kernel in issue order, its begin and end in ms relative to
+    // the earliest begin: tags[k] = layer * 4 + kind (0 phase A, 1 mid-step, 2 phase B, 3 omega), ms[2k], ms[2k+1].
+    if (!h || !tags || !ms || !h->timeline) return MRGP_EINVAL;
+    const int n = h->cfg.n_layers * 4;
+    if (cap < n) return MRGP_EINVAL;
+    std::vector<unsigned long long> init((size_t)kMaxLayers * 8), got((size_t)kMaxLayers * 8);
+    for (size_t k = 0; k < init.size(); k += 2) {
+        init[k] = ~0ull;
+        init[k + 1] = 0ull;
+    }
+    CK(cudaMemcpyAsync(h->ts, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+    int rc = mrgp_sweep(h, 1);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(got.data(), h->ts, got.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned long long t0 = ~0ull;
+    for (int k = 0; k < n; ++k)
+        if (got[2 * k + 1] != 0ull) t0 = std::min(t0, got[2 * k]);
+    for (int k = 0; k < n; ++k) {
+        tags[k] = k;
+        const bool ran = got[2 * k + 1] != 0ull;
+        ms[2 * k] = ran ? (float)((got[2 * k] - t0) * 1e-6) : -1.f;
+        ms[2 * k + 1] = ran ? (float)((got[2 * k + 1] - t0) * 1e-6) : -1.f;
+    }
+    return n;
 }
 
 // ---- host-only hooks ----------------------------------------------------------------------------

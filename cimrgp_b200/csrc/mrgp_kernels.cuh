@@ -18,6 +18,20 @@
 
 namespace mrgp {
 
+// Debug timeline: when `ts` is non-null every kernel of the sweep stamps the global timer at the entry of its
+// first-scheduled CTA (min) and at the exit of every CTA (max) into slot (layer * 4 + kind).
+__device__ __forceinline__ unsigned long long global_timer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void ts_begin(unsigned long long *ts, int slot) {
+    if (ts && threadIdx.x == 0) atomicMin(&ts[slot * 2], global_timer());
+}
+__device__ __forceinline__ void ts_end(unsigned long long *ts, int slot) {
+    if (ts && threadIdx.x == 0) atomicMax(&ts[slot * 2 + 1], global_timer());
+}
+
 constexpr int kThreads = 256;      // streaming CTA size (8 warps)
 constexpr int kPartBStride = 8;    // doubles per phase-B partial (dy + 3 <= 8)
 constexpr int kRedChunk = 32;      // values reduced per block_reduce round
@@ -57,7 +71,8 @@ struct StreamArgs {
     unsigned int *done_counter;
     const int32_t *region_run;   // (R + 1)
     const int64_t *offsets;      // (R + 1)
-    int32_t R, infer, fuse_tail;
+    int32_t R, infer, fuse_tail, layer;
+    unsigned long long *ts;
     const double *bias_prec0, *bias_mean0, *noise_shape0, *noise_scale0;
     double *bias_mean_out, *bias_prec, *bias_var, *noise_shape, *noise_scale, *noise_mean, *noise_log_mean, *yvar, *sumsB;
 };
@@ -67,22 +82,28 @@ struct StreamArgs {
 // ------------------------------------------------------------------------------------------------
 
 // Sum NV per-thread values over the 256 threads of the block, fixed order; out[v] written by warp 0.
-template <int NV>
+template <int NV, bool NAMED = false>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *red, double *out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *part = red + kRedChunk * kThreads;
+    auto sync = [] {
+        if (NAMED)
+            compute_sync<kThreads>();
+        else
+            __syncthreads();
+    };
 #pragma unroll
     for (int c = 0; c < (NV + kRedChunk - 1) / kRedChunk; ++c) {
-        __syncthreads();
+        sync();
 #pragma unroll
         for (int k = 0; k < kRedChunk; ++k)
             if (c * kRedChunk + k < NV) red[k * kThreads + tid] = v[c * kRedChunk + k];
-        __syncthreads();
+        sync();
         double s = 0.0;
 #pragma unroll 8
         for (int k = 0; k < 32; ++k) s += red[lane * kThreads + warp * 32 + ((k + lane) & 31)];
         part[warp * 32 + lane] = s;
-        __syncthreads();
+        sync();
         if (tid < 32 && c * kRedChunk + tid < NV) {
             double t = 0.0;
 #pragma unroll
@@ -105,16 +126,22 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 // Few values (NV <= 8): shuffle inside the warp, then across the 8 warps through shared memory.
-template <int NV, bool MAX, int NT = kThreads>
+template <int NV, bool MAX, int NT = kThreads, bool NAMED = false>
 __device__ __forceinline__ void block_reduce_small(double (&v)[NV], double *sm /* >= (NT/32)*8 */, double *out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __syncthreads();
+    auto sync = [] {
+        if (NAMED)
+            compute_sync<NT>();
+        else
+            __syncthreads();
+    };
+    sync();
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         const double s = MAX ? warp_max(v[k]) : warp_sum(v[k]);
         if (lane == 0) sm[warp * 8 + k] = s;
     }
-    __syncthreads();
+    sync();
     if (tid < NV) {
         double t = sm[tid];
 #pragma unroll
@@ -219,9 +246,9 @@ __device__ __forceinline__ void bias_noise_region(const StreamArgs &p, int r, co
 
 // All regions of the layer by one block: `lpr` lanes (power of two <= 32) share the run loop of a region,
 // the lane sums are combined by shuffles in a fixed order.
-template <int DY>
+template <int DY, int NT>
 __device__ __forceinline__ void bias_noise_all(const StreamArgs &p, int lpr) {
-    const int groups = blockDim.x / lpr;
+    const int groups = NT / lpr;
     const int grp = threadIdx.x / lpr, sl = threadIdx.x % lpr;
     for (int base = 0; base < p.R; base += groups) {
         const int r = base + grp;
@@ -253,7 +280,7 @@ __device__ __forceinline__ void bias_noise_all(const StreamArgs &p, int lpr) {
 constexpr int kS = 4;
 constexpr int kTile = kThreads * kS;
 constexpr int kStages = 3;
-constexpr int kThreadsB = 512;              // phase B: 16 warps, kSB samples per thread (same tile)
+constexpr int kThreadsB = 256;              // phase B block size, kSB samples per thread (same tile)
 constexpr int kSB = kTile / kThreadsB;
 
 template <int DY, bool NEED_Y, bool NEED_G, bool NEED_H>
@@ -285,6 +312,31 @@ __device__ __forceinline__ void issue_tile(const StreamArgs &p, double *stage, u
     if (NEED_G) bulk_g2s(stage + L::kG, p.g + start * DY, (uint32_t)cnt * DY * 8u, bar);
 }
 
+// Lane 0 of warp 0 feeds the pipeline: before it starts tile t it issues every tile up to t + kStages - 1
+// whose stage has been released by all compute warps (non-blocking probe of the stage's "empty" barrier) and
+// blocks only for tile t itself.  No warp ever waits at a CTA-wide barrier between tiles, so the warps drift
+// apart by up to kStages - 1 tiles and the latency-bound parts of one warp (sincospi, epilogue) overlap the
+// FMA streams of the others.
+template <int DY, bool NEED_Y, bool NEED_G, bool NEED_H>
+__device__ __forceinline__ void refill(const StreamArgs &p, double *stages, uint64_t *full_bar, uint64_t *empty_bar, int &next_issue,
+                                       int t, int n_tiles, int64_t c0, int64_t c1) {
+    using L = TileLayout<DY, NEED_Y, NEED_G, NEED_H>;
+    while (next_issue < n_tiles && next_issue < t + kStages) {
+        const int stage = next_issue % kStages;
+        if (next_issue >= kStages) {
+            const uint32_t parity = (uint32_t)(((next_issue / kStages) - 1) & 1);
+            if (next_issue == t)
+                mbar_wait(&empty_bar[stage], parity);
+            else if (!mbar_test(&empty_bar[stage], parity))
+                break;
+        }
+        const int64_t start = c0 + (int64_t)next_issue * kTile;
+        const int cnt = (int)((c1 - start < kTile) ? c1 - start : kTile);
+        issue_tile<DY, NEED_Y, NEED_G, NEED_H>(p, stages + stage * L::kDoubles, &full_bar[stage], start, cnt);
+        ++next_issue;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Phase A: T[i][d] = sum_n phi_i(n) r_d(n),  r = y - (fbar + b + Phi A_old^T)
 //   INFER  : targets are the layer's own prediction Phi A_old^T + (b_old + fbar)   (ci, j > 0;
@@ -295,8 +347,8 @@ __device__ __forceinline__ void issue_tile(const StreamArgs &p, double *stage, u
 // once for Phi^T r) instead of being kept in registers: 30 extra FMAs buy kS samples in flight.
 // ------------------------------------------------------------------------------------------------
 template <int DY, int M, int SB, bool INFER, bool LATENT>
-__device__ __forceinline__ void phase_a_block(double (&T)[M * DY], const double *st, int k0, int64_t tile_lo, int64_t pos,
-                                              int64_t hi, const double *sA, double inv2L, double rs, const double (&b)[DY],
+__device__ __forceinline__ void phase_a_block(double (&T)[M * DY], const double *st, int k0, int lo_rel, int hi_rel,
+                                              const double *sA, double inv2L, double rs, const double (&b)[DY],
                                               const double (&pb)[DY]) {
     using L = TileLayout<DY, !INFER, LATENT, false>;
     asm volatile("" ::: "memory");   // keep the region coefficients in shared memory, not in registers
@@ -305,8 +357,7 @@ __device__ __forceinline__ void phase_a_block(double (&T)[M * DY], const double 
 #pragma unroll
     for (int q = 0; q < SB; ++q) {
         const int idx = (k0 + q) * kThreads + threadIdx.x;
-        const int64_t n = tile_lo + idx;
-        act[q] = n >= pos && n < hi;
+        act[q] = idx >= lo_rel && idx < hi_rel;
         const double x = act[q] ? st[L::kX + idx] : 0.0;
         basis_seed(x, inv2L, act[q] ? rs : 0.0, f1[q], c2[q]);
         f[q] = f1[q];
@@ -359,29 +410,29 @@ __device__ __forceinline__ void phase_a_block(double (&T)[M * DY], const double 
 template <int DY, int M, bool INFER, bool LATENT>
 __global__ void __launch_bounds__(kThreads, 1) k_phase_a(StreamArgs p) {
     using L = TileLayout<DY, !INFER, LATENT, false>;
+    constexpr int NCW = kThreads / 32;
     extern __shared__ __align__(128) double dsm[];
     double *stages = dsm;
     double *red = dsm + kStages * L::kDoubles;
-    __shared__ double sA[M * DY];
-    __shared__ double sScal[2 + 2 * DY];
-    __shared__ __align__(8) uint64_t bars[kStages];
-    const int tid = threadIdx.x;
+    __shared__ double sA_all[NCW][M * DY];   // region coefficients, one private copy per warp
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t c0 = (int64_t)blockIdx.x * p.cta_quantum;
     const int64_t c1 = (c0 + p.cta_quantum < p.n_samples) ? c0 + p.cta_quantum : p.n_samples;
     const int n_tiles = (c1 > c0) ? (int)((c1 - c0 + kTile - 1) / kTile) : 0;
+    ts_begin(p.ts, p.layer * 4 + 0);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NCW);
+        }
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int t = 0; t < kStages && t < n_tiles; ++t) {
-            const int64_t start = c0 + (int64_t)t * kTile;
-            const int cnt = (int)((c1 - start < kTile) ? c1 - start : kTile);
-            issue_tile<DY, !INFER, LATENT, false>(p, stages + t * L::kDoubles, &bars[t], start, cnt);
-        }
-    }
+    int next_issue = 0;
+    double *sA = sA_all[warp];
     double T[M * DY];
 #pragma unroll
     for (int i = 0; i < M * DY; ++i) T[i] = 0.0;
@@ -396,30 +447,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_phase_a(StreamArgs p) {
     for (int t = 0; t < n_tiles; ++t) {
         const int stage = t % kStages;
         const double *st = stages + stage * L::kDoubles;
-        mbar_wait(&bars[stage], (uint32_t)((t / kStages) & 1));
+        if (tid == 0) refill<DY, !INFER, LATENT, false>(p, stages, full_bar, empty_bar, next_issue, t, n_tiles, c0, c1);
+        mbar_wait(&full_bar[stage], (uint32_t)((t / kStages) & 1));
         const int64_t tile_lo = c0 + (int64_t)t * kTile;
         const int64_t tile_hi = (tile_lo + kTile < c1) ? tile_lo + kTile : c1;
         int64_t pos = tile_lo;
         while (pos < tile_hi) {
             if (loaded != s) {
-                __syncthreads();
-                if (tid < M * DY) sA[tid] = p.A[(size_t)sg.region * (M * DY) + tid];
-                if (tid == 0) {
-                    sScal[0] = p.inv2L[sg.region];
-                    sScal[1] = p.rsqrtL[sg.region];
-                }
-                if (tid < DY) {
-                    sScal[2 + tid] = p.bias[(size_t)sg.region * DY + tid];
-                    sScal[2 + DY + tid] = LATENT ? p.pbias[(size_t)sg.parent * DY + tid] : 0.0;
-                }
-                __syncthreads();
-                inv2L = sScal[0];
-                rs = sScal[1];
+                __syncwarp();
+                for (int q = lane; q < M * DY; q += 32) sA[q] = p.A[(size_t)sg.region * (M * DY) + q];
+                inv2L = p.inv2L[sg.region];
+                rs = p.rsqrtL[sg.region];
 #pragma unroll
                 for (int d = 0; d < DY; ++d) {
-                    b[d] = sScal[2 + d];
-                    pb[d] = sScal[2 + DY + d];
+                    b[d] = p.bias[(size_t)sg.region * DY + d];
+                    pb[d] = LATENT ? p.pbias[(size_t)sg.parent * DY + d] : 0.0;
                 }
+                __syncwarp();
                 loaded = s;
             }
             const int64_t seg_end = sg.start + sg.len;
@@ -430,20 +474,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_phase_a(StreamArgs p) {
             while (ka <= kb) {
                 const int left = kb - ka + 1;
                 if (left >= 4) {
-                    phase_a_block<DY, M, 4, INFER, LATENT>(T, st, ka, tile_lo, pos, hi, sA, inv2L, rs, b, pb);
+                    phase_a_block<DY, M, 4, INFER, LATENT>(T, st, ka, (int)(pos - tile_lo), (int)(hi - tile_lo), sA, inv2L, rs, b, pb);
                     ka += 4;
                 } else if (left >= 2) {
-                    phase_a_block<DY, M, 2, INFER, LATENT>(T, st, ka, tile_lo, pos, hi, sA, inv2L, rs, b, pb);
+                    phase_a_block<DY, M, 2, INFER, LATENT>(T, st, ka, (int)(pos - tile_lo), (int)(hi - tile_lo), sA, inv2L, rs, b, pb);
                     ka += 2;
                 } else {
-                    phase_a_block<DY, M, 1, INFER, LATENT>(T, st, ka, tile_lo, pos, hi, sA, inv2L, rs, b, pb);
+                    phase_a_block<DY, M, 1, INFER, LATENT>(T, st, ka, (int)(pos - tile_lo), (int)(hi - tile_lo), sA, inv2L, rs, b, pb);
                     ka += 1;
                 }
             }
             pos = hi;
             if (hi == seg_end) {
                 if (sg.flush) {
-                    block_reduce_store<M * DY>(T, red, p.part + (size_t)sg.run * p.part_stride);
+                    block_reduce_store<M * DY, true>(T, red, p.part + (size_t)sg.run * p.part_stride);
 #pragma unroll
                     for (int i = 0; i < M * DY; ++i) T[i] = 0.0;
                 }
@@ -451,13 +495,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_phase_a(StreamArgs p) {
                 if (s < s_end) sg = p.segs[s];
             }
         }
-        __syncthreads();   // every thread is done reading this stage
-        if (tid == 0 && t + kStages < n_tiles) {
-            const int64_t start = c0 + (int64_t)(t + kStages) * kTile;
-            const int cnt = (int)((c1 - start < kTile) ? c1 - start : kTile);
-            issue_tile<DY, !INFER, LATENT, false>(p, stages + stage * L::kDoubles, &bars[stage], start, cnt);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);   // this warp is done with the stage
     }
+    ts_end(p.ts, p.layer * 4 + 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -469,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_phase_a(StreamArgs p) {
 // ------------------------------------------------------------------------------------------------
 template <int DY, int M, int SB, int NT, bool INFER, bool LATENT, bool PROPAGATE>
 __device__ __forceinline__ void phase_b_block(double (&acc)[DY + 3], const StreamArgs &p, const double *st, int k0, int64_t tile_lo,
-                                              int64_t pos, int64_t hi, const double *sAn, const double *sAo, const double *sC,
+                                              int lo_rel, int hi_rel, const double *sAn, const double *sAo, const double *sC,
                                               double inv2L, double rs, double pbv, const double (&b)[DY], const double (&pb)[DY]) {
     using L = TileLayout<DY, !INFER, LATENT, LATENT>;
     asm volatile("" ::: "memory");
@@ -478,8 +519,7 @@ __device__ __forceinline__ void phase_b_block(double (&acc)[DY + 3], const Strea
 #pragma unroll
     for (int q = 0; q < SB; ++q) {
         const int idx = (k0 + q) * NT + threadIdx.x;
-        const int64_t n = tile_lo + idx;
-        act[q] = n >= pos && n < hi;
+        act[q] = idx >= lo_rel && idx < hi_rel;
         const double x = act[q] ? st[L::kX + idx] : 0.0;
         basis_seed(x, inv2L, act[q] ? rs : 0.0, f[q], c2[q]);
         fm[q] = 0.0;
@@ -536,32 +576,34 @@ __device__ __forceinline__ void phase_b_block(double (&acc)[DY + 3], const Strea
 template <int DY, int M, bool INFER, bool LATENT, bool PROPAGATE>
 __global__ void __launch_bounds__(kThreadsB, 1) k_phase_b(StreamArgs p) {
     constexpr int NT = kThreadsB;
+    constexpr int NCW = NT / 32;
     using L = TileLayout<DY, !INFER, LATENT, LATENT>;
     extern __shared__ __align__(128) double dsm[];
     double *stages = dsm;
-    __shared__ double sAn[M * DY];
-    __shared__ double sAo[INFER ? M * DY : 1];
-    __shared__ double sC[M];
-    __shared__ double sScal[4 + 2 * DY];
-    __shared__ double sRed[(kThreadsB / 32) * 8];
-    __shared__ __align__(8) uint64_t bars[kStages];
-    const int tid = threadIdx.x;
+    __shared__ double sAn_all[NCW][M * DY];        // region coefficients, one private copy per warp
+    __shared__ double sAo_all[INFER ? NCW : 1][INFER ? M * DY : 1];
+    __shared__ double sC_all[NCW][M];
+    __shared__ double sRed[NCW * 8];
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t c0 = (int64_t)blockIdx.x * p.cta_quantum;
     const int64_t c1 = (c0 + p.cta_quantum < p.n_samples) ? c0 + p.cta_quantum : p.n_samples;
     const int n_tiles = (c1 > c0) ? (int)((c1 - c0 + kTile - 1) / kTile) : 0;
+    ts_begin(p.ts, p.layer * 4 + 2);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NCW);
+        }
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int t = 0; t < kStages && t < n_tiles; ++t) {
-            const int64_t start = c0 + (int64_t)t * kTile;
-            const int cnt = (int)((c1 - start < kTile) ? c1 - start : kTile);
-            issue_tile<DY, !INFER, LATENT, LATENT>(p, stages + t * L::kDoubles, &bars[t], start, cnt);
-        }
-    }
+    int next_issue = 0;
+    double *sAn = sAn_all[warp];
+    double *sAo = sAo_all[INFER ? warp : 0];
+    double *sC = sC_all[warp];
     double acc[DY + 3];
 #pragma unroll
     for (int i = 0; i < DY + 3; ++i) acc[i] = 0.0;
@@ -576,36 +618,28 @@ __global__ void __launch_bounds__(kThreadsB, 1) k_phase_b(StreamArgs p) {
     for (int t = 0; t < n_tiles; ++t) {
         const int stage = t % kStages;
         const double *st = stages + stage * L::kDoubles;
-        mbar_wait(&bars[stage], (uint32_t)((t / kStages) & 1));
+        if (tid == 0) refill<DY, !INFER, LATENT, LATENT>(p, stages, full_bar, empty_bar, next_issue, t, n_tiles, c0, c1);
+        mbar_wait(&full_bar[stage], (uint32_t)((t / kStages) & 1));
         const int64_t tile_lo = c0 + (int64_t)t * kTile;
         const int64_t tile_hi = (tile_lo + kTile < c1) ? tile_lo + kTile : c1;
         int64_t pos = tile_lo;
         while (pos < tile_hi) {
             if (loaded != s) {
-                __syncthreads();
-                if (tid < M * DY) {
-                    sAn[tid] = p.A[(size_t)sg.region * (M * DY) + tid];
-                    if (INFER) sAo[tid] = p.A_prev[(size_t)sg.region * (M * DY) + tid];
+                __syncwarp();
+                for (int q = lane; q < M * DY; q += 32) {
+                    sAn[q] = p.A[(size_t)sg.region * (M * DY) + q];
+                    if (INFER) sAo[q] = p.A_prev[(size_t)sg.region * (M * DY) + q];
                 }
-                if (tid < M) sC[tid] = p.cm2[(size_t)sg.region * M + tid];
-                if (tid == 0) {
-                    sScal[0] = p.inv2L[sg.region];
-                    sScal[1] = p.rsqrtL[sg.region];
-                    sScal[2] = LATENT ? p.pbias_var[sg.parent] : 0.0;
-                }
-                if (tid < DY) {
-                    sScal[4 + tid] = p.bias[(size_t)sg.region * DY + tid];
-                    sScal[4 + DY + tid] = LATENT ? p.pbias[(size_t)sg.parent * DY + tid] : 0.0;
-                }
-                __syncthreads();
-                inv2L = sScal[0];
-                rs = sScal[1];
-                pbv = sScal[2];
+                for (int q = lane; q < M; q += 32) sC[q] = p.cm2[(size_t)sg.region * M + q];
+                inv2L = p.inv2L[sg.region];
+                rs = p.rsqrtL[sg.region];
+                pbv = LATENT ? p.pbias_var[sg.parent] : 0.0;
 #pragma unroll
                 for (int d = 0; d < DY; ++d) {
-                    b[d] = sScal[4 + d];
-                    pb[d] = sScal[4 + DY + d];
+                    b[d] = p.bias[(size_t)sg.region * DY + d];
+                    pb[d] = LATENT ? p.pbias[(size_t)sg.parent * DY + d] : 0.0;
                 }
+                __syncwarp();
                 loaded = s;
             }
             const int64_t seg_end = sg.start + sg.len;
@@ -615,20 +649,20 @@ __global__ void __launch_bounds__(kThreadsB, 1) k_phase_b(StreamArgs p) {
             while (ka <= kb) {
                 const int left = kb - ka + 1;
                 if (kSB >= 4 && left >= 4) {
-                    phase_b_block<DY, M, 4, NT, INFER, LATENT, PROPAGATE>(acc, p, st, ka, tile_lo, pos, hi, sAn, sAo, sC, inv2L, rs, pbv, b, pb);
+                    phase_b_block<DY, M, 4, NT, INFER, LATENT, PROPAGATE>(acc, p, st, ka, tile_lo, (int)(pos - tile_lo), (int)(hi - tile_lo), sAn, sAo, sC, inv2L, rs, pbv, b, pb);
                     ka += 4;
                 } else if (left >= 2) {
-                    phase_b_block<DY, M, 2, NT, INFER, LATENT, PROPAGATE>(acc, p, st, ka, tile_lo, pos, hi, sAn, sAo, sC, inv2L, rs, pbv, b, pb);
+                    phase_b_block<DY, M, 2, NT, INFER, LATENT, PROPAGATE>(acc, p, st, ka, tile_lo, (int)(pos - tile_lo), (int)(hi - tile_lo), sAn, sAo, sC, inv2L, rs, pbv, b, pb);
                     ka += 2;
                 } else {
-                    phase_b_block<DY, M, 1, NT, INFER, LATENT, PROPAGATE>(acc, p, st, ka, tile_lo, pos, hi, sAn, sAo, sC, inv2L, rs, pbv, b, pb);
+                    phase_b_block<DY, M, 1, NT, INFER, LATENT, PROPAGATE>(acc, p, st, ka, tile_lo, (int)(pos - tile_lo), (int)(hi - tile_lo), sAn, sAo, sC, inv2L, rs, pbv, b, pb);
                     ka += 1;
                 }
             }
             pos = hi;
             if (hi == seg_end) {
                 if (sg.flush) {
-                    block_reduce_small<DY + 3, false, NT>(acc, sRed, p.part + (size_t)sg.run * p.part_stride);
+                    block_reduce_small<DY + 3, false, NT, true>(acc, sRed, p.part + (size_t)sg.run * p.part_stride);
 #pragma unroll
                     for (int i = 0; i < DY + 3; ++i) acc[i] = 0.0;
                 }
@@ -636,27 +670,25 @@ __global__ void __launch_bounds__(kThreadsB, 1) k_phase_b(StreamArgs p) {
                 if (s < s_end) sg = p.segs[s];
             }
         }
-        __syncthreads();
-        if (tid == 0 && t + kStages < n_tiles) {
-            const int64_t start = c0 + (int64_t)(t + kStages) * kTile;
-            const int cnt = (int)((c1 - start < kTile) ? c1 - start : kTile);
-            issue_tile<DY, !INFER, LATENT, LATENT>(p, stages + stage * L::kDoubles, &bars[stage], start, cnt);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
     }
     // ---- tail: the last CTA to finish turns the run partials into the bias / noise posteriors --------
-    if (!p.fuse_tail) return;
+    if (!p.fuse_tail) {
+        ts_end(p.ts, p.layer * 4 + 2);
+        return;
+    }
     __shared__ int sLast;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) sLast = (atomicAdd(p.done_counter, 1u) == gridDim.x - 1);
-    __syncthreads();
+    compute_sync<NT>();
+    if (tid == 0) sLast = (atom_add_acq_rel_gpu(p.done_counter, 1u) == gridDim.x - 1);
+    compute_sync<NT>();
     if (sLast) {
-        __threadfence();
         int lpr = 32;
         while (lpr > 1 && (NT / lpr) < p.R) lpr >>= 1;
-        bias_noise_all<DY>(p, lpr);
+        bias_noise_all<DY, NT>(p, lpr);
         if (tid == 0) *p.done_counter = 0u;
     }
+    ts_end(p.ts, p.layer * 4 + 2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -678,11 +710,12 @@ struct RegionArgs {
     double *bias_prec, *bias_prec0, *bias_mean, *bias_mean0, *bias_var, *yvar, *sumsB;
     // shared (ci) or per-region (fi) axis / ARD
     double *axB, *axKappa, *axRho, *axLogC, *axCov, *ardShape, *ardScale, *ardMean, *ardLogMean;
-    double *omega, *logOmegaHat, *omegaIters, *ardPartial;
+    double *omega, *logOmegaHat, *omegaIters, *ardPartial, *omegaEta, *omegaWarm;
     double *primeB, *primeLogC, *primeShape, *primeScale;   // snapshot read by ARD / omega (ci)
     const double *priorB, *priorLogC, *priorShape, *priorScale;
     double *bcontrib;          // (R, M, 3) ci: 0.5 noise zeta ytil ytil^T
     unsigned long long *chol_count;
+    unsigned long long *ts;
     double fi_shape0_mix, fi_scale0_mix;   // sum_k (1/M) shape0_k, sum_k (1/M) scale0_k (Posteriors.py:293-295)
     // spectral density
     int32_t use_prior;
@@ -816,51 +849,33 @@ __global__ void __launch_bounds__(512) k_reduce_scale(RegionArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// ci mid-step in ONE launch: a thread-block cluster of up to 8 CTAs does P1-finish, P2 (+ guard, Bingham),
-// S1, S2, P3, S3 and the log omega_hat table; the two cross-region sums (B_i over regions, ARD scale over
-// regions) go through distributed shared memory with cluster barriers instead of separate kernels.
-//   regions are split contiguously over the CTAs; `lpi` lanes (power of two) share the run loop of one
-//   (region, basis) item on coarse layers where a region has many run partials.
-// Same arithmetic and summation order as k_reduce_scale / k_axis_shared / k_scale_stats / k_ard.
+// ci mid-step, two wide launches (the work is latency-bound: a few dependent global loads per item, so it
+// is spread over many SMs instead of a few fat CTAs):
+//   k_mid1  P1-finish per (region, basis) item: run partials -> y_tilde, precision, zeta and the item's
+//           contribution to B_i (Posteriors.py:35-78, 507-517); the LAST CTA to finish then sums the
+//           contributions over the regions in a fixed order, mixes in the previous posterior, runs the PD
+//           guard and the Bingham update (P2, S1: Posteriors.py:497-530, Stats.py:375-382);
+//   k_mid3  S2 per item with the new axis covariance: a, m2, cm2 (Stats.py:67-100) and per-CTA sums of
+//           m2/S for the ARD update that k_omega finishes off the critical path.
+// `lpi` lanes (power of two) share the run loop of one item on coarse layers where a region has many runs.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMidThreads = 512;
-constexpr int kMidChunk = 32;   // regions per shared-memory reduction chunk
-
-__host__ __device__ inline size_t mid_smem_doubles(int M) { return (size_t)M * M + 4 * M + 3 * M + 4 * M + 3 * 128 + (size_t)kMidChunk * M * 4; }
+constexpr int kMidThreads = 256;
 
 template <int DY>
-__global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, int regions_per_cta) {
+__global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, int regions_per_cta, unsigned int *sync_words) {
     static_assert(DY == 2, "dy == 2 only");
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int NC = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-    const int M = a.M, tid = threadIdx.x;
-    extern __shared__ double sm[];
-    double *sOmega = sm;                  // M*M
-    double *sPB = sOmega + M * M;         // M*4  previous posterior B ("prime")
-    double *sPLogC = sPB + 4 * M;         // M
-    double *sPShape = sPLogC + M;         // M
-    double *sPScale = sPShape + M;        // M
-    double *sCov = sPScale + M;           // M*4
-    double *sPubB = sCov + 4 * M;         // 128  this CTA's sums of the B contributions (read by peers)
-    double *sPubA = sPubB + 128;          // 128  this CTA's sums of m2/S
-    double *sTot = sPubA + 128;           // 128
-    double *sContrib = sTot + 128;        // kMidChunk * M * 4
-    const bool first = (a.layer == 0);
-    for (int t = tid; t < M * M; t += kMidThreads) sOmega[t] = a.omega[t];
-    for (int t = tid; t < M * 4; t += kMidThreads) sPB[t] = first ? a.priorB[t] : a.axB[t];
-    for (int t = tid; t < M; t += kMidThreads) {
-        sPLogC[t] = first ? a.priorLogC[t] : a.axLogC[t];
-        sPShape[t] = first ? a.priorShape[t] : a.ardShape[t];
-        sPScale[t] = first ? a.priorScale[t] : a.ardScale[t];
-    }
-    const int r0 = rank * regions_per_cta;
+    extern __shared__ double sm[];   // contrib[32 * M * 4] + sums[96]; last CTA: omega[M*M], primeB[M*4], data[96]
+    __shared__ int sLast;
+    const int M = a.M, tid = threadIdx.x, NV = M * 3;
+    double *sContrib = sm, *sSum = sm + 32 * M * 4;
+    ts_begin(a.ts, a.layer * 4 + 1);
+    if (tid < 96) sSum[tid] = 0.0;
+    __syncthreads();
+    const int r0 = blockIdx.x * regions_per_cta;
     const int r1 = (r0 + regions_per_cta < a.R) ? r0 + regions_per_cta : a.R;
     const int groups = kMidThreads / lpi, grp = tid / lpi, sl = tid % lpi;
-    // ---- step 1: y_tilde, precision, zeta per (region, basis); B contributions summed over my regions ----
-    double accB = 0.0;
-    for (int cb = r0; cb < r1; cb += kMidChunk) {
-        const int nreg = (cb + kMidChunk < r1) ? kMidChunk : r1 - cb;
+    for (int cb = r0; cb < r1; cb += 32) {
+        const int nreg = (cb + 32 < r1) ? 32 : r1 - cb;
         const int nitems = nreg * M;
         for (int base = 0; base < nitems; base += groups) {
             const int it = base + grp;
@@ -895,21 +910,61 @@ __global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, i
             }
         }
         __syncthreads();
-        if (tid < M * 3) {
-            const int i = tid / 3, c = tid % 3;
-            for (int k = 0; k < nreg; ++k) accB += sContrib[(k * M + i) * 4 + c];
+        // sum over the regions of the chunk: 32 lanes hold one region each, shuffle tree (fixed order)
+        for (int vv = tid >> 5; vv < NV; vv += kMidThreads / 32) {
+            const int i = vv / 3, c = vv % 3, k = tid & 31;
+            double t = (k < nreg) ? sContrib[(k * M + i) * 4 + c] : 0.0;
+            t = warp_sum(t);
+            if (k == 0) sSum[vv] += t;
         }
         __syncthreads();
     }
-    if (tid < M * 3) sPubB[tid] = accB;
-    cluster.sync();
-    if (tid < M * 3) {
-        double t = 0.0;
-        for (int c = 0; c < NC; ++c) t += cluster.map_shared_rank(sPubB, c)[tid];
-        sTot[tid] = t;
+    if (tid < 96) a.bcontrib[(size_t)blockIdx.x * 96 + tid] = sSum[tid];   // per-CTA partial of sum_l contrib
+    // ---- grid barrier with work: the last CTA to arrive does the cross-region part, the others wait for it ----
+    // (cooperative launch: all CTAs are co-resident; sync_words = {arrival counter, completed generations} of
+    // this layer, both only ever incremented, so the captured graph can be replayed without resetting them)
+    __syncthreads();
+    __shared__ unsigned int sGen;
+    if (tid == 0) {
+        const unsigned int ticket = atom_add_acq_rel_gpu(&sync_words[0], 1u);
+        sGen = ticket / gridDim.x;
+        sLast = (ticket % gridDim.x == gridDim.x - 1);
     }
     __syncthreads();
-    // ---- step 2: B_i, PD guard, Bingham parameters, axis covariance (every CTA, identical results) --------
+    const unsigned int gen = sGen;
+    if (sLast) {
+    const bool first = (a.layer == 0);
+    double *sOmega = sm, *sPB = sOmega + M * M, *sData = sPB + 4 * M;
+    for (int t = tid; t < M * M; t += kMidThreads) sOmega[t] = a.omega[t];
+    for (int t = tid; t < M * 4; t += kMidThreads) {
+        const double v = first ? a.priorB[t] : a.axB[t];
+        sPB[t] = v;
+        a.primeB[t] = v;   // snapshot of the previous posterior (MRGP.py:575 / :581), read by k_omega
+    }
+    for (int t = tid; t < M; t += kMidThreads) {
+        a.primeLogC[t] = first ? a.priorLogC[t] : a.axLogC[t];
+        a.primeShape[t] = first ? a.priorShape[t] : a.ardShape[t];
+        a.primeScale[t] = first ? a.priorScale[t] : a.ardScale[t];
+    }
+    {   // sum of the per-CTA partials: two slices of CTAs per value, four loads in flight per thread
+        double *sHalf = sData + 96;
+        const int v = tid % 96, half = tid / 96, nb = (int)gridDim.x;
+        if (half < 2) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int q = half;
+            for (; q + 6 < nb; q += 8) {
+                a0 += __ldcg(a.bcontrib + (size_t)q * 96 + v);
+                a1 += __ldcg(a.bcontrib + (size_t)(q + 2) * 96 + v);
+                a2 += __ldcg(a.bcontrib + (size_t)(q + 4) * 96 + v);
+                a3 += __ldcg(a.bcontrib + (size_t)(q + 6) * 96 + v);
+            }
+            for (; q < nb; q += 2) a0 += __ldcg(a.bcontrib + (size_t)q * 96 + v);
+            sHalf[half * 96 + v] = (a0 + a1) + (a2 + a3);
+        }
+        __syncthreads();
+        if (tid < 96) sData[tid] = sHalf[tid] + sHalf[96 + tid];
+    }
+    __syncthreads();
     if (tid < M) {
         const int i = tid;
         double b00 = 0.0, b01 = 0.0, b11 = 0.0;
@@ -920,45 +975,43 @@ __global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, i
             b11 += w * sPB[k * 4 + 3];
         }
         Bingham2 bg;
-        bingham2(b00 + sTot[i * 3 + 0], b01 + sTot[i * 3 + 1], b11 + sTot[i * 3 + 2], bg);
-        sCov[i * 4 + 0] = bg.cov[0];
-        sCov[i * 4 + 1] = bg.cov[1];
-        sCov[i * 4 + 2] = bg.cov[2];
-        if (rank == 0) {
-            atomicAdd(a.chol_count, (unsigned long long)bg.n_chol);
-            a.axB[i * 4 + 0] = bg.b[0];
-            a.axB[i * 4 + 1] = bg.b[1];
-            a.axB[i * 4 + 2] = bg.b[1];
-            a.axB[i * 4 + 3] = bg.b[2];
-            a.axKappa[i * 2 + 0] = bg.kappa[0];
-            a.axKappa[i * 2 + 1] = bg.kappa[1];
-            a.axRho[i * 2 + 0] = bg.rho[0];
-            a.axRho[i * 2 + 1] = bg.rho[1];
-            a.axLogC[i] = bg.logc;
-            a.axCov[i * 4 + 0] = bg.cov[0];
-            a.axCov[i * 4 + 1] = bg.cov[1];
-            a.axCov[i * 4 + 2] = bg.cov[1];
-            a.axCov[i * 4 + 3] = bg.cov[2];
-        }
+        bingham2(b00 + sData[i * 3 + 0], b01 + sData[i * 3 + 1], b11 + sData[i * 3 + 2], bg);
+        atomicAdd(a.chol_count, (unsigned long long)bg.n_chol);
+        a.axB[i * 4 + 0] = bg.b[0];
+        a.axB[i * 4 + 1] = bg.b[1];
+        a.axB[i * 4 + 2] = bg.b[1];
+        a.axB[i * 4 + 3] = bg.b[2];
+        a.axKappa[i * 2 + 0] = bg.kappa[0];
+        a.axKappa[i * 2 + 1] = bg.kappa[1];
+        a.axRho[i * 2 + 0] = bg.rho[0];
+        a.axRho[i * 2 + 1] = bg.rho[1];
+        a.axLogC[i] = bg.logc;
+        a.axCov[i * 4 + 0] = bg.cov[0];
+        a.axCov[i * 4 + 1] = bg.cov[1];
+        a.axCov[i * 4 + 2] = bg.cov[1];
+        a.axCov[i * 4 + 3] = bg.cov[2];
     }
-    if (rank == 0) {   // snapshot of the previous posterior, read by the ELBO / kept for inspection
-        for (int t = tid; t < M * 4; t += kMidThreads) a.primeB[t] = sPB[t];
-        for (int t = tid; t < M; t += kMidThreads) {
-            a.primeLogC[t] = sPLogC[t];
-            a.primeShape[t] = sPShape[t];
-            a.primeScale[t] = sPScale[t];
-        }
+        __syncthreads();
+        if (tid == 0) st_release_gpu(&sync_words[1], gen + 1u);
+    } else {
+        if (tid == 0)
+            while ((int)(ld_acquire_gpu(&sync_words[1]) - (gen + 1u)) < 0) {
+            }
+        __syncthreads();
     }
+    // ---- S2 per item with the new axis covariance: a, m2, cm2 (Stats.py:67-100); per-CTA sums of m2/S --------
+    double *sCov = sm, *sC2 = sCov + 4 * M, *sSumA = sC2 + 32 * M;
     __syncthreads();
-    // ---- step 3: a, m2, cm2 per (region, basis) (Stats.py:67-100); m2/S summed over my regions --------------
-    double accA = 0.0;
-    for (int cb = r0; cb < r1; cb += kMidChunk) {
-        const int nreg = (cb + kMidChunk < r1) ? kMidChunk : r1 - cb;
+    for (int t = tid; t < M * 4; t += kMidThreads) sCov[t] = __ldcg(a.axCov + t);
+    if (tid < M) sSumA[tid] = 0.0;
+    __syncthreads();
+    for (int cb = r0; cb < r1; cb += 32) {
+        const int nreg = (cb + 32 < r1) ? 32 : r1 - cb;
         const int nitems = nreg * M;
         for (int it = tid; it < nitems; it += kMidThreads) {
             const int l = cb + it / M, i = it % M;
             const size_t ri = (size_t)l * M + i;
-            const double c00 = sCov[i * 4 + 0], c01 = sCov[i * 4 + 1], c11 = sCov[i * 4 + 2];
+            const double c00 = sCov[i * 4 + 0], c01 = sCov[i * 4 + 1], c11 = sCov[i * 4 + 3];
             const double y0 = a.ytil[ri * 2], y1 = a.ytil[ri * 2 + 1];
             const double zeta = a.zeta[ri], prec = a.prec[ri];
             const double cy0 = c00 * y0 + c01 * y1, cy1 = c01 * y0 + c11 * y1;
@@ -971,16 +1024,19 @@ __global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, i
             const double ccy0 = c00 * cy0 + c01 * cy1, ccy1 = c01 * cy0 + c11 * cy1;
             a.m2[ri] = m2;
             a.cm2[ri] = 1.0 / prec + z2 * (y0 * (cy0 - ccy0) + y1 * (cy1 - ccy1));
-            sContrib[it] = m2 / a.S[ri];
+            sC2[it] = m2 / a.S[ri];
         }
         __syncthreads();
-        if (tid < M)
-            for (int k = 0; k < nreg; ++k) accA += sContrib[k * M + tid];
+        for (int vv = tid >> 5; vv < M; vv += kMidThreads / 32) {
+            const int k = tid & 31;
+            double t = (k < nreg) ? sC2[k * M + vv] : 0.0;
+            t = warp_sum(t);
+            if (k == 0) sSumA[vv] += t;
+        }
         __syncthreads();
     }
-    // m2/S sums of my regions: finished (ARD, log omega_hat, omega) by k_omega off the critical path
-    if (tid < M) a.ardPartial[rank * M + tid] = accA;
-    cluster.sync();   // peers keep their shared memory alive until everybody has read the B sums
+    if (tid < M) a.ardPartial[(size_t)blockIdx.x * M + tid] = sSumA[tid];
+    ts_end(a.ts, a.layer * 4 + 1);
 }
 
 // ci, off the critical path (side stream): ARD posterior and moments from the per-CTA m2/S sums of
@@ -989,14 +1045,15 @@ __global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, i
 // (mrgp_math.cuh), one block of 256 threads, warp per matrix row / column.
 constexpr int kOmegaThreads = 256;
 
-__host__ __device__ inline size_t omega_smem_doubles(int M) { return (size_t)3 * M * M + 10 * M + 8; }
+__host__ __device__ inline size_t omega_smem_doubles(int M) { return (size_t)3 * M * M + 12 * M + 8; }
 
 __global__ void __launch_bounds__(kOmegaThreads) k_omega(RegionArgs a, int n_partials) {
     extern __shared__ double sm[];
     const int M = a.M, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kOmegaThreads / 32;
     double *K = sm, *P = K + M * M, *S = P + M * M, *v = S + M * M, *c = v + M, *rhs = c + M, *dinv = rhs + M;
-    double *yv = dinv + M, *xv = yv + M, *s_mean = xv + M, *s_lmean = s_mean + M, *s_k = s_lmean + M, *red = s_k + M;
+    double *yv = dinv + M, *xv = yv + M, *s_mean = xv + M, *s_lmean = s_mean + M, *s_k = s_lmean + M, *cshift = s_k + M, *red = cshift + M;
+    ts_begin(a.ts, a.layer * 4 + 3);
     for (int t = tid; t < M * M; t += kOmegaThreads) P[t] = a.omega[t];   // the OLD omega mixes the ARD prior
     __syncthreads();
     if (tid < M) {
@@ -1043,11 +1100,17 @@ __global__ void __launch_bounds__(kOmegaThreads) k_omega(RegionArgs a, int n_par
         for (int i = lane; i < M; i += 32) mx = fmax(mx, K[i * M + k]);
         mx = warp_max(mx);
         for (int i = lane; i < M; i += 32) K[i * M + k] = exp(K[i * M + k] - mx);
+        if (lane == 0) cshift[k] = mx;   // column shift (row shifts cancel in the row normalisation)
     }
-    if (tid < M) v[tid] = 1.0;
+    // warm start: the log column scalings of the previous sweep's solve for this layer (stored relative to
+    // the un-shifted table, so that they do not depend on the shifts) seed the iteration
+    const bool warm = a.omegaWarm[a.layer] > 0.5;
+    __syncthreads();
+    if (tid < M) v[tid] = warm ? exp(fmax(-700.0, fmin(700.0, a.omegaEta[a.layer * 64 + tid] + cshift[tid]))) : 1.0;
     __syncthreads();
     int iters = 0;
     double err_prev = INFINITY;
+    const int n_warmup = warm ? 0 : kOmegaWarmup;
     for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
         ++iters;
         for (int i = warp; i < M; i += NW) {
@@ -1074,32 +1137,34 @@ __global__ void __launch_bounds__(kOmegaThreads) k_omega(RegionArgs a, int n_par
         __syncthreads();
         const double err = red[0];
         if (err < kOmegaTol) break;
-        if (it < kOmegaWarmup || !(err < err_prev)) {
+        if (it < n_warmup || !(err < err_prev)) {
             if (tid < M) v[tid] /= c[tid];   // Sinkhorn column step
-            err_prev = (it < kOmegaWarmup) ? INFINITY : err;
+            err_prev = (it < n_warmup) ? INFINITY : err;
             __syncthreads();
             continue;
         }
         err_prev = err;
-        for (int e = tid; e < M * M; e += kOmegaThreads) {
-            const int k = e / M, m = e % M;
-            if (m <= k) {
-                double s = 0.0;
-                for (int i = 0; i < M; ++i) s = fma(P[i * M + k], P[i * M + m], s);
-                S[e] = ((k == m) ? c[k] : 0.0) - s + 1.0 / (double)M;
+        for (int k = warp; k < M; k += NW)
+            for (int m = lane; m <= k; m += 32) {
+                double s0 = 0.0, s1 = 0.0;
+                int i = 0;
+                for (; i + 1 < M; i += 2) {
+                    s0 = fma(P[i * M + k], P[i * M + m], s0);
+                    s1 = fma(P[(i + 1) * M + k], P[(i + 1) * M + m], s1);
+                }
+                if (i < M) s0 = fma(P[i * M + k], P[i * M + m], s0);
+                S[k * M + m] = ((k == m) ? c[k] : 0.0) - (s0 + s1) + 1.0 / (double)M;
             }
-        }
         if (tid < M) rhs[tid] = 1.0 - c[tid];
         __syncthreads();
         for (int j = 0; j < M; ++j) {   // Cholesky, lower triangle in place, diagonal untouched, 1/l_jj aside
-            const double di = 1.0 / sqrt(S[j * M + j]);
+            const double di = rsqrt(S[j * M + j]);
             if (tid > j && tid < M) S[tid * M + j] *= di;
             if (tid == 0) dinv[j] = di;
             __syncthreads();
-            const int w = M - j - 1;
-            for (int e = tid; e < w * w; e += kOmegaThreads) {
-                const int r = j + 1 + e / w, q = j + 1 + e % w;
-                if (q <= r) S[r * M + q] -= S[r * M + j] * S[q * M + j];
+            for (int r = j + 1 + warp; r < M; r += NW) {
+                const double lrj = S[r * M + j];
+                for (int q = j + 1 + lane; q <= r; q += 32) S[r * M + q] = fma(-lrj, S[q * M + j], S[r * M + q]);
             }
             __syncthreads();
         }
@@ -1119,7 +1184,12 @@ __global__ void __launch_bounds__(kOmegaThreads) k_omega(RegionArgs a, int n_par
         __syncthreads();
     }
     for (int t = tid; t < M * M; t += kOmegaThreads) a.omega[t] = P[t];
-    if (tid == 0) a.omegaIters[a.layer] = (double)iters;
+    if (tid < M) a.omegaEta[a.layer * 64 + tid] = log(v[tid]) - cshift[tid];
+    if (tid == 0) {
+        a.omegaIters[a.layer] = (double)iters;
+        a.omegaWarm[a.layer] = 1.0;
+    }
+    ts_end(a.ts, a.layer * 4 + 3);
 }
 
 // Standalone bias / noise update (per-phase ABI entry; the sweep uses the fused tail of phase B).
@@ -1127,7 +1197,7 @@ template <int DY>
 __global__ void __launch_bounds__(kThreadsB) k_bias_noise(StreamArgs p) {
     int lpr = 32;
     while (lpr > 1 && (kThreadsB / lpr) < p.R) lpr >>= 1;
-    bias_noise_all<DY>(p, lpr);
+    bias_noise_all<DY, kThreadsB>(p, lpr);
 }
 
 // ------------------------------------------------------------------------------------------------

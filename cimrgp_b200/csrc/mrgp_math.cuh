@@ -287,15 +287,46 @@ inline int omega_solve_serial(const double *lw, int M, double *omega, double *K,
 // Basis angle: theta = pi (x + L)/(2L) = pi (u + 1/2), u = x / (2L)  (KernelClass.py:31-35), so
 // sin(theta) = cos(pi u) and cos(theta) = -sin(pi u).  Returns phi_1 = L^-1/2 sin(theta) and
 // c2 = 2 cos(theta); higher orders follow phi_{i+1} = c2 phi_i - phi_{i-1} with phi_0 = 0.
+// sin(pi u), cos(pi u): u = k/2 + r with k = rint(2u), |r| <= 1/4; Taylor polynomials of sin(pi r)/r (8 terms)
+// and cos(pi r) (9 terms) in r^2 are exact to 1-2 ulp on that range; the quadrant k mod 4 swaps and negates.
+// About 22 FP64 operations and a dozen integer ones per call (the library sincospi spends ~100 instructions,
+// most of them on special values that cannot occur here); valid for |u| < 2^30.
+MRGP_HD void sincospi_fast(double u, double &s, double &c) {
+    const double k = rint(u + u);
+    const double r = fma(k, -0.5, u);
+#if defined(__CUDA_ARCH__)
+    const int q = __double2int_rn(k);
+#else
+    const int q = (int)(long long)k;
+#endif
+    const double r2 = r * r;
+    double ps = 7.95205400147550838e-07 * 0.0 + -2.19153534478302037e-05;
+    ps = fma(ps, r2, 4.66302805767612337e-04);
+    ps = fma(ps, r2, -7.37043094571434784e-03);
+    ps = fma(ps, r2, 8.21458866111281910e-02);
+    ps = fma(ps, r2, -5.99264529320791883e-01);
+    ps = fma(ps, r2, 2.55016403987734508e+00);
+    ps = fma(ps, r2, -5.16771278004996937e+00);
+    ps = fma(ps, r2, 3.14159265358979312e+00);
+    ps *= r;
+    double pc = 4.30306958703294391e-06;
+    pc = fma(pc, r2, -1.04638104924845650e-04);
+    pc = fma(pc, r2, 1.92957430940392206e-03);
+    pc = fma(pc, r2, -2.58068913900140508e-02);
+    pc = fma(pc, r2, 2.35330630358893123e-01);
+    pc = fma(pc, r2, -1.33526276885458928e+00);
+    pc = fma(pc, r2, 4.05871212641676760e+00);
+    pc = fma(pc, r2, -4.93480220054467900e+00);
+    pc = fma(pc, r2, 1.0);
+    s = (q & 1) ? pc : ps;
+    c = (q & 1) ? ps : pc;
+    if (q & 2) s = -s;
+    if ((q + 1) & 2) c = -c;
+}
+
 MRGP_HD void basis_seed(double x, double inv2L, double rsqrtL, double &phi1, double &c2) {
     double sp, cp;
-#if defined(__CUDA_ARCH__)
-    sincospi(x * inv2L, &sp, &cp);
-#else
-    const double u = x * inv2L;
-    sp = sin(kPi * u);
-    cp = cos(kPi * u);
-#endif
+    sincospi_fast(x * inv2L, sp, cp);
     phi1 = rsqrtL * cp;
     c2 = -2.0 * sp;
 }

@@ -33,6 +33,52 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+// non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// barrier among the first `count` threads of the block (compute warps), id 1; the producer warp stays out
+template <int COUNT>
+__device__ __forceinline__ void compute_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(COUNT) : "memory");
+}
+
+// ---- inter-CTA hand-off through global memory -----------------------------------------------------------
+// __threadfence() compiles to MEMBAR.SC.GPU (+ an L1 invalidate) in EVERY thread that executes it and was the
+// single most expensive instruction of the small kernels.  The pattern used instead: all threads write,
+// __syncthreads(), then ONE thread performs a release/acquire operation at gpu scope (fences are cumulative
+// over the CTA barrier), __syncthreads() again before the others read.
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int *p, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_gpu(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // bytes must be a multiple of 16, src and dst 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),

@@ -195,6 +195,13 @@ int mrgp_batched_cholesky(void *cuda_stream, double *a_dev, int32_t n, int64_t b
  * writes the elapsed milliseconds; used to measure the FP64 pipe roofline.                          */
 int mrgp_fp64_probe(void *cuda_stream, int64_t iters, double *sink_dev, float *ms_out);
 
+/* Debug aid: global-timer stamps written by the kernels of the captured sweep graph.  Enable before the first
+ * mrgp_sweep(); mrgp_timeline_read() runs ONE sweep and returns n = 4 * n_layers entries: tags[k] = layer * 4 + kind
+ * (0 phase A, 1 mid-step, 2 phase B, 3 omega), ms[2k] / ms[2k+1] = begin / end of that kernel in ms since the first
+ * begin (-1 when the kernel did not run).  cap = capacity of tags[]; ms[] must hold 2 * cap floats.              */
+int mrgp_timeline_enable(mrgp_handle *h, int32_t on);
+int mrgp_timeline_read(mrgp_handle *h, int32_t *tags, float *ms, int32_t cap);
+
 /* ---- host-only hooks (no GPU needed; used by the CPU tests) ------------------------------------ */
 
 /* Plan introspection: number of streaming CTAs, segments and runs of a layer. */
