@@ -248,7 +248,7 @@ size_t carve(mrgp_handle *h, char *base) {
         d.bias_var = c.take<double>(R);
         d.yvar = c.take<double>(R);
         d.sumsB = c.take<double>(R * (DY + 3));
-        d.bcontrib = c.take<double>(std::max<size_t>(RM * 3, 32 * 96));
+        d.bcontrib = c.take<double>(std::max<size_t>(RM * 3, 48 * 160));
         if (fi) {
             d.axB = c.take<double>(RM * DY * DY);
             d.axKappa = c.take<double>(RM * DY);
@@ -580,7 +580,8 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega) {
         const int items_cta = std::min(rpc, 32) * M;
         int lpi = 1;
         while (lpi < 32 && lpi * 2 <= mr && lpi * 2 * items_cta <= kMidThreads) lpi *= 2;
-        const size_t smem = (size_t)(std::max(std::max(32 * M * 4 + 96, M * M + 4 * M + 3 * 96), 37 * M)) * sizeof(double);
+        const int nvp = (M * 3 + 31) & ~31;
+        const size_t smem = (size_t)(std::max(std::max(32 * M * 4 + nvp, M * M + 4 * M + 3 * nvp), 37 * M)) * sizeof(double);
         CK(set_smem(k_mid_ci<2>, smem));
         int rpc_arg = rpc;
         unsigned int *sync_words = h->mid_sync + 2 * j;

@@ -866,10 +866,10 @@ __global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, i
     static_assert(DY == 2, "dy == 2 only");
     extern __shared__ double sm[];   // contrib[32 * M * 4] + sums[96]; last CTA: omega[M*M], primeB[M*4], data[96]
     __shared__ int sLast;
-    const int M = a.M, tid = threadIdx.x, NV = M * 3;
+    const int M = a.M, tid = threadIdx.x, NV = M * 3, NVP = (NV + 31) & ~31;   // NVP: padded length of a B-sum vector
     double *sContrib = sm, *sSum = sm + 32 * M * 4;
     ts_begin(a.ts, a.layer * 4 + 1);
-    if (tid < 96) sSum[tid] = 0.0;
+    if (tid < NVP) sSum[tid] = 0.0;
     __syncthreads();
     const int r0 = blockIdx.x * regions_per_cta;
     const int r1 = (r0 + regions_per_cta < a.R) ? r0 + regions_per_cta : a.R;
@@ -919,7 +919,7 @@ __global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, i
         }
         __syncthreads();
     }
-    if (tid < 96) a.bcontrib[(size_t)blockIdx.x * 96 + tid] = sSum[tid];   // per-CTA partial of sum_l contrib
+    if (tid < NVP) a.bcontrib[(size_t)blockIdx.x * NVP + tid] = sSum[tid];   // per-CTA partial of sum_l contrib
     // ---- grid barrier with work: the last CTA to arrive does the cross-region part, the others wait for it ----
     // (cooperative launch: all CTAs are co-resident; sync_words = {arrival counter, completed generations} of
     // this layer, both only ever incremented, so the captured graph can be replayed without resetting them)
@@ -946,23 +946,24 @@ __global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, i
         a.primeShape[t] = first ? a.priorShape[t] : a.ardShape[t];
         a.primeScale[t] = first ? a.priorScale[t] : a.ardScale[t];
     }
-    {   // sum of the per-CTA partials: two slices of CTAs per value, four loads in flight per thread
-        double *sHalf = sData + 96;
-        const int v = tid % 96, half = tid / 96, nb = (int)gridDim.x;
-        if (half < 2) {
+    {   // sum of the per-CTA partials: `halves` slices of CTAs per value, four loads in flight per thread
+        double *sHalf = sData + NVP;
+        const int halves = kMidThreads / NVP;   // 1 or 2
+        const int v = tid % NVP, half = tid / NVP, nb = (int)gridDim.x;
+        if (half < halves) {
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int q = half;
-            for (; q + 6 < nb; q += 8) {
-                a0 += __ldcg(a.bcontrib + (size_t)q * 96 + v);
-                a1 += __ldcg(a.bcontrib + (size_t)(q + 2) * 96 + v);
-                a2 += __ldcg(a.bcontrib + (size_t)(q + 4) * 96 + v);
-                a3 += __ldcg(a.bcontrib + (size_t)(q + 6) * 96 + v);
+            for (; q + 3 * halves < nb; q += 4 * halves) {
+                a0 += __ldcg(a.bcontrib + (size_t)q * NVP + v);
+                a1 += __ldcg(a.bcontrib + (size_t)(q + halves) * NVP + v);
+                a2 += __ldcg(a.bcontrib + (size_t)(q + 2 * halves) * NVP + v);
+                a3 += __ldcg(a.bcontrib + (size_t)(q + 3 * halves) * NVP + v);
             }
-            for (; q < nb; q += 2) a0 += __ldcg(a.bcontrib + (size_t)q * 96 + v);
-            sHalf[half * 96 + v] = (a0 + a1) + (a2 + a3);
+            for (; q < nb; q += halves) a0 += __ldcg(a.bcontrib + (size_t)q * NVP + v);
+            sHalf[half * NVP + v] = (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
-        if (tid < 96) sData[tid] = sHalf[tid] + sHalf[96 + tid];
+        if (tid < NVP) sData[tid] = sHalf[tid] + (halves > 1 ? sHalf[NVP + tid] : 0.0);
     }
     __syncthreads();
     if (tid < M) {

@@ -1,0 +1,14 @@
+import sys, numpy as np
+sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests/golden')
+import workloads
+from cimrgp_b200 import IndexSetUniform, LaplacianEigenpairs, MaternKernel
+from cimrgp_b200.MRGP import MultiResolutionGaussianProcess
+N=int(sys.argv[1]); J=int(sys.argv[2])
+x,y = workloads.workload1(N)
+m = MultiResolutionGaussianProcess([x,y],30,IndexSetUniform(N,J-1,2),LaplacianEigenpairs(),MaternKernel(1,1,1))
+e=m._engine
+print('built', flush=True)
+for j in range(J):
+    for name,fn in (('A',e.phase_a),('mid',e.axis_update),('B',e.phase_b),('post',e.bias_noise)):
+        fn(j); e.synchronize(); print('layer',j,name,'ok', flush=True)
+e.sweep(1); e.synchronize(); print('graph sweep ok')
