@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcimrgp.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MODE_CI, MODE_FI = 0, 1
 OK, EINVAL, ENODEVICE, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4, -5
 
@@ -26,7 +26,7 @@ class Config(C.Structure):
     _fields_ = [('abi_version', C.c_int32), ('mode', C.c_int32), ('n_samples', C.c_int64), ('dx', C.c_int32),
                 ('dy', C.c_int32), ('n_basis', C.c_int32), ('n_layers', C.c_int32),
                 ('noise_region_specific', C.c_int32), ('bias_region_specific', C.c_int32), ('device', C.c_int32),
-                ('n_ctas', C.c_int32)]
+                ('n_ctas', C.c_int32), ('sample_begin', C.c_int64), ('sample_end', C.c_int64)]
 
 
 class MrgpError(RuntimeError):
@@ -65,6 +65,9 @@ SIGNATURES = {
     'mrgp_elbo': (C.c_int, [_P, _D]),
     'mrgp_predict_mean': (C.c_int, [_P, _P, C.c_int64, _I64PP, C.c_int32, _P]),
     'mrgp_predict_var': (C.c_int, [_P, _P, C.c_int64, _P]),
+    'mrgp_region_sums': (C.c_int, [_P, C.c_int32, C.c_int32]),
+    'mrgp_exchange_buffer': (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    'mrgp_build_basis_stage': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_double]),
     'mrgp_launch_count': (C.c_int64, [_P]),
     'mrgp_cholesky_count': (C.c_int64, [_P]),
     'mrgp_batched_cholesky': (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P]),

@@ -26,13 +26,14 @@ struct LayerPlan {
     std::vector<int32_t> cta_seg;     // n_ctas + 1
     std::vector<int32_t> seg_cta;     // per segment (host only)
     std::vector<int32_t> region_run;  // R + 1
+    std::vector<int32_t> ident_run;   // 0 .. R (dense exchange buffer: one "run" per region)
     int32_t R = 0, n_runs = 0;
 };
 
 struct LayerDev {
     // plan
     Segment *segs = nullptr;
-    int32_t *cta_seg = nullptr, *region_run = nullptr;
+    int32_t *cta_seg = nullptr, *region_run = nullptr, *ident_run = nullptr;
     int64_t *offsets = nullptr;
     // static
     double *L = nullptr, *inv2L = nullptr, *rsqrtL = nullptr, *lam = nullptr, *S = nullptr, *d = nullptr;
@@ -72,6 +73,9 @@ struct mrgp_handle {
     size_t ws_bytes = 0;
     char *ws = nullptr;
     bool bound = false, have_data = false, state_init = false;
+    bool sharded = false;
+    int64_t lo = 0, hi = 0;   // owned samples [lo, hi)
+    double *xchg = nullptr;   // dense exchange buffer (max R) x part_stride
     const double *x = nullptr, *y = nullptr;
     double *x_ws = nullptr, *y_ws = nullptr, *g = nullptr, *hvar = nullptr, *tmp_mean = nullptr, *tmp_var = nullptr;
     double *part = nullptr, *elbo_out = nullptr;
@@ -120,16 +124,20 @@ bool basis_supported(int m) { return m == 8 || m == 20 || m == 30 || m == 40; }
 
 // ---- plan -------------------------------------------------------------------------------------
 void build_plan(mrgp_handle *h) {
-    const int64_t N = h->cfg.n_samples;
+    const int64_t lo = h->lo, N = h->hi;   // the owned chunk [lo, N)
     const int J = h->cfg.n_layers;
     const int64_t Q = h->cta_quantum;
     const int G = h->n_ctas;
     for (int j = 0; j < J; ++j) {
         LayerPlan &lp = h->plan[j];
         std::vector<int64_t> cuts;
-        cuts.insert(cuts.end(), lp.offsets.begin(), lp.offsets.end());
-        if (j > 0) cuts.insert(cuts.end(), h->plan[j - 1].offsets.begin(), h->plan[j - 1].offsets.end());
-        for (int c = 0; c < G; ++c) cuts.push_back(std::min<int64_t>(N, (int64_t)c * Q));
+        for (int64_t o : lp.offsets)
+            if (o > lo && o < N) cuts.push_back(o);
+        if (j > 0)
+            for (int64_t o : h->plan[j - 1].offsets)
+                if (o > lo && o < N) cuts.push_back(o);
+        for (int c = 0; c < G; ++c) cuts.push_back(std::min<int64_t>(N, lo + (int64_t)c * Q));
+        cuts.push_back(lo);
         cuts.push_back(N);
         std::sort(cuts.begin(), cuts.end());
         cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
@@ -144,7 +152,7 @@ void build_plan(mrgp_handle *h) {
             while (lp.offsets[region + 1] <= s) ++region;
             if (poff)
                 while ((*poff)[parent + 1] <= s) ++parent;
-            const int cta = (int)(s / Q);
+            const int cta = (int)((s - lo) / Q);
             if (cta != prev_cta || region != prev_region) {
                 ++run;
                 if (region != prev_region)
@@ -164,7 +172,9 @@ void build_plan(mrgp_handle *h) {
             prev_region = region;
         }
         lp.n_runs = run + 1;
-        lp.region_run[lp.R] = lp.n_runs;
+        for (int r = prev_region + 1; r <= lp.R; ++r) lp.region_run[r] = lp.n_runs;   // regions past the chunk: empty
+        lp.ident_run.resize(lp.R + 1);
+        for (int r = 0; r <= lp.R; ++r) lp.ident_run[r] = r;
         for (size_t k = 0; k < lp.segs.size(); ++k)
             lp.segs[k].flush = (k + 1 == lp.segs.size() || lp.segs[k + 1].run != lp.segs[k].run) ? 1 : 0;
         // first segment of each CTA (CTAs past the data get an empty range)
@@ -192,7 +202,7 @@ struct Carver {
 
 size_t carve(mrgp_handle *h, char *base) {
     Carver c(base);
-    const int64_t N = h->cfg.n_samples;
+    const int64_t N = h->hi - h->lo;   // local samples
     const int DY = h->cfg.dy, M = h->cfg.n_basis, J = h->cfg.n_layers;
     const bool fi = h->cfg.mode == MRGP_MODE_FI;
     h->x_ws = c.take<double>(N * h->cfg.dx);
@@ -205,6 +215,11 @@ size_t carve(mrgp_handle *h, char *base) {
     for (int j = 0; j < J; ++j) h->max_runs = std::max(h->max_runs, h->plan[j].n_runs);
     h->part_stride = std::max(M * DY, kPartBStride);
     h->part = c.take<double>((size_t)h->max_runs * h->part_stride);
+    {
+        int rmax = 1;
+        for (int j = 0; j < J; ++j) rmax = std::max(rmax, h->plan[j].R);
+        h->xchg = c.take<double>((size_t)rmax * h->part_stride);
+    }
     h->elbo_out = c.take<double>((size_t)J * 6);
     h->elbo_args = c.take<RegionArgs>(J);
     h->off_total = 0;
@@ -221,6 +236,7 @@ size_t carve(mrgp_handle *h, char *base) {
         d.segs = c.take<Segment>(lp.segs.size());
         d.cta_seg = c.take<int32_t>(lp.cta_seg.size());
         d.region_run = c.take<int32_t>(lp.region_run.size());
+        d.ident_run = c.take<int32_t>(lp.ident_run.size());
         d.offsets = c.take<int64_t>(lp.offsets.size());
         d.L = c.take<double>(R);
         d.inv2L = c.take<double>(R);
@@ -294,10 +310,11 @@ StreamArgs stream_args(mrgp_handle *h, int j) {
     StreamArgs a{};
     a.segs = d.segs;
     a.cta_seg = d.cta_seg;
-    a.x = h->x;
-    a.y = h->y;
-    a.g = h->g;
-    a.h = h->hvar;
+    // kernels index samples by their global number: shift the (local) arrays by the chunk start
+    a.x = h->x - h->lo;
+    a.y = h->y - h->lo * h->cfg.dy;
+    a.g = h->g - h->lo * h->cfg.dy;
+    a.h = h->hvar - h->lo;
     a.inv2L = d.inv2L;
     a.rsqrtL = d.rsqrtL;
     a.A = d.A;
@@ -308,7 +325,8 @@ StreamArgs stream_args(mrgp_handle *h, int j) {
     a.pbias_var = j > 0 ? h->dev[j - 1].bias_var : nullptr;
     a.part = h->part;
     a.part_stride = h->part_stride;
-    a.n_samples = h->cfg.n_samples;
+    a.sample_begin = h->lo;
+    a.n_samples = h->hi;
     a.cta_quantum = h->cta_quantum;
     a.done_counter = h->done_counter;
     a.region_run = d.region_run;
@@ -415,6 +433,10 @@ RegionArgs region_args(mrgp_handle *h, int j) {
     a.ts = h->timeline ? h->ts : nullptr;
     a.fi_shape0_mix = h->fi_shape0_mix;
     a.fi_scale0_mix = h->fi_scale0_mix;
+    if (h->sharded) {   // the small-matrix steps read the all-reduced dense statistics: one "run" per region
+        a.region_run = d.ident_run;
+        a.part = h->xchg;
+    }
     a.use_prior = d.use_prior;
     a.nu = d.nu;
     a.ell = d.ell;
@@ -555,7 +577,7 @@ int do_axis_update(mrgp_handle *h, int j, bool fork_omega) {
     const LayerPlan &lp = h->plan[j];
     {
         const int nv = M * DY, nval = (nv + 31) & ~31;
-        const int threads = std::max(reduce_threads(nv, max_region_runs(lp), 512), ((M + 31) & ~31));
+        const int threads = std::max(reduce_threads(nv, h->sharded ? 1 : max_region_runs(lp), 512), ((M + 31) & ~31));
         const int slices = threads / nval;
         const size_t smem = (size_t)(slices * nval + nv) * sizeof(double);
         CK(set_smem(k_reduce_scale<2>, smem));
@@ -573,7 +595,7 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega) {
     if (fork_omega && j > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_join[j - 1], 0));
     int n_partials = 1;
     {
-        const int mr = max_region_runs(lp);
+        const int mr = h->sharded ? 1 : max_region_runs(lp);
         int nb = std::min(48, lp.R);
         const int rpc = (lp.R + nb - 1) / nb;
         nb = (lp.R + rpc - 1) / rpc;
@@ -621,6 +643,10 @@ int do_phase_b(mrgp_handle *h, int j, bool fuse_tail) {
 
 int do_bias_noise(mrgp_handle *h, int j) {
     StreamArgs a = stream_args(h, j);
+    if (h->sharded) {
+        a.region_run = h->dev[j].ident_run;
+        a.part = h->xchg;
+    }
     k_bias_noise<2><<<1, kThreadsB, 0, h->stream>>>(a);
     CK(cudaGetLastError());
     count(h);
@@ -765,8 +791,13 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     if (cfg->n_samples < 1) return fail(h, MRGP_EINVAL, "n_samples < 1");
     if (!cfg->noise_region_specific || !cfg->bias_region_specific)
         return fail(h, MRGP_EINVAL, "only region-specific noise and bias are implemented on the device");
+    if (cfg->sample_begin < 0 || cfg->sample_end < cfg->sample_begin || cfg->sample_end > cfg->n_samples)
+        return fail(h, MRGP_EINVAL, "bad sample range");
     h = new mrgp_handle();
     h->cfg = *cfg;
+    h->sharded = cfg->sample_end > cfg->sample_begin;   // an explicit range selects the exchange-buffer path
+    h->lo = h->sharded ? cfg->sample_begin : 0;
+    h->hi = h->sharded ? cfg->sample_end : cfg->n_samples;
     h->plan.resize(cfg->n_layers);
     h->dev.resize(cfg->n_layers);
     for (int j = 0; j < cfg->n_layers; ++j) {
@@ -796,12 +827,13 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     h->sm_count = sms;
     int want = cfg->n_ctas > 0 ? cfg->n_ctas : sms;
     const int64_t min_per_cta = 4 * kThreads;
-    const int64_t cap = std::max<int64_t>(1, (cfg->n_samples + min_per_cta - 1) / min_per_cta);
+    const int64_t n_local = h->hi - h->lo;
+    const int64_t cap = std::max<int64_t>(1, (n_local + min_per_cta - 1) / min_per_cta);
     want = (int)std::min<int64_t>(want, cap);
-    int64_t q = (cfg->n_samples + want - 1) / want;
+    int64_t q = (n_local + want - 1) / want;
     q = ((q + 31) / 32) * 32;
     h->cta_quantum = q;
-    h->n_ctas = (int)((cfg->n_samples + q - 1) / q);
+    h->n_ctas = (int)((n_local + q - 1) / q);
     build_plan(h);
     h->ws_bytes = carve(h, nullptr);
     *out = h;
@@ -856,13 +888,14 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
         CK(cudaMemcpyAsync(d.segs, lp.segs.data(), lp.segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(d.cta_seg, lp.cta_seg.data(), lp.cta_seg.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(d.region_run, lp.region_run.data(), lp.region_run.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d.ident_run, lp.ident_run.data(), lp.ident_run.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(d.offsets, lp.offsets.data(), lp.offsets.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     }
     CK(cudaMemsetAsync(h->chol_count, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->done_counter, 0, sizeof(unsigned int), h->stream));
     CK(cudaMemsetAsync(h->mid_sync, 0, 2 * kMaxLayers * sizeof(unsigned int), h->stream));
-    CK(cudaMemsetAsync(h->g, 0, (size_t)h->cfg.n_samples * h->cfg.dy * sizeof(double), h->stream));
-    CK(cudaMemsetAsync(h->hvar, 0, (size_t)h->cfg.n_samples * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->g, 0, (size_t)(h->hi - h->lo) * h->cfg.dy * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->hvar, 0, (size_t)(h->hi - h->lo) * sizeof(double), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->bound = true;
     return MRGP_OK;
@@ -892,7 +925,7 @@ int mrgp_set_data(mrgp_handle *h, const double *x_dev, const double *y_dev) {
 int mrgp_set_data_host(mrgp_handle *h, const double *x_host, const double *y_host) {
     if (!h || !x_host || !y_host) return fail(h, MRGP_EINVAL, "null argument");
     if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
-    const size_t N = (size_t)h->cfg.n_samples;
+    const size_t N = (size_t)(h->hi - h->lo);
     CK(cudaMemcpyAsync(h->x_ws, x_host, N * h->cfg.dx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->y_ws, y_host, N * h->cfg.dy * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if (h->x != h->x_ws || h->y != h->y_ws) drop_graph(h);
@@ -915,6 +948,7 @@ int mrgp_set_spectral(mrgp_handle *h, int32_t layer, int32_t use_prior, double n
 int mrgp_build_basis(mrgp_handle *h, int32_t layer, double interval_factor, const double *L_host) {
     int rc = check_ready(h, layer, false);
     if (rc) return rc;
+    if (h->sharded) return fail(h, MRGP_ESTATE, "sharded handle: use mrgp_build_basis_stage with all-reduces in between");
     LayerDev &d = h->dev[layer];
     const LayerPlan &lp = h->plan[layer];
     StreamArgs sa = stream_args(h, layer);
@@ -978,8 +1012,8 @@ int mrgp_init_state(mrgp_handle *h, double noise_var0, double ard_prior_influenc
         CK(cudaGetLastError());
         count(h);
     }
-    CK(cudaMemsetAsync(h->g, 0, (size_t)h->cfg.n_samples * h->cfg.dy * sizeof(double), h->stream));
-    CK(cudaMemsetAsync(h->hvar, 0, (size_t)h->cfg.n_samples * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->g, 0, (size_t)(h->hi - h->lo) * h->cfg.dy * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->hvar, 0, (size_t)(h->hi - h->lo) * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->sh.omegaWarm, 0, kMaxLayers * sizeof(double), h->stream));
     drop_graph(h);
     h->sweeps_done = 0;
@@ -999,6 +1033,7 @@ int mrgp_get_state(mrgp_handle *h, int32_t layer, int32_t field, double *dst_hos
     FieldRef f = field_ref(h, layer, field);
     if (!f.ptr || f.n <= 0) return fail(h, MRGP_EINVAL, "unknown field %d for layer %d", field, layer);
     if ((int64_t)n_elems != f.n) return fail(h, MRGP_EINVAL, "field %d has %lld elements, caller passed %zu", field, (long long)f.n, n_elems);
+    if ((field == MRGP_F_FBAR || field == MRGP_F_FVAR) && h->sharded) return fail(h, MRGP_EINVAL, "latent export is not available on a sharded handle");
     if (field == MRGP_F_FBAR || field == MRGP_F_FVAR) {
         // latent functions of `layer`: sum over coarser layers (Stats.py:126-157), recomputed on demand
         int rc = check_ready(h, layer, true);
@@ -1062,6 +1097,7 @@ int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
     int rc = check_ready(h, 0, true);
     if (rc) return rc;
     if (n_iter < 0) return fail(h, MRGP_EINVAL, "n_iter < 0");
+    if (h->sharded) return fail(h, MRGP_ESTATE, "mrgp_sweep on a sharded handle: drive the phases and the all-reduces from the host");
     if (!h->graph_exec) {
         h->launches_per_sweep = 0;
         h->capturing = true;
@@ -1163,6 +1199,64 @@ int mrgp_predict_var(mrgp_handle *h, const double *x_test_dev, int64_t n_test, d
     CK(cudaGetLastError());
     count(h);
     CK(cudaStreamSynchronize(h->stream));
+    return MRGP_OK;
+}
+
+int mrgp_region_sums(mrgp_handle *h, int32_t layer, int32_t which) {
+    int rc = check_ready(h, layer, false);
+    if (rc) return rc;
+    if (!h->sharded) return fail(h, MRGP_ESTATE, "not a sharded handle");
+    const LayerPlan &lp = h->plan[layer];
+    const int nv = which == MRGP_X_PHASE_A ? h->cfg.n_basis * h->cfg.dy : h->cfg.dy + 3;
+    const int total = lp.R * h->part_stride;
+    k_region_sums<false><<<(total + 255) / 256, 256, 0, h->stream>>>(h->dev[layer].region_run, h->part, h->part_stride, nv, lp.R, h->xchg);
+    CK(cudaGetLastError());
+    count(h);
+    return MRGP_OK;
+}
+
+int mrgp_exchange_buffer(mrgp_handle *h, int32_t layer, int32_t which, void **dev_ptr, size_t *n_doubles) {
+    if (!h || !dev_ptr || !n_doubles || layer < 0 || layer >= h->cfg.n_layers) return fail(h, MRGP_EINVAL, "bad argument");
+    if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
+    (void)which;
+    *dev_ptr = h->xchg;
+    *n_doubles = (size_t)h->plan[layer].R * h->part_stride;
+    return MRGP_OK;
+}
+
+int mrgp_build_basis_stage(mrgp_handle *h, int32_t layer, int32_t stage, double interval_factor) {
+    int rc = check_ready(h, layer, false);
+    if (rc) return rc;
+    if (!h->sharded) return fail(h, MRGP_ESTATE, "not a sharded handle");
+    LayerDev &d = h->dev[layer];
+    const LayerPlan &lp = h->plan[layer];
+    StreamArgs sa = stream_args(h, layer);
+    RegionArgs ra = region_args(h, layer);
+    ra.interval_factor = interval_factor;
+    const int total = lp.R * h->part_stride;
+    if (stage == 0) {          // local max|x| per region -> exchange buffer (caller: all-reduce MAX)
+        k_absmax<<<h->n_ctas, kThreads, 0, h->stream>>>(sa);
+        CK(cudaGetLastError());
+        k_region_sums<true><<<(total + 255) / 256, 256, 0, h->stream>>>(d.region_run, h->part, h->part_stride, 1, lp.R, h->xchg);
+        CK(cudaGetLastError());
+        count(h, 2);
+    } else if (stage == 1) {   // L, lambda, S from the global max; local sum phi^2 -> exchange buffer (all-reduce SUM)
+        k_region_setup<<<(lp.R + 7) / 8, 256, 0, h->stream>>>(ra);
+        CK(cudaGetLastError());
+        cudaError_t e = cudaErrorInvalidValue;
+        DISPATCH_M(h->cfg.n_basis, e = launch_phi2sum<MM>(h, sa));
+        CK(e);
+        k_region_sums<false><<<(total + 255) / 256, 256, 0, h->stream>>>(d.region_run, h->part, h->part_stride, h->cfg.n_basis, lp.R, h->xchg);
+        CK(cudaGetLastError());
+        count(h, 3);
+    } else if (stage == 2) {   // d = global sum phi^2
+        k_reduce_d<<<lp.R, 64, 0, h->stream>>>(ra);
+        CK(cudaGetLastError());
+        count(h);
+        d.basis_built = true;
+    } else {
+        return fail(h, MRGP_EINVAL, "stage must be 0, 1 or 2");
+    }
     return MRGP_OK;
 }
 

@@ -65,7 +65,8 @@ struct StreamArgs {
     const double *pbias_var;     // (Rp)
     double *part;                // partial sums per run
     int32_t part_stride;
-    int64_t n_samples;
+    int64_t sample_begin;        // first sample of this handle's chunk (0 unless sharded over GPUs)
+    int64_t n_samples;           // end of the chunk (exclusive)
     int64_t cta_quantum;         // samples per CTA range (multiple of 32)
     // bias / noise update fused into the tail of phase B (run by the last CTA to finish)
     unsigned int *done_counter;
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_phase_a(StreamArgs p) {
     __shared__ __align__(8) uint64_t full_bar[kStages];
     __shared__ __align__(8) uint64_t empty_bar[kStages];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t c0 = (int64_t)blockIdx.x * p.cta_quantum;
+    const int64_t c0 = p.sample_begin + (int64_t)blockIdx.x * p.cta_quantum;
     const int64_t c1 = (c0 + p.cta_quantum < p.n_samples) ? c0 + p.cta_quantum : p.n_samples;
     const int n_tiles = (c1 > c0) ? (int)((c1 - c0 + kTile - 1) / kTile) : 0;
     ts_begin(p.ts, p.layer * 4 + 0);
@@ -587,7 +588,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) k_phase_b(StreamArgs p) {
     __shared__ __align__(8) uint64_t full_bar[kStages];
     __shared__ __align__(8) uint64_t empty_bar[kStages];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t c0 = (int64_t)blockIdx.x * p.cta_quantum;
+    const int64_t c0 = p.sample_begin + (int64_t)blockIdx.x * p.cta_quantum;
     const int64_t c1 = (c0 + p.cta_quantum < p.n_samples) ? c0 + p.cta_quantum : p.n_samples;
     const int n_tiles = (c1 > c0) ? (int)((c1 - c0 + kTile - 1) / kTile) : 0;
     ts_begin(p.ts, p.layer * 4 + 2);
@@ -1191,6 +1192,22 @@ __global__ void __launch_bounds__(kOmegaThreads) k_omega(RegionArgs a, int n_par
         a.omegaWarm[a.layer] = 1.0;
     }
     ts_end(a.ts, a.layer * 4 + 3);
+}
+
+// Dense per-region sums of the run partials (multi-GPU exchange buffer): out[r][v] = sum over the
+// local runs of region r (zero for regions without local samples); MAX = true for the max|x| partials.
+template <bool MAX>
+__global__ void k_region_sums(const int32_t *region_run, const double *part, int part_stride, int nv, int R, double *out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= R * part_stride) return;
+    const int r = t / part_stride, v = t % part_stride;
+    double acc = 0.0;
+    if (v < nv)
+        for (int q = region_run[r]; q < region_run[r + 1]; ++q) {
+            const double x = part[(size_t)q * part_stride + v];
+            acc = MAX ? fmax(acc, x) : acc + x;
+        }
+    out[(size_t)r * part_stride + v] = acc;   // padding columns are kept at zero
 }
 
 // Standalone bias / noise update (per-phase ABI entry; the sweep uses the fused tail of phase B).

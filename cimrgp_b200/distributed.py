@@ -1,0 +1,100 @@
+"""Sample-sharded engine: one process per GPU, torch.distributed (NCCL) for the exchange step.
+
+Each rank owns a contiguous chunk of the samples (x, y and the latent buffers never leave the GPU); after each
+streaming phase the per-region sufficient statistics (<= R x 60 doubles per layer) are summed over the ranks
+with one all-reduce, and the small-matrix steps are replicated (identical inputs -> identical state on every
+rank, no broadcast).  SURVEY.md §8e.  The whole sweep, collectives included, is captured once in a CUDA graph.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .engine import Engine
+
+
+def chunk_bounds(n_samples, world_size, rank):
+    """Contiguous, 32-aligned split of [0, n_samples): the same chunking for every layer."""
+    per = -(-n_samples // world_size)
+    per = -(-per // 32) * 32
+    lo = min(n_samples, rank * per)
+    hi = min(n_samples, lo + per)
+    return lo, hi
+
+
+class TorchComm(object):
+    """all-reduce of a device tensor over a torch.distributed process group (NCCL on GPUs)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+
+    def all_reduce(self, tensor, op):
+        d = self.dist
+        d.all_reduce(tensor, op=d.ReduceOp.MAX if op == 'max' else d.ReduceOp.SUM, group=self.group)
+
+
+class ShardedEngine(Engine):
+    def __init__(self, x_norm, y, offsets, n_basis, rank, world_size, comm=None, **kw):
+        self.comm = comm if comm is not None else TorchComm()
+        self.rank, self.world_size = rank, world_size
+        n_total = int(offsets[0][-1])
+        lo, hi = chunk_bounds(n_total, world_size, rank)
+        if hi <= lo:
+            raise ValueError('rank %d owns no samples' % rank)
+        Engine.__init__(self, x_norm[lo:hi], y[lo:hi], offsets, n_basis, chunk=(lo, hi), defer_build=True, **kw)
+        torch = self.torch
+        self._xchg = []
+        for j in range(self.J):
+            ptr, n = C.c_void_p(), C.c_size_t()
+            self._ck(self.lib.mrgp_exchange_buffer(self.handle, j, 0, C.byref(ptr), C.byref(n)))
+            off = ptr.value - self.workspace.data_ptr()
+            self._xchg.append(self.workspace[off:off + 8 * n.value].view(torch.float64))
+        self._graph = None
+        with torch.cuda.stream(self.stream):
+            for j in range(self.J):
+                self._ck(self.lib.mrgp_build_basis_stage(self.handle, j, 0, float(self._interval_factor[j])))
+                self.comm.all_reduce(self._xchg[j], 'max')
+                self._ck(self.lib.mrgp_build_basis_stage(self.handle, j, 1, float(self._interval_factor[j])))
+                self.comm.all_reduce(self._xchg[j], 'sum')
+                self._ck(self.lib.mrgp_build_basis_stage(self.handle, j, 2, float(self._interval_factor[j])))
+            self._ck(self.lib.mrgp_init_state(self.handle, *self._init_args))
+        self.synchronize()
+
+    def _sweep_body(self):
+        lib, h = self.lib, self.handle
+        for j in range(self.J):
+            self._ck(lib.mrgp_phase_a(h, j))
+            self._ck(lib.mrgp_region_sums(h, j, 0))
+            self.comm.all_reduce(self._xchg[j], 'sum')
+            self._ck(lib.mrgp_axis_update(h, j))
+            self._ck(lib.mrgp_phase_b(h, j))
+            self._ck(lib.mrgp_region_sums(h, j, 1))
+            self.comm.all_reduce(self._xchg[j], 'sum')
+            self._ck(lib.mrgp_bias_noise(h, j))
+
+    def sweep(self, n_iter=1, use_graph=True):
+        torch = self.torch
+        if not use_graph:
+            with torch.cuda.stream(self.stream):
+                for _ in range(n_iter):
+                    self._sweep_body()
+            return
+        if self._graph is None:
+            with torch.cuda.stream(self.stream):
+                self._sweep_body()                       # warm-up outside capture (NCCL lazy init)
+            self.stream.synchronize()
+            n_iter -= 1
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph, stream=self.stream):
+                self._sweep_body()
+            # capture records, it does not execute
+        for _ in range(n_iter):
+            with torch.cuda.stream(self.stream):
+                self._graph.replay()
+
+    def latent(self, j):
+        raise NotImplementedError('latent export is not available on a sharded engine')
+
+    def state(self, latent=False):
+        return Engine.state(self, latent=False)

@@ -25,12 +25,14 @@ class Engine(object):
 
     def __init__(self, x_norm, y, offsets, n_basis, mode='ci', spectral=None, interval_factor=None,
                  noise_var0=1.0, ard_prior_influence=1.0, noise_region_specific=True, bias_region_specific=True,
-                 device=0, n_ctas=0, intervals=None):
+                 device=0, n_ctas=0, intervals=None, chunk=None, defer_build=False):
         import torch
         self.torch = torch
         self.lib = _lib.load()
         self.handle = None
         self.N = int(x_norm.shape[0])
+        self.chunk = chunk            # (lo, hi) of the N_total samples owned by this handle, or None
+        self.N_total = int(offsets[0][-1])
         self.dx = int(x_norm.shape[1]) if x_norm.ndim > 1 else 1
         self.dy = int(y.shape[1])
         self.M = int(n_basis)
@@ -38,9 +40,10 @@ class Engine(object):
         self.mode = mode
         self.offsets = [np.ascontiguousarray(o, dtype=np.int64) for o in offsets]
         self.R = [len(o) - 1 for o in self.offsets]
-        cfg = _lib.Config(_lib.ABI_VERSION, _lib.MODE_CI if mode == 'ci' else _lib.MODE_FI, self.N, self.dx, self.dy,
+        lo, hi = chunk if chunk is not None else (0, 0)
+        cfg = _lib.Config(_lib.ABI_VERSION, _lib.MODE_CI if mode == 'ci' else _lib.MODE_FI, self.N_total, self.dx, self.dy,
                           self.M, self.J, int(bool(noise_region_specific)), int(bool(bias_region_specific)),
-                          int(device), int(n_ctas))
+                          int(device), int(n_ctas), int(lo), int(hi))
         ptrs, keep = _lib.offsets_arg(self.offsets)
         nreg = (C.c_int32 * self.J)(*self.R)
         out = C.c_void_p()
@@ -63,15 +66,19 @@ class Engine(object):
         self.set_data(x_norm, y)
         spectral = spectral if spectral is not None else [(1., 1., 1.)] * self.J
         interval_factor = interval_factor if interval_factor is not None else [1.0] * self.J
+        self._interval_factor = interval_factor
+        self._init_args = (float(noise_var0), float(ard_prior_influence))
         for j in range(self.J):
             sp = spectral[j]
             if sp is None:
                 self._ck(self.lib.mrgp_set_spectral(self.handle, j, 0, 1., 1., 1.))
             else:
                 self._ck(self.lib.mrgp_set_spectral(self.handle, j, 1, float(sp[0]), float(sp[1]), float(sp[2])))
-            self.build_basis(j, interval_factor[j], None if intervals is None else intervals[j])
-        self._ck(self.lib.mrgp_init_state(self.handle, float(noise_var0), float(ard_prior_influence)))
-        self.synchronize()
+            if not defer_build:
+                self.build_basis(j, interval_factor[j], None if intervals is None else intervals[j])
+        if not defer_build:
+            self._ck(self.lib.mrgp_init_state(self.handle, float(noise_var0), float(ard_prior_influence)))
+            self.synchronize()
 
     # ------------------------------------------------------------------------------------------
     def _ck(self, rc):

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MRGP_ABI_VERSION 1
+#define MRGP_ABI_VERSION 2
 
 enum {
     MRGP_OK = 0,
@@ -104,6 +104,8 @@ typedef struct mrgp_config {
     int32_t bias_region_specific;   /* MRGP.py:28 (1 supported)                                      */
     int32_t device;                 /* CUDA device ordinal                                           */
     int32_t n_ctas;                 /* streaming grid size; 0 = one persistent CTA per SM            */
+    int64_t sample_begin;           /* sample sharding (multi-GPU): this handle owns samples           */
+    int64_t sample_end;             /* [sample_begin, sample_end) of the N; 0, 0 = all of them         */
 } mrgp_config;
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
@@ -181,6 +183,23 @@ int mrgp_predict_mean(mrgp_handle *h, const double *x_test_dev, int64_t n_test,
                       const int64_t *const *test_offsets, int32_t n_test_layers, double *out_dev);
 /* Layer-0 central second moment sum_i cm2_i phi_i^2 + bias_var (MRGP.py:833-861). out_dev (n_test,). */
 int mrgp_predict_var(mrgp_handle *h, const double *x_test_dev, int64_t n_test, double *out_dev);
+
+/* ---- sample sharding over several GPUs ------------------------------------------ */
+
+/* A handle created with [sample_begin, sample_end) streams only its chunk of x, y (mrgp_set_data* take the
+ * LOCAL rows) but knows every region.  The per-region sufficient statistics of a phase are gathered into one
+ * dense exchange buffer, summed over the ranks by the caller (NCCL all-reduce on the handle's stream) and
+ * consumed by the replicated small-matrix step:
+ *     mrgp_phase_a   -> mrgp_region_sums(layer, MRGP_X_PHASE_A) -> all-reduce SUM -> mrgp_axis_update
+ *     mrgp_phase_b   -> mrgp_region_sums(layer, MRGP_X_PHASE_B) -> all-reduce SUM -> mrgp_bias_noise
+ * and at construction
+ *     mrgp_build_basis_stage(layer, 0) -> all-reduce MAX -> stage 1 -> all-reduce SUM -> stage 2.
+ * mrgp_sweep() is refused on a sharded handle (the collectives belong to the caller, who captures the whole
+ * sequence in a CUDA graph).  No per-sample data ever leaves a GPU.                                       */
+enum { MRGP_X_PHASE_A = 0, MRGP_X_PHASE_B = 1 };
+int mrgp_region_sums(mrgp_handle *h, int32_t layer, int32_t which);
+int mrgp_exchange_buffer(mrgp_handle *h, int32_t layer, int32_t which, void **dev_ptr, size_t *n_doubles);
+int mrgp_build_basis_stage(mrgp_handle *h, int32_t layer, int32_t stage, double interval_factor);
 
 /* ---- counters and micro-benchmarks ------------------------------------------------------------ */
 

@@ -262,3 +262,69 @@ def test_constructor_errors_match_reference():
         m.get_predicted_mean(x, index_set_obj=IndexSetUniform(64, 2, 3))               # MRGP.py:762-764
     assert len(m.posterior_obj) == 3 and m.stats_obj[2].scale_axis_mean[3].shape == (2, 30)
     assert m.phi_x[1][1].shape == (32, 30) and m.stats_obj[1].latent_f_var[0].shape == (32, 1)
+
+
+class _ThreadComm(object):
+    """In-process stand-in for the NCCL all-reduce: the ranks are Python threads driving their own handle (all on
+    cuda:0); tensors are summed through host-synchronised device ops."""
+
+    def __init__(self, world):
+        import threading
+        self.world, self.slots, self.barrier = world, [None] * world, threading.Barrier(world)
+        self.local = threading.local()
+
+    def all_reduce(self, tensor, op):
+        import torch
+        torch.cuda.synchronize()
+        self.slots[self.local.rank] = tensor
+        self.barrier.wait()
+        stack = torch.stack([t for t in self.slots])
+        res = stack.max(0).values if op == 'max' else stack.sum(0)
+        torch.cuda.synchronize()
+        self.barrier.wait()
+        tensor.copy_(res)
+        torch.cuda.synchronize()
+        self.barrier.wait()
+
+
+@pytest.mark.parametrize('fi,world', [(False, 2), (True, 3)])
+def test_sample_sharding_matches_single_handle(fi, world):
+    """The multi-GPU decomposition (sample chunks + all-reduced region statistics) on one device: every rank must
+    end with the state of the unsharded run (up to the summation order of the exchanged statistics)."""
+    import threading
+    from cimrgp_b200.distributed import ShardedEngine, chunk_bounds
+    from cimrgp_b200.engine import Engine
+    n, res, M = 30000, 6, 30
+    x, y = workloads.workload1(n)
+    xs = (x - x.mean(0)) / x.std(0)
+    offsets = O.uniform_offsets(n, res, 2)
+    mode = 'fi' if fi else 'ci'
+    ref = Engine(xs, y, offsets, M, mode=mode)
+    ref.sweep(3)
+    ref.synchronize()
+    comm = _ThreadComm(world)
+    engines, errors = [None] * world, []
+
+    def work(rank):
+        try:
+            comm.local.rank = rank
+            e = ShardedEngine(xs, y, offsets, M, rank, world, comm=comm, mode=mode)
+            for _ in range(3):
+                e.sweep(1, use_graph=False)
+            e.synchronize()
+            engines[rank] = e
+        except Exception as ex:   # pragma: no cover
+            errors.append(ex)
+            comm.barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    assert sum(hi - lo for lo, hi in (chunk_bounds(n, world, r) for r in range(world))) == n
+    want = ref.state(latent=False)
+    for e in engines:
+        compare(e.state(), want, rtol=1e-9)
+    a, b = engines[0].state(), engines[-1].state()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k     # replicated small-matrix steps: identical on every rank
