@@ -52,7 +52,8 @@ class MultiResolutionGaussianProcess(object):
                  forced_independence=False,
                  verbose=False,
                  device=0,
-                 n_ctas=0):
+                 n_ctas=0,
+                 distributed=False):
         self.verbose = verbose
         self.forced_independence = forced_independence
         # MRGP.py:38-50
@@ -145,11 +146,20 @@ class MultiResolutionGaussianProcess(object):
             else:
                 spectral.append((1., 1., 1.))
                 host_spectral.append(s)       # any object with .spectral(s): evaluated on the host, uploaded
-        self._engine = Engine(x_used, y_train, self._offsets, n_basis, mode='fi' if forced_independence else 'ci',
-                              spectral=spectral, interval_factor=[float(f) for f in self.interval_factor],
-                              noise_var0=noise_var0, ard_prior_influence=float(np.mean(sf)),
-                              noise_region_specific=noise_region_specific, bias_region_specific=bias_region_specific,
-                              device=device, n_ctas=n_ctas)
+        engine_kw = dict(mode='fi' if forced_independence else 'ci',
+                         spectral=spectral, interval_factor=[float(f) for f in self.interval_factor],
+                         noise_var0=noise_var0, ard_prior_influence=float(np.mean(sf)),
+                         noise_region_specific=noise_region_specific, bias_region_specific=bias_region_specific,
+                         device=device, n_ctas=n_ctas)
+        if distributed:
+            # one process per GPU (torch.distributed initialised by the caller): this rank keeps its chunk of
+            # the samples, the region statistics are all-reduced, the model state is replicated on every rank
+            import torch.distributed as dist
+            from .distributed import ShardedEngine
+            self._engine = ShardedEngine(x_used, y_train, self._offsets, n_basis, dist.get_rank(),
+                                         dist.get_world_size(), **engine_kw)
+        else:
+            self._engine = Engine(x_used, y_train, self._offsets, n_basis, **engine_kw)
         if any(s is not None for s in host_spectral):
             eng = self._engine
             for j, s in enumerate(host_spectral):

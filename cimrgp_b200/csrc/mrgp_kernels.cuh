@@ -1108,11 +1108,14 @@ __global__ void __launch_bounds__(kOmegaThreads) k_omega(RegionArgs a, int n_par
     // the un-shifted table, so that they do not depend on the shifts) seed the iteration
     const bool warm = a.omegaWarm[a.layer] > 0.5;
     __syncthreads();
-    if (tid < M) v[tid] = warm ? exp(fmax(-700.0, fmin(700.0, a.omegaEta[a.layer * 64 + tid] + cshift[tid]))) : 1.0;
+    if (tid < M) {
+        const double eta = a.omegaEta[a.layer * 64 + tid] + cshift[tid];
+        v[tid] = (warm && isfinite(eta)) ? exp(fmax(-600.0, fmin(600.0, eta))) : 1.0;
+    }
     __syncthreads();
     int iters = 0;
     double err_prev = INFINITY;
-    const int n_warmup = warm ? 0 : kOmegaWarmup;
+    int n_warmup = warm ? 0 : kOmegaWarmup;
     for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
         ++iters;
         for (int i = warp; i < M; i += NW) {
@@ -1139,8 +1142,15 @@ __global__ void __launch_bounds__(kOmegaThreads) k_omega(RegionArgs a, int n_par
         __syncthreads();
         const double err = red[0];
         if (err < kOmegaTol) break;
+        if (!isfinite(err)) {   // a bad (warm) start or an overshooting Newton step: start again from the shifts alone
+            if (tid < M) v[tid] = 1.0;
+            err_prev = INFINITY;
+            n_warmup = it + 1 + kOmegaWarmup;
+            __syncthreads();
+            continue;
+        }
         if (it < n_warmup || !(err < err_prev)) {
-            if (tid < M) v[tid] /= c[tid];   // Sinkhorn column step
+            if (tid < M) v[tid] = fmax(1e-280, fmin(1e280, v[tid] / c[tid]));   // Sinkhorn column step
             err_prev = (it < n_warmup) ? INFINITY : err;
             __syncthreads();
             continue;
@@ -1182,7 +1192,37 @@ __global__ void __launch_bounds__(kOmegaThreads) k_omega(RegionArgs a, int n_par
             if (tid == j) xv[j] = xj;
             __syncthreads();
         }
-        if (tid < M) v[tid] *= exp(fmax(-30.0, fmin(30.0, xv[tid])));
+        if (tid < M) v[tid] = fmax(1e-280, fmin(1e280, v[tid] * exp(fmax(-30.0, fmin(30.0, xv[tid])))));
+        __syncthreads();
+    }
+    // last resort: plain Sinkhorn sweeps (see omega_solve_serial); on model tables the loop exits at its first test
+    for (int it = 0; it < kOmegaFallbackSweeps; ++it) {
+        for (int i = warp; i < M; i += NW) {
+            double s = 0.0;
+            for (int k = lane; k < M; k += 32) s = fma(K[i * M + k], v[k], s);
+            s = warp_sum(s);
+            const double u = 1.0 / s;
+            for (int k = lane; k < M; k += 32) P[i * M + k] = K[i * M + k] * v[k] * u;
+        }
+        __syncthreads();
+        for (int k = warp; k < M; k += NW) {
+            double s = 0.0;
+            for (int i = lane; i < M; i += 32) s += P[i * M + k];
+            s = warp_sum(s);
+            if (lane == 0) c[k] = s;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double e = 0.0;
+            for (int k = lane; k < M; k += 32) e = fmax(e, fabs(c[k] - 1.0));
+            e = warp_max(e);
+            if (lane == 0) red[0] = e;
+        }
+        __syncthreads();
+        const double err = red[0];
+        if (err < kOmegaTol || !isfinite(err)) break;
+        ++iters;
+        if (tid < M) v[tid] = fmax(1e-280, fmin(1e280, v[tid] / c[tid]));
         __syncthreads();
     }
     for (int t = tid; t < M * M; t += kOmegaThreads) a.omega[t] = P[t];

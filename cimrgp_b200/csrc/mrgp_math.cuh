@@ -218,6 +218,7 @@ MRGP_HD void bingham2(double a, double b, double c, Bingham2 &out) {
 constexpr int kOmegaWarmup = 6;
 constexpr int kOmegaMaxNewton = 40;
 constexpr double kOmegaTol = 1e-13;
+constexpr int kOmegaFallbackSweeps = 2000;
 
 inline int omega_solve_serial(const double *lw, int M, double *omega, double *K, double *P, double *S, double *v,
                               double *c, double *rhs, double *dinv) {
@@ -233,6 +234,7 @@ inline int omega_solve_serial(const double *lw, int M, double *omega, double *K,
         v[k] = 1.0;
     }
     int iters = 0;
+    int n_warmup = kOmegaWarmup;
     double err_prev = INFINITY;
     for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
         ++iters;
@@ -250,9 +252,15 @@ inline int omega_solve_serial(const double *lw, int M, double *omega, double *K,
             err = fmax(err, fabs(s - 1.0));
         }
         if (err < kOmegaTol) break;
-        if (it < kOmegaWarmup || !(err < err_prev)) {
-            for (int k = 0; k < M; ++k) v[k] /= c[k];   // Sinkhorn column step
-            err_prev = (it < kOmegaWarmup) ? INFINITY : err;
+        if (!isfinite(err)) {   // overshooting Newton step: start again from the shifts alone
+            for (int k = 0; k < M; ++k) v[k] = 1.0;
+            err_prev = INFINITY;
+            n_warmup = it + 1 + kOmegaWarmup;
+            continue;
+        }
+        if (it < n_warmup || !(err < err_prev)) {
+            for (int k = 0; k < M; ++k) v[k] = fmax(1e-280, fmin(1e280, v[k] / c[k]));   // Sinkhorn column step
+            err_prev = (it < n_warmup) ? INFINITY : err;
             continue;
         }
         err_prev = err;
@@ -278,7 +286,27 @@ inline int omega_solve_serial(const double *lw, int M, double *omega, double *K,
             rhs[j] *= dinv[j];
             for (int i = 0; i < j; ++i) rhs[i] -= S[j * M + i] * rhs[j];
         }
-        for (int k = 0; k < M; ++k) v[k] *= exp(fmax(-30.0, fmin(30.0, rhs[k])));
+        for (int k = 0; k < M; ++k) v[k] = fmax(1e-280, fmin(1e280, v[k] * exp(fmax(-30.0, fmin(30.0, rhs[k])))));
+    }
+    // last resort (not seen on model tables, reachable with synthetic near-permutation input): plain Sinkhorn
+    // sweeps from the current scalings until the tolerance or the iteration cap
+    for (int it = 0; it < kOmegaFallbackSweeps; ++it) {
+        double err = 0.0;
+        for (int i = 0; i < M; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < M; ++k) s = fma(K[i * M + k], v[k], s);
+            const double u = 1.0 / s;
+            for (int k = 0; k < M; ++k) P[i * M + k] = K[i * M + k] * v[k] * u;
+        }
+        for (int k = 0; k < M; ++k) {
+            double s = 0.0;
+            for (int i = 0; i < M; ++i) s += P[i * M + k];
+            c[k] = s;
+            err = fmax(err, fabs(s - 1.0));
+        }
+        if (err < kOmegaTol || !isfinite(err)) break;
+        ++iters;
+        for (int k = 0; k < M; ++k) v[k] = fmax(1e-280, fmin(1e280, v[k] / c[k]));
     }
     for (int t = 0; t < M * M; ++t) omega[t] = P[t];
     return iters;

@@ -73,8 +73,11 @@ class ShardedEngine(Engine):
             self.comm.all_reduce(self._xchg[j], 'sum')
             self._ck(lib.mrgp_bias_noise(h, j))
 
-    def sweep(self, n_iter=1, use_graph=True):
+    def sweep(self, n_iter=1, use_graph=None):
+        import os
         torch = self.torch
+        if use_graph is None:
+            use_graph = os.environ.get('MRGP_SHARDED_GRAPH', '1') != '0'
         if not use_graph:
             with torch.cuda.stream(self.stream):
                 for _ in range(n_iter):
