@@ -596,21 +596,27 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega) {
     int n_partials = 1;
     {
         const int mr = h->sharded ? 1 : max_region_runs(lp);
-        int nb = std::min(48, lp.R);
+        int nb = std::min(32, lp.R);
         const int rpc = (lp.R + nb - 1) / nb;
         nb = (lp.R + rpc - 1) / rpc;
         const int items_cta = std::min(rpc, 32) * M;
         int lpi = 1;
         while (lpi < 32 && lpi * 2 <= mr && lpi * 2 * items_cta <= kMidThreads) lpi *= 2;
         const int nvp = (M * 3 + 31) & ~31;
-        const size_t smem = (size_t)(std::max(std::max(32 * M * 4 + nvp, M * M + 4 * M + 3 * nvp), 37 * M)) * sizeof(double);
-        CK(set_smem(k_mid_ci<2>, smem));
-        int rpc_arg = rpc;
-        unsigned int *sync_words = h->mid_sync + 2 * j;
-        void *args[] = {&a, &lpi, &rpc_arg, &sync_words};
-        CK(cudaLaunchCooperativeKernel((const void *)k_mid_ci<2>, dim3(nb), dim3(kMidThreads), args, smem, h->stream));
+        const size_t smem1 = (size_t)(32 * M * 4 + nvp) * sizeof(double);
+        CK(set_smem(k_mid1<2>, smem1));
+        k_mid1<2><<<nb, kMidThreads, smem1, h->stream>>>(a, lpi, rpc);
+        CK(cudaGetLastError());
         count(h);
-        n_partials = nb;
+        int nb2 = std::min(h->sm_count, lp.R);
+        const int rpc2 = (lp.R + nb2 - 1) / nb2;
+        nb2 = (lp.R + rpc2 - 1) / rpc2;
+        const size_t smem2 = (size_t)(std::max(33 * M, M * M + 4 * M + 3 * nvp) + 4 * M) * sizeof(double);
+        CK(set_smem(k_mid2<2>, smem2));
+        k_mid2<2><<<nb2, kMidThreads, smem2, h->stream>>>(a, rpc2, nb);
+        CK(cudaGetLastError());
+        count(h);
+        n_partials = nb2;
     }
     {
         cudaStream_t st = h->stream;

@@ -863,10 +863,9 @@ __global__ void __launch_bounds__(512) k_reduce_scale(RegionArgs a) {
 constexpr int kMidThreads = 256;
 
 template <int DY>
-__global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, int regions_per_cta, unsigned int *sync_words) {
+__global__ void __launch_bounds__(kMidThreads) k_mid1(RegionArgs a, int lpi, int regions_per_cta) {
     static_assert(DY == 2, "dy == 2 only");
     extern __shared__ double sm[];   // contrib[32 * M * 4] + sums[96]; last CTA: omega[M*M], primeB[M*4], data[96]
-    __shared__ int sLast;
     const int M = a.M, tid = threadIdx.x, NV = M * 3, NVP = (NV + 31) & ~31;   // NVP: padded length of a B-sum vector
     double *sContrib = sm, *sSum = sm + 32 * M * 4;
     ts_begin(a.ts, a.layer * 4 + 1);
@@ -921,36 +920,37 @@ __global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, i
         __syncthreads();
     }
     if (tid < NVP) a.bcontrib[(size_t)blockIdx.x * NVP + tid] = sSum[tid];   // per-CTA partial of sum_l contrib
-    // ---- grid barrier with work: the last CTA to arrive does the cross-region part, the others wait for it ----
-    // (cooperative launch: all CTAs are co-resident; sync_words = {arrival counter, completed generations} of
-    // this layer, both only ever incremented, so the captured graph can be replayed without resetting them)
-    __syncthreads();
-    __shared__ unsigned int sGen;
-    if (tid == 0) {
-        const unsigned int ticket = atom_add_acq_rel_gpu(&sync_words[0], 1u);
-        sGen = ticket / gridDim.x;
-        sLast = (ticket % gridDim.x == gridDim.x - 1);
+    if (blockIdx.x == 0) {   // snapshot of the previous posterior (MRGP.py:575 / :581): k_mid2 and k_omega read it
+        const bool first = (a.layer == 0);
+        for (int t = tid; t < M * 4; t += kMidThreads) a.primeB[t] = first ? a.priorB[t] : a.axB[t];
+        for (int t = tid; t < M; t += kMidThreads) {
+            a.primeLogC[t] = first ? a.priorLogC[t] : a.axLogC[t];
+            a.primeShape[t] = first ? a.priorShape[t] : a.ardShape[t];
+            a.primeScale[t] = first ? a.priorScale[t] : a.ardScale[t];
+        }
     }
-    __syncthreads();
-    const unsigned int gen = sGen;
-    if (sLast) {
-    const bool first = (a.layer == 0);
+    ts_end(a.ts, a.layer * 4 + 1);
+}
+
+// Second half of the ci mid-step.  Every CTA re-derives the axis update from the per-CTA partial sums of k_mid1
+// (a few microseconds of redundant work instead of a grid-wide hand-off), then finishes S2 for its regions.
+template <int DY>
+__global__ void __launch_bounds__(kMidThreads) k_mid2(RegionArgs a, int regions_per_cta, int n_partials) {
+    static_assert(DY == 2, "dy == 2 only");
+    extern __shared__ double sm[];
+    const int M = a.M, tid = threadIdx.x, NV = M * 3, NVP = (NV + 31) & ~31;
+    (void)NV;
+    ts_begin(a.ts, a.layer * 4 + 1);
+    const int r0 = blockIdx.x * regions_per_cta;
+    const int r1 = (r0 + regions_per_cta < a.R) ? r0 + regions_per_cta : a.R;
     double *sOmega = sm, *sPB = sOmega + M * M, *sData = sPB + 4 * M;
+    double *sCovOut = sm + ((33 * M > M * M + 4 * M + 3 * NVP) ? 33 * M : M * M + 4 * M + 3 * NVP);
     for (int t = tid; t < M * M; t += kMidThreads) sOmega[t] = a.omega[t];
-    for (int t = tid; t < M * 4; t += kMidThreads) {
-        const double v = first ? a.priorB[t] : a.axB[t];
-        sPB[t] = v;
-        a.primeB[t] = v;   // snapshot of the previous posterior (MRGP.py:575 / :581), read by k_omega
-    }
-    for (int t = tid; t < M; t += kMidThreads) {
-        a.primeLogC[t] = first ? a.priorLogC[t] : a.axLogC[t];
-        a.primeShape[t] = first ? a.priorShape[t] : a.ardShape[t];
-        a.primeScale[t] = first ? a.priorScale[t] : a.ardScale[t];
-    }
+    for (int t = tid; t < M * 4; t += kMidThreads) sPB[t] = a.primeB[t];
     {   // sum of the per-CTA partials: `halves` slices of CTAs per value, four loads in flight per thread
         double *sHalf = sData + NVP;
-        const int halves = kMidThreads / NVP;   // 1 or 2
-        const int v = tid % NVP, half = tid / NVP, nb = (int)gridDim.x;
+        const int halves = (kMidThreads / NVP >= 2) ? 2 : 1;
+        const int v = tid % NVP, half = tid / NVP, nb = n_partials;
         if (half < halves) {
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int q = half;
@@ -978,6 +978,11 @@ __global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, i
         }
         Bingham2 bg;
         bingham2(b00 + sData[i * 3 + 0], b01 + sData[i * 3 + 1], b11 + sData[i * 3 + 2], bg);
+        sCovOut[i * 4 + 0] = bg.cov[0];
+        sCovOut[i * 4 + 1] = bg.cov[1];
+        sCovOut[i * 4 + 2] = bg.cov[1];
+        sCovOut[i * 4 + 3] = bg.cov[2];
+        if (blockIdx.x == 0) {
         atomicAdd(a.chol_count, (unsigned long long)bg.n_chol);
         a.axB[i * 4 + 0] = bg.b[0];
         a.axB[i * 4 + 1] = bg.b[1];
@@ -992,19 +997,11 @@ __global__ void __launch_bounds__(kMidThreads) k_mid_ci(RegionArgs a, int lpi, i
         a.axCov[i * 4 + 1] = bg.cov[1];
         a.axCov[i * 4 + 2] = bg.cov[1];
         a.axCov[i * 4 + 3] = bg.cov[2];
+        }
     }
-        __syncthreads();
-        if (tid == 0) st_release_gpu(&sync_words[1], gen + 1u);
-    } else {
-        if (tid == 0)
-            while ((int)(ld_acquire_gpu(&sync_words[1]) - (gen + 1u)) < 0) {
-            }
-        __syncthreads();
-    }
-    // ---- S2 per item with the new axis covariance: a, m2, cm2 (Stats.py:67-100); per-CTA sums of m2/S --------
-    double *sCov = sm, *sC2 = sCov + 4 * M, *sSumA = sC2 + 32 * M;
     __syncthreads();
-    for (int t = tid; t < M * 4; t += kMidThreads) sCov[t] = __ldcg(a.axCov + t);
+    // ---- S2 per item with the new axis covariance: a, m2, cm2 (Stats.py:67-100); per-CTA sums of m2/S --------
+    double *sCov = sCovOut, *sC2 = sm, *sSumA = sC2 + 32 * M;   // the staging area above is free again
     if (tid < M) sSumA[tid] = 0.0;
     __syncthreads();
     for (int cb = r0; cb < r1; cb += 32) {
