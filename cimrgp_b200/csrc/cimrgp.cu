@@ -55,7 +55,7 @@ struct LayerDev {
 struct SharedDev {
     double *axB = nullptr, *axKappa = nullptr, *axRho = nullptr, *axLogC = nullptr, *axCov = nullptr;
     double *ardShape = nullptr, *ardScale = nullptr, *ardMean = nullptr, *ardLogMean = nullptr;
-    double *omega = nullptr, *logOmegaHat = nullptr, *omegaIters = nullptr, *ardPartial = nullptr, *omegaEta = nullptr, *omegaWarm = nullptr;
+    double *omega = nullptr, *logOmegaHat = nullptr, *omegaIters = nullptr, *ardPartial = nullptr, *omegaEta = nullptr, *omegaWarm = nullptr, *omegaL = nullptr;
     double *primeB = nullptr, *primeLogC = nullptr, *primeShape = nullptr, *primeScale = nullptr;
     double *priorB = nullptr, *priorLogC = nullptr, *priorShape = nullptr, *priorScale = nullptr;
 };
@@ -87,7 +87,7 @@ struct mrgp_handle {
     unsigned int *done_counter = nullptr, *mid_sync = nullptr;
     cudaStream_t stream = nullptr, side = nullptr;
     bool own_stream = false;
-    std::vector<cudaEvent_t> ev_fork, ev_join;
+    std::vector<cudaEvent_t> ev_fork, ev_join, ev_ard;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     int64_t launches = 0, launches_per_sweep = 0, sweeps_done = 0;
@@ -293,6 +293,7 @@ size_t carve(mrgp_handle *h, char *base) {
     s.ardPartial = c.take<double>((size_t)256 * M);
     s.omegaEta = c.take<double>((size_t)kMaxLayers * 64);
     s.omegaWarm = c.take<double>(kMaxLayers);
+    s.omegaL = c.take<double>((size_t)J * 64 * 64);
     s.primeB = c.take<double>((size_t)M * DY * DY);
     s.primeLogC = c.take<double>(M);
     s.primeShape = c.take<double>(M);
@@ -421,6 +422,7 @@ RegionArgs region_args(mrgp_handle *h, int j) {
     a.ardPartial = s.ardPartial;
     a.omegaEta = s.omegaEta;
     a.omegaWarm = s.omegaWarm;
+    a.omegaL = s.omegaL;
     a.primeB = s.primeB;
     a.primeLogC = s.primeLogC;
     a.primeShape = s.primeShape;
@@ -592,7 +594,7 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega) {
     const int M = h->cfg.n_basis;
     RegionArgs a = region_args(h, j);
     const LayerPlan &lp = h->plan[j];
-    if (fork_omega && j > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_join[j - 1], 0));
+    if (fork_omega && j > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_ard[j - 1], 0));   // k_mid1 reads ard_mean
     int n_partials = 1;
     {
         const int mr = h->sharded ? 1 : max_region_runs(lp);
@@ -608,10 +610,11 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega) {
         k_mid1<2><<<nb, kMidThreads, smem1, h->stream>>>(a, lpi, rpc);
         CK(cudaGetLastError());
         count(h);
-        int nb2 = std::min(h->sm_count, lp.R);
+        int nb2 = std::min(48, lp.R);
         const int rpc2 = (lp.R + nb2 - 1) / nb2;
         nb2 = (lp.R + rpc2 - 1) / rpc2;
         const size_t smem2 = (size_t)(std::max(33 * M, M * M + 4 * M + 3 * nvp) + 4 * M) * sizeof(double);
+        if (fork_omega && j > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_join[j - 1], 0));   // k_mid2 reads omega
         CK(set_smem(k_mid2<2>, smem2));
         k_mid2<2><<<nb2, kMidThreads, smem2, h->stream>>>(a, rpc2, nb);
         CK(cudaGetLastError());
@@ -626,10 +629,14 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega) {
             st = h->side;
         }
         const size_t smem = omega_smem_doubles(M) * sizeof(double);
-        CK(set_smem(k_omega, smem));
-        k_omega<<<1, kOmegaThreads, smem, st>>>(a, n_partials);
+        CK(set_smem(k_ard, smem));
+        k_ard<<<1, kOmegaThreads, smem, st>>>(a, n_partials);
         CK(cudaGetLastError());
-        count(h);
+        if (fork_omega) CK(cudaEventRecord(h->ev_ard[j], h->side));
+        CK(set_smem(k_scale, smem));
+        k_scale<<<1, kOmegaThreads, smem, st>>>(a);
+        CK(cudaGetLastError());
+        count(h, 2);
         if (fork_omega) CK(cudaEventRecord(h->ev_join[j], h->side));
     }
     return MRGP_OK;
@@ -668,7 +675,10 @@ int sweep_once(mrgp_handle *h, bool fork_omega) {
         if ((rc = do_axis_update(h, j, fork_omega && ci))) return rc;
         if ((rc = do_phase_b(h, j, true))) return rc;   // bias / noise update fused into the kernel tail
     }
-    if (fork_omega && ci) CK(cudaStreamWaitEvent(h->stream, h->ev_join[J - 1], 0));
+    if (fork_omega && ci) {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_ard[J - 1], 0));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_join[J - 1], 0));
+    }
     return MRGP_OK;
 }
 
@@ -697,6 +707,7 @@ FieldRef field_ref(mrgp_handle *h, int layer, int field) {
             case MRGP_F_OMEGA: f = {s.omega, (int64_t)M * M}; break;
             case MRGP_F_LOG_OMEGA_HAT: f = {s.logOmegaHat, (int64_t)M * M}; break;
             case MRGP_F_OMEGA_ITERS: f = {s.omegaIters, h->cfg.n_layers}; break;
+            case 52: f = {s.omegaL, (int64_t)h->cfg.n_layers * 64 * 64}; break;   // debug: residual trace
             default: break;
         }
         return f;
@@ -831,7 +842,9 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
         cudaGetLastError();
     }
     h->sm_count = sms;
-    int want = cfg->n_ctas > 0 ? cfg->n_ctas : sms;
+    // ci: one SM is left to the omega solver, which runs beside phase B / phase A on a side stream (a phase-A CTA
+    // takes the whole register file of its SM, and sharing an SM with phase B halves the solver's FP64 rate)
+    int want = cfg->n_ctas > 0 ? cfg->n_ctas : (cfg->mode == MRGP_MODE_CI && sms > 8 ? sms - 1 : sms);
     const int64_t min_per_cta = 4 * kThreads;
     const int64_t n_local = h->hi - h->lo;
     const int64_t cap = std::max<int64_t>(1, (n_local + min_per_cta - 1) / min_per_cta);
@@ -851,6 +864,7 @@ void mrgp_destroy(mrgp_handle *h) {
     drop_graph(h);
     for (auto e : h->ev_fork) cudaEventDestroy(e);
     for (auto e : h->ev_join) cudaEventDestroy(e);
+    for (auto e : h->ev_ard) cudaEventDestroy(e);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -879,9 +893,11 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
     if (h->ev_fork.empty()) {
         h->ev_fork.resize(h->cfg.n_layers);
         h->ev_join.resize(h->cfg.n_layers);
+        h->ev_ard.resize(h->cfg.n_layers);
         for (int j = 0; j < h->cfg.n_layers; ++j) {
             CK(cudaEventCreateWithFlags(&h->ev_fork[j], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&h->ev_join[j], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_ard[j], cudaEventDisableTiming));
         }
     }
     h->ws = static_cast<char *>(dev_ptr);

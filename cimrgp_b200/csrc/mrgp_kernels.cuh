@@ -711,7 +711,7 @@ struct RegionArgs {
     double *bias_prec, *bias_prec0, *bias_mean, *bias_mean0, *bias_var, *yvar, *sumsB;
     // shared (ci) or per-region (fi) axis / ARD
     double *axB, *axKappa, *axRho, *axLogC, *axCov, *ardShape, *ardScale, *ardMean, *ardLogMean;
-    double *omega, *logOmegaHat, *omegaIters, *ardPartial, *omegaEta, *omegaWarm;
+    double *omega, *logOmegaHat, *omegaIters, *ardPartial, *omegaEta, *omegaWarm, *omegaL;
     double *primeB, *primeLogC, *primeShape, *primeScale;   // snapshot read by ARD / omega (ci)
     const double *priorB, *priorLogC, *priorShape, *priorScale;
     double *bcontrib;          // (R, M, 3) ci: 0.5 noise zeta ytil ytil^T
@@ -1046,12 +1046,10 @@ constexpr int kOmegaThreads = 256;
 
 __host__ __device__ inline size_t omega_smem_doubles(int M) { return (size_t)3 * M * M + 12 * M + 8; }
 
-__global__ void __launch_bounds__(kOmegaThreads) k_omega(RegionArgs a, int n_partials) {
+__global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_partials) {
     extern __shared__ double sm[];
-    const int M = a.M, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kOmegaThreads / 32;
-    double *K = sm, *P = K + M * M, *S = P + M * M, *v = S + M * M, *c = v + M, *rhs = c + M, *dinv = rhs + M;
-    double *yv = dinv + M, *xv = yv + M, *s_mean = xv + M, *s_lmean = s_mean + M, *s_k = s_lmean + M, *cshift = s_k + M, *red = cshift + M;
+    const int M = a.M, tid = threadIdx.x;
+    double *P = sm, *s_mean = P + M * M, *s_lmean = s_mean + M, *s_k = s_lmean + M;
     ts_begin(a.ts, a.layer * 4 + 3);
     for (int t = tid; t < M * M; t += kOmegaThreads) P[t] = a.omega[t];   // the OLD omega mixes the ARD prior
     __syncthreads();
@@ -1084,8 +1082,18 @@ __global__ void __launch_bounds__(kOmegaThreads) k_omega(RegionArgs a, int n_par
         const double tr = C[0] * B[0] + C[1] * B[2] + C[2] * B[1] + C[3] * B[3];   // trace(C_i B'_k)
         const double lw = tr + s_k[k] + (a.primeShape[k] - 1.0) * s_lmean[i] - a.primeScale[k] * s_mean[i];
         a.logOmegaHat[t] = lw;
-        K[t] = lw;
     }
+}
+
+
+// Second kernel of the side stream: the doubly-stochastic scaling of exp(log omega_hat) (Stats.py:413-420).
+__global__ void __launch_bounds__(kOmegaThreads) k_scale(RegionArgs a) {
+    extern __shared__ double sm[];
+    const int M = a.M, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kOmegaThreads / 32;
+    double *K = sm, *P = K + M * M, *S = P + M * M, *v = S + M * M, *c = v + M, *rhs = c + M, *dinv = rhs + M;
+    double *yv = dinv + M, *xv = yv + M, *cshift = xv + M, *red = cshift + M;
+    for (int t = tid; t < M * M; t += kOmegaThreads) K[t] = a.logOmegaHat[t];
     __syncthreads();
     for (int i = warp; i < M; i += NW) {
         double mx = -INFINITY;
@@ -1171,10 +1179,8 @@ __global__ void __launch_bounds__(kOmegaThreads) k_omega(RegionArgs a, int n_par
             if (tid > j && tid < M) S[tid * M + j] *= di;
             if (tid == 0) dinv[j] = di;
             __syncthreads();
-            for (int r = j + 1 + warp; r < M; r += NW) {
-                const double lrj = S[r * M + j];
-                for (int q = j + 1 + lane; q <= r; q += 32) S[r * M + q] = fma(-lrj, S[q * M + j], S[r * M + q]);
-            }
+            for (int r = j + 1 + (tid >> 4); r < M; r += 16)
+                for (int q = j + 1 + (tid & 15); q <= r; q += 16) S[r * M + q] = fma(-S[r * M + j], S[q * M + j], S[r * M + q]);
             __syncthreads();
         }
         for (int j = 0; j < M; ++j) {   // L y = rhs

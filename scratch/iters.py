@@ -4,6 +4,8 @@ import bench
 from cimrgp_b200 import _lib
 m = bench.make_model(1000000, 0)
 e = m._engine
-for s in range(30):
+for s in range(6):
     e.sweep(1); e.synchronize()
-    if s in (0,1,2,3,5,8,12,16,20,25,29): print('sweep', s, e.get(-1, _lib.F_OMEGA_ITERS, (10,)).astype(int), 'noise0 %.6f'%e.get(0,_lib.F_NOISE_MEAN,(1,))[0])
+it=e.get(-1, _lib.F_OMEGA_ITERS, (10,)).astype(int)
+tr=e.get(-1, 52, (10,64*64))
+for j in (1,5,9): print('L%d iters %d  cycles: prologue %d eval %d S %d chol %d solve %d total %d'%((j,it[j])+tuple(int(v) for v in tr[j][16:22])))

@@ -179,9 +179,9 @@ def test_host_omega_matches_reference_within_its_solver_tolerance():
         it = C.c_int32()
         assert lib.mrgp_host_omega(lw.ctypes.data_as(P), m, om.ctypes.data_as(P), C.byref(it)) == 0
         assert it.value < 1000
-        assert np.max(np.abs(om.sum(0) - 1)) < 1e-12 and np.max(np.abs(om.sum(1) - 1)) < 1e-12
+        assert np.max(np.abs(om.sum(0) - 1)) < 1e-10 and np.max(np.abs(om.sum(1) - 1)) < 1e-12   # kOmegaTol
         assert mismatch(om, ref, 1e-6) is None            # fsolve's own error is ~1e-8
-        assert mismatch(om, O.omega_sinkhorn(lw), 1e-10) is None
+        assert mismatch(om, O.omega_sinkhorn(lw), 1e-8) is None
 
 
 def test_index_sets_bit_exact():
