@@ -1,6 +1,8 @@
 """Basis intervals: drop-in for the reference's src/BasisInterval.py constructor and static interval rule.
-The per-sweep interval optimisation (`learn`, BasisInterval.py:18-134) is the next row of the scope table
- and is not on the device yet: passing a BasisInterval object to the model raises."""
+The per-sweep interval optimisation (`learn`, BasisInterval.py:18-134) runs on the device: the model reads
+`use_prior` and `opt_interval_factor` from the object of each layer and hands them to
+mrgp_set_adaptive_intervals (include/cimrgp.h); the bounded scalar search of all regions of a layer runs in
+lock-step as CUDA kernels inside the sweep."""
 import numpy as np
 
 

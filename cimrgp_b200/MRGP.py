@@ -4,7 +4,7 @@ public state) with the variational-inference sweep running on one B200 through l
 Same constructor arguments, same exceptions for the same misuse (MRGP.py:37-126), same meaning of every
 method.  What is NOT carried over (raises NotImplementedError with the reason): the GPy input-warp model
 (`adaptive_inputs=True` without an `input_model`; third-party GP), per-sweep
-interval optimisation (`basis_interval_obj`, next scope row), shared (non region-specific) noise or bias,
+shared (non region-specific) noise or bias,
 dx > 1 and dy > 2 on the device.
 """
 import numpy as np
@@ -104,9 +104,10 @@ class MultiResolutionGaussianProcess(object):
             self.adaptive_basis_intervals = False
             self.basis_interval_obj = [BasisInterval() for _ in range(self.n_layers)]
         else:
-            per_layer(basis_interval_obj, 'basis_interval_obj')
-            raise NotImplementedError('adaptive basis intervals (BasisInterval.learn, BasisInterval.py:18-134) are '
-                                      'not on the device yet; pass basis_interval_obj=None')
+            self.adaptive_basis_intervals = True                             # MRGP.py:110-124
+            self.basis_interval_obj = per_layer(basis_interval_obj, 'basis_interval_obj')
+            if distributed:
+                raise NotImplementedError('adaptive basis intervals are not available on the sample-sharded path')
         for b in self.basis_function_obj:
             if getattr(b, 'name', None) != 'Laplacian':
                 raise TypeError('the device path implements the Laplacian eigenfunction basis only')
@@ -167,6 +168,14 @@ class MultiResolutionGaussianProcess(object):
                     lam = eng.get(j, _lib.F_LAMBDA, (self.n_regions[j], n_basis))
                     eng.put(j, _lib.F_SPECTRAL, np.vectorize(lambda v: s.spectral(np.sqrt(v)))(lam))
             eng._ck(eng.lib.mrgp_init_state(eng.handle, float(noise_var0), float(np.mean(sf))))
+        if self.adaptive_basis_intervals:
+            if self.dx != 1:
+                raise NotImplementedError('adaptive basis intervals: one input dimension on the device path')
+            for j, (b, s) in enumerate(zip(self.basis_interval_obj, host_spectral)):
+                if s is not None and b.use_prior:
+                    raise NotImplementedError('adaptive basis intervals with use_prior need the Matern spectral '
+                                              'density on the device (custom spectral objects are host-evaluated)')
+                self._engine.set_adaptive_intervals(j, bool(b.use_prior), tuple(b.opt_interval_factor))
         self.lower_bound_layer = [[] for _ in range(self.n_layers)]
         self.lower_bound = []
         self.lower_bound_terms = []
@@ -205,6 +214,10 @@ class MultiResolutionGaussianProcess(object):
             self._engine.sweep(n_iter)      # MRGP.py:400-401: no bound, no early stop in fi mode
             self._engine.synchronize()
             return
+        if self.adaptive_basis_intervals:
+            raise NotImplementedError('fit with a tolerance needs the lower bound, which the device path does not '
+                                      'keep under adaptive basis intervals; use fit(n_iter, None) as the '
+                                      "reference's own scripts do (scripts/tests/ciMRGP_vs_fiMRGP.py:61)")
         if n_iter < min_iter:
             min_iter = n_iter
         for iter_ in range(1, n_iter + 1):

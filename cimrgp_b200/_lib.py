@@ -60,6 +60,9 @@ SIGNATURES = {
     'mrgp_axis_update': (C.c_int, [_P, C.c_int32]),
     'mrgp_phase_b': (C.c_int, [_P, C.c_int32]),
     'mrgp_bias_noise': (C.c_int, [_P, C.c_int32]),
+    'mrgp_set_adaptive_intervals': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double]),
+    'mrgp_interval_failures': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    'mrgp_learn_intervals': (C.c_int, [_P, C.c_int32]),
     'mrgp_sweep': (C.c_int, [_P, C.c_int32]),
     'mrgp_synchronize': (C.c_int, [_P]),
     'mrgp_elbo': (C.c_int, [_P, _D]),

@@ -36,7 +36,11 @@ struct LayerDev {
     int32_t *cta_seg = nullptr, *region_run = nullptr, *ident_run = nullptr;
     int64_t *offsets = nullptr;
     // static
-    double *L = nullptr, *inv2L = nullptr, *rsqrtL = nullptr, *lam = nullptr, *S = nullptr, *d = nullptr;
+    double *L = nullptr, *inv2L = nullptr, *rsqrtL = nullptr, *lam = nullptr, *S = nullptr, *d = nullptr, *absx = nullptr;
+    double *bias_prev = nullptr, *brent = nullptr, *trial_inv2L = nullptr, *trial_rsqrtL = nullptr, *wq = nullptr;
+    bool adaptive = false;
+    int32_t ad_use_prior = 1;
+    double ad_lo = 1.0, ad_hi = 1.2;
     // posterior / stats
     double *prec = nullptr, *zeta = nullptr, *ytil = nullptr, *A = nullptr, *A_prev = nullptr, *m2 = nullptr, *cm2 = nullptr;
     double *noise_shape = nullptr, *noise_scale = nullptr, *noise_shape0 = nullptr, *noise_scale0 = nullptr;
@@ -93,6 +97,9 @@ struct mrgp_handle {
     int64_t launches = 0, launches_per_sweep = 0, sweeps_done = 0;
     bool capturing = false;
     bool timeline = false;
+    // adaptive basis intervals (BasisInterval.learn): the per-layer switches live in LayerDev
+    int32_t ad_iters = 40;
+    unsigned long long *brent_fail = nullptr;
     unsigned long long *ts = nullptr;   // (kMaxLayers * 4) x {begin, end} global-timer stamps
     double fi_shape0_mix = 0.0, fi_scale0_mix = 0.0;
     std::string err;
@@ -227,6 +234,7 @@ size_t carve(mrgp_handle *h, char *base) {
     h->off_staging = c.take<int64_t>(h->off_total);
     h->chol_count = c.take<unsigned long long>(1);
     h->done_counter = c.take<unsigned int>(1);
+    h->brent_fail = c.take<unsigned long long>(1);
     h->mid_sync = c.take<unsigned int>(2 * kMaxLayers);
     h->ts = c.take<unsigned long long>(kMaxLayers * 8);
     for (int j = 0; j < J; ++j) {
@@ -244,6 +252,12 @@ size_t carve(mrgp_handle *h, char *base) {
         d.lam = c.take<double>(RM);
         d.S = c.take<double>(RM);
         d.d = c.take<double>(RM);
+        d.absx = c.take<double>(R);
+        d.bias_prev = c.take<double>(R * DY);
+        d.brent = c.take<double>(R * BrentState::NFIELDS);
+        d.trial_inv2L = c.take<double>(R);
+        d.trial_rsqrtL = c.take<double>(R);
+        d.wq = c.take<double>(RM);
         d.prec = c.take<double>(RM);
         d.zeta = c.take<double>(RM);
         d.ytil = c.take<double>(RM * DY);
@@ -342,6 +356,7 @@ StreamArgs stream_args(mrgp_handle *h, int j) {
     a.noise_shape0 = d.noise_shape0;
     a.noise_scale0 = d.noise_scale0;
     a.bias_mean_out = d.bias_mean;
+    a.bias_prev_out = d.bias_prev;
     a.bias_prec = d.bias_prec;
     a.bias_var = d.bias_var;
     a.noise_shape = d.noise_shape;
@@ -374,6 +389,7 @@ RegionArgs region_args(mrgp_handle *h, int j) {
     a.lam = d.lam;
     a.S = d.S;
     a.d = d.d;
+    a.absx = d.absx;
     a.prec = d.prec;
     a.zeta = d.zeta;
     a.ytil = d.ytil;
@@ -642,9 +658,10 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega) {
     return MRGP_OK;
 }
 
-int do_phase_b(mrgp_handle *h, int j, bool fuse_tail) {
+int do_phase_b(mrgp_handle *h, int j, bool fuse_tail, int prop_override = -1) {
     const bool fi = h->cfg.mode == MRGP_MODE_FI;
-    const bool infer = !fi && j > 0, latent = j > 0, prop = j + 1 < h->cfg.n_layers;
+    const bool infer = !fi && j > 0, latent = j > 0;
+    const bool prop = prop_override < 0 ? (j + 1 < h->cfg.n_layers) : (prop_override != 0);
     StreamArgs a = stream_args(h, j);
     a.fuse_tail = fuse_tail ? 1 : 0;
     cudaError_t e = cudaErrorInvalidValue;
@@ -666,6 +683,79 @@ int do_bias_noise(mrgp_handle *h, int j) {
     return MRGP_OK;
 }
 
+template <int M>
+cudaError_t launch_objective(mrgp_handle *h, const IntervalArgs &q, bool infer, bool latent) {
+    dim3 grid(h->n_ctas), block(kThreads);
+    if (infer)
+        k_interval_objective<2, M, true, true><<<grid, block, 0, h->stream>>>(q);
+    else if (latent)
+        k_interval_objective<2, M, false, true><<<grid, block, 0, h->stream>>>(q);
+    else
+        k_interval_objective<2, M, false, false><<<grid, block, 0, h->stream>>>(q);
+    return cudaGetLastError();
+}
+
+// B1: BasisInterval.learn for one layer (BasisInterval.py:18-134), then the rebuild of lambda, S and sum phi^2
+// (MRGP.py:640-641).  ci mode only (MRGP.py:108-109 switches it off for fi).
+int do_learn_intervals(mrgp_handle *h, int j) {
+    LayerDev &d = h->dev[j];
+    const LayerPlan &lp = h->plan[j];
+    const int M = h->cfg.n_basis;
+    const bool infer = j > 0, latent = j > 0;
+    BrentArgs b{};
+    b.R = lp.R;
+    b.M = M;
+    b.first = 1;
+    b.region_run = d.region_run;
+    b.part = h->part;
+    b.part_stride = h->part_stride;
+    b.st = d.brent;
+    b.trial_inv2L = d.trial_inv2L;
+    b.trial_rsqrtL = d.trial_rsqrtL;
+    b.noise_mean = d.noise_mean;
+    b.ard_mean = h->sh.ardMean;
+    b.m2 = d.m2;
+    b.use_prior = d.ad_use_prior ? 1 : 0;
+    b.nu = d.nu;
+    b.ell = d.ell;
+    b.sf = d.sf;
+    b.xatol = 1e-5;
+    b.maxfun = 500;
+    const int total = lp.R * M;
+    k_brent_start<<<(total + 127) / 128, 128, 0, h->stream>>>(b, d.absx, d.ad_lo, d.ad_hi, d.A, d.cm2, d.wq);
+    CK(cudaGetLastError());
+    count(h);
+    IntervalArgs q{};
+    q.s = stream_args(h, j);
+    q.trial_inv2L = d.trial_inv2L;
+    q.trial_rsqrtL = d.trial_rsqrtL;
+    q.w = d.wq;
+    q.bias_old = d.bias_prev;
+    for (int it = 0; it < h->ad_iters; ++it) {
+        cudaError_t e = cudaErrorInvalidValue;
+        DISPATCH_M(M, e = launch_objective<MM>(h, q, infer, latent));
+        CK(e);
+        b.first = (it == 0) ? 1 : 0;
+        k_brent_step<<<(lp.R + 3) / 4, 128, 0, h->stream>>>(b);
+        CK(cudaGetLastError());
+        count(h, 2);
+    }
+    k_brent_finish<<<(lp.R + 127) / 128, 128, 0, h->stream>>>(b, d.L, h->brent_fail);
+    CK(cudaGetLastError());
+    RegionArgs ra = region_args(h, j);
+    ra.L_given = 1;
+    k_region_setup<<<(lp.R + 7) / 8, 256, 0, h->stream>>>(ra);
+    CK(cudaGetLastError());
+    StreamArgs sa = stream_args(h, j);
+    cudaError_t e = cudaErrorInvalidValue;
+    DISPATCH_M(M, e = launch_phi2sum<MM>(h, sa));
+    CK(e);
+    k_reduce_d<<<lp.R, 64, 0, h->stream>>>(ra);
+    CK(cudaGetLastError());
+    count(h, 4);
+    return MRGP_OK;
+}
+
 int sweep_once(mrgp_handle *h, bool fork_omega) {
     const int J = h->cfg.n_layers;
     const bool ci = h->cfg.mode == MRGP_MODE_CI;
@@ -673,7 +763,15 @@ int sweep_once(mrgp_handle *h, bool fork_omega) {
     for (int j = 0; j < J; ++j) {
         if ((rc = do_phase_a(h, j))) return rc;
         if ((rc = do_axis_update(h, j, fork_omega && ci))) return rc;
-        if ((rc = do_phase_b(h, j, true))) return rc;   // bias / noise update fused into the kernel tail
+        if (h->dev[j].adaptive && ci) {
+            // the latent functions of the next layer use the re-learnt basis (MRGP.py:632-649): statistics first,
+            // then the interval search, then a second pass that only propagates
+            if ((rc = do_phase_b(h, j, true, 0))) return rc;
+            if ((rc = do_learn_intervals(h, j))) return rc;
+            if (j + 1 < J && (rc = do_phase_b(h, j, false, 1))) return rc;
+        } else {
+            if ((rc = do_phase_b(h, j, true))) return rc;   // bias / noise update fused into the kernel tail
+        }
     }
     if (fork_omega && ci) {
         CK(cudaStreamWaitEvent(h->stream, h->ev_ard[J - 1], 0));
@@ -915,6 +1013,7 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
     }
     CK(cudaMemsetAsync(h->chol_count, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->done_counter, 0, sizeof(unsigned int), h->stream));
+    CK(cudaMemsetAsync(h->brent_fail, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->mid_sync, 0, 2 * kMaxLayers * sizeof(unsigned int), h->stream));
     CK(cudaMemsetAsync(h->g, 0, (size_t)(h->hi - h->lo) * h->cfg.dy * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->hvar, 0, (size_t)(h->hi - h->lo) * sizeof(double), h->stream));
@@ -1115,6 +1214,43 @@ int mrgp_bias_noise(mrgp_handle *h, int32_t layer) {
     return rc ? rc : do_bias_noise(h, layer);
 }
 
+int mrgp_set_adaptive_intervals(mrgp_handle *h, int32_t layer, int32_t enabled, int32_t use_prior, double factor_lo, double factor_hi) {
+    if (!h) return MRGP_EINVAL;
+    if (layer < -1 || layer >= h->cfg.n_layers) return fail(h, MRGP_EINVAL, "layer out of range");
+    if (enabled && h->cfg.mode != MRGP_MODE_CI) return fail(h, MRGP_EINVAL, "adaptive intervals exist in ci mode only (MRGP.py:108-109)");
+    if (enabled && h->sharded) return fail(h, MRGP_EINVAL, "adaptive intervals are not available on a sharded handle");
+    if (enabled && !(factor_lo > 0.0 && factor_hi > 0.0)) return fail(h, MRGP_EINVAL, "opt_interval_factor must be positive");
+    for (int j = 0; j < h->cfg.n_layers; ++j) {
+        if (layer >= 0 && j != layer) continue;
+        LayerDev &d = h->dev[j];
+        if (enabled && use_prior && !d.use_prior)
+            return fail(h, MRGP_EINVAL, "use_prior needs a spectral density on the layer (BasisInterval.py:121)");
+        d.adaptive = enabled != 0;
+        d.ad_use_prior = use_prior;
+        d.ad_lo = factor_lo;
+        d.ad_hi = factor_hi;
+    }
+    drop_graph(h);
+    return MRGP_OK;
+}
+
+int mrgp_learn_intervals(mrgp_handle *h, int32_t layer) {
+    int rc = check_ready(h, layer, true);
+    if (rc) return rc;
+    if (!h->dev[layer].adaptive) return fail(h, MRGP_ESTATE, "adaptive intervals are not enabled on this layer");
+    return do_learn_intervals(h, layer);
+}
+
+int mrgp_interval_failures(mrgp_handle *h, uint64_t *out) {
+    if (!h || !out) return MRGP_EINVAL;
+    if (!h->brent_fail) return fail(h, MRGP_ESTATE, "workspace not bound");
+    unsigned long long v = 0;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(&v, h->brent_fail, sizeof(v), cudaMemcpyDeviceToHost));
+    *out = v;
+    return MRGP_OK;
+}
+
 int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
     int rc = check_ready(h, 0, true);
     if (rc) return rc;
@@ -1157,6 +1293,9 @@ int mrgp_elbo(mrgp_handle *h, double *out_host) {
     if (rc) return rc;
     if (!out_host) return fail(h, MRGP_EINVAL, "null argument");
     if (h->cfg.mode != MRGP_MODE_CI) return fail(h, MRGP_EINVAL, "the lower bound is defined for ci mode only (MRGP.py:378-401)");
+    for (int j = 0; j < h->cfg.n_layers; ++j)
+        if (h->dev[j].adaptive)
+            return fail(h, MRGP_ESTATE, "the lower bound is not kept with adaptive intervals: its data sums belong to the basis before the interval update");
     std::vector<RegionArgs> args(h->cfg.n_layers);
     for (int j = 0; j < h->cfg.n_layers; ++j) args[j] = region_args(h, j);
     CK(cudaMemcpyAsync(h->elbo_args, args.data(), args.size() * sizeof(RegionArgs), cudaMemcpyHostToDevice, h->stream));

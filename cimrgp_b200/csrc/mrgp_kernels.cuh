@@ -75,7 +75,7 @@ struct StreamArgs {
     int32_t R, infer, fuse_tail, layer;
     unsigned long long *ts;
     const double *bias_prec0, *bias_mean0, *noise_shape0, *noise_scale0;
-    double *bias_mean_out, *bias_prec, *bias_var, *noise_shape, *noise_scale, *noise_mean, *noise_log_mean, *yvar, *sumsB;
+    double *bias_mean_out, *bias_prev_out, *bias_prec, *bias_var, *noise_shape, *noise_scale, *noise_mean, *noise_log_mean, *yvar, *sumsB;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -225,6 +225,7 @@ __device__ __forceinline__ void bias_noise_region(const StreamArgs &p, int r, co
     for (int d = 0; d < DY; ++d) {
         const double m0 = p.bias_mean0[(size_t)r * DY + d];
         const double m = (1.0 / bp) * (m0 * bp0 + sums[d]);
+        p.bias_prev_out[(size_t)r * DY + d] = p.bias_mean_out[(size_t)r * DY + d];
         p.bias_mean_out[(size_t)r * DY + d] = m;
         t3 += m0 * m0;
         t4 += m * m;
@@ -704,7 +705,7 @@ struct RegionArgs {
     const double *part;        // partials of the preceding streaming kernel
     int32_t part_stride;
     // static
-    double *L, *inv2L, *rsqrtL, *lam, *S, *d;
+    double *L, *inv2L, *rsqrtL, *lam, *S, *d, *absx;
     // posterior / stats
     double *prec, *zeta, *ytil, *A, *A_prev, *m2, *cm2;
     double *noise_shape, *noise_scale, *noise_shape0, *noise_scale0, *noise_mean, *noise_log_mean;
@@ -737,6 +738,7 @@ __global__ void k_region_setup(RegionArgs a) {
         double m = 0.0;
         for (int q = a.region_run[r] + lane; q < a.region_run[r + 1]; q += 32) m = fmax(m, a.part[(size_t)q * a.part_stride]);
         m = warp_max(m);
+        if (lane == 0) a.absx[r] = m;
         L = a.interval_factor * m;
     }
     if (lane == 0) {
@@ -1259,6 +1261,295 @@ __global__ void __launch_bounds__(kThreadsB) k_bias_noise(StreamArgs p) {
     int lpr = 32;
     while (lpr > 1 && (kThreadsB / lpr) < p.R) lpr >>= 1;
     bias_noise_all<DY, kThreadsB>(p, lpr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// B1: per-region optimisation of the basis half-interval L (BasisInterval.py:18-134, ci mode, dx == 1).
+// All regions of a layer run the bounded Brent minimiser of SciPy's fminbound in lock-step (the reference calls
+// scipy.optimize.fminbound(h, lo, hi) per region, BasisInterval.py:85-90; `_minimize_scalar_bounded`, xatol 1e-5,
+// maxfun 500, is transcribed step for step in k_brent_step because the returned L sits within xatol of a bracket
+// edge and only identical steps reproduce it).  One iteration = one streaming evaluation of the
+// data part of the objective for every region at its own trial L (k_interval_objective) + one small kernel that
+// adds the prior part, consumes the value and proposes the next trial point.
+//   h(L) = 1/2 noise sum_n [ sum_i (2|a_i|^2 + cm2_i) phi_i(n; L)^2 + (Phi(L) A^T)_n . (4 (b + fbar_n) - 2 y_n) ]
+//          + 1/2 sum_i (log S_i(L) - 1/2 ard_mean_i m2_i / S_i(L))                       (BasisInterval.py:94-134)
+// with the NEW a, m2, cm2, b, noise of the layer step and y the targets of the step (for inferred targets the
+// layer's own prediction with the OLD coefficients and the OLD interval, LatentOutputs.py:25-49).
+// ------------------------------------------------------------------------------------------------
+struct BrentState {   // one per region, SoA in the workspace: field f of region r at st[f * R + r]
+    enum { A = 0, B, FULC, NFC, XF, RAT, E, X, FX, FFULC, FNFC, XM, TOL1, TOL2, NUM, DONE, NFIELDS };
+};
+
+struct IntervalArgs {
+    StreamArgs s;
+    const double *trial_inv2L, *trial_rsqrtL;   // (R) trial interval of every region
+    const double *w;                             // (R, M) 2 |a_i|^2 + cm2_i
+    const double *bias_old;                      // (R, DY) bias used by the targets of the step
+};
+
+template <int DY, int M, bool INFER, bool LATENT>
+__global__ void __launch_bounds__(kThreads) k_interval_objective(IntervalArgs q) {
+    const StreamArgs &p = q.s;
+    __shared__ double sA[M * DY], sAo[INFER ? M * DY : 1], sW[M], sScal[4 + 3 * DY], sRed[64];
+    const int tid = threadIdx.x;
+    double acc[1] = {0.0};
+    const int s0 = p.cta_seg[blockIdx.x], s1 = p.cta_seg[blockIdx.x + 1];
+    for (int s = s0; s < s1; ++s) {
+        const Segment sg = p.segs[s];
+        __syncthreads();
+        if (tid < M * DY) {
+            sA[tid] = p.A[(size_t)sg.region * (M * DY) + tid];
+            if (INFER) sAo[tid] = p.A_prev[(size_t)sg.region * (M * DY) + tid];
+        }
+        if (tid < M) sW[tid] = q.w[(size_t)sg.region * M + tid];
+        if (tid == 0) {
+            sScal[0] = q.trial_inv2L[sg.region];
+            sScal[1] = q.trial_rsqrtL[sg.region];
+            sScal[2] = p.inv2L[sg.region];
+            sScal[3] = p.rsqrtL[sg.region];
+        }
+        if (tid < DY) {
+            sScal[4 + tid] = p.bias[(size_t)sg.region * DY + tid];                      // new bias
+            sScal[4 + DY + tid] = q.bias_old[(size_t)sg.region * DY + tid];             // bias of the targets
+            sScal[4 + 2 * DY + tid] = LATENT ? p.pbias[(size_t)sg.parent * DY + tid] : 0.0;
+        }
+        __syncthreads();
+        const double ti2L = sScal[0], trs = sScal[1], oi2L = sScal[2], ors = sScal[3];
+        const int64_t end = sg.start + sg.len;
+        for (int64_t n = sg.start + tid; n < end; n += kThreads) {
+            asm volatile("" ::: "memory");
+            const double x = p.x[n];
+            double f1, c2;
+            basis_seed(x, ti2L, trs, f1, c2);
+            double fm = 0.0, f = f1, e[DY], qv = 0.0;
+#pragma unroll
+            for (int d = 0; d < DY; ++d) e[d] = 0.0;
+#pragma unroll 5
+            for (int i = 0; i < M; ++i) {
+#pragma unroll
+                for (int d = 0; d < DY; ++d) e[d] = fma(f, sA[i * DY + d], e[d]);
+                qv = fma(f * sW[i], f, qv);
+                const double fn = fma(c2, f, -fm);
+                fm = f;
+                f = fn;
+            }
+            double eo[DY];
+#pragma unroll
+            for (int d = 0; d < DY; ++d) eo[d] = 0.0;
+            if (INFER) {
+                basis_seed(x, oi2L, ors, f1, c2);
+                fm = 0.0;
+                f = f1;
+#pragma unroll 5
+                for (int i = 0; i < M; ++i) {
+#pragma unroll
+                    for (int d = 0; d < DY; ++d) eo[d] = fma(f, sAo[i * DY + d], eo[d]);
+                    const double fn = fma(c2, f, -fm);
+                    fm = f;
+                    f = fn;
+                }
+            }
+            double dot = 0.0;
+#pragma unroll
+            for (int d = 0; d < DY; ++d) {
+                const double fb = LATENT ? p.g[n * DY + d] + sScal[4 + 2 * DY + d] : 0.0;
+                const double y = INFER ? eo[d] + (sScal[4 + DY + d] + fb) : p.y[n * DY + d];
+                dot = fma(e[d], 4.0 * (sScal[4 + d] + fb) - 2.0 * y, dot);
+            }
+            acc[0] += qv + dot;
+        }
+        if (sg.flush) {
+            block_reduce_small<1, false>(acc, sRed, p.part + (size_t)sg.run * p.part_stride);
+            acc[0] = 0.0;
+        }
+    }
+}
+
+struct BrentArgs {
+    int32_t R, M, first;          // first: 1 = the value just computed is f(x0) of the initial point
+    const int32_t *region_run;
+    const double *part;
+    int32_t part_stride;
+    double *st;                   // BrentState fields
+    double *trial_inv2L, *trial_rsqrtL;
+    const double *noise_mean, *ard_mean, *m2;   // (R), (M), (R, M)
+    int32_t use_prior;
+    double nu, ell, sf, xatol;
+    int32_t maxfun;
+};
+
+// One warp per region.  Transcription of scipy.optimize._optimize._minimize_scalar_bounded (SciPy 1.18.1).
+__global__ void k_brent_step(BrentArgs a) {
+    using B = BrentState;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= a.R) return;
+    double *st = a.st;
+    const int R = a.R;
+#define ST(f) st[(size_t)(B::f) * R + r]
+    if (ST(DONE) != 0.0) return;
+    const double x = ST(X);
+    // ---- objective at the trial point: data part from the run partials, prior part here --------------------------
+    double data = 0.0;
+    for (int q = a.region_run[r] + lane; q < a.region_run[r + 1]; q += 32) data += a.part[(size_t)q * a.part_stride];
+    data = warp_sum(data);
+    double prior = 0.0;
+    if (a.use_prior)
+        for (int i = lane; i < a.M; i += 32) {
+            const double w = (kPi * (double)(i + 1)) / (2.0 * x);
+            const double S = matern_spectral(w * w + 0.0, a.nu, a.ell, a.sf);   // lambda_penalty == 0 for dx == 1
+            prior += log(S) - 0.5 * (a.ard_mean[i] * a.m2[(size_t)r * a.M + i]) / S;
+        }
+    prior = warp_sum(prior);
+    const double ll = -0.5 * a.noise_mean[r] * data;
+    const double fval = a.use_prior ? -(ll + -0.5 * prior) : -ll;
+    if (lane != 0) return;
+    const double sqrt_eps = sqrt(2.2e-16);
+    const double golden_mean = 0.5 * (3.0 - sqrt(5.0));
+    double av = ST(A), bv = ST(B), fulc = ST(FULC), nfc = ST(NFC), xf = ST(XF), rat = ST(RAT), e = ST(E);
+    double fx = ST(FX), ffulc = ST(FFULC), fnfc = ST(FNFC), xm = ST(XM), tol1 = ST(TOL1), tol2 = ST(TOL2);
+    double num = ST(NUM);
+    if (a.first) {
+        fx = fval;
+        num = 1.0;
+        ffulc = fnfc = fx;
+        xm = 0.5 * (av + bv);
+        tol1 = sqrt_eps * fabs(xf) + a.xatol / 3.0;
+        tol2 = 2.0 * tol1;
+    } else {
+        const double fu = fval;
+        num += 1.0;
+        if (fu <= fx) {
+            if (x >= xf)
+                av = xf;
+            else
+                bv = xf;
+            fulc = nfc;
+            ffulc = fnfc;
+            nfc = xf;
+            fnfc = fx;
+            xf = x;
+            fx = fu;
+        } else {
+            if (x < xf)
+                av = x;
+            else
+                bv = x;
+            if ((fu <= fnfc) || (nfc == xf)) {
+                fulc = nfc;
+                ffulc = fnfc;
+                nfc = x;
+                fnfc = fu;
+            } else if ((fu <= ffulc) || (fulc == xf) || (fulc == nfc)) {
+                fulc = x;
+                ffulc = fu;
+            }
+        }
+        xm = 0.5 * (av + bv);
+        tol1 = sqrt_eps * fabs(xf) + a.xatol / 3.0;
+        tol2 = 2.0 * tol1;
+        if (num >= (double)a.maxfun) ST(DONE) = 1.0;
+    }
+    double xn = x;
+    if (ST(DONE) == 0.0) {
+        if (!(fabs(xf - xm) > (tol2 - 0.5 * (bv - av)))) {
+            ST(DONE) = 1.0;   // while-condition false: converged, xf is the answer
+        } else {
+            bool golden = true;
+            if (fabs(e) > tol1) {   // parabolic fit
+                golden = false;
+                double rr = (xf - nfc) * (fx - ffulc);
+                double qq = (xf - fulc) * (fx - fnfc);
+                double pp = (xf - fulc) * qq - (xf - nfc) * rr;
+                qq = 2.0 * (qq - rr);
+                if (qq > 0.0) pp = -pp;
+                qq = fabs(qq);
+                rr = e;
+                e = rat;
+                if ((fabs(pp) < fabs(0.5 * qq * rr)) && (pp > qq * (av - xf)) && (pp < qq * (bv - xf))) {
+                    rat = (pp + 0.0) / qq;
+                    xn = xf + rat;
+                    if (((xn - av) < tol2) || ((bv - xn) < tol2)) {
+                        const double d = xm - xf;
+                        const double si = (d > 0.0 ? 1.0 : (d < 0.0 ? -1.0 : 0.0)) + (d == 0.0 ? 1.0 : 0.0);
+                        rat = tol1 * si;
+                    }
+                } else {
+                    golden = true;
+                }
+            }
+            if (golden) {
+                e = (xf >= xm) ? av - xf : bv - xf;
+                rat = golden_mean * e;
+            }
+            const double si = (rat > 0.0 ? 1.0 : (rat < 0.0 ? -1.0 : 0.0)) + (rat == 0.0 ? 1.0 : 0.0);
+            xn = xf + si * fmax(fabs(rat), tol1);
+        }
+    }
+    ST(A) = av;
+    ST(B) = bv;
+    ST(FULC) = fulc;
+    ST(NFC) = nfc;
+    ST(XF) = xf;
+    ST(RAT) = rat;
+    ST(E) = e;
+    ST(X) = xn;
+    ST(FX) = fx;
+    ST(FFULC) = ffulc;
+    ST(FNFC) = fnfc;
+    ST(XM) = xm;
+    ST(TOL1) = tol1;
+    ST(TOL2) = tol2;
+    ST(NUM) = num;
+    a.trial_inv2L[r] = 0.5 / xn;
+    a.trial_rsqrtL[r] = 1.0 / sqrt(xn);
+#undef ST
+}
+
+// Bracket and first trial point of every region (BasisInterval.py:77-84 and the head of the minimiser); also
+// w = 2 |a_i|^2 + cm2_i.  absx = max|x| of the region.
+__global__ void k_brent_start(BrentArgs a, const double *absx, double f_lo, double f_hi, const double *A, const double *cm2, double *w) {
+    using B = BrentState;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int R = a.R, M = a.M;
+    if (t < R * M) w[t] = 2.0 * (A[(size_t)t * 2] * A[(size_t)t * 2] + A[(size_t)t * 2 + 1] * A[(size_t)t * 2 + 1]) + cm2[t];
+    if (t >= R) return;
+    const int r = t;
+    const double lo = absx[r] * f_lo;
+    double hi = fmin((double)M, lo * f_hi);
+    if (hi < lo) hi = lo * f_hi;
+    const double golden_mean = 0.5 * (3.0 - sqrt(5.0));
+    const double fulc = lo + golden_mean * (hi - lo);
+    double *st = a.st;
+#define ST(f) st[(size_t)(B::f) * R + r]
+    ST(A) = lo;
+    ST(B) = hi;
+    ST(FULC) = fulc;
+    ST(NFC) = fulc;
+    ST(XF) = fulc;
+    ST(RAT) = 0.0;
+    ST(E) = 0.0;
+    ST(X) = fulc;
+    ST(FX) = 0.0;
+    ST(FFULC) = 0.0;
+    ST(FNFC) = 0.0;
+    ST(XM) = 0.0;
+    ST(TOL1) = 0.0;
+    ST(TOL2) = 0.0;
+    ST(NUM) = 0.0;
+    ST(DONE) = 0.0;
+#undef ST
+    a.trial_inv2L[r] = 0.5 / fulc;
+    a.trial_rsqrtL[r] = 1.0 / sqrt(fulc);
+}
+
+// The optimum of every region becomes its interval; counts the regions that did not converge.
+__global__ void k_brent_finish(BrentArgs a, double *L, unsigned long long *not_converged) {
+    using B = BrentState;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    L[r] = a.st[(size_t)B::XF * a.R + r];
+    if (a.st[(size_t)B::DONE * a.R + r] == 0.0) atomicAdd(not_converged, 1ull);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -126,6 +126,20 @@ class Engine(object):
             self._ck(self.lib.mrgp_build_basis(self.handle, layer, float(interval_factor), _dptr(L)))
 
     # ------------------------------------------------------------------------------------------
+    def set_adaptive_intervals(self, layer, use_prior=True, opt_interval_factor=(1., 1.2), enabled=True):
+        """BasisInterval(use_prior, opt_interval_factor) of `layer` (-1: all layers): every sweep re-learns the
+        layer's basis intervals after its bias / noise update (BasisInterval.py:18-134, MRGP.py:632-641)."""
+        self._ck(self.lib.mrgp_set_adaptive_intervals(self.handle, int(layer), int(bool(enabled)), int(bool(use_prior)),
+                                                      float(opt_interval_factor[0]), float(opt_interval_factor[1])))
+
+    def learn_intervals(self, j):
+        self._ck(self.lib.mrgp_learn_intervals(self.handle, int(j)))
+
+    def interval_failures(self):
+        out = C.c_uint64(0)
+        self._ck(self.lib.mrgp_interval_failures(self.handle, C.byref(out)))
+        return int(out.value)
+
     def sweep(self, n_iter=1):
         self._ck(self.lib.mrgp_sweep(self.handle, int(n_iter)))
 

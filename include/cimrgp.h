@@ -166,6 +166,16 @@ int mrgp_axis_update(mrgp_handle *h, int32_t layer);
 int mrgp_phase_b(mrgp_handle *h, int32_t layer);
 /* P4, P5, S5 finish: bias and noise posteriors and their moments (Stats.py:102-124 / 292-314).     */
 int mrgp_bias_noise(mrgp_handle *h, int32_t layer);
+/* B1: BasisInterval.learn (BasisInterval.py:18-134) + rebuild of the layer's basis (MRGP.py:632-641), ci mode,
+ * dx == 1.  mrgp_set_adaptive_intervals(layer | -1 = all, enabled, use_prior, opt_interval_factor[0], [1])
+ * mirrors BasisInterval(use_prior, opt_interval_factor) of that layer; once enabled every sweep learns the
+ * intervals of the layer after its bias / noise update (bounded search, scipy fminbound semantics: xatol
+ * 1e-5, run in lock-step over all regions).  mrgp_learn_intervals runs the search for one layer (per-phase
+ * use).  mrgp_interval_failures: regions whose search had not converged when the fixed iteration budget
+ * ran out, summed since mrgp_init_state.                                                             */
+int mrgp_set_adaptive_intervals(mrgp_handle *h, int32_t layer, int32_t enabled, int32_t use_prior, double factor_lo, double factor_hi);
+int mrgp_learn_intervals(mrgp_handle *h, int32_t layer);
+int mrgp_interval_failures(mrgp_handle *h, uint64_t *out);
 /* n_iter full sweeps (all layers, Gauss-Seidel order), replayed from one captured CUDA graph.       */
 int mrgp_sweep(mrgp_handle *h, int32_t n_iter);
 int mrgp_synchronize(mrgp_handle *h);

@@ -24,13 +24,13 @@ def split(g, prefix):
     return {k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)}
 
 
-def build(x, y, m, resolution, fi, **kw):
+def build(x, y, m, resolution, fi, basis_interval_obj=None, **kw):
     from cimrgp_b200 import IndexSetUniform, LaplacianEigenpairs, MaternKernel
     from cimrgp_b200.MRGP import MultiResolutionGaussianProcess
     return MultiResolutionGaussianProcess(
         train_xy=[x, y], n_basis=m, index_set_obj=IndexSetUniform(x.shape[0], resolution, 2),
         basis_function_obj=LaplacianEigenpairs(), spectral_density_obj=MaternKernel(nu=1, l=1, sf=1),
-        adaptive_inputs=False, standard_normalized_inputs=True, basis_interval_obj=None, interval_factor=1,
+        adaptive_inputs=False, standard_normalized_inputs=True, basis_interval_obj=basis_interval_obj, interval_factor=1,
         forced_independence=fi, **kw)
 
 
@@ -131,6 +131,53 @@ def test_elbo_matches_reference_golden():
     assert mismatch(np.array(m.lower_bound_terms), g['terms'], RTOL) is None
     assert mismatch(np.array(m.lower_bound_layer), g['lower_bound_layer'], RTOL) is None
     assert mismatch(np.array(m.lower_bound), g['lower_bound'], RTOL) is None
+
+
+def test_adaptive_intervals_match_reference_golden():
+    """B1 (BasisInterval.learn): the reference's own run with BasisInterval(opt_interval_factor=(1, 1.2))."""
+    from cimrgp_b200 import BasisInterval
+    g = load('c1_ci_adaptive')
+    x, y = g['x'], g['y']
+    m = build(x, y, int(g['meta.M']), int(g['meta.resolution']), False,
+              basis_interval_obj=BasisInterval(opt_interval_factor=(1, 1.2)))
+    assert m.adaptive_basis_intervals is True
+    done = 0
+    for k in g['meta.checkpoints']:
+        m.fit(int(k) - done, None)
+        done = int(k)
+        compare(m._engine.state(), split(g, 'k%d.' % k))
+    assert m._engine.interval_failures() == 0
+    with pytest.raises(NotImplementedError):
+        m.fit(2, 1e-3)
+
+
+@pytest.mark.parametrize('use_prior', [True, False])
+def test_adaptive_intervals_against_oracle(use_prior):
+    """Ragged regions over several CTAs, with and without the spectral prior in the objective."""
+    from cimrgp_b200 import BasisInterval
+    n = 6000
+    x, y = workloads.workload1(n)
+    offsets = O.uniform_offsets(n, 4, 2)
+    ora = O.OracleMRGP(x, y, 20, offsets, mode='ci', adaptive=dict(use_prior=use_prior, opt_interval_factor=(1., 1.3)))
+    m = build(x, y, 20, 4, False, basis_interval_obj=BasisInterval(use_prior=use_prior, opt_interval_factor=(1., 1.3)))
+    for _ in range(2):
+        ora.sweep()
+    m.fit(2, None)
+    ref = ora.state()
+    got = m._engine.state()
+    # the optimum is located to xatol = 1e-5 by both sides with the same steps; the intervals do move
+    static = np.max(np.abs(x - np.mean(x)) / np.std(x))
+    assert abs(float(ref['L0.L'].ravel()[0]) / static - 1.0) > 1e-7
+    compare(got, ref)
+    assert m._engine.interval_failures() == 0
+
+
+def test_adaptive_intervals_are_switched_off_in_fi_mode():
+    """MRGP.py:108-109."""
+    from cimrgp_b200 import BasisInterval
+    x, y = workloads.workload1(512)
+    m = build(x, y, 20, 3, True, basis_interval_obj=BasisInterval())
+    assert m.adaptive_basis_intervals is False
 
 
 def test_graph_replay_equals_stepwise_phases_and_is_deterministic():
