@@ -207,7 +207,8 @@ def run_gpu(args, rank, world, local_rank):
         ev[k][1].record(eng.stream)
     barrier()
     launches = eng.launch_count() - l0
-    if multi:
+    exchange = getattr(eng, 'exchange', None)
+    if multi and exchange == 'nccl':
         launches = 80 * args.steps   # per rank and sweep: 10 x (phase A, sums, mid, omega, phase B, sums, bias/noise) + NCCL
     step_ms = [max_over_ranks(a.elapsed_time(b)) for a, b in ev]
     total_s = sum(step_ms) / 1e3
@@ -239,7 +240,11 @@ def run_gpu(args, rank, world, local_rank):
                 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * total_s / args.steps,
                 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': WORKLOAD, 'l2': 'flushed between timed steps (256 MB write)',
-                           'parallelism': 'samples sharded in %d contiguous chunks; 2 NCCL all-reduces of <= 245 KB per layer' % world},
+                           'parallelism': ('samples sharded in %d contiguous chunks; 2 exchanges of <= 245 KB of region '
+                                           'statistics per layer, ' % world) +
+                                          ('own kernels over NVLink peer memory, whole sweep in one CUDA graph'
+                                           if exchange == 'peer' else 'NCCL all-reduce'),
+                           'exchange': exchange},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
                 'roofline': {'bound': 'hbm', 'achieved': BYTES_SWEEP_PER_SAMPLE_LAYER * N_SAMPLES * N_LAYERS / (total_s / args.steps) / 1e9,
                              'peak': peak * world, 'peak_source': peak_src, 'unit': 'GB/s',

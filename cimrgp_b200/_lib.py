@@ -8,6 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcimrgp.so')
 
+COMM_BLOB_BYTES = 128
 ABI_VERSION = 2
 MODE_CI, MODE_FI = 0, 1
 OK, EINVAL, ENODEVICE, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4, -5
@@ -68,6 +69,9 @@ SIGNATURES = {
     'mrgp_elbo': (C.c_int, [_P, _D]),
     'mrgp_predict_mean': (C.c_int, [_P, _P, C.c_int64, _I64PP, C.c_int32, _P]),
     'mrgp_predict_var': (C.c_int, [_P, _P, C.c_int64, _P]),
+    'mrgp_comm_export': (C.c_int, [_P, C.c_void_p]),
+    'mrgp_comm_bind': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]),
+    'mrgp_exchange': (C.c_int, [_P, C.c_int32, C.c_int32]),
     'mrgp_region_sums': (C.c_int, [_P, C.c_int32, C.c_int32]),
     'mrgp_exchange_buffer': (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     'mrgp_build_basis_stage': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_double]),

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 #include "mrgp_kernels.cuh"
 
@@ -97,6 +98,18 @@ struct mrgp_handle {
     int64_t launches = 0, launches_per_sweep = 0, sweeps_done = 0;
     bool capturing = false;
     bool timeline = false;
+    // peer-memory exchange (multi-GPU): arena + flags in one cudaMalloc'ed block that the peers map through CUDA IPC
+    struct Comm {
+        bool exported = false, ready = false;
+        void *mem = nullptr;
+        size_t bytes = 0, slot_doubles = 0;
+        double *arena = nullptr;
+        unsigned long long *flags = nullptr, *seq = nullptr;
+        unsigned int *err = nullptr;
+        void *peer_base[kMaxRanks] = {};
+        bool opened[kMaxRanks] = {};
+        CommArgs args{};
+    } comm;
     // adaptive basis intervals (BasisInterval.learn): the per-layer switches live in LayerDev
     int32_t ad_iters = 40;
     unsigned long long *brent_fail = nullptr;
@@ -683,6 +696,30 @@ int do_bias_noise(mrgp_handle *h, int j) {
     return MRGP_OK;
 }
 
+// One exchange over peer memory: local dense sums -> arena slot, publish, reduce over the owning ranks -> h->xchg.
+int do_exchange(mrgp_handle *h, int j, int slot, int nv, bool is_max) {
+    if (!h->comm.ready) return fail(h, MRGP_ESTATE, "no peer exchange bound: mrgp_comm_export / mrgp_comm_bind first");
+    const LayerPlan &lp = h->plan[j];
+    LayerDev &d = h->dev[j];
+    const int total = lp.R * h->part_stride;
+    const size_t off = (size_t)slot * h->comm.slot_doubles;
+    if (is_max)
+        k_region_sums<true><<<(total + 255) / 256, 256, 0, h->stream>>>(d.region_run, h->part, h->part_stride, nv, lp.R, h->comm.arena + off);
+    else
+        k_region_sums<false><<<(total + 255) / 256, 256, 0, h->stream>>>(d.region_run, h->part, h->part_stride, nv, lp.R, h->comm.arena + off);
+    CK(cudaGetLastError());
+    k_comm_signal<<<1, 32, 0, h->stream>>>(h->comm.args);
+    CK(cudaGetLastError());
+    const int grid = std::max(1, std::min(96, (total + 255) / 256));
+    if (is_max)
+        k_comm_reduce<true><<<grid, 256, 0, h->stream>>>(h->comm.args, off, d.offsets, lp.R, h->part_stride, nv, h->xchg);
+    else
+        k_comm_reduce<false><<<grid, 256, 0, h->stream>>>(h->comm.args, off, d.offsets, lp.R, h->part_stride, nv, h->xchg);
+    CK(cudaGetLastError());
+    count(h, 3);
+    return MRGP_OK;
+}
+
 template <int M>
 cudaError_t launch_objective(mrgp_handle *h, const IntervalArgs &q, bool infer, bool latent) {
     dim3 grid(h->n_ctas), block(kThreads);
@@ -762,6 +799,15 @@ int sweep_once(mrgp_handle *h, bool fork_omega) {
     int rc;
     for (int j = 0; j < J; ++j) {
         if ((rc = do_phase_a(h, j))) return rc;
+        if (h->sharded) {
+            // sample-sharded: the region statistics of both streaming phases are summed over the ranks
+            if ((rc = do_exchange(h, j, 0, h->cfg.n_basis * h->cfg.dy, false))) return rc;
+            if ((rc = do_axis_update(h, j, fork_omega && ci))) return rc;
+            if ((rc = do_phase_b(h, j, false))) return rc;
+            if ((rc = do_exchange(h, j, 1, h->cfg.dy + 3, false))) return rc;
+            if ((rc = do_bias_noise(h, j))) return rc;
+            continue;
+        }
         if ((rc = do_axis_update(h, j, fork_omega && ci))) return rc;
         if (h->dev[j].adaptive && ci) {
             // the latent functions of the next layer use the re-learnt basis (MRGP.py:632-649): statistics first,
@@ -963,6 +1009,9 @@ void mrgp_destroy(mrgp_handle *h) {
     for (auto e : h->ev_fork) cudaEventDestroy(e);
     for (auto e : h->ev_join) cudaEventDestroy(e);
     for (auto e : h->ev_ard) cudaEventDestroy(e);
+    for (int q = 0; q < kMaxRanks; ++q)
+        if (h->comm.opened[q]) cudaIpcCloseMemHandle(h->comm.peer_base[q]);
+    if (h->comm.mem) cudaFree(h->comm.mem);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1066,10 +1115,21 @@ int mrgp_set_spectral(mrgp_handle *h, int32_t layer, int32_t use_prior, double n
     return MRGP_OK;
 }
 
+int mrgp_build_basis_stage(mrgp_handle *h, int32_t layer, int32_t stage, double interval_factor);
+
 int mrgp_build_basis(mrgp_handle *h, int32_t layer, double interval_factor, const double *L_host) {
     int rc = check_ready(h, layer, false);
     if (rc) return rc;
-    if (h->sharded) return fail(h, MRGP_ESTATE, "sharded handle: use mrgp_build_basis_stage with all-reduces in between");
+    if (h->sharded && !h->comm.ready) return fail(h, MRGP_ESTATE, "sharded handle: bind the peer exchange first, or use mrgp_build_basis_stage with all-reduces in between");
+    if (h->sharded) {
+        if (L_host) return fail(h, MRGP_EINVAL, "given intervals are not supported on a sharded handle");
+        int rs;
+        if ((rs = mrgp_build_basis_stage(h, layer, -1, interval_factor))) return rs;   // local max|x| partials
+        if ((rs = do_exchange(h, layer, 0, 1, true))) return rs;
+        if ((rs = mrgp_build_basis_stage(h, layer, -2, interval_factor))) return rs;   // L, lambda, S; local sum phi^2 partials
+        if ((rs = do_exchange(h, layer, 1, h->cfg.n_basis, false))) return rs;
+        return mrgp_build_basis_stage(h, layer, 2, interval_factor);
+    }
     LayerDev &d = h->dev[layer];
     const LayerPlan &lp = h->plan[layer];
     StreamArgs sa = stream_args(h, layer);
@@ -1255,7 +1315,8 @@ int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
     int rc = check_ready(h, 0, true);
     if (rc) return rc;
     if (n_iter < 0) return fail(h, MRGP_EINVAL, "n_iter < 0");
-    if (h->sharded) return fail(h, MRGP_ESTATE, "mrgp_sweep on a sharded handle: drive the phases and the all-reduces from the host");
+    if (h->sharded && !h->comm.ready)
+        return fail(h, MRGP_ESTATE, "mrgp_sweep on a sharded handle needs the peer exchange (mrgp_comm_bind); without it drive the phases and the all-reduces from the host");
     if (!h->graph_exec) {
         h->launches_per_sweep = 0;
         h->capturing = true;
@@ -1285,6 +1346,11 @@ int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
 int mrgp_synchronize(mrgp_handle *h) {
     if (!h || !h->stream) return fail(h, MRGP_ESTATE, "no stream");
     CK(cudaStreamSynchronize(h->stream));
+    if (h->comm.ready) {
+        unsigned int err = 0;
+        CK(cudaMemcpy(&err, h->comm.err, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) return fail(h, MRGP_ECUDA, "peer exchange timed out: a rank did not publish its region sums");
+    }
     return MRGP_OK;
 }
 
@@ -1363,6 +1429,113 @@ int mrgp_predict_var(mrgp_handle *h, const double *x_test_dev, int64_t n_test, d
     return MRGP_OK;
 }
 
+namespace {
+struct CommBlob {          // what the ranks all-gather; MRGP_COMM_BLOB_BYTES in the header
+    uint64_t magic;
+    int64_t pid;
+    uint64_t ptr;
+    int32_t device, pad;
+    uint64_t bytes;
+    cudaIpcMemHandle_t handle;
+};
+static_assert(sizeof(CommBlob) <= 128, "blob must fit MRGP_COMM_BLOB_BYTES");
+constexpr uint64_t kBlobMagic = 0x6d726770636f6d31ull;
+}   // namespace
+
+int mrgp_comm_export(mrgp_handle *h, void *blob_out) {
+    if (!h || !blob_out) return fail(h, MRGP_EINVAL, "null argument");
+    if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
+    if (!h->sharded) return fail(h, MRGP_ESTATE, "not a sharded handle");
+    auto &c = h->comm;
+    if (!c.exported) {
+        int rmax = 0;
+        for (auto &lp : h->plan) rmax = std::max(rmax, lp.R);
+        c.slot_doubles = ((size_t)rmax * h->part_stride + 31) & ~(size_t)31;
+        c.bytes = 512 + 2 * c.slot_doubles * sizeof(double);
+        CK(cudaSetDevice(h->cfg.device));
+        CK(cudaMalloc(&c.mem, c.bytes));
+        CK(cudaMemset(c.mem, 0, c.bytes));
+        c.flags = reinterpret_cast<unsigned long long *>(c.mem);
+        c.seq = reinterpret_cast<unsigned long long *>(static_cast<char *>(c.mem) + 256);
+        c.err = reinterpret_cast<unsigned int *>(static_cast<char *>(c.mem) + 320);
+        c.arena = reinterpret_cast<double *>(static_cast<char *>(c.mem) + 512);
+        c.exported = true;
+    }
+    CommBlob b{};
+    b.magic = kBlobMagic;
+    b.pid = (int64_t)getpid();
+    b.ptr = (uint64_t)(uintptr_t)c.mem;
+    b.device = h->cfg.device;
+    b.bytes = c.bytes;
+    CK(cudaIpcGetMemHandle(&b.handle, c.mem));
+    std::memset(blob_out, 0, 128);
+    std::memcpy(blob_out, &b, sizeof b);
+    return MRGP_OK;
+}
+
+int mrgp_comm_bind(mrgp_handle *h, int32_t rank, int32_t world, const void *blobs, const int64_t *bounds) {
+    if (!h || !blobs || !bounds) return fail(h, MRGP_EINVAL, "null argument");
+    auto &c = h->comm;
+    if (!c.exported) return fail(h, MRGP_ESTATE, "mrgp_comm_export first");
+    if (c.ready) return fail(h, MRGP_ESTATE, "peer exchange already bound");
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(h, MRGP_EINVAL, "rank / world out of range (at most %d ranks)", kMaxRanks);
+    if (bounds[0] != 0 || bounds[world] != h->cfg.n_samples || bounds[rank] != h->lo || bounds[rank + 1] != h->hi)
+        return fail(h, MRGP_EINVAL, "bounds do not match the sample range of this handle");
+    for (int q = 0; q < world; ++q)
+        if (bounds[q + 1] < bounds[q]) return fail(h, MRGP_EINVAL, "bounds must be non-decreasing");
+    CK(cudaSetDevice(h->cfg.device));
+    CommArgs a{};
+    a.rank = rank;
+    a.world = world;
+    a.seq = c.seq;
+    a.err = c.err;
+    for (int q = 0; q <= world; ++q) a.bounds[q] = bounds[q];
+    for (int q = 0; q < world; ++q) {
+        CommBlob b;
+        std::memcpy(&b, static_cast<const char *>(blobs) + (size_t)q * 128, sizeof b);
+        if (b.magic != kBlobMagic || b.bytes != c.bytes) return fail(h, MRGP_EINVAL, "blob of rank %d is not from a matching handle", q);
+        void *base = nullptr;
+        if (q == rank) {
+            base = c.mem;
+        } else if (b.pid == (int64_t)getpid()) {
+            base = reinterpret_cast<void *>((uintptr_t)b.ptr);      // same process (several handles, threads): plain pointer
+            if (b.device != h->cfg.device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, h->cfg.device, b.device));
+                if (!can) return fail(h, MRGP_ENODEVICE, "device %d cannot map the memory of device %d", h->cfg.device, b.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+                cudaGetLastError();
+            }
+        } else {
+            CK(cudaIpcOpenMemHandle(&base, b.handle, cudaIpcMemLazyEnablePeerAccess));
+            c.peer_base[q] = base;
+            c.opened[q] = true;
+        }
+        a.flags[q] = reinterpret_cast<unsigned long long *>(base);
+        a.arena[q] = reinterpret_cast<const double *>(static_cast<char *>(base) + 512);
+    }
+    // same shared-memory carveout as the rest of the sweep: no SM reconfiguration around the exchanges
+    CK(cudaFuncSetAttribute(k_region_sums<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_region_sums<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_comm_signal, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_comm_reduce<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_comm_reduce<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_bias_noise<2>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    c.args = a;
+    c.ready = true;
+    drop_graph(h);
+    return MRGP_OK;
+}
+
+int mrgp_exchange(mrgp_handle *h, int32_t layer, int32_t which) {
+    int rc = check_ready(h, layer, false);
+    if (rc) return rc;
+    if (!h->sharded) return fail(h, MRGP_ESTATE, "not a sharded handle");
+    if (which != MRGP_X_PHASE_A && which != MRGP_X_PHASE_B) return fail(h, MRGP_EINVAL, "which must be MRGP_X_PHASE_A or MRGP_X_PHASE_B");
+    return do_exchange(h, layer, which, which == MRGP_X_PHASE_A ? h->cfg.n_basis * h->cfg.dy : h->cfg.dy + 3, false);
+}
+
 int mrgp_region_sums(mrgp_handle *h, int32_t layer, int32_t which) {
     int rc = check_ready(h, layer, false);
     if (rc) return rc;
@@ -1395,7 +1568,18 @@ int mrgp_build_basis_stage(mrgp_handle *h, int32_t layer, int32_t stage, double 
     RegionArgs ra = region_args(h, layer);
     ra.interval_factor = interval_factor;
     const int total = lp.R * h->part_stride;
-    if (stage == 0) {          // local max|x| per region -> exchange buffer (caller: all-reduce MAX)
+    if (stage == -1) {         // peer exchange variant of stage 0: partials only
+        k_absmax<<<h->n_ctas, kThreads, 0, h->stream>>>(sa);
+        CK(cudaGetLastError());
+        count(h);
+    } else if (stage == -2) {  // peer exchange variant of stage 1
+        k_region_setup<<<(lp.R + 7) / 8, 256, 0, h->stream>>>(ra);
+        CK(cudaGetLastError());
+        cudaError_t e = cudaErrorInvalidValue;
+        DISPATCH_M(h->cfg.n_basis, e = launch_phi2sum<MM>(h, sa));
+        CK(e);
+        count(h, 2);
+    } else if (stage == 0) {   // local max|x| per region -> exchange buffer (caller: all-reduce MAX)
         k_absmax<<<h->n_ctas, kThreads, 0, h->stream>>>(sa);
         CK(cudaGetLastError());
         k_region_sums<true><<<(total + 255) / 256, 256, 0, h->stream>>>(d.region_run, h->part, h->part_stride, 1, lp.R, h->xchg);

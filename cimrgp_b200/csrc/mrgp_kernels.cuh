@@ -1255,6 +1255,103 @@ __global__ void k_region_sums(const int32_t *region_run, const double *part, int
     out[(size_t)r * part_stride + v] = acc;   // padding columns are kept at zero
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU exchange over peer memory (NVLink / NVSwitch).  Every rank keeps a small arena that
+// its peers have mapped (CUDA IPC).  One exchange = (1) the dense per-region sums of the local run partials are
+// written into the local arena, (2) the rank stores the next sequence number into its slot of every peer's flag
+// array (st.release.sys), (3) a reduce kernel waits until every peer's number has arrived and sums, per region,
+// the arenas of exactly the ranks whose sample chunk overlaps the region, in rank order - every rank forms the
+// same sum in the same order, so the replicated small-matrix state stays bit-identical across ranks.  Two arena
+// slots (phase A / phase B) are enough: a rank can only overwrite a slot after it has waited for a later signal
+// of every peer, which each peer sends after its own read of that slot (stream order).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+
+struct CommArgs {
+    int32_t rank, world;
+    const double *arena[kMaxRanks];            // arena base of every rank (own entry: the local pointer)
+    unsigned long long *flags[kMaxRanks];      // flags[p][src]: last sequence number rank src has published to rank p
+    unsigned long long *seq;                   // local: sequence number of the last exchange
+    unsigned int *err;                         // local: set when a wait timed out
+    int64_t bounds[kMaxRanks + 1];             // rank q owns the samples [bounds[q], bounds[q + 1])
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Publish: the arena of this rank holds the sums of exchange number (*seq + 1).  One warp.
+__global__ void k_comm_signal(CommArgs c) {
+    __shared__ unsigned long long s;
+    if (threadIdx.x == 0) {
+        s = *c.seq + 1ull;
+        *c.seq = s;
+    }
+    __syncthreads();
+    __threadfence_system();
+    if ((int)threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + c.rank, s);
+}
+
+constexpr unsigned long long kCommTimeoutNs = 4000000000ull;   // a lost peer must not hang the GPU
+
+// out[r][v] = sum (or max) over the ranks that own samples of region r of their arena entries.
+template <bool MAX>
+__global__ void __launch_bounds__(256) k_comm_reduce(CommArgs c, size_t slot_offset, const int64_t *offsets, int R, int stride, int nv,
+                                                     double *out) {
+    __shared__ int ok;
+    if (threadIdx.x < 32) {
+        const unsigned long long want = *c.seq;
+        bool good = *reinterpret_cast<volatile unsigned int *>(c.err) == 0u;   // one time-out ends all later waits
+        if (good && (int)threadIdx.x < c.world && (int)threadIdx.x != c.rank) {
+            const unsigned long long *f = c.flags[c.rank] + threadIdx.x;
+            const unsigned long long t0 = global_ns();
+            while (ld_acquire_sys(f) < want) {
+                if (global_ns() - t0 > kCommTimeoutNs) {
+                    good = false;
+                    atomicExch(c.err, 1u);
+                    break;
+                }
+                __nanosleep(64);
+            }
+        }
+        good = __all_sync(0xffffffffu, good);
+        if (threadIdx.x == 0) ok = good ? 1 : 0;
+    }
+    __syncthreads();
+    if (!ok) return;
+    const int total = R * stride;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int r = t / stride, v = t - r * stride;
+        double acc = 0.0;
+        const int64_t lo = offsets[r], hi = offsets[r + 1];
+        if (v < nv && hi > lo) {
+            int q0 = 0, q1 = c.world - 1;
+            while (c.bounds[q0 + 1] <= lo) ++q0;
+            while (c.bounds[q1] >= hi) --q1;
+            for (int q = q0; q <= q1; ++q) {
+                const double x = ld_relaxed_sys(c.arena[q] + slot_offset + t);
+                acc = MAX ? fmax(acc, x) : acc + x;
+            }
+        }
+        out[t] = acc;
+    }
+}
+
 // Standalone bias / noise update (per-phase ABI entry; the sweep uses the fused tail of phase B).
 template <int DY>
 __global__ void __launch_bounds__(kThreadsB) k_bias_noise(StreamArgs p) {

@@ -197,16 +197,33 @@ int mrgp_predict_var(mrgp_handle *h, const double *x_test_dev, int64_t n_test, d
 /* ---- sample sharding over several GPUs ------------------------------------------ */
 
 /* A handle created with [sample_begin, sample_end) streams only its chunk of x, y (mrgp_set_data* take the
- * LOCAL rows) but knows every region.  The per-region sufficient statistics of a phase are gathered into one
- * dense exchange buffer, summed over the ranks by the caller (NCCL all-reduce on the handle's stream) and
- * consumed by the replicated small-matrix step:
- *     mrgp_phase_a   -> mrgp_region_sums(layer, MRGP_X_PHASE_A) -> all-reduce SUM -> mrgp_axis_update
- *     mrgp_phase_b   -> mrgp_region_sums(layer, MRGP_X_PHASE_B) -> all-reduce SUM -> mrgp_bias_noise
- * and at construction
- *     mrgp_build_basis_stage(layer, 0) -> all-reduce MAX -> stage 1 -> all-reduce SUM -> stage 2.
- * mrgp_sweep() is refused on a sharded handle (the collectives belong to the caller, who captures the whole
- * sequence in a CUDA graph).  No per-sample data ever leaves a GPU.                                       */
+ * LOCAL rows) but knows every region.  The per-region sufficient statistics of a phase (<= R x 60 doubles) are
+ * summed over the ranks and consumed by the replicated small-matrix step; no per-sample data ever leaves a GPU.
+ *
+ * (1) Peer-memory exchange (the product path): every rank keeps a small arena that the peers map over
+ *     NVLink / NVSwitch (CUDA IPC between processes, plain pointers inside one process).
+ *         mrgp_comm_export(h, blob)                     -> 128-byte description of this rank's arena
+ *         (all-gather the blobs of all ranks with any transport: torch.distributed, MPI, a file)
+ *         mrgp_comm_bind(h, rank, world, blobs, bounds) -> maps the peers; bounds[q], bounds[q+1] = samples of rank q
+ *     Afterwards mrgp_build_basis, mrgp_sweep (one CUDA graph, exchanges included) and mrgp_exchange work on the
+ *     sharded handle.  One exchange = dense local sums -> arena, a release-store of the next sequence number into
+ *     every peer's flag array, and a reduce kernel that waits for all peers and sums, per region, the arenas of
+ *     exactly the ranks that own samples of the region, in rank order: every rank computes bit-identical sums.
+ *     A peer that never publishes makes the wait time out (4 s) and mrgp_synchronize return MRGP_ECUDA.
+ *         mrgp_phase_a -> mrgp_exchange(layer, MRGP_X_PHASE_A) -> mrgp_axis_update
+ *         mrgp_phase_b -> mrgp_exchange(layer, MRGP_X_PHASE_B) -> mrgp_bias_noise
+ * (2) Caller-side collective (NCCL all-reduce on the handle's stream; kept as the comparison arm):
+ *         mrgp_phase_a -> mrgp_region_sums(layer, MRGP_X_PHASE_A) -> all-reduce SUM -> mrgp_axis_update
+ *         mrgp_phase_b -> mrgp_region_sums(layer, MRGP_X_PHASE_B) -> all-reduce SUM -> mrgp_bias_noise
+ *     and at construction
+ *         mrgp_build_basis_stage(layer, 0) -> all-reduce MAX -> stage 1 -> all-reduce SUM -> stage 2.
+ *     mrgp_sweep() is refused on a sharded handle without (1).                                            */
 enum { MRGP_X_PHASE_A = 0, MRGP_X_PHASE_B = 1 };
+#define MRGP_COMM_BLOB_BYTES 128
+#define MRGP_COMM_MAX_RANKS 16
+int mrgp_comm_export(mrgp_handle *h, void *blob_out);
+int mrgp_comm_bind(mrgp_handle *h, int32_t rank, int32_t world, const void *blobs, const int64_t *bounds);
+int mrgp_exchange(mrgp_handle *h, int32_t layer, int32_t which);
 int mrgp_region_sums(mrgp_handle *h, int32_t layer, int32_t which);
 int mrgp_exchange_buffer(mrgp_handle *h, int32_t layer, int32_t which, void **dev_ptr, size_t *n_doubles);
 int mrgp_build_basis_stage(mrgp_handle *h, int32_t layer, int32_t stage, double interval_factor);

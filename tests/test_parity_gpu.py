@@ -300,8 +300,8 @@ def test_constructor_errors_match_reference():
         M([x, y], 30, idx, le, [mk, mk])                                                # MRGP.py:75
     with pytest.raises(ValueError):
         M([x, y], 30, idx, le, mk, interval_factor=[1, 1])                              # MRGP.py:102
-    with pytest.raises(NotImplementedError):
-        M([x, y], 30, idx, le, mk, basis_interval_obj=BasisInterval())
+    with pytest.raises(ValueError):
+        M([x, y], 30, idx, le, mk, basis_interval_obj=[BasisInterval()])                # MRGP.py:123
     m = M([x, y], 30, idx, le, mk)
     with pytest.raises(ValueError):
         m.get_predicted_mean(x, index_set_obj=IndexSetUniform(64, 3, 2))               # MRGP.py:758-760
@@ -333,11 +333,23 @@ class _ThreadComm(object):
         torch.cuda.synchronize()
         self.barrier.wait()
 
+    def all_gather_bytes(self, payload):
+        self.slots[self.local.rank] = bytes(payload)
+        self.barrier.wait()
+        out = list(self.slots)
+        self.barrier.wait()
+        return out
 
-@pytest.mark.parametrize('fi,world', [(False, 2), (True, 3)])
-def test_sample_sharding_matches_single_handle(fi, world):
-    """The multi-GPU decomposition (sample chunks + all-reduced region statistics) on one device: every rank must
-    end with the state of the unsharded run (up to the summation order of the exchanged statistics)."""
+    def sync(self):
+        self.barrier.wait()
+
+
+@pytest.mark.parametrize('fi,world,exchange', [(False, 2, 'nccl'), (True, 3, 'nccl'), (False, 3, 'peer'), (True, 2, 'peer')])
+def test_sample_sharding_matches_single_handle(fi, world, exchange):
+    """The multi-GPU decomposition (sample chunks + summed region statistics) on one device: every rank must
+    end with the state of the unsharded run (up to the summation order of the exchanged statistics).  'peer':
+    the library's own exchange through mapped arenas (here: handles of one process, plain pointers), driven phase
+    by phase (the captured-graph form runs between processes, next test); 'nccl': the caller-side all-reduce arm."""
     import threading
     from cimrgp_b200.distributed import ShardedEngine, chunk_bounds
     from cimrgp_b200.engine import Engine
@@ -355,7 +367,7 @@ def test_sample_sharding_matches_single_handle(fi, world):
     def work(rank):
         try:
             comm.local.rank = rank
-            e = ShardedEngine(xs, y, offsets, M, rank, world, comm=comm, mode=mode)
+            e = ShardedEngine(xs, y, offsets, M, rank, world, comm=comm, exchange=exchange, mode=mode)
             for _ in range(3):
                 e.sweep(1, use_graph=False)
             e.synchronize()
@@ -375,3 +387,20 @@ def test_sample_sharding_matches_single_handle(fi, world):
     a, b = engines[0].state(), engines[-1].state()
     for k in a:
         assert np.array_equal(a[k], b[k]), k     # replicated small-matrix steps: identical on every rank
+
+
+@pytest.mark.parametrize('mode,world', [('ci', 2), ('fi', 3)])
+def test_peer_exchange_between_processes(mode, world):
+    """The product form of the multi-GPU path: one process per rank, arenas mapped through CUDA IPC, the sweep one
+    CUDA graph with the exchanges inside.  The ranks share cuda:0 here (the parity box has one GPU)."""
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'sharded_worker.py')
+    port = 29600 + os.getpid() % 300
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
+           '--master-addr', '127.0.0.1', '--master-port', str(port), worker, mode]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    import re
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    oks = re.findall(r'rank \d+ ok ', res.stdout)      # the ranks' lines may interleave
+    assert len(oks) == world and 'MISMATCH' not in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
