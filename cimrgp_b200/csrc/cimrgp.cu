@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -60,7 +61,7 @@ struct LayerDev {
 struct SharedDev {
     double *axB = nullptr, *axKappa = nullptr, *axRho = nullptr, *axLogC = nullptr, *axCov = nullptr;
     double *ardShape = nullptr, *ardScale = nullptr, *ardMean = nullptr, *ardLogMean = nullptr;
-    double *omega = nullptr, *logOmegaHat = nullptr, *omegaIters = nullptr, *ardPartial = nullptr, *omegaEta = nullptr, *omegaWarm = nullptr, *omegaL = nullptr;
+    double *omega = nullptr, *logOmegaHat = nullptr, *omegaIters = nullptr, *ardPartial = nullptr, *omegaEta = nullptr, *omegaWarm = nullptr, *omegaK = nullptr;
     double *primeB = nullptr, *primeLogC = nullptr, *primeShape = nullptr, *primeScale = nullptr;
     double *priorB = nullptr, *priorLogC = nullptr, *priorShape = nullptr, *priorScale = nullptr;
 };
@@ -98,6 +99,7 @@ struct mrgp_handle {
     int64_t launches = 0, launches_per_sweep = 0, sweeps_done = 0;
     bool capturing = false;
     bool timeline = false;
+    bool omega_warp = true;   // single-warp register-resident omega solve for M <= 32 (MRGP_OMEGA_BLOCK=1: block version)
     // peer-memory exchange (multi-GPU): arena + flags in one cudaMalloc'ed block that the peers map through CUDA IPC
     struct Comm {
         bool exported = false, ready = false;
@@ -105,7 +107,7 @@ struct mrgp_handle {
         size_t bytes = 0, slot_doubles = 0;
         double *arena = nullptr;
         unsigned long long *flags = nullptr, *seq = nullptr;
-        unsigned int *err = nullptr;
+        unsigned int *err = nullptr, *counter = nullptr;
         void *peer_base[kMaxRanks] = {};
         bool opened[kMaxRanks] = {};
         CommArgs args{};
@@ -320,7 +322,7 @@ size_t carve(mrgp_handle *h, char *base) {
     s.ardPartial = c.take<double>((size_t)256 * M);
     s.omegaEta = c.take<double>((size_t)kMaxLayers * 64);
     s.omegaWarm = c.take<double>(kMaxLayers);
-    s.omegaL = c.take<double>((size_t)J * 64 * 64);
+    s.omegaK = c.take<double>((size_t)64 * 64 + 64);   // shifted, exponentiated table (column-major) + column shifts
     s.primeB = c.take<double>((size_t)M * DY * DY);
     s.primeLogC = c.take<double>(M);
     s.primeShape = c.take<double>(M);
@@ -451,7 +453,7 @@ RegionArgs region_args(mrgp_handle *h, int j) {
     a.ardPartial = s.ardPartial;
     a.omegaEta = s.omegaEta;
     a.omegaWarm = s.omegaWarm;
-    a.omegaL = s.omegaL;
+    a.omegaK = s.omegaK;
     a.primeB = s.primeB;
     a.primeLogC = s.primeLogC;
     a.primeShape = s.primeShape;
@@ -662,8 +664,19 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega) {
         k_ard<<<1, kOmegaThreads, smem, st>>>(a, n_partials);
         CK(cudaGetLastError());
         if (fork_omega) CK(cudaEventRecord(h->ev_ard[j], h->side));
-        CK(set_smem(k_scale, smem));
-        k_scale<<<1, kOmegaThreads, smem, st>>>(a);
+        if (h->omega_warp && M == 30) {
+            CK(cudaFuncSetAttribute(k_scale_warp<30>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            k_scale_warp<30><<<1, 32, 0, st>>>(a);
+        } else if (h->omega_warp && M == 20) {
+            CK(cudaFuncSetAttribute(k_scale_warp<20>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            k_scale_warp<20><<<1, 32, 0, st>>>(a);
+        } else if (h->omega_warp && M == 8) {
+            CK(cudaFuncSetAttribute(k_scale_warp<8>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            k_scale_warp<8><<<1, 32, 0, st>>>(a);
+        } else {
+            CK(set_smem(k_scale, smem));
+            k_scale<<<1, kOmegaThreads, smem, st>>>(a);
+        }
         CK(cudaGetLastError());
         count(h, 2);
         if (fork_omega) CK(cudaEventRecord(h->ev_join[j], h->side));
@@ -690,7 +703,7 @@ int do_bias_noise(mrgp_handle *h, int j) {
         a.region_run = h->dev[j].ident_run;
         a.part = h->xchg;
     }
-    k_bias_noise<2><<<1, kThreadsB, 0, h->stream>>>(a);
+    k_bias_noise<2><<<std::max(1, std::min(32, (h->plan[j].R + 7) / 8)), kThreadsB, 0, h->stream>>>(a);
     CK(cudaGetLastError());
     count(h);
     return MRGP_OK;
@@ -703,12 +716,11 @@ int do_exchange(mrgp_handle *h, int j, int slot, int nv, bool is_max) {
     LayerDev &d = h->dev[j];
     const int total = lp.R * h->part_stride;
     const size_t off = (size_t)slot * h->comm.slot_doubles;
+    if (h->part_stride > 256) return fail(h, MRGP_EINVAL, "exchange rows of more than 256 values are not supported");
     if (is_max)
-        k_region_sums<true><<<(total + 255) / 256, 256, 0, h->stream>>>(d.region_run, h->part, h->part_stride, nv, lp.R, h->comm.arena + off);
+        k_comm_sums_signal<true><<<lp.R, 256, 0, h->stream>>>(h->comm.args, d.region_run, h->part, h->part_stride, nv, h->comm.arena + off, h->comm.counter);
     else
-        k_region_sums<false><<<(total + 255) / 256, 256, 0, h->stream>>>(d.region_run, h->part, h->part_stride, nv, lp.R, h->comm.arena + off);
-    CK(cudaGetLastError());
-    k_comm_signal<<<1, 32, 0, h->stream>>>(h->comm.args);
+        k_comm_sums_signal<false><<<lp.R, 256, 0, h->stream>>>(h->comm.args, d.region_run, h->part, h->part_stride, nv, h->comm.arena + off, h->comm.counter);
     CK(cudaGetLastError());
     const int grid = std::max(1, std::min(96, (total + 255) / 256));
     if (is_max)
@@ -716,7 +728,7 @@ int do_exchange(mrgp_handle *h, int j, int slot, int nv, bool is_max) {
     else
         k_comm_reduce<false><<<grid, 256, 0, h->stream>>>(h->comm.args, off, d.offsets, lp.R, h->part_stride, nv, h->xchg);
     CK(cudaGetLastError());
-    count(h, 3);
+    count(h, 2);
     return MRGP_OK;
 }
 
@@ -839,6 +851,7 @@ FieldRef field_ref(mrgp_handle *h, int layer, int field) {
         if (layer != -1) return f;
         SharedDev &s = h->sh;
         switch (field) {
+            case 52: f = {s.omegaK + 64 * 64 + 32, 3}; break;   // MRGP_OMEGA_PROF builds: cycles of the Newton stages
             case MRGP_F_AXIS_B: f = {s.axB, (int64_t)M * DY * DY}; break;
             case MRGP_F_AXIS_KAPPA: f = {s.axKappa, (int64_t)M * DY}; break;
             case MRGP_F_AXIS_RHO: f = {s.axRho, (int64_t)M * DY}; break;
@@ -851,7 +864,6 @@ FieldRef field_ref(mrgp_handle *h, int layer, int field) {
             case MRGP_F_OMEGA: f = {s.omega, (int64_t)M * M}; break;
             case MRGP_F_LOG_OMEGA_HAT: f = {s.logOmegaHat, (int64_t)M * M}; break;
             case MRGP_F_OMEGA_ITERS: f = {s.omegaIters, h->cfg.n_layers}; break;
-            case 52: f = {s.omegaL, (int64_t)h->cfg.n_layers * 64 * 64}; break;   // debug: residual trace
             default: break;
         }
         return f;
@@ -956,6 +968,7 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
         return fail(h, MRGP_EINVAL, "bad sample range");
     h = new mrgp_handle();
     h->cfg = *cfg;
+    if (const char *e = getenv("MRGP_OMEGA_BLOCK")) h->omega_warp = !(e[0] == '1');
     h->sharded = cfg->sample_end > cfg->sample_begin;   // an explicit range selects the exchange-buffer path
     h->lo = h->sharded ? cfg->sample_begin : 0;
     h->hi = h->sharded ? cfg->sample_end : cfg->n_samples;
@@ -1458,6 +1471,7 @@ int mrgp_comm_export(mrgp_handle *h, void *blob_out) {
         c.flags = reinterpret_cast<unsigned long long *>(c.mem);
         c.seq = reinterpret_cast<unsigned long long *>(static_cast<char *>(c.mem) + 256);
         c.err = reinterpret_cast<unsigned int *>(static_cast<char *>(c.mem) + 320);
+        c.counter = reinterpret_cast<unsigned int *>(static_cast<char *>(c.mem) + 384);
         c.arena = reinterpret_cast<double *>(static_cast<char *>(c.mem) + 512);
         c.exported = true;
     }
@@ -1519,6 +1533,8 @@ int mrgp_comm_bind(mrgp_handle *h, int32_t rank, int32_t world, const void *blob
     CK(cudaFuncSetAttribute(k_region_sums<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_region_sums<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_comm_signal, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_comm_sums_signal<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_comm_sums_signal<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_comm_reduce<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_comm_reduce<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_bias_noise<2>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -1659,7 +1675,8 @@ int mrgp_timeline_read(mrgp_handle *h, int32_t *tags, float *ms, int32_t cap) {
     // Runs one sweep with fresh stamps and returns, per kernel in issue order, its begin and end in ms relative to
     // the earliest begin: tags[k] = layer * 4 + kind (0 phase A, 1 mid-step, 2 phase B, 3 omega), ms[2k], ms[2k+1].
     if (!h || !tags || !ms || !h->timeline) return MRGP_EINVAL;
-    const int n = h->cfg.n_layers * 4;
+    if (h->cfg.n_layers > kMaxLayersTs) return MRGP_EINVAL;
+    const int n = kMaxLayersTs * 4 + h->cfg.n_layers * 4;   // kernel slots, then the debug slots of the omega solve
     if (cap < n) return MRGP_EINVAL;
     std::vector<unsigned long long> init((size_t)kMaxLayers * 8), got((size_t)kMaxLayers * 8);
     for (size_t k = 0; k < init.size(); k += 2) {

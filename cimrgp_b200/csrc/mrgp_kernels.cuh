@@ -32,6 +32,14 @@ __device__ __forceinline__ void ts_end(unsigned long long *ts, int slot) {
     if (ts && threadIdx.x == 0) atomicMax(&ts[slot * 2 + 1], global_timer());
 }
 
+constexpr int kMaxLayersTs = 12;    // timeline: 4 kernel slots per layer, then 4 debug slots per layer
+__device__ __forceinline__ void ts_dbg(unsigned long long *ts, int layer, int k, bool end) {
+    if (layer >= kMaxLayersTs) return;
+    if (end)
+        ts_end(ts, kMaxLayersTs * 4 + layer * 4 + k);
+    else
+        ts_begin(ts, kMaxLayersTs * 4 + layer * 4 + k);
+}
 constexpr int kThreads = 256;      // streaming CTA size (8 warps)
 constexpr int kPartBStride = 8;    // doubles per phase-B partial (dy + 3 <= 8)
 constexpr int kRedChunk = 32;      // values reduced per block_reduce round
@@ -249,10 +257,10 @@ __device__ __forceinline__ void bias_noise_region(const StreamArgs &p, int r, co
 // All regions of the layer by one block: `lpr` lanes (power of two <= 32) share the run loop of a region,
 // the lane sums are combined by shuffles in a fixed order.
 template <int DY, int NT>
-__device__ __forceinline__ void bias_noise_all(const StreamArgs &p, int lpr) {
+__device__ __forceinline__ void bias_noise_all(const StreamArgs &p, int lpr, int block = 0, int n_blocks = 1) {
     const int groups = NT / lpr;
     const int grp = threadIdx.x / lpr, sl = threadIdx.x % lpr;
-    for (int base = 0; base < p.R; base += groups) {
+    for (int base = block * groups; base < p.R; base += n_blocks * groups) {
         const int r = base + grp;
         double acc[DY + 3];
 #pragma unroll
@@ -712,7 +720,7 @@ struct RegionArgs {
     double *bias_prec, *bias_prec0, *bias_mean, *bias_mean0, *bias_var, *yvar, *sumsB;
     // shared (ci) or per-region (fi) axis / ARD
     double *axB, *axKappa, *axRho, *axLogC, *axCov, *ardShape, *ardScale, *ardMean, *ardLogMean;
-    double *omega, *logOmegaHat, *omegaIters, *ardPartial, *omegaEta, *omegaWarm, *omegaL;
+    double *omega, *logOmegaHat, *omegaIters, *ardPartial, *omegaEta, *omegaWarm, *omegaK;
     double *primeB, *primeLogC, *primeShape, *primeScale;   // snapshot read by ARD / omega (ci)
     const double *priorB, *priorLogC, *priorShape, *priorScale;
     double *bcontrib;          // (R, M, 3) ci: 0.5 noise zeta ytil ytil^T
@@ -1084,7 +1092,30 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
         const double tr = C[0] * B[0] + C[1] * B[2] + C[2] * B[1] + C[3] * B[3];   // trace(C_i B'_k)
         const double lw = tr + s_k[k] + (a.primeShape[k] - 1.0) * s_lmean[i] - a.primeScale[k] * s_mean[i];
         a.logOmegaHat[t] = lw;
+        P[t] = lw;                      // the old omega is no longer needed
     }
+    // head of the scaling solve, done here by the whole block: row shift, column shift, exponentials.  The solve
+    // (one warp, k_scale_warp) starts from the table K = exp(lw - rowmax - colmax), stored column-major, and the
+    // column shifts (row shifts cancel in the row normalisation).
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kOmegaThreads / 32;
+    for (int i = warp; i < M; i += NW) {
+        double mx = -INFINITY;
+        for (int k = lane; k < M; k += 32) mx = fmax(mx, P[i * M + k]);
+        mx = warp_max(mx);
+        for (int k = lane; k < M; k += 32) P[i * M + k] -= mx;
+    }
+    __syncthreads();
+    for (int k = warp; k < M; k += NW) {
+        double mx = -INFINITY;
+        for (int i = lane; i < M; i += 32) mx = fmax(mx, P[i * M + k]);
+        mx = warp_max(mx);
+        for (int i = lane; i < M; i += 32) a.omegaK[k * M + i] = exp(P[i * M + k] - mx);
+        if (lane == 0) a.omegaK[64 * 64 + k] = mx;
+    }
+    ts_dbg(a.ts, a.layer, 0, false);   // debug slots: [0] = (k_ard begin, k_ard end)
+    ts_dbg(a.ts, a.layer, 0, true);
 }
 
 
@@ -1255,6 +1286,199 @@ __global__ void k_region_sums(const int32_t *region_run, const double *part, int
     out[(size_t)r * part_stride + v] = acc;   // padding columns are kept at zero
 }
 
+// The same solve for M <= 32 in ONE warp, matrices resident in registers: lane i owns row i of the kernel table
+// (and of the Newton matrix), every loop over the M columns is unrolled, the only communication is warp
+// shuffles plus two transposes through shared memory per Newton step.  No block barriers: a Newton step costs
+// about a sixth of the block version's (which spends its time in 120 __syncthreads per step).  Same iteration
+// (shifts, warm start, Sinkhorn warm-up, Newton on the log column scalings, cold restart, fallback sweeps) and
+// same tolerances as k_scale / omega_solve_serial.
+template <int M>
+struct OmegaWarp {
+    static constexpr int LD = 34;   // even: 16-byte aligned rows for the paired loads; 34 * 8 B rows are conflict-free
+    // Row-normalised table P = diag(u) K diag(v) (rows in registers), its transpose in shared memory (T[k][i] =
+    // P[i][k]) and, on lane k, column k (Q) with its sum c.  Returns max |c - 1| (NaN if any entry is NaN).
+    static __device__ __forceinline__ double eval(const double (&K)[M], double (&P)[M], double (&Q)[M], double v, double &c,
+                                                  double *T, bool row, int lane) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; k += 2) {
+            P[k] = K[k] * __shfl_sync(0xffffffffu, v, k);
+            P[k + 1] = K[k + 1] * __shfl_sync(0xffffffffu, v, k + 1);
+            s0 += P[k];
+            s1 += P[k + 1];
+        }
+        const double u = row ? 1.0 / (s0 + s1) : 0.0;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            P[k] *= u;
+            T[k * LD + lane] = P[k];
+        }
+        __syncwarp();
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+        const double2 *col = reinterpret_cast<const double2 *>(T + (row ? lane : 0) * LD);
+#pragma unroll
+        for (int i = 0; i < M; i += 2) {
+            const double2 t = col[i >> 1];
+            Q[i] = t.x;
+            Q[i + 1] = t.y;
+            if (i & 2) {
+                c2 += t.x;
+                c3 += t.y;
+            } else {
+                c0 += t.x;
+                c1 += t.y;
+            }
+        }
+        c = (c0 + c1) + (c2 + c3);
+        double e = row ? fabs(c - 1.0) : 0.0;
+        const bool bad = !(e == e);
+        e = warp_max(e);
+        return __any_sync(0xffffffffu, bad) ? NAN : e;
+    }
+};
+
+template <int M>
+__global__ void __launch_bounds__(32, 1) k_scale_warp(RegionArgs a) {
+    static_assert(M <= 32 && (M & 1) == 0, "one lane per row, columns in pairs");
+    using W = OmegaWarp<M>;
+    constexpr int LD = W::LD;
+    __shared__ __align__(16) double T[M * LD];
+    const int lane = threadIdx.x;
+    const bool row = lane < M;
+    double K[M], P[M], Q[M];
+    ts_dbg(a.ts, a.layer, 1, false);   // debug slots: [1] = prologue, [2] = iteration
+#pragma unroll
+    for (int k = 0; k < M; ++k) K[k] = row ? a.omegaK[k * M + lane] : 0.0;
+    const double cshift = row ? a.omegaK[64 * 64 + lane] : 0.0;
+    // warm start: the log column scalings of the previous sweep's solve for this layer (stored relative to the
+    // un-shifted table, so that they do not depend on the shifts) seed the iteration
+    const bool warm = a.omegaWarm[a.layer] > 0.5;
+    double v = 1.0;
+    if (row) {
+        const double eta = a.omegaEta[a.layer * 64 + lane] + cshift;
+        v = (warm && isfinite(eta)) ? exp(fmax(-600.0, fmin(600.0, eta))) : 1.0;
+    }
+    int iters = 0;
+    double err_prev = INFINITY, c = 1.0;
+    int n_warmup = warm ? 0 : kOmegaWarmup;
+    ts_dbg(a.ts, a.layer, 1, true);
+    ts_dbg(a.ts, a.layer, 2, false);
+    for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
+        ++iters;
+        const double err = W::eval(K, P, Q, v, c, T, row, lane);
+        if (err < kOmegaTol) break;
+        if (!isfinite(err)) {   // a bad (warm) start or an overshooting Newton step: start again from the shifts alone
+            v = 1.0;
+            err_prev = INFINITY;
+            n_warmup = it + 1 + kOmegaWarmup;
+            continue;
+        }
+        if (it < n_warmup || !(err < err_prev)) {
+            if (row) v = fmax(1e-280, fmin(1e280, v / c));   // Sinkhorn column step
+            err_prev = (it < n_warmup) ? INFINITY : err;
+            continue;
+        }
+        err_prev = err;
+#ifdef MRGP_OMEGA_PROF
+        const long long pc0 = clock64();
+#endif
+        // ---- Newton matrix: lane j builds row j of diag(c) - P^T P + 1/M from its column Q and the transposed table
+        double H[M];
+#pragma unroll
+        for (int k = 0; k < M; k += 2) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double2 *r0 = reinterpret_cast<const double2 *>(T + k * LD);
+            const double2 *r1 = reinterpret_cast<const double2 *>(T + (k + 1) * LD);
+#pragma unroll
+            for (int i = 0; i < M; i += 2) {
+                const double2 t0 = r0[i >> 1], t1 = r1[i >> 1];
+                a0 = fma(Q[i], t0.x, a0);
+                a1 = fma(Q[i + 1], t0.y, a1);
+                a2 = fma(Q[i], t1.x, a2);
+                a3 = fma(Q[i + 1], t1.y, a3);
+            }
+            H[k] = ((lane == k) ? c : 0.0) - (a0 + a1) + 1.0 / (double)M;
+            H[k + 1] = ((lane == k + 1) ? c : 0.0) - (a2 + a3) + 1.0 / (double)M;
+        }
+        // ---- Cholesky (right-looking, lane = row) fused with the forward substitution; the next pivot is formed
+        //      first in every step so that its reciprocal square root overlaps the rest of the rank-1 update
+#ifdef MRGP_OMEGA_PROF
+        const long long pc1 = clock64();
+#endif
+        double rhs = 1.0 - c, y = 0.0, dinv = 0.0;
+        double piv = __shfl_sync(0xffffffffu, H[0], 0);
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            const double di = rsqrt(piv);
+            H[k] *= di;                                               // l_ik for lanes i >= k (l_kk on lane k)
+            if (k + 1 < M) {
+                H[k + 1] = fma(-H[k], __shfl_sync(0xffffffffu, H[k], k + 1), H[k + 1]);
+                piv = __shfl_sync(0xffffffffu, H[k + 1], k + 1);
+            }
+            const double yk = __shfl_sync(0xffffffffu, rhs, k) * di;
+            if (lane == k) {
+                dinv = di;
+                y = yk;
+            }
+            if (lane > k) rhs = fma(-H[k], yk, rhs);
+#pragma unroll
+            for (int j = k + 2; j < M; ++j) H[j] = fma(-H[k], __shfl_sync(0xffffffffu, H[k], j), H[j]);
+        }
+#ifdef MRGP_OMEGA_PROF
+        const long long pc2 = clock64();
+#endif
+        // ---- L^T x = y with the transposed factor: lane i reads l_ki, k > i, from shared memory -------------------
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < M; ++k) T[k * LD + lane] = H[k];          // T[k][i] = l_ik (valid for i >= k)
+        __syncwarp();
+        {
+            const double2 *lt = reinterpret_cast<const double2 *>(T + (row ? lane : 0) * LD);
+#pragma unroll
+            for (int k = 0; k < M; k += 2) {
+                const double2 t = lt[k >> 1];
+                Q[k] = t.x;                                           // l_k,lane
+                Q[k + 1] = t.y;
+            }
+        }
+        double x = 0.0;
+#pragma unroll
+        for (int k = M - 1; k >= 0; --k) {
+            const double xk = __shfl_sync(0xffffffffu, y, k) * __shfl_sync(0xffffffffu, dinv, k);
+            if (lane == k) x = xk;
+            if (lane < k) y = fma(-Q[k], xk, y);
+        }
+        if (row) v = fmax(1e-280, fmin(1e280, v * exp(fmax(-30.0, fmin(30.0, x)))));
+#ifdef MRGP_OMEGA_PROF
+        if (lane == 0) {
+            const long long pc3 = clock64();
+            a.omegaK[64 * 64 + 32 + 0] = (double)(pc1 - pc0);
+            a.omegaK[64 * 64 + 32 + 1] = (double)(pc2 - pc1);
+            a.omegaK[64 * 64 + 32 + 2] = (double)(pc3 - pc2);
+        }
+#endif
+    }
+    ts_dbg(a.ts, a.layer, 2, true);
+    // last resort: plain Sinkhorn sweeps (see omega_solve_serial); on model tables the loop exits at its first test
+    for (int it = 0; it < kOmegaFallbackSweeps; ++it) {
+        const double err = W::eval(K, P, Q, v, c, T, row, lane);
+        if (err < kOmegaTol || !isfinite(err)) break;
+        ++iters;
+        if (row) v = fmax(1e-280, fmin(1e280, v / c));
+    }
+    if (row) {
+#pragma unroll
+        for (int k = 0; k < M; ++k) a.omega[lane * M + k] = P[k];
+        a.omegaEta[a.layer * 64 + lane] = log(v) - cshift;
+    }
+    if (lane == 0) {
+        a.omegaIters[a.layer] = (double)iters;
+        a.omegaWarm[a.layer] = 1.0;
+    }
+    ts_end(a.ts, a.layer * 4 + 3);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Multi-GPU exchange over peer memory (NVLink / NVSwitch).  Every rank keeps a small arena that
 // its peers have mapped (CUDA IPC).  One exchange = (1) the dense per-region sums of the local run partials are
@@ -1307,6 +1531,43 @@ __global__ void k_comm_signal(CommArgs c) {
     if ((int)threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + c.rank, s);
 }
 
+// Dense per-region sums of the local run partials into the arena, one block per region (threads = value x
+// run slice), and - by the block that finishes last - the publication of k_comm_signal.
+template <bool MAX>
+__global__ void __launch_bounds__(256) k_comm_sums_signal(CommArgs c, const int32_t *region_run, const double *part, int stride, int nv,
+                                                          double *out, unsigned int *counter) {
+    __shared__ double sm[256];
+    __shared__ int sLast;
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const int slices = 256 / stride > 0 ? 256 / stride : 1;
+    const int v = tid % stride, sl = tid / stride;
+    double acc = 0.0;
+    if (sl < slices && v < nv)
+        for (int q = region_run[r] + sl; q < region_run[r + 1]; q += slices) {
+            const double x = __ldcg(part + (size_t)q * stride + v);
+            acc = MAX ? fmax(acc, x) : acc + x;
+        }
+    sm[tid] = acc;
+    __syncthreads();
+    if (tid < stride) {
+        double t = sm[tid];
+        for (int k = 1; k < slices; ++k) t = MAX ? fmax(t, sm[k * stride + tid]) : t + sm[k * stride + tid];
+        out[(size_t)r * stride + tid] = t;      // padding columns are kept at zero
+    }
+    __syncthreads();
+    if (tid == 0) sLast = (atom_add_acq_rel_gpu(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!sLast) return;
+    if (tid == 0) {
+        *counter = 0u;
+        sm[0] = 0.0;
+        *c.seq = *c.seq + 1ull;
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (tid < c.world) st_release_sys(c.flags[tid] + c.rank, *c.seq);
+}
+
 constexpr unsigned long long kCommTimeoutNs = 4000000000ull;   // a lost peer must not hang the GPU
 
 // out[r][v] = sum (or max) over the ranks that own samples of region r of their arena entries.
@@ -1357,7 +1618,7 @@ template <int DY>
 __global__ void __launch_bounds__(kThreadsB) k_bias_noise(StreamArgs p) {
     int lpr = 32;
     while (lpr > 1 && (kThreadsB / lpr) < p.R) lpr >>= 1;
-    bias_noise_all<DY, kThreadsB>(p, lpr);
+    bias_noise_all<DY, kThreadsB>(p, lpr, blockIdx.x, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------

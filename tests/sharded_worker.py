@@ -17,6 +17,7 @@ import workloads
 from oracle import mrgp_oracle as O
 from cimrgp_b200.distributed import ShardedEngine
 from cimrgp_b200.engine import Engine
+from parity import compare
 
 rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
 mode = sys.argv[1]
@@ -34,7 +35,12 @@ ref = Engine(xs, y, offsets, M, mode=mode, device=0)
 ref.sweep(3)
 ref.synchronize()
 a, b = e.state(), ref.state(latent=False)
-worst = max(float(np.max(np.abs(a[k] - b[k]) / (np.abs(b[k]) + 1e-12 * np.abs(b[k]).max() + 1e-300))) for k in b)
+try:
+    compare(a, b, rtol=1e-9)       # the comparison rule of all parity tests (tests/parity.py)
+    worst = 0.0
+except AssertionError as ex:
+    print('rank %d: %s' % (rank, str(ex)[:1500]), flush=True)
+    worst = 1.0
 # replicated state must be bit-identical on every rank: compare a digest
 digest = float(sum(np.sum(a[k]) for k in sorted(a)))
 out = [None] * world

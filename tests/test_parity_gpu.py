@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import mrgp_oracle as O
-from parity import assert_state_close, mismatch
+from parity import ATOL_ABS, assert_state_close, compare, mask_degenerate, mismatch
 import workloads
 
 pytestmark = pytest.mark.gpu
@@ -32,38 +32,6 @@ def build(x, y, m, resolution, fi, basis_interval_obj=None, **kw):
         basis_function_obj=LaplacianEigenpairs(), spectral_density_obj=MaternKernel(nu=1, l=1, sf=1),
         adaptive_inputs=False, standard_normalized_inputs=True, basis_interval_obj=basis_interval_obj, interval_factor=1,
         forced_independence=fi, **kw)
-
-
-# sum_n phi^2 is pure roundoff (|sin(i pi)|^2 ~ 1e-32) for one-sample regions whose point sits on the
-# interval edge; both sides are "zero" at the scale of phi^2 <= 1/L
-ATOL_ABS = {'d': 1e-20}
-
-
-def mask_degenerate(state, ref):
-    """Regions whose samples all sit on the edge of the basis interval (x = +-L, e.g. one-sample regions:
-    L = |x|, BasisInterval.py:15-16) have phi == 0 in exact arithmetic: y_tilde, A and the fi-mode B /
-    kappa of such a region are pure roundoff in the reference itself.  They are excluded."""
-    state, ref = dict(state), dict(ref)
-    for key in [k for k in ref if k.endswith('.d')]:
-        layer = key[:-2]
-        dead = np.max(ref[key], axis=1) < 1e-20
-        if not np.any(dead):
-            continue
-        for name in ('ytil', 'A', 'B', 'kappa'):
-            k2 = layer + '.' + name
-            if k2 in ref and ref[k2].shape[0] == dead.shape[0]:
-                for d in (state, ref):
-                    d[k2] = np.array(d[k2])
-                    d[k2][dead] = 0.0
-    return state, ref
-
-
-def compare(state, ref, rtol=RTOL):
-    state, ref = mask_degenerate(state, ref)
-    assert_state_close(state, ref, rtol, skip=('kappa',), atol_abs=ATOL_ABS)
-    for key in ref:
-        if key.endswith('kappa'):
-            assert mismatch(state[key], ref[key], rtol, atol_scale=1e-12) is None, key
 
 
 CASES = [('c1_ci', False, {}), ('c1_fi', True, {}), ('n2000_ci', False, {}), ('n2000_fi', True, {}),
