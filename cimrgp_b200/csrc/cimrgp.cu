@@ -99,6 +99,7 @@ struct mrgp_handle {
     int64_t launches = 0, launches_per_sweep = 0, sweeps_done = 0;
     bool capturing = false;
     bool timeline = false;
+    bool inferred_shortcut = true;   // skip phase A where Phi^T r == 0 identically (MRGP_STREAM_ALL=1: stream everything)
     bool omega_warp = true;   // single-warp register-resident omega solve for M <= 32 (MRGP_OMEGA_BLOCK=1: block version)
     // peer-memory exchange (multi-GPU): arena + flags in one cudaMalloc'ed block that the peers map through CUDA IPC
     struct Comm {
@@ -476,6 +477,7 @@ RegionArgs region_args(mrgp_handle *h, int j) {
     a.sf = d.sf;
     a.interval_factor = 1.0;
     a.L_given = 0;
+    a.zero_T = 0;
     return a;
 }
 
@@ -600,12 +602,12 @@ int max_region_runs(const LayerPlan &lp) {
     return m;
 }
 
-int do_mid_ci(mrgp_handle *h, int j, bool fork_omega);
+int do_mid_ci(mrgp_handle *h, int j, bool fork_omega, bool zero_T = false);
 
-int do_axis_update(mrgp_handle *h, int j, bool fork_omega) {
+int do_axis_update(mrgp_handle *h, int j, bool fork_omega, bool zero_T = false) {
     const bool fi = h->cfg.mode == MRGP_MODE_FI;
     const int M = h->cfg.n_basis, DY = h->cfg.dy;
-    if (!fi) return do_mid_ci(h, j, fork_omega);
+    if (!fi) return do_mid_ci(h, j, fork_omega, zero_T);
     RegionArgs a = region_args(h, j);
     const LayerPlan &lp = h->plan[j];
     {
@@ -621,9 +623,10 @@ int do_axis_update(mrgp_handle *h, int j, bool fork_omega) {
     return MRGP_OK;
 }
 
-int do_mid_ci(mrgp_handle *h, int j, bool fork_omega) {
+int do_mid_ci(mrgp_handle *h, int j, bool fork_omega, bool zero_T) {
     const int M = h->cfg.n_basis;
     RegionArgs a = region_args(h, j);
+    a.zero_T = zero_T ? 1 : 0;
     const LayerPlan &lp = h->plan[j];
     if (fork_omega && j > 0) CK(cudaStreamWaitEvent(h->stream, h->ev_ard[j - 1], 0));   // k_mid1 reads ard_mean
     int n_partials = 1;
@@ -715,18 +718,18 @@ int do_exchange(mrgp_handle *h, int j, int slot, int nv, bool is_max) {
     const LayerPlan &lp = h->plan[j];
     LayerDev &d = h->dev[j];
     const int total = lp.R * h->part_stride;
-    const size_t off = (size_t)slot * h->comm.slot_doubles;
+    (void)slot;   // the arena slot follows the exchange number on the device (k_comm_sums_signal)
     if (h->part_stride > 256) return fail(h, MRGP_EINVAL, "exchange rows of more than 256 values are not supported");
     if (is_max)
-        k_comm_sums_signal<true><<<lp.R, 256, 0, h->stream>>>(h->comm.args, d.region_run, h->part, h->part_stride, nv, h->comm.arena + off, h->comm.counter);
+        k_comm_sums_signal<true><<<lp.R, 256, 0, h->stream>>>(h->comm.args, d.region_run, h->part, h->part_stride, nv, h->comm.arena, h->comm.counter);
     else
-        k_comm_sums_signal<false><<<lp.R, 256, 0, h->stream>>>(h->comm.args, d.region_run, h->part, h->part_stride, nv, h->comm.arena + off, h->comm.counter);
+        k_comm_sums_signal<false><<<lp.R, 256, 0, h->stream>>>(h->comm.args, d.region_run, h->part, h->part_stride, nv, h->comm.arena, h->comm.counter);
     CK(cudaGetLastError());
     const int grid = std::max(1, std::min(96, (total + 255) / 256));
     if (is_max)
-        k_comm_reduce<true><<<grid, 256, 0, h->stream>>>(h->comm.args, off, d.offsets, lp.R, h->part_stride, nv, h->xchg);
+        k_comm_reduce<true><<<grid, 256, 0, h->stream>>>(h->comm.args, d.offsets, lp.R, h->part_stride, nv, h->xchg);
     else
-        k_comm_reduce<false><<<grid, 256, 0, h->stream>>>(h->comm.args, off, d.offsets, lp.R, h->part_stride, nv, h->xchg);
+        k_comm_reduce<false><<<grid, 256, 0, h->stream>>>(h->comm.args, d.offsets, lp.R, h->part_stride, nv, h->xchg);
     CK(cudaGetLastError());
     count(h, 2);
     return MRGP_OK;
@@ -810,17 +813,23 @@ int sweep_once(mrgp_handle *h, bool fork_omega) {
     const bool ci = h->cfg.mode == MRGP_MODE_CI;
     int rc;
     for (int j = 0; j < J; ++j) {
-        if ((rc = do_phase_a(h, j))) return rc;
+        // ci layers above the first regress on targets inferred from their own posterior, y = Phi A + b + fbar
+        // (LatentOutputs.py:20-49), so the residual of the P1 statistics, y - fbar - b - Phi A with the same A and b
+        // (Posteriors.py:61-78), vanishes identically: Phi^T r == 0 and y_tilde == d a.  The streaming pass that
+        // would add up those zeros (plus roundoff) is not launched; mrgp_phase_a still runs it on request and
+        // MRGP_STREAM_ALL=1 puts it back into the sweep.
+        const bool zero_T = ci && j > 0 && h->inferred_shortcut;
+        if (!zero_T && (rc = do_phase_a(h, j))) return rc;
         if (h->sharded) {
             // sample-sharded: the region statistics of both streaming phases are summed over the ranks
-            if ((rc = do_exchange(h, j, 0, h->cfg.n_basis * h->cfg.dy, false))) return rc;
-            if ((rc = do_axis_update(h, j, fork_omega && ci))) return rc;
+            if (!zero_T && (rc = do_exchange(h, j, 0, h->cfg.n_basis * h->cfg.dy, false))) return rc;
+            if ((rc = do_axis_update(h, j, fork_omega && ci, zero_T))) return rc;
             if ((rc = do_phase_b(h, j, false))) return rc;
             if ((rc = do_exchange(h, j, 1, h->cfg.dy + 3, false))) return rc;
             if ((rc = do_bias_noise(h, j))) return rc;
             continue;
         }
-        if ((rc = do_axis_update(h, j, fork_omega && ci))) return rc;
+        if ((rc = do_axis_update(h, j, fork_omega && ci, zero_T))) return rc;
         if (h->dev[j].adaptive && ci) {
             // the latent functions of the next layer use the re-learnt basis (MRGP.py:632-649): statistics first,
             // then the interval search, then a second pass that only propagates
@@ -969,6 +978,7 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     h = new mrgp_handle();
     h->cfg = *cfg;
     if (const char *e = getenv("MRGP_OMEGA_BLOCK")) h->omega_warp = !(e[0] == '1');
+    if (const char *e = getenv("MRGP_STREAM_ALL")) h->inferred_shortcut = !(e[0] == '1');
     h->sharded = cfg->sample_end > cfg->sample_begin;   // an explicit range selects the exchange-buffer path
     h->lo = h->sharded ? cfg->sample_begin : 0;
     h->hi = h->sharded ? cfg->sample_end : cfg->n_samples;
@@ -1464,7 +1474,7 @@ int mrgp_comm_export(mrgp_handle *h, void *blob_out) {
         int rmax = 0;
         for (auto &lp : h->plan) rmax = std::max(rmax, lp.R);
         c.slot_doubles = ((size_t)rmax * h->part_stride + 31) & ~(size_t)31;
-        c.bytes = 512 + 2 * c.slot_doubles * sizeof(double);
+        c.bytes = 512 + kCommSlots * c.slot_doubles * sizeof(double);
         CK(cudaSetDevice(h->cfg.device));
         CK(cudaMalloc(&c.mem, c.bytes));
         CK(cudaMemset(c.mem, 0, c.bytes));
@@ -1503,6 +1513,7 @@ int mrgp_comm_bind(mrgp_handle *h, int32_t rank, int32_t world, const void *blob
     a.world = world;
     a.seq = c.seq;
     a.err = c.err;
+    a.slot_doubles = c.slot_doubles;
     for (int q = 0; q <= world; ++q) a.bounds[q] = bounds[q];
     for (int q = 0; q < world; ++q) {
         CommBlob b;

@@ -731,6 +731,7 @@ struct RegionArgs {
     int32_t use_prior;
     double nu, ell, sf, interval_factor;
     int32_t L_given;
+    int32_t zero_T;   // 1: Phi^T r is identically zero (inferred targets, see sweep_once): y_tilde = d a
 };
 
 // K3 + K2: L = factor max|x| (BasisInterval.py:15-16), 1/(2L), L^-1/2, lambda (KernelClass.py:36),
@@ -892,7 +893,7 @@ __global__ void __launch_bounds__(kMidThreads) k_mid1(RegionArgs a, int lpi, int
             const bool valid = it < nitems;
             const int l = cb + (valid ? it / M : 0), i = valid ? it % M : 0;
             double t0 = 0.0, t1 = 0.0;
-            if (valid)
+            if (valid && !a.zero_T)
                 for (int q = a.region_run[l] + sl; q < a.region_run[l + 1]; q += lpi) {
                     const double2 v = *reinterpret_cast<const double2 *>(a.part + (size_t)q * a.part_stride + i * 2);
                     t0 += v.x;
@@ -1485,11 +1486,13 @@ __global__ void __launch_bounds__(32, 1) k_scale_warp(RegionArgs a) {
 // written into the local arena, (2) the rank stores the next sequence number into its slot of every peer's flag
 // array (st.release.sys), (3) a reduce kernel waits until every peer's number has arrived and sums, per region,
 // the arenas of exactly the ranks whose sample chunk overlaps the region, in rank order - every rank forms the
-// same sum in the same order, so the replicated small-matrix state stays bit-identical across ranks.  Two arena
-// slots (phase A / phase B) are enough: a rank can only overwrite a slot after it has waited for a later signal
-// of every peer, which each peer sends after its own read of that slot (stream order).
+// same sum in the same order, so the replicated small-matrix state stays bit-identical across ranks.  The arena
+// has three slots used round-robin by exchange number: when a rank writes exchange e it has waited for every
+// peer's signal e - 1, which a peer sends after it finished reading exchange e - 2 (stream order), so only the
+// slots of e - 1 and e can be in use by a peer - never slot (e mod 3) of exchange e - 3.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxRanks = 16;
+constexpr int kCommSlots = 3;
 
 struct CommArgs {
     int32_t rank, world;
@@ -1497,6 +1500,7 @@ struct CommArgs {
     unsigned long long *flags[kMaxRanks];      // flags[p][src]: last sequence number rank src has published to rank p
     unsigned long long *seq;                   // local: sequence number of the last exchange
     unsigned int *err;                         // local: set when a wait timed out
+    unsigned long long slot_doubles;           // arena slot e mod kCommSlots starts at (e mod kCommSlots) * slot_doubles
     int64_t bounds[kMaxRanks + 1];             // rank q owns the samples [bounds[q], bounds[q + 1])
 };
 
@@ -1539,6 +1543,7 @@ __global__ void __launch_bounds__(256) k_comm_sums_signal(CommArgs c, const int3
     __shared__ double sm[256];
     __shared__ int sLast;
     const int r = blockIdx.x, tid = threadIdx.x;
+    out += ((*c.seq + 1ull) % kCommSlots) * c.slot_doubles;   // the exchange this kernel publishes
     const int slices = 256 / stride > 0 ? 256 / stride : 1;
     const int v = tid % stride, sl = tid / stride;
     double acc = 0.0;
@@ -1572,7 +1577,7 @@ constexpr unsigned long long kCommTimeoutNs = 4000000000ull;   // a lost peer mu
 
 // out[r][v] = sum (or max) over the ranks that own samples of region r of their arena entries.
 template <bool MAX>
-__global__ void __launch_bounds__(256) k_comm_reduce(CommArgs c, size_t slot_offset, const int64_t *offsets, int R, int stride, int nv,
+__global__ void __launch_bounds__(256) k_comm_reduce(CommArgs c, const int64_t *offsets, int R, int stride, int nv,
                                                      double *out) {
     __shared__ int ok;
     if (threadIdx.x < 32) {
@@ -1595,6 +1600,7 @@ __global__ void __launch_bounds__(256) k_comm_reduce(CommArgs c, size_t slot_off
     }
     __syncthreads();
     if (!ok) return;
+    const size_t slot_offset = (size_t)((*c.seq % kCommSlots) * c.slot_doubles);
     const int total = R * stride;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const int r = t / stride, v = t - r * stride;

@@ -164,6 +164,27 @@ def test_graph_replay_equals_stepwise_phases_and_is_deterministic():
         assert np.array_equal(sa[k], sb[k]), k          # graph replay == per-phase ABI calls
 
 
+def test_skipped_statistics_pass_of_inferred_layers_is_an_identity():
+    """The sweep does not launch the P1 statistics pass on ci layers above the first, whose targets are inferred
+    from the layer's own posterior (Phi^T r == 0, y_tilde == d a).  The per-phase ABI still streams it.  On a state
+    whose upper layers are NOT inert (coefficients and biases set by hand) both forms must agree to roundoff."""
+    from cimrgp_b200 import _lib
+    x, y = workloads.workload1(40000)
+    models = [build(x, y, 30, 5, False) for _ in range(2)]
+    rng = np.random.RandomState(3)
+    pert = [(0.05 * rng.standard_normal((2 ** j, 30, 2)), 0.3 * rng.standard_normal((2 ** j, 2))) for j in range(6)]
+    for m in models:
+        m.fit(2, None)
+        for j in range(1, 6):
+            m._engine.put(j, _lib.F_A, pert[j][0])
+            m._engine.put(j, _lib.F_BIAS_MEAN, pert[j][1])
+    models[0]._engine.sweep(1)              # captured sweep: no statistics pass on layers 1..5
+    models[1]._engine.sweep_stepwise()      # per-phase calls: every layer streams both passes
+    sa, sb = models[0]._engine.state(), models[1]._engine.state()
+    assert np.max(np.abs(sb['L3.ytil'])) > 1e-3          # the upper layers really carry signal here
+    compare(sa, sb, rtol=1e-9)
+
+
 def test_results_do_not_depend_on_grid_size():
     x, y = workloads.workload1(30000)
     a = build(x, y, 30, 6, True, n_ctas=148)
