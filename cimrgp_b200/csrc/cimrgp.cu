@@ -24,6 +24,9 @@ std::string g_create_error;
 
 struct LayerPlan {
     std::vector<int64_t> offsets;     // R + 1
+    // pieces region x coarser region (closed-form statistics): CSR over (coarser layer, region)
+    std::vector<int32_t> pc_ptr, pc_jp, pc_anc;
+    std::vector<int64_t> pc_lo, pc_hi;
     std::vector<Segment> segs;
     std::vector<int32_t> cta_seg;     // n_ctas + 1
     std::vector<int32_t> seg_cta;     // per segment (host only)
@@ -56,13 +59,18 @@ struct LayerDev {
     int32_t use_prior = 1;
     double nu = 1.0, ell = 1.0, sf = 1.0;
     bool basis_built = false;
+    // invariants of the closed-form statistics (ci layers above the first): s (R, M), G (R, M, M), D (layer, R, M)
+    double *sumPhi = nullptr, *gram = nullptr, *ancD = nullptr;
+    int32_t *pc_ptr = nullptr, *pc_jp = nullptr, *pc_anc = nullptr;
+    int64_t *pc_lo = nullptr, *pc_hi = nullptr;
+    bool inv_built = false;
 };
 
 struct SharedDev {
     double *axB = nullptr, *axKappa = nullptr, *axRho = nullptr, *axLogC = nullptr, *axCov = nullptr;
     double *ardShape = nullptr, *ardScale = nullptr, *ardMean = nullptr, *ardLogMean = nullptr;
     double *omega = nullptr, *logOmegaHat = nullptr, *omegaIters = nullptr, *ardPartial = nullptr, *omegaEta = nullptr, *omegaWarm = nullptr, *omegaK = nullptr;
-    double *primeB = nullptr, *primeLogC = nullptr, *primeShape = nullptr, *primeScale = nullptr;
+    double *primeB = nullptr, *primeLogC = nullptr, *primeShape = nullptr, *primeScale = nullptr, *primeSk = nullptr;
     double *priorB = nullptr, *priorLogC = nullptr, *priorShape = nullptr, *priorScale = nullptr;
 };
 
@@ -94,11 +102,15 @@ struct mrgp_handle {
     cudaStream_t stream = nullptr, side = nullptr;
     bool own_stream = false;
     std::vector<cudaEvent_t> ev_fork, ev_join, ev_ard;
+    cudaEvent_t ev_prefetch = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     int64_t launches = 0, launches_per_sweep = 0, sweeps_done = 0;
     bool capturing = false;
     bool timeline = false;
+    size_t state_begin = 0, state_end = 0;
+    double *build_part = nullptr;    // split partials of the invariant builds
+    size_t build_part_doubles = 0;
     bool inferred_shortcut = true;   // skip phase A where Phi^T r == 0 identically (MRGP_STREAM_ALL=1: stream everything)
     bool omega_warp = true;   // single-warp register-resident omega solve for M <= 32 (MRGP_OMEGA_BLOCK=1: block version)
     // peer-memory exchange (multi-GPU): arena + flags in one cudaMalloc'ed block that the peers map through CUDA IPC
@@ -223,6 +235,9 @@ struct Carver {
     }
 };
 
+// Blocks per region of the invariant builds: about two waves of the SMs per layer.
+int build_splits(int R) { return std::max(1, (296 + R - 1) / R); }
+
 size_t carve(mrgp_handle *h, char *base) {
     Carver c(base);
     const int64_t N = h->hi - h->lo;   // local samples
@@ -243,6 +258,17 @@ size_t carve(mrgp_handle *h, char *base) {
         for (int j = 0; j < J; ++j) rmax = std::max(rmax, h->plan[j].R);
         h->xchg = c.take<double>((size_t)rmax * h->part_stride);
     }
+    if (!fi && !h->sharded && J > 1) {   // closed-form statistics of the layers above the first
+        const size_t np = (size_t)M * (M + 1) / 2 + M;
+        size_t need = 0;
+        for (int j = 1; j < J; ++j) {
+            const size_t blocks = (size_t)h->plan[j].R * build_splits(h->plan[j].R);
+            const size_t P = h->plan[j].pc_jp.size();
+            need = std::max(need, std::max(blocks * np, P * build_splits((int)P) * M));
+        }
+        h->build_part_doubles = need;
+        h->build_part = c.take<double>(need);
+    }
     h->elbo_out = c.take<double>((size_t)J * 6);
     h->elbo_args = c.take<RegionArgs>(J);
     h->off_total = 0;
@@ -253,6 +279,7 @@ size_t carve(mrgp_handle *h, char *base) {
     h->brent_fail = c.take<unsigned long long>(1);
     h->mid_sync = c.take<unsigned int>(2 * kMaxLayers);
     h->ts = c.take<unsigned long long>(kMaxLayers * 8);
+    h->state_begin = c.off;   // everything from here to state_end is the small-matrix state (L2 prefetch range)
     for (int j = 0; j < J; ++j) {
         const LayerPlan &lp = h->plan[j];
         LayerDev &d = h->dev[j];
@@ -269,6 +296,16 @@ size_t carve(mrgp_handle *h, char *base) {
         d.S = c.take<double>(RM);
         d.d = c.take<double>(RM);
         d.absx = c.take<double>(R);
+        if (!fi && !h->sharded && j > 0) {
+            const size_t P = lp.pc_jp.size();
+            d.sumPhi = c.take<double>(RM);
+            d.ancD = c.take<double>(P * M);
+            d.pc_ptr = c.take<int32_t>(lp.pc_ptr.size());
+            d.pc_jp = c.take<int32_t>(P);
+            d.pc_anc = c.take<int32_t>(P);
+            d.pc_lo = c.take<int64_t>(P);
+            d.pc_hi = c.take<int64_t>(P);
+        }
         d.bias_prev = c.take<double>(R * DY);
         d.brent = c.take<double>(R * BrentState::NFIELDS);
         d.trial_inv2L = c.take<double>(R);
@@ -328,10 +365,14 @@ size_t carve(mrgp_handle *h, char *base) {
     s.primeLogC = c.take<double>(M);
     s.primeShape = c.take<double>(M);
     s.primeScale = c.take<double>(M);
+    s.primeSk = c.take<double>(M);
     s.priorB = c.take<double>((size_t)M * DY * DY);
     s.priorLogC = c.take<double>(M);
     s.priorShape = c.take<double>(M);
     s.priorScale = c.take<double>(M);
+    h->state_end = c.off;
+    if (!fi && !h->sharded)
+        for (int j = 1; j < J; ++j) h->dev[j].gram = c.take<double>((size_t)h->plan[j].R * M * M);   // read only when dA != 0
     return (c.off + 255) & ~(size_t)255;
 }
 
@@ -459,6 +500,7 @@ RegionArgs region_args(mrgp_handle *h, int j) {
     a.primeLogC = s.primeLogC;
     a.primeShape = s.primeShape;
     a.primeScale = s.primeScale;
+    a.primeSk = s.primeSk;
     a.priorB = s.priorB;
     a.priorLogC = s.priorLogC;
     a.priorShape = s.priorShape;
@@ -808,10 +850,90 @@ int do_learn_intervals(mrgp_handle *h, int j) {
     return MRGP_OK;
 }
 
+int fill_eval_layers(mrgp_handle *h, EvalArgs &ea, int n_layers, const int64_t *const *dev_offsets);
+
+// ci, static intervals, nested regions, one GPU: the layers above the first take their P4 / P5 statistics in closed
+// form (k_stats_b) instead of streaming the samples.
+bool use_closed_form(const mrgp_handle *h) {
+    if (h->cfg.mode != MRGP_MODE_CI || h->sharded || !h->inferred_shortcut || !h->build_part) return false;
+    for (const auto &d : h->dev)
+        if (d.adaptive) return false;
+    return h->cfg.n_layers > 1;
+}
+
+template <int M>
+int launch_build_invariants(mrgp_handle *h, int j) {
+    LayerDev &d = h->dev[j];
+    const LayerPlan &lp = h->plan[j];
+    const int splits = build_splits(lp.R), blocks = lp.R * splits;
+    constexpr int NP = M * (M + 1) / 2;
+    CK(cudaFuncSetAttribute(k_build_gram<M>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    k_build_gram<M><<<blocks, 256, 0, h->stream>>>(h->x, d.offsets, d.inv2L, d.rsqrtL, splits, h->build_part);
+    CK(cudaGetLastError());
+    k_reduce_gram<<<(lp.R * (NP + M) + 255) / 256, 256, 0, h->stream>>>(h->build_part, splits, lp.R, M, d.gram, d.sumPhi);
+    CK(cudaGetLastError());
+    EvalArgs ea{};
+    int rc = fill_eval_layers(h, ea, j, nullptr);
+    if (rc) return rc;
+    const int P = (int)lp.pc_jp.size(), psplits = build_splits(P);
+    const PieceTable pt{d.pc_ptr, d.pc_jp, d.pc_anc, d.pc_lo, d.pc_hi, P};
+    k_build_ancD<M><<<P * psplits, 256, 0, h->stream>>>(ea, h->x, pt, psplits, h->build_part);
+    CK(cudaGetLastError());
+    k_reduce_ancD<<<(P * M + 255) / 256, 256, 0, h->stream>>>(h->build_part, psplits, P, M, d.ancD);
+    CK(cudaGetLastError());
+    count(h, 4);
+    d.inv_built = true;
+    return MRGP_OK;
+}
+
+int build_invariants(mrgp_handle *h) {
+    if (!use_closed_form(h)) return MRGP_OK;
+    for (int j = 1; j < h->cfg.n_layers; ++j) {
+        if (h->dev[j].inv_built) continue;
+        int rc = MRGP_EINVAL;
+        DISPATCH_M(h->cfg.n_basis, rc = launch_build_invariants<MM>(h, j));
+        if (rc) return rc;
+    }
+    return MRGP_OK;
+}
+
+int do_stats_b(mrgp_handle *h, int j) {
+    LayerDev &d = h->dev[j];
+    StatsBArgs q{};
+    q.p = stream_args(h, j);
+    q.p.infer = 1;
+    int rc = fill_eval_layers(h, q.anc, j, nullptr);
+    if (rc) return rc;
+    q.s = d.sumPhi;
+    q.G = d.gram;
+    q.D = d.ancD;
+    q.pt = PieceTable{d.pc_ptr, d.pc_jp, d.pc_anc, d.pc_lo, d.pc_hi, (int32_t)h->plan[j].pc_jp.size()};
+    q.A = d.A;
+    q.A_prev = d.A_prev;
+    q.d = d.d;
+    q.cm2 = d.cm2;
+    CK(cudaFuncSetAttribute(k_stats_b<2>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    k_stats_b<2><<<(h->plan[j].R + 7) / 8, 256, 0, h->stream>>>(q);
+    CK(cudaGetLastError());
+    count(h);
+    return MRGP_OK;
+}
+
 int sweep_once(mrgp_handle *h, bool fork_omega) {
     const int J = h->cfg.n_layers;
     const bool ci = h->cfg.mode == MRGP_MODE_CI;
+    const bool closed = use_closed_form(h);
     int rc;
+    if (fork_omega && ci && h->state_end > h->state_begin) {
+        // the small-matrix state (a few MB) is pulled into L2 by the side stream while layer 0 streams the samples:
+        // the short kernels that follow are chains of dependent loads and would otherwise each pay HBM latency
+        CK(cudaEventRecord(h->ev_prefetch, h->stream));
+        CK(cudaStreamWaitEvent(h->side, h->ev_prefetch, 0));
+        const size_t lines = (h->state_end - h->state_begin + 127) / 128;
+        k_prefetch_l2<<<(unsigned)std::min<size_t>((lines + 255) / 256, 1024), 256, 0, h->side>>>(h->ws + h->state_begin, lines);
+        CK(cudaGetLastError());
+        count(h);
+    }
     for (int j = 0; j < J; ++j) {
         // ci layers above the first regress on targets inferred from their own posterior, y = Phi A + b + fbar
         // (LatentOutputs.py:20-49), so the residual of the P1 statistics, y - fbar - b - Phi A with the same A and b
@@ -836,8 +958,12 @@ int sweep_once(mrgp_handle *h, bool fork_omega) {
             if ((rc = do_phase_b(h, j, true, 0))) return rc;
             if ((rc = do_learn_intervals(h, j))) return rc;
             if (j + 1 < J && (rc = do_phase_b(h, j, false, 1))) return rc;
+        } else if (closed && j > 0) {
+            if ((rc = do_stats_b(h, j))) return rc;         // inferred targets: statistics from the basis invariants
         } else {
-            if ((rc = do_phase_b(h, j, true))) return rc;   // bias / noise update fused into the kernel tail
+            // bias / noise update fused into the kernel tail; nothing reads the latent buffers when the layers below
+            // take the closed form
+            if ((rc = do_phase_b(h, j, true, closed ? 0 : -1))) return rc;
         }
     }
     if (fork_omega && ci) {
@@ -1021,6 +1147,27 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     h->cta_quantum = q;
     h->n_ctas = (int)((n_local + q - 1) / q);
     build_plan(h);
+    if (cfg->mode == MRGP_MODE_CI && !h->sharded)
+        for (int j = 1; j < cfg->n_layers; ++j) {
+            LayerPlan &lp = h->plan[j];
+            lp.pc_ptr.assign((size_t)j * (lp.R + 1), 0);
+            for (int jp = 0; jp < j; ++jp) {
+                const auto &po = h->plan[jp].offsets;
+                size_t a = 0;
+                for (int c = 0; c < lp.R; ++c) {
+                    lp.pc_ptr[(size_t)jp * (lp.R + 1) + c] = (int32_t)lp.pc_jp.size();
+                    const int64_t lo = lp.offsets[c], hi = lp.offsets[c + 1];
+                    while (po[a + 1] <= lo) ++a;
+                    for (size_t q = a; q + 1 < po.size() && po[q] < hi; ++q) {
+                        lp.pc_jp.push_back(jp);
+                        lp.pc_anc.push_back((int32_t)q);
+                        lp.pc_lo.push_back(std::max(lo, po[q]));
+                        lp.pc_hi.push_back(std::min(hi, po[q + 1]));
+                    }
+                }
+                lp.pc_ptr[(size_t)jp * (lp.R + 1) + lp.R] = (int32_t)lp.pc_jp.size();
+            }
+        }
     h->ws_bytes = carve(h, nullptr);
     *out = h;
     return MRGP_OK;
@@ -1032,6 +1179,7 @@ void mrgp_destroy(mrgp_handle *h) {
     for (auto e : h->ev_fork) cudaEventDestroy(e);
     for (auto e : h->ev_join) cudaEventDestroy(e);
     for (auto e : h->ev_ard) cudaEventDestroy(e);
+    if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
     for (int q = 0; q < kMaxRanks; ++q)
         if (h->comm.opened[q]) cudaIpcCloseMemHandle(h->comm.peer_base[q]);
     if (h->comm.mem) cudaFree(h->comm.mem);
@@ -1060,6 +1208,7 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
         h->own_stream = true;
     }
     if (!h->side) CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    if (!h->ev_prefetch) CK(cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
     if (h->ev_fork.empty()) {
         h->ev_fork.resize(h->cfg.n_layers);
         h->ev_join.resize(h->cfg.n_layers);
@@ -1082,6 +1231,14 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
         CK(cudaMemcpyAsync(d.region_run, lp.region_run.data(), lp.region_run.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(d.ident_run, lp.ident_run.data(), lp.ident_run.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(d.offsets, lp.offsets.data(), lp.offsets.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+        if (d.pc_ptr) {
+            const size_t P = lp.pc_jp.size();
+            CK(cudaMemcpyAsync(d.pc_ptr, lp.pc_ptr.data(), lp.pc_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(d.pc_jp, lp.pc_jp.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(d.pc_anc, lp.pc_anc.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(d.pc_lo, lp.pc_lo.data(), P * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(d.pc_hi, lp.pc_hi.data(), P * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+        }
     }
     CK(cudaMemsetAsync(h->chol_count, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->done_counter, 0, sizeof(unsigned int), h->stream));
@@ -1177,6 +1334,8 @@ int mrgp_build_basis(mrgp_handle *h, int32_t layer, double interval_factor, cons
     CK(cudaGetLastError());
     count(h);
     d.basis_built = true;
+    for (int jj = layer; jj < h->cfg.n_layers; ++jj) h->dev[jj].inv_built = false;   // s, G of the layer; D of the finer ones
+    drop_graph(h);
     return MRGP_OK;
 }
 
@@ -1309,6 +1468,7 @@ int mrgp_set_adaptive_intervals(mrgp_handle *h, int32_t layer, int32_t enabled, 
         if (enabled && use_prior && !d.use_prior)
             return fail(h, MRGP_EINVAL, "use_prior needs a spectral density on the layer (BasisInterval.py:121)");
         d.adaptive = enabled != 0;
+        for (auto &dd : h->dev) dd.inv_built = false;
         d.ad_use_prior = use_prior;
         d.ad_lo = factor_lo;
         d.ad_hi = factor_hi;
@@ -1341,6 +1501,7 @@ int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
     if (h->sharded && !h->comm.ready)
         return fail(h, MRGP_ESTATE, "mrgp_sweep on a sharded handle needs the peer exchange (mrgp_comm_bind); without it drive the phases and the all-reduces from the host");
     if (!h->graph_exec) {
+        if ((rc = build_invariants(h))) return rc;
         h->launches_per_sweep = 0;
         h->capturing = true;
         cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);

@@ -720,7 +720,7 @@ struct RegionArgs {
     double *bias_prec, *bias_prec0, *bias_mean, *bias_mean0, *bias_var, *yvar, *sumsB;
     // shared (ci) or per-region (fi) axis / ARD
     double *axB, *axKappa, *axRho, *axLogC, *axCov, *ardShape, *ardScale, *ardMean, *ardLogMean;
-    double *omega, *logOmegaHat, *omegaIters, *ardPartial, *omegaEta, *omegaWarm, *omegaK;
+    double *omega, *logOmegaHat, *omegaIters, *ardPartial, *omegaEta, *omegaWarm, *omegaK, *primeSk;
     double *primeB, *primeLogC, *primeShape, *primeScale;   // snapshot read by ARD / omega (ci)
     const double *priorB, *priorLogC, *priorShape, *priorScale;
     double *bcontrib;          // (R, M, 3) ci: 0.5 noise zeta ytil ytil^T
@@ -935,9 +935,13 @@ __global__ void __launch_bounds__(kMidThreads) k_mid1(RegionArgs a, int lpi, int
         const bool first = (a.layer == 0);
         for (int t = tid; t < M * 4; t += kMidThreads) a.primeB[t] = first ? a.priorB[t] : a.axB[t];
         for (int t = tid; t < M; t += kMidThreads) {
-            a.primeLogC[t] = first ? a.priorLogC[t] : a.axLogC[t];
-            a.primeShape[t] = first ? a.priorShape[t] : a.ardShape[t];
-            a.primeScale[t] = first ? a.priorScale[t] : a.ardScale[t];
+            const double lc = first ? a.priorLogC[t] : a.axLogC[t];
+            const double shp = first ? a.priorShape[t] : a.ardShape[t];
+            const double scp = first ? a.priorScale[t] : a.ardScale[t];
+            a.primeLogC[t] = lc;
+            a.primeShape[t] = shp;
+            a.primeScale[t] = scp;
+            a.primeSk[t] = -lc + shp * log(scp) - lgamma(shp);   // the terms of log omega_hat that depend on k only
         }
     }
     ts_end(a.ts, a.layer * 4 + 1);
@@ -1055,24 +1059,41 @@ __global__ void __launch_bounds__(kMidThreads) k_mid2(RegionArgs a, int regions_
 // (mrgp_math.cuh), one block of 256 threads, warp per matrix row / column.
 constexpr int kOmegaThreads = 256;
 
-__host__ __device__ inline size_t omega_smem_doubles(int M) { return (size_t)3 * M * M + 12 * M + 8; }
+__host__ __device__ inline size_t omega_smem_doubles(int M) { return (size_t)3 * M * M + 24 * M + 8; }
 
 __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_partials) {
     extern __shared__ double sm[];
-    const int M = a.M, tid = threadIdx.x;
-    double *P = sm, *s_mean = P + M * M, *s_lmean = s_mean + M, *s_k = s_lmean + M;
+    const int M = a.M, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kOmegaThreads / 32;
+    double *P = sm, *s_mean = P + M * M, *s_lmean = s_mean + M, *s_k = s_lmean + M, *s_shape = s_k + M, *s_scale = s_shape + M;
+    double *s_B = s_scale + M, *s_C = s_B + 4 * M, *s_part = s_C + 4 * M;   // s_part: NW x M
     ts_begin(a.ts, a.layer * 4 + 3);
+    // every input is staged in shared memory by one wave of loads
     for (int t = tid; t < M * M; t += kOmegaThreads) P[t] = a.omega[t];   // the OLD omega mixes the ARD prior
+    for (int t = tid; t < 4 * M; t += kOmegaThreads) {
+        s_B[t] = a.primeB[t];
+        s_C[t] = a.axCov[t];
+    }
+    for (int t = tid; t < M; t += kOmegaThreads) {
+        s_k[t] = a.primeSk[t];
+        s_shape[t] = a.primeShape[t];
+        s_scale[t] = a.primeScale[t];
+    }
+    for (int i = lane; i < M; i += 32) {   // sum_l m2 / S: the per-CTA partials of k_mid2, one slice of them per warp
+        double t = 0.0;
+        for (int q = warp; q < n_partials; q += NW) t += a.ardPartial[q * M + i];
+        s_part[warp * M + i] = t;
+    }
     __syncthreads();
     if (tid < M) {
         const int i = tid;
         double beta2 = 0.0;
-        for (int q = 0; q < n_partials; ++q) beta2 += a.ardPartial[q * M + i];
+        for (int w = 0; w < NW; ++w) beta2 += s_part[w * M + i];
         double sh = 0.0, sc = 0.0;
         for (int k = 0; k < M; ++k) {
             const double w = P[i * M + k];
-            sh += w * a.primeShape[k];
-            sc += w * a.primeScale[k];
+            sh += w * s_shape[k];
+            sc += w * s_scale[k];
         }
         const double shape = sh + 0.5 * (double)a.R;
         const double scale = sc + 0.5 * beta2;
@@ -1083,15 +1104,13 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
         a.ardLogMean[i] = lmean;
         s_mean[i] = mean;
         s_lmean[i] = lmean;
-        const double shp = a.primeShape[i], scp = a.primeScale[i];
-        s_k[i] = -a.primeLogC[i] + shp * log(scp) - lgamma(shp);   // the terms of log omega_hat that depend on k only
     }
     __syncthreads();
     for (int t = tid; t < M * M; t += kOmegaThreads) {
         const int i = t / M, k = t % M;
-        const double *C = a.axCov + i * 4, *B = a.primeB + k * 4;
+        const double *C = s_C + i * 4, *B = s_B + k * 4;
         const double tr = C[0] * B[0] + C[1] * B[2] + C[2] * B[1] + C[3] * B[3];   // trace(C_i B'_k)
-        const double lw = tr + s_k[k] + (a.primeShape[k] - 1.0) * s_lmean[i] - a.primeScale[k] * s_mean[i];
+        const double lw = tr + s_k[k] + (s_shape[k] - 1.0) * s_lmean[i] - s_scale[k] * s_mean[i];
         a.logOmegaHat[t] = lw;
         P[t] = lw;                      // the old omega is no longer needed
     }
@@ -1099,8 +1118,6 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
     // (one warp, k_scale_warp) starts from the table K = exp(lw - rowmax - colmax), stored column-major, and the
     // column shifts (row shifts cancel in the row normalisation).
     __syncthreads();
-    const int lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kOmegaThreads / 32;
     for (int i = warp; i < M; i += NW) {
         double mx = -INFINITY;
         for (int k = lane; k < M; k += 32) mx = fmax(mx, P[i * M + k]);
@@ -1154,7 +1171,7 @@ __global__ void __launch_bounds__(kOmegaThreads) k_scale(RegionArgs a) {
     __syncthreads();
     int iters = 0;
     double err_prev = INFINITY;
-    int n_warmup = warm ? 0 : kOmegaWarmup;
+    int last = kOmegaNone;
     for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
         ++iters;
         for (int i = warp; i < M; i += NW) {
@@ -1184,17 +1201,19 @@ __global__ void __launch_bounds__(kOmegaThreads) k_scale(RegionArgs a) {
         if (!isfinite(err)) {   // a bad (warm) start or an overshooting Newton step: start again from the shifts alone
             if (tid < M) v[tid] = 1.0;
             err_prev = INFINITY;
-            n_warmup = it + 1 + kOmegaWarmup;
+            last = kOmegaNone;
             __syncthreads();
             continue;
         }
-        if (it < n_warmup || !(err < err_prev)) {
+        if (!omega_take_newton(err, err_prev, last)) {
             if (tid < M) v[tid] = fmax(1e-280, fmin(1e280, v[tid] / c[tid]));   // Sinkhorn column step
-            err_prev = (it < n_warmup) ? INFINITY : err;
+            err_prev = err;
+            last = kOmegaSinkhorn;
             __syncthreads();
             continue;
         }
         err_prev = err;
+        last = kOmegaNewton;
         for (int k = warp; k < M; k += NW)
             for (int m = lane; m <= k; m += 32) {
                 double s0 = 0.0, s1 = 0.0;
@@ -1362,7 +1381,7 @@ __global__ void __launch_bounds__(32, 1) k_scale_warp(RegionArgs a) {
     }
     int iters = 0;
     double err_prev = INFINITY, c = 1.0;
-    int n_warmup = warm ? 0 : kOmegaWarmup;
+    int last = kOmegaNone;
     ts_dbg(a.ts, a.layer, 1, true);
     ts_dbg(a.ts, a.layer, 2, false);
     for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
@@ -1372,15 +1391,17 @@ __global__ void __launch_bounds__(32, 1) k_scale_warp(RegionArgs a) {
         if (!isfinite(err)) {   // a bad (warm) start or an overshooting Newton step: start again from the shifts alone
             v = 1.0;
             err_prev = INFINITY;
-            n_warmup = it + 1 + kOmegaWarmup;
+            last = kOmegaNone;
             continue;
         }
-        if (it < n_warmup || !(err < err_prev)) {
+        if (!omega_take_newton(err, err_prev, last)) {
             if (row) v = fmax(1e-280, fmin(1e280, v / c));   // Sinkhorn column step
-            err_prev = (it < n_warmup) ? INFINITY : err;
+            err_prev = err;
+            last = kOmegaSinkhorn;
             continue;
         }
         err_prev = err;
+        last = kOmegaNewton;
 #ifdef MRGP_OMEGA_PROF
         const long long pc0 = clock64();
 #endif
@@ -1409,10 +1430,14 @@ __global__ void __launch_bounds__(32, 1) k_scale_warp(RegionArgs a) {
 #endif
         double rhs = 1.0 - c, y = 0.0, dinv = 0.0;
         double piv = __shfl_sync(0xffffffffu, H[0], 0);
+        double *colbuf = T;                                           // the transposed table is no longer needed
+        __syncwarp();
 #pragma unroll
         for (int k = 0; k < M; ++k) {
             const double di = rsqrt(piv);
             H[k] *= di;                                               // l_ik for lanes i >= k (l_kk on lane k)
+            double *cb = colbuf + (k & 1) * 32;                       // two buffers: no barrier between the steps
+            cb[lane] = H[k];
             if (k + 1 < M) {
                 H[k + 1] = fma(-H[k], __shfl_sync(0xffffffffu, H[k], k + 1), H[k + 1]);
                 piv = __shfl_sync(0xffffffffu, H[k + 1], k + 1);
@@ -1423,8 +1448,9 @@ __global__ void __launch_bounds__(32, 1) k_scale_warp(RegionArgs a) {
                 y = yk;
             }
             if (lane > k) rhs = fma(-H[k], yk, rhs);
+            __syncwarp();
 #pragma unroll
-            for (int j = k + 2; j < M; ++j) H[j] = fma(-H[k], __shfl_sync(0xffffffffu, H[k], j), H[j]);
+            for (int j = k + 2; j < M; ++j) H[j] = fma(-H[k], cb[j], H[j]);   // broadcast loads of l_jk
         }
 #ifdef MRGP_OMEGA_PROF
         const long long pc2 = clock64();
@@ -1985,6 +2011,270 @@ __global__ void k_eval_layers(EvalArgs a) {
 #pragma unroll
         for (int d = 0; d < DY; ++d) a.out_mean[n * DY + d] = mean[d];
     if (a.out_var) a.out_var[n] = var;
+}
+
+// Pull a byte range into L2 (one prefetch per 128-byte line, nothing waits on it).
+__global__ void k_prefetch_l2(const char *base, size_t lines) {
+    for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < lines; l += (size_t)gridDim.x * blockDim.x)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + l * 128));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Closed-form statistics of the ci layers above the first (static intervals).
+//
+// Such a layer regresses on targets inferred from its own posterior, y = Phi A_old + b_old + fbar
+// (LatentOutputs.py:20-49), so every per-sample quantity the P4 / P5 statistics add up (Posteriors.py:81-93,
+// 132-148) is a polynomial in the region's coefficients with basis-only weights:
+//     r_n = y_n - Phi_n A_new - fbar_n = Phi_n (A_old - A_new) + b_old
+//     sum_n r_d   = sum_i s_i dA_id + n b_old,d                                   s_i  = sum_n phi_i(n)
+//     sum_n |r|^2 = sum_d dA_d^T G dA_d + 2 b_old . (s^T dA) + n |b_old|^2         G    = Phi^T Phi
+//     sum_n fvar  = sum_{jp<j} (n bias_var_jp,anc + sum_i cm2_jp,anc,i D_jp,i)     D_jp = sum_n phi^jp_i(n)^2
+//     sum_n sum_i phi_i^2 cm2_i = sum_i d_i cm2_i
+// (for regions nested in the coarser layer jp; in general the last sum runs over the pieces region x coarser
+// region, each with its own anc and D, see PieceTable).  s, G and D depend on
+// x and the basis intervals only: they are built once (k_build_gram, k_build_ancD) and the layer's statistics
+// become O(R M^2) work instead of a pass over the samples.  With the non-informative initialisation dA == 0 and
+// b_old == 0 exactly (the layers are inert) and the first two sums are exact zeros in both forms.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGramRows = 128;
+
+template <int M>
+__global__ void __launch_bounds__(256) k_build_gram(const double *x, const int64_t *offsets, const double *inv2L, const double *rsqrtL,
+                                                    int splits, double *partial /* [blocks][NP + M] */) {
+    constexpr int NP = M * (M + 1) / 2, NQ = (NP + 255) / 256;
+    __shared__ double sPhi[kGramRows][M + 1];
+    __shared__ unsigned char sI[NP], sK[NP];
+    const int tid = threadIdx.x, blk = blockIdx.x, c = blk / splits, sp = blk % splits;
+    for (int p = tid; p < NP; p += 256) {   // pair p = (i, k), i <= k, rows of the upper triangle one after the other
+        int i = 0, rem = p;
+        while (rem >= M - i) {
+            rem -= M - i;
+            ++i;
+        }
+        sI[p] = (unsigned char)i;
+        sK[p] = (unsigned char)(i + rem);
+    }
+    const int64_t lo = offsets[c], hi = offsets[c + 1];
+    const int64_t per = (hi - lo + splits - 1) / splits;
+    const int64_t a = lo + sp * per, b = (a + per < hi) ? a + per : hi;
+    const double i2 = inv2L[c], rs = rsqrtL[c];
+    double acc[NQ], sacc = 0.0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
+    __syncthreads();
+    for (int64_t base = a; base < b; base += kGramRows) {
+        if (tid < kGramRows) {
+            const int64_t n = base + tid;
+            if (n < b) {
+                double f1, c2;
+                basis_seed(x[n], i2, rs, f1, c2);
+                double fm = 0.0, f = f1;
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    sPhi[tid][i] = f;
+                    const double fn = fma(c2, f, -fm);
+                    fm = f;
+                    f = fn;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < M; ++i) sPhi[tid][i] = 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int p = tid + q * 256;
+            if (p < NP) {
+                const int i = sI[p], k = sK[p];
+                double t0 = 0.0, t1 = 0.0;
+#pragma unroll 8
+                for (int r = 0; r < kGramRows; r += 2) {
+                    t0 = fma(sPhi[r][i], sPhi[r][k], t0);
+                    t1 = fma(sPhi[r + 1][i], sPhi[r + 1][k], t1);
+                }
+                acc[q] += t0 + t1;
+            }
+        }
+        if (tid < M) {
+            double t = 0.0;
+            for (int r = 0; r < kGramRows; ++r) t += sPhi[r][tid];
+            sacc += t;
+        }
+        __syncthreads();
+    }
+    double *out = partial + (size_t)blk * (NP + M);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const int p = tid + q * 256;
+        if (p < NP) out[p] = acc[q];
+    }
+    if (tid < M) out[NP + tid] = sacc;
+}
+
+// G[c][i][k] (full, symmetric) and s[c][i] from the split partials, summed in split order.
+__global__ void k_reduce_gram(const double *partial, int splits, int R, int M, double *G, double *s) {
+    const int NP = M * (M + 1) / 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= R * (NP + M)) return;
+    const int c = t / (NP + M), p = t % (NP + M);
+    double acc = 0.0;
+    for (int sp = 0; sp < splits; ++sp) acc += partial[((size_t)c * splits + sp) * (NP + M) + p];
+    if (p >= NP) {
+        s[(size_t)c * M + (p - NP)] = acc;
+        return;
+    }
+    int i = 0, rem = p;
+    while (rem >= M - i) {
+        rem -= M - i;
+        ++i;
+    }
+    const int k = i + rem;
+    G[((size_t)c * M + i) * M + k] = acc;
+    G[((size_t)c * M + k) * M + i] = acc;
+}
+
+// D[piece][i] = sum over the samples of the piece of the squared basis functions of its coarser layer.  A piece is
+// the intersection of a region of the layer with a region of a coarser layer jp (regions need not be nested: the
+// uniform index sets of the reference are not, IndexSetGenerator.py:25-42); blockIdx.x = (piece, split).
+struct PieceTable {
+    const int32_t *ptr;    // (n_anc, R + 1): pieces of (jp, region) are ptr[jp * (R + 1) + c] .. ptr[.. + 1]
+    const int32_t *jp;     // (P) coarser layer of the piece
+    const int32_t *anc;    // (P) region of that layer
+    const int64_t *lo, *hi;   // (P) sample range
+    int32_t P;
+};
+
+template <int M>
+__global__ void __launch_bounds__(256) k_build_ancD(EvalArgs ea, const double *x, PieceTable pt, int splits, double *partial) {
+    __shared__ double sW[8][M];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int blk = blockIdx.x, pc = blk / splits, sp = blk % splits;
+    const EvalLayer &ly = ea.layer[pt.jp[pc]];
+    const int anc = pt.anc[pc];
+    const int64_t lo = pt.lo[pc], hi = pt.hi[pc];
+    const double i2 = ly.inv2L[anc], rs = ly.rsqrtL[anc];
+    const int64_t per = (hi - lo + splits - 1) / splits;
+    const int64_t a = lo + sp * per, b = (a + per < hi) ? a + per : hi;
+    double acc[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) acc[i] = 0.0;
+    for (int64_t n = a + tid; n < b; n += 256) {
+        double f1, c2;
+        basis_seed(x[n], i2, rs, f1, c2);
+        double fm = 0.0, f = f1;
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            acc[i] = fma(f, f, acc[i]);
+            const double fn = fma(c2, f, -fm);
+            fm = f;
+            f = fn;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        const double t = warp_sum(acc[i]);
+        if (lane == 0) sW[warp][i] = t;
+    }
+    __syncthreads();
+    if (tid < M) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sW[w][tid];
+        partial[(size_t)blk * M + tid] = t;
+    }
+}
+
+__global__ void k_reduce_ancD(const double *partial, int splits, int P, int M, double *D) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P * M) return;
+    const int i = t % M, pc = t / M;
+    double acc = 0.0;
+    for (int sp = 0; sp < splits; ++sp) acc += partial[((size_t)pc * splits + sp) * M + i];
+    D[t] = acc;
+}
+
+struct StatsBArgs {
+    StreamArgs p;             // bias / noise fields of the layer
+    EvalArgs anc;             // the coarser layers (cm2, bias_var, offsets)
+    const double *s, *G, *D;  // invariants of the layer: (R, M), (R, M, M), (P, M)
+    PieceTable pt;
+    const double *A, *A_prev, *d, *cm2;
+};
+
+// One warp per region: the five sums of the header, then P4 / P5 / S5 for the region.
+template <int DY>
+__global__ void __launch_bounds__(256) k_stats_b(StatsBArgs q) {
+    static_assert(DY == 2, "dy == 2 only");
+    const StreamArgs &p = q.p;
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    ts_begin(p.ts, p.layer * 4 + 2);
+    if (c < p.R) {
+        const int M = q.anc.M;
+        const double n = (double)(p.offsets[c + 1] - p.offsets[c]);
+        // dA = A_old - A_new for this lane's basis functions (M <= 64: two per lane)
+        double dA[2][2], sd0 = 0.0, sd1 = 0.0, dc = 0.0;
+        bool any = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            dA[h][0] = dA[h][1] = 0.0;
+            if (i < M) {
+                const size_t ri = (size_t)c * M + i;
+                dA[h][0] = q.A_prev[ri * 2 + 0] - q.A[ri * 2 + 0];
+                dA[h][1] = q.A_prev[ri * 2 + 1] - q.A[ri * 2 + 1];
+                const double si = q.s[ri];
+                sd0 = fma(si, dA[h][0], sd0);
+                sd1 = fma(si, dA[h][1], sd1);
+                dc = fma(q.d[ri], q.cm2[ri], dc);
+                any = any || dA[h][0] != 0.0 || dA[h][1] != 0.0;
+            }
+        }
+        sd0 = warp_sum(sd0);
+        sd1 = warp_sum(sd1);
+        dc = warp_sum(dc);
+        double quad = 0.0;
+        if (__any_sync(0xffffffffu, any)) {   // dA^T G dA, column i of the symmetric G per lane (coalesced rows)
+            const double *G = q.G + (size_t)c * M * M;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane + 32 * h;
+                double t0 = 0.0, t1 = 0.0;
+                for (int k = 0; k < M; ++k) {
+                    const double g = (i < M) ? G[(size_t)k * M + i] : 0.0;
+                    const int src = k & 31;
+                    const double a0 = __shfl_sync(0xffffffffu, (k < 32) ? dA[0][0] : dA[1][0], src);
+                    const double a1 = __shfl_sync(0xffffffffu, (k < 32) ? dA[0][1] : dA[1][1], src);
+                    t0 = fma(g, a0, t0);
+                    t1 = fma(g, a1, t1);
+                }
+                quad += dA[h][0] * t0 + dA[h][1] * t1;
+            }
+            quad = warp_sum(quad);
+        }
+        double fv = 0.0;
+        for (int jp = 0; jp < q.anc.n_layers; ++jp) {
+            const EvalLayer &ly = q.anc.layer[jp];
+            const int32_t *pp = q.pt.ptr + (size_t)jp * (p.R + 1) + c;
+            for (int pc = pp[0]; pc < pp[1]; ++pc) {
+                const int anc = q.pt.anc[pc];
+                double t = 0.0;
+                for (int i = lane; i < M; i += 32) t = fma(ly.cm2[(size_t)anc * M + i], q.D[(size_t)pc * M + i], t);
+                fv += warp_sum(t) + (double)(q.pt.hi[pc] - q.pt.lo[pc]) * ly.bias_var[anc];
+            }
+        }
+        if (lane == 0) {
+            const double b0 = p.bias_mean_out[(size_t)c * 2 + 0], b1 = p.bias_mean_out[(size_t)c * 2 + 1];   // b_old
+            double sums[DY + 3];
+            sums[0] = sd0 + n * b0;
+            sums[1] = sd1 + n * b1;
+            sums[2] = quad + 2.0 * (b0 * sd0 + b1 * sd1) + n * (b0 * b0 + b1 * b1);
+            sums[3] = fv;
+            sums[4] = dc;
+            bias_noise_region<DY>(p, c, sums);
+        }
+    }
+    ts_end(p.ts, p.layer * 4 + 2);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -217,6 +217,19 @@ MRGP_HD void bingham2(double a, double b, double c, Bingham2 &out) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kOmegaWarmup = 6;
 constexpr int kOmegaMaxNewton = 40;
+// Step policy (the same in omega_solve_serial, k_scale and k_scale_warp).  The first step is a Sinkhorn column
+// step; Sinkhorn goes on while it contracts the residual by more than kOmegaFast per step (peaked tables: rate
+// ~0.1, a step costs a tenth of a Newton step); otherwise a Newton step is taken once the residual is below
+// kOmegaNewtonBelow (further out the Newton matrix can lose definiteness), unless the previous Newton step failed
+// to reduce the residual.
+constexpr double kOmegaFast = 0.33;
+constexpr double kOmegaNewtonBelow = 0.2;
+enum { kOmegaNone = 0, kOmegaSinkhorn = 1, kOmegaNewton = 2 };
+__host__ __device__ inline bool omega_take_newton(double err, double err_prev, int last) {
+    const bool sink_fast = last == kOmegaSinkhorn && err < kOmegaFast * err_prev;
+    const bool newton_ok = last != kOmegaNone && err < kOmegaNewtonBelow && !(last == kOmegaNewton && !(err < err_prev));
+    return newton_ok && !sink_fast;
+}
 constexpr double kOmegaTol = 1e-10;   // max |column sum - 1| (rows are exact); the reference solver stops near 1e-8
 constexpr int kOmegaFallbackSweeps = 2000;
 
@@ -234,7 +247,7 @@ inline int omega_solve_serial(const double *lw, int M, double *omega, double *K,
         v[k] = 1.0;
     }
     int iters = 0;
-    int n_warmup = kOmegaWarmup;
+    int last = kOmegaNone;
     double err_prev = INFINITY;
     for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
         ++iters;
@@ -255,15 +268,17 @@ inline int omega_solve_serial(const double *lw, int M, double *omega, double *K,
         if (!isfinite(err)) {   // overshooting Newton step: start again from the shifts alone
             for (int k = 0; k < M; ++k) v[k] = 1.0;
             err_prev = INFINITY;
-            n_warmup = it + 1 + kOmegaWarmup;
+            last = kOmegaNone;
             continue;
         }
-        if (it < n_warmup || !(err < err_prev)) {
+        if (!omega_take_newton(err, err_prev, last)) {
             for (int k = 0; k < M; ++k) v[k] = fmax(1e-280, fmin(1e280, v[k] / c[k]));   // Sinkhorn column step
-            err_prev = (it < n_warmup) ? INFINITY : err;
+            err_prev = err;
+            last = kOmegaSinkhorn;
             continue;
         }
         err_prev = err;
+        last = kOmegaNewton;
         for (int k = 0; k < M; ++k)
             for (int m = 0; m <= k; ++m) {
                 double s = 0.0;

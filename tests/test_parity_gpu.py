@@ -161,7 +161,9 @@ def test_graph_replay_equals_stepwise_phases_and_is_deterministic():
     sa, sb, sc = a._engine.state(), b._engine.state(), c._engine.state()
     for k in sa:
         assert np.array_equal(sa[k], sc[k]), k          # same launch geometry -> bitwise reproducible
-        assert np.array_equal(sa[k], sb[k]), k          # graph replay == per-phase ABI calls
+    # graph replay == per-phase ABI calls, up to the summation order of the layer statistics: the per-phase calls
+    # stream every layer, the captured sweep takes the statistics of the inferred-target layers in closed form
+    compare(sa, sb, rtol=1e-11)
 
 
 def test_skipped_statistics_pass_of_inferred_layers_is_an_identity():
