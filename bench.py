@@ -263,29 +263,44 @@ def run_gpu(args, rank, world, local_rank):
         sys.stdout.flush()
         os._exit(0)
 
-    # ---- per-kernel timing for the roofline (CUDA events around single launches on the engine stream) --
-    reps = 3
-    t_a = [time_phase(eng, eng.phase_a, j, torch, reps) for j in range(N_LAYERS)]
-    t_mid = [time_phase(eng, eng.axis_update, j, torch, reps) for j in range(N_LAYERS)]
-    t_b = [time_phase(eng, eng.phase_b, j, torch, reps) for j in range(N_LAYERS)]
-    t_post = [time_phase(eng, eng.bias_noise, j, torch, reps) for j in range(N_LAYERS)]
-    med = lambda rows: [float(np.median(r)) for r in rows]
-    ta, tm, tb, tp = med(t_a), med(t_mid), med(t_b), med(t_post)
-    # dominant kernel: phase B with inferred targets, latent input and propagation (layers 1 .. J-2)
-    dom = tb[1:N_LAYERS - 1]
-    dom_ms = float(np.mean(dom))
-    # bytes one launch has to move: x (8) + latent mean (16) + latent var (8) read, latent mean/var (24)
-    # written per sample; y is not read when the targets are inferred (SURVEY.md counts 72 with y)
-    dom_bytes = 56 * N_SAMPLES
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'k_phase_b<2,30,infer,latent,propagate>', 'achieved': achieved,
-                'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-                'bytes_per_launch': dom_bytes, 'ms_per_launch': dom_ms,
-                'sweep_algorithmic_gbs': BYTES_SWEEP_PER_SAMPLE_LAYER * N_SAMPLES * N_LAYERS / (total_s / args.steps) / 1e9,
-                'kernel_ms': {'phase_a': ta, 'axis_update': tm, 'phase_b': tb, 'bias_noise': tp}}
-    # FP64 pipe: measured DFMA peak next to the FMA count of the dominant kernel (7 per basis function
-    # and sample: recurrence 1, Phi A_new 2, Phi A_old 2, phi^2 cm2 2; + ~40 for sincospi and the tail)
+    # ---- per-kernel timing for the roofline ----------------------------------------------------------
+    # The captured ci sweep streams the samples on layer 0 only (phase A and phase B over x and y); the layers above
+    # take their statistics in closed form and every other kernel is a latency-bound small-matrix step.
+    # Phase A of layer 0 is the same kernel in the sweep and behind mrgp_phase_a: it is timed alone with CUDA events
+    # on the engine stream, L2 flushed before every launch.
     import ctypes as C
+    dom_samples = []
+    for _ in range(7):
+        flush.zero_()
+        eng.stream.wait_stream(torch.cuda.current_stream())
+        dom_samples += time_phase(eng, eng.phase_a, 0, torch, 1)
+    dom_ms = float(np.median(dom_samples))
+    dom_bytes = 24 * N_SAMPLES           # x (8) + y (16) per sample; layer 0 has no latent input
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    # where the time of one sweep goes: global-timer stamps written by the kernels inside the captured graph
+    eng.lib.mrgp_timeline_enable(eng.handle, 1)
+    eng.sweep(2)
+    eng.synchronize()
+    tags, tms = (C.c_int32 * 128)(), (C.c_float * 256)()
+    eng.lib.mrgp_timeline_read(eng.handle, tags, tms, 128)
+    eng.lib.mrgp_timeline_enable(eng.handle, 0)
+    def stamp(j, k):
+        b, e = tms[2 * (4 * j + k)], tms[2 * (4 * j + k) + 1]
+        return None if b < 0 else [round(1e3 * b, 1), round(1e3 * e, 1)]
+    timeline = {name: [stamp(j, k) for j in range(N_LAYERS)]
+                for k, name in enumerate(('phase_a', 'mid', 'phase_b_or_closed_form', 'omega_side_stream'))}
+    ends = [v[1] for rows in timeline.values() for v in rows if v]
+    sweep_us = max(ends) if ends else None
+    stream_us = sum(v[1] - v[0] for v in (timeline['phase_a'][0], timeline['phase_b_or_closed_form'][0]) if v)
+    roofline = {'bound': 'hbm', 'kernel': 'k_phase_a<2,30,observed targets,no latent input> (layer 0)', 'achieved': achieved,
+                'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': 24041216, 'traffic_source': 'ncu --set full, profiles/r01_ncu_summary.md',
+                'bytes_per_launch': dom_bytes, 'ms_per_launch': dom_ms,
+                'note': 'FP64-bound kernel (see fp64); the sweep is dominated by latency-bound small-matrix kernels',
+                'sweep_timeline_us': timeline, 'sweep_us_in_graph_warm_l2': sweep_us,
+                'streaming_share_of_sweep': (stream_us / sweep_us) if sweep_us else None}
+    # FP64 pipe: measured DFMA peak next to the FMA count of that kernel (6 per basis function and sample:
+    # recurrence 1 and Phi A 2 in the first pass, recurrence 1 and Phi^T r 2 in the second; + ~40 for sincospi)
     sink = torch.zeros(8, dtype=torch.float64, device='cuda')
     ms = C.c_float()
     iters = 200000
@@ -293,7 +308,7 @@ def run_gpu(args, rank, world, local_rank):
     eng.lib.mrgp_fp64_probe(None, iters, C.c_void_p(sink.data_ptr()), C.byref(ms))
     sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     fp64_peak = sms * 4 * 256 * iters * 8 * 2 / (ms.value * 1e-3) / 1e12
-    dom_flops = (7 * N_BASIS + 40) * 2 * N_SAMPLES
+    dom_flops = (6 * N_BASIS + 40) * 2 * N_SAMPLES
     roofline['fp64'] = {'peak_tflops_measured': fp64_peak, 'achieved_tflops': dom_flops / (dom_ms * 1e-3) / 1e12,
                         'frac': dom_flops / (dom_ms * 1e-3) / 1e12 / fp64_peak}
 
