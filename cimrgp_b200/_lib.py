@@ -72,6 +72,7 @@ SIGNATURES = {
     'mrgp_comm_export': (C.c_int, [_P, C.c_void_p]),
     'mrgp_comm_bind': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]),
     'mrgp_exchange': (C.c_int, [_P, C.c_int32, C.c_int32]),
+    'mrgp_set_all_inputs_host': (C.c_int, [_P, _D]),
     'mrgp_region_sums': (C.c_int, [_P, C.c_int32, C.c_int32]),
     'mrgp_exchange_buffer': (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     'mrgp_build_basis_stage': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_double]),

@@ -108,6 +108,8 @@ struct mrgp_handle {
     int64_t launches = 0, launches_per_sweep = 0, sweeps_done = 0;
     bool capturing = false;
     bool timeline = false;
+    double *x_all = nullptr;         // sharded handles: inputs of ALL ranks (mrgp_set_all_inputs_host), else unused
+    bool have_x_all = false;
     size_t state_begin = 0, state_end = 0;
     double *build_part = nullptr;    // split partials of the invariant builds
     size_t build_part_doubles = 0;
@@ -258,7 +260,8 @@ size_t carve(mrgp_handle *h, char *base) {
         for (int j = 0; j < J; ++j) rmax = std::max(rmax, h->plan[j].R);
         h->xchg = c.take<double>((size_t)rmax * h->part_stride);
     }
-    if (!fi && !h->sharded && J > 1) {   // closed-form statistics of the layers above the first
+    if (!fi && J > 1) {   // closed-form statistics of the layers above the first
+        if (h->sharded) h->x_all = c.take<double>((size_t)h->cfg.n_samples * h->cfg.dx);   // replicated inputs: the invariants need every sample
         const size_t np = (size_t)M * (M + 1) / 2 + M;
         size_t need = 0;
         for (int j = 1; j < J; ++j) {
@@ -296,7 +299,7 @@ size_t carve(mrgp_handle *h, char *base) {
         d.S = c.take<double>(RM);
         d.d = c.take<double>(RM);
         d.absx = c.take<double>(R);
-        if (!fi && !h->sharded && j > 0) {
+        if (!fi && j > 0) {
             const size_t P = lp.pc_jp.size();
             d.sumPhi = c.take<double>(RM);
             d.ancD = c.take<double>(P * M);
@@ -371,7 +374,7 @@ size_t carve(mrgp_handle *h, char *base) {
     s.priorShape = c.take<double>(M);
     s.priorScale = c.take<double>(M);
     h->state_end = c.off;
-    if (!fi && !h->sharded)
+    if (!fi)
         for (int j = 1; j < J; ++j) h->dev[j].gram = c.take<double>((size_t)h->plan[j].R * M * M);   // read only when dA != 0
     return (c.off + 255) & ~(size_t)255;
 }
@@ -855,7 +858,8 @@ int fill_eval_layers(mrgp_handle *h, EvalArgs &ea, int n_layers, const int64_t *
 // ci, static intervals, nested regions, one GPU: the layers above the first take their P4 / P5 statistics in closed
 // form (k_stats_b) instead of streaming the samples.
 bool use_closed_form(const mrgp_handle *h) {
-    if (h->cfg.mode != MRGP_MODE_CI || h->sharded || !h->inferred_shortcut || !h->build_part) return false;
+    if (h->cfg.mode != MRGP_MODE_CI || !h->inferred_shortcut || !h->build_part) return false;
+    if (h->sharded && !h->have_x_all) return false;
     for (const auto &d : h->dev)
         if (d.adaptive) return false;
     return h->cfg.n_layers > 1;
@@ -868,7 +872,8 @@ int launch_build_invariants(mrgp_handle *h, int j) {
     const int splits = build_splits(lp.R), blocks = lp.R * splits;
     constexpr int NP = M * (M + 1) / 2;
     CK(cudaFuncSetAttribute(k_build_gram<M>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    k_build_gram<M><<<blocks, 256, 0, h->stream>>>(h->x, d.offsets, d.inv2L, d.rsqrtL, splits, h->build_part);
+    const double *xg = h->sharded ? h->x_all : h->x;   // indexed by the global sample number
+    k_build_gram<M><<<blocks, 256, 0, h->stream>>>(xg, d.offsets, d.inv2L, d.rsqrtL, splits, h->build_part);
     CK(cudaGetLastError());
     k_reduce_gram<<<(lp.R * (NP + M) + 255) / 256, 256, 0, h->stream>>>(h->build_part, splits, lp.R, M, d.gram, d.sumPhi);
     CK(cudaGetLastError());
@@ -877,7 +882,7 @@ int launch_build_invariants(mrgp_handle *h, int j) {
     if (rc) return rc;
     const int P = (int)lp.pc_jp.size(), psplits = build_splits(P);
     const PieceTable pt{d.pc_ptr, d.pc_jp, d.pc_anc, d.pc_lo, d.pc_hi, P};
-    k_build_ancD<M><<<P * psplits, 256, 0, h->stream>>>(ea, h->x, pt, psplits, h->build_part);
+    k_build_ancD<M><<<P * psplits, 256, 0, h->stream>>>(ea, xg, pt, psplits, h->build_part);
     CK(cudaGetLastError());
     k_reduce_ancD<<<(P * M + 255) / 256, 256, 0, h->stream>>>(h->build_part, psplits, P, M, d.ancD);
     CK(cudaGetLastError());
@@ -946,7 +951,11 @@ int sweep_once(mrgp_handle *h, bool fork_omega) {
             // sample-sharded: the region statistics of both streaming phases are summed over the ranks
             if (!zero_T && (rc = do_exchange(h, j, 0, h->cfg.n_basis * h->cfg.dy, false))) return rc;
             if ((rc = do_axis_update(h, j, fork_omega && ci, zero_T))) return rc;
-            if ((rc = do_phase_b(h, j, false))) return rc;
+            if (closed && j > 0) {   // replicated closed form: no samples, no exchange
+                if ((rc = do_stats_b(h, j))) return rc;
+                continue;
+            }
+            if ((rc = do_phase_b(h, j, false, closed ? 0 : -1))) return rc;
             if ((rc = do_exchange(h, j, 1, h->cfg.dy + 3, false))) return rc;
             if ((rc = do_bias_noise(h, j))) return rc;
             continue;
@@ -1147,7 +1156,7 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     h->cta_quantum = q;
     h->n_ctas = (int)((n_local + q - 1) / q);
     build_plan(h);
-    if (cfg->mode == MRGP_MODE_CI && !h->sharded)
+    if (cfg->mode == MRGP_MODE_CI)
         for (int j = 1; j < cfg->n_layers; ++j) {
             LayerPlan &lp = h->plan[j];
             lp.pc_ptr.assign((size_t)j * (lp.R + 1), 0);
@@ -1282,6 +1291,18 @@ int mrgp_set_data_host(mrgp_handle *h, const double *x_host, const double *y_hos
     h->x = h->x_ws;
     h->y = h->y_ws;
     h->have_data = true;
+    return MRGP_OK;
+}
+
+int mrgp_set_all_inputs_host(mrgp_handle *h, const double *x_all_host) {
+    if (!h || !x_all_host) return fail(h, MRGP_EINVAL, "null argument");
+    if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
+    if (!h->sharded) return fail(h, MRGP_ESTATE, "not a sharded handle: mrgp_set_data* already holds every sample");
+    if (!h->x_all) return fail(h, MRGP_ESTATE, "this handle has no use for the replicated inputs (fi mode or one layer)");
+    CK(cudaMemcpyAsync(h->x_all, x_all_host, (size_t)h->cfg.n_samples * h->cfg.dx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->have_x_all = true;
+    for (auto &d : h->dev) d.inv_built = false;
+    drop_graph(h);
     return MRGP_OK;
 }
 

@@ -70,6 +70,12 @@ class ShardedEngine(Engine):
             bounds = (C.c_int64 * (world_size + 1))(*([chunk_bounds(n_total, world_size, q)[0] for q in range(world_size)]
                                                       + [n_total]))
             self._ck(self.lib.mrgp_comm_bind(self.handle, rank, world_size, blobs, bounds))
+            if self.mode == 'ci' and self.J > 1:
+                # inputs of all ranks (x only, 8 B per sample): the closed-form statistics of the upper layers
+                xa = np.ascontiguousarray(x_norm, dtype=np.float64)
+                self._ck(self.lib.mrgp_set_all_inputs_host(self.handle, _lib._dptr(xa) if hasattr(_lib, '_dptr') else
+                                                           xa.ctypes.data_as(C.POINTER(C.c_double))))
+                self.synchronize()
             for j in range(self.J):
                 self._ck(self.lib.mrgp_build_basis(self.handle, j, float(self._interval_factor[j]), None))
             self._ck(self.lib.mrgp_init_state(self.handle, *self._init_args))

@@ -224,6 +224,10 @@ enum { MRGP_X_PHASE_A = 0, MRGP_X_PHASE_B = 1 };
 int mrgp_comm_export(mrgp_handle *h, void *blob_out);
 int mrgp_comm_bind(mrgp_handle *h, int32_t rank, int32_t world, const void *blobs, const int64_t *bounds);
 int mrgp_exchange(mrgp_handle *h, int32_t layer, int32_t which);
+/* Optional on a sharded ci handle: the normalised inputs of ALL ranks (n_samples x dx doubles, host memory; 8 MB at
+ * N = 1e6).  With them every rank builds the basis invariants of the closed-form statistics and
+ * the layers above the first need neither their samples nor an exchange in mrgp_sweep.  y never leaves its rank. */
+int mrgp_set_all_inputs_host(mrgp_handle *h, const double *x_all_host);
 int mrgp_region_sums(mrgp_handle *h, int32_t layer, int32_t which);
 int mrgp_exchange_buffer(mrgp_handle *h, int32_t layer, int32_t which, void **dev_ptr, size_t *n_doubles);
 int mrgp_build_basis_stage(mrgp_handle *h, int32_t layer, int32_t stage, double interval_factor);
