@@ -53,42 +53,54 @@ def peak_hbm():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
-        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
-        'clocks_event_reasons.sw_power_cap'
+    """SM clock and throttle reasons sampled DURING the timed region: NVML from a polling thread (one sample
+    every ~2 ms; the timed region of this benchmark lasts tens of milliseconds, too short for `nvidia-smi -lms`),
+    with the nvidia-smi one-shot query of B200_PROFILING.md as the fallback."""
+    REASONS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.max_sm, self.stop_flag, self.thread, self.nvml = index, [], 0, None, False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)))
+                get = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.mask |= int(get(self.dev))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.max_sm,
+                    'reasons': [n for n, bit in self.REASONS if self.mask & bit], 'samples': len(self.sm), 'source': 'nvml'}
         try:
-            self.proc.wait(timeout=5)
+            q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+                'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+            out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(',')
+            names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+            return {'sm_mhz': float(out[0]), 'sm_max_mhz': float(out[1]),
+                    'reasons': [n for k, n in enumerate(names) if out[2 + k].strip() == 'Active'], 'samples': 1,
+                    'source': 'nvidia-smi after the timed region'}
         except Exception:
-            self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace('.', '').isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 8 and r[4 + k] == 'Active' for r in self.rows)]
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml and nvidia-smi unavailable'], 'samples': 0}
 
 
 def make_model(n, device, n_ctas=0, distributed=False):

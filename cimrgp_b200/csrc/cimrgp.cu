@@ -1725,7 +1725,6 @@ int mrgp_comm_bind(mrgp_handle *h, int32_t rank, int32_t world, const void *blob
     // same shared-memory carveout as the rest of the sweep: no SM reconfiguration around the exchanges
     CK(cudaFuncSetAttribute(k_region_sums<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_region_sums<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(k_comm_signal, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_comm_sums_signal<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_comm_sums_signal<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k_comm_reduce<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));

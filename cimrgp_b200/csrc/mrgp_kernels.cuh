@@ -1549,20 +1549,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-// Publish: the arena of this rank holds the sums of exchange number (*seq + 1).  One warp.
-__global__ void k_comm_signal(CommArgs c) {
-    __shared__ unsigned long long s;
-    if (threadIdx.x == 0) {
-        s = *c.seq + 1ull;
-        *c.seq = s;
-    }
-    __syncthreads();
-    __threadfence_system();
-    if ((int)threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + c.rank, s);
-}
-
 // Dense per-region sums of the local run partials into the arena, one block per region (threads = value x
-// run slice), and - by the block that finishes last - the publication of k_comm_signal.
+// run slice), and - by the block that finishes last - the publication: the next sequence number is release-stored
+// into this rank's slot of every peer's flag array.
 template <bool MAX>
 __global__ void __launch_bounds__(256) k_comm_sums_signal(CommArgs c, const int32_t *region_run, const double *part, int stride, int nv,
                                                           double *out, unsigned int *counter) {
