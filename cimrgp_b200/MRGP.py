@@ -53,7 +53,8 @@ class MultiResolutionGaussianProcess(object):
                  verbose=False,
                  device=0,
                  n_ctas=0,
-                 distributed=False):
+                 distributed=False,
+                 _engine_opts=None):
         self.verbose = verbose
         self.forced_independence = forced_independence
         # MRGP.py:38-50
@@ -152,6 +153,8 @@ class MultiResolutionGaussianProcess(object):
                          noise_var0=noise_var0, ard_prior_influence=float(np.mean(sf)),
                          noise_region_specific=noise_region_specific, bias_region_specific=bias_region_specific,
                          device=device, n_ctas=n_ctas)
+        if _engine_opts:
+            engine_kw.update(_engine_opts)      # shared stream / workspace slice / pinned staging (cimrgp_b200/batch.py)
         if distributed:
             # one process per GPU (torch.distributed initialised by the caller): this rank keeps its chunk of
             # the samples, the region statistics are all-reduced, the model state is replicated on every rank

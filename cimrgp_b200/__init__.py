@@ -7,11 +7,15 @@ from .BasisInterval import BasisInterval
 from .IndexSetGenerator import IndexSetUniform
 from .KernelClass import LaplacianEigenpairs, MaternKernel
 
-__all__ = ['MultiResolutionGaussianProcess', 'IndexSetUniform', 'LaplacianEigenpairs', 'MaternKernel', 'BasisInterval']
+__all__ = ['MultiResolutionGaussianProcess', 'IndexSetUniform', 'LaplacianEigenpairs', 'MaternKernel', 'BasisInterval',
+           'SeriesBatch']
 
 
 def __getattr__(name):
     if name == 'MultiResolutionGaussianProcess':
         from .MRGP import MultiResolutionGaussianProcess
         return MultiResolutionGaussianProcess
+    if name == 'SeriesBatch':
+        from .batch import SeriesBatch
+        return SeriesBatch
     raise AttributeError(name)

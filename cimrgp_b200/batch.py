@@ -1,0 +1,75 @@
+"""Batch of independent series (BASELINE config 5): one MultiResolutionGaussianProcess per series,
+all of them in ONE device allocation and one pinned staging area, their sweeps in flight on a small pool of CUDA
+streams so that the short kernels of different series overlap on the GPU.
+
+The reference has no such API - every series is a separate object fitted one after the other
+(scripts/tests/*.py loop over models) - so this is a front end over the drop-in class, not a new model: series s
+behaves exactly like `MultiResolutionGaussianProcess([xs[s], ys[s]], ...)` and `batch[s]` IS that object.
+Series are independent: over several GPUs they are split by rank with no collective ("replicas only").
+"""
+import numpy as np
+
+from .engine import Engine
+from .IndexSetGenerator import IndexSetUniform, offsets_of
+from .MRGP import MultiResolutionGaussianProcess
+
+
+class SeriesBatch(object):
+    def __init__(self, xs, ys, n_basis, resolution, basis_function_obj, spectral_density_obj=None, divider=2,
+                 forced_independence=False, n_streams=16, device=0, n_ctas=None, **model_kw):
+        """xs[s]: (N_s, 1) inputs, ys[s]: (N_s, dy) observations of series s; the other arguments as for
+        MultiResolutionGaussianProcess (one index set IndexSetUniform(N_s, resolution, divider) per series).
+        n_ctas: streaming grid per model (default: one CTA per 1024 samples, so that many models fit on the GPU)."""
+        import torch
+        self.torch = torch
+        self.n_series = len(xs)
+        if len(ys) != self.n_series or self.n_series == 0:
+            raise ValueError('xs and ys must list the same, non-zero number of series')
+        dev = torch.device('cuda', int(device))
+        mode = 'fi' if forced_independence else 'ci'
+        sizes = [int(np.asarray(x).shape[0]) for x in xs]
+        dy = int(np.asarray(ys[0]).shape[1])
+        index_sets, need, ctas = [], [], []
+        probe = {}
+        for n in sizes:
+            idx = IndexSetUniform(n, resolution, divider)
+            index_sets.append(idx)
+            c = int(n_ctas) if n_ctas else max(1, min(64, n // 1024))
+            ctas.append(c)
+            if (n, c) not in probe:
+                probe[(n, c)] = Engine.probe_workspace_bytes(offsets_of(idx), n_basis, dy=dy, mode=mode, n_ctas=c,
+                                                             device=device)
+            need.append((probe[(n, c)] + 255) & ~255)
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(int(n_streams), self.n_series)))]
+        self.workspace = torch.empty(int(sum(need)), dtype=torch.uint8, device=dev)
+        total = int(sum(sizes))
+        self.pinned_x = torch.empty((total, 1), dtype=torch.float64).pin_memory()
+        self.pinned_y = torch.empty((total, dy), dtype=torch.float64).pin_memory()
+        self.models = []
+        w_off = s_off = 0
+        for s in range(self.n_series):
+            opts = dict(stream=self.streams[s % len(self.streams)], workspace=self.workspace[w_off:w_off + need[s]],
+                        pinned=(self.pinned_x[s_off:s_off + sizes[s]], self.pinned_y[s_off:s_off + sizes[s]]))
+            self.models.append(MultiResolutionGaussianProcess(
+                [np.asarray(xs[s], dtype=np.float64), np.asarray(ys[s], dtype=np.float64)], n_basis, index_sets[s],
+                basis_function_obj, spectral_density_obj, forced_independence=forced_independence, device=device,
+                n_ctas=ctas[s], _engine_opts=opts, **model_kw))
+            w_off += need[s]
+            s_off += sizes[s]
+
+    def __len__(self):
+        return self.n_series
+
+    def __getitem__(self, s):
+        return self.models[s]
+
+    def fit(self, n_iter=1):
+        """n_iter sweeps of every series (fit(n_iter, None) of each model), interleaved over the stream pool."""
+        for _ in range(int(n_iter)):
+            for m in self.models:
+                m._engine.sweep(1)
+        self.synchronize()
+
+    def synchronize(self):
+        for st in self.streams:
+            st.synchronize()

@@ -25,7 +25,8 @@ class Engine(object):
 
     def __init__(self, x_norm, y, offsets, n_basis, mode='ci', spectral=None, interval_factor=None,
                  noise_var0=1.0, ard_prior_influence=1.0, noise_region_specific=True, bias_region_specific=True,
-                 device=0, n_ctas=0, intervals=None, chunk=None, defer_build=False):
+                 device=0, n_ctas=0, intervals=None, chunk=None, defer_build=False, stream=None, workspace=None,
+                 pinned=None):
         import torch
         self.torch = torch
         self.lib = _lib.load()
@@ -54,15 +55,21 @@ class Engine(object):
         if not torch.cuda.is_available():
             raise _lib.MrgpError(_lib.ENODEVICE, 'no CUDA device: cimrgp_b200 has no CPU path')
         self.device = torch.device('cuda', int(device))
-        self.stream = torch.cuda.Stream(device=self.device)
+        # a batch of models (cimrgp_b200/batch.py) shares streams, one device allocation and one pinned staging area
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=self.device)
         nbytes = self.lib.mrgp_workspace_bytes(self.handle)
-        self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+        if workspace is not None:
+            if workspace.numel() < nbytes + 256:
+                raise ValueError('workspace slice of %d bytes, %d needed' % (workspace.numel(), nbytes + 256))
+            self.workspace = workspace
+        else:
+            self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
         base = self.workspace.data_ptr()
         aligned = (base + 255) & ~255
         torch.cuda.synchronize(self.device)
         self._ck(self.lib.mrgp_set_stream(self.handle, C.c_void_p(self.stream.cuda_stream)))
         self._ck(self.lib.mrgp_bind_workspace(self.handle, C.c_void_p(aligned), nbytes))
-        self._pinned = None
+        self._pinned = pinned
         self.set_data(x_norm, y)
         spectral = spectral if spectral is not None else [(1., 1., 1.)] * self.J
         interval_factor = interval_factor if interval_factor is not None else [1.0] * self.J
@@ -79,6 +86,24 @@ class Engine(object):
         if not defer_build:
             self._ck(self.lib.mrgp_init_state(self.handle, float(noise_var0), float(ard_prior_influence)))
             self.synchronize()
+
+    @staticmethod
+    def probe_workspace_bytes(offsets, n_basis, dy=2, mode='ci', n_ctas=0, device=0):
+        """Bytes Engine will ask for (plus 256 for alignment) for a model of this shape: lets a caller carve many
+        workspaces out of one allocation.  Host-only (plan construction), no device work."""
+        lib = _lib.load()
+        offs = [np.ascontiguousarray(o, dtype=np.int64) for o in offsets]
+        cfg = _lib.Config(_lib.ABI_VERSION, _lib.MODE_CI if mode == 'ci' else _lib.MODE_FI, int(offs[0][-1]), 1, int(dy),
+                          int(n_basis), len(offs), 1, 1, int(device), int(n_ctas), 0, 0)
+        ptrs, keep = _lib.offsets_arg(offs)
+        nreg = (C.c_int32 * len(offs))(*[len(o) - 1 for o in offs])
+        out = C.c_void_p()
+        rc = lib.mrgp_create(C.byref(cfg), ptrs, nreg, C.byref(out))
+        if rc != 0:
+            raise _lib.MrgpError(rc, lib.mrgp_last_error(None).decode())
+        n = int(lib.mrgp_workspace_bytes(out))
+        lib.mrgp_destroy(out)
+        return n + 256
 
     # ------------------------------------------------------------------------------------------
     def _ck(self, rc):

@@ -395,3 +395,29 @@ def test_peer_exchange_between_processes(mode, world):
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     oks = re.findall(r'rank \d+ ok ', res.stdout)      # the ranks' lines may interleave
     assert len(oks) == world and 'MISMATCH' not in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize('fi', [False, True])
+def test_series_batch_equals_separate_models(fi):
+    """Config 5 front end: models carved out of one device allocation, sweeps interleaved over a stream pool, must
+    give exactly the states of models built and fitted one by one (same launch geometry -> bit for bit)."""
+    from cimrgp_b200 import LaplacianEigenpairs, MaternKernel, SeriesBatch, IndexSetUniform
+    from cimrgp_b200.MRGP import MultiResolutionGaussianProcess
+    n, res, M, S = 2048, 5, 30, 6
+    xs, ys = [], []
+    for s in range(S):
+        x, y = workloads.workload1(n, seed=10 + s)
+        xs.append(x)
+        ys.append(y)
+    batch = SeriesBatch(xs, ys, M, res, LaplacianEigenpairs(), MaternKernel(nu=1, l=1, sf=1), forced_independence=fi,
+                        n_streams=3)
+    batch.fit(4)
+    for s in (0, 3, 5):
+        m = MultiResolutionGaussianProcess([xs[s], ys[s]], M, IndexSetUniform(n, res, 2), LaplacianEigenpairs(),
+                                           MaternKernel(nu=1, l=1, sf=1), forced_independence=fi, n_ctas=2)
+        m.fit(4, None)
+        a, b = batch[s]._engine.state(), m._engine.state()
+        for k in b:
+            assert np.array_equal(a[k], b[k]), (s, k)
+    xt = np.atleast_2d(np.linspace(1, 3, 500)).T
+    assert batch[1].get_predicted_mean(xt).shape == (500, 2)
