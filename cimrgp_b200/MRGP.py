@@ -3,7 +3,7 @@ public state) with the variational-inference sweep running on one B200 through l
 
 Same constructor arguments, same exceptions for the same misuse (MRGP.py:37-126), same meaning of every
 method.  What is NOT carried over (raises NotImplementedError with the reason): the GPy input-warp model
-(`adaptive_inputs=True` without an `input_model`; third-party GP), per-sweep
+(`adaptive_inputs=True` without an `input_model`; third-party GP),
 shared (non region-specific) noise or bias,
 dx > 1 and dy > 2 on the device.
 """
@@ -299,8 +299,15 @@ class MultiResolutionGaussianProcess(object):
         test_x = self._norm(test_x)
         if index_set_obj is None:
             return self._engine.predict_var(self._warp(test_x))
-        raise NotImplementedError('get_central_moment2 with an index set (MRGP.py:863-932) overwrites the latent '
-                                  'functions of the model in the reference; not offered on the device yet')
+        # MRGP.py:863-932.  The reference walks every layer of the MODEL with the test index set and overwrites the
+        # model's latent functions on the way; here the state is left untouched.
+        test_offsets = offsets_of(index_set_obj)
+        if len(test_offsets) != self.n_layers:
+            raise ValueError('the test index set must have the resolutions of the training index set')
+        for j, off in enumerate(test_offsets):
+            if len(off) - 1 != self.n_regions[j]:
+                raise ValueError('number of regions in the training must be the same as test.')
+        return self._engine.predict_var_indexed(self._warp(test_x), test_offsets)
 
     def get_test_likelihood(self, test, index_set_obj=None, number_of_regions=None):
         # MRGP.py:825-831

@@ -68,6 +68,7 @@ SIGNATURES = {
     'mrgp_synchronize': (C.c_int, [_P]),
     'mrgp_elbo': (C.c_int, [_P, _D]),
     'mrgp_predict_mean': (C.c_int, [_P, _P, C.c_int64, _I64PP, C.c_int32, _P]),
+    'mrgp_predict_var_indexed': (C.c_int, [_P, _P, C.c_int64, _I64PP, C.c_int32, _P]),
     'mrgp_predict_var': (C.c_int, [_P, _P, C.c_int64, _P]),
     'mrgp_comm_export': (C.c_int, [_P, C.c_void_p]),
     'mrgp_comm_bind': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]),

@@ -1070,6 +1070,7 @@ int fill_eval_layers(mrgp_handle *h, EvalArgs &ea, int n_layers, const int64_t *
         l.cm2 = d.cm2;
         l.bias = d.bias_mean;
         l.bias_var = d.bias_var;
+        l.noise_mean = d.noise_mean;
         l.R = h->plan[j].R;
     }
     return MRGP_OK;
@@ -1610,6 +1611,36 @@ int mrgp_predict_mean(mrgp_handle *h, const double *x_test_dev, int64_t n_test, 
     ea.out_mean = out_dev;
     ea.out_var = nullptr;
     k_eval_layers<2><<<(unsigned)((n_test + 127) / 128), 128, 0, h->stream>>>(ea);
+    CK(cudaGetLastError());
+    count(h);
+    CK(cudaStreamSynchronize(h->stream));
+    return MRGP_OK;
+}
+
+int mrgp_predict_var_indexed(mrgp_handle *h, const double *x_test_dev, int64_t n_test, const int64_t *const *test_offsets,
+                             int32_t n_test_layers, double *out_dev) {
+    int rc = check_ready(h, 0, true);
+    if (rc) return rc;
+    if (!x_test_dev || !out_dev || !test_offsets || n_test < 1) return fail(h, MRGP_EINVAL, "bad argument");
+    if (n_test_layers != h->cfg.n_layers)
+        return fail(h, MRGP_EINVAL, "the test index set must have the resolutions of the train set (MRGP.py:877-879 walks every layer)");
+    EvalArgs ea{};
+    std::vector<const int64_t *> dev_off;
+    size_t o = 0;
+    for (int j = 0; j < n_test_layers; ++j) {
+        const size_t cnt = h->plan[j].R + 1;
+        if (test_offsets[j][0] != 0 || test_offsets[j][cnt - 1] != n_test) return fail(h, MRGP_EINVAL, "test offsets of layer %d do not cover the test points", j);
+        CK(cudaMemcpyAsync(h->off_staging + o, test_offsets[j], cnt * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+        dev_off.push_back(h->off_staging + o);
+        o += cnt;
+    }
+    if ((rc = fill_eval_layers(h, ea, n_test_layers, dev_off.data()))) return rc;
+    ea.single_region = 0;
+    ea.n = n_test;
+    ea.x = x_test_dev;
+    ea.out_mean = nullptr;
+    ea.out_var = out_dev;
+    k_eval_var_indexed<2><<<(unsigned)((n_test + 127) / 128), 128, 0, h->stream>>>(ea);
     CK(cudaGetLastError());
     count(h);
     CK(cudaStreamSynchronize(h->stream));

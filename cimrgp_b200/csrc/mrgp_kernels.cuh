@@ -1948,7 +1948,7 @@ __device__ __forceinline__ int find_region(const int64_t *off, int R, int64_t n)
 
 struct EvalLayer {
     const int64_t *offsets;   // region offsets used to assign sample positions to regions
-    const double *inv2L, *rsqrtL, *A, *cm2, *bias, *bias_var;
+    const double *inv2L, *rsqrtL, *A, *cm2, *bias, *bias_var, *noise_mean;
     int32_t R;
 };
 
@@ -2264,6 +2264,46 @@ __global__ void __launch_bounds__(256) k_stats_b(StatsBArgs q) {
         }
     }
     ts_end(p.ts, p.layer * 4 + 2);
+}
+
+// Index-set form of the predictive second moment (MRGP.py:863-932): per test point the sum over the layers of
+//   sum_i phi_i^2 cm2_i + bias_var + n_test(region) / noise_mean + f_var(first test point of the region)
+// where f_var is the latent variance of the coarser layers at that point (Stats.py:126-157; the reference adds
+// `latent_f_var[l][0]`, the value of the region's FIRST sample, to every sample of the region, MRGP.py:929) and the
+// squared-mean term of MRGP.py:928 vanishes identically (the targets are inferred from the same statistics).
+template <int DY>
+__device__ __forceinline__ double layer_var_at(const EvalLayer &ly, int M, int r, double x) {
+    double f1, c2;
+    basis_seed(x, ly.inv2L[r], ly.rsqrtL[r], f1, c2);
+    double fm = 0.0, f = f1, v = 0.0;
+    const double *Cm = ly.cm2 + (size_t)r * M;
+    for (int i = 0; i < M; ++i) {
+        v = fma(f * Cm[i], f, v);
+        const double fn = fma(c2, f, -fm);
+        fm = f;
+        f = fn;
+    }
+    return v + ly.bias_var[r];
+}
+
+template <int DY>
+__global__ void k_eval_var_indexed(EvalArgs a) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= a.n) return;
+    const double x = a.x[n];
+    double total = 0.0;
+    for (int j = 0; j < a.n_layers; ++j) {
+        const EvalLayer &ly = a.layer[j];
+        const int r = find_region(ly.offsets, ly.R, n);
+        const int64_t first = ly.offsets[r];
+        total += layer_var_at<DY>(ly, a.M, r, x) + (double)(ly.offsets[r + 1] - first) / ly.noise_mean[r];
+        const double xf = a.x[first];
+        for (int jp = 0; jp < j; ++jp) {
+            const EvalLayer &lp = a.layer[jp];
+            total += layer_var_at<DY>(lp, a.M, find_region(lp.offsets, lp.R, first), xf);
+        }
+    }
+    a.out_var[n] = total;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -282,6 +282,16 @@ class Engine(object):
                                                 len(test_offsets), C.c_void_p(out.data_ptr())))
         return out.cpu().numpy()
 
+    def predict_var_indexed(self, x_test_norm, test_offsets):
+        torch = self.torch
+        xt = torch.as_tensor(np.ascontiguousarray(x_test_norm, dtype=np.float64).reshape(-1), device=self.device)
+        out = torch.empty((xt.shape[0],), dtype=torch.float64, device=self.device)
+        torch.cuda.synchronize(self.device)
+        ptrs, keep = _lib.offsets_arg(test_offsets)
+        self._ck(self.lib.mrgp_predict_var_indexed(self.handle, C.c_void_p(xt.data_ptr()), xt.shape[0], ptrs,
+                                                   len(test_offsets), C.c_void_p(out.data_ptr())))
+        return out.cpu().numpy()
+
     def predict_var(self, x_test_norm):
         torch = self.torch
         xt = torch.as_tensor(np.ascontiguousarray(x_test_norm, dtype=np.float64).reshape(-1), device=self.device)

@@ -207,6 +207,28 @@ def run_kats(name):
     print(name, 'done', flush=True)
 
 
+def run_predvar(name, x, y, n_basis, resolution, fi, n_sweeps, xt):
+    """Index-set form of get_central_moment2 / get_test_likelihood (MRGP.py:863-932).  The call overwrites the
+    latent functions of the model (MRGP.py:893-901), so it comes last."""
+    m = build(x, y, n_basis, resolution, fi)
+    for _ in range(n_sweeps):
+        if fi:
+            m._independent_fit()
+        else:
+            m._fit()
+    out = {'meta.N': x.shape[0], 'meta.M': n_basis, 'meta.resolution': resolution, 'meta.fi': int(fi),
+           'meta.sweeps': n_sweeps, 'x': x, 'y': y, 'pred.x': xt}
+    idx_t = R.IndexSetGenerator.IndexSetUniform(sample_length=xt.shape[0], resolution=resolution, divider=2)
+    yt = workloads.signal1(xt)[:, :, 0].T
+    out['pred.y'] = yt
+    out['pred.mean_indexed'] = m.get_predicted_mean(xt, index_set_obj=idx_t)
+    out['pred.var_global'] = m.get_central_moment2(xt)
+    out['pred.var_indexed'] = m.get_central_moment2(xt, index_set_obj=idx_t)
+    out['pred.test_likelihood_indexed'] = np.array(m.get_test_likelihood([xt, yt], index_set_obj=idx_t))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print(name, 'done', out['pred.var_indexed'][:3], float(out['pred.test_likelihood_indexed']), flush=True)
+
+
 JOBS = {
     'kats': lambda: run_kats('kats'),
     'c1_ci': lambda: run_sweeps('c1_ci', *workloads.workload1(32), 30, 5, False, [1, 3, 15],
@@ -220,6 +242,10 @@ JOBS = {
     'c2_fi': lambda: run_sweeps('c2_fi', *workloads.workload2(), 40, 7, True, [1, 3]),
     'n2000_ci': lambda: run_sweeps('n2000_ci', *workloads.workload1(2000), 30, 5, False, [1, 3]),
     'n2000_fi': lambda: run_sweeps('n2000_fi', *workloads.workload1(2000), 30, 5, True, [1, 3]),
+    'predvar_ci': lambda: run_predvar('predvar_ci', *workloads.workload1(600), 20, 3, False, 3,
+                                      np.atleast_2d(np.linspace(1, 3, 1000)).T),
+    'predvar_fi': lambda: run_predvar('predvar_fi', *workloads.workload1(600), 20, 3, True, 3,
+                                      np.atleast_2d(np.linspace(1, 3, 1000)).T),
     'n600_ci_snr_shared': lambda: run_sweeps('n600_ci_snr', *workloads.workload1(600), 20, 3, False, [1, 3],
                                              snr_ratio=10.),
 }

@@ -421,3 +421,23 @@ def test_series_batch_equals_separate_models(fi):
             assert np.array_equal(a[k], b[k]), (s, k)
     xt = np.atleast_2d(np.linspace(1, 3, 500)).T
     assert batch[1].get_predicted_mean(xt).shape == (500, 2)
+
+
+@pytest.mark.parametrize('name,fi', [('predvar_ci', False), ('predvar_fi', True)])
+def test_indexed_second_moment_and_test_likelihood_match_reference(name, fi):
+    """O1, index-set form (MRGP.py:863-932, 825-831) against the reference's own output."""
+    from cimrgp_b200 import IndexSetUniform
+    g = load(name)
+    m = build(g['x'], g['y'], int(g['meta.M']), int(g['meta.resolution']), fi)
+    m.fit(int(g['meta.sweeps']), None)
+    xt, yt = g['pred.x'], g['pred.y']
+    idx_t = IndexSetUniform(xt.shape[0], int(g['meta.resolution']), 2)
+    before = m._engine.state()
+    assert mismatch(m.get_predicted_mean(xt, index_set_obj=idx_t), g['pred.mean_indexed'], RTOL) is None
+    assert mismatch(m.get_central_moment2(xt), g['pred.var_global'], RTOL) is None
+    assert mismatch(m.get_central_moment2(xt, index_set_obj=idx_t), g['pred.var_indexed'], RTOL) is None
+    got = m.get_test_likelihood([xt, yt], index_set_obj=idx_t)
+    assert abs(got - float(g['pred.test_likelihood_indexed'])) <= RTOL * abs(float(g['pred.test_likelihood_indexed']))
+    after = m._engine.state()
+    for k in before:
+        assert np.array_equal(before[k], after[k]), k       # prediction leaves the model untouched
