@@ -995,7 +995,8 @@ FieldRef field_ref(mrgp_handle *h, int layer, int field) {
         if (layer != -1) return f;
         SharedDev &s = h->sh;
         switch (field) {
-            case 52: f = {s.omegaK + 64 * 64 + 32, 3}; break;   // MRGP_OMEGA_PROF builds: cycles of the Newton stages
+            case 52: f = {s.omegaK + 64 * 64 + 32, 3}; break;
+            case 53: f = {s.omegaK + 64 * 64 + 40, 5}; break;   // MRGP_OMEGA_PROF builds: cycles of the k_ard phases   // MRGP_OMEGA_PROF builds: cycles of the Newton stages
             case MRGP_F_AXIS_B: f = {s.axB, (int64_t)M * DY * DY}; break;
             case MRGP_F_AXIS_KAPPA: f = {s.axKappa, (int64_t)M * DY}; break;
             case MRGP_F_AXIS_RHO: f = {s.axRho, (int64_t)M * DY}; break;

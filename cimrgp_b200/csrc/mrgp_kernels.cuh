@@ -1068,6 +1068,13 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
     double *P = sm, *s_mean = P + M * M, *s_lmean = s_mean + M, *s_k = s_lmean + M, *s_shape = s_k + M, *s_scale = s_shape + M;
     double *s_B = s_scale + M, *s_C = s_B + 4 * M, *s_part = s_C + 4 * M;   // s_part: NW x M
     ts_begin(a.ts, a.layer * 4 + 3);
+#ifdef MRGP_OMEGA_PROF
+    long long pc[6];
+    pc[0] = clock64();
+#define ARD_PC(k) pc[k] = clock64()
+#else
+#define ARD_PC(k)
+#endif
     // every input is staged in shared memory by one wave of loads
     for (int t = tid; t < M * M; t += kOmegaThreads) P[t] = a.omega[t];   // the OLD omega mixes the ARD prior
     for (int t = tid; t < 4 * M; t += kOmegaThreads) {
@@ -1080,11 +1087,20 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
         s_scale[t] = a.primeScale[t];
     }
     for (int i = lane; i < M; i += 32) {   // sum_l m2 / S: the per-CTA partials of k_mid2, one slice of them per warp
+        double p[8];                         // (<= 64 partials: all loads of a lane are in flight together)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int q = warp + u * NW;
+            p[u] = (q < n_partials) ? a.ardPartial[q * M + i] : 0.0;
+        }
         double t = 0.0;
-        for (int q = warp; q < n_partials; q += NW) t += a.ardPartial[q * M + i];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t += p[u];
+        for (int q = warp + 8 * NW; q < n_partials; q += NW) t += a.ardPartial[q * M + i];
         s_part[warp * M + i] = t;
     }
     __syncthreads();
+    ARD_PC(1);
     if (tid < M) {
         const int i = tid;
         double beta2 = 0.0;
@@ -1106,6 +1122,7 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
         s_lmean[i] = lmean;
     }
     __syncthreads();
+    ARD_PC(2);
     for (int t = tid; t < M * M; t += kOmegaThreads) {
         const int i = t / M, k = t % M;
         const double *C = s_C + i * 4, *B = s_B + k * 4;
@@ -1116,22 +1133,34 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
     }
     // head of the scaling solve, done here by the whole block: row shift, column shift, exponentials.  The solve
     // (one warp, k_scale_warp) starts from the table K = exp(lw - rowmax - colmax), stored column-major, and the
-    // column shifts (row shifts cancel in the row normalisation).
+    // column shifts (row shifts cancel in the row normalisation).  One thread per row, then one per column: a serial
+    // chain of M maxima is shorter than the rounds of warp reductions it replaces.
     __syncthreads();
-    for (int i = warp; i < M; i += NW) {
+    ARD_PC(3);
+    double *s_rowmax = s_part, *s_colmax = s_part + M;   // the partial sums are no longer needed
+    if (tid < M) {
         double mx = -INFINITY;
-        for (int k = lane; k < M; k += 32) mx = fmax(mx, P[i * M + k]);
-        mx = warp_max(mx);
-        for (int k = lane; k < M; k += 32) P[i * M + k] -= mx;
+        for (int k = 0; k < M; ++k) mx = fmax(mx, P[tid * M + k]);
+        s_rowmax[tid] = mx;
     }
     __syncthreads();
-    for (int k = warp; k < M; k += NW) {
+    if (tid < M) {
         double mx = -INFINITY;
-        for (int i = lane; i < M; i += 32) mx = fmax(mx, P[i * M + k]);
-        mx = warp_max(mx);
-        for (int i = lane; i < M; i += 32) a.omegaK[k * M + i] = exp(P[i * M + k] - mx);
-        if (lane == 0) a.omegaK[64 * 64 + k] = mx;
+        for (int i = 0; i < M; ++i) mx = fmax(mx, P[i * M + tid] - s_rowmax[i]);
+        s_colmax[tid] = mx;
+        a.omegaK[64 * 64 + tid] = mx;
     }
+    __syncthreads();
+    ARD_PC(4);
+    for (int t = tid; t < M * M; t += kOmegaThreads) {
+        const int k = t / M, i = t % M;        // column-major output: coalesced stores
+        a.omegaK[t] = exp((P[i * M + k] - s_rowmax[i]) - s_colmax[k]);
+    }
+    ARD_PC(5);
+#ifdef MRGP_OMEGA_PROF
+    if (tid == 0)
+        for (int k = 0; k < 5; ++k) a.omegaK[64 * 64 + 40 + k] = (double)(pc[k + 1] - pc[k]);
+#endif
     ts_dbg(a.ts, a.layer, 0, false);   // debug slots: [0] = (k_ard begin, k_ard end)
     ts_dbg(a.ts, a.layer, 0, true);
 }
@@ -1424,7 +1453,7 @@ __global__ void __launch_bounds__(32, 1) k_scale_warp(RegionArgs a) {
             H[k + 1] = ((lane == k + 1) ? c : 0.0) - (a2 + a3) + 1.0 / (double)M;
         }
         // ---- Cholesky (right-looking, lane = row) fused with the forward substitution; the next pivot is formed
-        //      first in every step so that its reciprocal square root overlaps the rest of the rank-1 update
+        //      first in every step (one shuffle) so that its reciprocal square root overlaps the rank-1 update
 #ifdef MRGP_OMEGA_PROF
         const long long pc1 = clock64();
 #endif
@@ -1438,10 +1467,8 @@ __global__ void __launch_bounds__(32, 1) k_scale_warp(RegionArgs a) {
             H[k] *= di;                                               // l_ik for lanes i >= k (l_kk on lane k)
             double *cb = colbuf + (k & 1) * 32;                       // two buffers: no barrier between the steps
             cb[lane] = H[k];
-            if (k + 1 < M) {
-                H[k + 1] = fma(-H[k], __shfl_sync(0xffffffffu, H[k], k + 1), H[k + 1]);
-                piv = __shfl_sync(0xffffffffu, H[k + 1], k + 1);
-            }
+            if (k + 1 < M)   // the next pivot only needs its own row: h_jj - l_jk^2 on lane j = k + 1
+                piv = __shfl_sync(0xffffffffu, fma(-H[k], H[k], H[k + 1]), k + 1);
             const double yk = __shfl_sync(0xffffffffu, rhs, k) * di;
             if (lane == k) {
                 dinv = di;
@@ -1450,7 +1477,7 @@ __global__ void __launch_bounds__(32, 1) k_scale_warp(RegionArgs a) {
             if (lane > k) rhs = fma(-H[k], yk, rhs);
             __syncwarp();
 #pragma unroll
-            for (int j = k + 2; j < M; ++j) H[j] = fma(-H[k], cb[j], H[j]);   // broadcast loads of l_jk
+            for (int j = k + 1; j < M; ++j) H[j] = fma(-H[k], cb[j], H[j]);   // broadcast loads of l_jk
         }
 #ifdef MRGP_OMEGA_PROF
         const long long pc2 = clock64();

@@ -5,5 +5,6 @@ m = bench.make_model(1000000, 0)
 e = m._engine
 for s in range(12): e.sweep(1)
 e.synchronize()
-print('cycles H, chol+fwd, back+exp:', e.get(-1, 52, (3,)))
+print('Newton cycles H, chol+fwd, back+exp:', e.get(-1, 52, (3,)))
+print('k_ard cycles stage/partials, ard stats, table, rowmax, colmax+exp:', e.get(-1, 53, (5,)))
 print('iters', e.get(-1, 51, (10,)))
