@@ -4,7 +4,6 @@ public state) with the variational-inference sweep running on one B200 through l
 Same constructor arguments, same exceptions for the same misuse (MRGP.py:37-126), same meaning of every
 method.  What is NOT carried over (raises NotImplementedError with the reason): the GPy input-warp model
 (`adaptive_inputs=True` without an `input_model`; third-party GP),
-shared (non region-specific) noise or bias,
 dx > 1 and dy > 2 on the device.
 """
 import numpy as np
@@ -368,10 +367,10 @@ class MultiResolutionGaussianProcess(object):
             'scale_precision': lambda: e.get(j, F.F_SCALE_PRECISION, (R, M)),
             'scale_mean_zeta': lambda: list(e.get(j, F.F_ZETA, (R, M))),
             'scale_mean_y_tilde': lambda: list(np.swapaxes(e.get(j, F.F_YTILDE, (R, M, dy)), 1, 2)),
-            'noise_gamma_shape': lambda: e.get(j, F.F_NOISE_SHAPE, (R,)),
-            'noise_gamma_scale': lambda: e.get(j, F.F_NOISE_SCALE, (R,)),
-            'bias_normal_precision': lambda: e.get(j, F.F_BIAS_PRECISION, (R,)),
-            'bias_normal_mean': lambda: e.get(j, F.F_BIAS_MEAN, (R, dy)),
+            'noise_gamma_shape': lambda: self._shared(e.get(j, F.F_NOISE_SHAPE, (R,)), self.noise_region_specific),
+            'noise_gamma_scale': lambda: self._shared(e.get(j, F.F_NOISE_SCALE, (R,)), self.noise_region_specific),
+            'bias_normal_precision': lambda: self._shared(e.get(j, F.F_BIAS_PRECISION, (R,)), self.bias_region_specific),
+            'bias_normal_mean': lambda: self._shared(e.get(j, F.F_BIAS_MEAN, (R, dy)), self.bias_region_specific),
         }
         if self.forced_independence:
             g.update({
@@ -382,7 +381,8 @@ class MultiResolutionGaussianProcess(object):
                 'ard_gamma_shape': lambda: list(e.get(j, F.F_ARD_SHAPE, (R, M))),
                 'ard_gamma_scale': lambda: list(e.get(j, F.F_ARD_SCALE, (R, M))),
             })
-        return _View(self, g, dict(dy=dy, n_basis=M, n_regions=R, noise_region_specific=True, bias_region_specific=True))
+        return _View(self, g, dict(dy=dy, n_basis=M, n_regions=R, noise_region_specific=self.noise_region_specific,
+                                   bias_region_specific=self.bias_region_specific))
 
     def _stats_view(self, j):
         e, R, M, dy = self._engine, self.n_regions[j], self.n_basis, self.dy
@@ -391,10 +391,10 @@ class MultiResolutionGaussianProcess(object):
             'scale_axis_mean': lambda: list(np.swapaxes(e.get(j, F.F_A, (R, M, dy)), 1, 2)),
             'scale_moment2': lambda: list(e.get(j, F.F_M2, (R, M))),
             'scale_axis_central_moment2': lambda: list(e.get(j, F.F_CM2, (R, M))),
-            'noise_mean': lambda: list(e.get(j, F.F_NOISE_MEAN, (R,))),
-            'noise_log_mean': lambda: list(e.get(j, F.F_NOISE_LOG_MEAN, (R,))),
-            'bias_mean': lambda: list(e.get(j, F.F_BIAS_MEAN, (R, dy))),
-            'bias_var': lambda: list(e.get(j, F.F_BIAS_VAR, (R,))),
+            'noise_mean': lambda: self._shared(e.get(j, F.F_NOISE_MEAN, (R,)), self.noise_region_specific, True),
+            'noise_log_mean': lambda: self._shared(e.get(j, F.F_NOISE_LOG_MEAN, (R,)), self.noise_region_specific, True),
+            'bias_mean': lambda: self._shared(e.get(j, F.F_BIAS_MEAN, (R, dy)), self.bias_region_specific, True),
+            'bias_var': lambda: self._shared(e.get(j, F.F_BIAS_VAR, (R,)), self.bias_region_specific, True),
             'latent_f_mean': lambda: self._split(j, e.latent(j)[0]),
             'latent_f_var': lambda: self._split(j, e.latent(j)[1][:, None]),
         }
@@ -405,7 +405,16 @@ class MultiResolutionGaussianProcess(object):
                 'ard_log_mean': lambda: list(e.get(j, F.F_ARD_LOG_MEAN, (R, M))),
                 'omega': lambda: [np.ones((M, M)) / M for _ in range(R)],
             })
-        return _View(self, g, dict(dy=dy, n_basis=M, n_regions=R, noise_region_specific=True, bias_region_specific=True))
+        return _View(self, g, dict(dy=dy, n_basis=M, n_regions=R, noise_region_specific=self.noise_region_specific,
+                                   bias_region_specific=self.bias_region_specific))
+
+    @staticmethod
+    def _shared(per_region, region_specific, as_list=False):
+        """A posterior shared by the regions of a layer is stored once per region on the device (all entries equal)
+        and exposed with the reference's shape: a scalar / one (dy,) vector (Posteriors.py:17-25, Stats.py:29-49)."""
+        if region_specific:
+            return list(per_region) if as_list else per_region
+        return per_region[0]
 
     @property
     def posterior_obj(self):

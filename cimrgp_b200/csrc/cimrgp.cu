@@ -415,6 +415,9 @@ StreamArgs stream_args(mrgp_handle *h, int j) {
     a.bias_mean0 = d.bias_mean0;
     a.noise_shape0 = d.noise_shape0;
     a.noise_scale0 = d.noise_scale0;
+    a.noise_rs = h->cfg.noise_region_specific ? 1 : 0;
+    a.bias_rs = h->cfg.bias_region_specific ? 1 : 0;
+    a.ci = h->cfg.mode == MRGP_MODE_CI ? 1 : 0;
     a.bias_mean_out = d.bias_mean;
     a.bias_prev_out = d.bias_prev;
     a.bias_prec = d.bias_prec;
@@ -732,6 +735,8 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega, bool zero_T) {
     return MRGP_OK;
 }
 
+int do_bias_noise_shared(mrgp_handle *h, int j);
+
 int do_phase_b(mrgp_handle *h, int j, bool fuse_tail, int prop_override = -1) {
     const bool fi = h->cfg.mode == MRGP_MODE_FI;
     const bool infer = !fi && j > 0, latent = j > 0;
@@ -741,6 +746,16 @@ int do_phase_b(mrgp_handle *h, int j, bool fuse_tail, int prop_override = -1) {
     cudaError_t e = cudaErrorInvalidValue;
     DISPATCH_M(h->cfg.n_basis, e = launch_phase_b<MM>(h, a, infer, latent, prop));
     CK(e);
+    count(h);
+    return fuse_tail ? do_bias_noise_shared(h, j) : MRGP_OK;
+}
+
+// Second stage of the bias / noise update when noise or bias is shared by the regions of a layer.
+int do_bias_noise_shared(mrgp_handle *h, int j) {
+    if (h->cfg.noise_region_specific && h->cfg.bias_region_specific) return MRGP_OK;
+    StreamArgs a = stream_args(h, j);
+    k_bias_noise_shared<2><<<1, 256, 0, h->stream>>>(a);
+    CK(cudaGetLastError());
     count(h);
     return MRGP_OK;
 }
@@ -754,7 +769,7 @@ int do_bias_noise(mrgp_handle *h, int j) {
     k_bias_noise<2><<<std::max(1, std::min(32, (h->plan[j].R + 7) / 8)), kThreadsB, 0, h->stream>>>(a);
     CK(cudaGetLastError());
     count(h);
-    return MRGP_OK;
+    return do_bias_noise_shared(h, j);
 }
 
 // One exchange over peer memory: local dense sums -> arena slot, publish, reduce over the owning ranks -> h->xchg.
@@ -921,7 +936,7 @@ int do_stats_b(mrgp_handle *h, int j) {
     k_stats_b<2><<<(h->plan[j].R + 7) / 8, 256, 0, h->stream>>>(q);
     CK(cudaGetLastError());
     count(h);
-    return MRGP_OK;
+    return do_bias_noise_shared(h, j);
 }
 
 int sweep_once(mrgp_handle *h, bool fork_omega) {
@@ -1108,8 +1123,6 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     if (!basis_supported(cfg->n_basis)) return fail(h, MRGP_EINVAL, "n_basis = %d: compiled for 8, 20, 30, 40", cfg->n_basis);
     if (cfg->n_layers < 1 || cfg->n_layers > kMaxLayers) return fail(h, MRGP_EINVAL, "n_layers out of range");
     if (cfg->n_samples < 1) return fail(h, MRGP_EINVAL, "n_samples < 1");
-    if (!cfg->noise_region_specific || !cfg->bias_region_specific)
-        return fail(h, MRGP_EINVAL, "only region-specific noise and bias are implemented on the device");
     if (cfg->sample_begin < 0 || cfg->sample_end < cfg->sample_begin || cfg->sample_end > cfg->n_samples)
         return fail(h, MRGP_EINVAL, "bad sample range");
     h = new mrgp_handle();

@@ -83,6 +83,7 @@ struct StreamArgs {
     int32_t R, infer, fuse_tail, layer;
     unsigned long long *ts;
     const double *bias_prec0, *bias_mean0, *noise_shape0, *noise_scale0;
+    int32_t noise_rs, bias_rs, ci;   // noise / bias region specific (MRGP.py:27-28); ci or fi (Posteriors.py:113-211 vs 377-475)
     double *bias_mean_out, *bias_prev_out, *bias_prec, *bias_var, *noise_shape, *noise_scale, *noise_mean, *noise_log_mean, *yvar, *sumsB;
 };
 
@@ -225,6 +226,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_phi2sum(StreamArgs p) {
 // ------------------------------------------------------------------------------------------------
 template <int DY>
 __device__ __forceinline__ void bias_noise_region(const StreamArgs &p, int r, const double *sums) {
+    if (!(p.noise_rs && p.bias_rs)) {   // shared noise and / or bias: the sums of all regions first (k_bias_noise_shared)
+#pragma unroll
+        for (int d = 0; d < DY + 3; ++d) p.sumsB[(size_t)r * (DY + 3) + d] = sums[d];
+        return;
+    }
     const double n = (double)(p.offsets[r + 1] - p.offsets[r]);
     const double bp0 = p.bias_prec0[r];
     const double bp = bp0 + n;
@@ -1667,6 +1673,117 @@ __global__ void __launch_bounds__(kThreadsB) k_bias_noise(StreamArgs p) {
     int lpr = 32;
     while (lpr > 1 && (kThreadsB / lpr) < p.R) lpr >>= 1;
     bias_noise_all<DY, kThreadsB>(p, lpr, blockIdx.x, gridDim.x);
+}
+
+// Shared noise and / or shared bias (noise_region_specific / bias_region_specific False, MRGP.py:27-28): the three
+// other variants of Posteriors.py:81-211 (ci) and 345-475 (fi), from the per-region sums [sum r_d, sum |r|^2,
+// sum f_var, sum phi^2 cm2] left in sumsB.  A shared posterior is stored once per region (all entries equal), so
+// every consumer - P1, the ELBO (whose terms the reference also adds once per region, MRGP.py:426-475), prediction -
+// reads it as before.  y_var is multiplied by the region's sample count except where the reference does not
+// (Posteriors.py:138, 422).  One block; sums over the regions in a fixed order.
+template <int DY>
+__global__ void __launch_bounds__(256) k_bias_noise_shared(StreamArgs p) {
+    __shared__ double red[256];
+    __shared__ double sh[DY + 4];
+    const int tid = threadIdx.x, R = p.R;
+    auto block_sum = [&](double v) {
+        red[tid] = v;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) red[tid] += red[tid + o];
+            __syncthreads();
+        }
+        const double t = red[0];
+        __syncthreads();
+        return t;
+    };
+    const double n_all = (double)(p.offsets[R] - p.offsets[0]);
+    // ---- bias (Posteriors.py:81-110 / 345-374) --------------------------------------------------------------
+    if (!p.bias_rs) {
+        double S[DY];
+        for (int d = 0; d < DY; ++d) {
+            double v = 0.0;
+            for (int r = tid; r < R; r += 256) v += p.sumsB[(size_t)r * (DY + 3) + d];
+            S[d] = block_sum(v);
+        }
+        if (tid == 0) {
+            const double bp0 = p.bias_prec0[0], bp = bp0 + n_all;
+            double t3 = 0.0, t4 = 0.0;
+            for (int d = 0; d < DY; ++d) {
+                const double m0 = p.bias_mean0[d], m = (1.0 / bp) * (m0 * bp0 + S[d]);
+                sh[d] = m;
+                t3 += m0 * m0;
+                t4 += m * m;
+            }
+            sh[DY] = bp;
+            sh[DY + 1] = bp0 * t3;
+            sh[DY + 2] = bp * t4;
+        }
+        __syncthreads();
+    }
+    // ---- per region: bias posterior, the bracket of the noise scale -------------------------------------------
+    const bool times_n = !p.noise_rs || (p.ci ? !p.bias_rs : p.bias_rs);
+    double bracket_sum = 0.0;
+    for (int r = tid; r < R; r += 256) {
+        const double n = (double)(p.offsets[r + 1] - p.offsets[r]);
+        const double *sums = p.sumsB + (size_t)r * (DY + 3);
+        double bp, t3, t4;
+        if (p.bias_rs) {
+            const double bp0 = p.bias_prec0[r];
+            bp = bp0 + n;
+            t3 = t4 = 0.0;
+            for (int d = 0; d < DY; ++d) {
+                const double m0 = p.bias_mean0[(size_t)r * DY + d], m = (1.0 / bp) * (m0 * bp0 + sums[d]);
+                p.bias_prev_out[(size_t)r * DY + d] = p.bias_mean_out[(size_t)r * DY + d];
+                p.bias_mean_out[(size_t)r * DY + d] = m;
+                t3 += m0 * m0;
+                t4 += m * m;
+            }
+            t3 *= bp0;
+            t4 *= bp;
+        } else {
+            bp = sh[DY];
+            t3 = sh[DY + 1];
+            t4 = sh[DY + 2];
+            for (int d = 0; d < DY; ++d) {
+                p.bias_prev_out[(size_t)r * DY + d] = p.bias_mean_out[(size_t)r * DY + d];
+                p.bias_mean_out[(size_t)r * DY + d] = sh[d];
+            }
+        }
+        p.bias_prec[r] = bp;
+        p.bias_var[r] = 1.0 / bp;
+        const double yvar = p.infer ? 1.0 / p.noise_mean[r] : 0.0;
+        p.yvar[r] = yvar;
+        const double yv = times_n ? yvar * n : yvar;
+        double bracket;
+        if (!p.noise_rs && !p.bias_rs)
+            bracket = sums[DY] + sums[DY + 1] + sums[DY + 2] + yv;      // the bias terms enter once (Posteriors.py:189-211)
+        else
+            bracket = t3 - t4 + sums[DY] + sums[DY + 1] + sums[DY + 2] + yv;
+        if (p.noise_rs) {
+            const double shape = p.noise_shape0[r] + 0.5 * (double)DY * n;
+            const double scale = p.noise_scale0[r] + 0.5 * bracket;
+            p.noise_shape[r] = shape;
+            p.noise_scale[r] = scale;
+            p.noise_mean[r] = shape / scale;
+            p.noise_log_mean[r] = digamma(shape) - log(scale);
+        } else {
+            bracket_sum += bracket;
+        }
+    }
+    if (!p.noise_rs) {
+        double total = block_sum(bracket_sum);
+        if (!p.bias_rs) total += sh[DY + 1] - sh[DY + 2];
+        const double shape = p.noise_shape0[0] + 0.5 * (double)DY * n_all;
+        const double scale = p.noise_scale0[0] + 0.5 * total;
+        const double mean = shape / scale, lmean = digamma(shape) - log(scale);
+        for (int r = tid; r < R; r += 256) {
+            p.noise_shape[r] = shape;
+            p.noise_scale[r] = scale;
+            p.noise_mean[r] = mean;
+            p.noise_log_mean[r] = lmean;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -100,8 +100,8 @@ typedef struct mrgp_config {
     int32_t dy;                     /* output dimension (>= 2, MRGP.py:65-66; 2 supported)           */
     int32_t n_basis;                /* M (<= 48)                                                     */
     int32_t n_layers;               /* J = resolution + 1                                            */
-    int32_t noise_region_specific;  /* MRGP.py:27 (1 supported)                                      */
-    int32_t bias_region_specific;   /* MRGP.py:28 (1 supported)                                      */
+    int32_t noise_region_specific;  /* MRGP.py:27; 0 = one noise posterior per layer (stored once per region) */
+    int32_t bias_region_specific;   /* MRGP.py:28; 0 = one bias posterior per layer (stored once per region)  */
     int32_t device;                 /* CUDA device ordinal                                           */
     int32_t n_ctas;                 /* streaming grid size; 0 = one persistent CTA per SM            */
     int64_t sample_begin;           /* sample sharding (multi-GPU): this handle owns samples           */

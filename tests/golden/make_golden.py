@@ -246,6 +246,24 @@ JOBS = {
                                       np.atleast_2d(np.linspace(1, 3, 1000)).T),
     'predvar_fi': lambda: run_predvar('predvar_fi', *workloads.workload1(600), 20, 3, True, 3,
                                       np.atleast_2d(np.linspace(1, 3, 1000)).T),
+    'shared_ci_nb': lambda: run_sweeps('shared_ci_nb', *workloads.workload1(600), 20, 3, False, [1, 3],
+                                       noise_region_specific=True, bias_region_specific=False),
+    'shared_ci_sn': lambda: run_sweeps('shared_ci_sn', *workloads.workload1(600), 20, 3, False, [1, 3],
+                                       noise_region_specific=False, bias_region_specific=True),
+    'shared_ci_ss': lambda: run_sweeps('shared_ci_ss', *workloads.workload1(600), 20, 3, False, [1, 3],
+                                       noise_region_specific=False, bias_region_specific=False,
+                                       predict=np.atleast_2d(np.linspace(1, 3, 500)).T),
+    'shared_fi_nb': lambda: run_sweeps('shared_fi_nb', *workloads.workload1(600), 20, 3, True, [1, 3],
+                                       noise_region_specific=True, bias_region_specific=False),
+    'shared_fi_sn': lambda: run_sweeps('shared_fi_sn', *workloads.workload1(600), 20, 3, True, [1, 3],
+                                       noise_region_specific=False, bias_region_specific=True),
+    'shared_fi_ss': lambda: run_sweeps('shared_fi_ss', *workloads.workload1(600), 20, 3, True, [1, 3],
+                                       noise_region_specific=False, bias_region_specific=False,
+                                       predict=np.atleast_2d(np.linspace(1, 3, 500)).T),
+    'shared_ci_ss_elbo': lambda: run_elbo('shared_ci_ss_elbo', *workloads.workload1(600), 20, 3, 3,
+                                          noise_region_specific=False, bias_region_specific=False),
+    'shared_ci_nb_elbo': lambda: run_elbo('shared_ci_nb_elbo', *workloads.workload1(600), 20, 3, 3,
+                                          noise_region_specific=True, bias_region_specific=False),
     'n600_ci_snr_shared': lambda: run_sweeps('n600_ci_snr', *workloads.workload1(600), 20, 3, False, [1, 3],
                                              snr_ratio=10.),
 }

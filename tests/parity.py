@@ -60,9 +60,23 @@ def mask_degenerate(state, ref):
     return state, ref
 
 
-def compare(state, ref, rtol=1e-6):
+# a shared bias of an upper fi layer is a sum of residuals that cancel to roundoff (|y| ~ 1): compare it at that scale
+ATOL_ABS_SHARED = {'d': 1e-20, 'bias_mean': 1e-12}
+
+
+def compare(state, ref, rtol=1e-6, atol_abs=None):
     state, ref = mask_degenerate(state, ref)
-    assert_state_close(state, ref, rtol, skip=('kappa',), atol_abs=ATOL_ABS)
+    assert_state_close(state, ref, rtol, skip=('kappa',), atol_abs=ATOL_ABS if atol_abs is None else atol_abs)
     for key in ref:
         if key.endswith('kappa'):
             assert mismatch(state[key], ref[key], rtol, atol_scale=1e-12) is None, key
+
+
+def expand_shared(ref_state, like):
+    """Goldens of the shared noise / bias variants hold the reference's shapes (a scalar, one (dy,) vector per
+    layer); the oracle and the device store a shared posterior once per region.  Broadcast the golden."""
+    out = dict(ref_state)
+    for k, v in ref_state.items():
+        if k in like and np.shape(v) != np.shape(like[k]):
+            out[k] = np.broadcast_to(np.asarray(v), np.shape(like[k])).copy()
+    return out

@@ -87,9 +87,13 @@ def test_create_rejects_what_the_reference_rejects():
     bad[1][1] = 0
     lib, rc, h = _create(64, bad)
     assert rc == _lib.EINVAL
-    for kw in (dict(dy=3), dict(dx=2), dict(m=31), dict(noise=0), dict(bias=0)):
+    for kw in (dict(dy=3), dict(dx=2), dict(m=31)):
         lib, rc, h = _create(64, off, **kw)
         assert rc == _lib.EINVAL, kw
+    for kw in (dict(noise=0), dict(bias=0), dict(noise=0, bias=0)):      # shared noise / bias variants are accepted
+        lib, rc, h = _create(64, off, **kw)
+        assert rc == 0, kw
+        lib.mrgp_destroy(h)
 
 
 def test_no_gpu_means_no_compute():

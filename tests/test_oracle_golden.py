@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import mrgp_oracle as O
-from parity import assert_state_close, mismatch
+from parity import ATOL_ABS_SHARED, assert_state_close, expand_shared, mismatch
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
@@ -84,6 +84,13 @@ def test_kat_omega():
 CASES = [
     ('c1_ci', 'ci', None), ('c1_fi', 'fi', None), ('n2000_ci', 'ci', None), ('n2000_fi', 'fi', None),
     ('c2_ci', 'ci', None), ('c2_fi', 'fi', None), ('n600_ci_snr', 'ci', dict(snr_ratio=10.)),
+    # shared noise and / or bias (Posteriors.py:150-211, 414-475)
+    ('shared_ci_nb', 'ci', dict(noise_region_specific=True, bias_region_specific=False)),
+    ('shared_ci_sn', 'ci', dict(noise_region_specific=False, bias_region_specific=True)),
+    ('shared_ci_ss', 'ci', dict(noise_region_specific=False, bias_region_specific=False)),
+    ('shared_fi_nb', 'fi', dict(noise_region_specific=True, bias_region_specific=False)),
+    ('shared_fi_sn', 'fi', dict(noise_region_specific=False, bias_region_specific=True)),
+    ('shared_fi_ss', 'fi', dict(noise_region_specific=False, bias_region_specific=False)),
 ]
 
 
@@ -93,7 +100,7 @@ def test_sweeps_match_reference(name, mode, kw):
     x, y = g['x'], g['y']
     m = O.OracleMRGP(x, y, int(g['meta.M']), O.uniform_offsets(x.shape[0], int(g['meta.resolution']), 2),
                      mode=mode, **(kw or {}))
-    assert_state_close(m.state(), split(g, 'k0.'), 1e-13, skip=('kappa',))
+    assert_state_close(m.state(), expand_shared(split(g, 'k0.'), m.state()), 1e-13, skip=('kappa',))
     done = 0
     for k in g['meta.checkpoints']:
         for _ in range(int(k) - done):
@@ -101,8 +108,9 @@ def test_sweeps_match_reference(name, mode, kw):
         done = int(k)
         # kappa: only the unclamped eigenvalues enter the model; tiny trailing eigenvalues of rank-1 B
         # are roundoff (SURVEY.md §7 "roundoff-dependent branches"), compare them at absolute scale.
-        st, ref = m.state(), split(g, 'k%d.' % k)
-        assert_state_close(st, ref, RTOL, skip=('kappa',))
+        st = m.state()
+        ref = expand_shared(split(g, 'k%d.' % k), st)
+        assert_state_close(st, ref, RTOL, skip=('kappa',), atol_abs=ATOL_ABS_SHARED if name.startswith('shared') else None)
         for key in ref:
             if key.endswith('kappa'):
                 assert mismatch(st[key], ref[key], RTOL, atol_scale=1e-13) is None, key

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import mrgp_oracle as O
-from parity import ATOL_ABS, assert_state_close, compare, mask_degenerate, mismatch
+from parity import ATOL_ABS, ATOL_ABS_SHARED, assert_state_close, compare, expand_shared, mask_degenerate, mismatch
 import workloads
 
 pytestmark = pytest.mark.gpu
@@ -441,3 +441,45 @@ def test_indexed_second_moment_and_test_likelihood_match_reference(name, fi):
     after = m._engine.state()
     for k in before:
         assert np.array_equal(before[k], after[k]), k       # prediction leaves the model untouched
+
+
+SHARED = [('shared_ci_nb', False, True, False), ('shared_ci_sn', False, False, True), ('shared_ci_ss', False, False, False),
+          ('shared_fi_nb', True, True, False), ('shared_fi_sn', True, False, True), ('shared_fi_ss', True, False, False)]
+
+
+@pytest.mark.parametrize('name,fi,noise_rs,bias_rs', SHARED)
+def test_shared_noise_and_bias_variants_match_reference(name, fi, noise_rs, bias_rs):
+    """The three other variants of the bias / noise update (Posteriors.py:94-110, 150-211, 358-374, 414-475)."""
+    g = load(name)
+    m = build(g['x'], g['y'], int(g['meta.M']), int(g['meta.resolution']), fi, noise_region_specific=noise_rs,
+              bias_region_specific=bias_rs)
+    done = 0
+    for k in g['meta.checkpoints']:
+        m.fit(int(k) - done, None)
+        done = int(k)
+        st = m._engine.state()
+        compare(st, expand_shared(split(g, 'k%d.' % k), st), atol_abs=ATOL_ABS_SHARED)
+    # public shapes (Posteriors.py:17-25, Stats.py:29-49)
+    R1 = m.n_regions[1]
+    assert np.shape(m.posterior_obj[1].noise_gamma_shape) == ((R1,) if noise_rs else ())
+    assert np.shape(m.stats_obj[1].noise_mean) == ((R1,) if noise_rs else ())
+    assert np.shape(m.posterior_obj[1].bias_normal_mean) == ((R1, 2) if bias_rs else (2,))
+    assert np.shape(m.stats_obj[1].bias_var) == ((R1,) if bias_rs else ())
+    if 'pred.x' in g.files:
+        from cimrgp_b200 import IndexSetUniform
+        xt = g['pred.x']
+        assert mismatch(m.get_predicted_mean(xt), g['pred.mean_global'], RTOL) is None
+        idx_t = IndexSetUniform(xt.shape[0], int(g['meta.resolution']), 2)
+        assert mismatch(m.get_predicted_mean(xt, index_set_obj=idx_t), g['pred.mean_indexed'], RTOL) is None
+        assert mismatch(m.get_central_moment2(xt), g['pred.var_global'], RTOL) is None
+
+
+@pytest.mark.parametrize('name,noise_rs,bias_rs', [('shared_ci_ss_elbo', False, False), ('shared_ci_nb_elbo', True, False)])
+def test_elbo_of_shared_variants_matches_reference(name, noise_rs, bias_rs):
+    g = load(name)
+    n_iter = g['lower_bound'].shape[0]
+    m = build(g['x'], g['y'], int(g['meta.M']), int(g['meta.resolution']), False, noise_region_specific=noise_rs,
+              bias_region_specific=bias_rs)
+    m.fit(n_iter=n_iter, tol=1e-300, min_iter=n_iter)
+    assert mismatch(np.array(m.lower_bound_terms), g['terms'], RTOL) is None
+    assert mismatch(np.array(m.lower_bound_layer), g['lower_bound_layer'], RTOL) is None
