@@ -65,6 +65,10 @@ SIGNATURES = {
     'mrgp_interval_failures': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     'mrgp_learn_intervals': (C.c_int, [_P, C.c_int32]),
     'mrgp_sweep': (C.c_int, [_P, C.c_int32]),
+    'mrgp_group_create': (C.c_int, [C.POINTER(_P), C.c_int32, _P, C.POINTER(_P)]),
+    'mrgp_group_sweep': (C.c_int, [_P, C.c_int32]),
+    'mrgp_group_synchronize': (C.c_int, [_P]),
+    'mrgp_group_destroy': (None, [_P]),
     'mrgp_synchronize': (C.c_int, [_P]),
     'mrgp_elbo': (C.c_int, [_P, _D]),
     'mrgp_predict_mean': (C.c_int, [_P, _P, C.c_int64, _I64PP, C.c_int32, _P]),

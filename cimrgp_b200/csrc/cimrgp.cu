@@ -1563,6 +1563,129 @@ int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
     return MRGP_OK;
 }
 
+// ---- groups of independent models: one captured graph, the models as parallel branches ---------------------
+struct mrgp_group {
+    std::vector<mrgp_handle *> handles;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<int64_t> launches_per_sweep;
+    std::string error;
+};
+
+static int gfail(mrgp_group *g, int code, const char *what, cudaError_t e) {
+    if (g) g->error = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return code;
+}
+
+int mrgp_group_create(mrgp_handle *const *handles, int32_t n, void *cuda_stream, mrgp_group **out) {
+    if (!handles || !out || n < 1) return MRGP_EINVAL;
+    *out = nullptr;
+    for (int i = 0; i < n; ++i) {
+        mrgp_handle *h = handles[i];
+        int rc = check_ready(h, 0, true);
+        if (rc) return rc;
+        if (h->sharded) return fail(h, MRGP_EINVAL, "sharded handles cannot join a group");
+        if (h->cfg.device != handles[0]->cfg.device) return fail(h, MRGP_EINVAL, "all models of a group live on one device");
+        if ((rc = build_invariants(h))) return rc;
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(h, MRGP_ECUDA, "stream synchronisation failed");
+    }
+    mrgp_group *g = new mrgp_group();
+    g->handles.assign(handles, handles + n);
+    g->launches_per_sweep.assign(n, 0);
+    cudaError_t e;
+    if (cuda_stream) {
+        g->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            delete g;
+            return MRGP_ECUDA;
+        }
+        g->own_stream = true;
+    }
+    // the streams only shape the captured DAG (one branch per model); the replay does not use them
+    std::vector<cudaStream_t> tmp(n, nullptr);
+    std::vector<cudaEvent_t> done(n, nullptr);
+    cudaEvent_t start = nullptr;
+    int rc = MRGP_OK;
+    auto cleanup = [&]() {
+        for (auto s : tmp)
+            if (s) cudaStreamDestroy(s);
+        for (auto ev : done)
+            if (ev) cudaEventDestroy(ev);
+        if (start) cudaEventDestroy(start);
+    };
+    for (int i = 0; i < n && rc == MRGP_OK; ++i) {
+        if (cudaStreamCreateWithFlags(&tmp[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess)
+            rc = MRGP_ECUDA;
+    }
+    if (rc == MRGP_OK && cudaEventCreateWithFlags(&start, cudaEventDisableTiming) != cudaSuccess) rc = MRGP_ECUDA;
+    if (rc == MRGP_OK && (e = cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal)) != cudaSuccess)
+        rc = gfail(g, MRGP_ECUDA, "cudaStreamBeginCapture", e);
+    if (rc == MRGP_OK) {
+        cudaEventRecord(start, g->stream);
+        for (int i = 0; i < n; ++i) {
+            mrgp_handle *h = handles[i];
+            cudaStreamWaitEvent(tmp[i], start, 0);
+            cudaStream_t saved = h->stream;
+            h->stream = tmp[i];
+            h->launches_per_sweep = 0;
+            h->capturing = true;
+            const int r = sweep_once(h, true);
+            h->capturing = false;
+            h->stream = saved;
+            g->launches_per_sweep[i] = h->launches_per_sweep;
+            if (r && rc == MRGP_OK) rc = r;
+            cudaEventRecord(done[i], tmp[i]);
+            cudaStreamWaitEvent(g->stream, done[i], 0);
+        }
+        e = cudaStreamEndCapture(g->stream, &g->graph);
+        if (rc == MRGP_OK && e != cudaSuccess) rc = gfail(g, MRGP_ECUDA, "cudaStreamEndCapture", e);
+        if (rc == MRGP_OK && (e = cudaGraphInstantiate(&g->exec, g->graph, 0)) != cudaSuccess)
+            rc = gfail(g, MRGP_ECUDA, "cudaGraphInstantiate", e);
+    }
+    cleanup();
+    if (rc != MRGP_OK) {
+        if (g->exec) cudaGraphExecDestroy(g->exec);
+        if (g->graph) cudaGraphDestroy(g->graph);
+        if (g->own_stream) cudaStreamDestroy(g->stream);
+        delete g;
+        return rc;
+    }
+    *out = g;
+    return MRGP_OK;
+}
+
+int mrgp_group_sweep(mrgp_group *g, int32_t n_iter) {
+    if (!g || n_iter < 0) return MRGP_EINVAL;
+    for (int it = 0; it < n_iter; ++it) {
+        cudaError_t e = cudaGraphLaunch(g->exec, g->stream);
+        if (e != cudaSuccess) return gfail(g, MRGP_ECUDA, "cudaGraphLaunch", e);
+    }
+    for (size_t i = 0; i < g->handles.size(); ++i) {
+        g->handles[i]->launches += g->launches_per_sweep[i] * n_iter;
+        g->handles[i]->sweeps_done += n_iter;
+    }
+    return MRGP_OK;
+}
+
+int mrgp_group_synchronize(mrgp_group *g) {
+    if (!g) return MRGP_EINVAL;
+    cudaError_t e = cudaStreamSynchronize(g->stream);
+    return e == cudaSuccess ? MRGP_OK : gfail(g, MRGP_ECUDA, "cudaStreamSynchronize", e);
+}
+
+void mrgp_group_destroy(mrgp_group *g) {
+    if (!g) return;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+    delete g;
+}
+
 int mrgp_synchronize(mrgp_handle *h) {
     if (!h || !h->stream) return fail(h, MRGP_ESTATE, "no stream");
     CK(cudaStreamSynchronize(h->stream));

@@ -238,6 +238,18 @@ int mrgp_region_sums(mrgp_handle *h, int32_t layer, int32_t which);
 int mrgp_exchange_buffer(mrgp_handle *h, int32_t layer, int32_t which, void **dev_ptr, size_t *n_doubles);
 int mrgp_build_basis_stage(mrgp_handle *h, int32_t layer, int32_t stage, double interval_factor);
 
+/* ---- groups of independent models (BASELINE config 5: a batch of series) --------------------------------- */
+
+/* One sweep of every model of the group captured as parallel branches of ONE CUDA graph: a launch per group and
+ * iteration instead of one per model (the reference fits its models one after the other; they are independent).
+ * The models must be initialised, unsharded and on one device; their state is what mrgp_sweep would leave.
+ * cuda_stream: the stream the group graph is launched on (NULL: the group creates one).                      */
+typedef struct mrgp_group mrgp_group;
+int mrgp_group_create(mrgp_handle *const *handles, int32_t n, void *cuda_stream, mrgp_group **out);
+int mrgp_group_sweep(mrgp_group *g, int32_t n_iter);
+int mrgp_group_synchronize(mrgp_group *g);
+void mrgp_group_destroy(mrgp_group *g);
+
 /* ---- counters and micro-benchmarks ------------------------------------------------------------ */
 
 /* Number of kernels launched on the handle so far (for bench.py's gpu_launches). */

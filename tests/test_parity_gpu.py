@@ -397,8 +397,8 @@ def test_peer_exchange_between_processes(mode, world):
     assert len(oks) == world and 'MISMATCH' not in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 
-@pytest.mark.parametrize('fi', [False, True])
-def test_series_batch_equals_separate_models(fi):
+@pytest.mark.parametrize('fi,group_size', [(False, 4), (True, 4), (False, 0)])
+def test_series_batch_equals_separate_models(fi, group_size):
     """Config 5 front end: models carved out of one device allocation, sweeps interleaved over a stream pool, must
     give exactly the states of models built and fitted one by one (same launch geometry -> bit for bit)."""
     from cimrgp_b200 import LaplacianEigenpairs, MaternKernel, SeriesBatch, IndexSetUniform
@@ -410,8 +410,9 @@ def test_series_batch_equals_separate_models(fi):
         xs.append(x)
         ys.append(y)
     batch = SeriesBatch(xs, ys, M, res, LaplacianEigenpairs(), MaternKernel(nu=1, l=1, sf=1), forced_independence=fi,
-                        n_streams=3)
-    batch.fit(4)
+                        n_streams=3, group_size=group_size)
+    batch.fit(3)
+    batch.fit(1)
     for s in (0, 3, 5):
         m = MultiResolutionGaussianProcess([xs[s], ys[s]], M, IndexSetUniform(n, res, 2), LaplacianEigenpairs(),
                                            MaternKernel(nu=1, l=1, sf=1), forced_independence=fi, n_ctas=2)
