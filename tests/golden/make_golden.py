@@ -76,7 +76,7 @@ def build(x, y, n_basis, resolution, fi, adaptive=False, divider=2, **kw):
         train_xy=[x, y], n_basis=n_basis, index_set_obj=idx,
         basis_function_obj=R.KernelClass.LaplacianEigenpairs(),
         spectral_density_obj=R.KernelClass.MaternKernel(nu=1, l=1, sf=1),
-        adaptive_inputs=False, standard_normalized_inputs=True, basis_interval_obj=bi, interval_factor=1,
+        adaptive_inputs=kw.get('input_model') is not None, standard_normalized_inputs=True, basis_interval_obj=bi, interval_factor=1,
         forced_independence=fi, **kw)
 
 
@@ -264,6 +264,9 @@ JOBS = {
                                           noise_region_specific=False, bias_region_specific=False),
     'shared_ci_nb_elbo': lambda: run_elbo('shared_ci_nb_elbo', *workloads.workload1(600), 20, 3, 3,
                                           noise_region_specific=True, bias_region_specific=False),
+    'c2_ci_warp': lambda: run_sweeps('c2_ci_warp', *workloads.workload2(), 40, 7, False, [1, 3],
+                                     predict=np.atleast_2d(np.linspace(1, 4, 300)).T,
+                                     input_model=workloads.InterpInputModel(workloads.workload2()[0])),
     'n600_ci_snr_shared': lambda: run_sweeps('n600_ci_snr', *workloads.workload1(600), 20, 3, False, [1, 3],
                                              snr_ratio=10.),
 }

@@ -39,3 +39,17 @@ def workload2(seed=10):
     dy = 1 + 1 * np.random.random(y.shape)
     y = y + .5 * np.random.normal(0, dy)
     return x, y
+
+
+class InterpInputModel(object):
+    """Deterministic stand-in for the reference's GPy input-warp model (Inputs.py:22-49, RegressionInput.py:55-67;
+    GPy is absent): maps a normalised input to the warped coordinate z by interpolating the training pairs
+    (x_n, z_n), z = linspace(min x, max x, N) (Inputs.py:12).  SURVEY.md §8d, config 2 (ii)."""
+
+    def __init__(self, x_train):
+        xn = (x_train - np.mean(x_train, axis=0)) / np.std(x_train, axis=0)
+        self.xn = xn[:, 0].copy()
+        self.z = np.linspace(np.min(xn), np.max(xn), xn.shape[0])
+
+    def predict(self, x):
+        return np.atleast_2d(np.interp(np.asarray(x)[:, 0], self.xn, self.z)).T

@@ -484,3 +484,28 @@ def test_elbo_of_shared_variants_matches_reference(name, noise_rs, bias_rs):
     m.fit(n_iter=n_iter, tol=1e-300, min_iter=n_iter)
     assert mismatch(np.array(m.lower_bound_terms), g['terms'], RTOL) is None
     assert mismatch(np.array(m.lower_bound_layer), g['lower_bound_layer'], RTOL) is None
+
+
+def test_adaptive_inputs_with_an_injected_input_model_match_reference():
+    """adaptive_inputs=True trains on the warped coordinate z (Inputs.py:12, 50-51) and
+    routes test inputs through input_model.predict (MRGP.py:733-739); the GPy warp model itself is out of scope, a
+    deterministic interpolating model is injected on both sides."""
+    from cimrgp_b200 import IndexSetUniform, LaplacianEigenpairs, MaternKernel
+    from cimrgp_b200.MRGP import MultiResolutionGaussianProcess
+    g = load('c2_ci_warp')
+    x, y = g['x'], g['y']
+    m = MultiResolutionGaussianProcess(
+        train_xy=[x, y], n_basis=int(g['meta.M']), index_set_obj=IndexSetUniform(x.shape[0], int(g['meta.resolution']), 2),
+        basis_function_obj=LaplacianEigenpairs(), spectral_density_obj=MaternKernel(nu=1, l=1, sf=1),
+        adaptive_inputs=True, standard_normalized_inputs=True, input_model=workloads.InterpInputModel(x))
+    compare(m._engine.state(), split(g, 'k0.'))
+    done = 0
+    for k in g['meta.checkpoints']:
+        m.fit(int(k) - done, None)
+        done = int(k)
+        compare(m._engine.state(), split(g, 'k%d.' % k))
+    xt = g['pred.x']
+    assert mismatch(m.get_predicted_mean(xt), g['pred.mean_global'], RTOL) is None
+    idx_t = IndexSetUniform(xt.shape[0], int(g['meta.resolution']), 2)
+    assert mismatch(m.get_predicted_mean(xt, index_set_obj=idx_t), g['pred.mean_indexed'], RTOL) is None
+    assert mismatch(m.get_central_moment2(xt), g['pred.var_global'], RTOL) is None
