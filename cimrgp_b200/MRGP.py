@@ -216,10 +216,6 @@ class MultiResolutionGaussianProcess(object):
             self._engine.sweep(n_iter)      # MRGP.py:400-401: no bound, no early stop in fi mode
             self._engine.synchronize()
             return
-        if self.adaptive_basis_intervals:
-            raise NotImplementedError('fit with a tolerance needs the lower bound, which the device path does not '
-                                      'keep under adaptive basis intervals; use fit(n_iter, None) as the '
-                                      "reference's own scripts do (scripts/tests/ciMRGP_vs_fiMRGP.py:61)")
         if n_iter < min_iter:
             min_iter = n_iter
         for iter_ in range(1, n_iter + 1):

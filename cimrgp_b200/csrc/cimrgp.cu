@@ -43,6 +43,7 @@ struct LayerDev {
     // static
     double *L = nullptr, *inv2L = nullptr, *rsqrtL = nullptr, *lam = nullptr, *S = nullptr, *d = nullptr, *absx = nullptr;
     double *bias_prev = nullptr, *brent = nullptr, *trial_inv2L = nullptr, *trial_rsqrtL = nullptr, *wq = nullptr;
+    double *inv2L_old = nullptr, *rsqrtL_old = nullptr, *sumsE = nullptr;   // adaptive intervals: basis of the step's targets, ELBO sums
     bool adaptive = false;
     int32_t ad_use_prior = 1;
     double ad_lo = 1.0, ad_hi = 1.2;
@@ -314,6 +315,9 @@ size_t carve(mrgp_handle *h, char *base) {
         d.trial_inv2L = c.take<double>(R);
         d.trial_rsqrtL = c.take<double>(R);
         d.wq = c.take<double>(RM);
+        d.inv2L_old = c.take<double>(R);
+        d.rsqrtL_old = c.take<double>(R);
+        d.sumsE = c.take<double>(R * (DY + 3));
         d.prec = c.take<double>(RM);
         d.zeta = c.take<double>(RM);
         d.ytil = c.take<double>(RM * DY);
@@ -807,6 +811,18 @@ cudaError_t launch_objective(mrgp_handle *h, const IntervalArgs &q, bool infer, 
     return cudaGetLastError();
 }
 
+template <int M>
+cudaError_t launch_elbo_sums(mrgp_handle *h, const IntervalArgs &q, bool infer, bool latent) {
+    dim3 grid(h->n_ctas), block(kThreads);
+    if (infer)
+        k_adaptive_elbo_sums<2, M, true, true><<<grid, block, 0, h->stream>>>(q);
+    else if (latent)
+        k_adaptive_elbo_sums<2, M, false, true><<<grid, block, 0, h->stream>>>(q);
+    else
+        k_adaptive_elbo_sums<2, M, false, false><<<grid, block, 0, h->stream>>>(q);
+    return cudaGetLastError();
+}
+
 // B1: BasisInterval.learn for one layer (BasisInterval.py:18-134), then the rebuild of lambda, S and sum phi^2
 // (MRGP.py:640-641).  ci mode only (MRGP.py:108-109 switches it off for fi).
 int do_learn_intervals(mrgp_handle *h, int j) {
@@ -854,6 +870,9 @@ int do_learn_intervals(mrgp_handle *h, int j) {
     }
     k_brent_finish<<<(lp.R + 127) / 128, 128, 0, h->stream>>>(b, d.L, h->brent_fail);
     CK(cudaGetLastError());
+    // the targets of this step were inferred with the current basis: keep it for the lower bound
+    CK(cudaMemcpyAsync(d.inv2L_old, d.inv2L, lp.R * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(d.rsqrtL_old, d.rsqrtL, lp.R * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     RegionArgs ra = region_args(h, j);
     ra.L_given = 1;
     k_region_setup<<<(lp.R + 7) / 8, 256, 0, h->stream>>>(ra);
@@ -865,6 +884,24 @@ int do_learn_intervals(mrgp_handle *h, int j) {
     k_reduce_d<<<lp.R, 64, 0, h->stream>>>(ra);
     CK(cudaGetLastError());
     count(h, 4);
+    // data-term sums of the lower bound with the re-learnt basis (before the propagation overwrites g, h)
+    {
+        IntervalArgs qe{};
+        qe.s = stream_args(h, j);
+        qe.trial_inv2L = d.inv2L_old;
+        qe.trial_rsqrtL = d.rsqrtL_old;
+        qe.w = nullptr;
+        qe.bias_old = d.bias_prev;
+        cudaError_t ee = cudaErrorInvalidValue;
+        DISPATCH_M(M, ee = launch_elbo_sums<MM>(h, qe, infer, latent));
+        CK(ee);
+        StreamArgs se = stream_args(h, j);
+        se.sums_only = 1;
+        se.sumsB = d.sumsE;
+        k_bias_noise<2><<<std::max(1, std::min(32, (lp.R + 7) / 8)), kThreadsB, 0, h->stream>>>(se);
+        CK(cudaGetLastError());
+        count(h, 2);
+    }
     return MRGP_OK;
 }
 
@@ -1702,11 +1739,12 @@ int mrgp_elbo(mrgp_handle *h, double *out_host) {
     if (rc) return rc;
     if (!out_host) return fail(h, MRGP_EINVAL, "null argument");
     if (h->cfg.mode != MRGP_MODE_CI) return fail(h, MRGP_EINVAL, "the lower bound is defined for ci mode only (MRGP.py:378-401)");
-    for (int j = 0; j < h->cfg.n_layers; ++j)
-        if (h->dev[j].adaptive)
-            return fail(h, MRGP_ESTATE, "the lower bound is not kept with adaptive intervals: its data sums belong to the basis before the interval update");
     std::vector<RegionArgs> args(h->cfg.n_layers);
-    for (int j = 0; j < h->cfg.n_layers; ++j) args[j] = region_args(h, j);
+    for (int j = 0; j < h->cfg.n_layers; ++j) {
+        args[j] = region_args(h, j);
+        // adaptive intervals: the data sums with the re-learnt basis (MRGP.py:535-569 reads phi_x after MRGP.py:640)
+        if (h->dev[j].adaptive && h->sweeps_done > 0) args[j].sumsB = h->dev[j].sumsE;
+    }
     CK(cudaMemcpyAsync(h->elbo_args, args.data(), args.size() * sizeof(RegionArgs), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // args is a local
     k_elbo<2><<<h->cfg.n_layers, 256, 0, h->stream>>>(h->elbo_args, h->elbo_out);

@@ -83,6 +83,7 @@ struct StreamArgs {
     int32_t R, infer, fuse_tail, layer;
     unsigned long long *ts;
     const double *bias_prec0, *bias_mean0, *noise_shape0, *noise_scale0;
+    int32_t sums_only;               // bias_noise_*: only store the per-region sums in sumsB
     int32_t noise_rs, bias_rs, ci;   // noise / bias region specific (MRGP.py:27-28); ci or fi (Posteriors.py:113-211 vs 377-475)
     double *bias_mean_out, *bias_prev_out, *bias_prec, *bias_var, *noise_shape, *noise_scale, *noise_mean, *noise_log_mean, *yvar, *sumsB;
 };
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_phi2sum(StreamArgs p) {
 // ------------------------------------------------------------------------------------------------
 template <int DY>
 __device__ __forceinline__ void bias_noise_region(const StreamArgs &p, int r, const double *sums) {
-    if (!(p.noise_rs && p.bias_rs)) {   // shared noise and / or bias: the sums of all regions first (k_bias_noise_shared)
+    if (p.sums_only || !(p.noise_rs && p.bias_rs)) {   // shared noise and / or bias: the sums of all regions first (k_bias_noise_shared)
 #pragma unroll
         for (int d = 0; d < DY + 3; ++d) p.sumsB[(size_t)r * (DY + 3) + d] = sums[d];
         return;
@@ -1884,6 +1885,96 @@ __global__ void __launch_bounds__(kThreads) k_interval_objective(IntervalArgs q)
         if (sg.flush) {
             block_reduce_small<1, false>(acc, sRed, p.part + (size_t)sg.run * p.part_stride);
             acc[0] = 0.0;
+        }
+    }
+}
+
+// Lower bound under adaptive intervals (MRGP.py:535-569 after MRGP.py:632-641): the data term is evaluated with the
+// RE-LEARNT basis of the layer while its targets were inferred with the basis of the beginning of the step
+// (LatentOutputs.py:20-49).  One pass per adaptive layer, after the rebuild and before the propagation:
+//   r = target - Phi_new A^T - fbar,  target = Phi_old A_prev^T + b_old + fbar (or y on layer 0);
+//   partial = [sum r_d, sum |r|^2, sum f_var, sum_i phi_new,i^2 cm2_i]   -> per-region sums for k_elbo.
+template <int DY, int M, bool INFER, bool LATENT>
+__global__ void __launch_bounds__(kThreads) k_adaptive_elbo_sums(IntervalArgs q) {
+    const StreamArgs &p = q.s;
+    __shared__ double sA[M * DY], sAo[INFER ? M * DY : 1], sW[M], sScal[5 + 3 * DY], sRed[64];
+    const int tid = threadIdx.x;
+    double acc[DY + 3];
+#pragma unroll
+    for (int d = 0; d < DY + 3; ++d) acc[d] = 0.0;
+    const int s0 = p.cta_seg[blockIdx.x], s1 = p.cta_seg[blockIdx.x + 1];
+    for (int s = s0; s < s1; ++s) {
+        const Segment sg = p.segs[s];
+        __syncthreads();
+        if (tid < M * DY) {
+            sA[tid] = p.A[(size_t)sg.region * (M * DY) + tid];
+            if (INFER) sAo[tid] = p.A_prev[(size_t)sg.region * (M * DY) + tid];
+        }
+        if (tid < M) sW[tid] = p.cm2[(size_t)sg.region * M + tid];
+        if (tid == 0) {
+            sScal[0] = p.inv2L[sg.region];              // re-learnt interval
+            sScal[1] = p.rsqrtL[sg.region];
+            sScal[2] = q.trial_inv2L[sg.region];        // here: the interval of the beginning of the step
+            sScal[3] = q.trial_rsqrtL[sg.region];
+            sScal[4] = LATENT ? p.pbias_var[sg.parent] : 0.0;
+        }
+        if (tid < DY) {
+            sScal[5 + tid] = q.bias_old[(size_t)sg.region * DY + tid];             // bias of the targets
+            sScal[5 + DY + tid] = LATENT ? p.pbias[(size_t)sg.parent * DY + tid] : 0.0;
+        }
+        __syncthreads();
+        const double ni2L = sScal[0], nrs = sScal[1], oi2L = sScal[2], ors = sScal[3], pbv = sScal[4];
+        const int64_t end = sg.start + sg.len;
+        for (int64_t n = sg.start + tid; n < end; n += kThreads) {
+            asm volatile("" ::: "memory");
+            const double x = p.x[n];
+            double f1, c2;
+            basis_seed(x, ni2L, nrs, f1, c2);
+            double fm = 0.0, f = f1, e[DY], v = 0.0;
+#pragma unroll
+            for (int d = 0; d < DY; ++d) e[d] = 0.0;
+#pragma unroll 5
+            for (int i = 0; i < M; ++i) {
+#pragma unroll
+                for (int d = 0; d < DY; ++d) e[d] = fma(f, sA[i * DY + d], e[d]);
+                v = fma(f * sW[i], f, v);
+                const double fn = fma(c2, f, -fm);
+                fm = f;
+                f = fn;
+            }
+            double eo[DY];
+#pragma unroll
+            for (int d = 0; d < DY; ++d) eo[d] = 0.0;
+            if (INFER) {
+                basis_seed(x, oi2L, ors, f1, c2);
+                fm = 0.0;
+                f = f1;
+#pragma unroll 5
+                for (int i = 0; i < M; ++i) {
+#pragma unroll
+                    for (int d = 0; d < DY; ++d) eo[d] = fma(f, sAo[i * DY + d], eo[d]);
+                    const double fn = fma(c2, f, -fm);
+                    fm = f;
+                    f = fn;
+                }
+            }
+            double rr = 0.0;
+#pragma unroll
+            for (int d = 0; d < DY; ++d) {
+                const double fb = LATENT ? p.g[n * DY + d] + sScal[5 + DY + d] : 0.0;
+                const double target = INFER ? eo[d] + (sScal[5 + d] + fb) : p.y[n * DY + d];
+                const double r = (target - e[d]) - fb;
+                acc[d] += r;
+                rr = fma(r, r, rr);
+            }
+            acc[DY] += rr;
+            acc[DY + 1] += LATENT ? p.h[n] + pbv : 0.0;
+            acc[DY + 2] += v;
+        }
+        if (sg.flush) {
+            block_reduce_small<DY + 3, false>(acc, sRed, p.part + (size_t)sg.run * p.part_stride);
+#pragma unroll
+            for (int d = 0; d < DY + 3; ++d) acc[d] = 0.0;
         }
     }
 }

@@ -267,6 +267,8 @@ JOBS = {
     'c2_ci_warp': lambda: run_sweeps('c2_ci_warp', *workloads.workload2(), 40, 7, False, [1, 3],
                                      predict=np.atleast_2d(np.linspace(1, 4, 300)).T,
                                      input_model=workloads.InterpInputModel(workloads.workload2()[0])),
+    'c1_ci_adaptive_elbo': lambda: run_elbo('c1_ci_adaptive_elbo', *workloads.workload1(32), 30, 5, 3, adaptive=True),
+    'n600_ci_adaptive_elbo': lambda: run_elbo('n600_ci_adaptive_elbo', *workloads.workload1(600), 20, 3, 3, adaptive=True),
     'n600_ci_snr_shared': lambda: run_sweeps('n600_ci_snr', *workloads.workload1(600), 20, 3, False, [1, 3],
                                              snr_ratio=10.),
 }

@@ -115,8 +115,6 @@ def test_adaptive_intervals_match_reference_golden():
         done = int(k)
         compare(m._engine.state(), split(g, 'k%d.' % k))
     assert m._engine.interval_failures() == 0
-    with pytest.raises(NotImplementedError):
-        m.fit(2, 1e-3)
 
 
 @pytest.mark.parametrize('use_prior', [True, False])
@@ -509,3 +507,17 @@ def test_adaptive_inputs_with_an_injected_input_model_match_reference():
     idx_t = IndexSetUniform(xt.shape[0], int(g['meta.resolution']), 2)
     assert mismatch(m.get_predicted_mean(xt, index_set_obj=idx_t), g['pred.mean_indexed'], RTOL) is None
     assert mismatch(m.get_central_moment2(xt), g['pred.var_global'], RTOL) is None
+
+
+@pytest.mark.parametrize('name', ['c1_ci_adaptive_elbo', 'n600_ci_adaptive_elbo'])
+def test_elbo_under_adaptive_intervals_matches_reference(name):
+    """fit(n_iter, tol) with BasisInterval: the data term of the bound uses the re-learnt basis of every layer while
+    its targets were inferred with the basis of the beginning of the step (MRGP.py:535-569 after :632-641)."""
+    from cimrgp_b200 import BasisInterval
+    g = load(name)
+    n_iter = g['lower_bound'].shape[0]
+    m = build(g['x'], g['y'], int(g['meta.M']), int(g['meta.resolution']), False,
+              basis_interval_obj=BasisInterval(opt_interval_factor=(1, 1.2)))
+    m.fit(n_iter=n_iter, tol=1e-300, min_iter=n_iter)
+    assert mismatch(np.array(m.lower_bound_terms), g['terms'], RTOL) is None
+    assert mismatch(np.array(m.lower_bound_layer), g['lower_bound_layer'], RTOL) is None
