@@ -52,7 +52,7 @@ struct LayerDev {
     double *noise_shape = nullptr, *noise_scale = nullptr, *noise_shape0 = nullptr, *noise_scale0 = nullptr;
     double *noise_mean = nullptr, *noise_log_mean = nullptr;
     double *bias_prec = nullptr, *bias_prec0 = nullptr, *bias_mean = nullptr, *bias_mean0 = nullptr, *bias_var = nullptr;
-    double *yvar = nullptr, *sumsB = nullptr, *bcontrib = nullptr;
+    double *yvar = nullptr, *sumsB = nullptr, *bcontrib = nullptr, *wcontrib = nullptr;
     // fi: per-region axis / ARD
     double *axB = nullptr, *axKappa = nullptr, *axRho = nullptr, *axLogC = nullptr, *axCov = nullptr;
     double *ardShape = nullptr, *ardScale = nullptr, *ardMean = nullptr, *ardLogMean = nullptr;
@@ -71,7 +71,7 @@ struct SharedDev {
     double *axB = nullptr, *axKappa = nullptr, *axRho = nullptr, *axLogC = nullptr, *axCov = nullptr;
     double *ardShape = nullptr, *ardScale = nullptr, *ardMean = nullptr, *ardLogMean = nullptr;
     double *omega = nullptr, *logOmegaHat = nullptr, *omegaIters = nullptr, *ardPartial = nullptr, *omegaEta = nullptr, *omegaWarm = nullptr, *omegaK = nullptr;
-    double *primeB = nullptr, *primeLogC = nullptr, *primeShape = nullptr, *primeScale = nullptr, *primeSk = nullptr;
+    double *primeB = nullptr, *primeLogC = nullptr, *primeShape = nullptr, *primeScale = nullptr, *primeSk = nullptr, *skTag = nullptr;
     double *priorB = nullptr, *priorLogC = nullptr, *priorShape = nullptr, *priorScale = nullptr;
 };
 
@@ -102,7 +102,7 @@ struct mrgp_handle {
     unsigned int *done_counter = nullptr, *mid_sync = nullptr;
     cudaStream_t stream = nullptr, side = nullptr;
     bool own_stream = false;
-    std::vector<cudaEvent_t> ev_fork, ev_join, ev_ard;
+    std::vector<cudaEvent_t> ev_fork, ev_join, ev_ard, ev_mid2;
     cudaEvent_t ev_prefetch = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
@@ -339,6 +339,7 @@ size_t carve(mrgp_handle *h, char *base) {
         d.yvar = c.take<double>(R);
         d.sumsB = c.take<double>(R * (DY + 3));
         d.bcontrib = c.take<double>(std::max<size_t>(RM * 3, 48 * 160));
+        d.wcontrib = c.take<double>((size_t)48 * 192);
         if (fi) {
             d.axB = c.take<double>(RM * DY * DY);
             d.axKappa = c.take<double>(RM * DY);
@@ -372,7 +373,8 @@ size_t carve(mrgp_handle *h, char *base) {
     s.primeLogC = c.take<double>(M);
     s.primeShape = c.take<double>(M);
     s.primeScale = c.take<double>(M);
-    s.primeSk = c.take<double>(M);
+    s.primeSk = c.take<double>(3 * 64);   // k-only terms of log omega_hat: slots for odd / even layers and layer 0
+    s.skTag = c.take<double>(4);
     s.priorB = c.take<double>((size_t)M * DY * DY);
     s.priorLogC = c.take<double>(M);
     s.priorShape = c.take<double>(M);
@@ -478,6 +480,7 @@ RegionArgs region_args(mrgp_handle *h, int j) {
     a.yvar = d.yvar;
     a.sumsB = d.sumsB;
     a.bcontrib = d.bcontrib;
+    a.wcontrib = d.wcontrib;
     if (fi) {
         a.axB = d.axB;
         a.axKappa = d.axKappa;
@@ -511,6 +514,7 @@ RegionArgs region_args(mrgp_handle *h, int j) {
     a.primeShape = s.primeShape;
     a.primeScale = s.primeScale;
     a.primeSk = s.primeSk;
+    a.skTag = s.skTag;
     a.priorB = s.priorB;
     a.priorLogC = s.priorLogC;
     a.priorShape = s.priorShape;
@@ -690,12 +694,28 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega, bool zero_T) {
         const int items_cta = std::min(rpc, 32) * M;
         int lpi = 1;
         while (lpi < 32 && lpi * 2 <= mr && lpi * 2 * items_cta <= kMidThreads) lpi *= 2;
-        const int nvp = (M * 3 + 31) & ~31;
-        const size_t smem1 = (size_t)(32 * M * 4 + nvp) * sizeof(double);
+        const int nvp = (M * 3 + 31) & ~31, nvwp = (M * 4 + 31) & ~31;
+        const size_t smem1 = (size_t)(2 * 32 * M * 4 + nvp + nvwp) * sizeof(double);
         CK(set_smem(k_mid1<2>, smem1));
         k_mid1<2><<<nb, kMidThreads, smem1, h->stream>>>(a, lpi, rpc);
         CK(cudaGetLastError());
         count(h);
+        n_partials = nb;
+        // The critical chain of the sweep is omega(j-1) -> axis / ARD update and table (k_ard) -> omega(j): k_ard only
+        // needs the region sums of k_mid1, so it is forked here and runs beside k_mid2 (S2 of the regions).
+        cudaStream_t st = h->stream;
+        if (fork_omega) {
+            CK(cudaEventRecord(h->ev_fork[j], h->stream));
+            CK(cudaStreamWaitEvent(h->side, h->ev_fork[j], 0));
+            st = h->side;
+        }
+        const size_t smem = omega_smem_doubles(M) * sizeof(double);
+        if (fork_omega) {
+            CK(set_smem(k_ard, smem));
+            k_ard<<<1, kOmegaThreads, smem, st>>>(a, n_partials);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(h->ev_ard[j], h->side));
+        }
         int nb2 = std::min(48, lp.R);
         const int rpc2 = (lp.R + nb2 - 1) / nb2;
         nb2 = (lp.R + rpc2 - 1) / rpc2;
@@ -705,20 +725,15 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega, bool zero_T) {
         k_mid2<2><<<nb2, kMidThreads, smem2, h->stream>>>(a, rpc2, nb);
         CK(cudaGetLastError());
         count(h);
-        n_partials = nb2;
-    }
-    {
-        cudaStream_t st = h->stream;
         if (fork_omega) {
-            CK(cudaEventRecord(h->ev_fork[j], h->stream));
-            CK(cudaStreamWaitEvent(h->side, h->ev_fork[j], 0));
-            st = h->side;
+            // k_scale_warp overwrites omega, which k_mid2 reads
+            CK(cudaEventRecord(h->ev_mid2[j], h->stream));
+            CK(cudaStreamWaitEvent(h->side, h->ev_mid2[j], 0));
+        } else {
+            CK(set_smem(k_ard, smem));
+            k_ard<<<1, kOmegaThreads, smem, st>>>(a, n_partials);
+            CK(cudaGetLastError());
         }
-        const size_t smem = omega_smem_doubles(M) * sizeof(double);
-        CK(set_smem(k_ard, smem));
-        k_ard<<<1, kOmegaThreads, smem, st>>>(a, n_partials);
-        CK(cudaGetLastError());
-        if (fork_omega) CK(cudaEventRecord(h->ev_ard[j], h->side));
         if (h->omega_warp && M == 30) {
             CK(cudaFuncSetAttribute(k_scale_warp<30>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             k_scale_warp<30><<<1, 32, 0, st>>>(a);
@@ -1240,6 +1255,7 @@ void mrgp_destroy(mrgp_handle *h) {
     for (auto e : h->ev_fork) cudaEventDestroy(e);
     for (auto e : h->ev_join) cudaEventDestroy(e);
     for (auto e : h->ev_ard) cudaEventDestroy(e);
+    for (auto e : h->ev_mid2) cudaEventDestroy(e);
     if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
     for (int q = 0; q < kMaxRanks; ++q)
         if (h->comm.opened[q]) cudaIpcCloseMemHandle(h->comm.peer_base[q]);
@@ -1274,10 +1290,12 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
         h->ev_fork.resize(h->cfg.n_layers);
         h->ev_join.resize(h->cfg.n_layers);
         h->ev_ard.resize(h->cfg.n_layers);
+        h->ev_mid2.resize(h->cfg.n_layers);
         for (int j = 0; j < h->cfg.n_layers; ++j) {
             CK(cudaEventCreateWithFlags(&h->ev_fork[j], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&h->ev_join[j], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&h->ev_ard[j], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_mid2[j], cudaEventDisableTiming));
         }
     }
     h->ws = static_cast<char *>(dev_ptr);
@@ -1504,6 +1522,10 @@ int mrgp_set_state(mrgp_handle *h, int32_t layer, int32_t field, const double *s
     if (!f.ptr || f.n <= 0) return fail(h, MRGP_EINVAL, "unknown field %d for layer %d", field, layer);
     if ((int64_t)n_elems != f.n) return fail(h, MRGP_EINVAL, "field %d has %lld elements, caller passed %zu", field, (long long)f.n, n_elems);
     CK(cudaMemcpyAsync(f.ptr, src_host, (size_t)f.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->sh.skTag) {   // terms prepared from the shared posterior by the previous layer's k_ard may be stale now
+        const double invalid[2] = {-1.0, -1.0};
+        CK(cudaMemcpyAsync(h->sh.skTag, invalid, sizeof(invalid), cudaMemcpyHostToDevice, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     return MRGP_OK;
 }

@@ -727,7 +727,7 @@ struct RegionArgs {
     double *bias_prec, *bias_prec0, *bias_mean, *bias_mean0, *bias_var, *yvar, *sumsB;
     // shared (ci) or per-region (fi) axis / ARD
     double *axB, *axKappa, *axRho, *axLogC, *axCov, *ardShape, *ardScale, *ardMean, *ardLogMean;
-    double *omega, *logOmegaHat, *omegaIters, *ardPartial, *omegaEta, *omegaWarm, *omegaK, *primeSk;
+    double *omega, *logOmegaHat, *omegaIters, *ardPartial, *omegaEta, *omegaWarm, *omegaK, *primeSk, *skTag, *wcontrib;
     double *primeB, *primeLogC, *primeShape, *primeScale;   // snapshot read by ARD / omega (ci)
     const double *priorB, *priorLogC, *priorShape, *priorScale;
     double *bcontrib;          // (R, M, 3) ci: 0.5 noise zeta ytil ytil^T
@@ -885,9 +885,11 @@ __global__ void __launch_bounds__(kMidThreads) k_mid1(RegionArgs a, int lpi, int
     static_assert(DY == 2, "dy == 2 only");
     extern __shared__ double sm[];   // contrib[32 * M * 4] + sums[96]; last CTA: omega[M*M], primeB[M*4], data[96]
     const int M = a.M, tid = threadIdx.x, NV = M * 3, NVP = (NV + 31) & ~31;   // NVP: padded length of a B-sum vector
-    double *sContrib = sm, *sSum = sm + 32 * M * 4;
+    const int NVW = M * 4, NVWP = (NVW + 31) & ~31;                                // ... of the ARD-sum vector
+    double *sContrib = sm, *sContribW = sm + 32 * M * 4, *sSum = sContribW + 32 * M * 4, *sSumW = sSum + NVP;
     ts_begin(a.ts, a.layer * 4 + 1);
-    if (tid < NVP) sSum[tid] = 0.0;
+    for (int t = tid; t < NVP; t += kMidThreads) sSum[t] = 0.0;
+    for (int t = tid; t < NVWP; t += kMidThreads) sSumW[t] = 0.0;
     __syncthreads();
     const int r0 = blockIdx.x * regions_per_cta;
     const int r1 = (r0 + regions_per_cta < a.R) ? r0 + regions_per_cta : a.R;
@@ -925,22 +927,43 @@ __global__ void __launch_bounds__(kMidThreads) k_mid1(RegionArgs a, int lpi, int
                 sContrib[it * 4 + 0] = w * (y0 * y0);
                 sContrib[it * 4 + 1] = w * (y0 * y1);
                 sContrib[it * 4 + 2] = w * (y1 * y1);
+                // sum_l m2_li / S_li of the ARD update (Posteriors.py:533-541) is linear in the axis covariance C_i that
+                // the Bingham update is about to produce: m2 = 1/prec + zeta^2 tr(y y^T C) (Stats.py:67-100), so
+                // sum_l m2/S = sum_l 1/(prec S) + tr((sum_l zeta^2 y y^T / S) C_i): the region sums are taken here
+                const double is = 1.0 / a.S[ri], z2s = zeta * zeta * is;
+                sContribW[it * 4 + 0] = is / prec;
+                sContribW[it * 4 + 1] = z2s * (y0 * y0);
+                sContribW[it * 4 + 2] = z2s * (y0 * y1);
+                sContribW[it * 4 + 3] = z2s * (y1 * y1);
             }
         }
         __syncthreads();
-        // sum over the regions of the chunk: 32 lanes hold one region each, shuffle tree (fixed order)
-        for (int vv = tid >> 5; vv < NV; vv += kMidThreads / 32) {
-            const int i = vv / 3, c = vv % 3, k = tid & 31;
-            double t = (k < nreg) ? sContrib[(k * M + i) * 4 + c] : 0.0;
-            t = warp_sum(t);
-            if (k == 0) sSum[vv] += t;
+        // sum over the regions of the chunk: one thread per value, regions in order (a serial chain of <= 32 adds is
+        // shorter than the rounds of warp reductions it replaces: the kernel sits on the critical chain of the sweep)
+        for (int vv = tid; vv < NV + NVW; vv += kMidThreads) {
+            double t = 0.0;
+            if (vv < NV) {
+                const int i = vv / 3, c = vv % 3;
+                for (int k = 0; k < nreg; ++k) t += sContrib[(k * M + i) * 4 + c];
+                sSum[vv] += t;
+            } else {
+                const int w = vv - NV;
+                for (int k = 0; k < nreg; ++k) t += sContribW[k * M * 4 + w];
+                sSumW[w] += t;
+            }
         }
         __syncthreads();
     }
-    if (tid < NVP) a.bcontrib[(size_t)blockIdx.x * NVP + tid] = sSum[tid];   // per-CTA partial of sum_l contrib
+    for (int t = tid; t < NVP; t += kMidThreads) a.bcontrib[(size_t)blockIdx.x * NVP + t] = sSum[t];   // per-CTA partials
+    for (int t = tid; t < NVWP; t += kMidThreads) a.wcontrib[(size_t)blockIdx.x * NVWP + t] = sSumW[t];
     if (blockIdx.x == 0) {   // snapshot of the previous posterior (MRGP.py:575 / :581): k_mid2 and k_omega read it
         const bool first = (a.layer == 0);
         for (int t = tid; t < M * 4; t += kMidThreads) a.primeB[t] = first ? a.priorB[t] : a.axB[t];
+        // the k-only terms of log omega_hat (-logC' + shape' log scale' - lgamma(shape')) are prepared off the critical
+        // path: by k_init_shared for layer 0 (its "previous posterior" is the prior) and by k_ard of the layer before
+        // for the others; they are computed here only if that did not happen (per-phase calls in an unusual order)
+        const int slot = first ? 2 : (a.layer & 1);
+        const bool have_sk = a.skTag[slot] == (double)a.layer;
         for (int t = tid; t < M; t += kMidThreads) {
             const double lc = first ? a.priorLogC[t] : a.axLogC[t];
             const double shp = first ? a.priorShape[t] : a.ardShape[t];
@@ -948,10 +971,34 @@ __global__ void __launch_bounds__(kMidThreads) k_mid1(RegionArgs a, int lpi, int
             a.primeLogC[t] = lc;
             a.primeShape[t] = shp;
             a.primeScale[t] = scp;
-            a.primeSk[t] = -lc + shp * log(scp) - lgamma(shp);   // the terms of log omega_hat that depend on k only
+            if (!have_sk) a.primeSk[slot * 64 + t] = -lc + shp * log(scp) - lgamma(shp);
         }
+        __syncthreads();
+        if (!have_sk && tid == 0) a.skTag[slot] = (double)a.layer;
     }
     ts_end(a.ts, a.layer * 4 + 1);
+}
+
+// Sum of the per-CTA partial vectors of k_mid1 (length NVP each) into sData: `halves` slices of CTAs per value, four
+// loads in flight per thread.  k_mid2 and k_ard both call it with 256 threads, so both form bit-identical sums.
+__device__ __forceinline__ void sum_b_partials(const double *bcontrib, int nb, int NVP, double *sData, double *sHalf) {
+    const int tid = threadIdx.x, nt = blockDim.x;      // NVP <= nt (M <= 85)
+    const int halves = (nt / NVP >= 2) ? 2 : 1;
+    const int v = tid % NVP, half = tid / NVP;
+    if (half < halves) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int q = half;
+        for (; q + 3 * halves < nb; q += 4 * halves) {
+            a0 += __ldcg(bcontrib + (size_t)q * NVP + v);
+            a1 += __ldcg(bcontrib + (size_t)(q + halves) * NVP + v);
+            a2 += __ldcg(bcontrib + (size_t)(q + 2 * halves) * NVP + v);
+            a3 += __ldcg(bcontrib + (size_t)(q + 3 * halves) * NVP + v);
+        }
+        for (; q < nb; q += halves) a0 += __ldcg(bcontrib + (size_t)q * NVP + v);
+        sHalf[half * NVP + v] = (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+    if (tid < NVP) sData[tid] = sHalf[tid] + (halves > 1 ? sHalf[NVP + tid] : 0.0);
 }
 
 // Second half of the ci mid-step.  Every CTA re-derives the axis update from the per-CTA partial sums of k_mid1
@@ -969,25 +1016,7 @@ __global__ void __launch_bounds__(kMidThreads) k_mid2(RegionArgs a, int regions_
     double *sCovOut = sm + ((33 * M > M * M + 4 * M + 3 * NVP) ? 33 * M : M * M + 4 * M + 3 * NVP);
     for (int t = tid; t < M * M; t += kMidThreads) sOmega[t] = a.omega[t];
     for (int t = tid; t < M * 4; t += kMidThreads) sPB[t] = a.primeB[t];
-    {   // sum of the per-CTA partials: `halves` slices of CTAs per value, four loads in flight per thread
-        double *sHalf = sData + NVP;
-        const int halves = (kMidThreads / NVP >= 2) ? 2 : 1;
-        const int v = tid % NVP, half = tid / NVP, nb = n_partials;
-        if (half < halves) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int q = half;
-            for (; q + 3 * halves < nb; q += 4 * halves) {
-                a0 += __ldcg(a.bcontrib + (size_t)q * NVP + v);
-                a1 += __ldcg(a.bcontrib + (size_t)(q + halves) * NVP + v);
-                a2 += __ldcg(a.bcontrib + (size_t)(q + 2 * halves) * NVP + v);
-                a3 += __ldcg(a.bcontrib + (size_t)(q + 3 * halves) * NVP + v);
-            }
-            for (; q < nb; q += halves) a0 += __ldcg(a.bcontrib + (size_t)q * NVP + v);
-            sHalf[half * NVP + v] = (a0 + a1) + (a2 + a3);
-        }
-        __syncthreads();
-        if (tid < NVP) sData[tid] = sHalf[tid] + (halves > 1 ? sHalf[NVP + tid] : 0.0);
-    }
+    sum_b_partials(a.bcontrib, n_partials, NVP, sData, sData + NVP);
     __syncthreads();
     if (tid < M) {
         const int i = tid;
@@ -1004,28 +1033,11 @@ __global__ void __launch_bounds__(kMidThreads) k_mid2(RegionArgs a, int regions_
         sCovOut[i * 4 + 1] = bg.cov[1];
         sCovOut[i * 4 + 2] = bg.cov[1];
         sCovOut[i * 4 + 3] = bg.cov[2];
-        if (blockIdx.x == 0) {
-        atomicAdd(a.chol_count, (unsigned long long)bg.n_chol);
-        a.axB[i * 4 + 0] = bg.b[0];
-        a.axB[i * 4 + 1] = bg.b[1];
-        a.axB[i * 4 + 2] = bg.b[1];
-        a.axB[i * 4 + 3] = bg.b[2];
-        a.axKappa[i * 2 + 0] = bg.kappa[0];
-        a.axKappa[i * 2 + 1] = bg.kappa[1];
-        a.axRho[i * 2 + 0] = bg.rho[0];
-        a.axRho[i * 2 + 1] = bg.rho[1];
-        a.axLogC[i] = bg.logc;
-        a.axCov[i * 4 + 0] = bg.cov[0];
-        a.axCov[i * 4 + 1] = bg.cov[1];
-        a.axCov[i * 4 + 2] = bg.cov[1];
-        a.axCov[i * 4 + 3] = bg.cov[2];
-        }
     }
     __syncthreads();
-    // ---- S2 per item with the new axis covariance: a, m2, cm2 (Stats.py:67-100); per-CTA sums of m2/S --------
-    double *sCov = sCovOut, *sC2 = sm, *sSumA = sC2 + 32 * M;   // the staging area above is free again
-    if (tid < M) sSumA[tid] = 0.0;
-    __syncthreads();
+    // ---- S2 per item with the new axis covariance: a, m2, cm2 (Stats.py:67-100).  (The axis state itself and the
+    //      ARD update are written by k_ard, which derives the same update on the side stream.) ---------------------
+    double *sCov = sCovOut;
     for (int cb = r0; cb < r1; cb += 32) {
         const int nreg = (cb + 32 < r1) ? 32 : r1 - cb;
         const int nitems = nreg * M;
@@ -1041,22 +1053,11 @@ __global__ void __launch_bounds__(kMidThreads) k_mid2(RegionArgs a, int regions_
             a.A[ri * 2 + 0] = zeta * cy0;
             a.A[ri * 2 + 1] = zeta * cy1;
             const double z2 = zeta * zeta;
-            const double m2 = 1.0 / prec + z2 * (y0 * cy0 + y1 * cy1);
             const double ccy0 = c00 * cy0 + c01 * cy1, ccy1 = c01 * cy0 + c11 * cy1;
-            a.m2[ri] = m2;
+            a.m2[ri] = 1.0 / prec + z2 * (y0 * cy0 + y1 * cy1);
             a.cm2[ri] = 1.0 / prec + z2 * (y0 * (cy0 - ccy0) + y1 * (cy1 - ccy1));
-            sC2[it] = m2 / a.S[ri];
         }
-        __syncthreads();
-        for (int vv = tid >> 5; vv < M; vv += kMidThreads / 32) {
-            const int k = tid & 31;
-            double t = (k < nreg) ? sC2[k * M + vv] : 0.0;
-            t = warp_sum(t);
-            if (k == 0) sSumA[vv] += t;
-        }
-        __syncthreads();
     }
-    if (tid < M) a.ardPartial[(size_t)blockIdx.x * M + tid] = sSumA[tid];
     ts_end(a.ts, a.layer * 4 + 1);
 }
 
@@ -1066,14 +1067,16 @@ __global__ void __launch_bounds__(kMidThreads) k_mid2(RegionArgs a, int regions_
 // (mrgp_math.cuh), one block of 256 threads, warp per matrix row / column.
 constexpr int kOmegaThreads = 256;
 
-__host__ __device__ inline size_t omega_smem_doubles(int M) { return (size_t)3 * M * M + 24 * M + 8; }
+__host__ __device__ inline size_t omega_smem_doubles(int M) { return (size_t)3 * M * M + 24 * M + 8 + 3 * ((3 * M + 31) & ~31) + 4 * M; }
 
 __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_partials) {
     extern __shared__ double sm[];
-    const int M = a.M, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = a.M, tid = threadIdx.x;
     constexpr int NW = kOmegaThreads / 32;
     double *P = sm, *s_mean = P + M * M, *s_lmean = s_mean + M, *s_k = s_lmean + M, *s_shape = s_k + M, *s_scale = s_shape + M;
     double *s_B = s_scale + M, *s_C = s_B + 4 * M, *s_part = s_C + 4 * M;   // s_part: NW x M
+    const int NVP = (3 * M + 31) & ~31, NVWP = (4 * M + 31) & ~31;
+    double *s_data = s_part + NW * M, *s_half = s_data + NVP, *s_w = s_half + 2 * NVP;   // B sums, scratch, ARD sums
     ts_begin(a.ts, a.layer * 4 + 3);
 #ifdef MRGP_OMEGA_PROF
     long long pc[6];
@@ -1084,34 +1087,63 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
 #endif
     // every input is staged in shared memory by one wave of loads
     for (int t = tid; t < M * M; t += kOmegaThreads) P[t] = a.omega[t];   // the OLD omega mixes the ARD prior
-    for (int t = tid; t < 4 * M; t += kOmegaThreads) {
-        s_B[t] = a.primeB[t];
-        s_C[t] = a.axCov[t];
-    }
+    for (int t = tid; t < 4 * M; t += kOmegaThreads) s_B[t] = a.primeB[t];
     for (int t = tid; t < M; t += kOmegaThreads) {
-        s_k[t] = a.primeSk[t];
+        s_k[t] = a.primeSk[(a.layer == 0 ? 2 : (a.layer & 1)) * 64 + t];
         s_shape[t] = a.primeShape[t];
         s_scale[t] = a.primeScale[t];
     }
-    for (int i = lane; i < M; i += 32) {   // sum_l m2 / S: the per-CTA partials of k_mid2, one slice of them per warp
-        double p[8];                         // (<= 64 partials: all loads of a lane are in flight together)
+    // sums over the CTAs of k_mid1: the data part of B (same code as k_mid2: same bits) and the ARD sums
+    sum_b_partials(a.bcontrib, n_partials, NVP, s_data, s_half);
+    for (int t = tid; t < 4 * M; t += kOmegaThreads) {
+        double p[8];                         // (<= 32 CTAs: all loads of a thread are in flight together)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int q = warp + u * NW;
-            p[u] = (q < n_partials) ? a.ardPartial[q * M + i] : 0.0;
+        for (int u = 0; u < 8; ++u) p[u] = (u < n_partials) ? __ldcg(a.wcontrib + (size_t)u * NVWP + t) : 0.0;
+        double acc = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+        for (int q = 8; q < n_partials; ++q) acc += __ldcg(a.wcontrib + (size_t)q * NVWP + t);
+        s_w[t] = acc;
+    }
+    __syncthreads();
+    // the shared axis update (P2, P2a-c, S1: Posteriors.py:497-530, Stats.py:375-382), exactly as every CTA of
+    // k_mid2 derives it for its own use; this kernel owns the stored axis state
+    if (tid < M) {
+        const int i = tid;
+        double b00 = 0.0, b01 = 0.0, b11 = 0.0;
+        for (int k = 0; k < M; ++k) {
+            const double w = P[i * M + k];
+            b00 += w * s_B[k * 4 + 0];
+            b01 += w * s_B[k * 4 + 1];
+            b11 += w * s_B[k * 4 + 3];
         }
-        double t = 0.0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) t += p[u];
-        for (int q = warp + 8 * NW; q < n_partials; q += NW) t += a.ardPartial[q * M + i];
-        s_part[warp * M + i] = t;
+        Bingham2 bg;
+        bingham2(b00 + s_data[i * 3 + 0], b01 + s_data[i * 3 + 1], b11 + s_data[i * 3 + 2], bg);
+        s_C[i * 4 + 0] = bg.cov[0];
+        s_C[i * 4 + 1] = bg.cov[1];
+        s_C[i * 4 + 2] = bg.cov[1];
+        s_C[i * 4 + 3] = bg.cov[2];
+        atomicAdd(a.chol_count, (unsigned long long)bg.n_chol);
+        a.axB[i * 4 + 0] = bg.b[0];
+        a.axB[i * 4 + 1] = bg.b[1];
+        a.axB[i * 4 + 2] = bg.b[1];
+        a.axB[i * 4 + 3] = bg.b[2];
+        a.axKappa[i * 2 + 0] = bg.kappa[0];
+        a.axKappa[i * 2 + 1] = bg.kappa[1];
+        a.axRho[i * 2 + 0] = bg.rho[0];
+        a.axRho[i * 2 + 1] = bg.rho[1];
+        a.axLogC[i] = bg.logc;
+        s_half[i] = bg.logc;                  // kept for the k-only terms of the next layer (below)
+        a.axCov[i * 4 + 0] = bg.cov[0];
+        a.axCov[i * 4 + 1] = bg.cov[1];
+        a.axCov[i * 4 + 2] = bg.cov[1];
+        a.axCov[i * 4 + 3] = bg.cov[2];
+        // sum_l m2_li / S_li = sum_l 1/(prec S) + tr((sum_l zeta^2 y y^T / S) C_i)
+        s_part[i] = s_w[i * 4 + 0] + (s_w[i * 4 + 1] * bg.cov[0] + 2.0 * s_w[i * 4 + 2] * bg.cov[1] + s_w[i * 4 + 3] * bg.cov[2]);
     }
     __syncthreads();
     ARD_PC(1);
     if (tid < M) {
         const int i = tid;
-        double beta2 = 0.0;
-        for (int w = 0; w < NW; ++w) beta2 += s_part[w * M + i];
+        const double beta2 = s_part[i];
         double sh = 0.0, sc = 0.0;
         for (int k = 0; k < M; ++k) {
             const double w = P[i * M + k];
@@ -1122,6 +1154,8 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
         const double scale = sc + 0.5 * beta2;
         a.ardShape[i] = shape;
         a.ardScale[i] = scale;
+        s_half[M + i] = shape;
+        s_half[2 * M + i] = scale;
         const double mean = shape / scale, lmean = digamma(shape) - log(scale);
         a.ardMean[i] = mean;
         a.ardLogMean[i] = lmean;
@@ -1149,6 +1183,12 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
         double mx = -INFINITY;
         for (int k = 0; k < M; ++k) mx = fmax(mx, P[tid * M + k]);
         s_rowmax[tid] = mx;
+    } else if (tid >= 64 && tid < 64 + M) {
+        // idle threads: the posterior just written is the "previous posterior" of the next layer; its k-only terms
+        // of log omega_hat (an lgamma per basis function) are ready before that layer's k_mid1 / k_ard need them
+        const int i = tid - 64, slot = (a.layer + 1) & 1;
+        a.primeSk[slot * 64 + i] = -s_half[i] + s_half[M + i] * log(s_half[2 * M + i]) - lgamma(s_half[M + i]);
+        if (i == 0) a.skTag[slot] = (double)(a.layer + 1);
     }
     __syncthreads();
     if (tid < M) {
@@ -2696,6 +2736,12 @@ __global__ void k_init_shared(RegionArgs a, double *priorB, double *priorLogC, d
         a.primeScale[t] = kEps / ard_influence;
         a.ardMean[t] = kEps / (kEps / ard_influence);
         a.ardLogMean[t] = digamma(kEps) - log(kEps / ard_influence);
+        a.primeSk[2 * 64 + t] = -logc0 + kEps * log(kEps / ard_influence) - lgamma(kEps);   // layer 0: the prior
+    }
+    if (threadIdx.x == 0) {
+        a.skTag[0] = -1.0;
+        a.skTag[1] = -1.0;
+        a.skTag[2] = 0.0;
     }
     for (int t = threadIdx.x; t < M * M; t += blockDim.x) {
         a.omega[t] = 1.0 / (double)M;
