@@ -979,24 +979,38 @@ __global__ void __launch_bounds__(kMidThreads) k_mid1(RegionArgs a, int lpi, int
     ts_end(a.ts, a.layer * 4 + 1);
 }
 
-// Sum of the per-CTA partial vectors of k_mid1 (length NVP each) into sData: `halves` slices of CTAs per value, four
-// loads in flight per thread.  k_mid2 and k_ard both call it with 256 threads, so both form bit-identical sums.
-__device__ __forceinline__ void sum_b_partials(const double *bcontrib, int nb, int NVP, double *sData, double *sHalf) {
+// Sum of the per-CTA partial vectors of k_mid1 (length NVP each) into sData, in two steps so that the caller can
+// issue its other global loads while these are in flight: load_b_partials puts up to 16 partials per thread into
+// registers (`halves` slices of CTAs per value), reduce_b_partials adds them in a fixed tree.  k_mid2 and k_ard both
+// use 256 threads, so both form bit-identical sums.
+struct BPartials {
+    double p[16];
+    double tail;
+};
+
+__device__ __forceinline__ void load_b_partials(const double *bcontrib, int nb, int NVP, BPartials &r) {
     const int tid = threadIdx.x, nt = blockDim.x;      // NVP <= nt (M <= 85)
     const int halves = (nt / NVP >= 2) ? 2 : 1;
     const int v = tid % NVP, half = tid / NVP;
-    if (half < halves) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int q = half;
-        for (; q + 3 * halves < nb; q += 4 * halves) {
-            a0 += __ldcg(bcontrib + (size_t)q * NVP + v);
-            a1 += __ldcg(bcontrib + (size_t)(q + halves) * NVP + v);
-            a2 += __ldcg(bcontrib + (size_t)(q + 2 * halves) * NVP + v);
-            a3 += __ldcg(bcontrib + (size_t)(q + 3 * halves) * NVP + v);
-        }
-        for (; q < nb; q += halves) a0 += __ldcg(bcontrib + (size_t)q * NVP + v);
-        sHalf[half * NVP + v] = (a0 + a1) + (a2 + a3);
+    r.tail = 0.0;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const int q = half + u * halves;
+        r.p[u] = (half < halves && q < nb) ? __ldcg(bcontrib + (size_t)q * NVP + v) : 0.0;
     }
+    if (half < halves)
+        for (int q = half + 16 * halves; q < nb; q += halves) r.tail += __ldcg(bcontrib + (size_t)q * NVP + v);
+}
+
+__device__ __forceinline__ void reduce_b_partials(BPartials &r, int NVP, double *sData, double *sHalf) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int halves = (nt / NVP >= 2) ? 2 : 1;
+    const int v = tid % NVP, half = tid / NVP;
+#pragma unroll
+    for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+        for (int u = 0; u < w; ++u) r.p[u] += r.p[u + w];
+    if (half < halves) sHalf[half * NVP + v] = r.p[0] + r.tail;
     __syncthreads();
     if (tid < NVP) sData[tid] = sHalf[tid] + (halves > 1 ? sHalf[NVP + tid] : 0.0);
 }
@@ -1014,9 +1028,11 @@ __global__ void __launch_bounds__(kMidThreads) k_mid2(RegionArgs a, int regions_
     const int r1 = (r0 + regions_per_cta < a.R) ? r0 + regions_per_cta : a.R;
     double *sOmega = sm, *sPB = sOmega + M * M, *sData = sPB + 4 * M;
     double *sCovOut = sm + ((33 * M > M * M + 4 * M + 3 * NVP) ? 33 * M : M * M + 4 * M + 3 * NVP);
+    BPartials bp;
+    load_b_partials(a.bcontrib, n_partials, NVP, bp);      // in flight together with the staging loads below
     for (int t = tid; t < M * M; t += kMidThreads) sOmega[t] = a.omega[t];
     for (int t = tid; t < M * 4; t += kMidThreads) sPB[t] = a.primeB[t];
-    sum_b_partials(a.bcontrib, n_partials, NVP, sData, sData + NVP);
+    reduce_b_partials(bp, NVP, sData, sData + NVP);
     __syncthreads();
     if (tid < M) {
         const int i = tid;
@@ -1085,24 +1101,30 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
 #else
 #define ARD_PC(k)
 #endif
-    // every input is staged in shared memory by one wave of loads
-    for (int t = tid; t < M * M; t += kOmegaThreads) P[t] = a.omega[t];   // the OLD omega mixes the ARD prior
+    // one wave of global loads: the per-CTA sums of k_mid1 (data part of B: same code as k_mid2, same bits; ARD sums:
+    // one value per thread, k_mid1 runs at most 32 CTAs) go to registers while every other input is staged in
+    // shared memory
+    BPartials bp;
+    load_b_partials(a.bcontrib, n_partials, NVP, bp);
+    double pw[32];
+    {
+        const int t = tid < 4 * M ? tid : 0;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) pw[u] = (tid < 4 * M && u < n_partials) ? __ldcg(a.wcontrib + (size_t)u * NVWP + t) : 0.0;
+    }
+    for (int t = tid; t < M * M; t += kOmegaThreads) P[t] = a.omega[t];   // the OLD omega mixes the previous posterior
     for (int t = tid; t < 4 * M; t += kOmegaThreads) s_B[t] = a.primeB[t];
     for (int t = tid; t < M; t += kOmegaThreads) {
         s_k[t] = a.primeSk[(a.layer == 0 ? 2 : (a.layer & 1)) * 64 + t];
         s_shape[t] = a.primeShape[t];
         s_scale[t] = a.primeScale[t];
     }
-    // sums over the CTAs of k_mid1: the data part of B (same code as k_mid2: same bits) and the ARD sums
-    sum_b_partials(a.bcontrib, n_partials, NVP, s_data, s_half);
-    for (int t = tid; t < 4 * M; t += kOmegaThreads) {
-        double p[8];                         // (<= 32 CTAs: all loads of a thread are in flight together)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) p[u] = (u < n_partials) ? __ldcg(a.wcontrib + (size_t)u * NVWP + t) : 0.0;
-        double acc = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
-        for (int q = 8; q < n_partials; ++q) acc += __ldcg(a.wcontrib + (size_t)q * NVWP + t);
-        s_w[t] = acc;
-    }
+    for (int w = 16; w > 0; w >>= 1)
+#pragma unroll
+        for (int u = 0; u < w; ++u) pw[u] += pw[u + w];
+    if (tid < 4 * M) s_w[tid] = pw[0];
+    reduce_b_partials(bp, NVP, s_data, s_half);
     __syncthreads();
     // the shared axis update (P2, P2a-c, S1: Posteriors.py:497-530, Stats.py:375-382), exactly as every CTA of
     // k_mid2 derives it for its own use; this kernel owns the stored axis state
