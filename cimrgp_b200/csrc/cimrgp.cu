@@ -736,13 +736,13 @@ int do_mid_ci(mrgp_handle *h, int j, bool fork_omega, bool zero_T) {
         }
         if (h->omega_warp && M == 30) {
             CK(cudaFuncSetAttribute(k_scale_warp<30>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-            k_scale_warp<30><<<1, 32, 0, st>>>(a);
+            k_scale_warp<30><<<1, 64, 0, st>>>(a);
         } else if (h->omega_warp && M == 20) {
             CK(cudaFuncSetAttribute(k_scale_warp<20>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-            k_scale_warp<20><<<1, 32, 0, st>>>(a);
+            k_scale_warp<20><<<1, 64, 0, st>>>(a);
         } else if (h->omega_warp && M == 8) {
             CK(cudaFuncSetAttribute(k_scale_warp<8>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-            k_scale_warp<8><<<1, 32, 0, st>>>(a);
+            k_scale_warp<8><<<1, 64, 0, st>>>(a);
         } else {
             CK(set_smem(k_scale, smem));
             k_scale<<<1, kOmegaThreads, smem, st>>>(a);

@@ -959,22 +959,11 @@ __global__ void __launch_bounds__(kMidThreads) k_mid1(RegionArgs a, int lpi, int
     if (blockIdx.x == 0) {   // snapshot of the previous posterior (MRGP.py:575 / :581): k_mid2 and k_omega read it
         const bool first = (a.layer == 0);
         for (int t = tid; t < M * 4; t += kMidThreads) a.primeB[t] = first ? a.priorB[t] : a.axB[t];
-        // the k-only terms of log omega_hat (-logC' + shape' log scale' - lgamma(shape')) are prepared off the critical
-        // path: by k_init_shared for layer 0 (its "previous posterior" is the prior) and by k_ard of the layer before
-        // for the others; they are computed here only if that did not happen (per-phase calls in an unusual order)
-        const int slot = first ? 2 : (a.layer & 1);
-        const bool have_sk = a.skTag[slot] == (double)a.layer;
         for (int t = tid; t < M; t += kMidThreads) {
-            const double lc = first ? a.priorLogC[t] : a.axLogC[t];
-            const double shp = first ? a.priorShape[t] : a.ardShape[t];
-            const double scp = first ? a.priorScale[t] : a.ardScale[t];
-            a.primeLogC[t] = lc;
-            a.primeShape[t] = shp;
-            a.primeScale[t] = scp;
-            if (!have_sk) a.primeSk[slot * 64 + t] = -lc + shp * log(scp) - lgamma(shp);
+            a.primeLogC[t] = first ? a.priorLogC[t] : a.axLogC[t];
+            a.primeShape[t] = first ? a.priorShape[t] : a.ardShape[t];
+            a.primeScale[t] = first ? a.priorScale[t] : a.ardScale[t];
         }
-        __syncthreads();
-        if (!have_sk && tid == 0) a.skTag[slot] = (double)a.layer;
     }
     ts_end(a.ts, a.layer * 4 + 1);
 }
@@ -1114,10 +1103,19 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
     }
     for (int t = tid; t < M * M; t += kOmegaThreads) P[t] = a.omega[t];   // the OLD omega mixes the previous posterior
     for (int t = tid; t < 4 * M; t += kOmegaThreads) s_B[t] = a.primeB[t];
-    for (int t = tid; t < M; t += kOmegaThreads) {
-        s_k[t] = a.primeSk[(a.layer == 0 ? 2 : (a.layer & 1)) * 64 + t];
-        s_shape[t] = a.primeShape[t];
-        s_scale[t] = a.primeScale[t];
+    {
+        // the k-only terms of the table, -logC' + shape' log scale' - lgamma(shape'), were prepared off the critical
+        // chain: by k_init_shared for layer 0 (its "previous posterior" is the prior) and by the second warp of the
+        // previous layer's k_scale_warp for the others; they are computed here only if that did not happen (block
+        // solver, per-phase calls in an unusual order, state set from the host)
+        const int slot = a.layer == 0 ? 2 : (a.layer & 1);
+        const bool have_sk = a.skTag[slot] == (double)a.layer;
+        for (int t = tid; t < M; t += kOmegaThreads) {
+            const double shp = a.primeShape[t], scp = a.primeScale[t];
+            s_shape[t] = shp;
+            s_scale[t] = scp;
+            s_k[t] = have_sk ? a.primeSk[slot * 64 + t] : -a.primeLogC[t] + shp * log(scp) - lgamma(shp);
+        }
     }
 #pragma unroll
     for (int w = 16; w > 0; w >>= 1)
@@ -1153,7 +1151,6 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
         a.axRho[i * 2 + 0] = bg.rho[0];
         a.axRho[i * 2 + 1] = bg.rho[1];
         a.axLogC[i] = bg.logc;
-        s_half[i] = bg.logc;                  // kept for the k-only terms of the next layer (below)
         a.axCov[i * 4 + 0] = bg.cov[0];
         a.axCov[i * 4 + 1] = bg.cov[1];
         a.axCov[i * 4 + 2] = bg.cov[1];
@@ -1176,8 +1173,6 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
         const double scale = sc + 0.5 * beta2;
         a.ardShape[i] = shape;
         a.ardScale[i] = scale;
-        s_half[M + i] = shape;
-        s_half[2 * M + i] = scale;
         const double mean = shape / scale, lmean = digamma(shape) - log(scale);
         a.ardMean[i] = mean;
         a.ardLogMean[i] = lmean;
@@ -1205,12 +1200,6 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
         double mx = -INFINITY;
         for (int k = 0; k < M; ++k) mx = fmax(mx, P[tid * M + k]);
         s_rowmax[tid] = mx;
-    } else if (tid >= 64 && tid < 64 + M) {
-        // idle threads: the posterior just written is the "previous posterior" of the next layer; its k-only terms
-        // of log omega_hat (an lgamma per basis function) are ready before that layer's k_mid1 / k_ard need them
-        const int i = tid - 64, slot = (a.layer + 1) & 1;
-        a.primeSk[slot * 64 + i] = -s_half[i] + s_half[M + i] * log(s_half[2 * M + i]) - lgamma(s_half[M + i]);
-        if (i == 0) a.skTag[slot] = (double)(a.layer + 1);
     }
     __syncthreads();
     if (tid < M) {
@@ -1457,11 +1446,24 @@ struct OmegaWarp {
 };
 
 template <int M>
-__global__ void __launch_bounds__(32, 1) k_scale_warp(RegionArgs a) {
+__global__ void __launch_bounds__(64, 1) k_scale_warp(RegionArgs a) {
     static_assert(M <= 32 && (M & 1) == 0, "one lane per row, columns in pairs");
     using W = OmegaWarp<M>;
     constexpr int LD = W::LD;
     __shared__ __align__(16) double T[M * LD];
+    if (threadIdx.x >= 32) {
+        // second warp, beside the solve: the posterior k_ard has just written is the "previous posterior" of the next
+        // layer; the k-only terms of that layer's log omega_hat table (one lgamma per basis function) are ready before
+        // its k_mid1 / k_ard need them
+        const int i = threadIdx.x - 32, slot = (a.layer + 1) & 1;
+        if (i < M) {
+            const double shp = a.ardShape[i];
+            a.primeSk[slot * 64 + i] = -a.axLogC[i] + shp * log(a.ardScale[i]) - lgamma(shp);
+        }
+        __syncwarp();
+        if (i == 0) a.skTag[slot] = (double)(a.layer + 1);
+        return;
+    }
     const int lane = threadIdx.x;
     const bool row = lane < M;
     double K[M], P[M], Q[M];
