@@ -176,12 +176,17 @@ int mrgp_bias_noise(mrgp_handle *h, int32_t layer);
 int mrgp_set_adaptive_intervals(mrgp_handle *h, int32_t layer, int32_t enabled, int32_t use_prior, double factor_lo, double factor_hi);
 int mrgp_learn_intervals(mrgp_handle *h, int32_t layer);
 int mrgp_interval_failures(mrgp_handle *h, uint64_t *out);
-/* n_iter full sweeps (all layers, Gauss-Seidel order), replayed from one captured CUDA graph.       */
+/* n_iter full sweeps (all layers, Gauss-Seidel order), replayed from one captured CUDA graph.  Same results as
+ * the per-phase calls above up to summation order (1e-11): in ci mode with static intervals the sweep does not
+ * stream the layers whose targets are inferred from their own posterior (LatentOutputs.py:20-49) - their P1
+ * residual vanishes identically and their P4 / P5 sums are evaluated in closed form from basis invariants built
+ * on the first call; MRGP_STREAM_ALL=1 in the environment streams every layer.        */
 int mrgp_sweep(mrgp_handle *h, int32_t n_iter);
 int mrgp_synchronize(mrgp_handle *h);
 
 /* E1-E6: the six ELBO terms per layer, out_host (J, 6) in the order data, scale|axis, axis, ard, bias,
- * noise (MRGP.py:414-569; ci only).                                                                 */
+ * noise (MRGP.py:414-569; ci only).  Under adaptive intervals the data term uses the re-learnt basis of every
+ * layer against the targets inferred with the previous one, as the reference does (MRGP.py:535-569 after :640). */
 int mrgp_elbo(mrgp_handle *h, double *out_host);
 
 /* ---- O1: prediction (MRGP.py:726-861) --------------------------------------------------------- */
