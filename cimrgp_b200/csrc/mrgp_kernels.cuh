@@ -1686,7 +1686,7 @@ __global__ void __launch_bounds__(256) k_comm_sums_signal(CommArgs c, const int3
     if (tid < c.world) st_release_sys(c.flags[tid] + c.rank, *c.seq);
 }
 
-constexpr unsigned long long kCommTimeoutNs = 4000000000ull;   // a lost peer must not hang the GPU
+constexpr unsigned long long kCommTimeoutNs = 15000000000ull;   // a lost peer must not hang the GPU
 
 // out[r][v] = sum (or max) over the ranks that own samples of region r of their arena entries.
 template <bool MAX>

@@ -220,7 +220,7 @@ int mrgp_predict_var_indexed(mrgp_handle *h, const double *x_test_dev, int64_t n
  *     sharded handle.  One exchange = dense local sums -> arena, a release-store of the next sequence number into
  *     every peer's flag array, and a reduce kernel that waits for all peers and sums, per region, the arenas of
  *     exactly the ranks that own samples of the region, in rank order: every rank computes bit-identical sums.
- *     A peer that never publishes makes the wait time out (4 s) and mrgp_synchronize return MRGP_ECUDA.
+ *     A peer that never publishes makes the wait time out (15 s) and mrgp_synchronize return MRGP_ECUDA.
  *         mrgp_phase_a -> mrgp_exchange(layer, MRGP_X_PHASE_A) -> mrgp_axis_update
  *         mrgp_phase_b -> mrgp_exchange(layer, MRGP_X_PHASE_B) -> mrgp_bias_noise
  * (2) Caller-side collective (NCCL all-reduce on the handle's stream; kept as the comparison arm):
