@@ -130,7 +130,11 @@ int mrgp_set_stream(mrgp_handle *h, void *cuda_stream);
  * The pointers are borrowed: they must stay valid while the handle is used.                        */
 int mrgp_set_data(mrgp_handle *h, const double *x_dev, const double *y_dev);
 /* Same from host buffers (pinned for full speed): asynchronous H2D copies on the handle's stream into
- * the workspace.  This is the entry the end-to-end benchmark times.                                 */
+ * the workspace.  This is the entry the end-to-end benchmark times.
+ * Everything derived from x alone - the basis intervals, lambda, S, sum phi^2 and the invariants of the
+ * closed-form statistics - is built by mrgp_build_basis / the first mrgp_sweep and is NOT refreshed here: new
+ * observations y at the same inputs need nothing else, new inputs x need mrgp_build_basis for every layer again
+ * (as the reference needs a new model object, MRGP.py:128-172).                                      */
 int mrgp_set_data_host(mrgp_handle *h, const double *x_host, const double *y_host);
 
 /* ---- K1-K3: basis intervals, eigenvalues, spectral density, sum phi^2 ---------------------------- */
