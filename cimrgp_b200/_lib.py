@@ -89,6 +89,7 @@ SIGNATURES = {
     'mrgp_timeline_read': (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_int32]),
     'mrgp_plan_info': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'mrgp_plan_segments': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64)]),
+    'mrgp_plan_pieces': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     'mrgp_host_digamma': (C.c_double, [C.c_double]),
     'mrgp_host_matern_spectral': (C.c_double, [C.c_double, C.c_double, C.c_double, C.c_double]),
     'mrgp_host_bingham2': (None, [_D, _D, _D, _D, _D, _D, C.POINTER(C.c_int32)]),

@@ -2143,6 +2143,25 @@ int mrgp_plan_segments(const mrgp_handle *h, int32_t layer, int64_t *seg_out) {
     return MRGP_OK;
 }
 
+int mrgp_plan_pieces(const mrgp_handle *h, int32_t layer, int32_t *n_pieces, int64_t *piece_out) {
+    if (!h || !n_pieces || layer < 0 || layer >= h->cfg.n_layers) return MRGP_EINVAL;
+    const LayerPlan &lp = h->plan[layer];
+    *n_pieces = (int32_t)lp.pc_jp.size();
+    if (!piece_out) return MRGP_OK;
+    const int R = lp.R;
+    for (size_t k = 0; k < lp.pc_jp.size(); ++k) {
+        const int jp = lp.pc_jp[k];
+        int c = 0;   // region of the layer that owns the piece: the CSR row of (jp, c) containing k
+        while (!(lp.pc_ptr[(size_t)jp * (R + 1) + c] <= (int32_t)k && (int32_t)k < lp.pc_ptr[(size_t)jp * (R + 1) + c + 1])) ++c;
+        piece_out[k * 5 + 0] = jp;
+        piece_out[k * 5 + 1] = c;
+        piece_out[k * 5 + 2] = lp.pc_anc[k];
+        piece_out[k * 5 + 3] = lp.pc_lo[k];
+        piece_out[k * 5 + 4] = lp.pc_hi[k];
+    }
+    return MRGP_OK;
+}
+
 double mrgp_host_digamma(double x) { return digamma(x); }
 
 double mrgp_host_matern_spectral(double lambda, double nu, double l, double sf) { return matern_spectral(lambda, nu, l, sf); }

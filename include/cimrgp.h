@@ -285,6 +285,10 @@ int mrgp_timeline_read(mrgp_handle *h, int32_t *tags, float *ms, int32_t cap);
 int mrgp_plan_info(const mrgp_handle *h, int32_t layer, int32_t *n_ctas, int32_t *n_segments, int32_t *n_runs);
 /* Copy the plan of a layer: seg (n_segments, 6) int64 = start, end, region, parent, run, cta. */
 int mrgp_plan_segments(const mrgp_handle *h, int32_t layer, int64_t *seg_out);
+/* Pieces of the closed-form statistics (ci mode, layers > 0): every intersection of a region of `layer` with a
+ * region of a coarser layer.  piece_out == NULL: only the count; else (n_pieces, 5) int64 = coarser layer, region
+ * of `layer`, region of the coarser layer, first sample, one past the last sample.                   */
+int mrgp_plan_pieces(const mrgp_handle *h, int32_t layer, int32_t *n_pieces, int64_t *piece_out);
 /* The device math routines compiled for the host (same source): digamma, Matern spectral density,
  * the 2x2 Bingham update (guard, eigen-solve, saddle point), basis recurrence, omega scaling.       */
 double mrgp_host_digamma(double x);

@@ -79,6 +79,48 @@ def test_plan_partitions_samples(n, res, div, ctas):
         lib.mrgp_destroy(h)
 
 
+@pytest.mark.parametrize('case', ['uniform', 'ragged'])
+def test_pieces_of_the_closed_form_statistics_tile_every_region(case):
+    """Bookkeeping of the closed-form layer statistics: for every layer j > 0 and every coarser layer
+    jp, the pieces (region of j) x (region of jp) must tile each region of j exactly once, in order, with the right
+    coarser region; the reference's uniform index sets are NOT nested (1e6 / 64 = 15625 is odd), ragged ones less so."""
+    if case == 'uniform':
+        n = 1000000
+        offsets = O.uniform_offsets(n, 9, 2)
+    else:
+        rng = np.random.RandomState(5)
+        n = 5000
+        offsets = [np.array([0, n], dtype=np.int64)]
+        for r in (3, 7, 20, 41):
+            cuts = np.sort(rng.choice(np.arange(1, n), size=r - 1, replace=False))
+            offsets.append(np.concatenate([[0], cuts, [n]]).astype(np.int64))
+    lib, rc, h = _create(n, offsets, n_ctas=16)
+    assert rc == 0, lib.mrgp_last_error(None)
+    try:
+        nested = True
+        for j in range(1, len(offsets)):
+            cnt = C.c_int32()
+            assert lib.mrgp_plan_pieces(h, j, C.byref(cnt), None) == 0
+            pcs = np.zeros((cnt.value, 5), dtype=np.int64)
+            assert lib.mrgp_plan_pieces(h, j, C.byref(cnt), pcs.ctypes.data_as(C.POINTER(C.c_int64))) == 0
+            R = len(offsets[j]) - 1
+            for jp in range(j):
+                sel = pcs[pcs[:, 0] == jp]
+                assert np.all(sel[:, 4] > sel[:, 3])
+                # the pieces of (jp, .) tile [0, n) in order and respect both partitions
+                assert sel[0, 3] == 0 and sel[-1, 4] == n and np.array_equal(sel[1:, 3], sel[:-1, 4])
+                for c in range(R):
+                    mine = sel[sel[:, 1] == c]
+                    assert mine[0, 3] == offsets[j][c] and mine[-1, 4] == offsets[j][c + 1]
+                    nested = nested and len(mine) == 1
+                anc = np.searchsorted(offsets[jp], sel[:, 3], side='right') - 1
+                assert np.array_equal(anc, sel[:, 2])
+                assert np.all(sel[:, 4] <= offsets[jp][sel[:, 2] + 1])
+        assert not nested      # both cases exercise regions that straddle coarser regions
+    finally:
+        lib.mrgp_destroy(h)
+
+
 def test_create_rejects_what_the_reference_rejects():
     off = O.uniform_offsets(64, 2, 2)
     lib, rc, h = _create(64, off, dy=1)
