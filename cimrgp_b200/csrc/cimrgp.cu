@@ -103,7 +103,9 @@ struct mrgp_handle {
     cudaStream_t stream = nullptr, side = nullptr;
     bool own_stream = false;
     std::vector<cudaEvent_t> ev_fork, ev_join, ev_ard, ev_mid2;
-    cudaEvent_t ev_prefetch = nullptr;
+    cudaEvent_t ev_prefetch = nullptr, ev_b0_fork = nullptr, ev_b0_done = nullptr;
+    cudaStream_t side2 = nullptr;    // layer 0's phase B beside the chain of layer 1 (closed-form ci sweeps)
+    bool b0_pending = false;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     int64_t launches = 0, launches_per_sweep = 0, sweeps_done = 0;
@@ -1035,7 +1037,23 @@ int sweep_once(mrgp_handle *h, bool fork_omega) {
             if ((rc = do_learn_intervals(h, j))) return rc;
             if (j + 1 < J && (rc = do_phase_b(h, j, false, 1))) return rc;
         } else if (closed && j > 0) {
+            if (h->b0_pending) {   // the statistics of this layer read the bias variance of layer 0
+                CK(cudaStreamWaitEvent(h->stream, h->ev_b0_done, 0));
+                h->b0_pending = false;
+            }
             if ((rc = do_stats_b(h, j))) return rc;         // inferred targets: statistics from the basis invariants
+        } else if (closed && j == 0 && fork_omega && J > 1 && h->side2) {
+            // Layer 0's statistics pass (26 us on 147 SMs) runs on a third stream: the small-matrix chain of layer 1
+            // (k_mid1 -> k_ard -> k_scale_warp on the SM left free) does not depend on it, only k_stats_b does.
+            CK(cudaEventRecord(h->ev_b0_fork, h->stream));
+            CK(cudaStreamWaitEvent(h->side2, h->ev_b0_fork, 0));
+            cudaStream_t main_stream = h->stream;
+            h->stream = h->side2;
+            rc = do_phase_b(h, j, true, 0);
+            h->stream = main_stream;
+            if (rc) return rc;
+            CK(cudaEventRecord(h->ev_b0_done, h->side2));
+            h->b0_pending = true;
         } else {
             // bias / noise update fused into the kernel tail; nothing reads the latent buffers when the layers below
             // take the closed form
@@ -1045,6 +1063,10 @@ int sweep_once(mrgp_handle *h, bool fork_omega) {
     if (fork_omega && ci) {
         CK(cudaStreamWaitEvent(h->stream, h->ev_ard[J - 1], 0));
         CK(cudaStreamWaitEvent(h->stream, h->ev_join[J - 1], 0));
+    }
+    if (h->b0_pending) {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_b0_done, 0));
+        h->b0_pending = false;
     }
     return MRGP_OK;
 }
@@ -1257,6 +1279,9 @@ void mrgp_destroy(mrgp_handle *h) {
     for (auto e : h->ev_ard) cudaEventDestroy(e);
     for (auto e : h->ev_mid2) cudaEventDestroy(e);
     if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
+    if (h->ev_b0_fork) cudaEventDestroy(h->ev_b0_fork);
+    if (h->ev_b0_done) cudaEventDestroy(h->ev_b0_done);
+    if (h->side2) cudaStreamDestroy(h->side2);
     for (int q = 0; q < kMaxRanks; ++q)
         if (h->comm.opened[q]) cudaIpcCloseMemHandle(h->comm.peer_base[q]);
     if (h->comm.mem) cudaFree(h->comm.mem);
@@ -1285,7 +1310,12 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
         h->own_stream = true;
     }
     if (!h->side) CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-    if (!h->ev_prefetch) CK(cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
+    if (!h->ev_prefetch) {
+        CK(cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_b0_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_b0_done, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
+    }
     if (h->ev_fork.empty()) {
         h->ev_fork.resize(h->cfg.n_layers);
         h->ev_join.resize(h->cfg.n_layers);
