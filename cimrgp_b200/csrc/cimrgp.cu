@@ -1037,11 +1037,19 @@ int sweep_once(mrgp_handle *h, bool fork_omega) {
             if ((rc = do_learn_intervals(h, j))) return rc;
             if (j + 1 < J && (rc = do_phase_b(h, j, false, 1))) return rc;
         } else if (closed && j > 0) {
-            if (h->b0_pending) {   // the statistics of this layer read the bias variance of layer 0
-                CK(cudaStreamWaitEvent(h->stream, h->ev_b0_done, 0));
-                h->b0_pending = false;
+            // inferred targets: statistics from the basis invariants.  In the captured sweep they follow layer 0's pass
+            // on the third stream (they read the bias variances of the coarser layers, nothing of the chain waits for
+            // them): k_mid1 of the next layer starts as soon as the ARD moments are there.
+            if (fork_omega && h->b0_pending) {
+                CK(cudaStreamWaitEvent(h->side2, h->ev_mid2[j], 0));   // A, cm2 of this layer (k_mid2)
+                cudaStream_t main_stream = h->stream;
+                h->stream = h->side2;
+                rc = do_stats_b(h, j);
+                h->stream = main_stream;
+                if (rc) return rc;
+            } else {
+                if ((rc = do_stats_b(h, j))) return rc;
             }
-            if ((rc = do_stats_b(h, j))) return rc;         // inferred targets: statistics from the basis invariants
         } else if (closed && j == 0 && fork_omega && J > 1 && h->side2) {
             // Layer 0's statistics pass (26 us on 147 SMs) runs on a third stream: the small-matrix chain of layer 1
             // (k_mid1 -> k_ard -> k_scale_warp on the SM left free) does not depend on it, only k_stats_b does.
@@ -1052,7 +1060,6 @@ int sweep_once(mrgp_handle *h, bool fork_omega) {
             rc = do_phase_b(h, j, true, 0);
             h->stream = main_stream;
             if (rc) return rc;
-            CK(cudaEventRecord(h->ev_b0_done, h->side2));
             h->b0_pending = true;
         } else {
             // bias / noise update fused into the kernel tail; nothing reads the latent buffers when the layers below
@@ -1064,7 +1071,8 @@ int sweep_once(mrgp_handle *h, bool fork_omega) {
         CK(cudaStreamWaitEvent(h->stream, h->ev_ard[J - 1], 0));
         CK(cudaStreamWaitEvent(h->stream, h->ev_join[J - 1], 0));
     }
-    if (h->b0_pending) {
+    if (h->b0_pending) {   // join the third stream (layer 0's pass and the closed-form statistics of the other layers)
+        CK(cudaEventRecord(h->ev_b0_done, h->side2));
         CK(cudaStreamWaitEvent(h->stream, h->ev_b0_done, 0));
         h->b0_pending = false;
     }
