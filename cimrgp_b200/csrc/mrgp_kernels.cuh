@@ -1156,13 +1156,10 @@ __global__ void __launch_bounds__(kOmegaThreads) k_ard(RegionArgs a, int n_parti
         a.axCov[i * 4 + 2] = bg.cov[1];
         a.axCov[i * 4 + 3] = bg.cov[2];
         // sum_l m2_li / S_li = sum_l 1/(prec S) + tr((sum_l zeta^2 y y^T / S) C_i)
-        s_part[i] = s_w[i * 4 + 0] + (s_w[i * 4 + 1] * bg.cov[0] + 2.0 * s_w[i * 4 + 2] * bg.cov[1] + s_w[i * 4 + 3] * bg.cov[2]);
-    }
-    __syncthreads();
-    ARD_PC(1);
-    if (tid < M) {
-        const int i = tid;
-        const double beta2 = s_part[i];
+        const double beta2 = s_w[i * 4 + 0] + (s_w[i * 4 + 1] * bg.cov[0] + 2.0 * s_w[i * 4 + 2] * bg.cov[1] + s_w[i * 4 + 3] * bg.cov[2]);
+        ARD_PC(1);
+        // ARD update of the same basis function in the same thread (no barrier: its sums do not depend on the axis
+        // update and fill the latency of the chain above)
         double sh = 0.0, sc = 0.0;
         for (int k = 0; k < M; ++k) {
             const double w = P[i * M + k];
