@@ -153,7 +153,7 @@ def run_reference(args, rank, world):
     line = {
         'impl': 'reference', 'metric': 'ciMRGP VI iters/sec at N=1e6, R=10', 'value': value, 'unit': 'it/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / value,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD},
         'cpu_baseline': {'value': value, 'unit': 'it/s', 'cores': 1, 'kind': 'port', 'sample': sample,
                          'host_cores': os.cpu_count()},
@@ -338,7 +338,7 @@ def run_gpu(args, rank, world, local_rank):
         'metric': 'ciMRGP VI iters/sec at N=1e6, R=10', 'value': value, 'unit': 'it/s', 'n_gpus': 1,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * total_s / args.steps,
         'step_ms': [round(v, 4) for v in step_ms],
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'l2': 'flushed between timed steps (256 MB write)',
                    'n_ctas': eng.lib and args.ctas or 'one persistent CTA per SM'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
