@@ -212,8 +212,11 @@ def run_gpu(args, rank, world, local_rank):
     l0 = eng.launch_count()
     barrier()
     for k in range(args.steps):
+        # the L2 flush (256 MB of HBM writes on torch's stream) must neither overlap the sweep before it nor the one
+        # after it: it starts when the previous timed sweep is over and ends before the next timed region starts
+        torch.cuda.current_stream().wait_stream(eng.stream)
         flush.zero_()
-        eng.stream.wait_stream(torch.cuda.current_stream())   # the L2 flush is over before the timed region starts
+        eng.stream.wait_stream(torch.cuda.current_stream())
         barrier()
         ev[k][0].record(eng.stream)
         eng.sweep(1)
