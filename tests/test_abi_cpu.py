@@ -230,6 +230,24 @@ def test_host_omega_matches_reference_within_its_solver_tolerance():
         assert mismatch(om, O.omega_sinkhorn(lw), 1e-8) is None
 
 
+def test_host_omega_on_peaked_tables_from_the_device_run():
+    """log omega_hat tables captured on the device at config 4 (layers 1 and 2, sweeps 2-7; scratch/dump_table.py):
+    overall range 2e5, every row's maximum ~49 above its second entry.  A Newton step from a far start loses
+    definiteness on them and plain Sinkhorn crawls on the flat ones; the step policy (omega_take_newton) must reach the
+    tolerance in a few dozen steps, cold and warm-started alike."""
+    lib = _lib.load()
+    P = C.POINTER(C.c_double)
+    g = np.load(os.path.join(GOLD, 'omega_hard.npz'))
+    for key in g.files:
+        lw = np.ascontiguousarray(g[key])
+        m = lw.shape[0]
+        om, it = np.zeros((m, m)), C.c_int32()
+        assert lib.mrgp_host_omega(lw.ctypes.data_as(P), m, om.ctypes.data_as(P), C.byref(it)) == 0
+        assert it.value <= 40, (key, it.value)
+        assert np.max(np.abs(om.sum(0) - 1)) < 1e-10 and np.max(np.abs(om.sum(1) - 1)) < 1e-12
+        assert mismatch(om, O.omega_sinkhorn(lw), 1e-8) is None, key
+
+
 def test_index_sets_bit_exact():
     from cimrgp_b200.IndexSetGenerator import IndexSetUniform, offsets_of
     k = np.load(os.path.join(GOLD, 'kats.npz'))
