@@ -868,14 +868,16 @@ __global__ void __launch_bounds__(512) k_reduce_scale(RegionArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// ci mid-step, two wide launches (the work is latency-bound: a few dependent global loads per item, so it
-// is spread over many SMs instead of a few fat CTAs):
-//   k_mid1  P1-finish per (region, basis) item: run partials -> y_tilde, precision, zeta and the item's
-//           contribution to B_i (Posteriors.py:35-78, 507-517); the LAST CTA to finish then sums the
-//           contributions over the regions in a fixed order, mixes in the previous posterior, runs the PD
-//           guard and the Bingham update (P2, S1: Posteriors.py:497-530, Stats.py:375-382);
-//   k_mid3  S2 per item with the new axis covariance: a, m2, cm2 (Stats.py:67-100) and per-CTA sums of
-//           m2/S for the ARD update that k_omega finishes off the critical path.
+// ci mid-step (the work is latency-bound: a few dependent global loads per item, so it is spread over many SMs
+// instead of a few fat CTAs):
+//   k_mid1  P1-finish per (region, basis) item: run partials -> y_tilde, precision, zeta (Posteriors.py:35-78) and
+//           per-CTA sums over the regions of the item's contribution to B_i (Posteriors.py:507-517) and of the two
+//           terms that make sum_l m2/S linear in the axis covariance (ARD update, Posteriors.py:533-541);
+//   k_ard   (side stream, critical chain) sums those partials, mixes in the previous posterior, runs the PD guard and
+//           the Bingham update (P2, S1: Posteriors.py:497-530, Stats.py:375-382), the ARD update and the log
+//           omega_hat table; k_scale_warp / k_scale then solve for omega;
+//   k_mid2  (main stream, beside k_ard) re-derives the same axis update per CTA and finishes S2 for its regions:
+//           a, m2, cm2 (Stats.py:67-100).
 // `lpi` lanes (power of two) share the run loop of one item on coarse layers where a region has many runs.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMidThreads = 256;
@@ -883,7 +885,7 @@ constexpr int kMidThreads = 256;
 template <int DY>
 __global__ void __launch_bounds__(kMidThreads) k_mid1(RegionArgs a, int lpi, int regions_per_cta) {
     static_assert(DY == 2, "dy == 2 only");
-    extern __shared__ double sm[];   // contrib[32 * M * 4] + sums[96]; last CTA: omega[M*M], primeB[M*4], data[96]
+    extern __shared__ double sm[];   // contrib[32 * M * 4], contribW[32 * M * 4], sums[NVP], sumsW[NVWP]
     const int M = a.M, tid = threadIdx.x, NV = M * 3, NVP = (NV + 31) & ~31;   // NVP: padded length of a B-sum vector
     const int NVW = M * 4, NVWP = (NVW + 31) & ~31;                                // ... of the ARD-sum vector
     double *sContrib = sm, *sContribW = sm + 32 * M * 4, *sSum = sContribW + 32 * M * 4, *sSumW = sSum + NVP;
