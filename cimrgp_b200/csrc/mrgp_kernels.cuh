@@ -1068,10 +1068,11 @@ __global__ void __launch_bounds__(kMidThreads) k_mid2(RegionArgs a, int regions_
     ts_end(a.ts, a.layer * 4 + 1);
 }
 
-// ci, off the critical path (side stream): ARD posterior and moments from the per-CTA m2/S sums of
-// k_mid_ci (Posteriors.py:533-541, Stats.py:385-388), the log omega_hat table (Stats.py:405-412) and the
-// doubly-stochastic scaling omega (Stats.py:413-420) by the warm-up + Newton scheme of omega_solve_serial
-// (mrgp_math.cuh), one block of 256 threads, warp per matrix row / column.
+// ci, side stream, the critical chain of the sweep: shared axis update from the region sums of k_mid1 (P2, S1),
+// ARD posterior and moments (Posteriors.py:533-541, Stats.py:385-388), the log omega_hat table (Stats.py:405-412)
+// with its shifts and exponentials (k_ard, one block); then the doubly-stochastic scaling omega
+// (Stats.py:413-420) by the Sinkhorn / Newton scheme of omega_solve_serial (mrgp_math.cuh): k_scale_warp (one
+// warp, registers) for M <= 32, k_scale (one block, shared memory) otherwise.
 constexpr int kOmegaThreads = 256;
 
 __host__ __device__ inline size_t omega_smem_doubles(int M) { return (size_t)3 * M * M + 24 * M + 8 + 3 * ((3 * M + 31) & ~31) + 4 * M; }
