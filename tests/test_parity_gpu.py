@@ -521,3 +521,19 @@ def test_elbo_under_adaptive_intervals_matches_reference(name):
     m.fit(n_iter=n_iter, tol=1e-300, min_iter=n_iter)
     assert mismatch(np.array(m.lower_bound_terms), g['terms'], RTOL) is None
     assert mismatch(np.array(m.lower_bound_layer), g['lower_bound_layer'], RTOL) is None
+
+
+@pytest.mark.parametrize('fi', [False, True])
+def test_smallest_compiled_basis_against_oracle(fi):
+    """n_basis = 8: the smallest instantiation of the streaming kernels, the one-warp omega solve and the invariant
+    builders (30 and 20 are covered by the goldens and the tests above, 40 by config 2 with the block solver)."""
+    x, y = workloads.workload1(2500)
+    offsets = O.uniform_offsets(2500, 4, 2)
+    ora = O.OracleMRGP(x, y, 8, offsets, mode='fi' if fi else 'ci')
+    m = build(x, y, 8, 4, fi)
+    for _ in range(3):
+        ora.sweep()
+    m.fit(3, None)
+    compare(m._engine.state(), ora.state())
+    if not fi:
+        assert mismatch(m._engine.elbo(), ora.elbo()[2], RTOL) is None
