@@ -537,3 +537,18 @@ def test_smallest_compiled_basis_against_oracle(fi):
     compare(m._engine.state(), ora.state())
     if not fi:
         assert mismatch(m._engine.elbo(), ora.elbo()[2], RTOL) is None
+
+
+@pytest.mark.parametrize('fi', [False, True])
+def test_single_layer_model_against_oracle(fi):
+    """resolution 0: one layer, one region - no closed-form layers, no third stream, nothing to propagate."""
+    x, y = workloads.workload1(777)
+    offsets = O.uniform_offsets(777, 0, 2)
+    ora = O.OracleMRGP(x, y, 20, offsets, mode='fi' if fi else 'ci')
+    m = build(x, y, 20, 0, fi)
+    for _ in range(3):
+        ora.sweep()
+    m.fit(3, None)
+    compare(m._engine.state(), ora.state())
+    xt = np.atleast_2d(np.linspace(1, 3, 100)).T
+    assert mismatch(m.get_predicted_mean(xt), ora.predict_mean(xt), RTOL) is None
