@@ -552,3 +552,19 @@ def test_single_layer_model_against_oracle(fi):
     compare(m._engine.state(), ora.state())
     xt = np.atleast_2d(np.linspace(1, 3, 100)).T
     assert mismatch(m.get_predicted_mean(xt), ora.predict_mean(xt), RTOL) is None
+
+
+def test_divider_three_and_block_omega_solver_against_oracle():
+    """divider 3 (27 regions on the finest layer, none nested in thirds of 5000) with n_basis = 40: the block version
+    of the omega solve, the table built by k_ard, closed-form statistics over three-way splits; with the ELBO."""
+    from cimrgp_b200 import IndexSetUniform, LaplacianEigenpairs, MaternKernel
+    from cimrgp_b200.MRGP import MultiResolutionGaussianProcess
+    x, y = workloads.workload1(5000)
+    idx = IndexSetUniform(5000, 3, 3)
+    m = MultiResolutionGaussianProcess([x, y], 40, idx, LaplacianEigenpairs(), MaternKernel(1, 1, 1))
+    ora = O.OracleMRGP(x, y, 40, idx.offsets, mode='ci')
+    for _ in range(3):
+        ora.sweep()
+    m.fit(3, None)
+    compare(m._engine.state(), ora.state())
+    assert mismatch(m._engine.elbo(), ora.elbo()[2], RTOL) is None
