@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <unistd.h>
@@ -88,6 +90,7 @@ struct mrgp_handle {
     size_t ws_bytes = 0;
     char *ws = nullptr;
     bool bound = false, have_data = false, state_init = false;
+    bool ystats_valid = false;   // layer-0 sufficient statistics Phi^T y, sum y, sum |y|^2 match the current x, y, intervals
     bool sharded = false;
     int64_t lo = 0, hi = 0;   // owned samples [lo, hi)
     double *xchg = nullptr;   // dense exchange buffer (max R) x part_stride
@@ -544,11 +547,27 @@ constexpr size_t kRedSmemBytes = kRedSmemDoubles * sizeof(double);
 
 // Every kernel of the sweep asks for the same (maximum) shared-memory carveout: switching the L1 / shared split
 // between consecutive kernels drains and reconfigures the SMs, which costs more than the small kernels run.
+// The dynamic shared-memory limit of a kernel is process-wide state that captured graphs of other models rely on:
+// it is only ever RAISED (a high-water mark per kernel function, guarded by a mutex), never rewritten to a smaller
+// launch's size.
+std::mutex g_smem_mu;
+std::map<const void *, size_t> g_smem_high_water;
+
 template <typename K>
 cudaError_t set_smem(K kernel, size_t bytes) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 1));
+    std::lock_guard<std::mutex> lock(g_smem_mu);
+    const void *key = reinterpret_cast<const void *>(kernel);
+    auto it = g_smem_high_water.find(key);
+    if (it == g_smem_high_water.end()) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        it = g_smem_high_water.emplace(key, 0).first;
+    }
+    bytes = std::max<size_t>(bytes, 1);
+    if (bytes <= it->second) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) it->second = bytes;
+    return e;
 }
 
 template <int M>
@@ -626,6 +645,10 @@ int check_ready(mrgp_handle *h, int layer, bool need_state) {
     if (!h->have_data) return fail(h, MRGP_ESTATE, "no data set");
     if (layer < 0 || layer >= h->cfg.n_layers) return fail(h, MRGP_EINVAL, "layer %d out of range", layer);
     if (need_state && !h->state_init) return fail(h, MRGP_ESTATE, "state not initialised");
+    if (need_state)
+        for (int j = 0; j < h->cfg.n_layers; ++j)
+            if (!h->dev[j].basis_built)
+                return fail(h, MRGP_ESTATE, "the inputs changed: rebuild the basis of layer %d (mrgp_build_basis) before the next phase or sweep", j);
     return MRGP_OK;
 }
 
@@ -1378,11 +1401,22 @@ int mrgp_set_stream(mrgp_handle *h, void *cuda_stream) {
     return MRGP_OK;
 }
 
+// New inputs x: everything derived from them (intervals, lambda, S, sum phi^2, the invariants of the closed-form
+// statistics, the captured graph) is stale.  The basis of every layer has to be rebuilt before the next phase / sweep.
+static void invalidate_inputs(mrgp_handle *h) {
+    for (auto &d : h->dev) {
+        d.basis_built = false;
+        d.inv_built = false;
+    }
+    h->ystats_valid = false;
+    drop_graph(h);
+}
+
 int mrgp_set_data(mrgp_handle *h, const double *x_dev, const double *y_dev) {
     if (!h || !x_dev || !y_dev) return fail(h, MRGP_EINVAL, "null argument");
     if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
     if (((uintptr_t)y_dev & 15) != 0 || ((uintptr_t)x_dev & 15) != 0) return fail(h, MRGP_EINVAL, "x and y must be 16-byte aligned (bulk copies)");
-    if (h->x != x_dev || h->y != y_dev) drop_graph(h);
+    if (h->have_data) invalidate_inputs(h);
     h->x = x_dev;
     h->y = y_dev;
     h->have_data = true;
@@ -1395,10 +1429,31 @@ int mrgp_set_data_host(mrgp_handle *h, const double *x_host, const double *y_hos
     const size_t N = (size_t)(h->hi - h->lo);
     CK(cudaMemcpyAsync(h->x_ws, x_host, N * h->cfg.dx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->y_ws, y_host, N * h->cfg.dy * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (h->x != h->x_ws || h->y != h->y_ws) drop_graph(h);
+    if (h->have_data) invalidate_inputs(h);
     h->x = h->x_ws;
     h->y = h->y_ws;
     h->have_data = true;
+    return MRGP_OK;
+}
+
+int mrgp_set_observations(mrgp_handle *h, const double *y_dev) {
+    if (!h || !y_dev) return fail(h, MRGP_EINVAL, "null argument");
+    if (!h->have_data) return fail(h, MRGP_ESTATE, "no inputs yet: mrgp_set_data / mrgp_set_data_host first");
+    if (((uintptr_t)y_dev & 15) != 0) return fail(h, MRGP_EINVAL, "y must be 16-byte aligned (bulk copies)");
+    if (h->y != y_dev) drop_graph(h);   // the captured kernels hold the pointer
+    h->y = y_dev;
+    h->ystats_valid = false;
+    return MRGP_OK;
+}
+
+int mrgp_set_observations_host(mrgp_handle *h, const double *y_host) {
+    if (!h || !y_host) return fail(h, MRGP_EINVAL, "null argument");
+    if (!h->have_data) return fail(h, MRGP_ESTATE, "no inputs yet: mrgp_set_data / mrgp_set_data_host first");
+    const size_t N = (size_t)(h->hi - h->lo);
+    CK(cudaMemcpyAsync(h->y_ws, y_host, N * h->cfg.dy * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->y != h->y_ws) drop_graph(h);
+    h->y = h->y_ws;
+    h->ystats_valid = false;
     return MRGP_OK;
 }
 
@@ -1464,6 +1519,7 @@ int mrgp_build_basis(mrgp_handle *h, int32_t layer, double interval_factor, cons
     count(h);
     d.basis_built = true;
     for (int jj = layer; jj < h->cfg.n_layers; ++jj) h->dev[jj].inv_built = false;   // s, G of the layer; D of the finer ones
+    h->ystats_valid = false;
     drop_graph(h);
     return MRGP_OK;
 }
@@ -2073,6 +2129,9 @@ int mrgp_build_basis_stage(mrgp_handle *h, int32_t layer, int32_t stage, double 
         CK(cudaGetLastError());
         count(h);
         d.basis_built = true;
+        for (int jj = layer; jj < h->cfg.n_layers; ++jj) h->dev[jj].inv_built = false;   // s, G of the layer; D of the finer ones
+        h->ystats_valid = false;
+        drop_graph(h);
     } else {
         return fail(h, MRGP_EINVAL, "stage must be 0, 1 or 2");
     }

@@ -2056,7 +2056,23 @@ struct BrentArgs {
     int32_t maxfun;
 };
 
-// One warp per region.  Transcription of scipy.optimize._optimize._minimize_scalar_bounded (SciPy 1.18.1).
+// One warp per region.  Step-exact transcription of scipy.optimize._optimize._minimize_scalar_bounded (SciPy 1.18.1),
+// required for parity.  That routine is
+//   Copyright (c) 2001-2002 Enthought, Inc. 2003, SciPy Developers.  All rights reserved.
+//   Redistribution and use in source and binary forms, with or without modification, are permitted provided that the
+//   following conditions are met: 1. Redistributions of source code must retain the above copyright notice, this
+//   list of conditions and the following disclaimer.  2. Redistributions in binary form must reproduce the above
+//   copyright notice, this list of conditions and the following disclaimer in the documentation and/or other
+//   materials provided with the distribution.  3. Neither the name of the copyright holder nor the names of its
+//   contributors may be used to endorse or promote products derived from this software without specific prior
+//   written permission.
+//   THIS SOFTWARE IS PROVIDED BY THE COPYRIGHT HOLDERS AND CONTRIBUTORS "AS IS" AND ANY EXPRESS OR IMPLIED WARRANTIES,
+//   INCLUDING, BUT NOT LIMITED TO, THE IMPLIED WARRANTIES OF MERCHANTABILITY AND FITNESS FOR A PARTICULAR PURPOSE ARE
+//   DISCLAIMED.  IN NO EVENT SHALL THE COPYRIGHT OWNER OR CONTRIBUTORS BE LIABLE FOR ANY DIRECT, INDIRECT, INCIDENTAL,
+//   SPECIAL, EXEMPLARY, OR CONSEQUENTIAL DAMAGES (INCLUDING, BUT NOT LIMITED TO, PROCUREMENT OF SUBSTITUTE GOODS OR
+//   SERVICES; LOSS OF USE, DATA, OR PROFITS; OR BUSINESS INTERRUPTION) HOWEVER CAUSED AND ON ANY THEORY OF LIABILITY,
+//   WHETHER IN CONTRACT, STRICT LIABILITY, OR TORT (INCLUDING NEGLIGENCE OR OTHERWISE) ARISING IN ANY WAY OUT OF THE
+//   USE OF THIS SOFTWARE, EVEN IF ADVISED OF THE POSSIBILITY OF SUCH DAMAGE.                    (BSD 3-clause, SciPy)
 __global__ void k_brent_step(BrentArgs a) {
     using B = BrentState;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

@@ -57,9 +57,12 @@ class ShardedEngine(Engine):
         if self.exchange not in ('peer', 'nccl'):
             raise ValueError("exchange must be 'peer' or 'nccl'")
         n_total = int(offsets[0][-1])
+        # the same deterministic check on every rank, BEFORE any collective: either all ranks raise or none does
+        empty = [q for q in range(world_size) if chunk_bounds(n_total, world_size, q)[1] <= chunk_bounds(n_total, world_size, q)[0]]
+        if empty:
+            raise ValueError('%d samples over %d ranks in 32-aligned chunks leave rank(s) %s without samples: use at '
+                             'most %d ranks' % (n_total, world_size, empty, max(1, -(-n_total // 32))))
         lo, hi = chunk_bounds(n_total, world_size, rank)
-        if hi <= lo:
-            raise ValueError('rank %d owns no samples' % rank)
         Engine.__init__(self, x_norm[lo:hi], y[lo:hi], offsets, n_basis, chunk=(lo, hi), defer_build=True, **kw)
         torch = self.torch
         self._graph, self._xchg = None, []
@@ -108,8 +111,11 @@ class ShardedEngine(Engine):
         Engine.close(self)
 
     def __del__(self):
+        # Never a collective from the garbage collector.  Call close() explicitly on every rank (it synchronises and
+        # meets the peers at a barrier before the arena is freed): a rank that is merely garbage-collected frees its
+        # arena while peers may still read it.
         try:
-            Engine.close(self)      # never a collective from the garbage collector
+            Engine.close(self)
         except Exception:
             pass
 
@@ -142,6 +148,8 @@ class ShardedEngine(Engine):
     def sweep(self, n_iter=1, use_graph=None):
         import os
         torch = self.torch
+        if n_iter <= 0:
+            return
         if self.exchange == 'peer':
             if use_graph is False:
                 for _ in range(n_iter):

@@ -86,6 +86,7 @@ class Engine(object):
         if not defer_build:
             self._ck(self.lib.mrgp_init_state(self.handle, float(noise_var0), float(ard_prior_influence)))
             self.synchronize()
+        self._constructed = True
 
     @staticmethod
     def probe_workspace_bytes(offsets, n_basis, dy=2, mode='ci', n_ctas=0, device=0):
@@ -121,7 +122,11 @@ class Engine(object):
             pass
 
     def set_data(self, x_norm, y):
+        """Inputs AND observations.  After construction this invalidates everything derived from x on the device
+        (include/cimrgp.h, mrgp_set_data*): the basis of every layer is rebuilt here with the static interval rule
+        (BasisInterval.py:15-16); the variational state is kept."""
         torch = self.torch
+        rebuild = getattr(self, '_constructed', False)
         if isinstance(x_norm, np.ndarray):
             x_h = np.ascontiguousarray(x_norm, dtype=np.float64).reshape(self.N, self.dx)
             y_h = np.ascontiguousarray(y, dtype=np.float64).reshape(self.N, self.dy)
@@ -130,18 +135,33 @@ class Engine(object):
                                 torch.empty((self.N, self.dy), dtype=torch.float64).pin_memory())
             self._pinned[0].numpy()[...] = x_h
             self._pinned[1].numpy()[...] = y_h
-            self.copy_in_from_pinned()
+            self._ck(self.lib.mrgp_set_data_host(self.handle, C.c_void_p(self._pinned[0].data_ptr()),
+                                                 C.c_void_p(self._pinned[1].data_ptr())))
             self.x_dev = self.y_dev = None
         else:
             self.x_dev = x_norm.to(device=self.device, dtype=torch.float64).contiguous()
             self.y_dev = y.to(device=self.device, dtype=torch.float64).contiguous()
             self._ck(self.lib.mrgp_set_data(self.handle, C.c_void_p(self.x_dev.data_ptr()),
                                             C.c_void_p(self.y_dev.data_ptr())))
+        if rebuild:
+            for j in range(self.J):
+                self.build_basis(j, self._interval_factor[j])
 
-    def copy_in_from_pinned(self):
-        """Asynchronous H2D of the pinned (x, y) staging buffers on the engine's stream."""
-        self._ck(self.lib.mrgp_set_data_host(self.handle, C.c_void_p(self._pinned[0].data_ptr()),
-                                             C.c_void_p(self._pinned[1].data_ptr())))
+    def set_observations(self, y):
+        """New observations at the same inputs (NumPy array: staged in pinned memory; torch CUDA tensor: borrowed)."""
+        torch = self.torch
+        if isinstance(y, np.ndarray):
+            if self._pinned is None:
+                raise ValueError('this engine borrows device tensors: pass a CUDA tensor')
+            self._pinned[1].numpy()[...] = np.ascontiguousarray(y, dtype=np.float64).reshape(self.N, self.dy)
+            self.upload_observations()
+        else:
+            self.y_dev = y.to(device=self.device, dtype=torch.float64).contiguous()
+            self._ck(self.lib.mrgp_set_observations(self.handle, C.c_void_p(self.y_dev.data_ptr())))
+
+    def upload_observations(self):
+        """Asynchronous H2D of the pinned y staging buffer on the engine's stream (16 B per sample)."""
+        self._ck(self.lib.mrgp_set_observations_host(self.handle, C.c_void_p(self._pinned[1].data_ptr())))
 
     def build_basis(self, layer, interval_factor=1.0, intervals=None):
         if intervals is None:

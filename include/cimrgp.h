@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MRGP_ABI_VERSION 2
+#define MRGP_ABI_VERSION 3
 
 enum {
     MRGP_OK = 0,
@@ -127,15 +127,21 @@ int mrgp_set_stream(mrgp_handle *h, void *cuda_stream);
 /* ---- data ------------------------------------------------------------------------------------ */
 
 /* Normalised inputs x (N, dx) and observations y (N, dy), already on the device (MRGP.py:61-69).
- * The pointers are borrowed: they must stay valid while the handle is used.                        */
+ * The pointers are borrowed: they must stay valid while the handle is used.
+ * NEW INPUTS INVALIDATE EVERYTHING DERIVED FROM x: after the first call, every further mrgp_set_data /
+ * mrgp_set_data_host marks the basis of all layers (intervals, lambda, S, sum phi^2), the invariants of the
+ * closed-form statistics and the captured sweep as stale; phases and sweeps then fail with MRGP_ESTATE until
+ * mrgp_build_basis has run for every layer again (the reference needs a new model object for new inputs,
+ * MRGP.py:128-172).  New observations at the SAME inputs go through mrgp_set_observations*, which keep all of
+ * that (only the layer-0 sufficient statistics Phi^T y, sum y, sum |y|^2 are refreshed by the next sweep).     */
 int mrgp_set_data(mrgp_handle *h, const double *x_dev, const double *y_dev);
-/* Same from host buffers (pinned for full speed): asynchronous H2D copies on the handle's stream into
- * the workspace.  This is the entry the end-to-end benchmark times.
- * Everything derived from x alone - the basis intervals, lambda, S, sum phi^2 and the invariants of the
- * closed-form statistics - is built by mrgp_build_basis / the first mrgp_sweep and is NOT refreshed here: new
- * observations y at the same inputs need nothing else, new inputs x need mrgp_build_basis for every layer again
- * (as the reference needs a new model object, MRGP.py:128-172).                                      */
+/* Same from host buffers (pinned for full speed): asynchronous H2D copies on the handle's stream into the
+ * workspace.                                                                                                   */
 int mrgp_set_data_host(mrgp_handle *h, const double *x_host, const double *y_host);
+/* New observations y (N, dy) at unchanged inputs: borrowed device pointer / asynchronous copy from host memory.
+ * mrgp_set_observations_host is the entry the end-to-end benchmark times (16 B per sample and step).           */
+int mrgp_set_observations(mrgp_handle *h, const double *y_dev);
+int mrgp_set_observations_host(mrgp_handle *h, const double *y_host);
 
 /* ---- K1-K3: basis intervals, eigenvalues, spectral density, sum phi^2 ---------------------------- */
 

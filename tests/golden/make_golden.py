@@ -269,6 +269,9 @@ JOBS = {
                                      input_model=workloads.InterpInputModel(workloads.workload2()[0])),
     'c1_ci_adaptive_elbo': lambda: run_elbo('c1_ci_adaptive_elbo', *workloads.workload1(32), 30, 5, 3, adaptive=True),
     'n600_ci_adaptive_elbo': lambda: run_elbo('n600_ci_adaptive_elbo', *workloads.workload1(600), 20, 3, 3, adaptive=True),
+    # one series of BASELINE config 5 (N = 2048, 6 resolutions, seed 10 + s with s = 0 and s = 3)
+    'c5_ci': lambda: run_sweeps('c5_ci', *workloads.workload1(2048, seed=10), 30, 5, False, [1, 3]),
+    'c5_fi': lambda: run_sweeps('c5_fi', *workloads.workload1(2048, seed=13), 30, 5, True, [1, 3]),
     'n600_ci_snr_shared': lambda: run_sweeps('n600_ci_snr', *workloads.workload1(600), 20, 3, False, [1, 3],
                                              snr_ratio=10.),
 }

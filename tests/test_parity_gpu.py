@@ -568,3 +568,72 @@ def test_divider_three_and_block_omega_solver_against_oracle():
     m.fit(3, None)
     compare(m._engine.state(), ora.state())
     assert mismatch(m._engine.elbo(), ora.elbo()[2], RTOL) is None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE configs 3, 4 and 5 at their full sizes ("pin configs 3 and 4 at full size")
+# ------------------------------------------------------------------------------------------------------------
+def _oracle_vs_device_at_size(n, resolution, fi, checkpoints, elbo):
+    x, y = workloads.workload1(n)
+    ora = O.OracleMRGP(x, y, 30, O.uniform_offsets(n, resolution, 2), mode='fi' if fi else 'ci')
+    m = build(x, y, 30, resolution, fi)
+    done = 0
+    for k in checkpoints:
+        for _ in range(k - done):
+            ora.sweep()
+        m.fit(k - done, None)
+        done = k
+        compare(m._engine.state(), ora.state())
+    if elbo:
+        assert mismatch(m._engine.elbo(), ora.elbo()[2], RTOL) is None     # per layer and per term
+    return m, ora
+
+
+@pytest.mark.parametrize('fi', [False, True])
+def test_config3_full_size_against_oracle(fi):
+    """BASELINE config 3: N = 1e5, 8 resolutions (255 regions), M = 30: every state array after 1 and 3 sweeps and
+    (ci) the six ELBO terms per layer against the CPU oracle at the SURVEY §8c rule."""
+    _oracle_vs_device_at_size(100000, 7, fi, (1, 3), elbo=not fi)
+
+
+def test_config4_full_size_against_oracle():
+    """BASELINE config 4 (the headline): N = 1e6, 10 resolutions (1023 regions), M = 30, ci: state after 1 and 3 sweeps
+    and the ELBO per term against the CPU oracle (the oracle needs ~45 s per sweep at this size)."""
+    _oracle_vs_device_at_size(1000000, 9, False, (1, 3), elbo=True)
+
+
+def test_config4_closed_form_statistics_at_full_size_on_a_non_inert_state(monkeypatch):
+    """The cancellation test of the Gram-based closed forms at N = 1e6: on a state whose upper layers carry signal
+    (coefficients and biases set by hand) the captured sweep (sufficient statistics / closed-form layer statistics)
+    must agree with the sweep that streams every layer over the samples (MRGP_STREAM_ALL=1) to 1e-9."""
+    from cimrgp_b200 import _lib
+    n, res = 1000000, 9
+    x, y = workloads.workload1(n)
+    rng = np.random.RandomState(7)
+    pert = [(0.05 * rng.standard_normal((2 ** j, 30, 2)), 0.3 * rng.standard_normal((2 ** j, 2))) for j in range(res + 1)]
+    states = []
+    for stream_all in ('0', '1'):
+        monkeypatch.setenv('MRGP_STREAM_ALL', stream_all)
+        m = build(x, y, 30, res, False)
+        m.fit(2, None)
+        for j in range(1, res + 1):
+            m._engine.put(j, _lib.F_A, pert[j][0])
+            m._engine.put(j, _lib.F_BIAS_MEAN, pert[j][1])
+        m.fit(2, None)
+        states.append(m._engine.state(latent=False))
+        del m
+    assert np.max(np.abs(states[1]['L5.ytil'])) > 1e-3          # the upper layers really carry signal here
+    compare(states[0], states[1], rtol=1e-9)
+
+
+@pytest.mark.parametrize('name,fi', [('c5_ci', False), ('c5_fi', True)])
+def test_config5_series_matches_reference_golden(name, fi):
+    """One series of BASELINE config 5 (N = 2048, 6 resolutions, M = 30) against the unmodified reference."""
+    g = load(name)
+    m = build(g['x'], g['y'], int(g['meta.M']), int(g['meta.resolution']), fi)
+    compare(m._engine.state(), split(g, 'k0.'))
+    done = 0
+    for k in g['meta.checkpoints']:
+        m.fit(int(k) - done, None)
+        done = int(k)
+        compare(m._engine.state(), split(g, 'k%d.' % k))
