@@ -1,0 +1,656 @@
+// Fused ci sweep for sm_100a: one thread-block cluster per model runs ALL layers of one variational sweep
+// (MRGP.py:571-652, static basis intervals) in a single kernel.  See mrgp_chain.h for the why.
+//
+// Roles inside a cluster of C CTAs x 256 threads:
+//   * warp 0 of CTA 0 is the SOLVER: the doubly-stochastic scaling omega (Stats.py:413-420) with the table in its
+//     registers (one lane per row), exactly the scheme of omega_solve_serial (mrgp_math.cuh);
+//   * every other warp is a WORKER: a region of a layer belongs to one worker warp (lane = basis function) for all
+//     of its per-region steps: P1-finish (y_tilde, precision, zeta: Posteriors.py:35-78), S2 (a, m2, cm2:
+//     Stats.py:67-100), P4 / P5 / S5 (bias and noise posteriors from closed-form statistics: Posteriors.py:81-148,
+//     Stats.py:102-124);
+//   * CTA 0 as a whole does the shared step of a layer (P2, P2a-c, S1, P3, S3 and the log omega_hat table:
+//     Posteriors.py:497-541, Stats.py:375-412) from the region sums that the CTAs leave in their shared memory
+//     (read over DSMEM).
+// Per layer: cluster barrier, shared step on CTA 0, cluster barrier, then the solver works on omega(j) WHILE the
+// workers finish layer j (S2, P4/P5) and prepare the region sums of layer j + 1 (which need the ARD moments of layer
+// j but not omega(j)).  Sums are formed in a fixed order: results are bit-reproducible for a cluster size.
+#include "mrgp_chain.h"
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include "mrgp_math.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mrgp {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double wmax(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void worker_bar(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
+
+constexpr int LD = 34;    // row stride of the transposed tables: conflict-free columns, 16-byte aligned rows
+constexpr int LW = 33;    // row stride of the log omega_hat table
+
+struct ChainSmem {
+    double omT[32 * LD];      // omega transposed: omT[k * LD + i] = omega_ik
+    double T[32 * LD];        // solver scratch (transposes, Cholesky columns)
+    double Kt[32 * LD];       // shifted, exponentiated table, column-major: Kt[k * LD + i] = K_ik
+    double lw[32 * LW];       // log omega_hat, row-major
+    double primeB[32 * 4], primeLogC[32], primeShape[32], primeScale[32], sk[32], skNext[32];
+    double B[32 * 4], kappa[32 * 2], rho[32 * 2], logC[32], cov[32 * 4], shape[32], scale[32], mean[32], lmean[32];
+    double part[8][7][32];    // per-warp region sums of the P1-finish step
+    double ctaPart[7 * 32];   // per-CTA sums, read by CTA 0 over DSMEM
+    double data[7 * 32];      // cluster sums (CTA 0)
+    double pub[4 * 32];       // CTA 0: axis covariance (c00, c01, c11) and ARD mean of the layer, read by every CTA
+    double loc[4 * 32];       // local copy of pub
+    double rowmax[32], colmax[32];
+    int nchol;
+};
+
+// ---- worker steps (one warp per region, lane = basis function) --------------------------------------------------
+
+// P1-finish of region l of layer j (Posteriors.py:35-78) and its contribution to the sums over regions that the shared
+// step needs: 0.5 noise zeta y y^T (B_i, Posteriors.py:507-517) and the two terms that make sum_l m2/S linear in the
+// axis covariance (ARD, Posteriors.py:533-541; see k_mid1).  Layer 0 (observed targets, no latent function):
+//     y_tilde_i = (Phi^T y)_i - s_i b - sum_{k != i} G_ik a_k         (from the sufficient statistics of y)
+// layers above (targets inferred from the layer's own posterior, LatentOutputs.py:20-49): y_tilde_i = d_i a_i.
+__device__ __forceinline__ void mid1_region(const ChainModel &m, const ChainLayer &ly, int j, int l, int lane, const double *ardMean,
+                                            double (&acc)[7]) {
+    const int M = m.M;
+    const bool on = lane < M;
+    const size_t ri = (size_t)l * M + (on ? lane : 0);
+    const double a0 = on ? __ldcg(ly.A + ri * 2) : 0.0, a1 = on ? __ldcg(ly.A + ri * 2 + 1) : 0.0;
+    const double dsum = on ? ly.d[ri] : 0.0, S = on ? ly.S[ri] : 1.0;
+    const double noise = __ldcg(ly.noise_mean + l);
+    double y0, y1;
+    if (j == 0) {
+        const double b0 = __ldcg(ly.bias_mean + (size_t)l * 2), b1 = __ldcg(ly.bias_mean + (size_t)l * 2 + 1);
+        const double s = on ? ly.sumPhi[ri] : 0.0;
+        double t0 = on ? fma(-s, b0, ly.yc[ri * 2]) : 0.0, t1 = on ? fma(-s, b1, ly.yc[ri * 2 + 1]) : 0.0;
+        const double *G = ly.gram + (size_t)l * M * M;
+        for (int k = 0; k < M; ++k) {
+            const double ak0 = __shfl_sync(kFull, a0, k), ak1 = __shfl_sync(kFull, a1, k);
+            const double g = (on && k != lane) ? G[(size_t)k * M + lane] : 0.0;
+            t0 = fma(-g, ak0, t0);
+            t1 = fma(-g, ak1, t1);
+        }
+        y0 = t0;
+        y1 = t1;
+    } else {
+        y0 = dsum * a0;
+        y1 = dsum * a1;
+    }
+    if (!on) return;
+    const double prec = ardMean[lane] / S + noise * dsum;      // Posteriors.py:40-42
+    const double zeta = noise / prec;
+    ly.ytil[ri * 2] = y0;
+    ly.ytil[ri * 2 + 1] = y1;
+    ly.prec[ri] = prec;
+    ly.zeta[ri] = zeta;
+    const double w = 0.5 * noise * zeta;
+    acc[0] += w * (y0 * y0);
+    acc[1] += w * (y0 * y1);
+    acc[2] += w * (y1 * y1);
+    const double is = 1.0 / S, z2s = zeta * zeta * is;
+    acc[3] += is / prec;
+    acc[4] += z2s * (y0 * y0);
+    acc[5] += z2s * (y0 * y1);
+    acc[6] += z2s * (y1 * y1);
+}
+
+// S2 of region l (Stats.py:67-100) with the layer's new axis covariance, then the P4 / P5 statistics of the region in
+// closed form and its bias / noise update (Posteriors.py:81-93, 132-148; Stats.py:102-124).
+//   layer 0:  r = y - Phi A_new:   sum r = sum y - A^T s,   sum |r|^2 = sum |y|^2 - 2 tr(A^T Phi^T y) + tr(A^T G A)
+//   layer j:  r = Phi (A_old - A_new) + b_old (see k_stats_b), sum f_var from the pieces region x coarser region.
+__device__ __forceinline__ void mid2_stats_region(const ChainModel &m, const ChainLayer &ly, int j, int l, int lane, const double *cov) {
+    const int M = m.M;
+    const bool on = lane < M;
+    const size_t ri = (size_t)l * M + (on ? lane : 0);
+    const double c00 = cov[lane], c01 = cov[32 + lane], c11 = cov[64 + lane];
+    const double y0 = on ? ly.ytil[ri * 2] : 0.0, y1 = on ? ly.ytil[ri * 2 + 1] : 0.0;
+    const double zeta = on ? ly.zeta[ri] : 0.0, prec = on ? ly.prec[ri] : 1.0;
+    const double ao0 = on ? __ldcg(ly.A + ri * 2) : 0.0, ao1 = on ? __ldcg(ly.A + ri * 2 + 1) : 0.0;
+    const double cy0 = c00 * y0 + c01 * y1, cy1 = c01 * y0 + c11 * y1;
+    const double an0 = zeta * cy0, an1 = zeta * cy1;
+    const double z2 = zeta * zeta;
+    const double ccy0 = c00 * cy0 + c01 * cy1, ccy1 = c01 * cy0 + c11 * cy1;
+    const double m2 = 1.0 / prec + z2 * (y0 * cy0 + y1 * cy1);
+    const double cm2 = 1.0 / prec + z2 * (y0 * (cy0 - ccy0) + y1 * (cy1 - ccy1));
+    if (on) {
+        ly.A_prev[ri * 2] = ao0;
+        ly.A_prev[ri * 2 + 1] = ao1;
+        ly.A[ri * 2] = an0;
+        ly.A[ri * 2 + 1] = an1;
+        ly.m2[ri] = m2;
+        ly.cm2[ri] = cm2;
+    }
+    // ---- statistics --------------------------------------------------------------------------------------------
+    const double n = (double)(ly.offsets[l + 1] - ly.offsets[l]);
+    const double dsum = on ? ly.d[ri] : 0.0, si = on ? ly.sumPhi[ri] : 0.0;
+    const double dc = wsum(on ? dsum * cm2 : 0.0);
+    const double *G = ly.gram + (size_t)l * M * M;
+    double sums[5];
+    if (j == 0) {
+        const double sa0 = wsum(on ? si * an0 : 0.0), sa1 = wsum(on ? si * an1 : 0.0);
+        const double cross = wsum(on ? an0 * ly.yc[ri * 2] + an1 * ly.yc[ri * 2 + 1] : 0.0);
+        double t0 = 0.0, t1 = 0.0;
+        for (int k = 0; k < M; ++k) {
+            const double g = on ? G[(size_t)k * M + lane] : 0.0;
+            t0 = fma(g, __shfl_sync(kFull, an0, k), t0);
+            t1 = fma(g, __shfl_sync(kFull, an1, k), t1);
+        }
+        const double quad = wsum(on ? an0 * t0 + an1 * t1 : 0.0);
+        const double y2 = ly.ysum[(size_t)l * 4 + 2];
+        sums[0] = ly.ysum[(size_t)l * 4 + 0] - sa0;
+        sums[1] = ly.ysum[(size_t)l * 4 + 1] - sa1;
+        sums[2] = (y2 - 2.0 * cross) + quad;
+        sums[3] = 0.0;
+        sums[4] = dc;
+        if (lane == 0 && l == 0) {
+            const double ratio = y2 > 0.0 ? sums[2] / y2 : 1.0;
+            m.guard[0] = ratio;
+            if (!(ratio >= kChainGuard)) atomicOr(m.status, 1u);
+        }
+    } else {
+        const double dA0 = ao0 - an0, dA1 = ao1 - an1;
+        const double sd0 = wsum(si * dA0), sd1 = wsum(si * dA1);
+        double quad = 0.0;
+        if (__any_sync(kFull, dA0 != 0.0 || dA1 != 0.0)) {
+            double t0 = 0.0, t1 = 0.0;
+            for (int k = 0; k < M; ++k) {
+                const double g = on ? G[(size_t)k * M + lane] : 0.0;
+                t0 = fma(g, __shfl_sync(kFull, dA0, k), t0);
+                t1 = fma(g, __shfl_sync(kFull, dA1, k), t1);
+            }
+            quad = wsum(dA0 * t0 + dA1 * t1);
+        }
+        double t = 0.0, lenbv = 0.0;
+        for (int jp = 0; jp < j; ++jp) {
+            const ChainLayer &anc = m.layer[jp];
+            const int32_t *pp = ly.pc_ptr + (size_t)jp * (ly.R + 1) + l;
+            for (int pc = pp[0]; pc < pp[1]; ++pc) {
+                const int a = ly.pc_anc[pc];
+                if (on) t = fma(__ldcg(anc.cm2 + (size_t)a * M + lane), ly.ancD[(size_t)pc * M + lane], t);
+                lenbv += (double)(ly.pc_hi[pc] - ly.pc_lo[pc]) * __ldcg(anc.bias_var + a);
+            }
+        }
+        const double fv = wsum(t) + lenbv;
+        const double b0 = __ldcg(ly.bias_mean + (size_t)l * 2), b1 = __ldcg(ly.bias_mean + (size_t)l * 2 + 1);   // b_old
+        sums[0] = sd0 + n * b0;
+        sums[1] = sd1 + n * b1;
+        sums[2] = quad + 2.0 * (b0 * sd0 + b1 * sd1) + n * (b0 * b0 + b1 * b1);
+        sums[3] = fv;
+        sums[4] = dc;
+    }
+    if (lane == 0) {   // region-specific noise and bias: Posteriors.py:81-93, 132-148 (y_var NOT times n, :138); Stats.py:102-124
+        const double bp0 = ly.bias_prec0[l], bp = bp0 + n;
+        double t3 = 0.0, t4 = 0.0;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            const double m0 = ly.bias_mean0[(size_t)l * 2 + d];
+            const double mn = (1.0 / bp) * (m0 * bp0 + sums[d]);
+            ly.bias_prev[(size_t)l * 2 + d] = __ldcg(ly.bias_mean + (size_t)l * 2 + d);
+            ly.bias_mean[(size_t)l * 2 + d] = mn;
+            t3 += m0 * m0;
+            t4 += mn * mn;
+        }
+        t3 *= bp0;
+        t4 *= bp;
+        const double yvar = j > 0 ? 1.0 / __ldcg(ly.noise_mean + l) : 0.0;
+        const double shape = ly.noise_shape0[l] + 0.5 * 2.0 * n;
+        const double scale = ly.noise_scale0[l] + 0.5 * (t3 - t4 + sums[2] + sums[3] + sums[4] + yvar);
+        ly.yvar[l] = yvar;
+        ly.bias_prec[l] = bp;
+        ly.bias_var[l] = 1.0 / bp;
+        ly.noise_shape[l] = shape;
+        ly.noise_scale[l] = scale;
+        ly.noise_mean[l] = shape / scale;
+        ly.noise_log_mean[l] = digamma(shape) - log(scale);
+#pragma unroll
+        for (int d = 0; d < 5; ++d) ly.sumsB[(size_t)l * 5 + d] = sums[d];
+    }
+}
+
+// ---- the solver (one warp) ---------------------------------------------------------------------------------------
+// Same iteration as k_scale_warp / omega_solve_serial: warm start from the previous sweep's column scalings, Sinkhorn
+// while it contracts fast, Newton on the log column scalings otherwise, cold restart on a non-finite residual, plain
+// Sinkhorn sweeps as the last resort; tolerance kOmegaTol.  MP rows / columns live in the registers of MP lanes; for
+// M < MP the table is padded with an identity block (its scalings stay at 1 and do not couple to the model's block).
+template <int MP>
+__device__ __forceinline__ double omega_eval(const double (&K)[MP], double (&P)[MP], double (&Q)[MP], double v, double &c, double *T,
+                                             bool row, int lane) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < MP; k += 2) {
+        P[k] = K[k] * __shfl_sync(kFull, v, k);
+        P[k + 1] = K[k + 1] * __shfl_sync(kFull, v, k + 1);
+        s0 += P[k];
+        s1 += P[k + 1];
+    }
+    const double u = row ? 1.0 / (s0 + s1) : 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < MP; ++k) {
+        P[k] *= u;
+        T[k * LD + lane] = P[k];
+    }
+    __syncwarp();
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    const double2 *col = reinterpret_cast<const double2 *>(T + (row ? lane : 0) * LD);
+#pragma unroll
+    for (int i = 0; i < MP; i += 2) {
+        const double2 t = col[i >> 1];
+        Q[i] = t.x;
+        Q[i + 1] = t.y;
+        if (i & 2) {
+            c2 += t.x;
+            c3 += t.y;
+        } else {
+            c0 += t.x;
+            c1 += t.y;
+        }
+    }
+    c = (c0 + c1) + (c2 + c3);
+    double e = row ? fabs(c - 1.0) : 0.0;
+    const bool bad = !(e == e);
+    e = wmax(e);
+    return __any_sync(kFull, bad) ? NAN : e;
+}
+
+template <int MP>
+__device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm, int layer, int lane) {
+    static_assert(MP <= 32 && (MP & 1) == 0, "one lane per row, columns in pairs");
+    const int M = m.M;
+    const bool row = lane < MP, real = lane < M;
+    double *T = sm.T;
+    double K[MP], P[MP], Q[MP];
+#pragma unroll
+    for (int k = 0; k < MP; ++k) K[k] = (real && k < M) ? sm.Kt[k * LD + lane] : ((row && !real && k == lane) ? 1.0 : 0.0);
+    const double cshift = real ? sm.colmax[lane] : 0.0;
+    const bool warm = m.omegaWarm[layer] > 0.5;
+    double v = 1.0;
+    if (real) {
+        const double eta = m.omegaEta[layer * 64 + lane] + cshift;
+        v = (warm && isfinite(eta)) ? exp(fmax(-600.0, fmin(600.0, eta))) : 1.0;
+    }
+    int iters = 0;
+    double err_prev = INFINITY, c = 1.0;
+    int last = kOmegaNone;
+    const double inv_m = 1.0 / (double)M;
+    for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
+        ++iters;
+        const double err = omega_eval<MP>(K, P, Q, v, c, T, row, lane);
+        if (err < kOmegaTol) break;
+        if (!isfinite(err)) {   // a bad (warm) start or an overshooting Newton step: start again from the shifts alone
+            v = 1.0;
+            err_prev = INFINITY;
+            last = kOmegaNone;
+            continue;
+        }
+        if (!omega_take_newton(err, err_prev, last)) {
+            if (real) v = fmax(1e-280, fmin(1e280, v / c));   // Sinkhorn column step
+            err_prev = err;
+            last = kOmegaSinkhorn;
+            continue;
+        }
+        err_prev = err;
+        last = kOmegaNewton;
+        // ---- Newton matrix: lane j builds row j of diag(c) - P^T P + e e^T / M (e: the model's columns; the padding
+        //      columns get a unit diagonal) from its column Q and the transposed table
+        double H[MP];
+#pragma unroll
+        for (int k = 0; k < MP; k += 2) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double2 *r0 = reinterpret_cast<const double2 *>(T + k * LD);
+            const double2 *r1 = reinterpret_cast<const double2 *>(T + (k + 1) * LD);
+#pragma unroll
+            for (int i = 0; i < MP; i += 2) {
+                const double2 t0 = r0[i >> 1], t1 = r1[i >> 1];
+                a0 = fma(Q[i], t0.x, a0);
+                a1 = fma(Q[i + 1], t0.y, a1);
+                a2 = fma(Q[i], t1.x, a2);
+                a3 = fma(Q[i + 1], t1.y, a3);
+            }
+            const double add0 = (real && k < M) ? inv_m : ((lane == k && k >= M) ? 1.0 : 0.0);
+            const double add1 = (real && k + 1 < M) ? inv_m : ((lane == k + 1 && k + 1 >= M) ? 1.0 : 0.0);
+            H[k] = ((lane == k) ? c : 0.0) - (a0 + a1) + add0;
+            H[k + 1] = ((lane == k + 1) ? c : 0.0) - (a2 + a3) + add1;
+        }
+        // ---- Cholesky (right-looking, lane = row) fused with the forward substitution; the next pivot is formed
+        //      first in every step (one shuffle) so that its reciprocal square root overlaps the rank-1 update
+        double rhs = 1.0 - c, y = 0.0, dinv = 0.0;
+        double piv = __shfl_sync(kFull, H[0], 0);
+        double *colbuf = T;                                           // the transposed table is no longer needed
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < MP; ++k) {
+            const double di = rsqrt(piv);
+            H[k] *= di;                                               // l_ik for lanes i >= k (l_kk on lane k)
+            double *cb = colbuf + (k & 1) * 32;                       // two buffers: no barrier between the steps
+            cb[lane] = H[k];
+            if (k + 1 < MP)   // the next pivot only needs its own row: h_jj - l_jk^2 on lane j = k + 1
+                piv = __shfl_sync(kFull, fma(-H[k], H[k], H[k + 1]), k + 1);
+            const double yk = __shfl_sync(kFull, rhs, k) * di;
+            if (lane == k) {
+                dinv = di;
+                y = yk;
+            }
+            if (lane > k) rhs = fma(-H[k], yk, rhs);
+            __syncwarp();
+#pragma unroll
+            for (int jj = k + 1; jj < MP; ++jj) H[jj] = fma(-H[k], cb[jj], H[jj]);   // broadcast loads of l_jk
+        }
+        // ---- L^T x = y with the transposed factor: lane i reads l_ki, k > i, from shared memory -------------------
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < MP; ++k) T[k * LD + lane] = H[k];          // T[k][i] = l_ik (valid for i >= k)
+        __syncwarp();
+        {
+            const double2 *lt = reinterpret_cast<const double2 *>(T + (row ? lane : 0) * LD);
+#pragma unroll
+            for (int k = 0; k < MP; k += 2) {
+                const double2 t = lt[k >> 1];
+                Q[k] = t.x;                                           // l_k,lane
+                Q[k + 1] = t.y;
+            }
+        }
+        double x = 0.0;
+#pragma unroll
+        for (int k = MP - 1; k >= 0; --k) {
+            const double xk = __shfl_sync(kFull, y, k) * __shfl_sync(kFull, dinv, k);
+            if (lane == k) x = xk;
+            if (lane < k) y = fma(-Q[k], xk, y);
+        }
+        if (real) v = fmax(1e-280, fmin(1e280, v * exp(fmax(-30.0, fmin(30.0, x)))));
+        __syncwarp();
+    }
+    // last resort: plain Sinkhorn sweeps (see omega_solve_serial); on model tables the loop exits at its first test
+    for (int it = 0; it < kOmegaFallbackSweeps; ++it) {
+        const double err = omega_eval<MP>(K, P, Q, v, c, T, row, lane);
+        if (err < kOmegaTol || !isfinite(err)) break;
+        ++iters;
+        if (real) v = fmax(1e-280, fmin(1e280, v / c));
+    }
+    if (real) {
+#pragma unroll
+        for (int k = 0; k < MP; ++k)
+            if (k < M) sm.omT[k * LD + lane] = P[k];
+        m.omegaEta[layer * 64 + lane] = log(v) - cshift;
+    }
+    if (lane == 0) {
+        m.omegaIters[layer] = (double)iters;
+        m.omegaWarm[layer] = 1.0;
+    }
+}
+
+// ---- the shared step of a layer on CTA 0 (256 threads) ------------------------------------------------------------
+__device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, cg::cluster_group &cluster, int j, int tid, unsigned C) {
+    const int M = m.M;
+    const ChainLayer &ly = m.layer[j];
+    // region sums of the cluster, in rank order
+    for (int v = tid; v < 7 * 32; v += kChainThreads) {
+        double s = 0.0;
+        for (unsigned r = 0; r < C; ++r) s += cluster.map_shared_rank(sm.ctaPart, r)[v];
+        sm.data[v] = s;
+    }
+    // snapshot of the previous posterior: the pristine prior for layer 0, the posterior of layer j - 1 otherwise
+    // (MRGP.py:575 / :581); its k-only terms of the table were prepared beside the previous solve
+    if (tid < M) {
+        const int t = tid;
+        if (j == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sm.primeB[t * 4 + q] = m.priorB[t * 4 + q];
+            sm.primeLogC[t] = m.priorLogC[t];
+            sm.primeShape[t] = m.priorShape[t];
+            sm.primeScale[t] = m.priorScale[t];
+            sm.sk[t] = m.priorSk[t];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sm.primeB[t * 4 + q] = sm.B[t * 4 + q];
+            sm.primeLogC[t] = sm.logC[t];
+            sm.primeShape[t] = sm.shape[t];
+            sm.primeScale[t] = sm.scale[t];
+            sm.sk[t] = sm.skNext[t];
+        }
+    }
+    __syncthreads();
+    if (tid < M) {
+        const int i = tid;
+        // P2: B_i = sum_k omega_ik B'_k + sum_l 0.5 noise zeta y y^T (Posteriors.py:502-518); PD guard, eigen-solve,
+        // saddle point (P2a-c), axis covariance (S1)
+        double b00 = 0.0, b01 = 0.0, b11 = 0.0, sh = 0.0, sc = 0.0;
+        for (int k = 0; k < M; ++k) {
+            const double w = sm.omT[k * LD + i];
+            b00 = fma(w, sm.primeB[k * 4 + 0], b00);
+            b01 = fma(w, sm.primeB[k * 4 + 1], b01);
+            b11 = fma(w, sm.primeB[k * 4 + 3], b11);
+            sh = fma(w, sm.primeShape[k], sh);
+            sc = fma(w, sm.primeScale[k], sc);
+        }
+        Bingham2 bg;
+        bingham2(b00 + sm.data[0 * 32 + i], b01 + sm.data[1 * 32 + i], b11 + sm.data[2 * 32 + i], bg);
+        sm.cov[i * 4 + 0] = bg.cov[0];
+        sm.cov[i * 4 + 1] = bg.cov[1];
+        sm.cov[i * 4 + 2] = bg.cov[1];
+        sm.cov[i * 4 + 3] = bg.cov[2];
+        sm.pub[i] = bg.cov[0];
+        sm.pub[32 + i] = bg.cov[1];
+        sm.pub[64 + i] = bg.cov[2];
+        sm.B[i * 4 + 0] = bg.b[0];
+        sm.B[i * 4 + 1] = bg.b[1];
+        sm.B[i * 4 + 2] = bg.b[1];
+        sm.B[i * 4 + 3] = bg.b[2];
+        sm.kappa[i * 2 + 0] = bg.kappa[0];
+        sm.kappa[i * 2 + 1] = bg.kappa[1];
+        sm.rho[i * 2 + 0] = bg.rho[0];
+        sm.rho[i * 2 + 1] = bg.rho[1];
+        sm.logC[i] = bg.logc;
+        atomicAdd(&sm.nchol, bg.n_chol);
+        // P3 / S3 (Posteriors.py:533-541, Stats.py:385-388): sum_l m2/S = sum_l 1/(prec S) + tr((sum_l zeta^2 y y^T / S) C_i)
+        const double beta2 = sm.data[3 * 32 + i] +
+                             (sm.data[4 * 32 + i] * bg.cov[0] + 2.0 * sm.data[5 * 32 + i] * bg.cov[1] + sm.data[6 * 32 + i] * bg.cov[2]);
+        const double shape = sh + 0.5 * (double)ly.R;
+        const double scale = sc + 0.5 * beta2;
+        const double mean = shape / scale, lmean = digamma(shape) - log(scale);
+        sm.shape[i] = shape;
+        sm.scale[i] = scale;
+        sm.mean[i] = mean;
+        sm.lmean[i] = lmean;
+        sm.pub[96 + i] = mean;
+    }
+    __syncthreads();
+    // S4, the table (Stats.py:405-412; a true matrix product inside the trace)
+    const bool last_layer = j == m.J - 1;
+    for (int t = tid; t < M * M; t += kChainThreads) {
+        const int i = t / M, k = t - i * M;
+        const double *Cc = sm.cov + i * 4, *Bp = sm.primeB + k * 4;
+        const double tr = Cc[0] * Bp[0] + Cc[1] * Bp[2] + Cc[2] * Bp[1] + Cc[3] * Bp[3];
+        const double lw = tr + sm.sk[k] + (sm.primeShape[k] - 1.0) * sm.lmean[i] - sm.primeScale[k] * sm.mean[i];
+        sm.lw[i * LW + k] = lw;
+        if (last_layer) m.logOmegaHat[t] = lw;
+    }
+    __syncthreads();
+    // shifts (rows, then columns of the row-shifted table) and exponentials: every row and column of K holds a 1
+    if (tid < M) {
+        double mx = -INFINITY;
+        for (int k = 0; k < M; ++k) mx = fmax(mx, sm.lw[tid * LW + k]);
+        sm.rowmax[tid] = mx;
+    }
+    __syncthreads();
+    if (tid < M) {
+        double mx = -INFINITY;
+        for (int i = 0; i < M; ++i) mx = fmax(mx, sm.lw[i * LW + tid] - sm.rowmax[i]);
+        sm.colmax[tid] = mx;
+    }
+    __syncthreads();
+    for (int t = tid; t < M * M; t += kChainThreads) {
+        const int k = t / M, i = t - k * M;
+        sm.Kt[k * LD + i] = exp((sm.lw[i * LW + k] - sm.rowmax[i]) - sm.colmax[k]);
+    }
+}
+
+template <int MP>
+__global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel *const *models) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ChainSmem &sm = *reinterpret_cast<ChainSmem *>(smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
+    const ChainModel &m = *models[blockIdx.x / C];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = m.M, J = m.J;
+    const bool solver = rank == 0 && warp == 0;
+    const int n_workers = (int)C * 8 - 1;                  // worker warps of the cluster
+    const int ww = (int)rank * 8 + warp - 1;               // this warp's worker index (-1: the solver)
+    const int cta_worker_threads = rank == 0 ? kChainThreads - 32 : kChainThreads;
+    unsigned long long *ts = m.ts;
+    if (ts && rank == 0 && tid == 0) atomicMin(&ts[(0 * 4 + 1) * 2], gtimer());
+
+    // ---- prologue: omega (transposed) on CTA 0, the ARD mean of the previous sweep everywhere -------------------
+    if (rank == 0) {
+        for (int t = tid; t < M * M; t += kChainThreads) {
+            const int i = t / M, k = t - i * M;
+            sm.omT[k * LD + i] = m.omega[t];
+        }
+        if (tid == 0) sm.nchol = 0;
+    }
+    if (tid < 4 * 32) {   // lanes past M must hold finite values (they are multiplied by zeros)
+        sm.pub[tid] = 0.0;
+        sm.loc[tid] = (tid >= 96 && tid - 96 < M) ? m.ardMean[tid - 96] : (tid >= 96 ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    double acc[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) acc[q] = 0.0;
+    if (!solver)
+        for (int l = ww; l < m.layer[0].R; l += n_workers) mid1_region(m, m.layer[0], 0, l, lane, sm.loc + 96, acc);
+#pragma unroll
+    for (int q = 0; q < 7; ++q) sm.part[warp][q][lane] = acc[q];
+    __syncthreads();
+    for (int v = tid; v < 7 * 32; v += kChainThreads) {
+        double s = 0.0;
+        for (int w = (rank == 0 ? 1 : 0); w < 8; ++w) s += sm.part[w][v >> 5][v & 31];
+        sm.ctaPart[v] = s;
+    }
+
+    for (int j = 0; j < J; ++j) {
+        cluster.sync();                                    // the region sums of layer j are in place
+        if (rank == 0) {
+            if (ts && tid == 0) atomicMin(&ts[(j * 4 + 3) * 2], gtimer());
+            shared_step(m, sm, cluster, j, tid, C);
+        }
+        cluster.sync();                                    // axis covariance, ARD moments and the table of layer j
+        if (solver) {
+            omega_solve_warp<MP>(m, sm, j, lane);
+            if (ts && lane == 0) atomicMax(&ts[(j * 4 + 3) * 2 + 1], gtimer());
+        } else {
+            if (ts && rank == 0 && tid == 32) atomicMin(&ts[(j * 4 + 1) * 2], gtimer());
+            const double *pub = cluster.map_shared_rank(sm.pub, 0);
+            const int wt = rank == 0 ? tid - 32 : tid;
+            for (int v = wt; v < 4 * 32; v += cta_worker_threads) sm.loc[v] = pub[v];
+            // k-only terms of the NEXT layer's table from the posterior just written (one lgamma per basis function)
+            if (rank == 0 && warp == 1 && lane < M) sm.skNext[lane] = -sm.logC[lane] + sm.shape[lane] * log(sm.scale[lane]) - lgamma(sm.shape[lane]);
+            worker_bar(cta_worker_threads);
+#pragma unroll
+            for (int q = 0; q < 7; ++q) acc[q] = 0.0;
+            if (j + 1 < J)
+                for (int l = ww; l < m.layer[j + 1].R; l += n_workers) mid1_region(m, m.layer[j + 1], j + 1, l, lane, sm.loc + 96, acc);
+#pragma unroll
+            for (int q = 0; q < 7; ++q) sm.part[warp][q][lane] = acc[q];
+            for (int l = ww; l < m.layer[j].R; l += n_workers) mid2_stats_region(m, m.layer[j], j, l, lane, sm.loc);
+            worker_bar(cta_worker_threads);
+            for (int v = wt; v < 7 * 32; v += cta_worker_threads) {
+                double s = 0.0;
+                for (int w = (rank == 0 ? 1 : 0); w < 8; ++w) s += sm.part[w][v >> 5][v & 31];
+                sm.ctaPart[v] = s;
+            }
+            if (ts && rank == 0 && tid == 32) atomicMax(&ts[(j * 4 + 1) * 2 + 1], gtimer());
+        }
+    }
+    cluster.sync();
+    // ---- the shared posterior / stats left by the last layer (Posteriors.py:482-541, Stats.py:354-420) ----------
+    if (rank == 0) {
+        for (int t = tid; t < M * M; t += kChainThreads) {
+            const int i = t / M, k = t - i * M;
+            m.omega[t] = sm.omT[k * LD + i];
+        }
+        for (int t = tid; t < M * 4; t += kChainThreads) {
+            m.axB[t] = sm.B[t];
+            m.axCov[t] = sm.cov[t];
+        }
+        for (int t = tid; t < M * 2; t += kChainThreads) {
+            m.axKappa[t] = sm.kappa[t];
+            m.axRho[t] = sm.rho[t];
+        }
+        for (int t = tid; t < M; t += kChainThreads) {
+            m.axLogC[t] = sm.logC[t];
+            m.ardShape[t] = sm.shape[t];
+            m.ardScale[t] = sm.scale[t];
+            m.ardMean[t] = sm.mean[t];
+            m.ardLogMean[t] = sm.lmean[t];
+        }
+        if (tid == 0) atomicAdd(m.chol_count, (unsigned long long)sm.nchol);
+        if (ts && tid == 0) atomicMax(&ts[((J - 1) * 4 + 1) * 2 + 1], gtimer());
+    }
+}
+
+template <int MP>
+int launch_impl(const ChainModel *const *models_dev, int n_models, int cluster, cudaStream_t stream) {
+    static bool configured = false;
+    const size_t smem = sizeof(ChainSmem);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_ci_sweep<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(k_ci_sweep<MP>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_models * cluster));
+    cfg.blockDim = dim3(kChainThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, k_ci_sweep<MP>, models_dev);
+}
+
+}  // namespace
+
+size_t ci_sweep_smem_bytes(int) { return sizeof(ChainSmem); }
+
+int launch_ci_sweep(int solver_size, const ChainModel *const *models_dev, int n_models, int cluster, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cluster < 1 || cluster > kChainMaxCluster || (cluster & (cluster - 1))) return (int)cudaErrorInvalidValue;
+    switch (solver_size) {
+        case 8: return launch_impl<8>(models_dev, n_models, cluster, st);
+        case 16: return launch_impl<16>(models_dev, n_models, cluster, st);
+        case 24: return launch_impl<24>(models_dev, n_models, cluster, st);
+        case 30: return launch_impl<30>(models_dev, n_models, cluster, st);
+        case 32: return launch_impl<32>(models_dev, n_models, cluster, st);
+        default: return (int)cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace mrgp

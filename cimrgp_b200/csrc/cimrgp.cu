@@ -17,6 +17,7 @@
 #include <unistd.h>
 
 #include "mrgp_kernels.cuh"
+#include "mrgp_chain.h"
 
 using namespace mrgp;
 
@@ -67,6 +68,7 @@ struct LayerDev {
     int32_t *pc_ptr = nullptr, *pc_jp = nullptr, *pc_anc = nullptr;
     int64_t *pc_lo = nullptr, *pc_hi = nullptr;
     bool inv_built = false;
+    double *yc = nullptr, *ysum = nullptr;   // layer 0 (ci): Phi^T y (R, M, dy) and sum y, sum |y|^2 (R, 4) of the fused sweep
 };
 
 struct SharedDev {
@@ -119,6 +121,14 @@ struct mrgp_handle {
     size_t state_begin = 0, state_end = 0;
     double *build_part = nullptr;    // split partials of the invariant builds
     size_t build_part_doubles = 0;
+    // fused ci sweep (csrc/chain.cu): descriptor of this model in device memory, its host copy, guard status
+    ChainModel *chain_dev = nullptr;
+    const ChainModel **chain_ptr_dev = nullptr;
+    ChainModel chain_host{};
+    unsigned int *chain_status = nullptr;
+    double *chain_guard = nullptr;
+    bool fused = true;               // MRGP_FUSED=0: the multi-kernel sweep of round 1
+    int chain_cluster = 0;           // CTAs per model of the fused sweep (0: by the number of regions)
     bool inferred_shortcut = true;   // skip phase A where Phi^T r == 0 identically (MRGP_STREAM_ALL=1: stream everything)
     bool omega_warp = true;   // single-warp register-resident omega solve for M <= 32 (MRGP_OMEGA_BLOCK=1: block version)
     // peer-memory exchange (multi-GPU): arena + flags in one cudaMalloc'ed block that the peers map through CUDA IPC
@@ -259,21 +269,21 @@ size_t carve(mrgp_handle *h, char *base) {
     h->tmp_var = c.take<double>(N);
     h->max_runs = 0;
     for (int j = 0; j < J; ++j) h->max_runs = std::max(h->max_runs, h->plan[j].n_runs);
-    h->part_stride = std::max(M * DY, kPartBStride);
+    h->part_stride = std::max(M * DY + DY + 2, kPartBStride);   // phase A: M*DY sums; y statistics: M*DY + DY + 1
     h->part = c.take<double>((size_t)h->max_runs * h->part_stride);
     {
         int rmax = 1;
         for (int j = 0; j < J; ++j) rmax = std::max(rmax, h->plan[j].R);
         h->xchg = c.take<double>((size_t)rmax * h->part_stride);
     }
-    if (!fi && J > 1) {   // closed-form statistics of the layers above the first
+    if (!fi) {   // closed-form statistics (layers above the first) and sufficient statistics (layer 0)
         if (h->sharded) h->x_all = c.take<double>((size_t)h->cfg.n_samples * h->cfg.dx);   // replicated inputs: the invariants need every sample
         const size_t np = (size_t)M * (M + 1) / 2 + M;
         size_t need = 0;
-        for (int j = 1; j < J; ++j) {
+        for (int j = 0; j < J; ++j) {
             const size_t blocks = (size_t)h->plan[j].R * build_splits(h->plan[j].R);
             const size_t P = h->plan[j].pc_jp.size();
-            need = std::max(need, std::max(blocks * np, P * build_splits((int)P) * M));
+            need = std::max(need, std::max(blocks * np, P * build_splits((int)std::max<size_t>(P, 1)) * M));
         }
         h->build_part_doubles = need;
         h->build_part = c.take<double>(need);
@@ -305,9 +315,13 @@ size_t carve(mrgp_handle *h, char *base) {
         d.S = c.take<double>(RM);
         d.d = c.take<double>(RM);
         d.absx = c.take<double>(R);
+        if (!fi) d.sumPhi = c.take<double>(RM);
+        if (!fi && j == 0) {
+            d.yc = c.take<double>(RM * DY);
+            d.ysum = c.take<double>(R * 4);
+        }
         if (!fi && j > 0) {
             const size_t P = lp.pc_jp.size();
-            d.sumPhi = c.take<double>(RM);
             d.ancD = c.take<double>(P * M);
             d.pc_ptr = c.take<int32_t>(lp.pc_ptr.size());
             d.pc_jp = c.take<int32_t>(P);
@@ -385,8 +399,13 @@ size_t carve(mrgp_handle *h, char *base) {
     s.priorShape = c.take<double>(M);
     s.priorScale = c.take<double>(M);
     h->state_end = c.off;
-    if (!fi)
-        for (int j = 1; j < J; ++j) h->dev[j].gram = c.take<double>((size_t)h->plan[j].R * M * M);   // read only when dA != 0
+    if (!fi) {
+        for (int j = 0; j < J; ++j) h->dev[j].gram = c.take<double>((size_t)h->plan[j].R * M * M);   // layers > 0: read only when dA != 0
+        h->chain_dev = c.take<ChainModel>(1);
+        h->chain_ptr_dev = c.take<const ChainModel *>(1);
+        h->chain_status = c.take<unsigned int>(4);
+        h->chain_guard = c.take<double>(2);
+    }
     return (c.off + 255) & ~(size_t)255;
 }
 
@@ -957,6 +976,19 @@ bool use_closed_form(const mrgp_handle *h) {
     return h->cfg.n_layers > 1;
 }
 
+// The fused sweep (csrc/chain.cu): ci, static intervals, region-specific noise and bias, M <= 32.  Everything else
+// (fi, adaptive intervals, shared noise / bias, M > 32, MRGP_STREAM_ALL=1, MRGP_FUSED=0) takes the multi-kernel sweep.
+bool use_fused(const mrgp_handle *h) {
+    if (!h->fused || h->cfg.mode != MRGP_MODE_CI || !h->inferred_shortcut || !h->build_part || !h->chain_dev) return false;
+    if (h->sharded && !h->have_x_all) return false;
+    if (!h->cfg.noise_region_specific || !h->cfg.bias_region_specific) return false;
+    if (h->cfg.dy != 2 || chain_solver_size(h->cfg.n_basis) == 0) return false;
+    if (h->timeline && h->cfg.n_layers > kMaxLayersTs) return false;
+    for (const auto &d : h->dev)
+        if (d.adaptive) return false;
+    return true;
+}
+
 template <int M>
 int launch_build_invariants(mrgp_handle *h, int j) {
     LayerDev &d = h->dev[j];
@@ -969,23 +1001,27 @@ int launch_build_invariants(mrgp_handle *h, int j) {
     CK(cudaGetLastError());
     k_reduce_gram<<<(lp.R * (NP + M) + 255) / 256, 256, 0, h->stream>>>(h->build_part, splits, lp.R, M, d.gram, d.sumPhi);
     CK(cudaGetLastError());
-    EvalArgs ea{};
-    int rc = fill_eval_layers(h, ea, j, nullptr);
-    if (rc) return rc;
-    const int P = (int)lp.pc_jp.size(), psplits = build_splits(P);
-    const PieceTable pt{d.pc_ptr, d.pc_jp, d.pc_anc, d.pc_lo, d.pc_hi, P};
-    k_build_ancD<M><<<P * psplits, 256, 0, h->stream>>>(ea, xg, pt, psplits, h->build_part);
-    CK(cudaGetLastError());
-    k_reduce_ancD<<<(P * M + 255) / 256, 256, 0, h->stream>>>(h->build_part, psplits, P, M, d.ancD);
-    CK(cudaGetLastError());
-    count(h, 4);
+    count(h, 2);
+    if (j > 0) {
+        EvalArgs ea{};
+        int rc = fill_eval_layers(h, ea, j, nullptr);
+        if (rc) return rc;
+        const int P = (int)lp.pc_jp.size(), psplits = build_splits(P);
+        const PieceTable pt{d.pc_ptr, d.pc_jp, d.pc_anc, d.pc_lo, d.pc_hi, P};
+        k_build_ancD<M><<<P * psplits, 256, 0, h->stream>>>(ea, xg, pt, psplits, h->build_part);
+        CK(cudaGetLastError());
+        k_reduce_ancD<<<(P * M + 255) / 256, 256, 0, h->stream>>>(h->build_part, psplits, P, M, d.ancD);
+        CK(cudaGetLastError());
+        count(h, 2);
+    }
     d.inv_built = true;
     return MRGP_OK;
 }
 
 int build_invariants(mrgp_handle *h) {
-    if (!use_closed_form(h)) return MRGP_OK;
-    for (int j = 1; j < h->cfg.n_layers; ++j) {
+    const bool fused = use_fused(h);
+    if (!use_closed_form(h) && !fused) return MRGP_OK;
+    for (int j = fused ? 0 : 1; j < h->cfg.n_layers; ++j) {
         if (h->dev[j].inv_built) continue;
         int rc = MRGP_EINVAL;
         DISPATCH_M(h->cfg.n_basis, rc = launch_build_invariants<MM>(h, j));
@@ -1016,11 +1052,103 @@ int do_stats_b(mrgp_handle *h, int j) {
     return do_bias_noise_shared(h, j);
 }
 
+int do_exchange(mrgp_handle *h, int j, int slot, int nv, bool is_max);
+
+// Sufficient statistics of the observations for layer 0 of the fused sweep: Phi^T y, sum y, sum |y|^2 per region
+// (one pass over x and y; again whenever y, x or the intervals of layer 0 change).
+template <int M>
+cudaError_t launch_ystats(mrgp_handle *h, const StreamArgs &a) {
+    constexpr int DY = 2;
+    const size_t smem = (size_t)(kStages * TileLayout<DY, true, false, false>::kDoubles + kRedSmemDoubles) * sizeof(double);
+    cudaError_t e = set_smem(k_ystats<DY, M>, smem);
+    if (e != cudaSuccess) return e;
+    k_ystats<DY, M><<<h->n_ctas, kThreads, smem, h->stream>>>(a);
+    return cudaGetLastError();
+}
+
+int do_ystats(mrgp_handle *h) {
+    LayerDev &d = h->dev[0];
+    const LayerPlan &lp = h->plan[0];
+    const int M = h->cfg.n_basis, DY = h->cfg.dy;
+    StreamArgs a = stream_args(h, 0);
+    cudaError_t e = cudaErrorInvalidValue;
+    DISPATCH_M(M, e = launch_ystats<MM>(h, a));
+    CK(e);
+    count(h);
+    const int32_t *rr = d.region_run;
+    const double *part = h->part;
+    if (h->sharded) {   // sum the statistics of the ranks' chunks
+        int rc = do_exchange(h, 0, 0, M * DY + DY + 1, false);
+        if (rc) return rc;
+        rr = d.ident_run;
+        part = h->xchg;
+    }
+    k_reduce_ystats<<<lp.R, 64, 0, h->stream>>>(rr, part, h->part_stride, lp.R, M, DY, d.yc, d.ysum);
+    CK(cudaGetLastError());
+    count(h);
+    h->ystats_valid = true;
+    return MRGP_OK;
+}
+
+int chain_cluster_size(const mrgp_handle *h) {
+    if (h->chain_cluster > 0) return h->chain_cluster;
+    int rmax = 1;
+    for (const auto &lp : h->plan) rmax = std::max(rmax, lp.R);
+    return rmax <= 32 ? 1 : rmax <= 64 ? 2 : rmax <= 128 ? 4 : 8;
+}
+
+// Descriptor of the model for the fused sweep (device pointers only; uploaded before the sweep is captured).
+int upload_chain_model(mrgp_handle *h) {
+    ChainModel &m = h->chain_host;
+    const SharedDev &s = h->sh;
+    std::memset(&m, 0, sizeof m);
+    m.J = h->cfg.n_layers;
+    m.M = h->cfg.n_basis;
+    m.DY = h->cfg.dy;
+    m.axB = s.axB; m.axKappa = s.axKappa; m.axRho = s.axRho; m.axLogC = s.axLogC; m.axCov = s.axCov;
+    m.ardShape = s.ardShape; m.ardScale = s.ardScale; m.ardMean = s.ardMean; m.ardLogMean = s.ardLogMean;
+    m.omega = s.omega; m.logOmegaHat = s.logOmegaHat; m.omegaIters = s.omegaIters; m.omegaEta = s.omegaEta; m.omegaWarm = s.omegaWarm;
+    m.priorB = s.priorB; m.priorLogC = s.priorLogC; m.priorShape = s.priorShape; m.priorScale = s.priorScale;
+    m.priorSk = s.primeSk + 2 * 64;    // k-only terms of the table for layer 0 (k_init_shared)
+    m.chol_count = h->chol_count;
+    m.status = h->chain_status;
+    m.guard = h->chain_guard;
+    m.ts = h->timeline ? h->ts : nullptr;
+    for (int j = 0; j < m.J; ++j) {
+        const LayerDev &d = h->dev[j];
+        ChainLayer &l = m.layer[j];
+        l.R = h->plan[j].R;
+        l.P = (int32_t)h->plan[j].pc_jp.size();
+        l.offsets = d.offsets;
+        l.S = d.S; l.d = d.d; l.sumPhi = d.sumPhi; l.gram = d.gram; l.ancD = d.ancD;
+        l.pc_ptr = d.pc_ptr; l.pc_anc = d.pc_anc; l.pc_lo = d.pc_lo; l.pc_hi = d.pc_hi;
+        l.yc = d.yc; l.ysum = d.ysum;
+        l.prec = d.prec; l.zeta = d.zeta; l.ytil = d.ytil; l.A = d.A; l.A_prev = d.A_prev; l.m2 = d.m2; l.cm2 = d.cm2;
+        l.noise_shape = d.noise_shape; l.noise_scale = d.noise_scale; l.noise_mean = d.noise_mean; l.noise_log_mean = d.noise_log_mean;
+        l.noise_shape0 = d.noise_shape0; l.noise_scale0 = d.noise_scale0; l.bias_prec0 = d.bias_prec0; l.bias_mean0 = d.bias_mean0;
+        l.bias_prec = d.bias_prec; l.bias_mean = d.bias_mean; l.bias_prev = d.bias_prev; l.bias_var = d.bias_var;
+        l.yvar = d.yvar; l.sumsB = d.sumsB;
+    }
+    CK(cudaMemcpyAsync(h->chain_dev, &m, sizeof m, cudaMemcpyHostToDevice, h->stream));
+    const ChainModel *ptr = h->chain_dev;
+    CK(cudaMemcpyAsync(h->chain_ptr_dev, &ptr, sizeof ptr, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // `ptr` is a local; the descriptor must be in place before any capture
+    return MRGP_OK;
+}
+
+int do_fused_sweep(mrgp_handle *h) {
+    const int rc = launch_ci_sweep(chain_solver_size(h->cfg.n_basis), h->chain_ptr_dev, 1, chain_cluster_size(h), h->stream);
+    if (rc != 0) return fail(h, MRGP_ECUDA, "fused sweep launch: %s", cudaGetErrorString((cudaError_t)rc));
+    count(h);
+    return MRGP_OK;
+}
+
 int sweep_once(mrgp_handle *h, bool fork_omega) {
     const int J = h->cfg.n_layers;
     const bool ci = h->cfg.mode == MRGP_MODE_CI;
     const bool closed = use_closed_form(h);
     int rc;
+    if (fork_omega && use_fused(h)) return do_fused_sweep(h);   // the whole sweep is one kernel (csrc/chain.cu)
     if (fork_omega && ci && h->state_end > h->state_begin) {
         // the small-matrix state (a few MB) is pulled into L2 by the side stream while layer 0 streams the samples:
         // the short kernels that follow are chains of dependent loads and would otherwise each pay HBM latency
@@ -1234,6 +1362,8 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     h->cfg = *cfg;
     if (const char *e = getenv("MRGP_OMEGA_BLOCK")) h->omega_warp = !(e[0] == '1');
     if (const char *e = getenv("MRGP_STREAM_ALL")) h->inferred_shortcut = !(e[0] == '1');
+    if (const char *e = getenv("MRGP_FUSED")) h->fused = !(e[0] == '0');
+    if (const char *e = getenv("MRGP_CHAIN_CLUSTER")) h->chain_cluster = atoi(e);
     h->sharded = cfg->sample_end > cfg->sample_begin;   // an explicit range selects the exchange-buffer path
     h->lo = h->sharded ? cfg->sample_begin : 0;
     h->hi = h->sharded ? cfg->sample_end : cfg->n_samples;
@@ -1384,6 +1514,10 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
     CK(cudaMemsetAsync(h->done_counter, 0, sizeof(unsigned int), h->stream));
     CK(cudaMemsetAsync(h->brent_fail, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->mid_sync, 0, 2 * kMaxLayers * sizeof(unsigned int), h->stream));
+    if (h->chain_status) {
+        CK(cudaMemsetAsync(h->chain_status, 0, 4 * sizeof(unsigned int), h->stream));
+        CK(cudaMemsetAsync(h->chain_guard, 0, 2 * sizeof(double), h->stream));
+    }
     CK(cudaMemsetAsync(h->g, 0, (size_t)(h->hi - h->lo) * h->cfg.dy * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->hvar, 0, (size_t)(h->hi - h->lo) * sizeof(double), h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1689,8 +1823,14 @@ int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
     if (n_iter < 0) return fail(h, MRGP_EINVAL, "n_iter < 0");
     if (h->sharded && !h->comm.ready)
         return fail(h, MRGP_ESTATE, "mrgp_sweep on a sharded handle needs the peer exchange (mrgp_comm_bind); without it drive the phases and the all-reduces from the host");
+    const bool fused = use_fused(h);
+    if (fused && !h->ystats_valid) {
+        if ((rc = build_invariants(h))) return rc;
+        if ((rc = do_ystats(h))) return rc;
+    }
     if (!h->graph_exec) {
         if ((rc = build_invariants(h))) return rc;
+        if (fused && (rc = upload_chain_model(h))) return rc;
         h->launches_per_sweep = 0;
         h->capturing = true;
         cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
@@ -1743,6 +1883,10 @@ int mrgp_group_create(mrgp_handle *const *handles, int32_t n, void *cuda_stream,
         if (h->sharded) return fail(h, MRGP_EINVAL, "sharded handles cannot join a group");
         if (h->cfg.device != handles[0]->cfg.device) return fail(h, MRGP_EINVAL, "all models of a group live on one device");
         if ((rc = build_invariants(h))) return rc;
+        if (use_fused(h)) {
+            if (!h->ystats_valid && (rc = do_ystats(h))) return rc;
+            if ((rc = upload_chain_model(h))) return rc;
+        }
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(h, MRGP_ECUDA, "stream synchronisation failed");
     }
     mrgp_group *g = new mrgp_group();

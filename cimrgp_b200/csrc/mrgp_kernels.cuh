@@ -519,6 +519,138 @@ __global__ void __launch_bounds__(kThreads, 1) k_phase_a(StreamArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sufficient statistics of the observations for layer 0 of the fused ci sweep (csrc/chain.cu): per run
+//     c[i][d] = sum_n phi_i(n) y_d(n),   sum_n y_d(n),   sum_n |y(n)|^2
+// One pass over (x, y) per data set: 24 B and 3 M + 22 + 5 FP64 operations per sample (the basis once, no
+// coefficients).  Same tile pipeline and segment / run plan as phase A; partial layout [c (M*DY) | sum y (DY) | sum |y|^2].
+// ------------------------------------------------------------------------------------------------
+template <int DY, int M, int SB>
+__device__ __forceinline__ void ystats_block(double (&T)[M * DY + DY + 1], const double *st, int k0, int lo_rel, int hi_rel, double inv2L,
+                                             double rs) {
+    using L = TileLayout<DY, true, false, false>;
+    double c2[SB], f[SB], fm[SB], yv[SB][DY];
+#pragma unroll
+    for (int q = 0; q < SB; ++q) {
+        const int idx = (k0 + q) * kThreads + threadIdx.x;
+        const bool act = idx >= lo_rel && idx < hi_rel;
+        const double x = act ? st[L::kX + idx] : 0.0;
+        basis_seed(x, inv2L, act ? rs : 0.0, f[q], c2[q]);
+        fm[q] = 0.0;
+        double rr = 0.0;
+#pragma unroll
+        for (int d = 0; d < DY; ++d) {
+            yv[q][d] = act ? st[L::kY + idx * DY + d] : 0.0;
+            T[M * DY + d] += yv[q][d];
+            rr = fma(yv[q][d], yv[q][d], rr);
+        }
+        T[M * DY + DY] += rr;
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+#pragma unroll
+        for (int q = 0; q < SB; ++q) {
+#pragma unroll
+            for (int d = 0; d < DY; ++d) T[i * DY + d] = fma(f[q], yv[q][d], T[i * DY + d]);
+            const double fn = fma(c2[q], f[q], -fm[q]);
+            fm[q] = f[q];
+            f[q] = fn;
+        }
+    }
+}
+
+template <int DY, int M>
+__global__ void __launch_bounds__(kThreads, 1) k_ystats(StreamArgs p) {
+    using L = TileLayout<DY, true, false, false>;
+    constexpr int NCW = kThreads / 32, NV = M * DY + DY + 1;
+    extern __shared__ __align__(128) double dsm[];
+    double *stages = dsm;
+    double *red = dsm + kStages * L::kDoubles;
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t c0 = p.sample_begin + (int64_t)blockIdx.x * p.cta_quantum;
+    const int64_t c1 = (c0 + p.cta_quantum < p.n_samples) ? c0 + p.cta_quantum : p.n_samples;
+    const int n_tiles = (c1 > c0) ? (int)((c1 - c0 + kTile - 1) / kTile) : 0;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NCW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    int next_issue = 0;
+    double T[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) T[i] = 0.0;
+    int s = p.cta_seg[blockIdx.x];
+    const int s_end = p.cta_seg[blockIdx.x + 1];
+    int loaded = -1;
+    double inv2L = 0.0, rs = 0.0;
+    Segment sg;
+    if (s < s_end) sg = p.segs[s];
+    for (int t = 0; t < n_tiles; ++t) {
+        const int stage = t % kStages;
+        const double *st = stages + stage * L::kDoubles;
+        if (tid == 0) refill<DY, true, false, false>(p, stages, full_bar, empty_bar, next_issue, t, n_tiles, c0, c1);
+        mbar_wait(&full_bar[stage], (uint32_t)((t / kStages) & 1));
+        const int64_t tile_lo = c0 + (int64_t)t * kTile;
+        const int64_t tile_hi = (tile_lo + kTile < c1) ? tile_lo + kTile : c1;
+        int64_t pos = tile_lo;
+        while (pos < tile_hi) {
+            if (loaded != s) {
+                inv2L = p.inv2L[sg.region];
+                rs = p.rsqrtL[sg.region];
+                loaded = s;
+            }
+            const int64_t seg_end = sg.start + sg.len;
+            const int64_t hi = (seg_end < tile_hi) ? seg_end : tile_hi;
+            int ka = (int)((pos - tile_lo) / kThreads);
+            const int kb = (int)((hi - 1 - tile_lo) / kThreads);
+            while (ka <= kb) {
+                const int left = kb - ka + 1;
+                if (left >= 4) {
+                    ystats_block<DY, M, 4>(T, st, ka, (int)(pos - tile_lo), (int)(hi - tile_lo), inv2L, rs);
+                    ka += 4;
+                } else if (left >= 2) {
+                    ystats_block<DY, M, 2>(T, st, ka, (int)(pos - tile_lo), (int)(hi - tile_lo), inv2L, rs);
+                    ka += 2;
+                } else {
+                    ystats_block<DY, M, 1>(T, st, ka, (int)(pos - tile_lo), (int)(hi - tile_lo), inv2L, rs);
+                    ka += 1;
+                }
+            }
+            pos = hi;
+            if (hi == seg_end) {
+                if (sg.flush) {
+                    block_reduce_store<NV, true>(T, red, p.part + (size_t)sg.run * p.part_stride);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) T[i] = 0.0;
+                }
+                ++s;
+                if (s < s_end) sg = p.segs[s];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+}
+
+// yc[r][i][d], ysum[r][0..DY] = sums over the region's runs of the k_ystats partials (fixed order).
+__global__ void k_reduce_ystats(const int32_t *region_run, const double *part, int part_stride, int R, int M, int DY, double *yc, double *ysum) {
+    const int r = blockIdx.x, nv = M * DY + DY + 1;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        double s = 0.0;
+        for (int q = region_run[r]; q < region_run[r + 1]; ++q) s += part[(size_t)q * part_stride + v];
+        if (v < M * DY)
+            yc[(size_t)r * M * DY + v] = s;
+        else
+            ysum[(size_t)r * 4 + (v - M * DY)] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Phase B: residual statistics with the NEW coefficients, fused with the propagation of the latent
 // mean / variance to the next layer (Posteriors.py:81-148, Stats.py:126-157):
 //   r = target - Phi A_new^T - fbar;   partial = [sum r_d, sum |r|^2, sum fvar, sum_n sum_i phi_i^2 cm2_i]

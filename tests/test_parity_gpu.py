@@ -573,17 +573,40 @@ def test_divider_three_and_block_omega_solver_against_oracle():
 # ------------------------------------------------------------------------------------------------------------
 # BASELINE configs 3, 4 and 5 at their full sizes ("pin configs 3 and 4 at full size")
 # ------------------------------------------------------------------------------------------------------------
-def _oracle_vs_device_at_size(n, resolution, fi, checkpoints, elbo):
+# Fields downstream of the chain of permutation weights omega(0) ... omega(J-1).  The reference solves for omega with
+# MINPACK hybrd at xtol 1.5e-8 (Stats.py:413); the device computes the exact doubly-stochastic scaling.  Through 10
+# layers and 3 sweeps the reference's own solver slack accumulates to 2.4e-6 on S.B / S.logC at N = 1e6 (measured: the
+# oracle with the exact scaling agrees with the device to 1e-13, with the reference-faithful fsolve oracle to 2.4e-6).
+OMEGA_CHAIN = ('S.B', 'S.kappa', 'S.logC', 'S.rho', 'S.omega')
+
+
+def _oracle_vs_device_at_size(n, resolution, fi, checkpoints, elbo, omega_chain_rtol=None):
     x, y = workloads.workload1(n)
     ora = O.OracleMRGP(x, y, 30, O.uniform_offsets(n, resolution, 2), mode='fi' if fi else 'ci')
+    exact = None
+    if omega_chain_rtol is not None:
+        exact = O.OracleMRGP(x, y, 30, O.uniform_offsets(n, resolution, 2), mode='ci', omega_solver='sinkhorn')
     m = build(x, y, 30, resolution, fi)
     done = 0
     for k in checkpoints:
         for _ in range(k - done):
             ora.sweep()
+            if exact is not None:
+                exact.sweep()
         m.fit(k - done, None)
         done = k
-        compare(m._engine.state(), ora.state())
+        got, ref = m._engine.state(), ora.state()
+        if exact is None:
+            compare(got, ref)
+        else:
+            # reference-faithful oracle: 1e-6 everywhere except the omega chain (its own solver tolerance, see above)
+            compare({k_: v for k_, v in got.items() if k_ not in OMEGA_CHAIN}, {k_: v for k_, v in ref.items() if k_ not in OMEGA_CHAIN})
+            for k_ in OMEGA_CHAIN:
+                assert mismatch(got[k_], ref[k_], omega_chain_rtol, atol_scale=omega_chain_rtol) is None, k_
+            # oracle with the exact scaling: the shared state to 1e-9
+            ex = exact.state()
+            for k_ in [k_ for k_ in ex if k_.startswith('S.')]:
+                assert mismatch(got[k_], ex[k_], 1e-9, atol_scale=1e-9 if k_ == 'S.omega' else 1e-12) is None, k_
     if elbo:
         assert mismatch(m._engine.elbo(), ora.elbo()[2], RTOL) is None     # per layer and per term
     return m, ora
@@ -599,7 +622,7 @@ def test_config3_full_size_against_oracle(fi):
 def test_config4_full_size_against_oracle():
     """BASELINE config 4 (the headline): N = 1e6, 10 resolutions (1023 regions), M = 30, ci: state after 1 and 3 sweeps
     and the ELBO per term against the CPU oracle (the oracle needs ~45 s per sweep at this size)."""
-    _oracle_vs_device_at_size(1000000, 9, False, (1, 3), elbo=True)
+    _oracle_vs_device_at_size(1000000, 9, False, (1, 3), elbo=True, omega_chain_rtol=1e-5)
 
 
 def test_config4_closed_form_statistics_at_full_size_on_a_non_inert_state(monkeypatch):
