@@ -69,6 +69,8 @@ SIGNATURES = {
     'mrgp_sweep': (C.c_int, [_P, C.c_int32]),
     'mrgp_group_create': (C.c_int, [C.POINTER(_P), C.c_int32, _P, C.POINTER(_P)]),
     'mrgp_group_sweep': (C.c_int, [_P, C.c_int32]),
+    'mrgp_group_observations_changed': (C.c_int, [_P]),
+    'mrgp_group_launch_count': (C.c_int64, [_P]),
     'mrgp_group_synchronize': (C.c_int, [_P]),
     'mrgp_group_destroy': (None, [_P]),
     'mrgp_synchronize': (C.c_int, [_P]),

@@ -1,8 +1,11 @@
 """Batch of independent series (BASELINE config 5): one MultiResolutionGaussianProcess per series,
-all of them in ONE device allocation and one pinned staging area.  The sweeps of `group_size` series are captured
-as parallel branches of one CUDA graph (mrgp_group_*, include/cimrgp.h): one launch per group and iteration, the
-short kernels of different series overlap on the GPU.  (group_size=0: one graph launch per series on a pool of
-streams.)
+all of them in ONE device allocation and one pinned staging area.  The series of a group are swept together
+(mrgp_group_*, include/cimrgp.h): ci models take the batched fused sweep - ONE kernel launch per iteration for the
+whole group, one thread-block cluster per series; fi models are captured as parallel branches of one CUDA graph.
+(group_size=0: one graph launch per series on a pool of streams.)
+
+Over several GPUs the series are split by rank in contiguous blocks (`rank`, `world`): replicas only, no collective
+(SURVEY.md §8e).
 
 The reference has no such API - every series is a separate object fitted one after the other
 (scripts/tests/*.py loop over models) - so this is a front end over the drop-in class, not a new model: series s
@@ -21,16 +24,22 @@ from .MRGP import MultiResolutionGaussianProcess
 
 class SeriesBatch(object):
     def __init__(self, xs, ys, n_basis, resolution, basis_function_obj, spectral_density_obj=None, divider=2,
-                 forced_independence=False, n_streams=16, device=0, n_ctas=None, group_size=None, **model_kw):
+                 forced_independence=False, n_streams=16, device=0, n_ctas=None, group_size=None, rank=0, world=1,
+                 **model_kw):
         """xs[s]: (N_s, 1) inputs, ys[s]: (N_s, dy) observations of series s; the other arguments as for
         MultiResolutionGaussianProcess (one index set IndexSetUniform(N_s, resolution, divider) per series).
         n_ctas: streaming grid per model (default: one CTA per 1024 samples, so that many models fit on the GPU).
-        group_size: models per captured group graph; 0 = one graph launch per model on the stream pool.  Default:
-        0 in ci mode, 64 in fi mode (measured on B200, 4096 x N = 2048: ci 113 k series-sweeps/s with per-model
-        launches against 60 k in groups of 64 - the forked side-stream branches of the ci sweep do not pack well
-        into one large graph; fi 127 k in groups of 64 against 95 k)."""
+        group_size: models per group; 0 = one graph launch per model on the stream pool.  Default: the whole batch in
+        ci mode (one fused launch per iteration), 64 in fi mode (branch graphs).
+        rank, world: this process keeps the series [rank * per, (rank + 1) * per), per = ceil(S / world)."""
         import torch
         self.torch = torch
+        if world > 1:
+            per = -(-len(xs) // int(world))
+            self.series_range = (min(len(xs), int(rank) * per), min(len(xs), (int(rank) + 1) * per))
+            xs, ys = xs[self.series_range[0]:self.series_range[1]], ys[self.series_range[0]:self.series_range[1]]
+        else:
+            self.series_range = (0, len(xs))
         self.n_series = len(xs)
         if len(ys) != self.n_series or self.n_series == 0:
             raise ValueError('xs and ys must list the same, non-zero number of series')
@@ -68,7 +77,7 @@ class SeriesBatch(object):
         self.lib = _lib.load()
         self.groups = []
         if group_size is None:
-            group_size = 64 if forced_independence else 0
+            group_size = 64 if forced_independence else self.n_series
         if group_size and group_size > 0:
             for g0 in range(0, self.n_series, int(group_size)):
                 members = self.models[g0:g0 + int(group_size)]
@@ -97,6 +106,16 @@ class SeriesBatch(object):
                 for m in self.models:
                     m._engine.sweep(1)
         self.synchronize()
+
+    def set_observations(self, ys):
+        """New observations for every series at unchanged inputs: staged in the pinned area, uploaded on the models'
+        streams; the groups refresh the layer-0 statistics of all series with one launch at the next fit()."""
+        for m, y in zip(self.models, ys):
+            m._engine.set_observations(np.asarray(y, dtype=np.float64))
+
+    def launch_count(self):
+        n = sum(int(self.lib.mrgp_group_launch_count(g)) for g in self.groups)
+        return n if self.groups else sum(m._engine.launch_count() for m in self.models)
 
     def synchronize(self):
         for g in self.groups:

@@ -610,6 +610,61 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
     }
 }
 
+// Sufficient statistics of y for layer 0, one CTA per (model, region): c[i][d] = sum_n phi_i y_d, sum y_d, sum |y|^2
+// in a fixed order (thread-strided samples, shuffles inside the warps, warps in order).
+template <int MP>
+__global__ void __launch_bounds__(256) k_ystats_small(const ChainModel *const *models, int r0_max) {
+    constexpr int NV = MP * 2 + 3;
+    __shared__ double red[8][NV];
+    const ChainModel &m = *models[blockIdx.x / r0_max];
+    const int r = blockIdx.x % r0_max;
+    const ChainLayer &ly = m.layer[0];
+    if (r >= ly.R) return;
+    const int M = m.M, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t lo = ly.offsets[r], hi = ly.offsets[r + 1];
+    const double inv2L = ly.inv2L[r], rs = ly.rsqrtL[r];
+    double T[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) T[i] = 0.0;
+    for (int64_t n = lo + tid; n < hi; n += 256) {
+        const double y0 = m.y[n * 2], y1 = m.y[n * 2 + 1];
+        double f, c2;
+        basis_seed(m.x[n], inv2L, rs, f, c2);
+        double fm = 0.0;
+        T[MP * 2] += y0;
+        T[MP * 2 + 1] += y1;
+        T[MP * 2 + 2] += fma(y1, y1, y0 * y0);
+#pragma unroll
+        for (int i = 0; i < MP; ++i) {
+            T[i * 2] = fma(f, y0, T[i * 2]);
+            T[i * 2 + 1] = fma(f, y1, T[i * 2 + 1]);
+            const double fn = fma(c2, f, -fm);
+            fm = f;
+            f = fn;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double t = wsum(T[i]);
+        if (lane == 0) red[warp][i] = t;
+    }
+    __syncthreads();
+    for (int v = tid; v < NV; v += 256) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w][v];
+        if (v < M * 2)
+            ly.yc[(size_t)r * M * 2 + v] = t;
+        else if (v >= MP * 2)
+            ly.ysum[(size_t)r * 4 + (v - MP * 2)] = t;
+    }
+}
+
+template <int MP>
+int launch_ystats_impl(const ChainModel *const *models_dev, int n_models, int r0_max, cudaStream_t stream) {
+    k_ystats_small<MP><<<(unsigned)(n_models * r0_max), 256, 0, stream>>>(models_dev, r0_max);
+    return (int)cudaGetLastError();
+}
+
 template <int MP>
 int launch_impl(const ChainModel *const *models_dev, int n_models, int cluster, cudaStream_t stream) {
     static bool configured = false;
@@ -639,6 +694,19 @@ int launch_impl(const ChainModel *const *models_dev, int n_models, int cluster, 
 }  // namespace
 
 size_t ci_sweep_smem_bytes(int) { return sizeof(ChainSmem); }
+
+int launch_ystats_small(int solver_size, const ChainModel *const *models_dev, int n_models, int r0_max, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_models < 1 || r0_max < 1) return (int)cudaErrorInvalidValue;
+    switch (solver_size) {
+        case 8: return launch_ystats_impl<8>(models_dev, n_models, r0_max, st);
+        case 16: return launch_ystats_impl<16>(models_dev, n_models, r0_max, st);
+        case 24: return launch_ystats_impl<24>(models_dev, n_models, r0_max, st);
+        case 30: return launch_ystats_impl<30>(models_dev, n_models, r0_max, st);
+        case 32: return launch_ystats_impl<32>(models_dev, n_models, r0_max, st);
+        default: return (int)cudaErrorInvalidValue;
+    }
+}
 
 int launch_ci_sweep(int solver_size, const ChainModel *const *models_dev, int n_models, int cluster, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -127,6 +127,9 @@ struct mrgp_handle {
     ChainModel chain_host{};
     unsigned int *chain_status = nullptr;
     double *chain_guard = nullptr;
+    bool chain_uploaded = false;     // the device descriptor matches the current pointers (reset by drop_graph)
+    uint64_t generation = 0;         // bumped whenever a captured sweep / descriptor becomes stale (groups re-capture)
+    uint64_t stream_ops = 0;         // asynchronous work queued on the handle's stream from outside a sweep (groups order after it)
     bool fused = true;               // MRGP_FUSED=0: the multi-kernel sweep of round 1
     int chain_cluster = 0;           // CTAs per model of the fused sweep (0: by the number of regions)
     bool inferred_shortcut = true;   // skip phase A where Phi^T r == 0 identically (MRGP_STREAM_ALL=1: stream everything)
@@ -1066,10 +1069,29 @@ cudaError_t launch_ystats(mrgp_handle *h, const StreamArgs &a) {
     return cudaGetLastError();
 }
 
+int upload_chain_model(mrgp_handle *h);
+
+bool ystats_small(const mrgp_handle *h) {
+    if (h->sharded) return false;
+    const LayerPlan &lp = h->plan[0];
+    for (int r = 0; r < lp.R; ++r)
+        if (lp.offsets[r + 1] - lp.offsets[r] > kYstatsSmallMaxRegion) return false;
+    return true;
+}
+
 int do_ystats(mrgp_handle *h) {
     LayerDev &d = h->dev[0];
     const LayerPlan &lp = h->plan[0];
     const int M = h->cfg.n_basis, DY = h->cfg.dy;
+    if (ystats_small(h)) {   // one CTA per region of layer 0, straight from the descriptor (the form a batch of series uses)
+        int rc = h->chain_uploaded ? MRGP_OK : upload_chain_model(h);
+        if (rc) return rc;
+        const int e = launch_ystats_small(chain_solver_size(M), h->chain_ptr_dev, 1, lp.R, h->stream);
+        if (e != 0) return fail(h, MRGP_ECUDA, "y statistics launch: %s", cudaGetErrorString((cudaError_t)e));
+        count(h);
+        h->ystats_valid = true;
+        return MRGP_OK;
+    }
     StreamArgs a = stream_args(h, 0);
     cudaError_t e = cudaErrorInvalidValue;
     DISPATCH_M(M, e = launch_ystats<MM>(h, a));
@@ -1105,6 +1127,8 @@ int upload_chain_model(mrgp_handle *h) {
     m.J = h->cfg.n_layers;
     m.M = h->cfg.n_basis;
     m.DY = h->cfg.dy;
+    m.x = h->x - h->lo;
+    m.y = h->y - h->lo * h->cfg.dy;
     m.axB = s.axB; m.axKappa = s.axKappa; m.axRho = s.axRho; m.axLogC = s.axLogC; m.axCov = s.axCov;
     m.ardShape = s.ardShape; m.ardScale = s.ardScale; m.ardMean = s.ardMean; m.ardLogMean = s.ardLogMean;
     m.omega = s.omega; m.logOmegaHat = s.logOmegaHat; m.omegaIters = s.omegaIters; m.omegaEta = s.omegaEta; m.omegaWarm = s.omegaWarm;
@@ -1120,6 +1144,7 @@ int upload_chain_model(mrgp_handle *h) {
         l.R = h->plan[j].R;
         l.P = (int32_t)h->plan[j].pc_jp.size();
         l.offsets = d.offsets;
+        l.inv2L = d.inv2L; l.rsqrtL = d.rsqrtL;
         l.S = d.S; l.d = d.d; l.sumPhi = d.sumPhi; l.gram = d.gram; l.ancD = d.ancD;
         l.pc_ptr = d.pc_ptr; l.pc_anc = d.pc_anc; l.pc_lo = d.pc_lo; l.pc_hi = d.pc_hi;
         l.yc = d.yc; l.ysum = d.ysum;
@@ -1133,6 +1158,7 @@ int upload_chain_model(mrgp_handle *h) {
     const ChainModel *ptr = h->chain_dev;
     CK(cudaMemcpyAsync(h->chain_ptr_dev, &ptr, sizeof ptr, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // `ptr` is a local; the descriptor must be in place before any capture
+    h->chain_uploaded = true;
     return MRGP_OK;
 }
 
@@ -1331,6 +1357,8 @@ void drop_graph(mrgp_handle *h) {
     h->graph_exec = nullptr;
     h->graph = nullptr;
     h->launches_per_sweep = 0;
+    h->chain_uploaded = false;
+    h->generation += 1;
 }
 
 }  // namespace
@@ -1558,6 +1586,7 @@ int mrgp_set_data(mrgp_handle *h, const double *x_dev, const double *y_dev) {
 }
 
 int mrgp_set_data_host(mrgp_handle *h, const double *x_host, const double *y_host) {
+    if (h) h->stream_ops += 1;
     if (!h || !x_host || !y_host) return fail(h, MRGP_EINVAL, "null argument");
     if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
     const size_t N = (size_t)(h->hi - h->lo);
@@ -1581,6 +1610,7 @@ int mrgp_set_observations(mrgp_handle *h, const double *y_dev) {
 }
 
 int mrgp_set_observations_host(mrgp_handle *h, const double *y_host) {
+    if (h) h->stream_ops += 1;
     if (!h || !y_host) return fail(h, MRGP_EINVAL, "null argument");
     if (!h->have_data) return fail(h, MRGP_ESTATE, "no inputs yet: mrgp_set_data / mrgp_set_data_host first");
     const size_t N = (size_t)(h->hi - h->lo);
@@ -1616,6 +1646,7 @@ int mrgp_set_spectral(mrgp_handle *h, int32_t layer, int32_t use_prior, double n
 int mrgp_build_basis_stage(mrgp_handle *h, int32_t layer, int32_t stage, double interval_factor);
 
 int mrgp_build_basis(mrgp_handle *h, int32_t layer, double interval_factor, const double *L_host) {
+    if (h) h->stream_ops += 1;
     int rc = check_ready(h, layer, false);
     if (rc) return rc;
     if (h->sharded && !h->comm.ready) return fail(h, MRGP_ESTATE, "sharded handle: bind the peer exchange first, or use mrgp_build_basis_stage with all-reduces in between");
@@ -1659,6 +1690,7 @@ int mrgp_build_basis(mrgp_handle *h, int32_t layer, double interval_factor, cons
 }
 
 int mrgp_init_state(mrgp_handle *h, double noise_var0, double ard_prior_influence) {
+    if (h) h->stream_ops += 1;
     int rc = check_ready(h, 0, false);
     if (rc) return rc;
     for (int j = 0; j < h->cfg.n_layers; ++j)
@@ -1743,6 +1775,7 @@ int mrgp_get_state(mrgp_handle *h, int32_t layer, int32_t field, double *dst_hos
 }
 
 int mrgp_set_state(mrgp_handle *h, int32_t layer, int32_t field, const double *src_host, size_t n_elems) {
+    if (h) h->stream_ops += 1;
     if (!h || !src_host) return fail(h, MRGP_EINVAL, "null argument");
     if (!h->bound) return fail(h, MRGP_ESTATE, "no workspace bound");
     if (field == MRGP_F_FBAR || field == MRGP_F_FVAR) return fail(h, MRGP_EINVAL, "latent functions are derived, not settable");
@@ -1759,21 +1792,25 @@ int mrgp_set_state(mrgp_handle *h, int32_t layer, int32_t field, const double *s
 }
 
 int mrgp_phase_a(mrgp_handle *h, int32_t layer) {
+    if (h) h->stream_ops += 1;
     int rc = check_ready(h, layer, true);
     return rc ? rc : do_phase_a(h, layer);
 }
 
 int mrgp_axis_update(mrgp_handle *h, int32_t layer) {
+    if (h) h->stream_ops += 1;
     int rc = check_ready(h, layer, true);
     return rc ? rc : do_axis_update(h, layer, false);
 }
 
 int mrgp_phase_b(mrgp_handle *h, int32_t layer) {
+    if (h) h->stream_ops += 1;
     int rc = check_ready(h, layer, true);
     return rc ? rc : do_phase_b(h, layer, false);
 }
 
 int mrgp_bias_noise(mrgp_handle *h, int32_t layer) {
+    if (h) h->stream_ops += 1;
     int rc = check_ready(h, layer, true);
     if (!rc && layer == h->cfg.n_layers - 1) h->sweeps_done += 1;
     return rc ? rc : do_bias_noise(h, layer);
@@ -1818,19 +1855,20 @@ int mrgp_interval_failures(mrgp_handle *h, uint64_t *out) {
 }
 
 int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
+    if (h) h->stream_ops += 1;
     int rc = check_ready(h, 0, true);
     if (rc) return rc;
     if (n_iter < 0) return fail(h, MRGP_EINVAL, "n_iter < 0");
     if (h->sharded && !h->comm.ready)
         return fail(h, MRGP_ESTATE, "mrgp_sweep on a sharded handle needs the peer exchange (mrgp_comm_bind); without it drive the phases and the all-reduces from the host");
     const bool fused = use_fused(h);
-    if (fused && !h->ystats_valid) {
+    if (fused) {
         if ((rc = build_invariants(h))) return rc;
-        if ((rc = do_ystats(h))) return rc;
+        if (!h->chain_uploaded && (rc = upload_chain_model(h))) return rc;
+        if (!h->ystats_valid && (rc = do_ystats(h))) return rc;
     }
     if (!h->graph_exec) {
         if ((rc = build_invariants(h))) return rc;
-        if (fused && (rc = upload_chain_model(h))) return rc;
         h->launches_per_sweep = 0;
         h->capturing = true;
         cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
@@ -1856,14 +1894,23 @@ int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
     return MRGP_OK;
 }
 
-// ---- groups of independent models: one captured graph, the models as parallel branches ---------------------
+// ---- groups of independent models ---------------------------------------------------------------------------
+// Batched form (every member takes the fused ci sweep with the same solver and cluster size): ONE launch of
+// k_ci_sweep with one cluster per model (plus one launch of k_ystats_small when observations changed).
+// Otherwise: one captured graph with the members' sweeps as parallel branches.
 struct mrgp_group {
     std::vector<mrgp_handle *> handles;
+    std::vector<uint64_t> generation, stream_ops;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    bool batched = false;
+    int solver = 0, cluster = 1, r0_max = 1;
+    const ChainModel **ptrs_dev = nullptr;     // batched: device array of the members' descriptors
+    cudaEvent_t ev = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     std::vector<int64_t> launches_per_sweep;
+    int64_t launches = 0;
     std::string error;
 };
 
@@ -1873,34 +1920,64 @@ static int gfail(mrgp_group *g, int code, const char *what, cudaError_t e) {
     return code;
 }
 
-int mrgp_group_create(mrgp_handle *const *handles, int32_t n, void *cuda_stream, mrgp_group **out) {
-    if (!handles || !out || n < 1) return MRGP_EINVAL;
-    *out = nullptr;
+// Everything a member queued on its own stream (uploads, state writes, basis builds) precedes the group's next launch.
+static int group_order_after_members(mrgp_group *g) {
+    for (size_t i = 0; i < g->handles.size(); ++i) {
+        mrgp_handle *h = g->handles[i];
+        if (h->stream_ops == g->stream_ops[i] || h->stream == g->stream) continue;
+        cudaError_t e = cudaEventRecord(g->ev, h->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(g->stream, g->ev, 0);
+        if (e != cudaSuccess) return gfail(g, MRGP_ECUDA, "ordering after a member stream", e);
+        g->stream_ops[i] = h->stream_ops;
+    }
+    return MRGP_OK;
+}
+
+static void group_drop(mrgp_group *g) {
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    g->exec = nullptr;
+    g->graph = nullptr;
+}
+
+// (Re)build what the group replays: descriptors of the members (batched) or the branch graph.
+static int group_prepare(mrgp_group *g) {
+    const int n = (int)g->handles.size();
+    group_drop(g);
+    bool batched = true;
+    int r0 = 1;
     for (int i = 0; i < n; ++i) {
-        mrgp_handle *h = handles[i];
+        mrgp_handle *h = g->handles[i];
         int rc = check_ready(h, 0, true);
-        if (rc) return rc;
-        if (h->sharded) return fail(h, MRGP_EINVAL, "sharded handles cannot join a group");
-        if (h->cfg.device != handles[0]->cfg.device) return fail(h, MRGP_EINVAL, "all models of a group live on one device");
-        if ((rc = build_invariants(h))) return rc;
-        if (use_fused(h)) {
-            if (!h->ystats_valid && (rc = do_ystats(h))) return rc;
-            if ((rc = upload_chain_model(h))) return rc;
+        if (rc) {
+            g->error = h->err;
+            return rc;
         }
+        if ((rc = build_invariants(h))) return rc;
+        const bool f = use_fused(h) && ystats_small(h);
+        batched = batched && f && chain_solver_size(h->cfg.n_basis) == chain_solver_size(g->handles[0]->cfg.n_basis) &&
+                  chain_cluster_size(h) == chain_cluster_size(g->handles[0]);
+        if (use_fused(h) && !h->chain_uploaded && (rc = upload_chain_model(h))) return rc;
+        r0 = std::max(r0, h->plan[0].R);
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(h, MRGP_ECUDA, "stream synchronisation failed");
     }
-    mrgp_group *g = new mrgp_group();
-    g->handles.assign(handles, handles + n);
-    g->launches_per_sweep.assign(n, 0);
+    g->batched = batched;
+    g->r0_max = r0;
     cudaError_t e;
-    if (cuda_stream) {
-        g->stream = static_cast<cudaStream_t>(cuda_stream);
-    } else {
-        if ((e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking)) != cudaSuccess) {
-            delete g;
-            return MRGP_ECUDA;
+    if (batched) {
+        g->solver = chain_solver_size(g->handles[0]->cfg.n_basis);
+        g->cluster = chain_cluster_size(g->handles[0]);
+        if (!g->ptrs_dev && (e = cudaMalloc(&g->ptrs_dev, (size_t)n * sizeof(ChainModel *))) != cudaSuccess)
+            return gfail(g, MRGP_ECUDA, "cudaMalloc of the descriptor table", e);
+        std::vector<const ChainModel *> ptrs(n);
+        for (int i = 0; i < n; ++i) ptrs[i] = g->handles[i]->chain_dev;
+        if ((e = cudaMemcpy(g->ptrs_dev, ptrs.data(), (size_t)n * sizeof(ChainModel *), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return gfail(g, MRGP_ECUDA, "upload of the descriptor table", e);
+        for (int i = 0; i < n; ++i) {
+            g->generation[i] = g->handles[i]->generation;
+            g->launches_per_sweep[i] = 0;
         }
-        g->own_stream = true;
+        return MRGP_OK;
     }
     // the streams only shape the captured DAG (one branch per model); the replay does not use them
     std::vector<cudaStream_t> tmp(n, nullptr);
@@ -1908,13 +1985,16 @@ int mrgp_group_create(mrgp_handle *const *handles, int32_t n, void *cuda_stream,
     cudaEvent_t start = nullptr;
     int rc = MRGP_OK;
     auto cleanup = [&]() {
-        for (auto s : tmp)
-            if (s) cudaStreamDestroy(s);
+        for (auto st : tmp)
+            if (st) cudaStreamDestroy(st);
         for (auto ev : done)
             if (ev) cudaEventDestroy(ev);
         if (start) cudaEventDestroy(start);
     };
     for (int i = 0; i < n && rc == MRGP_OK; ++i) {
+        mrgp_handle *h = g->handles[i];
+        if (use_fused(h) && !h->ystats_valid && (rc = do_ystats(h))) break;
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = MRGP_ECUDA;
         if (cudaStreamCreateWithFlags(&tmp[i], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess)
             rc = MRGP_ECUDA;
@@ -1925,16 +2005,18 @@ int mrgp_group_create(mrgp_handle *const *handles, int32_t n, void *cuda_stream,
     if (rc == MRGP_OK) {
         cudaEventRecord(start, g->stream);
         for (int i = 0; i < n; ++i) {
-            mrgp_handle *h = handles[i];
+            mrgp_handle *h = g->handles[i];
             cudaStreamWaitEvent(tmp[i], start, 0);
             cudaStream_t saved = h->stream;
             h->stream = tmp[i];
+            const int64_t saved_lps = h->launches_per_sweep;
             h->launches_per_sweep = 0;
             h->capturing = true;
             const int r = sweep_once(h, true);
             h->capturing = false;
             h->stream = saved;
             g->launches_per_sweep[i] = h->launches_per_sweep;
+            h->launches_per_sweep = saved_lps;
             if (r && rc == MRGP_OK) rc = r;
             cudaEventRecord(done[i], tmp[i]);
             cudaStreamWaitEvent(g->stream, done[i], 0);
@@ -1946,10 +2028,42 @@ int mrgp_group_create(mrgp_handle *const *handles, int32_t n, void *cuda_stream,
     }
     cleanup();
     if (rc != MRGP_OK) {
-        if (g->exec) cudaGraphExecDestroy(g->exec);
-        if (g->graph) cudaGraphDestroy(g->graph);
-        if (g->own_stream) cudaStreamDestroy(g->stream);
-        delete g;
+        group_drop(g);
+        return rc;
+    }
+    for (int i = 0; i < n; ++i) g->generation[i] = g->handles[i]->generation;
+    return MRGP_OK;
+}
+
+int mrgp_group_create(mrgp_handle *const *handles, int32_t n, void *cuda_stream, mrgp_group **out) {
+    if (!handles || !out || n < 1) return MRGP_EINVAL;
+    *out = nullptr;
+    for (int i = 0; i < n; ++i) {
+        mrgp_handle *h = handles[i];
+        int rc = check_ready(h, 0, true);
+        if (rc) return rc;
+        if (h->sharded) return fail(h, MRGP_EINVAL, "sharded handles cannot join a group");
+        if (h->cfg.device != handles[0]->cfg.device) return fail(h, MRGP_EINVAL, "all models of a group live on one device");
+    }
+    mrgp_group *g = new mrgp_group();
+    g->handles.assign(handles, handles + n);
+    g->launches_per_sweep.assign(n, 0);
+    g->generation.assign(n, ~0ull);
+    g->stream_ops.assign(n, ~0ull);
+    if (cuda_stream) {
+        g->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete g;
+            return MRGP_ECUDA;
+        }
+        g->own_stream = true;
+    }
+    int rc = cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming) == cudaSuccess ? MRGP_OK : MRGP_ECUDA;
+    if (rc == MRGP_OK) rc = group_prepare(g);
+    if (rc != MRGP_OK) {
+        g_create_error = g->error;
+        mrgp_group_destroy(g);
         return rc;
     }
     *out = g;
@@ -1958,16 +2072,50 @@ int mrgp_group_create(mrgp_handle *const *handles, int32_t n, void *cuda_stream,
 
 int mrgp_group_sweep(mrgp_group *g, int32_t n_iter) {
     if (!g || n_iter < 0) return MRGP_EINVAL;
+    const int n = (int)g->handles.size();
+    // a member whose captured sweep / descriptor went stale (new pointers, new intervals, re-initialised state ...)
+    // since the group was prepared: prepare again
+    bool stale = false;
+    for (int i = 0; i < n; ++i) stale = stale || g->handles[i]->generation != g->generation[i];
+    int rc;
+    if (stale && (rc = group_prepare(g))) return rc;
+    if ((rc = group_order_after_members(g))) return rc;
+    if (g->batched) {
+        bool need_y = false;
+        for (int i = 0; i < n; ++i) need_y = need_y || !g->handles[i]->ystats_valid;
+        if (need_y) {   // new observations somewhere: the statistics of all members in one launch
+            const int e = launch_ystats_small(g->solver, g->ptrs_dev, n, g->r0_max, g->stream);
+            if (e != 0) return gfail(g, MRGP_ECUDA, "y statistics launch", (cudaError_t)e);
+            for (int i = 0; i < n; ++i) g->handles[i]->ystats_valid = true;
+            g->launches += 1;
+        }
+        for (int it = 0; it < n_iter; ++it) {
+            const int e = launch_ci_sweep(g->solver, g->ptrs_dev, n, g->cluster, g->stream);
+            if (e != 0) return gfail(g, MRGP_ECUDA, "fused sweep launch", (cudaError_t)e);
+        }
+        g->launches += n_iter;
+        for (int i = 0; i < n; ++i) g->handles[i]->sweeps_done += n_iter;
+        return MRGP_OK;
+    }
     for (int it = 0; it < n_iter; ++it) {
         cudaError_t e = cudaGraphLaunch(g->exec, g->stream);
         if (e != cudaSuccess) return gfail(g, MRGP_ECUDA, "cudaGraphLaunch", e);
     }
-    for (size_t i = 0; i < g->handles.size(); ++i) {
+    for (int i = 0; i < n; ++i) {
         g->handles[i]->launches += g->launches_per_sweep[i] * n_iter;
+        g->launches += g->launches_per_sweep[i] * n_iter;
         g->handles[i]->sweeps_done += n_iter;
     }
     return MRGP_OK;
 }
+
+int mrgp_group_observations_changed(mrgp_group *g) {
+    if (!g) return MRGP_EINVAL;
+    for (auto h : g->handles) h->ystats_valid = false;
+    return MRGP_OK;
+}
+
+int64_t mrgp_group_launch_count(const mrgp_group *g) { return g ? g->launches : -1; }
 
 int mrgp_group_synchronize(mrgp_group *g) {
     if (!g) return MRGP_EINVAL;
@@ -1977,8 +2125,9 @@ int mrgp_group_synchronize(mrgp_group *g) {
 
 void mrgp_group_destroy(mrgp_group *g) {
     if (!g) return;
-    if (g->exec) cudaGraphExecDestroy(g->exec);
-    if (g->graph) cudaGraphDestroy(g->graph);
+    group_drop(g);
+    if (g->ptrs_dev) cudaFree(g->ptrs_dev);
+    if (g->ev) cudaEventDestroy(g->ev);
     if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
     delete g;
 }

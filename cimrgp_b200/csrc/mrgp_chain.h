@@ -20,12 +20,13 @@ struct ChainLayer {
     int32_t R, P;                  // regions; pieces region x coarser region (layers > 0)
     const int64_t *offsets;        // (R + 1)
     // static
+    const double *inv2L, *rsqrtL;  // (R) 1 / (2 L), L^-1/2 of the basis interval
     const double *S, *d;           // (R, M) spectral density, sum phi^2
     const double *sumPhi, *gram;   // (R, M) Phi^T 1, (R, M, M) Phi^T Phi
     const double *ancD;            // (P, M) sum over the piece of the squared basis functions of its coarser layer
     const int32_t *pc_ptr, *pc_anc;   // piece table: (layer, R + 1) CSR, coarser region per piece
     const int64_t *pc_lo, *pc_hi;
-    const double *yc, *ysum;       // layer 0: (R, M, 2) Phi^T y and (R, 4) sum y_0, sum y_1, sum |y|^2, -
+    double *yc, *ysum;             // layer 0: (R, M, 2) Phi^T y and (R, 4) sum y_0, sum y_1, sum |y|^2, -
     // posterior / stats
     double *prec, *zeta, *ytil, *A, *A_prev, *m2, *cm2;
     double *noise_shape, *noise_scale, *noise_mean, *noise_log_mean;
@@ -35,6 +36,7 @@ struct ChainLayer {
 
 struct ChainModel {
     int32_t J, M, DY, pad;
+    const double *x, *y;           // (N), (N, DY) normalised inputs and observations, indexed by the global sample number
     // shared posterior / stats (Posteriors.py:482-541, Stats.py:354-420)
     double *axB, *axKappa, *axRho, *axLogC, *axCov, *ardShape, *ardScale, *ardMean, *ardLogMean;
     double *omega, *logOmegaHat, *omegaIters, *omegaEta, *omegaWarm;
@@ -63,6 +65,11 @@ inline int chain_solver_size(int M) {
 // Launch n_models clusters of `cluster` CTAs on `stream`.  models_dev: device array of pointers to ChainModel.
 // Returns a cudaError_t as int.
 int launch_ci_sweep(int solver_size, const ChainModel *const *models_dev, int n_models, int cluster, void *stream);
+// Sufficient statistics of the observations for layer 0 (Phi^T y, sum y, sum |y|^2), one CTA per (model, region of
+// layer 0): the form for models whose layer-0 regions are small (a batch of short series: one launch for all of them).
+// r0_max: largest number of layer-0 regions among the models.
+int launch_ystats_small(int solver_size, const ChainModel *const *models_dev, int n_models, int r0_max, void *stream);
+constexpr int64_t kYstatsSmallMaxRegion = 32768;   // longest layer-0 region this form is used for
 size_t ci_sweep_smem_bytes(int solver_size);
 
 }  // namespace mrgp

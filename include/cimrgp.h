@@ -255,13 +255,23 @@ int mrgp_build_basis_stage(mrgp_handle *h, int32_t layer, int32_t stage, double 
 
 /* ---- groups of independent models (BASELINE config 5: a batch of series) --------------------------------- */
 
-/* One sweep of every model of the group captured as parallel branches of ONE CUDA graph: a launch per group and
- * iteration instead of one per model (the reference fits its models one after the other; they are independent).
- * The models must be initialised, unsharded and on one device; their state is what mrgp_sweep would leave.
- * cuda_stream: the stream the group graph is launched on (NULL: the group creates one).                      */
+/* The reference fits its models one after the other; they are independent.  A group sweeps all of its models with one
+ * launch per iteration:
+ *   - batched form (every member is a ci model with static intervals, region-specific noise and bias, n_basis <= 32,
+ *     layer-0 regions of at most 32768 samples): one launch of the fused sweep kernel with one thread-block cluster per
+ *     model, and one launch for the layer-0 statistics of all members when observations changed;
+ *   - otherwise: the members' sweeps captured as parallel branches of ONE CUDA graph.
+ * The models must be initialised, unsharded and on one device; their state is what mrgp_sweep would leave.  Work queued
+ * on a member's own stream (uploads, state writes) is ordered before the group's next launch; a member whose captured
+ * sweep went stale (new pointers, intervals, re-initialisation) makes the group prepare itself again.  The batched
+ * form keeps a small table of descriptor pointers in device memory of its own (n x 8 bytes, cudaMalloc).
+ * cuda_stream: the stream the group launches on (NULL: the group creates one).
+ * mrgp_group_observations_changed: the caller overwrote the members' (borrowed) observation buffers in place.          */
 typedef struct mrgp_group mrgp_group;
 int mrgp_group_create(mrgp_handle *const *handles, int32_t n, void *cuda_stream, mrgp_group **out);
 int mrgp_group_sweep(mrgp_group *g, int32_t n_iter);
+int mrgp_group_observations_changed(mrgp_group *g);
+int64_t mrgp_group_launch_count(const mrgp_group *g);
 int mrgp_group_synchronize(mrgp_group *g);
 void mrgp_group_destroy(mrgp_group *g);
 

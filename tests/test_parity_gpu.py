@@ -159,9 +159,9 @@ def test_graph_replay_equals_stepwise_phases_and_is_deterministic():
     sa, sb, sc = a._engine.state(), b._engine.state(), c._engine.state()
     for k in sa:
         assert np.array_equal(sa[k], sc[k]), k          # same launch geometry -> bitwise reproducible
-    # graph replay == per-phase ABI calls, up to the summation order of the layer statistics: the per-phase calls
-    # stream every layer, the captured sweep takes the statistics of the inferred-target layers in closed form
-    compare(sa, sb, rtol=1e-11)
+    # sweep == per-phase ABI calls, up to the summation order of the layer statistics: the per-phase calls stream every
+    # layer, the fused sweep takes layer 0 from the sufficient statistics of y and the layers above in closed form
+    compare(sa, sb, rtol=1e-9)
 
 
 def test_skipped_statistics_pass_of_inferred_layers_is_an_identity():
@@ -642,7 +642,7 @@ def test_config4_closed_form_statistics_at_full_size_on_a_non_inert_state(monkey
         for j in range(1, res + 1):
             m._engine.put(j, _lib.F_A, pert[j][0])
             m._engine.put(j, _lib.F_BIAS_MEAN, pert[j][1])
-        m.fit(2, None)
+        m.fit(1, None)       # (a second sweep would find the upper layers inert again: their noise precision is ~1e-45)
         states.append(m._engine.state(latent=False))
         del m
     assert np.max(np.abs(states[1]['L5.ytil'])) > 1e-3          # the upper layers really carry signal here
