@@ -43,8 +43,13 @@ __device__ __forceinline__ unsigned long long gtimer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#define PROF(k)                                                              \
+    do {                                                                     \
+        if (m.prof) m.prof[j * 16 + (k)] = (double)clock64();                \
+    } while (0)
 __device__ __forceinline__ void worker_bar(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 
+constexpr int kBatch = 4; // regions a worker warp handles at once (their L2 round trips overlap)
 constexpr int LD = 34;    // row stride of the transposed tables: conflict-free columns, 16-byte aligned rows
 constexpr int LW = 33;    // row stride of the log omega_hat table
 
@@ -61,47 +66,22 @@ struct ChainSmem {
     double pub[4 * 32];       // CTA 0: axis covariance (c00, c01, c11) and ARD mean of the layer, read by every CTA
     double loc[4 * 32];       // local copy of pub
     double rowmax[32], colmax[32];
+    double dg[32], sh[32], sc[32];              // shared step: digamma(shape), mixed prior shape / scale
+    double eta[kChainMaxLayers][32];            // warm start of the solver: log column scalings of the previous sweep
+    double warm[kChainMaxLayers];
     int nchol;
 };
 
 // ---- worker steps (one warp per region, lane = basis function) --------------------------------------------------
 
-// P1-finish of region l of layer j (Posteriors.py:35-78) and its contribution to the sums over regions that the shared
-// step needs: 0.5 noise zeta y y^T (B_i, Posteriors.py:507-517) and the two terms that make sum_l m2/S linear in the
-// axis covariance (ARD, Posteriors.py:533-541; see k_mid1).  Layer 0 (observed targets, no latent function):
-//     y_tilde_i = (Phi^T y)_i - s_i b - sum_{k != i} G_ik a_k         (from the sufficient statistics of y)
-// layers above (targets inferred from the layer's own posterior, LatentOutputs.py:20-49): y_tilde_i = d_i a_i.
-__device__ __forceinline__ void mid1_region(const ChainModel &m, const ChainLayer &ly, int j, int l, int lane, const double *ardMean,
-                                            double (&acc)[7]) {
-    const int M = m.M;
-    const bool on = lane < M;
-    const size_t ri = (size_t)l * M + (on ? lane : 0);
-    const double a0 = on ? __ldcg(ly.A + ri * 2) : 0.0, a1 = on ? __ldcg(ly.A + ri * 2 + 1) : 0.0;
-    const double dsum = on ? ly.d[ri] : 0.0, S = on ? ly.S[ri] : 1.0;
-    const double noise = __ldcg(ly.noise_mean + l);
-    double y0, y1;
-    if (j == 0) {
-        const double b0 = __ldcg(ly.bias_mean + (size_t)l * 2), b1 = __ldcg(ly.bias_mean + (size_t)l * 2 + 1);
-        const double s = on ? ly.sumPhi[ri] : 0.0;
-        double t0 = on ? fma(-s, b0, ly.yc[ri * 2]) : 0.0, t1 = on ? fma(-s, b1, ly.yc[ri * 2 + 1]) : 0.0;
-        const double *G = ly.gram + (size_t)l * M * M;
-        for (int k = 0; k < M; ++k) {
-            const double ak0 = __shfl_sync(kFull, a0, k), ak1 = __shfl_sync(kFull, a1, k);
-            const double g = (on && k != lane) ? G[(size_t)k * M + lane] : 0.0;
-            t0 = fma(-g, ak0, t0);
-            t1 = fma(-g, ak1, t1);
-        }
-        y0 = t0;
-        y1 = t1;
-    } else {
-        y0 = dsum * a0;
-        y1 = dsum * a1;
-    }
-    if (!on) return;
-    const double prec = ardMean[lane] / S + noise * dsum;      // Posteriors.py:40-42
+// P1-finish of a region (Posteriors.py:35-78) and its contribution to the sums over regions that the shared step
+// needs: 0.5 noise zeta y y^T (B_i, Posteriors.py:507-517) and the two terms that make sum_l m2/S linear in the axis
+// covariance (ARD, Posteriors.py:533-541; see k_mid1).
+__device__ __forceinline__ void p1_finish(const ChainLayer &ly, size_t ri, double y0, double y1, double dsum, double S, double noise,
+                                          double ard, double (&acc)[7]) {
+    const double prec = ard / S + noise * dsum;      // Posteriors.py:40-42
     const double zeta = noise / prec;
-    ly.ytil[ri * 2] = y0;
-    ly.ytil[ri * 2 + 1] = y1;
+    *reinterpret_cast<double2 *>(ly.ytil + ri * 2) = make_double2(y0, y1);
     ly.prec[ri] = prec;
     ly.zeta[ri] = zeta;
     const double w = 0.5 * noise * zeta;
@@ -115,117 +95,256 @@ __device__ __forceinline__ void mid1_region(const ChainModel &m, const ChainLaye
     acc[6] += z2s * (y1 * y1);
 }
 
-// S2 of region l (Stats.py:67-100) with the layer's new axis covariance, then the P4 / P5 statistics of the region in
-// closed form and its bias / noise update (Posteriors.py:81-93, 132-148; Stats.py:102-124).
-//   layer 0:  r = y - Phi A_new:   sum r = sum y - A^T s,   sum |r|^2 = sum |y|^2 - 2 tr(A^T Phi^T y) + tr(A^T G A)
-//   layer j:  r = Phi (A_old - A_new) + b_old (see k_stats_b), sum f_var from the pieces region x coarser region.
-__device__ __forceinline__ void mid2_stats_region(const ChainModel &m, const ChainLayer &ly, int j, int l, int lane, const double *cov) {
+// Layer 0 (observed targets, no latent function), from the sufficient statistics of y:
+//     y_tilde_i = (Phi^T y)_i - s_i b - sum_{k != i} G_ik a_k
+__device__ __forceinline__ void mid1_layer0(const ChainModel &m, const ChainLayer &ly, int l, int lane, const double *ardMean, double (&acc)[7]) {
     const int M = m.M;
     const bool on = lane < M;
     const size_t ri = (size_t)l * M + (on ? lane : 0);
-    const double c00 = cov[lane], c01 = cov[32 + lane], c11 = cov[64 + lane];
-    const double y0 = on ? ly.ytil[ri * 2] : 0.0, y1 = on ? ly.ytil[ri * 2 + 1] : 0.0;
-    const double zeta = on ? ly.zeta[ri] : 0.0, prec = on ? ly.prec[ri] : 1.0;
-    const double ao0 = on ? __ldcg(ly.A + ri * 2) : 0.0, ao1 = on ? __ldcg(ly.A + ri * 2 + 1) : 0.0;
-    const double cy0 = c00 * y0 + c01 * y1, cy1 = c01 * y0 + c11 * y1;
-    const double an0 = zeta * cy0, an1 = zeta * cy1;
+    const double2 a = on ? __ldcg(reinterpret_cast<const double2 *>(ly.A) + ri) : make_double2(0.0, 0.0);
+    const double dsum = on ? __ldg(ly.d + ri) : 0.0, S = on ? __ldg(ly.S + ri) : 1.0;
+    const double noise = __ldcg(ly.noise_mean + l);
+    const double b0 = __ldcg(ly.bias_mean + (size_t)l * 2), b1 = __ldcg(ly.bias_mean + (size_t)l * 2 + 1);
+    const double s = on ? __ldg(ly.sumPhi + ri) : 0.0;
+    double t0 = on ? fma(-s, b0, ly.yc[ri * 2]) : 0.0, t1 = on ? fma(-s, b1, ly.yc[ri * 2 + 1]) : 0.0;
+    const double *G = ly.gram + (size_t)l * M * M;
+#pragma unroll 6
+    for (int k = 0; k < M; ++k) {
+        const double ak0 = __shfl_sync(kFull, a.x, k), ak1 = __shfl_sync(kFull, a.y, k);
+        const double g = (on && k != lane) ? __ldg(G + (size_t)k * M + lane) : 0.0;
+        t0 = fma(-g, ak0, t0);
+        t1 = fma(-g, ak1, t1);
+    }
+    if (on) p1_finish(ly, ri, t0, t1, dsum, S, noise, ardMean[lane], acc);
+}
+
+// Layers above the first (targets inferred from the layer's own posterior, LatentOutputs.py:20-49): y_tilde_i = d_i a_i.
+// NB regions l0, l0 + stride, ... at once: their loads are issued together (the step is a chain of L2 round trips).
+template <int NB>
+__device__ __forceinline__ void mid1_upper(const ChainModel &m, const ChainLayer &ly, int l0, int stride, int lane, const double *ardMean,
+                                           double (&acc)[7]) {
+    const int M = m.M;
+    const bool on = lane < M;
+    double2 a[NB];
+    double dsum[NB], S[NB], noise[NB];
+    size_t ri[NB];
+    bool act[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        const int l = l0 + q * stride;
+        act[q] = on && l < ly.R;
+        ri[q] = (size_t)(act[q] ? l : 0) * M + (on ? lane : 0);
+        a[q] = act[q] ? __ldcg(reinterpret_cast<const double2 *>(ly.A) + ri[q]) : make_double2(0.0, 0.0);
+        dsum[q] = act[q] ? __ldg(ly.d + ri[q]) : 0.0;
+        S[q] = act[q] ? __ldg(ly.S + ri[q]) : 1.0;
+        noise[q] = act[q] ? __ldcg(ly.noise_mean + l) : 0.0;
+    }
+    const double ard = ardMean[lane];
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+        if (act[q]) p1_finish(ly, ri[q], dsum[q] * a[q].x, dsum[q] * a[q].y, dsum[q], S[q], noise[q], ard, acc);
+}
+
+// P4 / P5 / S5 of one region from its statistics sums = [sum r_0, sum r_1, sum |r|^2, sum f_var, sum phi^2 cm2]
+// (region-specific noise and bias: Posteriors.py:81-93, 132-148 - y_var NOT times n, :138; Stats.py:102-124).
+// rc: the region's constants [n, bias_prec0, bias_mean0 (2), noise_shape0, noise_scale0, digamma(noise shape), -].
+__device__ __forceinline__ void bias_noise_update(const ChainLayer &ly, int l, bool infer, const double (&sums)[5], const double (&rc)[7],
+                                                  double noise_old, double b0, double b1) {
+    const double n = rc[0], bp0 = rc[1], bp = bp0 + n, ibp = 1.0 / bp;
+    const double mn0 = ibp * (rc[2] * bp0 + sums[0]), mn1 = ibp * (rc[3] * bp0 + sums[1]);
+    const double t3 = bp0 * (rc[2] * rc[2] + rc[3] * rc[3]), t4 = bp * (mn0 * mn0 + mn1 * mn1);
+    const double yvar = infer ? 1.0 / noise_old : 0.0;
+    const double shape = rc[4] + 0.5 * 2.0 * n;
+    const double scale = rc[5] + 0.5 * (t3 - t4 + sums[2] + sums[3] + sums[4] + yvar);
+    *reinterpret_cast<double2 *>(ly.bias_prev + (size_t)l * 2) = make_double2(b0, b1);
+    *reinterpret_cast<double2 *>(ly.bias_mean + (size_t)l * 2) = make_double2(mn0, mn1);
+    ly.yvar[l] = yvar;
+    ly.bias_prec[l] = bp;
+    ly.bias_var[l] = ibp;
+    ly.noise_shape[l] = shape;
+    ly.noise_scale[l] = scale;
+    ly.noise_mean[l] = shape / scale;
+    ly.noise_log_mean[l] = rc[6] - log(scale);
+#pragma unroll
+    for (int d = 0; d < 5; ++d) ly.sumsB[(size_t)l * 5 + d] = sums[d];
+}
+
+// S2 of a region (Stats.py:67-100) with the layer's new axis covariance; returns the new coefficients and cm2.
+__device__ __forceinline__ void s2_region(const ChainLayer &ly, size_t ri, bool on, double c00, double c01, double c11, double2 yt,
+                                          double zeta, double prec, double2 ao, double2 &an, double &cm2) {
+    const double cy0 = c00 * yt.x + c01 * yt.y, cy1 = c01 * yt.x + c11 * yt.y;
+    an = make_double2(zeta * cy0, zeta * cy1);
     const double z2 = zeta * zeta;
     const double ccy0 = c00 * cy0 + c01 * cy1, ccy1 = c01 * cy0 + c11 * cy1;
-    const double m2 = 1.0 / prec + z2 * (y0 * cy0 + y1 * cy1);
-    const double cm2 = 1.0 / prec + z2 * (y0 * (cy0 - ccy0) + y1 * (cy1 - ccy1));
+    const double m2 = 1.0 / prec + z2 * (yt.x * cy0 + yt.y * cy1);
+    cm2 = 1.0 / prec + z2 * (yt.x * (cy0 - ccy0) + yt.y * (cy1 - ccy1));
     if (on) {
-        ly.A_prev[ri * 2] = ao0;
-        ly.A_prev[ri * 2 + 1] = ao1;
-        ly.A[ri * 2] = an0;
-        ly.A[ri * 2 + 1] = an1;
+        *reinterpret_cast<double2 *>(ly.A_prev + ri * 2) = ao;
+        *reinterpret_cast<double2 *>(ly.A + ri * 2) = an;
         ly.m2[ri] = m2;
         ly.cm2[ri] = cm2;
     }
-    // ---- statistics --------------------------------------------------------------------------------------------
-    const double n = (double)(ly.offsets[l + 1] - ly.offsets[l]);
-    const double dsum = on ? ly.d[ri] : 0.0, si = on ? ly.sumPhi[ri] : 0.0;
-    const double dc = wsum(on ? dsum * cm2 : 0.0);
+}
+
+// Layer 0: S2, then the P4 / P5 statistics from the sufficient statistics of y and the bias / noise update:
+//   r = y - Phi A_new:   sum r = sum y - A^T s,   sum |r|^2 = sum |y|^2 - 2 tr(A^T Phi^T y) + tr(A^T G A)
+__device__ __forceinline__ void mid2_stats_layer0(const ChainModel &m, const ChainLayer &ly, int l, int lane, const double *cov) {
+    const int M = m.M;
+    const bool on = lane < M;
+    const size_t ri = (size_t)l * M + (on ? lane : 0);
+    const double2 yt = on ? __ldcg(reinterpret_cast<const double2 *>(ly.ytil) + ri) : make_double2(0.0, 0.0);
+    const double zeta = on ? __ldcg(ly.zeta + ri) : 0.0, prec = on ? __ldcg(ly.prec + ri) : 1.0;
+    const double2 ao = on ? __ldcg(reinterpret_cast<const double2 *>(ly.A) + ri) : make_double2(0.0, 0.0);
+    const double dsum = on ? __ldg(ly.d + ri) : 0.0, si = on ? __ldg(ly.sumPhi + ri) : 0.0;
+    const double2 yc = on ? *reinterpret_cast<const double2 *>(ly.yc + ri * 2) : make_double2(0.0, 0.0);
+    const double rcl = lane < 7 ? __ldg(ly.rconst + (size_t)l * 8 + lane) : 0.0;
+    const double b0 = __ldcg(ly.bias_mean + (size_t)l * 2), b1 = __ldcg(ly.bias_mean + (size_t)l * 2 + 1);
+    const double ys0 = ly.ysum[(size_t)l * 4 + 0], ys1 = ly.ysum[(size_t)l * 4 + 1], y2 = ly.ysum[(size_t)l * 4 + 2];
+    double2 an;
+    double cm2;
+    s2_region(ly, ri, on, cov[lane], cov[32 + lane], cov[64 + lane], yt, zeta, prec, ao, an, cm2);
     const double *G = ly.gram + (size_t)l * M * M;
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll 6
+    for (int k = 0; k < M; ++k) {
+        const double g = on ? __ldg(G + (size_t)k * M + lane) : 0.0;
+        t0 = fma(g, __shfl_sync(kFull, an.x, k), t0);
+        t1 = fma(g, __shfl_sync(kFull, an.y, k), t1);
+    }
+    const double sa0 = wsum(si * an.x), sa1 = wsum(si * an.y);
+    const double cross = wsum(an.x * yc.x + an.y * yc.y);
+    const double quad = wsum(an.x * t0 + an.y * t1);
     double sums[5];
-    if (j == 0) {
-        const double sa0 = wsum(on ? si * an0 : 0.0), sa1 = wsum(on ? si * an1 : 0.0);
-        const double cross = wsum(on ? an0 * ly.yc[ri * 2] + an1 * ly.yc[ri * 2 + 1] : 0.0);
-        double t0 = 0.0, t1 = 0.0;
-        for (int k = 0; k < M; ++k) {
-            const double g = on ? G[(size_t)k * M + lane] : 0.0;
-            t0 = fma(g, __shfl_sync(kFull, an0, k), t0);
-            t1 = fma(g, __shfl_sync(kFull, an1, k), t1);
-        }
-        const double quad = wsum(on ? an0 * t0 + an1 * t1 : 0.0);
-        const double y2 = ly.ysum[(size_t)l * 4 + 2];
-        sums[0] = ly.ysum[(size_t)l * 4 + 0] - sa0;
-        sums[1] = ly.ysum[(size_t)l * 4 + 1] - sa1;
-        sums[2] = (y2 - 2.0 * cross) + quad;
-        sums[3] = 0.0;
-        sums[4] = dc;
-        if (lane == 0 && l == 0) {
+    sums[0] = ys0 - sa0;
+    sums[1] = ys1 - sa1;
+    sums[2] = (y2 - 2.0 * cross) + quad;
+    sums[3] = 0.0;
+    sums[4] = wsum(dsum * cm2);
+    double rc[7];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) rc[t] = __shfl_sync(kFull, rcl, t);
+    if (lane == 0) {
+        if (l == 0) {
             const double ratio = y2 > 0.0 ? sums[2] / y2 : 1.0;
             m.guard[0] = ratio;
             if (!(ratio >= kChainGuard)) atomicOr(m.status, 1u);
         }
-    } else {
-        const double dA0 = ao0 - an0, dA1 = ao1 - an1;
-        const double sd0 = wsum(si * dA0), sd1 = wsum(si * dA1);
+        bias_noise_update(ly, l, false, sums, rc, 1.0, b0, b1);
+    }
+}
+
+// Layers above the first: S2, then the statistics of r = Phi (A_old - A_new) + b_old in closed form (see k_stats_b):
+//   sum r = dA^T s + n b,  sum |r|^2 = sum_d dA_d^T G dA_d + 2 b . (dA^T s) + n |b|^2,  sum phi^2 cm2 = d . cm2,
+//   sum f_var = sum over the region's pieces with coarser regions of (len bias_var_anc + cm2_anc . D_piece)
+// and the bias / noise update.  NB regions at once: two L2 round trips per batch (own data + ancestor table, then the
+// ancestors' moments), the NB updates run on NB lanes side by side.
+template <int NB>
+__device__ __forceinline__ void mid2_stats_upper(const ChainModel &m, const ChainLayer &ly, int l0, int stride, int lane, const double *cov) {
+    const int M = m.M, E = ly.E;
+    const bool on = lane < M;
+    const double c00 = cov[lane], c01 = cov[32 + lane], c11 = cov[64 + lane];
+    double2 yt[NB], ao[NB];
+    double zeta[NB], prec[NB], dsum[NB], si[NB], rcl[NB];
+    size_t ri[NB];
+    bool live[NB];
+    AncEntry en[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        const int l = l0 + q * stride;
+        live[q] = l < ly.R;
+        const bool act = on && live[q];
+        ri[q] = (size_t)(live[q] ? l : 0) * M + (on ? lane : 0);
+        yt[q] = act ? __ldcg(reinterpret_cast<const double2 *>(ly.ytil) + ri[q]) : make_double2(0.0, 0.0);
+        zeta[q] = act ? __ldcg(ly.zeta + ri[q]) : 0.0;
+        prec[q] = act ? __ldcg(ly.prec + ri[q]) : 1.0;
+        ao[q] = act ? __ldcg(reinterpret_cast<const double2 *>(ly.A) + ri[q]) : make_double2(0.0, 0.0);
+        dsum[q] = act ? __ldg(ly.d + ri[q]) : 0.0;
+        si[q] = act ? __ldg(ly.sumPhi + ri[q]) : 0.0;
+        // lanes 0..6: the region's constants; 8: noise mean (old); 9, 10: bias mean (old)
+        rcl[q] = 0.0;
+        if (live[q]) {
+            if (lane < 7) rcl[q] = __ldg(ly.rconst + (size_t)l * 8 + lane);
+            else if (lane == 8) rcl[q] = __ldcg(ly.noise_mean + l);
+            else if (lane == 9 || lane == 10) rcl[q] = __ldcg(ly.bias_mean + (size_t)l * 2 + (lane - 9));
+        }
+        en[q].len = -1.0;
+        en[q].cm2_off = en[q].bv_off = en[q].d_off = 0;
+        if (live[q] && lane < E) en[q] = ly.anc_tab[(size_t)l * E + lane];
+    }
+    double2 an[NB];
+    double cm2[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) s2_region(ly, ri[q], on && live[q], c00, c01, c11, yt[q], zeta[q], prec[q], ao[q], an[q], cm2[q]);
+    // ancestors: lane e holds piece e of the region (E <= 32 per pass)
+    double t[NB], lenbv[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        t[q] = 0.0;
+        lenbv[q] = en[q].len >= 0.0 ? en[q].len * __ldcg(m.ws + en[q].bv_off) : 0.0;
+    }
+    const int e_pass = E < 32 ? E : 32;
+#pragma unroll 4
+    for (int e = 0; e < e_pass; ++e) {
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const long long oc = __shfl_sync(kFull, en[q].cm2_off, e), od = __shfl_sync(kFull, en[q].d_off, e);
+            const bool ok = __shfl_sync(kFull, en[q].len, e) >= 0.0;
+            if (on && ok) t[q] = fma(__ldcg(m.ws + oc + lane), __ldg(m.ws + od + lane), t[q]);
+        }
+    }
+    for (int e0 = 32; e0 < E; e0 += 32) {     // more than 32 pieces per region (deep, non-nested index sets): further passes
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            AncEntry x;
+            x.len = -1.0;
+            x.cm2_off = x.bv_off = x.d_off = 0;
+            if (live[q] && e0 + lane < E) x = ly.anc_tab[(size_t)(l0 + q * stride) * E + e0 + lane];
+            lenbv[q] += x.len >= 0.0 ? x.len * __ldcg(m.ws + x.bv_off) : 0.0;
+            for (int e = 0; e < 32 && e0 + e < E; ++e) {
+                const long long oc = __shfl_sync(kFull, x.cm2_off, e), od = __shfl_sync(kFull, x.d_off, e);
+                const bool ok = __shfl_sync(kFull, x.len, e) >= 0.0;
+                if (on && ok) t[q] = fma(__ldcg(m.ws + oc + lane), __ldg(m.ws + od + lane), t[q]);
+            }
+        }
+    }
+    double mine_sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, mine_rc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, mine_noise = 1.0, mine_b0 = 0.0, mine_b1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        const double dA0 = ao[q].x - an[q].x, dA1 = ao[q].y - an[q].y;
+        const double sd0 = wsum(si[q] * dA0), sd1 = wsum(si[q] * dA1);
         double quad = 0.0;
         if (__any_sync(kFull, dA0 != 0.0 || dA1 != 0.0)) {
+            const double *G = ly.gram + (size_t)(live[q] ? l0 + q * stride : 0) * M * M;
             double t0 = 0.0, t1 = 0.0;
+#pragma unroll 6
             for (int k = 0; k < M; ++k) {
-                const double g = on ? G[(size_t)k * M + lane] : 0.0;
+                const double g = (on && live[q]) ? __ldg(G + (size_t)k * M + lane) : 0.0;
                 t0 = fma(g, __shfl_sync(kFull, dA0, k), t0);
                 t1 = fma(g, __shfl_sync(kFull, dA1, k), t1);
             }
             quad = wsum(dA0 * t0 + dA1 * t1);
         }
-        double t = 0.0, lenbv = 0.0;
-        for (int jp = 0; jp < j; ++jp) {
-            const ChainLayer &anc = m.layer[jp];
-            const int32_t *pp = ly.pc_ptr + (size_t)jp * (ly.R + 1) + l;
-            for (int pc = pp[0]; pc < pp[1]; ++pc) {
-                const int a = ly.pc_anc[pc];
-                if (on) t = fma(__ldcg(anc.cm2 + (size_t)a * M + lane), ly.ancD[(size_t)pc * M + lane], t);
-                lenbv += (double)(ly.pc_hi[pc] - ly.pc_lo[pc]) * __ldcg(anc.bias_var + a);
-            }
-        }
-        const double fv = wsum(t) + lenbv;
-        const double b0 = __ldcg(ly.bias_mean + (size_t)l * 2), b1 = __ldcg(ly.bias_mean + (size_t)l * 2 + 1);   // b_old
-        sums[0] = sd0 + n * b0;
-        sums[1] = sd1 + n * b1;
-        sums[2] = quad + 2.0 * (b0 * sd0 + b1 * sd1) + n * (b0 * b0 + b1 * b1);
-        sums[3] = fv;
-        sums[4] = dc;
-    }
-    if (lane == 0) {   // region-specific noise and bias: Posteriors.py:81-93, 132-148 (y_var NOT times n, :138); Stats.py:102-124
-        const double bp0 = ly.bias_prec0[l], bp = bp0 + n;
-        double t3 = 0.0, t4 = 0.0;
+        const double dc = wsum(dsum[q] * cm2[q]);
+        const double fv = wsum(t[q]) + wsum(lenbv[q]);
+        const double n = __shfl_sync(kFull, rcl[q], 0);
+        const double b0 = __shfl_sync(kFull, rcl[q], 9), b1 = __shfl_sync(kFull, rcl[q], 10), noise_old = __shfl_sync(kFull, rcl[q], 8);
+        double rcq[7];
 #pragma unroll
-        for (int d = 0; d < 2; ++d) {
-            const double m0 = ly.bias_mean0[(size_t)l * 2 + d];
-            const double mn = (1.0 / bp) * (m0 * bp0 + sums[d]);
-            ly.bias_prev[(size_t)l * 2 + d] = __ldcg(ly.bias_mean + (size_t)l * 2 + d);
-            ly.bias_mean[(size_t)l * 2 + d] = mn;
-            t3 += m0 * m0;
-            t4 += mn * mn;
-        }
-        t3 *= bp0;
-        t4 *= bp;
-        const double yvar = j > 0 ? 1.0 / __ldcg(ly.noise_mean + l) : 0.0;
-        const double shape = ly.noise_shape0[l] + 0.5 * 2.0 * n;
-        const double scale = ly.noise_scale0[l] + 0.5 * (t3 - t4 + sums[2] + sums[3] + sums[4] + yvar);
-        ly.yvar[l] = yvar;
-        ly.bias_prec[l] = bp;
-        ly.bias_var[l] = 1.0 / bp;
-        ly.noise_shape[l] = shape;
-        ly.noise_scale[l] = scale;
-        ly.noise_mean[l] = shape / scale;
-        ly.noise_log_mean[l] = digamma(shape) - log(scale);
+        for (int k = 0; k < 7; ++k) rcq[k] = __shfl_sync(kFull, rcl[q], k);
+        if (lane == q) {
+            mine_sums[0] = sd0 + n * b0;
+            mine_sums[1] = sd1 + n * b1;
+            mine_sums[2] = quad + 2.0 * (b0 * sd0 + b1 * sd1) + n * (b0 * b0 + b1 * b1);
+            mine_sums[3] = fv;
+            mine_sums[4] = dc;
 #pragma unroll
-        for (int d = 0; d < 5; ++d) ly.sumsB[(size_t)l * 5 + d] = sums[d];
+            for (int k = 0; k < 7; ++k) mine_rc[k] = rcq[k];
+            mine_noise = noise_old;
+            mine_b0 = b0;
+            mine_b1 = b1;
+        }
     }
+    if (lane < NB && l0 + lane * stride < ly.R) bias_noise_update(ly, l0 + lane * stride, true, mine_sums, mine_rc, mine_noise, mine_b0, mine_b1);
 }
 
 // ---- the solver (one warp) ---------------------------------------------------------------------------------------
@@ -277,23 +396,25 @@ __device__ __forceinline__ double omega_eval(const double (&K)[MP], double (&P)[
 template <int MP>
 __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm, int layer, int lane) {
     static_assert(MP <= 32 && (MP & 1) == 0, "one lane per row, columns in pairs");
-    const int M = m.M;
+    const int M = m.M, j = layer;
+    if (lane == 0) PROF(6);
     const bool row = lane < MP, real = lane < M;
     double *T = sm.T;
     double K[MP], P[MP], Q[MP];
 #pragma unroll
     for (int k = 0; k < MP; ++k) K[k] = (real && k < M) ? sm.Kt[k * LD + lane] : ((row && !real && k == lane) ? 1.0 : 0.0);
     const double cshift = real ? sm.colmax[lane] : 0.0;
-    const bool warm = m.omegaWarm[layer] > 0.5;
+    const bool warm = sm.warm[layer] > 0.5;
     double v = 1.0;
     if (real) {
-        const double eta = m.omegaEta[layer * 64 + lane] + cshift;
+        const double eta = sm.eta[layer][lane] + cshift;
         v = (warm && isfinite(eta)) ? exp(fmax(-600.0, fmin(600.0, eta))) : 1.0;
     }
     int iters = 0;
     double err_prev = INFINITY, c = 1.0;
     int last = kOmegaNone;
     const double inv_m = 1.0 / (double)M;
+    if (lane == 0) PROF(7);
     for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
         ++iters;
         const double err = omega_eval<MP>(K, P, Q, v, c, T, row, lane);
@@ -381,6 +502,7 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
         if (real) v = fmax(1e-280, fmin(1e280, v * exp(fmax(-30.0, fmin(30.0, x)))));
         __syncwarp();
     }
+    if (lane == 0) PROF(8);
     // last resort: plain Sinkhorn sweeps (see omega_solve_serial); on model tables the loop exits at its first test
     for (int it = 0; it < kOmegaFallbackSweeps; ++it) {
         const double err = omega_eval<MP>(K, P, Q, v, c, T, row, lane);
@@ -397,23 +519,29 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
     if (lane == 0) {
         m.omegaIters[layer] = (double)iters;
         m.omegaWarm[layer] = 1.0;
+        PROF(9);
     }
 }
 
 // ---- the shared step of a layer on CTA 0 (256 threads) ------------------------------------------------------------
 __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, cg::cluster_group &cluster, int j, int tid, unsigned C) {
-    const int M = m.M;
+    const int M = m.M, lane = tid & 31, warp = tid >> 5;
     const ChainLayer &ly = m.layer[j];
-    // region sums of the cluster, in rank order
-    for (int v = tid; v < 7 * 32; v += kChainThreads) {
-        double s = 0.0;
-        for (unsigned r = 0; r < C; ++r) s += cluster.map_shared_rank(sm.ctaPart, r)[v];
-        sm.data[v] = s;
+    if (tid == 0) PROF(0);
+    // region sums of the cluster, in rank order (all DSMEM loads of a thread in flight at once)
+    if (tid < 7 * 32) {
+        double pv[kChainMaxCluster];
+#pragma unroll
+        for (unsigned r = 0; r < kChainMaxCluster; ++r) pv[r] = r < C ? cluster.map_shared_rank(sm.ctaPart, r)[tid] : 0.0;
+        double s = pv[0];
+#pragma unroll
+        for (unsigned r = 1; r < kChainMaxCluster; ++r) s += pv[r];
+        sm.data[tid] = s;
     }
     // snapshot of the previous posterior: the pristine prior for layer 0, the posterior of layer j - 1 otherwise
     // (MRGP.py:575 / :581); its k-only terms of the table were prepared beside the previous solve
-    if (tid < M) {
-        const int t = tid;
+    if (tid >= 224 && tid - 224 < M) {
+        const int t = tid - 224;
         if (j == 0) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) sm.primeB[t * 4 + q] = m.priorB[t * 4 + q];
@@ -431,18 +559,18 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
         }
     }
     __syncthreads();
-    if (tid < M) {
-        const int i = tid;
+    if (tid == 0) PROF(1);
+    if (warp == 0 && lane < M) {
+        const int i = lane;
         // P2: B_i = sum_k omega_ik B'_k + sum_l 0.5 noise zeta y y^T (Posteriors.py:502-518); PD guard, eigen-solve,
         // saddle point (P2a-c), axis covariance (S1)
-        double b00 = 0.0, b01 = 0.0, b11 = 0.0, sh = 0.0, sc = 0.0;
+        double b00 = 0.0, b01 = 0.0, b11 = 0.0;
+#pragma unroll 6
         for (int k = 0; k < M; ++k) {
             const double w = sm.omT[k * LD + i];
             b00 = fma(w, sm.primeB[k * 4 + 0], b00);
             b01 = fma(w, sm.primeB[k * 4 + 1], b01);
             b11 = fma(w, sm.primeB[k * 4 + 3], b11);
-            sh = fma(w, sm.primeShape[k], sh);
-            sc = fma(w, sm.primeScale[k], sc);
         }
         Bingham2 bg;
         bingham2(b00 + sm.data[0 * 32 + i], b01 + sm.data[1 * 32 + i], b11 + sm.data[2 * 32 + i], bg);
@@ -463,12 +591,31 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
         sm.rho[i * 2 + 1] = bg.rho[1];
         sm.logC[i] = bg.logc;
         atomicAdd(&sm.nchol, bg.n_chol);
-        // P3 / S3 (Posteriors.py:533-541, Stats.py:385-388): sum_l m2/S = sum_l 1/(prec S) + tr((sum_l zeta^2 y y^T / S) C_i)
-        const double beta2 = sm.data[3 * 32 + i] +
-                             (sm.data[4 * 32 + i] * bg.cov[0] + 2.0 * sm.data[5 * 32 + i] * bg.cov[1] + sm.data[6 * 32 + i] * bg.cov[2]);
+    } else if (warp == 1 && lane < M) {
+        // P3 beside it (Posteriors.py:533-541): the mixed prior shape / scale and psi(shape) do not depend on the axis update
+        const int i = lane;
+        double sh = 0.0, sc = 0.0;
+#pragma unroll 6
+        for (int k = 0; k < M; ++k) {
+            const double w = sm.omT[k * LD + i];
+            sh = fma(w, sm.primeShape[k], sh);
+            sc = fma(w, sm.primeScale[k], sc);
+        }
         const double shape = sh + 0.5 * (double)ly.R;
-        const double scale = sc + 0.5 * beta2;
-        const double mean = shape / scale, lmean = digamma(shape) - log(scale);
+        sm.sh[i] = shape;
+        sm.sc[i] = sc;
+        sm.dg[i] = digamma(shape);
+    }
+    __syncthreads();
+    if (tid == 0) PROF(2);
+    if (tid < M) {
+        // S3 (Stats.py:385-388): sum_l m2/S = sum_l 1/(prec S) + tr((sum_l zeta^2 y y^T / S) C_i)
+        const int i = tid;
+        const double beta2 = sm.data[3 * 32 + i] +
+                             (sm.data[4 * 32 + i] * sm.cov[i * 4 + 0] + 2.0 * sm.data[5 * 32 + i] * sm.cov[i * 4 + 1] + sm.data[6 * 32 + i] * sm.cov[i * 4 + 3]);
+        const double shape = sm.sh[i];
+        const double scale = sm.sc[i] + 0.5 * beta2;
+        const double mean = shape / scale, lmean = sm.dg[i] - log(scale);
         sm.shape[i] = shape;
         sm.scale[i] = scale;
         sm.mean[i] = mean;
@@ -476,34 +623,32 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
         sm.pub[96 + i] = mean;
     }
     __syncthreads();
-    // S4, the table (Stats.py:405-412; a true matrix product inside the trace)
+    if (tid == 0) PROF(3);
+    // S4, the table (Stats.py:405-412; a true matrix product inside the trace): a warp per row, the row maxima on the way
     const bool last_layer = j == m.J - 1;
-    for (int t = tid; t < M * M; t += kChainThreads) {
-        const int i = t / M, k = t - i * M;
-        const double *Cc = sm.cov + i * 4, *Bp = sm.primeB + k * 4;
-        const double tr = Cc[0] * Bp[0] + Cc[1] * Bp[2] + Cc[2] * Bp[1] + Cc[3] * Bp[3];
-        const double lw = tr + sm.sk[k] + (sm.primeShape[k] - 1.0) * sm.lmean[i] - sm.primeScale[k] * sm.mean[i];
-        sm.lw[i * LW + k] = lw;
-        if (last_layer) m.logOmegaHat[t] = lw;
+    for (int i = warp; i < M; i += kChainThreads / 32) {
+        double lw = -INFINITY;
+        if (lane < M) {
+            const int k = lane;
+            const double *Cc = sm.cov + i * 4, *Bp = sm.primeB + k * 4;
+            const double tr = Cc[0] * Bp[0] + Cc[1] * Bp[2] + Cc[2] * Bp[1] + Cc[3] * Bp[3];
+            lw = tr + sm.sk[k] + (sm.primeShape[k] - 1.0) * sm.lmean[i] - sm.primeScale[k] * sm.mean[i];
+            sm.lw[i * LW + k] = lw;
+            if (last_layer) m.logOmegaHat[i * M + k] = lw;
+        }
+        const double mx = wmax(lw);
+        if (lane == 0) sm.rowmax[i] = mx;
     }
     __syncthreads();
-    // shifts (rows, then columns of the row-shifted table) and exponentials: every row and column of K holds a 1
-    if (tid < M) {
-        double mx = -INFINITY;
-        for (int k = 0; k < M; ++k) mx = fmax(mx, sm.lw[tid * LW + k]);
-        sm.rowmax[tid] = mx;
+    if (tid == 0) PROF(4);
+    // shifts and exponentials, a warp per column: every row and column of K holds a 1 (no overflow, no empty line)
+    for (int k = warp; k < M; k += kChainThreads / 32) {
+        const double v = lane < M ? sm.lw[lane * LW + k] - sm.rowmax[lane] : -INFINITY;
+        const double mx = wmax(v);
+        if (lane < M) sm.Kt[k * LD + lane] = exp(v - mx);
+        if (lane == 0) sm.colmax[k] = mx;
     }
-    __syncthreads();
-    if (tid < M) {
-        double mx = -INFINITY;
-        for (int i = 0; i < M; ++i) mx = fmax(mx, sm.lw[i * LW + tid] - sm.rowmax[i]);
-        sm.colmax[tid] = mx;
-    }
-    __syncthreads();
-    for (int t = tid; t < M * M; t += kChainThreads) {
-        const int k = t / M, i = t - k * M;
-        sm.Kt[k * LD + i] = exp((sm.lw[i * LW + k] - sm.rowmax[i]) - sm.colmax[k]);
-    }
+    if (tid == 0) PROF(5);
 }
 
 template <int MP>
@@ -529,6 +674,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
             sm.omT[k * LD + i] = m.omega[t];
         }
         if (tid == 0) sm.nchol = 0;
+        for (int t = tid; t < J * 32; t += kChainThreads) sm.eta[t >> 5][t & 31] = m.omegaEta[(t >> 5) * 64 + (t & 31)];
+        if (tid < J) sm.warm[tid] = m.omegaWarm[tid];
     }
     if (tid < 4 * 32) {   // lanes past M must hold finite values (they are multiplied by zeros)
         sm.pub[tid] = 0.0;
@@ -539,7 +686,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
 #pragma unroll
     for (int q = 0; q < 7; ++q) acc[q] = 0.0;
     if (!solver)
-        for (int l = ww; l < m.layer[0].R; l += n_workers) mid1_region(m, m.layer[0], 0, l, lane, sm.loc + 96, acc);
+        for (int l = ww; l < m.layer[0].R; l += n_workers) mid1_layer0(m, m.layer[0], l, lane, sm.loc + 96, acc);
 #pragma unroll
     for (int q = 0; q < 7; ++q) sm.part[warp][q][lane] = acc[q];
     __syncthreads();
@@ -561,19 +708,30 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
             if (ts && lane == 0) atomicMax(&ts[(j * 4 + 3) * 2 + 1], gtimer());
         } else {
             if (ts && rank == 0 && tid == 32) atomicMin(&ts[(j * 4 + 1) * 2], gtimer());
+            if (rank == 0 && tid == 32) PROF(10);
             const double *pub = cluster.map_shared_rank(sm.pub, 0);
             const int wt = rank == 0 ? tid - 32 : tid;
             for (int v = wt; v < 4 * 32; v += cta_worker_threads) sm.loc[v] = pub[v];
             // k-only terms of the NEXT layer's table from the posterior just written (one lgamma per basis function)
             if (rank == 0 && warp == 1 && lane < M) sm.skNext[lane] = -sm.logC[lane] + sm.shape[lane] * log(sm.scale[lane]) - lgamma(sm.shape[lane]);
             worker_bar(cta_worker_threads);
+            if (rank == 0 && tid == 32) PROF(11);
 #pragma unroll
             for (int q = 0; q < 7; ++q) acc[q] = 0.0;
-            if (j + 1 < J)
-                for (int l = ww; l < m.layer[j + 1].R; l += n_workers) mid1_region(m, m.layer[j + 1], j + 1, l, lane, sm.loc + 96, acc);
+            if (j + 1 < J) {
+                const ChainLayer &nx = m.layer[j + 1];
+                for (int l = ww; l < nx.R; l += kBatch * n_workers) mid1_upper<kBatch>(m, nx, l, n_workers, lane, sm.loc + 96, acc);
+            }
 #pragma unroll
             for (int q = 0; q < 7; ++q) sm.part[warp][q][lane] = acc[q];
-            for (int l = ww; l < m.layer[j].R; l += n_workers) mid2_stats_region(m, m.layer[j], j, l, lane, sm.loc);
+            if (rank == 0 && tid == 32) PROF(12);
+            if (j == 0) {
+                for (int l = ww; l < m.layer[0].R; l += n_workers) mid2_stats_layer0(m, m.layer[0], l, lane, sm.loc);
+            } else {
+                const ChainLayer &cu = m.layer[j];
+                for (int l = ww; l < cu.R; l += kBatch * n_workers) mid2_stats_upper<kBatch>(m, cu, l, n_workers, lane, sm.loc);
+            }
+            if (rank == 0 && tid == 32) PROF(13);
             worker_bar(cta_worker_threads);
             for (int v = wt; v < 7 * 32; v += cta_worker_threads) {
                 double s = 0.0;
@@ -581,6 +739,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
                 sm.ctaPart[v] = s;
             }
             if (ts && rank == 0 && tid == 32) atomicMax(&ts[(j * 4 + 1) * 2 + 1], gtimer());
+            if (rank == 0 && tid == 32) PROF(14);
         }
     }
     cluster.sync();

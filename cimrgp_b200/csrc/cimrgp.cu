@@ -36,6 +36,7 @@ struct LayerPlan {
     std::vector<int32_t> region_run;  // R + 1
     std::vector<int32_t> ident_run;   // 0 .. R (dense exchange buffer: one "run" per region)
     int32_t R = 0, n_runs = 0;
+    int32_t E = 0;                    // largest number of pieces (over all coarser layers) of a region
 };
 
 struct LayerDev {
@@ -68,6 +69,8 @@ struct LayerDev {
     int32_t *pc_ptr = nullptr, *pc_jp = nullptr, *pc_anc = nullptr;
     int64_t *pc_lo = nullptr, *pc_hi = nullptr;
     bool inv_built = false;
+    double *rconst = nullptr;                // (R, 8) constants of the regions for the fused sweep (k_init_layer)
+    AncEntry *anc_tab = nullptr;             // (R, E) pieces of every region, flattened (fused sweep)
     double *yc = nullptr, *ysum = nullptr;   // layer 0 (ci): Phi^T y (R, M, dy) and sum y, sum |y|^2 (R, 4) of the fused sweep
 };
 
@@ -126,7 +129,8 @@ struct mrgp_handle {
     const ChainModel **chain_ptr_dev = nullptr;
     ChainModel chain_host{};
     unsigned int *chain_status = nullptr;
-    double *chain_guard = nullptr;
+    double *chain_guard = nullptr, *chain_prof = nullptr;
+    bool chain_prof_on = false;      // MRGP_CHAIN_PROF=1: SM-clock stamps of the fused sweep (field 54)
     bool chain_uploaded = false;     // the device descriptor matches the current pointers (reset by drop_graph)
     uint64_t generation = 0;         // bumped whenever a captured sweep / descriptor becomes stale (groups re-capture)
     uint64_t stream_ops = 0;         // asynchronous work queued on the handle's stream from outside a sweep (groups order after it)
@@ -318,7 +322,11 @@ size_t carve(mrgp_handle *h, char *base) {
         d.S = c.take<double>(RM);
         d.d = c.take<double>(RM);
         d.absx = c.take<double>(R);
-        if (!fi) d.sumPhi = c.take<double>(RM);
+        if (!fi) {
+            d.sumPhi = c.take<double>(RM);
+            d.rconst = c.take<double>(R * 8);
+            if (j > 0) d.anc_tab = c.take<AncEntry>(R * (size_t)std::max(lp.E, 1));
+        }
         if (!fi && j == 0) {
             d.yc = c.take<double>(RM * DY);
             d.ysum = c.take<double>(R * 4);
@@ -408,6 +416,7 @@ size_t carve(mrgp_handle *h, char *base) {
         h->chain_ptr_dev = c.take<const ChainModel *>(1);
         h->chain_status = c.take<unsigned int>(4);
         h->chain_guard = c.take<double>(2);
+        h->chain_prof = c.take<double>((size_t)kMaxLayers * 16);
     }
     return (c.off + 255) & ~(size_t)255;
 }
@@ -554,6 +563,7 @@ RegionArgs region_args(mrgp_handle *h, int j) {
         a.region_run = d.ident_run;
         a.part = h->xchg;
     }
+    a.rconst = d.rconst;
     a.use_prior = d.use_prior;
     a.nu = d.nu;
     a.ell = d.ell;
@@ -1127,6 +1137,7 @@ int upload_chain_model(mrgp_handle *h) {
     m.J = h->cfg.n_layers;
     m.M = h->cfg.n_basis;
     m.DY = h->cfg.dy;
+    m.ws = reinterpret_cast<double *>(h->ws);
     m.x = h->x - h->lo;
     m.y = h->y - h->lo * h->cfg.dy;
     m.axB = s.axB; m.axKappa = s.axKappa; m.axRho = s.axRho; m.axLogC = s.axLogC; m.axCov = s.axCov;
@@ -1138,12 +1149,16 @@ int upload_chain_model(mrgp_handle *h) {
     m.status = h->chain_status;
     m.guard = h->chain_guard;
     m.ts = h->timeline ? h->ts : nullptr;
+    m.prof = h->chain_prof_on ? h->chain_prof : nullptr;
     for (int j = 0; j < m.J; ++j) {
         const LayerDev &d = h->dev[j];
         ChainLayer &l = m.layer[j];
         l.R = h->plan[j].R;
         l.P = (int32_t)h->plan[j].pc_jp.size();
         l.offsets = d.offsets;
+        l.E = std::max(h->plan[j].E, 1);
+        l.anc_tab = d.anc_tab;
+        l.rconst = d.rconst;
         l.inv2L = d.inv2L; l.rsqrtL = d.rsqrtL;
         l.S = d.S; l.d = d.d; l.sumPhi = d.sumPhi; l.gram = d.gram; l.ancD = d.ancD;
         l.pc_ptr = d.pc_ptr; l.pc_anc = d.pc_anc; l.pc_lo = d.pc_lo; l.pc_hi = d.pc_hi;
@@ -1269,6 +1284,7 @@ FieldRef field_ref(mrgp_handle *h, int layer, int field) {
         if (layer != -1) return f;
         SharedDev &s = h->sh;
         switch (field) {
+            case 54: f = {h->chain_prof, (int64_t)h->cfg.n_layers * 16}; break;   // MRGP_CHAIN_PROF=1: clock stamps of the fused sweep
             case 52: f = {s.omegaK + 64 * 64 + 32, 3}; break;
             case 53: f = {s.omegaK + 64 * 64 + 40, 5}; break;   // MRGP_OMEGA_PROF builds: cycles of the k_ard phases   // MRGP_OMEGA_PROF builds: cycles of the Newton stages
             case MRGP_F_AXIS_B: f = {s.axB, (int64_t)M * DY * DY}; break;
@@ -1391,6 +1407,7 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     if (const char *e = getenv("MRGP_OMEGA_BLOCK")) h->omega_warp = !(e[0] == '1');
     if (const char *e = getenv("MRGP_STREAM_ALL")) h->inferred_shortcut = !(e[0] == '1');
     if (const char *e = getenv("MRGP_FUSED")) h->fused = !(e[0] == '0');
+    if (const char *e = getenv("MRGP_CHAIN_PROF")) h->chain_prof_on = e[0] == '1';
     if (const char *e = getenv("MRGP_CHAIN_CLUSTER")) h->chain_cluster = atoi(e);
     h->sharded = cfg->sample_end > cfg->sample_begin;   // an explicit range selects the exchange-buffer path
     h->lo = h->sharded ? cfg->sample_begin : 0;
@@ -1453,6 +1470,12 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
                     }
                 }
                 lp.pc_ptr[(size_t)jp * (lp.R + 1) + lp.R] = (int32_t)lp.pc_jp.size();
+            }
+            lp.E = 0;
+            for (int c = 0; c < lp.R; ++c) {
+                int cnt = 0;
+                for (int jp = 0; jp < j; ++jp) cnt += lp.pc_ptr[(size_t)jp * (lp.R + 1) + c + 1] - lp.pc_ptr[(size_t)jp * (lp.R + 1) + c];
+                lp.E = std::max(lp.E, cnt);
             }
         }
     h->ws_bytes = carve(h, nullptr);
@@ -1537,6 +1560,28 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
             CK(cudaMemcpyAsync(d.pc_lo, lp.pc_lo.data(), P * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(d.pc_hi, lp.pc_hi.data(), P * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
         }
+    }
+    // flattened piece table of the fused sweep: for every region its pieces over all coarser layers, coarse to fine
+    for (int j = 1; j < h->cfg.n_layers && h->cfg.mode == MRGP_MODE_CI; ++j) {
+        const LayerPlan &lp = h->plan[j];
+        LayerDev &d = h->dev[j];
+        const int E = std::max(lp.E, 1), M = h->cfg.n_basis;
+        std::vector<AncEntry> tab((size_t)lp.R * E);
+        const double *base = reinterpret_cast<const double *>(h->ws);
+        for (int c = 0; c < lp.R; ++c) {
+            int e = 0;
+            for (int jp = 0; jp < j; ++jp)
+                for (int pc = lp.pc_ptr[(size_t)jp * (lp.R + 1) + c]; pc < lp.pc_ptr[(size_t)jp * (lp.R + 1) + c + 1]; ++pc, ++e) {
+                    AncEntry &a = tab[(size_t)c * E + e];
+                    a.cm2_off = (h->dev[jp].cm2 - base) + (long long)lp.pc_anc[pc] * M;
+                    a.bv_off = (h->dev[jp].bias_var - base) + lp.pc_anc[pc];
+                    a.d_off = (d.ancD - base) + (long long)pc * M;
+                    a.len = (double)(lp.pc_hi[pc] - lp.pc_lo[pc]);
+                }
+            for (; e < E; ++e) tab[(size_t)c * E + e] = AncEntry{0, 0, 0, -1.0};
+        }
+        CK(cudaMemcpyAsync(d.anc_tab, tab.data(), tab.size() * sizeof(AncEntry), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));   // `tab` is a local
     }
     CK(cudaMemsetAsync(h->chol_count, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->done_counter, 0, sizeof(unsigned int), h->stream));

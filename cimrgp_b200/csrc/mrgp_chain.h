@@ -16,8 +16,19 @@ constexpr int kChainMaxLayers = 24;
 constexpr int kChainThreads = 256;
 constexpr int kChainMaxCluster = 8;
 
+// One piece of a region with a region of a coarser layer, for sum f_var of the closed-form statistics: offsets in
+// doubles from the workspace base of the coarser region's cm2 row and bias variance and of the piece's D row; its
+// number of samples (len < 0: unused slot of the fixed-stride table).
+struct AncEntry {
+    long long cm2_off, bv_off, d_off;
+    double len;
+};
+
 struct ChainLayer {
     int32_t R, P;                  // regions; pieces region x coarser region (layers > 0)
+    int32_t E, pad;                // slots per region of anc_tab (largest number of pieces of a region)
+    const AncEntry *anc_tab;       // (R, E)
+    const double *rconst;          // (R, 8): n, bias_prec0, bias_mean0 (2), noise_shape0, noise_scale0, psi(noise shape), -
     const int64_t *offsets;        // (R + 1)
     // static
     const double *inv2L, *rsqrtL;  // (R) 1 / (2 L), L^-1/2 of the basis interval
@@ -36,6 +47,7 @@ struct ChainLayer {
 
 struct ChainModel {
     int32_t J, M, DY, pad;
+    double *ws;                    // workspace base (AncEntry offsets are relative to it)
     const double *x, *y;           // (N), (N, DY) normalised inputs and observations, indexed by the global sample number
     // shared posterior / stats (Posteriors.py:482-541, Stats.py:354-420)
     double *axB, *axKappa, *axRho, *axLogC, *axCov, *ardShape, *ardScale, *ardMean, *ardLogMean;
@@ -45,6 +57,7 @@ struct ChainModel {
     unsigned int *status;          // [0]: layer-0 closed-form guard tripped (sum |r|^2 / sum |y|^2 below kChainGuard)
     double *guard;                 // [0]: last ratio sum |r|^2 / sum |y|^2 of layer 0
     unsigned long long *ts;        // timeline stamps or null
+    double *prof;                  // (J, 16) SM-clock stamps inside CTA 0 (MRGP_CHAIN_PROF=1) or null
     ChainLayer layer[kChainMaxLayers];
 };
 

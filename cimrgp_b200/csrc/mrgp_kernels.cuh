@@ -863,6 +863,7 @@ struct RegionArgs {
     double *primeB, *primeLogC, *primeShape, *primeScale;   // snapshot read by ARD / omega (ci)
     const double *priorB, *priorLogC, *priorShape, *priorScale;
     double *bcontrib;          // (R, M, 3) ci: 0.5 noise zeta ytil ytil^T
+    double *rconst;            // (R, 8) ci: constants of the regions for the fused sweep, or null
     unsigned long long *chol_count;
     unsigned long long *ts;
     double fi_shape0_mix, fi_scale0_mix;   // sum_k (1/M) shape0_k, sum_k (1/M) scale0_k (Posteriors.py:293-295)
@@ -2853,6 +2854,18 @@ __global__ void k_init_layer(RegionArgs a, double noise_var0, double ard_influen
             a.bias_mean[(size_t)r * DY + d] = 0.0;
         }
         for (int d = 0; d < DY + 3; ++d) a.sumsB[(size_t)r * (DY + 3) + d] = 0.0;
+        if (a.rconst) {   // what the fused sweep needs of the region besides its state (csrc/chain.cu, bias_noise_update)
+            const double n = (double)(a.offsets[r + 1] - a.offsets[r]);
+            double *rc = a.rconst + (size_t)r * 8;
+            rc[0] = n;
+            rc[1] = kEps;                                   // bias_prec0
+            rc[2] = 0.0;                                    // bias_mean0
+            rc[3] = 0.0;
+            rc[4] = kEps;                                   // noise_shape0
+            rc[5] = (kEps + 1.0) * noise_var0;              // noise_scale0
+            rc[6] = digamma(kEps + 0.5 * (double)DY * n);   // psi(noise shape): the shape is c0 + dy n / 2 in every sweep
+            rc[7] = 0.0;
+        }
     }
     if (t < a.R * M) {
         a.prec[t] = 1.0 / a.S[t];
