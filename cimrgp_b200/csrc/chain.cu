@@ -18,6 +18,7 @@
 
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <cstddef>
 
 #include "mrgp_math.cuh"
 
@@ -47,9 +48,20 @@ __device__ __forceinline__ unsigned long long gtimer() {
     do {                                                                     \
         if (m.prof) m.prof[j * 16 + (k)] = (double)clock64();                \
     } while (0)
+// N sums over the warp in lock-step: the butterflies of the N values overlap instead of running one after the other
+template <int N>
+__device__ __forceinline__ void wsum_n(double (&v)[N]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] += __shfl_xor_sync(kFull, v[k], o);
+    }
+}
+// split cluster barrier: arrive publishes this thread's writes, wait makes the others' visible
+__device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void worker_bar(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 
-constexpr int kBatch = 4; // regions a worker warp handles at once (their L2 round trips overlap)
 constexpr int LD = 34;    // row stride of the transposed tables: conflict-free columns, 16-byte aligned rows
 constexpr int LW = 33;    // row stride of the log omega_hat table
 
@@ -64,12 +76,16 @@ struct ChainSmem {
     double ctaPart[7 * 32];   // per-CTA sums, read by CTA 0 over DSMEM
     double data[7 * 32];      // cluster sums (CTA 0)
     double pub[4 * 32];       // CTA 0: axis covariance (c00, c01, c11) and ARD mean of the layer, read by every CTA
-    double loc[4 * 32];       // local copy of pub
+    double loc[2][4 * 32];    // local copies of pub, by layer parity (the background step of layer j reads its copy while
+                              // the copy of layer j + 1 is being written)
     double rowmax[32], colmax[32];
     double dg[32], sh[32], sc[32];              // shared step: digamma(shape), mixed prior shape / scale
     double eta[kChainMaxLayers][32];            // warm start of the solver: log column scalings of the previous sweep
     double warm[kChainMaxLayers];
     int nchol;
+    // the model's descriptor: every pointer of the sweep comes from here (a descriptor left in global memory costs an L2
+    // round trip before each data access: the cluster barriers invalidate L1)
+    alignas(16) unsigned char model[sizeof(ChainModel)];
 };
 
 // ---- worker steps (one warp per region, lane = basis function) --------------------------------------------------
@@ -79,8 +95,10 @@ struct ChainSmem {
 // covariance (ARD, Posteriors.py:533-541; see k_mid1).
 __device__ __forceinline__ void p1_finish(const ChainLayer &ly, size_t ri, double y0, double y1, double dsum, double S, double noise,
                                           double ard, double (&acc)[7]) {
-    const double prec = ard / S + noise * dsum;      // Posteriors.py:40-42
-    const double zeta = noise / prec;
+    const double is = 1.0 / S;
+    const double prec = fma(ard, is, noise * dsum);      // Posteriors.py:40-42: ard / S + noise sum phi^2
+    const double ip = 1.0 / prec;
+    const double zeta = noise * ip;
     *reinterpret_cast<double2 *>(ly.ytil + ri * 2) = make_double2(y0, y1);
     ly.prec[ri] = prec;
     ly.zeta[ri] = zeta;
@@ -88,8 +106,8 @@ __device__ __forceinline__ void p1_finish(const ChainLayer &ly, size_t ri, doubl
     acc[0] += w * (y0 * y0);
     acc[1] += w * (y0 * y1);
     acc[2] += w * (y1 * y1);
-    const double is = 1.0 / S, z2s = zeta * zeta * is;
-    acc[3] += is / prec;
+    const double z2s = zeta * zeta * is;
+    acc[3] += is * ip;
     acc[4] += z2s * (y0 * y0);
     acc[5] += z2s * (y0 * y1);
     acc[6] += z2s * (y1 * y1);
@@ -176,8 +194,9 @@ __device__ __forceinline__ void s2_region(const ChainLayer &ly, size_t ri, bool 
     an = make_double2(zeta * cy0, zeta * cy1);
     const double z2 = zeta * zeta;
     const double ccy0 = c00 * cy0 + c01 * cy1, ccy1 = c01 * cy0 + c11 * cy1;
-    const double m2 = 1.0 / prec + z2 * (yt.x * cy0 + yt.y * cy1);
-    cm2 = 1.0 / prec + z2 * (yt.x * (cy0 - ccy0) + yt.y * (cy1 - ccy1));
+    const double ip = 1.0 / prec;
+    const double m2 = ip + z2 * (yt.x * cy0 + yt.y * cy1);
+    cm2 = ip + z2 * (yt.x * (cy0 - ccy0) + yt.y * (cy1 - ccy1));
     if (on) {
         *reinterpret_cast<double2 *>(ly.A_prev + ri * 2) = ao;
         *reinterpret_cast<double2 *>(ly.A + ri * 2) = an;
@@ -236,15 +255,16 @@ __device__ __forceinline__ void mid2_stats_layer0(const ChainModel &m, const Cha
 // Layers above the first: S2, then the statistics of r = Phi (A_old - A_new) + b_old in closed form (see k_stats_b):
 //   sum r = dA^T s + n b,  sum |r|^2 = sum_d dA_d^T G dA_d + 2 b . (dA^T s) + n |b|^2,  sum phi^2 cm2 = d . cm2,
 //   sum f_var = sum over the region's pieces with coarser regions of (len bias_var_anc + cm2_anc . D_piece)
-// and the bias / noise update.  NB regions at once: two L2 round trips per batch (own data + ancestor table, then the
-// ancestors' moments), the NB updates run on NB lanes side by side.
+// and the bias / noise update.  NB regions at once: two L2 round trips per batch (own data + piece table, then the
+// coarser regions' moments), all warp sums of the batch in one lock-step butterfly, the NB updates on NB lanes side
+// by side (lane q loads the constants of region q itself).
 template <int NB>
 __device__ __forceinline__ void mid2_stats_upper(const ChainModel &m, const ChainLayer &ly, int l0, int stride, int lane, const double *cov) {
     const int M = m.M, E = ly.E;
     const bool on = lane < M;
     const double c00 = cov[lane], c01 = cov[32 + lane], c11 = cov[64 + lane];
     double2 yt[NB], ao[NB];
-    double zeta[NB], prec[NB], dsum[NB], si[NB], rcl[NB];
+    double zeta[NB], prec[NB], dsum[NB], si[NB];
     size_t ri[NB];
     bool live[NB];
     AncEntry en[NB];
@@ -260,60 +280,77 @@ __device__ __forceinline__ void mid2_stats_upper(const ChainModel &m, const Chai
         ao[q] = act ? __ldcg(reinterpret_cast<const double2 *>(ly.A) + ri[q]) : make_double2(0.0, 0.0);
         dsum[q] = act ? __ldg(ly.d + ri[q]) : 0.0;
         si[q] = act ? __ldg(ly.sumPhi + ri[q]) : 0.0;
-        // lanes 0..6: the region's constants; 8: noise mean (old); 9, 10: bias mean (old)
-        rcl[q] = 0.0;
-        if (live[q]) {
-            if (lane < 7) rcl[q] = __ldg(ly.rconst + (size_t)l * 8 + lane);
-            else if (lane == 8) rcl[q] = __ldcg(ly.noise_mean + l);
-            else if (lane == 9 || lane == 10) rcl[q] = __ldcg(ly.bias_mean + (size_t)l * 2 + (lane - 9));
-        }
-        en[q].len = -1.0;
+        en[q].len = -1;
         en[q].cm2_off = en[q].bv_off = en[q].d_off = 0;
         if (live[q] && lane < E) en[q] = ly.anc_tab[(size_t)l * E + lane];
+    }
+    // lane q < NB: constants and old noise / bias of region q for its update
+    const int lq = l0 + lane * stride;
+    const bool tail = lane < NB && lq < ly.R;
+    double rc[7] = {1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0}, noise_old = 1.0, b0 = 0.0, b1 = 0.0;
+    if (tail) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) rc[k] = __ldg(ly.rconst + (size_t)lq * 8 + k);
+        noise_old = __ldcg(ly.noise_mean + lq);
+        const double2 b = __ldcg(reinterpret_cast<const double2 *>(ly.bias_mean) + lq);
+        b0 = b.x;
+        b1 = b.y;
     }
     double2 an[NB];
     double cm2[NB];
 #pragma unroll
     for (int q = 0; q < NB; ++q) s2_region(ly, ri[q], on && live[q], c00, c01, c11, yt[q], zeta[q], prec[q], ao[q], an[q], cm2[q]);
-    // ancestors: lane e holds piece e of the region (E <= 32 per pass)
-    double t[NB], lenbv[NB];
+    // pieces: lane e holds piece e of the region (E <= 32 per pass); len * bias_var lane-parallel, cm2 . D by all lanes
+    double t[NB];
 #pragma unroll
-    for (int q = 0; q < NB; ++q) {
-        t[q] = 0.0;
-        lenbv[q] = en[q].len >= 0.0 ? en[q].len * __ldcg(m.ws + en[q].bv_off) : 0.0;
-    }
-    const int e_pass = E < 32 ? E : 32;
+    for (int q = 0; q < NB; ++q) t[q] = en[q].len >= 0 ? (double)en[q].len * __ldcg(m.sbase + en[q].bv_off) : 0.0;
+    int e_pass = 0;      // the slots of a region are filled from the front: the longest list of the batch
+#pragma unroll
+    for (int q = 0; q < NB; ++q) e_pass = max(e_pass, __popc(__ballot_sync(kFull, en[q].len >= 0)));
 #pragma unroll 4
     for (int e = 0; e < e_pass; ++e) {
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
-            const long long oc = __shfl_sync(kFull, en[q].cm2_off, e), od = __shfl_sync(kFull, en[q].d_off, e);
-            const bool ok = __shfl_sync(kFull, en[q].len, e) >= 0.0;
-            if (on && ok) t[q] = fma(__ldcg(m.ws + oc + lane), __ldg(m.ws + od + lane), t[q]);
+            const unsigned oc = __shfl_sync(kFull, en[q].cm2_off, e), od = __shfl_sync(kFull, en[q].d_off, e);
+            const int len = __shfl_sync(kFull, en[q].len, e);
+            if (on && len >= 0) t[q] = fma(__ldcg(m.sbase + oc + lane), __ldg(m.sbase + od + lane), t[q]);
         }
     }
     for (int e0 = 32; e0 < E; e0 += 32) {     // more than 32 pieces per region (deep, non-nested index sets): further passes
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
             AncEntry x;
-            x.len = -1.0;
+            x.len = -1;
             x.cm2_off = x.bv_off = x.d_off = 0;
             if (live[q] && e0 + lane < E) x = ly.anc_tab[(size_t)(l0 + q * stride) * E + e0 + lane];
-            lenbv[q] += x.len >= 0.0 ? x.len * __ldcg(m.ws + x.bv_off) : 0.0;
+            t[q] += x.len >= 0 ? (double)x.len * __ldcg(m.sbase + x.bv_off) : 0.0;
             for (int e = 0; e < 32 && e0 + e < E; ++e) {
-                const long long oc = __shfl_sync(kFull, x.cm2_off, e), od = __shfl_sync(kFull, x.d_off, e);
-                const bool ok = __shfl_sync(kFull, x.len, e) >= 0.0;
-                if (on && ok) t[q] = fma(__ldcg(m.ws + oc + lane), __ldg(m.ws + od + lane), t[q]);
+                const unsigned oc = __shfl_sync(kFull, x.cm2_off, e), od = __shfl_sync(kFull, x.d_off, e);
+                const int len = __shfl_sync(kFull, x.len, e);
+                if (on && len >= 0) t[q] = fma(__ldcg(m.sbase + oc + lane), __ldg(m.sbase + od + lane), t[q]);
             }
         }
     }
-    double mine_sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, mine_rc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, mine_noise = 1.0, mine_b0 = 0.0, mine_b1 = 0.0;
+    // warp sums: [dA . s (2), d . cm2, f_var] per region, all in one lock-step butterfly
+    double red[NB * 4];
+    bool any = false;
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
         const double dA0 = ao[q].x - an[q].x, dA1 = ao[q].y - an[q].y;
-        const double sd0 = wsum(si[q] * dA0), sd1 = wsum(si[q] * dA1);
-        double quad = 0.0;
-        if (__any_sync(kFull, dA0 != 0.0 || dA1 != 0.0)) {
+        any = any || dA0 != 0.0 || dA1 != 0.0;
+        red[q * 4 + 0] = si[q] * dA0;
+        red[q * 4 + 1] = si[q] * dA1;
+        red[q * 4 + 2] = dsum[q] * cm2[q];
+        red[q * 4 + 3] = t[q];
+    }
+    wsum_n<NB * 4>(red);
+    double quad[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) quad[q] = 0.0;
+    if (__any_sync(kFull, any)) {      // dA^T G dA (zero in the inert regime of the published model: skipped)
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const double dA0 = ao[q].x - an[q].x, dA1 = ao[q].y - an[q].y;
             const double *G = ly.gram + (size_t)(live[q] ? l0 + q * stride : 0) * M * M;
             double t0 = 0.0, t1 = 0.0;
 #pragma unroll 6
@@ -322,29 +359,22 @@ __device__ __forceinline__ void mid2_stats_upper(const ChainModel &m, const Chai
                 t0 = fma(g, __shfl_sync(kFull, dA0, k), t0);
                 t1 = fma(g, __shfl_sync(kFull, dA1, k), t1);
             }
-            quad = wsum(dA0 * t0 + dA1 * t1);
+            quad[q] = dA0 * t0 + dA1 * t1;
         }
-        const double dc = wsum(dsum[q] * cm2[q]);
-        const double fv = wsum(t[q]) + wsum(lenbv[q]);
-        const double n = __shfl_sync(kFull, rcl[q], 0);
-        const double b0 = __shfl_sync(kFull, rcl[q], 9), b1 = __shfl_sync(kFull, rcl[q], 10), noise_old = __shfl_sync(kFull, rcl[q], 8);
-        double rcq[7];
-#pragma unroll
-        for (int k = 0; k < 7; ++k) rcq[k] = __shfl_sync(kFull, rcl[q], k);
-        if (lane == q) {
-            mine_sums[0] = sd0 + n * b0;
-            mine_sums[1] = sd1 + n * b1;
-            mine_sums[2] = quad + 2.0 * (b0 * sd0 + b1 * sd1) + n * (b0 * b0 + b1 * b1);
-            mine_sums[3] = fv;
-            mine_sums[4] = dc;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) mine_rc[k] = rcq[k];
-            mine_noise = noise_old;
-            mine_b0 = b0;
-            mine_b1 = b1;
-        }
+        wsum_n<NB>(quad);
     }
-    if (lane < NB && l0 + lane * stride < ly.R) bias_noise_update(ly, l0 + lane * stride, true, mine_sums, mine_rc, mine_noise, mine_b0, mine_b1);
+    double sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+        if (lane == q) {
+            const double n = rc[0], sd0 = red[q * 4 + 0], sd1 = red[q * 4 + 1];
+            sums[0] = sd0 + n * b0;
+            sums[1] = sd1 + n * b1;
+            sums[2] = quad[q] + 2.0 * (b0 * sd0 + b1 * sd1) + n * (b0 * b0 + b1 * b1);
+            sums[3] = red[q * 4 + 3];
+            sums[4] = red[q * 4 + 2];
+        }
+    if (tail) bias_noise_update(ly, lq, true, sums, rc, noise_old, b0, b1);
 }
 
 // ---- the solver (one warp) ---------------------------------------------------------------------------------------
@@ -413,12 +443,16 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
     int iters = 0;
     double err_prev = INFINITY, c = 1.0;
     int last = kOmegaNone;
+    bool converged = false;
     const double inv_m = 1.0 / (double)M;
     if (lane == 0) PROF(7);
     for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
         ++iters;
         const double err = omega_eval<MP>(K, P, Q, v, c, T, row, lane);
-        if (err < kOmegaTol) break;
+        if (err < kOmegaTol) {
+            converged = true;
+            break;
+        }
         if (!isfinite(err)) {   // a bad (warm) start or an overshooting Newton step: start again from the shifts alone
             v = 1.0;
             err_prev = INFINITY;
@@ -504,7 +538,7 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
     }
     if (lane == 0) PROF(8);
     // last resort: plain Sinkhorn sweeps (see omega_solve_serial); on model tables the loop exits at its first test
-    for (int it = 0; it < kOmegaFallbackSweeps; ++it) {
+    for (int it = 0; it < kOmegaFallbackSweeps && !converged; ++it) {
         const double err = omega_eval<MP>(K, P, Q, v, c, T, row, lane);
         if (err < kOmegaTol || !isfinite(err)) break;
         ++iters;
@@ -521,6 +555,53 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
         m.omegaWarm[layer] = 1.0;
         PROF(9);
     }
+}
+
+// One Bingham axis update for dy == 2 on the critical chain (same mathematics as bingham2 of mrgp_math.cuh, arranged
+// for latency: division-free PD test, one rsqrt for the eigen-solve, the saddle point of
+// computeRealBinghamConstant.py:42-147 in the closed form of its root for p = 2 with one logarithm:
+//   Lam = (0.1, 0.1 + gap), gap = kappa_1 - kappa_2;  t = 0.1 - u,  u = (1 + 1 / (sqrt(1 + gap^2) + gap)) / 2;
+//   log C = (log 2 pi - log(K2 u (u + gap))) / 2 + u + kappa_1,   K2 u (u + gap) = (q + 1 / q) / 2,  q = (u + gap) / u.
+// The rare non-PD input takes the guard of bingham2 (SanityCheck.py:16-65).
+__device__ __forceinline__ void bingham2_chain(double a, double b, double c, Bingham2 &out) {
+    if (!(a > 0.0 && fma(a, c, -b * b) > 0.0)) {
+        bingham2(a, b, c, out);
+        return;
+    }
+    const double mid = 0.5 * (a + c), d = 0.5 * (a - c), qq = fma(d, d, b * b);
+    double h = 0.0, p00 = 1.0, p01 = 0.0, p11 = 0.0;
+    if (qq > 0.0) {
+        const double rh = rsqrt(qq);
+        h = qq * rh;
+        const double ih = 0.5 * rh;
+        p00 = fma(d, ih, 0.5);
+        p11 = fma(-d, ih, 0.5);
+        p01 = b * ih;
+    }
+    const double l1 = mid + h, l2 = mid - h, gap = l1 - l2;
+    const double u = 0.5 * (1.0 + 1.0 / (sqrt(fma(gap, gap, 1.0)) + gap));
+    const double ug = u + gap;
+    const double r0 = 1.0 / u, r1 = 1.0 / ug;
+    const double k2 = 0.5 * (r0 * r0 + r1 * r1), k3 = r0 * r0 * r0 + r1 * r1 * r1;
+    const double q = ug * r0;
+    out.logc = 0.5 * (kLog2Pi - log(0.5 * (q + u * r1))) + u + l1;
+    const double ik2 = 1.0 / k2, dsumlogdt = -(r0 + r1);
+    const double rr[2] = {r0, r1};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double dtdlam = 0.5 * rr[k] * rr[k] * ik2;
+        const double dk2dlam = fma(k3, dtdlam, -(rr[k] * rr[k] * rr[k]));
+        out.rho[k] = 0.5 * (dk2dlam * ik2) + 0.5 * fma(dsumlogdt, dtdlam, rr[k]) + dtdlam;
+    }
+    out.b[0] = a;
+    out.b[1] = b;
+    out.b[2] = c;
+    out.kappa[0] = l1 < 0.0 ? 0.0 : l1;
+    out.kappa[1] = l2 < 0.0 ? 0.0 : l2;
+    out.cov[0] = out.rho[0] * p00 + out.rho[1] * (1.0 - p00);
+    out.cov[1] = out.rho[0] * p01 - out.rho[1] * p01;
+    out.cov[2] = out.rho[0] * p11 + out.rho[1] * (1.0 - p11);
+    out.n_chol = 1;
 }
 
 // ---- the shared step of a layer on CTA 0 (256 threads) ------------------------------------------------------------
@@ -573,7 +654,7 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
             b11 = fma(w, sm.primeB[k * 4 + 3], b11);
         }
         Bingham2 bg;
-        bingham2(b00 + sm.data[0 * 32 + i], b01 + sm.data[1 * 32 + i], b11 + sm.data[2 * 32 + i], bg);
+        bingham2_chain(b00 + sm.data[0 * 32 + i], b01 + sm.data[1 * 32 + i], b11 + sm.data[2 * 32 + i], bg);
         sm.cov[i * 4 + 0] = bg.cov[0];
         sm.cov[i * 4 + 1] = bg.cov[1];
         sm.cov[i * 4 + 2] = bg.cov[1];
@@ -624,50 +705,126 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
     }
     __syncthreads();
     if (tid == 0) PROF(3);
-    // S4, the table (Stats.py:405-412; a true matrix product inside the trace): a warp per row, the row maxima on the way
+    // S4, the table (Stats.py:405-412; a true matrix product inside the trace): a warp per row, the row maxima on the
+    // way; the (at most 4) rows of a warp are independent instruction streams
     const bool last_layer = j == m.J - 1;
-    for (int i = warp; i < M; i += kChainThreads / 32) {
-        double lw = -INFINITY;
-        if (lane < M) {
-            const int k = lane;
-            const double *Cc = sm.cov + i * 4, *Bp = sm.primeB + k * 4;
-            const double tr = Cc[0] * Bp[0] + Cc[1] * Bp[2] + Cc[2] * Bp[1] + Cc[3] * Bp[3];
-            lw = tr + sm.sk[k] + (sm.primeShape[k] - 1.0) * sm.lmean[i] - sm.primeScale[k] * sm.mean[i];
-            sm.lw[i * LW + k] = lw;
-            if (last_layer) m.logOmegaHat[i * M + k] = lw;
+    {
+        double lwv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = warp + u * 8;
+            lwv[u] = -INFINITY;
+            if (i < M && lane < M) {
+                const int k = lane;
+                const double *Cc = sm.cov + i * 4, *Bp = sm.primeB + k * 4;
+                const double tr = Cc[0] * Bp[0] + Cc[1] * Bp[2] + Cc[2] * Bp[1] + Cc[3] * Bp[3];
+                lwv[u] = tr + sm.sk[k] + (sm.primeShape[k] - 1.0) * sm.lmean[i] - sm.primeScale[k] * sm.mean[i];
+                sm.lw[i * LW + k] = lwv[u];
+                if (last_layer) m.logOmegaHat[i * M + k] = lwv[u];
+            }
         }
-        const double mx = wmax(lw);
-        if (lane == 0) sm.rowmax[i] = mx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) lwv[u] = fmax(lwv[u], __shfl_xor_sync(kFull, lwv[u], o));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (lane == 0 && warp + u * 8 < M) sm.rowmax[warp + u * 8] = lwv[u];
     }
     __syncthreads();
     if (tid == 0) PROF(4);
     // shifts and exponentials, a warp per column: every row and column of K holds a 1 (no overflow, no empty line)
-    for (int k = warp; k < M; k += kChainThreads / 32) {
-        const double v = lane < M ? sm.lw[lane * LW + k] - sm.rowmax[lane] : -INFINITY;
-        const double mx = wmax(v);
-        if (lane < M) sm.Kt[k * LD + lane] = exp(v - mx);
-        if (lane == 0) sm.colmax[k] = mx;
+    {
+        double v[4], mx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = warp + u * 8;
+            v[u] = (k < M && lane < M) ? sm.lw[lane * LW + k] - sm.rowmax[lane] : -INFINITY;
+            mx[u] = v[u];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mx[u] = fmax(mx[u], __shfl_xor_sync(kFull, mx[u], o));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = warp + u * 8;
+            if (k < M && lane < M) sm.Kt[k * LD + lane] = exp(v[u] - mx[u]);
+            if (k < M && lane == 0) sm.colmax[k] = mx[u];
+        }
     }
     if (tid == 0) PROF(5);
 }
 
+// Worker steps of one warp for a whole layer, NB regions at a time (NB by the regions per worker warp).
+__device__ __forceinline__ void layer_mid1(const ChainModel &m, int j, int ww, int n_workers, int lane, const double *ardMean, double (&acc)[7]) {
+    const ChainLayer &ly = m.layer[j];
+    if (j == 0) {
+        for (int l = ww; l < ly.R; l += n_workers) mid1_layer0(m, ly, l, lane, ardMean, acc);
+    } else if (ly.R <= n_workers) {
+        if (ww < ly.R) mid1_upper<1>(m, ly, ww, n_workers, lane, ardMean, acc);
+    } else if (ly.R <= 2 * n_workers) {
+        mid1_upper<2>(m, ly, ww, n_workers, lane, ardMean, acc);
+    } else {
+        for (int l = ww; l < ly.R; l += 4 * n_workers) mid1_upper<4>(m, ly, l, n_workers, lane, ardMean, acc);
+    }
+}
+
+__device__ __forceinline__ void layer_finish(const ChainModel &m, int j, int ww, int n_workers, int lane, const double *cov) {
+    const ChainLayer &ly = m.layer[j];
+    if (j == 0) {
+        for (int l = ww; l < ly.R; l += n_workers) mid2_stats_layer0(m, ly, l, lane, cov);
+    } else if (ly.R <= n_workers) {
+        if (ww < ly.R) mid2_stats_upper<1>(m, ly, ww, n_workers, lane, cov);
+    } else if (ly.R <= 2 * n_workers) {
+        mid2_stats_upper<2>(m, ly, ww, n_workers, lane, cov);
+    } else {
+        for (int l = ww; l < ly.R; l += 4 * n_workers) mid2_stats_upper<4>(m, ly, l, n_workers, lane, cov);
+    }
+}
+
+// Cluster of C CTAs per model.  C >= 2: CTA 0 runs the shared step and the solver, the warps of CTAs 1 .. C-1 are the
+// workers and finish layer j (S2, P4 / P5) in the BACKGROUND: they arrive at the cluster barrier as soon as the region
+// sums of layer j + 1 are published and do that work before they wait, so the chain on CTA 0 never waits for it.
+// C == 1 (a batch of small models, one CTA each): warp 0 solves while warps 1-7 do the worker steps of the layer.
 template <int MP>
 __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel *const *models) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ChainSmem &sm = *reinterpret_cast<ChainSmem *>(smem_raw);
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
-    const ChainModel &m = *models[blockIdx.x / C];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const ChainModel *gm = models[blockIdx.x / C];
+        const int J0 = gm->J;
+        const size_t bytes = offsetof(ChainModel, layer) + (size_t)J0 * sizeof(ChainLayer);   // multiples of 8
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(gm);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(sm.model);
+        for (size_t t = tid; t < bytes / 8; t += kChainThreads) dst[t] = src[t];
+    }
+    __syncthreads();
+    const ChainModel &m = *reinterpret_cast<const ChainModel *>(sm.model);
     const int M = m.M, J = m.J;
+    const bool early = C >= 2;
     const bool solver = rank == 0 && warp == 0;
-    const int n_workers = (int)C * 8 - 1;                  // worker warps of the cluster
-    const int ww = (int)rank * 8 + warp - 1;               // this warp's worker index (-1: the solver)
-    const int cta_worker_threads = rank == 0 ? kChainThreads - 32 : kChainThreads;
+    const bool worker = early ? rank > 0 : warp > 0;
+    const int n_workers = early ? ((int)C - 1) * 8 : 7;                   // worker warps of the cluster
+    const int ww = early ? ((int)rank - 1) * 8 + warp : warp - 1;         // this warp's worker index
+    const int w0 = early ? 0 : 1;                                         // first worker warp of a CTA
+    const int wthreads = early ? kChainThreads : kChainThreads - 32;      // worker threads of a CTA
+    const int wt = tid - w0 * 32;
     unsigned long long *ts = m.ts;
     if (ts && rank == 0 && tid == 0) atomicMin(&ts[(0 * 4 + 1) * 2], gtimer());
 
-    // ---- prologue: omega (transposed) on CTA 0, the ARD mean of the previous sweep everywhere -------------------
+    // ---- prologue: the small-matrix state into L2 (the sweep is a chain of dependent loads), omega (transposed) and the
+    //      warm starts on CTA 0, the ARD mean of the previous sweep everywhere ---------------------------------------
+    {
+        const unsigned long long lines = m.pf_lines, nthr = (unsigned long long)C * kChainThreads;
+        for (unsigned long long l = (unsigned long long)rank * kChainThreads + tid; l < lines; l += nthr)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(m.pf_base + l * 128));
+    }
     if (rank == 0) {
         for (int t = tid; t < M * M; t += kChainThreads) {
             const int i = t / M, k = t - i * M;
@@ -678,71 +835,74 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
         if (tid < J) sm.warm[tid] = m.omegaWarm[tid];
     }
     if (tid < 4 * 32) {   // lanes past M must hold finite values (they are multiplied by zeros)
+        const double am = (tid >= 96 && tid - 96 < M) ? m.ardMean[tid - 96] : (tid >= 96 ? 1.0 : 0.0);
         sm.pub[tid] = 0.0;
-        sm.loc[tid] = (tid >= 96 && tid - 96 < M) ? m.ardMean[tid - 96] : (tid >= 96 ? 1.0 : 0.0);
+        sm.loc[0][tid] = am;
+        sm.loc[1][tid] = am;
     }
+    if (tid < 7 * 32) sm.ctaPart[tid] = 0.0;   // a CTA without worker warps (CTA 0 of a cluster of several) contributes zeros
     __syncthreads();
     double acc[7];
 #pragma unroll
     for (int q = 0; q < 7; ++q) acc[q] = 0.0;
-    if (!solver)
-        for (int l = ww; l < m.layer[0].R; l += n_workers) mid1_layer0(m, m.layer[0], l, lane, sm.loc + 96, acc);
+    if (worker) {
+        layer_mid1(m, 0, ww, n_workers, lane, sm.loc[0] + 96, acc);
 #pragma unroll
-    for (int q = 0; q < 7; ++q) sm.part[warp][q][lane] = acc[q];
-    __syncthreads();
-    for (int v = tid; v < 7 * 32; v += kChainThreads) {
-        double s = 0.0;
-        for (int w = (rank == 0 ? 1 : 0); w < 8; ++w) s += sm.part[w][v >> 5][v & 31];
-        sm.ctaPart[v] = s;
+        for (int q = 0; q < 7; ++q) sm.part[warp][q][lane] = acc[q];
+        worker_bar(wthreads);
+        for (int v = wt; v < 7 * 32; v += wthreads) {
+            double s = 0.0;
+            for (int w = w0; w < 8; ++w) s += sm.part[w][v >> 5][v & 31];
+            sm.ctaPart[v] = s;
+        }
     }
 
     for (int j = 0; j < J; ++j) {
-        cluster.sync();                                    // the region sums of layer j are in place
+        cl_arrive();                                       // A_j: this thread's share of the region sums of layer j is published
+        if (worker && early && j > 0) layer_finish(m, j - 1, ww, n_workers, lane, sm.loc[(j - 1) & 1]);   // background
+        cl_wait();
         if (rank == 0) {
             if (ts && tid == 0) atomicMin(&ts[(j * 4 + 3) * 2], gtimer());
             shared_step(m, sm, cluster, j, tid, C);
         }
-        cluster.sync();                                    // axis covariance, ARD moments and the table of layer j
+        cl_arrive();                                       // B_j: axis covariance, ARD moments and the table of layer j
+        cl_wait();
         if (solver) {
             omega_solve_warp<MP>(m, sm, j, lane);
             if (ts && lane == 0) atomicMax(&ts[(j * 4 + 3) * 2 + 1], gtimer());
-        } else {
-            if (ts && rank == 0 && tid == 32) atomicMin(&ts[(j * 4 + 1) * 2], gtimer());
-            if (rank == 0 && tid == 32) PROF(10);
+        }
+        // k-only terms of the NEXT layer's table from the posterior of this layer (one lgamma per basis function), beside the solve
+        if (rank == 0 && warp == 1 && lane < M) sm.skNext[lane] = -sm.logC[lane] + sm.shape[lane] * log(sm.scale[lane]) - lgamma(sm.shape[lane]);
+        if (worker) {
+            const bool stamp = ww == 0 && lane == 0;
+            if (ts && stamp) atomicMin(&ts[(j * 4 + 1) * 2], gtimer());
+            if (stamp) PROF(10);
+            double *loc = sm.loc[j & 1];
             const double *pub = cluster.map_shared_rank(sm.pub, 0);
-            const int wt = rank == 0 ? tid - 32 : tid;
-            for (int v = wt; v < 4 * 32; v += cta_worker_threads) sm.loc[v] = pub[v];
-            // k-only terms of the NEXT layer's table from the posterior just written (one lgamma per basis function)
-            if (rank == 0 && warp == 1 && lane < M) sm.skNext[lane] = -sm.logC[lane] + sm.shape[lane] * log(sm.scale[lane]) - lgamma(sm.shape[lane]);
-            worker_bar(cta_worker_threads);
-            if (rank == 0 && tid == 32) PROF(11);
+            for (int v = wt; v < 4 * 32; v += wthreads) loc[v] = pub[v];
+            worker_bar(wthreads);
+            if (stamp) PROF(11);
 #pragma unroll
             for (int q = 0; q < 7; ++q) acc[q] = 0.0;
-            if (j + 1 < J) {
-                const ChainLayer &nx = m.layer[j + 1];
-                for (int l = ww; l < nx.R; l += kBatch * n_workers) mid1_upper<kBatch>(m, nx, l, n_workers, lane, sm.loc + 96, acc);
-            }
+            if (j + 1 < J) layer_mid1(m, j + 1, ww, n_workers, lane, loc + 96, acc);
 #pragma unroll
             for (int q = 0; q < 7; ++q) sm.part[warp][q][lane] = acc[q];
-            if (rank == 0 && tid == 32) PROF(12);
-            if (j == 0) {
-                for (int l = ww; l < m.layer[0].R; l += n_workers) mid2_stats_layer0(m, m.layer[0], l, lane, sm.loc);
-            } else {
-                const ChainLayer &cu = m.layer[j];
-                for (int l = ww; l < cu.R; l += kBatch * n_workers) mid2_stats_upper<kBatch>(m, cu, l, n_workers, lane, sm.loc);
-            }
-            if (rank == 0 && tid == 32) PROF(13);
-            worker_bar(cta_worker_threads);
-            for (int v = wt; v < 7 * 32; v += cta_worker_threads) {
+            if (stamp) PROF(12);
+            worker_bar(wthreads);
+            for (int v = wt; v < 7 * 32; v += wthreads) {
                 double s = 0.0;
-                for (int w = (rank == 0 ? 1 : 0); w < 8; ++w) s += sm.part[w][v >> 5][v & 31];
+                for (int w = w0; w < 8; ++w) s += sm.part[w][v >> 5][v & 31];
                 sm.ctaPart[v] = s;
             }
-            if (ts && rank == 0 && tid == 32) atomicMax(&ts[(j * 4 + 1) * 2 + 1], gtimer());
-            if (rank == 0 && tid == 32) PROF(14);
+            if (stamp) PROF(13);
+            if (!early) layer_finish(m, j, ww, n_workers, lane, loc);
+            if (ts && stamp) atomicMax(&ts[(j * 4 + 1) * 2 + 1], gtimer());
+            if (stamp) PROF(14);
         }
     }
-    cluster.sync();
+    if (worker && early) layer_finish(m, J - 1, ww, n_workers, lane, sm.loc[(J - 1) & 1]);
+    cl_arrive();
+    cl_wait();
     // ---- the shared posterior / stats left by the last layer (Posteriors.py:482-541, Stats.py:354-420) ----------
     if (rank == 0) {
         for (int t = tid; t < M * M; t += kChainThreads) {
@@ -832,6 +992,8 @@ int launch_impl(const ChainModel *const *models_dev, int n_models, int cluster, 
         cudaError_t e = cudaFuncSetAttribute(k_ci_sweep<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(k_ci_sweep<MP>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(k_ci_sweep<MP>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }

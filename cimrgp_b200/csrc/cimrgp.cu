@@ -1126,7 +1126,7 @@ int chain_cluster_size(const mrgp_handle *h) {
     if (h->chain_cluster > 0) return h->chain_cluster;
     int rmax = 1;
     for (const auto &lp : h->plan) rmax = std::max(rmax, lp.R);
-    return rmax <= 32 ? 1 : rmax <= 64 ? 2 : rmax <= 128 ? 4 : 8;
+    return rmax <= 32 ? 1 : rmax <= 64 ? 2 : rmax <= 128 ? 4 : rmax <= 256 ? 8 : 16;
 }
 
 // Descriptor of the model for the fused sweep (device pointers only; uploaded before the sweep is captured).
@@ -1137,7 +1137,9 @@ int upload_chain_model(mrgp_handle *h) {
     m.J = h->cfg.n_layers;
     m.M = h->cfg.n_basis;
     m.DY = h->cfg.dy;
-    m.ws = reinterpret_cast<double *>(h->ws);
+    m.sbase = reinterpret_cast<double *>(h->ws + h->state_begin);
+    m.pf_base = h->ws + h->state_begin;
+    m.pf_lines = (h->state_end - h->state_begin + 127) / 128;
     m.x = h->x - h->lo;
     m.y = h->y - h->lo * h->cfg.dy;
     m.axB = s.axB; m.axKappa = s.axKappa; m.axRho = s.axRho; m.axLogC = s.axLogC; m.axCov = s.axCov;
@@ -1567,18 +1569,20 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
         LayerDev &d = h->dev[j];
         const int E = std::max(lp.E, 1), M = h->cfg.n_basis;
         std::vector<AncEntry> tab((size_t)lp.R * E);
-        const double *base = reinterpret_cast<const double *>(h->ws);
+        const double *base = reinterpret_cast<const double *>(h->ws + h->state_begin);
+        if ((h->state_end - h->state_begin) / sizeof(double) >= 0xffffffffull)
+            return fail(h, MRGP_EINVAL, "small-matrix state of more than 32 GB: not supported by the fused sweep tables");
         for (int c = 0; c < lp.R; ++c) {
             int e = 0;
             for (int jp = 0; jp < j; ++jp)
                 for (int pc = lp.pc_ptr[(size_t)jp * (lp.R + 1) + c]; pc < lp.pc_ptr[(size_t)jp * (lp.R + 1) + c + 1]; ++pc, ++e) {
                     AncEntry &a = tab[(size_t)c * E + e];
-                    a.cm2_off = (h->dev[jp].cm2 - base) + (long long)lp.pc_anc[pc] * M;
-                    a.bv_off = (h->dev[jp].bias_var - base) + lp.pc_anc[pc];
-                    a.d_off = (d.ancD - base) + (long long)pc * M;
-                    a.len = (double)(lp.pc_hi[pc] - lp.pc_lo[pc]);
+                    a.cm2_off = (uint32_t)((h->dev[jp].cm2 - base) + (long long)lp.pc_anc[pc] * M);
+                    a.bv_off = (uint32_t)((h->dev[jp].bias_var - base) + lp.pc_anc[pc]);
+                    a.d_off = (uint32_t)((d.ancD - base) + (long long)pc * M);
+                    a.len = (int32_t)(lp.pc_hi[pc] - lp.pc_lo[pc]);
                 }
-            for (; e < E; ++e) tab[(size_t)c * E + e] = AncEntry{0, 0, 0, -1.0};
+            for (; e < E; ++e) tab[(size_t)c * E + e] = AncEntry{0, 0, 0, -1};
         }
         CK(cudaMemcpyAsync(d.anc_tab, tab.data(), tab.size() * sizeof(AncEntry), cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));   // `tab` is a local

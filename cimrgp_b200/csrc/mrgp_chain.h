@@ -14,14 +14,14 @@ namespace mrgp {
 
 constexpr int kChainMaxLayers = 24;
 constexpr int kChainThreads = 256;
-constexpr int kChainMaxCluster = 8;
+constexpr int kChainMaxCluster = 16;   // above 8: non-portable cluster size (allowed on sm_100a)
 
 // One piece of a region with a region of a coarser layer, for sum f_var of the closed-form statistics: offsets in
-// doubles from the workspace base of the coarser region's cm2 row and bias variance and of the piece's D row; its
-// number of samples (len < 0: unused slot of the fixed-stride table).
+// doubles from the base of the small-matrix state (ChainModel::sbase) of the coarser region's cm2 row and bias variance
+// and of the piece's D row; its number of samples (len < 0: unused slot of the fixed-stride table).
 struct AncEntry {
-    long long cm2_off, bv_off, d_off;
-    double len;
+    uint32_t cm2_off, bv_off, d_off;
+    int32_t len;
 };
 
 struct ChainLayer {
@@ -47,7 +47,9 @@ struct ChainLayer {
 
 struct ChainModel {
     int32_t J, M, DY, pad;
-    double *ws;                    // workspace base (AncEntry offsets are relative to it)
+    double *sbase;                 // base of the small-matrix state in the workspace (AncEntry offsets are relative to it)
+    const char *pf_base;           // range pulled into L2 at the start of a sweep (the small-matrix state), 128-byte lines
+    unsigned long long pf_lines;
     const double *x, *y;           // (N), (N, DY) normalised inputs and observations, indexed by the global sample number
     // shared posterior / stats (Posteriors.py:482-541, Stats.py:354-420)
     double *axB, *axKappa, *axRho, *axLogC, *axCov, *ardShape, *ardScale, *ardMean, *ardLogMean;

@@ -11,6 +11,11 @@ n, res = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000, int(sys.argv[2]) if
 x, y = workloads.workload1(n)
 m = MultiResolutionGaussianProcess([x, y], 30, IndexSetUniform(n, res, 2), LaplacianEigenpairs(), MaternKernel(1, 1, 1))
 m.fit(12, None)
+if os.environ.get('FLUSH') == '1':
+    import torch
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+    m._engine.synchronize(); flush.zero_(); torch.cuda.synchronize()
+    m.fit(1, None)
 p = m._engine.get(-1, 54, (res + 1, 16))
 names = ['gather', 'bingham|ard', 'mean', 'table', 'exp', '->sync2', 'solve:load', 'solve:iter', 'solve:fb', None,
          'w:pubcopy', 'w:mid1', 'w:mid2stats', 'w:bar', None]
@@ -20,6 +25,6 @@ for j in range(res + 1):
     sh = ' '.join('%s=%d' % (names[k], r[k + 1] - r[k]) for k in range(5))
     so = ' '.join('%s=%d' % (names[k], r[k + 1] - r[k]) for k in (6, 7, 8))
     wo = ' '.join('%s=%d' % (names[k], r[k + 1] - r[k]) for k in (10, 11, 12, 13))
-    nxt = (p[j + 1][0] - max(r[9], r[14])) if j < res else 0
-    print('L%d shared[%s] sync2=%d | solve[%s] | worker[%s] | sync1=%d | layer=%d' % (
-        j, sh, min(r[6], r[10]) - r[5], so, wo, nxt, (p[j + 1][0] - r[0]) if j < res else max(r[9], r[14]) - r[0]))
+    nxt = (p[j + 1][0] - r[9]) if j < res else 0
+    print('L%d shared[%s] sync2=%d | solve[%s] ->next=%d | worker(other SM clock)[%s] | layer=%d' % (
+        j, sh, r[6] - r[5], so, nxt, wo, (p[j + 1][0] - r[0]) if j < res else r[9] - r[0]))
