@@ -1,12 +1,21 @@
 #!/usr/bin/env python
-"""Benchmark of the ciMRGP VI hot path (BASELINE.json: VI iterations/sec at N = 1e6, 10 resolutions).
+"""Benchmark of the ciMRGP VI hot path (BASELINE.json: VI iterations/sec at N = 1e6, 10 resolutions; batched
+Cholesky GFLOP/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" is one full variational sweep (`_fit()`, MRGP.py:571-652) over all 10 layers of the config-4
-workload (N = 1e6 samples, dx = 1, dy = 2, M = 30, 1023 regions, ci mode, fp64, static basis intervals).
-Prints ONE JSON line (see the keys below).  Timing: CUDA events on the engine's stream around every step,
-L2 flushed (256 MB write) between steps, max over ranks.
+One "step" is one full variational sweep (`_fit()`, MRGP.py:571-652) over all 10 layers of the config-4 workload
+(N = 1e6 samples, dx = 1, dy = 2, M = 30, 1023 regions, ci mode, fp64, static basis intervals).  Prints ONE JSON line.
+
+GPU arm.  `value`: sweeps per second with everything resident in HBM, CUDA events on the engine's stream around every
+step, L2 flushed (256 MB write) between steps, max over ranks.  `e2e`: the same sweep through the drop-in API with
+NEW OBSERVATIONS every step at unchanged inputs: 16 MB of y copied from pinned host memory, the layer-0 statistics pass
+over x and y, the sweep, the six ELBO terms per layer read back.  `roofline`: the streaming kernel that remains on the
+path, k_ystats (24 B per sample), against the measured HBM peak; the steady-state sweep itself is ONE latency-bound
+kernel (k_ci_sweep) that touches no sample, reported next to it.  `cpu_baseline` / `--impl reference`:
+the multi-threaded C restatement of the sweep (oracle/mrgp_port.c, kind "port") on the host cores, at the FULL config
+(no extrapolation), plus - when the reference itself travelled (oracle/_ref, bytecode compiled by build()) - one sweep of
+the UNMODIFIED reference at config-3 size as the calibration.
 """
 import argparse
 import json
@@ -25,8 +34,10 @@ def _finite(o):
         return {k: _finite(v) for k, v in o.items()}
     if isinstance(o, (list, tuple)):
         return [_finite(v) for v in o]
-    if isinstance(o, float) and not np.isfinite(o):
-        return None
+    if isinstance(o, (float, np.floating)):
+        return float(o) if np.isfinite(o) else None
+    if isinstance(o, np.integer):
+        return int(o)
     return o
 
 
@@ -38,18 +49,30 @@ N_SAMPLES = 1000000
 N_LAYERS = 10
 N_BASIS = 30
 DY = 2
+METRIC = 'ciMRGP VI iters/sec at N=1e6, R=10'
 WORKLOAD = 'config4: synthetic 1-D nonstationary signal (script-1 f, seed 10), N=1e6, dx=1, dy=2, M=30, ' \
            '10 resolutions (1023 regions), ciMRGP, fp64, static basis intervals'
+# the same `config` object on both arms (the driver compares them)
+CONFIG = {'workload': WORKLOAD, 'l2': 'GPU arm: L2 flushed between timed steps (256 MB write); CPU arm: n/a'}
 # algorithmic HBM bytes per sample-layer: phase A 8(dx+2dy) = 40, phase B 8(dx+2dy+1) + 8(dy+1) = 72
 BYTES_SWEEP_PER_SAMPLE_LAYER = 112
 
 
-def peak_hbm():
+def peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
             return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
     except Exception:
         return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the tracked ncu summary (profiles/r02_ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
 
 
 class ClockSampler(object):
@@ -103,89 +126,245 @@ class ClockSampler(object):
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml and nvidia-smi unavailable'], 'samples': 0}
 
 
-def make_model(n, device, n_ctas=0, distributed=False):
+def make_model(n, layers, device, fi=False, distributed=False, n_basis=N_BASIS, seed=10):
     import workloads
     from cimrgp_b200 import IndexSetUniform, LaplacianEigenpairs, MaternKernel
     from cimrgp_b200.MRGP import MultiResolutionGaussianProcess
-    x, y = workloads.workload1(n)
-    m = MultiResolutionGaussianProcess([x, y], N_BASIS, IndexSetUniform(n, N_LAYERS - 1, 2), LaplacianEigenpairs(),
-                                       MaternKernel(nu=1, l=1, sf=1), forced_independence=False, device=device,
-                                       n_ctas=n_ctas, distributed=distributed)
-    return m
+    x, y = workloads.workload1(n, seed=seed)
+    return MultiResolutionGaussianProcess([x, y], n_basis, IndexSetUniform(n, layers - 1, 2), LaplacianEigenpairs(),
+                                          MaternKernel(nu=1, l=1, sf=1), forced_independence=fi, device=device,
+                                          distributed=distributed)
 
 
-def oracle_sample(n_sample, sweeps):
-    """CPU oracle (NumPy port of the reference) on a bounded sample of the workload: the same signal,
-    layers and basis at n_sample samples.  Returns seconds per sweep and the fixed (N-independent) part
-    spent in the permutation-weight solver."""
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arms
+# ------------------------------------------------------------------------------------------------------------------
+def port_sweeps(n, layers, warmup, steps):
+    """The C restatement of the ci sweep (oracle/mrgp_port.c, OpenMP over all host threads) at FULL size n: seconds of
+    each of `steps` sweeps after `warmup` sweeps, the threads it used, the seconds of its constructor."""
     import workloads
     from oracle import mrgp_oracle as O
-    x, y = workloads.workload1(n_sample)
-    m = O.OracleMRGP(x, y, N_BASIS, O.uniform_offsets(n_sample, N_LAYERS - 1, 2), mode='ci')
+    from oracle import port_c
+    x, y = workloads.workload1(n)
+    t0 = time.perf_counter()
+    p = port_c.PortC(x, y, N_BASIS, O.uniform_offsets(n, layers - 1, 2))
+    t_ctor = time.perf_counter() - t0
+    p.sweep(warmup)
     times = []
-    for _ in range(sweeps):
+    for _ in range(steps):
         t0 = time.perf_counter()
-        m.sweep()
+        p.sweep(1)
         times.append(time.perf_counter() - t0)
-    return times, m.t_omega / sweeps
+    threads = p.threads
+    p.close()
+    return times, threads, t_ctor
 
 
-def scaled_rate(t_step, t_fixed, n_sample):
-    """it/s on the full N from a step on n_sample samples: streaming part scales linearly in N, the
-    permutation-weight solve does not depend on N."""
-    return 1.0 / (t_fixed + (t_step - t_fixed) * (float(N_SAMPLES) / n_sample))
+def load_reference():
+    """The UNMODIFIED reference: /root/reference/src in the build container, its bytecode under oracle/_ref (compiled by
+    __graft_entry__.build(), git-ignored, travels with the snapshot) on the GPU box.  None when neither is there."""
+    import types
+    import warnings
+    for path in ('/root/reference/src', os.path.join(ROOT, 'oracle', '_ref')):
+        if os.path.isdir(path) and (os.path.exists(os.path.join(path, 'MRGP.py')) or os.path.exists(os.path.join(path, 'MRGP.pyc'))):
+            import scipy.misc
+            import scipy.special
+            scipy.misc.logsumexp = scipy.special.logsumexp          # Stats.py:4
+            for name in ('GPy', 'gpflow'):                           # RegressionInput.py:4-5 (only used with adaptive_inputs)
+                sys.modules.setdefault(name, types.ModuleType(name))
+            if path not in sys.path:
+                sys.path.insert(0, path)
+            warnings.filterwarnings('ignore')
+            mods = {name: __import__(name) for name in ('IndexSetGenerator', 'KernelClass', 'MRGP')}
+            return types.SimpleNamespace(path=path, **mods)
+    return None
+
+
+def reference_calibration(n=100000, layers=8):
+    """One `_fit()` of the unmodified reference at config-3 size (N = 1e5, 8 resolutions) next to the C port at the same
+    size: how far the port is from the reference's own speed."""
+    R = load_reference()
+    if R is None:
+        return {'available': False, 'why': 'neither /root/reference/src nor oracle/_ref is present on this host'}
+    import workloads
+    x, y = workloads.workload1(n)
+    t0 = time.perf_counter()
+    m = R.MRGP.MultiResolutionGaussianProcess(
+        train_xy=[x, y], n_basis=N_BASIS, index_set_obj=R.IndexSetGenerator.IndexSetUniform(sample_length=n, resolution=layers - 1, divider=2),
+        basis_function_obj=R.KernelClass.LaplacianEigenpairs(), spectral_density_obj=R.KernelClass.MaternKernel(nu=1, l=1, sf=1),
+        adaptive_inputs=False, standard_normalized_inputs=True, basis_interval_obj=None, interval_factor=1, forced_independence=False)
+    t_ctor = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    m._fit()
+    t_fit = time.perf_counter() - t0
+    times, threads, _ = port_sweeps(n, layers, 1, 3)
+    return {'available': True, 'kind': 'reference', 'source': R.path, 'workload': 'config3: N=1e5, 8 resolutions (255 regions), M=30, ci',
+            'cores': 1, 'constructor_s': t_ctor, 's_per_sweep': t_fit, 'it_per_s': 1.0 / t_fit,
+            'port_same_size': {'s_per_sweep': float(np.mean(times)), 'cores': threads},
+            'port_speedup_over_reference': t_fit / float(np.mean(times))}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (its NumPy port, oracle/; the
-    reference itself is Python and does not exist on the GPU box) on the host cores."""
+    """--impl reference: the CPU implementation of the path on the host cores, at the full config (rank 0 only)."""
     if rank != 0:
         return
-    budget = 150.0
-    per_step = budget / max(1, args.steps + args.warmup)
-    n_sample = int(min(N_SAMPLES, max(20000, (per_step - 1.5) / 41.5e-6)))
-    n_sample = (n_sample // 1024) * 1024
-    times, t_fixed = oracle_sample(n_sample, args.steps + args.warmup)
-    t_step = float(np.mean(times[args.warmup:]))
-    value = scaled_rate(t_step, t_fixed, n_sample)
-    sample = '%d steps of one oracle sweep on N=%d samples (same 10 layers, M=30); scaled to N=1e6 as ' \
-             '1/(t_omega + (t_step - t_omega) * 1e6/N), t_step=%.2fs, t_omega=%.2fs' % (args.steps, n_sample, t_step, t_fixed)
+    times, threads, t_ctor = port_sweeps(N_SAMPLES, N_LAYERS, args.warmup, args.steps)
+    total = float(np.sum(times))
+    value = args.steps / total
+    calib = None if args.no_calibration else reference_calibration()
     line = {
-        'impl': 'reference', 'metric': 'ciMRGP VI iters/sec at N=1e6, R=10', 'value': value, 'unit': 'it/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / value,
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'it/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps, 'step_ms': [round(1e3 * t, 2) for t in times],
+        'steps_timed': args.steps, 'extrapolated': False,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD},
-        'cpu_baseline': {'value': value, 'unit': 'it/s', 'cores': 1, 'kind': 'port', 'sample': sample,
-                         'host_cores': os.cpu_count()},
+        'config': CONFIG,
+        'cpu_baseline': {'value': value, 'unit': 'it/s', 'cores': threads, 'kind': 'port', 'host_cores': os.cpu_count(),
+                         'sample': '%d full sweeps at the stated config (N=1e6, 10 layers, every layer streams its samples twice, as '
+                                   'the reference does) of oracle/mrgp_port.c, OpenMP over %d threads; constructor %.1f s not '
+                                   'included' % (args.steps, threads, t_ctor)},
         'e2e': {'value': value, 'unit': 'it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'reference_unmodified': calib,
+        'note': 'kind "port": the reference is single-threaded Python (295 s per sweep at this config in the survey container); '
+                'its own speed is calibrated under reference_unmodified',
     }
     print(json.dumps(_finite(line)))
 
 
-def time_phase(eng, fn, j, torch, reps):
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def timed_sweeps(eng, steps, flush, barrier, max_over_ranks, torch):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for k in range(steps):
+        # the L2 flush (256 MB of HBM writes on torch's stream) must neither overlap the sweep before it nor the one
+        # after it: it starts when the previous timed sweep is over and ends before the next timed region starts
+        torch.cuda.current_stream().wait_stream(eng.stream)
+        flush.zero_()
+        eng.stream.wait_stream(torch.cuda.current_stream())
+        barrier()
+        ev[k][0].record(eng.stream)
+        eng.sweep(1)
+        ev[k][1].record(eng.stream)
+    barrier()
+    return [max_over_ranks(a.elapsed_time(b)) for a, b in ev]
+
+
+def time_call(eng, fn, flush, torch, reps):
     out = []
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(reps):
-        ev0.record(eng.stream)
-        fn(j)
-        ev1.record(eng.stream)
-        ev1.synchronize()
-        out.append(ev0.elapsed_time(ev1))
+        if flush is not None:
+            torch.cuda.current_stream().wait_stream(eng.stream)
+            flush.zero_()
+            eng.stream.wait_stream(torch.cuda.current_stream())
+        a.record(eng.stream)
+        fn()
+        b.record(eng.stream)
+        b.synchronize()
+        out.append(a.elapsed_time(b))
     return out
 
 
+def cholesky_grid(lib, torch, fp64_peak_tflops):
+    """mrgp_batched_cholesky over n x batch: GFLOP/s (n^3 / 3 per matrix) and fraction of the measured FP64 peak."""
+    import ctypes as C
+    out = []
+    rng = np.random.RandomState(0)
+    for n in (2, 4, 8, 16, 32):
+        for batch in (1000, 10000, 100000, 1000000):
+            if n * n * batch * 8 > 2 ** 31:
+                continue
+            a = rng.randn(min(batch, 4096), n, n + 2)
+            a = a @ np.swapaxes(a, 1, 2) + n * np.eye(n)
+            base = torch.as_tensor(a, device='cuda')
+            src = base.repeat((batch + base.shape[0] - 1) // base.shape[0], 1, 1)[:batch].contiguous()
+            work = torch.empty_like(src)
+            info = torch.zeros(batch, dtype=torch.int32, device='cuda')
+            st = torch.cuda.current_stream()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = None
+            for rep in range(4):
+                work.copy_(src)
+                e0.record(st)
+                lib.mrgp_batched_cholesky(C.c_void_p(st.cuda_stream), C.c_void_p(work.data_ptr()), n, batch, C.c_void_p(info.data_ptr()))
+                e1.record(st)
+                e1.synchronize()
+                t = e0.elapsed_time(e1)
+                best = t if best is None or t < best else best
+            gflops = (n ** 3 / 3.0) * batch / (best * 1e-3) / 1e9
+            out.append({'n': n, 'batch': batch, 'ms': round(best, 4), 'gflops': round(gflops, 2),
+                        'frac_fp64_peak': gflops / (fp64_peak_tflops * 1e3), 'gbs': round(2 * n * n * 8 * batch / (best * 1e-3) / 1e9, 1)})
+    return out
+
+
+def extras_single_gpu(args, torch, local_rank, flush):
+    """BASELINE configs 3, 4 (fi) and 5 on the same GPU, short runs: it/s of a sweep, L2 flushed between timed sweeps."""
+    out = {}
+
+    def rate(m, steps=10, warm=4):
+        eng = m._engine
+        eng.sweep(warm)
+        eng.synchronize()
+        ms = timed_sweeps(eng, steps, flush, torch.cuda.synchronize, lambda v: v, torch)
+        return {'it_per_s': steps / (sum(ms) / 1e3), 'ms_per_sweep': float(np.mean(ms)), 'ms_median': float(np.median(ms))}
+    m = make_model(100000, 8, local_rank)
+    out['config3_ci'] = dict(rate(m), workload='N=1e5, 8 resolutions (255 regions), M=30, ci')
+    del m
+    m = make_model(N_SAMPLES, N_LAYERS, local_rank, fi=True)
+    r = rate(m, steps=8, warm=3)
+    r['hbm_gbs_contract'] = BYTES_SWEEP_PER_SAMPLE_LAYER * N_SAMPLES * N_LAYERS / (r['ms_per_sweep'] * 1e-3) / 1e9
+    r['workload'] = 'config 4 in fi mode: every layer streams its samples twice (112 B per sample-layer, SURVEY.md §8d)'
+    out['config4_fi'] = r
+    del m
+    if args.config5_series > 0:
+        out['config5'] = config5(args.config5_series, local_rank, torch)
+    return out
+
+
+def config5(n_series, device, torch, rank=0, world=1, n_iter=6):
+    """Batch of independent series (N = 2048, 6 resolutions, M = 30): seconds per iteration of the whole batch."""
+    import workloads
+    from cimrgp_b200 import LaplacianEigenpairs, MaternKernel, SeriesBatch
+    xs, ys = [], []
+    lo, hi = (rank * n_series) // world, ((rank + 1) * n_series) // world
+    for s in range(lo, hi):
+        x, y = workloads.workload1(2048, seed=10 + s)
+        xs.append(x)
+        ys.append(y)
+    res = {'series_total': n_series, 'series_this_rank': hi - lo, 'workload': 'N=2048, 6 resolutions (63 regions), M=30 per series'}
+    for fi in (False, True):
+        t0 = time.perf_counter()
+        batch = SeriesBatch(xs, ys, N_BASIS, 5, LaplacianEigenpairs(), MaternKernel(nu=1, l=1, sf=1), forced_independence=fi, device=device)
+        t_build = time.perf_counter() - t0
+        batch.fit(3)
+        torch.cuda.synchronize()
+        l0 = batch.launch_count()
+        t0 = time.perf_counter()
+        batch.fit(n_iter)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_iter
+        res['fi' if fi else 'ci'] = {'ms_per_batch_iteration': 1e3 * dt, 'series_sweeps_per_s': (hi - lo) / dt,
+                                     'launches_per_iteration': (batch.launch_count() - l0) / n_iter, 'build_s': t_build}
+        batch.close()
+        del batch
+    return res
+
+
 def run_gpu(args, rank, world, local_rank):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     multi = world > 1
     if multi:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    # strong scaling: the N = 1e6 problem is split into contiguous sample chunks, one per GPU
-    m = make_model(N_SAMPLES, local_rank, args.ctas, distributed=multi)
+    # strong scaling: the samples of the N = 1e6 problem are split into contiguous chunks, one per GPU; the small-matrix
+    # state is replicated.  In the fused ci sweep no sample-parallel work is left in the steady state (DESIGN.md §5).
+    m = make_model(N_SAMPLES, N_LAYERS, local_rank, distributed=multi)
     eng = m._engine
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
-    peak, peak_src = peak_hbm()
+    peak, peak_src = peaks()
 
     def barrier():
         torch.cuda.synchronize()
@@ -200,122 +379,51 @@ def run_gpu(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(max(args.warmup, 3)):
-        eng.sweep(1)
+    warm = max(args.warmup, 3)
+    eng.sweep(warm)
     eng.synchronize()
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # ---- device-resident timing: K sweeps, L2 flushed between steps ------------------------------
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # ---- device-resident timing -------------------------------------------------------------------------------
     l0 = eng.launch_count()
-    barrier()
-    for k in range(args.steps):
-        # the L2 flush (256 MB of HBM writes on torch's stream) must neither overlap the sweep before it nor the one
-        # after it: it starts when the previous timed sweep is over and ends before the next timed region starts
-        torch.cuda.current_stream().wait_stream(eng.stream)
-        flush.zero_()
-        eng.stream.wait_stream(torch.cuda.current_stream())
-        barrier()
-        ev[k][0].record(eng.stream)
-        eng.sweep(1)
-        ev[k][1].record(eng.stream)
-    barrier()
+    step_ms = timed_sweeps(eng, args.steps, flush, barrier, max_over_ranks, torch)
     launches = eng.launch_count() - l0
-    exchange = getattr(eng, 'exchange', None)
-    if multi and exchange == 'nccl':
-        launches = 80 * args.steps   # per rank and sweep: 10 x (phase A, sums, mid, omega, phase B, sums, bias/noise) + NCCL
-    step_ms = [max_over_ranks(a.elapsed_time(b)) for a, b in ev]
     total_s = sum(step_ms) / 1e3
     value = args.steps / total_s
 
-    # ---- end to end through the public API: pinned host -> device, sweep, ELBO terms back ----------
+    # ---- end to end through the public API: new observations from pinned host memory, statistics pass, sweep, ELBO back
     e2e = None
     if not args.no_e2e:
         e2e_ms = []
-        n_local = eng.N
         for k in range(args.steps):
+            torch.cuda.current_stream().wait_stream(eng.stream)
             flush.zero_()
             eng.stream.wait_stream(torch.cuda.current_stream())
             barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(eng.stream)
-            eng.upload_observations()          # H2D of this rank's rows of y (n,2) from pinned memory
-            m.fit(n_iter=1, tol=1e-300, min_iter=1)    # one sweep + the six ELBO terms per layer, read back
+            eng.upload_observations()                      # H2D of this rank's rows of y (n, 2) from pinned memory
+            m.fit(n_iter=1, tol=1e-300, min_iter=1)        # statistics pass + one sweep + the six ELBO terms per layer, read back
             b.record(eng.stream)
             b.synchronize()
             e2e_ms.append(max_over_ranks(a.elapsed_time(b)))
-        e2e = {'value': args.steps / (sum(e2e_ms) / 1e3), 'unit': 'it/s',
-               'h2d_bytes_per_step': n_local * DY * 8, 'd2h_bytes_per_step': N_LAYERS * 6 * 8,
-               'ms_per_step': float(np.mean(e2e_ms)), 'lower_bound_layer0': m.lower_bound_layer[0][-1]}
+        e2e = {'value': args.steps / (sum(e2e_ms) / 1e3), 'unit': 'it/s', 'h2d_bytes_per_step': eng.N * DY * 8,
+               'd2h_bytes_per_step': N_LAYERS * 6 * 8, 'ms_per_step': float(np.mean(e2e_ms)),
+               'what': 'new observations y every step at UNCHANGED inputs x (x-derived tables are reused; new inputs need the '
+                       'basis rebuilt, include/cimrgp.h): y from pinned host memory, layer-0 statistics pass over x and y, one '
+                       'sweep, ELBO terms back',
+               'lower_bound_layer0': m.lower_bound_layer[0][-1]}
     clocks = sampler.stop() if rank == 0 else None
-    if multi:
-        if rank == 0:
-            line = {
-                'metric': 'ciMRGP VI iters/sec at N=1e6, R=10', 'value': value, 'unit': 'it/s', 'n_gpus': world,
-                'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * total_s / args.steps,
-        'step_ms': [round(v, 4) for v in step_ms],
-                'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-                'config': {'workload': WORKLOAD, 'l2': 'flushed between timed steps (256 MB write)',
-                           'parallelism': ('samples sharded in %d contiguous chunks; 2 exchanges of <= 245 KB of region '
-                                           'statistics per layer, ' % world) +
-                                          ('own kernels over NVLink peer memory, whole sweep in one CUDA graph'
-                                           if exchange == 'peer' else 'NCCL all-reduce'),
-                           'exchange': exchange},
-                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
-                'roofline': {'bound': 'hbm', 'achieved': BYTES_SWEEP_PER_SAMPLE_LAYER * N_SAMPLES * N_LAYERS / (total_s / args.steps) / 1e9,
-                             'peak': peak * world, 'peak_source': peak_src, 'unit': 'GB/s',
-                             'frac': BYTES_SWEEP_PER_SAMPLE_LAYER * N_SAMPLES * N_LAYERS / (total_s / args.steps) / 1e9 / (peak * world),
-                             'traffic': None, 'note': 'whole-sweep algorithmic bytes (112 B per sample-layer) over all GPUs'},
-                'cpu_baseline': None,
-            }
-            print(json.dumps(_finite(line)))
-            sys.stdout.flush()
-        # leave without running destructors: tearing down a process group whose collectives live in a captured CUDA
-        # graph can block at interpreter exit
-        barrier()
-        sys.stdout.flush()
-        os._exit(0)
 
-    # ---- per-kernel timing for the roofline ----------------------------------------------------------
-    # The captured ci sweep streams the samples on layer 0 only (phase A and phase B over x and y); the layers above
-    # take their statistics in closed form and every other kernel is a latency-bound small-matrix step.
-    # Phase A of layer 0 is the same kernel in the sweep and behind mrgp_phase_a: it is timed alone with CUDA events
-    # on the engine stream, L2 flushed before every launch.
-    import ctypes as C
-    dom_samples = []
-    for _ in range(7):
-        flush.zero_()
-        eng.stream.wait_stream(torch.cuda.current_stream())
-        dom_samples += time_phase(eng, eng.phase_a, 0, torch, 1)
-    dom_ms = float(np.median(dom_samples))
-    dom_bytes = 24 * N_SAMPLES           # x (8) + y (16) per sample; layer 0 has no latent input
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    # where the time of one sweep goes: global-timer stamps written by the kernels inside the captured graph
-    eng.lib.mrgp_timeline_enable(eng.handle, 1)
-    eng.sweep(2)
-    eng.synchronize()
-    tags, tms = (C.c_int32 * 128)(), (C.c_float * 256)()
-    eng.lib.mrgp_timeline_read(eng.handle, tags, tms, 128)
-    eng.lib.mrgp_timeline_enable(eng.handle, 0)
-    def stamp(j, k):
-        b, e = tms[2 * (4 * j + k)], tms[2 * (4 * j + k) + 1]
-        return None if b < 0 else [round(1e3 * b, 1), round(1e3 * e, 1)]
-    timeline = {name: [stamp(j, k) for j in range(N_LAYERS)]
-                for k, name in enumerate(('phase_a', 'mid', 'phase_b_or_closed_form', 'omega_side_stream'))}
-    ends = [v[1] for rows in timeline.values() for v in rows if v]
-    sweep_us = max(ends) if ends else None
-    stream_us = sum(v[1] - v[0] for v in (timeline['phase_a'][0], timeline['phase_b_or_closed_form'][0]) if v)
-    roofline = {'bound': 'hbm', 'kernel': 'k_phase_a<2,30,observed targets,no latent input> (layer 0)', 'achieved': achieved,
-                'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': 24041216, 'traffic_source': 'ncu --set full, profiles/r01_ncu_summary.md',
-                'bytes_per_launch': dom_bytes, 'ms_per_launch': dom_ms,
-                'note': 'FP64-bound kernel (see fp64); the sweep is dominated by latency-bound small-matrix kernels',
-                'sweep_timeline_us': timeline, 'sweep_us_in_graph_warm_l2': sweep_us,
-                'streaming_share_of_sweep': (stream_us / sweep_us) if sweep_us else None}
-    # FP64 pipe: measured DFMA peak next to the FMA count of that kernel (6 per basis function and sample:
-    # recurrence 1 and Phi A 2 in the first pass, recurrence 1 and Phi^T r 2 in the second; + ~40 for sincospi)
+    # ---- kernels -------------------------------------------------------------------------------------------------
+    # k_ystats: the streaming pass of the path (per data set; every step of e2e).  Timed alone, L2 flushed before each launch.
+    ys_ms = [max_over_ranks(v) for v in time_call(eng, eng.refresh_statistics, flush, torch, 7)]
+    ys_med = float(np.median(ys_ms))
+    ys_bytes = 24 * eng.N                                  # x (8) + y (16) per sample
+    achieved = ys_bytes / (ys_med * 1e-3) / 1e9
+    # k_ci_sweep: the whole steady-state sweep, warm L2 (back-to-back sweeps as in fit(n_iter))
+    warm_ms = [max_over_ranks(v) for v in time_call(eng, lambda: eng.sweep(1), None, torch, 9)]
     sink = torch.zeros(8, dtype=torch.float64, device='cuda')
     ms = C.c_float()
     iters = 200000
@@ -323,31 +431,84 @@ def run_gpu(args, rank, world, local_rank):
     eng.lib.mrgp_fp64_probe(None, iters, C.c_void_p(sink.data_ptr()), C.byref(ms))
     sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     fp64_peak = sms * 4 * 256 * iters * 8 * 2 / (ms.value * 1e-3) / 1e12
-    dom_flops = (6 * N_BASIS + 40) * 2 * N_SAMPLES
-    roofline['fp64'] = {'peak_tflops_measured': fp64_peak, 'achieved_tflops': dom_flops / (dom_ms * 1e-3) / 1e12,
-                        'frac': dom_flops / (dom_ms * 1e-3) / 1e12 / fp64_peak}
+    ys_flops = (3 * N_BASIS + 22 + 5) * 2 * eng.N          # per sample: recurrence M, Phi^T y 2M, sincospi 22, sums 5 (FMA = 2 flop)
+    roofline = {
+        'bound': 'hbm', 'kernel': 'k_ystats<2,30> (layer-0 sufficient statistics of y: the streaming kernel of the path)',
+        'achieved': achieved * (world if multi else 1), 'peak': peak * (world if multi else 1), 'peak_source': peak_src, 'unit': 'GB/s',
+        'frac': achieved / peak,
+        'traffic': ncu_traffic('k_ystats'), 'traffic_source': 'ncu --set full, profiles/r02_ncu_traffic.json',
+        'bytes_per_launch': ys_bytes, 'ms_per_launch': ys_med,
+        'fp64': {'peak_tflops_measured': fp64_peak, 'achieved_tflops': ys_flops / (ys_med * 1e-3) / 1e12,
+                 'frac': ys_flops / (ys_med * 1e-3) / 1e12 / fp64_peak},
+        'sweep_kernel': {'kernel': 'k_ci_sweep<30> (one cluster of %s CTAs, all 10 layers)' % os.environ.get('MRGP_CHAIN_CLUSTER', '16'),
+                         'ms_warm_l2': float(np.median(warm_ms)), 'ms_flushed_l2_median': float(np.median(step_ms)),
+                         'traffic': ncu_traffic('k_ci_sweep'),
+                         'note': 'latency-bound chain of small-matrix steps (Bingham, ARD, omega): no sample is read; the '
+                                 '112 B per sample-layer of SURVEY.md §8d are not moved any more'},
+    }
+    if multi:
+        line = None
+        if rank == 0:
+            serial_us, shard_us = 1e3 * float(np.median(warm_ms)), 1e3 * ys_med * world
+            line = {
+                'metric': METRIC, 'value': value, 'unit': 'it/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warm,
+                'ms_per_step': 1e3 * total_s / args.steps, 'ms_per_step_median': float(np.median(step_ms)),
+                'step_ms': [round(v, 4) for v in step_ms],
+                'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': dict(CONFIG, parallelism='samples sharded in %d contiguous chunks (x, y never leave their GPU); the '
+                               'small-matrix sweep is replicated; one exchange of 63 doubles per data set (layer-0 statistics) over '
+                               'NVLink peer memory, none per sweep' % world),
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': None,
+                'amdahl': {'serial_us': serial_us, 'shardable_us_one_gpu': shard_us,
+                           'note': 'steady-state ci sweep: only the replicated chain is left (serial_us); the sharded work is the '
+                                   'statistics pass per data set (e2e). Strong scaling of `value` is therefore flat by construction; '
+                                   'e2e and the series batch (extras) are where more GPUs pay'},
+            }
+        extras = None
+        if args.config5_series > 0 and not args.no_extras:
+            torch.cuda.synchronize()
+            c5 = config5(args.config5_series, local_rank, torch, rank=rank, world=world)
+            # whole-job throughput: series of all ranks / slowest rank
+            t = torch.tensor([c5['ci']['ms_per_batch_iteration'], c5['fi']['ms_per_batch_iteration']], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            extras = {'config5_series_sharded': {'series_total': args.config5_series, 'ranks': world, 'collectives': 'none (replicas only)',
+                                                 'ci_ms_per_batch_iteration': float(t[0]), 'ci_series_sweeps_per_s': args.config5_series / (float(t[0]) * 1e-3),
+                                                 'fi_ms_per_batch_iteration': float(t[1]), 'fi_series_sweeps_per_s': args.config5_series / (float(t[1]) * 1e-3)}}
+        if rank == 0:
+            line['extras'] = extras
+            print(json.dumps(_finite(line)))
+            sys.stdout.flush()
+        barrier()
+        eng.close()
+        sys.stdout.flush()
+        os._exit(0)
 
     cpu = None
     if not args.no_cpu_baseline:
-        n_sample = 200000
-        times, t_fixed = oracle_sample(n_sample, 1)
-        cpu_value = scaled_rate(times[0], t_fixed, n_sample)
-        cpu = {'value': cpu_value, 'unit': 'it/s', 'cores': 1, 'kind': 'port', 'host_cores': os.cpu_count(),
-               'sample': 'one oracle sweep (NumPy port of MRGP._fit) on N=%d of the same signal, 10 layers, M=30: '
-                         '%.1fs, of which %.1fs in the N-independent fsolve; scaled to N=1e6 as '
-                         '1/(t_omega + (t - t_omega) * 5)' % (n_sample, times[0], t_fixed)}
-
+        times, threads, t_ctor = port_sweeps(N_SAMPLES, N_LAYERS, 1, 5)
+        cpu = {'value': 5 / float(np.sum(times)), 'unit': 'it/s', 'cores': threads, 'kind': 'port', 'host_cores': os.cpu_count(),
+               'sample': '5 full sweeps at the stated config (N=1e6, 10 layers) of oracle/mrgp_port.c, OpenMP over %d threads, %.2f s per '
+                         'sweep; not extrapolated' % (threads, float(np.mean(times)))}
+    chol_total = eng.cholesky_count()
+    omega_iters = [int(v) for v in eng.get(-1, 51, (N_LAYERS,))]
+    extras = None if args.no_extras else extras_single_gpu(args, torch, local_rank, flush)
+    grid = None if args.no_extras else cholesky_grid(eng.lib, torch, fp64_peak)
     line = {
-        'metric': 'ciMRGP VI iters/sec at N=1e6, R=10', 'value': value, 'unit': 'it/s', 'n_gpus': 1,
-        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * total_s / args.steps,
+        'metric': METRIC, 'value': value, 'unit': 'it/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': warm,
+        'ms_per_step': 1e3 * total_s / args.steps, 'ms_per_step_median': float(np.median(step_ms)),
+        'ms_per_step_settled': float(np.mean(step_ms[len(step_ms) // 2:])),
         'step_ms': [round(v, 4) for v in step_ms],
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'l2': 'flushed between timed steps (256 MB write)',
-                   'n_ctas': eng.lib and args.ctas or 'one persistent CTA per SM'},
-        'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
-        'omega_iters_last_sweep': [int(v) for v in eng.get(-1, 51, (N_LAYERS,))],
-        'batched_cholesky': {'count_total': eng.cholesky_count(), 'n': DY,
-                             'note': 'dy x dy PD guard inside k_mid2; < 1% of a sweep'},
+        'config': CONFIG, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
+        'omega_iters_last_sweep': omega_iters,
+        'batched_cholesky': {
+            'in_sweep': {'n': DY, 'factorisations_per_sweep': N_BASIS * N_LAYERS,
+                         'gflops': (DY ** 3 / 3.0) * N_BASIS * N_LAYERS / (float(np.median(step_ms)) * 1e-3) / 1e9,
+                         'count_total': chol_total,
+                         'note': 'the path has one Cholesky: the dy x dy PD test of the Bingham update (SanityCheck.py:59-65), M per '
+                                 'layer in ci mode; it lives in registers inside k_ci_sweep and is < 1 % of a sweep'},
+            'unit': 'GFLOP/s (n^3 / 3 per matrix)', 'fp64_peak_tflops_measured': fp64_peak, 'grid': grid},
+        'extras': extras,
     }
     print(json.dumps(_finite(line)))
 
@@ -358,9 +519,11 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
-    ap.add_argument('--ctas', type=int, default=0)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true')
+    ap.add_argument('--no-calibration', action='store_true')
+    ap.add_argument('--config5-series', type=int, default=1024, help='series of the config-5 extra (BASELINE: 4096)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

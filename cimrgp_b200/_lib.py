@@ -67,6 +67,7 @@ SIGNATURES = {
     'mrgp_interval_failures': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     'mrgp_learn_intervals': (C.c_int, [_P, C.c_int32]),
     'mrgp_sweep': (C.c_int, [_P, C.c_int32]),
+    'mrgp_refresh_statistics': (C.c_int, [_P]),
     'mrgp_group_create': (C.c_int, [C.POINTER(_P), C.c_int32, _P, C.POINTER(_P)]),
     'mrgp_group_sweep': (C.c_int, [_P, C.c_int32]),
     'mrgp_group_observations_changed': (C.c_int, [_P]),

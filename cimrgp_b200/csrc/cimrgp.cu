@@ -1903,6 +1903,16 @@ int mrgp_interval_failures(mrgp_handle *h, uint64_t *out) {
     return MRGP_OK;
 }
 
+int mrgp_refresh_statistics(mrgp_handle *h) {
+    int rc = check_ready(h, 0, true);
+    if (rc) return rc;
+    h->stream_ops += 1;
+    if (!use_fused(h)) return MRGP_OK;   // the multi-kernel sweep streams layer 0: nothing to prepare
+    if ((rc = build_invariants(h))) return rc;
+    if (!h->chain_uploaded && (rc = upload_chain_model(h))) return rc;
+    return do_ystats(h);
+}
+
 int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
     if (h) h->stream_ops += 1;
     int rc = check_ready(h, 0, true);
@@ -2493,8 +2503,22 @@ int64_t mrgp_cholesky_count(mrgp_handle *h) {
 int mrgp_batched_cholesky(void *cuda_stream, double *a_dev, int32_t n, int64_t batch, int32_t *info_dev) {
     mrgp_handle *h = nullptr;
     if (!a_dev || !info_dev || n < 1 || n > 32 || batch < 1) return fail(h, MRGP_EINVAL, "bad argument");
-    const int64_t threads = batch * 32;
-    k_batched_cholesky<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a_dev, n, batch, info_dev);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const unsigned small_grid = (unsigned)((batch + 255) / 256);
+    switch (n) {   // n <= 8: one thread per matrix; larger: one warp per matrix
+        case 1: k_batched_cholesky_small<1><<<small_grid, 256, 0, st>>>(a_dev, batch, info_dev); break;
+        case 2: k_batched_cholesky_small<2><<<small_grid, 256, 0, st>>>(a_dev, batch, info_dev); break;
+        case 3: k_batched_cholesky_small<3><<<small_grid, 256, 0, st>>>(a_dev, batch, info_dev); break;
+        case 4: k_batched_cholesky_small<4><<<small_grid, 256, 0, st>>>(a_dev, batch, info_dev); break;
+        case 5: k_batched_cholesky_small<5><<<small_grid, 256, 0, st>>>(a_dev, batch, info_dev); break;
+        case 6: k_batched_cholesky_small<6><<<small_grid, 256, 0, st>>>(a_dev, batch, info_dev); break;
+        case 7: k_batched_cholesky_small<7><<<small_grid, 256, 0, st>>>(a_dev, batch, info_dev); break;
+        case 8: k_batched_cholesky_small<8><<<small_grid, 256, 0, st>>>(a_dev, batch, info_dev); break;
+        default: {
+            const int64_t threads = batch * 32;
+            k_batched_cholesky<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a_dev, n, batch, info_dev);
+        }
+    }
     CK(cudaGetLastError());
     return MRGP_OK;
 }

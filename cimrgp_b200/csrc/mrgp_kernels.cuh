@@ -2969,6 +2969,38 @@ __global__ void k_batched_cholesky(double *a, int n, int64_t batch, int32_t *inf
     if (lane == 0) info[w] = bad;
 }
 
+// Small matrices (n <= 8): one THREAD per matrix, the factor in registers (a warp per 2 x 2 matrix would leave 31 lanes
+// idle; the PD guard of the model, SanityCheck.py:59-65, is this case with n = dy).  Same conventions as above.
+template <int N>
+__global__ void __launch_bounds__(256) k_batched_cholesky_small(double *a, int64_t batch, int32_t *info) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    double *A = a + b * (N * N);
+    double L[N][N];
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) L[r][c] = c <= r ? A[r * N + c] : 0.0;
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double piv = L[k][k];
+        if (!(piv > 0.0) && bad == 0) bad = k + 1;
+        const double rp = bad == 0 ? rsqrt(piv) : 0.0;
+#pragma unroll
+        for (int r = k; r < N; ++r) L[r][k] *= rp;
+#pragma unroll
+        for (int c = k + 1; c < N; ++c)
+#pragma unroll
+            for (int r = c; r < N; ++r) L[r][c] = fma(-L[r][k], L[c][k], L[r][c]);
+    }
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) A[r * N + c] = L[r][c];
+    info[b] = bad;
+}
+
 __global__ void k_fp64_probe(int64_t iters, double *sink) {
     double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
     double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;

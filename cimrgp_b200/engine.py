@@ -185,6 +185,10 @@ class Engine(object):
         self._ck(self.lib.mrgp_interval_failures(self.handle, C.byref(out)))
         return int(out.value)
 
+    def refresh_statistics(self):
+        """Layer-0 sufficient statistics of the fused ci sweep, now (mrgp_sweep does it on demand otherwise)."""
+        self._ck(self.lib.mrgp_refresh_statistics(self.handle))
+
     def sweep(self, n_iter=1):
         self._ck(self.lib.mrgp_sweep(self.handle, int(n_iter)))
 

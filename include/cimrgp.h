@@ -192,6 +192,12 @@ int mrgp_interval_failures(mrgp_handle *h, uint64_t *out);
  * residual vanishes identically and their P4 / P5 sums are evaluated in closed form from basis invariants built
  * on the first call; MRGP_STREAM_ALL=1 in the environment streams every layer.        */
 int mrgp_sweep(mrgp_handle *h, int32_t n_iter);
+/* The fused ci sweep (ci mode, static intervals, region-specific noise and bias, n_basis <= 32: one kernel per sweep,
+ * DESIGN.md §4) reads layer 0 through the sufficient statistics of its observations, Phi^T y, sum y, sum |y|^2: one
+ * pass over x and y (24 B per sample) whenever the observations, the inputs or the intervals of layer 0 changed.
+ * mrgp_sweep refreshes them on demand; this entry does it now (asynchronously on the handle's stream), e.g. right after
+ * mrgp_set_observations_host.  A no-op for models that take the multi-kernel sweep.                             */
+int mrgp_refresh_statistics(mrgp_handle *h);
 int mrgp_synchronize(mrgp_handle *h);
 
 /* E1-E6: the six ELBO terms per layer, out_host (J, 6) in the order data, scale|axis, axis, ard, bias,
