@@ -181,6 +181,9 @@ class MultiResolutionGaussianProcess(object):
         self.lower_bound_layer = [[] for _ in range(self.n_layers)]
         self.lower_bound = []
         self.lower_bound_terms = []
+        self._noise_var0 = noise_var0
+        self._ard_prior_influence = float(np.mean(sf))
+        self._sweeps = 0
 
     # ------------------------------------------------------------------------------------------
     def _normalize_inputs(self, x_train, full_x):
@@ -211,15 +214,18 @@ class MultiResolutionGaussianProcess(object):
         if tol is None:
             self._engine.sweep(n_iter)
             self._engine.synchronize()
+            self._sweeps += n_iter
             return
         if self.forced_independence:
             self._engine.sweep(n_iter)      # MRGP.py:400-401: no bound, no early stop in fi mode
             self._engine.synchronize()
+            self._sweeps += n_iter
             return
         if n_iter < min_iter:
             min_iter = n_iter
         for iter_ in range(1, n_iter + 1):
             self._engine.sweep(1)
+            self._sweeps += 1
             lower_bound, lower_bound_layer = self._compute_lower_bound()
             self.lower_bound.append(lower_bound)
             for j in range(self.n_layers):
@@ -237,9 +243,11 @@ class MultiResolutionGaussianProcess(object):
 
     def _fit(self):
         self._engine.sweep(1)
+        self._sweeps += 1
 
     def _independent_fit(self):
         self._engine.sweep(1)
+        self._sweeps += 1
 
     def _compute_lower_bound(self, prime_shared_posterior=None):
         # MRGP.py:414-424; the six terms per layer are kept in lower_bound_terms
@@ -427,6 +435,93 @@ class MultiResolutionGaussianProcess(object):
     @property
     def get_stats(self):
         return self.stats_obj
+
+    # ---- priors (Priors.py; non-informative initialisation only, as in the reference) -----------------------------
+    def _bingham_prior(self):
+        """Bingham(0) of Priors.py:29-36 / :168-189: kappa = 0, rho = 1 / dy, axes = I, log C = log of the sphere's
+        area (the saddle-point value the reference stores, computeRealBinghamConstant.py)."""
+        import ctypes as C
+        dy = self.dy
+        if dy != 2:
+            raise NotImplementedError('dy == 2 on the device path')
+        b = np.zeros(4)
+        out = np.zeros(4)
+        kappa, rho, logc, cov = np.zeros(2), np.zeros(2), C.c_double(), np.zeros(4)
+        D = C.POINTER(C.c_double)
+        _lib.load().mrgp_host_bingham2(b.ctypes.data_as(D), out.ctypes.data_as(D), kappa.ctypes.data_as(D), rho.ctypes.data_as(D),
+                                       C.byref(logc), cov.ctypes.data_as(D), None)
+        return kappa, rho, float(logc.value)
+
+    @property
+    def shared_prior(self):
+        """SharedPrior (Priors.py:8-53), MRGP.py:183-186."""
+        self._require_ci()
+        M, dy = self.n_basis, self.dy
+        kappa, rho, logc = self._bingham_prior()
+        shape = 1e-45 * np.ones(M)
+        return _View(self, {}, dict(
+            n_basis=M, dy=dy, axis_bingham_b=np.zeros((M, dy, dy)), axis_bingham_kappa=np.tile(kappa, (M, 1)),
+            axis_bingham_rho=np.tile(rho, (M, 1)), axis_bingham_axes=np.tile(np.eye(dy), (M, 1, 1)),
+            axis_bingham_log_const=np.full(M, logc), ard_gamma_shape=shape, ard_gamma_scale=shape / self._ard_prior_influence))
+
+    @property
+    def prior_obj(self):
+        """Prior / IndependentPrior per layer (Priors.py:56-278), MRGP.py:187-226."""
+        M, dy = self.n_basis, self.dy
+        out = []
+        for j in range(self.n_layers):
+            R = self.n_regions[j]
+            S = self._engine.get(j, _lib.F_SPECTRAL, (R, M))
+            noise_var = self._noise_var0 if j == 0 else 1.0
+            noise_scale, noise_shape = (1e-45 + 1) * noise_var, 1e-45                       # Priors.py:103-109
+            consts = dict(
+                n_basis=M, dy=dy, n_regions=R, scale_precision=[1 / S[l] for l in range(R)],                      # :74-78
+                noise_region_specific=self.noise_region_specific, bias_region_specific=self.bias_region_specific,
+                noise_gamma_scale=[noise_scale] * R if self.noise_region_specific else noise_scale,
+                noise_gamma_shape=[noise_shape] * R if self.noise_region_specific else noise_shape,
+                bias_normal_mean=[np.zeros(dy) for _ in range(R)] if self.bias_region_specific else np.zeros(dy),   # :132-135
+                bias_normal_precision=[1e-45] * R if self.bias_region_specific else 1e-45)
+            if self.forced_independence:
+                kappa, rho, logc = self._bingham_prior()
+                shape = 1e-45 * np.ones(M)
+                consts.update(
+                    axis_bingham_b=[np.zeros((M, dy, dy)) for _ in range(R)], axis_bingham_kappa=[np.tile(kappa, (M, 1)) for _ in range(R)],
+                    axis_bingham_rho=[np.tile(rho, (M, 1)) for _ in range(R)], axis_bingham_axes=[np.tile(np.eye(dy), (M, 1, 1)) for _ in range(R)],
+                    axis_bingham_log_const=[np.full(M, logc) for _ in range(R)], ard_gamma_shape=[shape.copy() for _ in range(R)],
+                    ard_gamma_scale=[shape / self._ard_prior_influence for _ in range(R)])
+            out.append(_View(self, {}, consts))
+        return out
+
+    # ---- targets of the last sweep (MRGP.py:650-652, kept there for the lower bound) --------------------------------
+    @property
+    def y_mean(self):
+        """y_mean[j][l]: empty lists before the first sweep (MRGP.py:262-271); afterwards the observations at layer 0
+        (LatentOutputs.py:6-9: ONE entry holding all of Y), in fi mode the observations of the region
+        (LatentOutputs.py:11-18), in ci mode the targets inferred from the layer's own posterior BEFORE its update,
+        Phi A_old^T + (b_old + latent_f_mean) (LatentOutputs.py:25-40), rebuilt on the host on demand."""
+        if self._sweeps == 0:
+            return [[[] for _ in range(R)] for R in self.n_regions]
+        out = []
+        phi = None
+        for j in range(self.n_layers):
+            R, M, dy = self.n_regions[j], self.n_basis, self.dy
+            if self.forced_independence:
+                out.append(self._split(j, self.observations))
+            elif j == 0:
+                out.append([self.observations] + [[] for _ in range(R - 1)])
+            else:
+                phi = self.phi_x if phi is None else phi
+                a_old = self._engine.get(j, _lib.F_A_PREV, (R, M, dy))
+                b_old = self._engine.get(j, _lib.F_BIAS_PREV, (R, dy))
+                fbar = self._split(j, self._engine.latent(j)[0])
+                out.append([phi[j][l] @ a_old[l] + (b_old[l] + fbar[l]) for l in range(R)])
+        return out
+
+    @property
+    def y_var(self):
+        if self._sweeps == 0:
+            return [[[] for _ in range(R)] for R in self.n_regions]
+        return [list(self._engine.get(j, _lib.F_YVAR, (self.n_regions[j],))) for j in range(self.n_layers)]
 
     def _require_ci(self):
         if self.forced_independence:

@@ -17,7 +17,7 @@ OK, EINVAL, ENODEVICE, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4, -5
 F_L, F_LAMBDA, F_SPECTRAL, F_PHI2SUM = 1, 2, 3, 4
 F_SCALE_PRECISION, F_ZETA, F_YTILDE, F_NOISE_SHAPE, F_NOISE_SCALE, F_BIAS_PRECISION = 10, 11, 12, 13, 14, 15
 F_A, F_M2, F_CM2, F_NOISE_MEAN, F_NOISE_LOG_MEAN, F_BIAS_MEAN, F_BIAS_VAR = 20, 21, 22, 23, 24, 25, 26
-F_FBAR, F_FVAR, F_YVAR, F_PHASE_B_SUMS = 27, 28, 29, 30
+F_FBAR, F_FVAR, F_YVAR, F_PHASE_B_SUMS, F_A_PREV, F_BIAS_PREV = 27, 28, 29, 30, 31, 32
 F_AXIS_B, F_AXIS_KAPPA, F_AXIS_RHO, F_AXIS_LOGC, F_AXIS_COV = 40, 41, 42, 43, 44
 F_ARD_SHAPE, F_ARD_SCALE, F_ARD_MEAN, F_ARD_LOG_MEAN, F_OMEGA, F_LOG_OMEGA_HAT = 45, 46, 47, 48, 49, 50
 F_OMEGA_ITERS = 51

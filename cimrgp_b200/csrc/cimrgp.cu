@@ -180,7 +180,10 @@ int fail(mrgp_handle *h, int code, const char *fmt, ...) {
         if (e_ != cudaSuccess) return fail(h, MRGP_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-bool basis_supported(int m) { return m == 8 || m == 20 || m == 30 || m == 40; }
+// Any number of basis functions up to 48: the streaming kernels are instantiated for 8, 20, 30, 40 and 48 functions and a
+// model runs on the smallest instantiation that holds its basis, the extra functions carrying zero weight.
+bool basis_supported(int m) { return m >= 1 && m <= 48; }
+int padded_basis(int m) { return m <= 8 ? 8 : m <= 20 ? 20 : m <= 30 ? 30 : m <= 40 ? 40 : 48; }
 
 // ---- plan -------------------------------------------------------------------------------------
 void build_plan(mrgp_handle *h) {
@@ -276,7 +279,7 @@ size_t carve(mrgp_handle *h, char *base) {
     h->tmp_var = c.take<double>(N);
     h->max_runs = 0;
     for (int j = 0; j < J; ++j) h->max_runs = std::max(h->max_runs, h->plan[j].n_runs);
-    h->part_stride = std::max(M * DY + DY + 2, kPartBStride);   // phase A: M*DY sums; y statistics: M*DY + DY + 1
+    h->part_stride = std::max(padded_basis(M) * DY + DY + 2, kPartBStride);   // phase A: MP*DY sums; y statistics: MP*DY + DY + 1
     h->part = c.take<double>((size_t)h->max_runs * h->part_stride);
     {
         int rmax = 1;
@@ -285,12 +288,12 @@ size_t carve(mrgp_handle *h, char *base) {
     }
     if (!fi) {   // closed-form statistics (layers above the first) and sufficient statistics (layer 0)
         if (h->sharded) h->x_all = c.take<double>((size_t)h->cfg.n_samples * h->cfg.dx);   // replicated inputs: the invariants need every sample
-        const size_t np = (size_t)M * (M + 1) / 2 + M;
+        const size_t MPb = (size_t)padded_basis(M), np = MPb * (MPb + 1) / 2 + MPb;
         size_t need = 0;
         for (int j = 0; j < J; ++j) {
             const size_t blocks = (size_t)h->plan[j].R * build_splits(h->plan[j].R);
             const size_t P = h->plan[j].pc_jp.size();
-            need = std::max(need, std::max(blocks * np, P * build_splits((int)std::max<size_t>(P, 1)) * M));
+            need = std::max(need, std::max(blocks * np, P * build_splits((int)std::max<size_t>(P, 1)) * MPb));
         }
         h->build_part_doubles = need;
         h->build_part = c.take<double>(need);
@@ -449,6 +452,7 @@ StreamArgs stream_args(mrgp_handle *h, int j) {
     a.region_run = d.region_run;
     a.offsets = d.offsets;
     a.R = h->plan[j].R;
+    a.n_basis = h->cfg.n_basis;
     a.infer = (h->cfg.mode == MRGP_MODE_CI && j > 0) ? 1 : 0;
     a.fuse_tail = 0;
     a.layer = j;
@@ -663,11 +667,12 @@ cudaError_t launch_phi2sum(mrgp_handle *h, const StreamArgs &a) {
 }
 
 #define DISPATCH_M(m, expr)                     \
-    switch (m) {                                \
+    switch (padded_basis(m)) {                  \
         case 8: { constexpr int MM = 8; expr; } break;   \
         case 20: { constexpr int MM = 20; expr; } break; \
         case 30: { constexpr int MM = 30; expr; } break; \
         case 40: { constexpr int MM = 40; expr; } break; \
+        case 48: { constexpr int MM = 48; expr; } break; \
         default: break;                         \
     }
 
@@ -1012,7 +1017,7 @@ int launch_build_invariants(mrgp_handle *h, int j) {
     const double *xg = h->sharded ? h->x_all : h->x;   // indexed by the global sample number
     k_build_gram<M><<<blocks, 256, 0, h->stream>>>(xg, d.offsets, d.inv2L, d.rsqrtL, splits, h->build_part);
     CK(cudaGetLastError());
-    k_reduce_gram<<<(lp.R * (NP + M) + 255) / 256, 256, 0, h->stream>>>(h->build_part, splits, lp.R, M, d.gram, d.sumPhi);
+    k_reduce_gram<<<(lp.R * (NP + M) + 255) / 256, 256, 0, h->stream>>>(h->build_part, splits, lp.R, h->cfg.n_basis, M, d.gram, d.sumPhi);
     CK(cudaGetLastError());
     count(h, 2);
     if (j > 0) {
@@ -1023,7 +1028,7 @@ int launch_build_invariants(mrgp_handle *h, int j) {
         const PieceTable pt{d.pc_ptr, d.pc_jp, d.pc_anc, d.pc_lo, d.pc_hi, P};
         k_build_ancD<M><<<P * psplits, 256, 0, h->stream>>>(ea, xg, pt, psplits, h->build_part);
         CK(cudaGetLastError());
-        k_reduce_ancD<<<(P * M + 255) / 256, 256, 0, h->stream>>>(h->build_part, psplits, P, M, d.ancD);
+        k_reduce_ancD<<<(P * h->cfg.n_basis + 255) / 256, 256, 0, h->stream>>>(h->build_part, psplits, P, h->cfg.n_basis, M, d.ancD);
         CK(cudaGetLastError());
         count(h, 2);
     }
@@ -1110,12 +1115,12 @@ int do_ystats(mrgp_handle *h) {
     const int32_t *rr = d.region_run;
     const double *part = h->part;
     if (h->sharded) {   // sum the statistics of the ranks' chunks
-        int rc = do_exchange(h, 0, 0, M * DY + DY + 1, false);
+        int rc = do_exchange(h, 0, 0, padded_basis(M) * DY + DY + 1, false);
         if (rc) return rc;
         rr = d.ident_run;
         part = h->xchg;
     }
-    k_reduce_ystats<<<lp.R, 64, 0, h->stream>>>(rr, part, h->part_stride, lp.R, M, DY, d.yc, d.ysum);
+    k_reduce_ystats<<<lp.R, 64, 0, h->stream>>>(rr, part, h->part_stride, lp.R, M, padded_basis(M), DY, d.yc, d.ysum);
     CK(cudaGetLastError());
     count(h);
     h->ystats_valid = true;
@@ -1330,6 +1335,8 @@ FieldRef field_ref(mrgp_handle *h, int layer, int field) {
         case MRGP_F_FVAR: f = {h->tmp_var, h->cfg.n_samples}; break;
         case MRGP_F_YVAR: f = {d.yvar, R}; break;
         case MRGP_F_PHASE_B_SUMS: f = {d.sumsB, R * (DY + 3)}; break;
+        case MRGP_F_A_PREV: f = {d.A_prev, RM * DY}; break;
+        case MRGP_F_BIAS_PREV: f = {d.bias_prev, R * DY}; break;
         default: break;
     }
     if (fi) {
@@ -1399,7 +1406,7 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     if (cfg->dy < 2) return fail(h, MRGP_EINVAL, "output dimension must be greater than 1");
     if (cfg->dy != 2) return fail(h, MRGP_EINVAL, "dy = %d: only dy == 2 is implemented on the device", cfg->dy);
     if (cfg->dx != 1) return fail(h, MRGP_EINVAL, "dx = %d: only dx == 1 is implemented on the device", cfg->dx);
-    if (!basis_supported(cfg->n_basis)) return fail(h, MRGP_EINVAL, "n_basis = %d: compiled for 8, 20, 30, 40", cfg->n_basis);
+    if (!basis_supported(cfg->n_basis)) return fail(h, MRGP_EINVAL, "n_basis = %d: 1 .. 48 basis functions are supported", cfg->n_basis);
     if (cfg->n_layers < 1 || cfg->n_layers > kMaxLayers) return fail(h, MRGP_EINVAL, "n_layers out of range");
     if (cfg->n_samples < 1) return fail(h, MRGP_EINVAL, "n_samples < 1");
     if (cfg->sample_begin < 0 || cfg->sample_end < cfg->sample_begin || cfg->sample_end > cfg->n_samples)

@@ -81,6 +81,8 @@ struct StreamArgs {
     const int32_t *region_run;   // (R + 1)
     const int64_t *offsets;      // (R + 1)
     int32_t R, infer, fuse_tail, layer;
+    int32_t n_basis;             // basis functions of the model; the kernels are instantiated for a padded M >= n_basis and
+                                 // treat the extra functions as zero-weight (their sums are never read)
     unsigned long long *ts;
     const double *bias_prec0, *bias_mean0, *noise_shape0, *noise_scale0;
     int32_t sums_only;               // bias_noise_*: only store the per-region sums in sumsB
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_phase_a(StreamArgs p) {
         while (pos < tile_hi) {
             if (loaded != s) {
                 __syncwarp();
-                for (int q = lane; q < M * DY; q += 32) sA[q] = p.A[(size_t)sg.region * (M * DY) + q];
+                for (int q = lane; q < M * DY; q += 32) sA[q] = q < p.n_basis * DY ? p.A[(size_t)sg.region * (p.n_basis * DY) + q] : 0.0;
                 inv2L = p.inv2L[sg.region];
                 rs = p.rsqrtL[sg.region];
 #pragma unroll
@@ -638,15 +640,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_ystats(StreamArgs p) {
 }
 
 // yc[r][i][d], ysum[r][0..DY] = sums over the region's runs of the k_ystats partials (fixed order).
-__global__ void k_reduce_ystats(const int32_t *region_run, const double *part, int part_stride, int R, int M, int DY, double *yc, double *ysum) {
-    const int r = blockIdx.x, nv = M * DY + DY + 1;
+// (MP: the padded number of basis functions the partials were written for.)
+__global__ void k_reduce_ystats(const int32_t *region_run, const double *part, int part_stride, int R, int M, int MP, int DY, double *yc, double *ysum) {
+    const int r = blockIdx.x, nv = MP * DY + DY + 1;
     for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        if (v >= M * DY && v < MP * DY) continue;
         double s = 0.0;
         for (int q = region_run[r]; q < region_run[r + 1]; ++q) s += part[(size_t)q * part_stride + v];
         if (v < M * DY)
             yc[(size_t)r * M * DY + v] = s;
         else
-            ysum[(size_t)r * 4 + (v - M * DY)] = s;
+            ysum[(size_t)r * 4 + (v - MP * DY)] = s;
     }
 }
 
@@ -776,10 +780,11 @@ __global__ void __launch_bounds__(kThreadsB, 1) k_phase_b(StreamArgs p) {
             if (loaded != s) {
                 __syncwarp();
                 for (int q = lane; q < M * DY; q += 32) {
-                    sAn[q] = p.A[(size_t)sg.region * (M * DY) + q];
-                    if (INFER) sAo[q] = p.A_prev[(size_t)sg.region * (M * DY) + q];
+                    const bool real = q < p.n_basis * DY;
+                    sAn[q] = real ? p.A[(size_t)sg.region * (p.n_basis * DY) + q] : 0.0;
+                    if (INFER) sAo[q] = real ? p.A_prev[(size_t)sg.region * (p.n_basis * DY) + q] : 0.0;
                 }
-                for (int q = lane; q < M; q += 32) sC[q] = p.cm2[(size_t)sg.region * M + q];
+                for (int q = lane; q < M; q += 32) sC[q] = q < p.n_basis ? p.cm2[(size_t)sg.region * p.n_basis + q] : 0.0;
                 inv2L = p.inv2L[sg.region];
                 rs = p.rsqrtL[sg.region];
                 pbv = LATENT ? p.pbias_var[sg.parent] : 0.0;
@@ -2019,10 +2024,11 @@ __global__ void __launch_bounds__(kThreads) k_interval_objective(IntervalArgs q)
         const Segment sg = p.segs[s];
         __syncthreads();
         if (tid < M * DY) {
-            sA[tid] = p.A[(size_t)sg.region * (M * DY) + tid];
-            if (INFER) sAo[tid] = p.A_prev[(size_t)sg.region * (M * DY) + tid];
+            const bool real = tid < p.n_basis * DY;
+            sA[tid] = real ? p.A[(size_t)sg.region * (p.n_basis * DY) + tid] : 0.0;
+            if (INFER) sAo[tid] = real ? p.A_prev[(size_t)sg.region * (p.n_basis * DY) + tid] : 0.0;
         }
-        if (tid < M) sW[tid] = q.w[(size_t)sg.region * M + tid];
+        if (tid < M) sW[tid] = tid < p.n_basis ? q.w[(size_t)sg.region * p.n_basis + tid] : 0.0;
         if (tid == 0) {
             sScal[0] = q.trial_inv2L[sg.region];
             sScal[1] = q.trial_rsqrtL[sg.region];
@@ -2104,10 +2110,11 @@ __global__ void __launch_bounds__(kThreads) k_adaptive_elbo_sums(IntervalArgs q)
         const Segment sg = p.segs[s];
         __syncthreads();
         if (tid < M * DY) {
-            sA[tid] = p.A[(size_t)sg.region * (M * DY) + tid];
-            if (INFER) sAo[tid] = p.A_prev[(size_t)sg.region * (M * DY) + tid];
+            const bool real = tid < p.n_basis * DY;
+            sA[tid] = real ? p.A[(size_t)sg.region * (p.n_basis * DY) + tid] : 0.0;
+            if (INFER) sAo[tid] = real ? p.A_prev[(size_t)sg.region * (p.n_basis * DY) + tid] : 0.0;
         }
-        if (tid < M) sW[tid] = p.cm2[(size_t)sg.region * M + tid];
+        if (tid < M) sW[tid] = tid < p.n_basis ? p.cm2[(size_t)sg.region * p.n_basis + tid] : 0.0;
         if (tid == 0) {
             sScal[0] = p.inv2L[sg.region];              // re-learnt interval
             sScal[1] = p.rsqrtL[sg.region];
@@ -2479,7 +2486,8 @@ template <int M>
 __global__ void __launch_bounds__(256) k_build_gram(const double *x, const int64_t *offsets, const double *inv2L, const double *rsqrtL,
                                                     int splits, double *partial /* [blocks][NP + M] */) {
     constexpr int NP = M * (M + 1) / 2, NQ = (NP + 255) / 256;
-    __shared__ double sPhi[kGramRows][M + 1];
+    constexpr int kRows = M > 40 ? 96 : kGramRows;   // 48 KB of static shared memory
+    __shared__ double sPhi[kRows][M + 1];
     __shared__ unsigned char sI[NP], sK[NP];
     const int tid = threadIdx.x, blk = blockIdx.x, c = blk / splits, sp = blk % splits;
     for (int p = tid; p < NP; p += 256) {   // pair p = (i, k), i <= k, rows of the upper triangle one after the other
@@ -2499,8 +2507,8 @@ __global__ void __launch_bounds__(256) k_build_gram(const double *x, const int64
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
     __syncthreads();
-    for (int64_t base = a; base < b; base += kGramRows) {
-        if (tid < kGramRows) {
+    for (int64_t base = a; base < b; base += kRows) {
+        if (tid < kRows) {
             const int64_t n = base + tid;
             if (n < b) {
                 double f1, c2;
@@ -2526,7 +2534,7 @@ __global__ void __launch_bounds__(256) k_build_gram(const double *x, const int64
                 const int i = sI[p], k = sK[p];
                 double t0 = 0.0, t1 = 0.0;
 #pragma unroll 8
-                for (int r = 0; r < kGramRows; r += 2) {
+                for (int r = 0; r < kRows; r += 2) {
                     t0 = fma(sPhi[r][i], sPhi[r][k], t0);
                     t1 = fma(sPhi[r + 1][i], sPhi[r + 1][k], t1);
                 }
@@ -2535,7 +2543,7 @@ __global__ void __launch_bounds__(256) k_build_gram(const double *x, const int64
         }
         if (tid < M) {
             double t = 0.0;
-            for (int r = 0; r < kGramRows; ++r) t += sPhi[r][tid];
+            for (int r = 0; r < kRows; ++r) t += sPhi[r][tid];
             sacc += t;
         }
         __syncthreads();
@@ -2550,23 +2558,30 @@ __global__ void __launch_bounds__(256) k_build_gram(const double *x, const int64
 }
 
 // G[c][i][k] (full, symmetric) and s[c][i] from the split partials, summed in split order.
-__global__ void k_reduce_gram(const double *partial, int splits, int R, int M, double *G, double *s) {
-    const int NP = M * (M + 1) / 2;
+// (MP: the padded number of basis functions of the partials; entries of the padding are dropped.)
+__global__ void k_reduce_gram(const double *partial, int splits, int R, int M, int MP, double *G, double *s) {
+    const int NP = MP * (MP + 1) / 2;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= R * (NP + M)) return;
-    const int c = t / (NP + M), p = t % (NP + M);
+    if (t >= R * (NP + MP)) return;
+    const int c = t / (NP + MP), p = t % (NP + MP);
+    int i = 0, k = 0;
+    if (p >= NP) {
+        if (p - NP >= M) return;
+    } else {
+        int rem = p;
+        while (rem >= MP - i) {
+            rem -= MP - i;
+            ++i;
+        }
+        k = i + rem;
+        if (k >= M) return;
+    }
     double acc = 0.0;
-    for (int sp = 0; sp < splits; ++sp) acc += partial[((size_t)c * splits + sp) * (NP + M) + p];
+    for (int sp = 0; sp < splits; ++sp) acc += partial[((size_t)c * splits + sp) * (NP + MP) + p];
     if (p >= NP) {
         s[(size_t)c * M + (p - NP)] = acc;
         return;
     }
-    int i = 0, rem = p;
-    while (rem >= M - i) {
-        rem -= M - i;
-        ++i;
-    }
-    const int k = i + rem;
     G[((size_t)c * M + i) * M + k] = acc;
     G[((size_t)c * M + k) * M + i] = acc;
 }
@@ -2621,12 +2636,12 @@ __global__ void __launch_bounds__(256) k_build_ancD(EvalArgs ea, const double *x
     }
 }
 
-__global__ void k_reduce_ancD(const double *partial, int splits, int P, int M, double *D) {
+__global__ void k_reduce_ancD(const double *partial, int splits, int P, int M, int MP, double *D) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P * M) return;
     const int i = t % M, pc = t / M;
     double acc = 0.0;
-    for (int sp = 0; sp < splits; ++sp) acc += partial[((size_t)pc * splits + sp) * M + i];
+    for (int sp = 0; sp < splits; ++sp) acc += partial[((size_t)pc * splits + sp) * MP + i];
     D[t] = acc;
 }
 

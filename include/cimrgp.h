@@ -74,6 +74,9 @@ enum {
     MRGP_F_FVAR = 28,           /* (N,)      latent_f_var of the layer                                */
     MRGP_F_YVAR = 29,           /* (R,)      y_var used at the layer's step (MRGP.py:650-652)         */
     MRGP_F_PHASE_B_SUMS = 30,   /* (R, dy+3) sum r, sum |r|^2, sum f_var, sum phi^2 cm2 of the step   */
+    MRGP_F_A_PREV = 31,         /* (R, M, dy) scale_axis_mean BEFORE the layer's last update: with MRGP_F_BIAS_PREV the
+                                 * coefficients the inferred targets y_mean[j] of the last sweep were made of (MRGP.py:577, 650) */
+    MRGP_F_BIAS_PREV = 32,      /* (R, dy)   bias_mean before the layer's last update                    */
     /* Bingham axis / ARD: shared_posterior + shared_stats in ci (layer == -1), posterior_obj[j] +
      * stats_obj[j] in fi (layer >= 0, leading R).  (Posteriors.py:482-541, Stats.py:354-388)        */
     MRGP_F_AXIS_B = 40,         /* ([R,] M, dy, dy)                                                  */

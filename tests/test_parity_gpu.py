@@ -660,3 +660,63 @@ def test_config5_series_matches_reference_golden(name, fi):
         m.fit(int(k) - done, None)
         done = int(k)
         compare(m._engine.state(), split(g, 'k%d.' % k))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# boundary generality: any number of basis functions, public state of SURVEY.md §8b
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('m_basis,fi', [(25, False), (25, True), (13, False), (45, False), (45, True), (3, False)])
+def test_any_number_of_basis_functions_against_oracle(m_basis, fi):
+    """The reference accepts any n_basis (MRGP.py:16-66).  The streaming kernels are instantiated for 8 / 20 / 30 / 40 /
+    48 functions and pad; the fused sweep pads its omega solve with an identity block (n_basis <= 32), n_basis > 32
+    takes the multi-kernel sweep with the block solver."""
+    x, y = workloads.workload1(3000)
+    offsets = O.uniform_offsets(3000, 4, 2)
+    ora = O.OracleMRGP(x, y, m_basis, offsets, mode='fi' if fi else 'ci')
+    m = build(x, y, m_basis, 4, fi)
+    for _ in range(3):
+        ora.sweep()
+    m.fit(3, None)
+    compare(m._engine.state(), ora.state())
+    if not fi:
+        assert mismatch(m._engine.elbo(), ora.elbo()[2], RTOL) is None
+    xt = np.atleast_2d(np.linspace(1, 3, 200)).T
+    assert mismatch(m.get_predicted_mean(xt), ora.predict_mean(xt), RTOL) is None
+
+
+@pytest.mark.parametrize('fi', [False, True])
+def test_public_state_priors_and_targets(fi):
+    """prior_obj, shared_prior, y_mean, y_var (MRGP.py:181-226, 262-271, 650-652; Priors.py)."""
+    x, y = workloads.workload1(1500)
+    offsets = O.uniform_offsets(1500, 3, 2)
+    m = build(x, y, 20, 3, fi, snr_ratio=5.)
+    assert m.y_mean[2][1] == [] and m.y_var[0][0] == []                       # MRGP.py:262-271
+    pr = m.prior_obj
+    assert len(pr) == 4 and len(pr[2].scale_precision) == 4 and pr[2].scale_precision[3].shape == (20,)
+    assert pr[1].noise_gamma_shape == [1e-45] * 2 and pr[1].noise_gamma_scale == [1e-45 + 1] * 2
+    y_var0 = (np.linalg.norm(y) ** 2) / 1500 - np.dot(np.mean(y, axis=0), np.mean(y, axis=0))
+    assert abs(pr[0].noise_gamma_scale[0] - (1e-45 + 1) * y_var0 / 5.) < 1e-12    # MRGP.py:195-199, 966-971
+    assert pr[3].bias_normal_precision == [1e-45] * 8 and np.array_equal(pr[3].bias_normal_mean[7], np.zeros(2))
+    if fi:
+        assert pr[2].axis_bingham_rho[1].shape == (20, 2) and abs(pr[2].axis_bingham_log_const[0][0] - 1.9189385332046727) < 1e-12
+        with pytest.raises(AttributeError):
+            m.shared_prior
+    else:
+        sp = m.shared_prior
+        assert np.array_equal(sp.axis_bingham_b, np.zeros((20, 2, 2))) and np.allclose(sp.axis_bingham_rho, 0.5)
+        assert abs(sp.axis_bingham_log_const[3] - 1.9189385332046727) < 1e-12            # SURVEY.md §8c KAT
+        assert np.array_equal(sp.ard_gamma_shape, 1e-45 * np.ones(20)) and np.array_equal(sp.ard_gamma_scale, 1e-45 * np.ones(20) / 1.0)
+    ora = O.OracleMRGP(x, y, 20, offsets, mode='fi' if fi else 'ci', snr_ratio=5.)
+    ora.sweep()
+    ora.sweep()
+    m.fit(2, None)
+    ym, yv = m.y_mean, m.y_var
+    for j in range(4):
+        ly = ora.layers[j]
+        if j == 0 and not fi:
+            assert np.array_equal(ym[0][0], y)                              # LatentOutputs.py:6-9: one entry with all of Y
+        else:
+            for l in range(ly.R):
+                ref = ly.y_target[ly.off[l]:ly.off[l + 1]]
+                assert mismatch(ym[j][l], ref, RTOL) is None
+        assert mismatch(np.array(yv[j], dtype=np.float64), ly.y_var, RTOL) is None
