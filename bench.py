@@ -233,16 +233,18 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
+def flush_l2(eng, flush, torch):
+    """256 MB of HBM writes ON THE ENGINE'S STREAM: evicts L2 and keeps the GPU busy while the host queues the timed work
+    behind it, so that the CUDA events around a step bracket device time only (no launch latency of an idle queue)."""
+    with torch.cuda.stream(eng.stream):
+        flush.zero_()
+
+
 def timed_sweeps(eng, steps, flush, barrier, max_over_ranks, torch):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
     for k in range(steps):
-        # the L2 flush (256 MB of HBM writes on torch's stream) must neither overlap the sweep before it nor the one
-        # after it: it starts when the previous timed sweep is over and ends before the next timed region starts
-        torch.cuda.current_stream().wait_stream(eng.stream)
-        flush.zero_()
-        eng.stream.wait_stream(torch.cuda.current_stream())
-        barrier()
+        flush_l2(eng, flush, torch)       # stream order: after the previous timed sweep, before this one
         ev[k][0].record(eng.stream)
         eng.sweep(1)
         ev[k][1].record(eng.stream)
@@ -251,19 +253,18 @@ def timed_sweeps(eng, steps, flush, barrier, max_over_ranks, torch):
 
 
 def time_call(eng, fn, flush, torch, reps):
-    out = []
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(reps):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    torch.cuda.synchronize()
+    for k in range(reps):
         if flush is not None:
-            torch.cuda.current_stream().wait_stream(eng.stream)
-            flush.zero_()
-            eng.stream.wait_stream(torch.cuda.current_stream())
-        a.record(eng.stream)
+            flush_l2(eng, flush, torch)
+        else:
+            eng.sweep(1)                  # keeps the queue busy (warm-L2 timing of back-to-back sweeps)
+        ev[k][0].record(eng.stream)
         fn()
-        b.record(eng.stream)
-        b.synchronize()
-        out.append(a.elapsed_time(b))
-    return out
+        ev[k][1].record(eng.stream)
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in ev]
 
 
 def cholesky_grid(lib, torch, fp64_peak_tflops):
@@ -397,10 +398,8 @@ def run_gpu(args, rank, world, local_rank):
     if not args.no_e2e:
         e2e_ms = []
         for k in range(args.steps):
-            torch.cuda.current_stream().wait_stream(eng.stream)
-            flush.zero_()
-            eng.stream.wait_stream(torch.cuda.current_stream())
             barrier()
+            flush_l2(eng, flush, torch)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(eng.stream)
             eng.upload_observations()                      # H2D of this rank's rows of y (n, 2) from pinned memory

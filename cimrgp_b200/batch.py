@@ -22,6 +22,12 @@ from .IndexSetGenerator import IndexSetUniform, offsets_of
 from .MRGP import MultiResolutionGaussianProcess
 
 
+def series_range(n_series, rank, world):
+    """Contiguous block of series kept by `rank` of `world` processes (replicas only, no collective)."""
+    per = -(-int(n_series) // int(world))
+    return min(n_series, int(rank) * per), min(n_series, (int(rank) + 1) * per)
+
+
 class SeriesBatch(object):
     def __init__(self, xs, ys, n_basis, resolution, basis_function_obj, spectral_density_obj=None, divider=2,
                  forced_independence=False, n_streams=16, device=0, n_ctas=None, group_size=None, rank=0, world=1,
@@ -34,12 +40,9 @@ class SeriesBatch(object):
         rank, world: this process keeps the series [rank * per, (rank + 1) * per), per = ceil(S / world)."""
         import torch
         self.torch = torch
+        self.series_range = series_range(len(xs), rank, world)
         if world > 1:
-            per = -(-len(xs) // int(world))
-            self.series_range = (min(len(xs), int(rank) * per), min(len(xs), (int(rank) + 1) * per))
             xs, ys = xs[self.series_range[0]:self.series_range[1]], ys[self.series_range[0]:self.series_range[1]]
-        else:
-            self.series_range = (0, len(xs))
         self.n_series = len(xs)
         if len(ys) != self.n_series or self.n_series == 0:
             raise ValueError('xs and ys must list the same, non-zero number of series')

@@ -131,6 +131,8 @@ struct mrgp_handle {
     unsigned int *chain_status = nullptr;
     double *chain_guard = nullptr, *chain_prof = nullptr;
     bool chain_prof_on = false;      // MRGP_CHAIN_PROF=1: SM-clock stamps of the fused sweep (field 54)
+    bool elbo_args_valid = false;    // the per-layer argument blocks of k_elbo on the device match generation / sweeps_done
+    uint64_t elbo_args_key = 0;
     bool chain_uploaded = false;     // the device descriptor matches the current pointers (reset by drop_graph)
     uint64_t generation = 0;         // bumped whenever a captured sweep / descriptor becomes stale (groups re-capture)
     uint64_t stream_ops = 0;         // asynchronous work queued on the handle's stream from outside a sweep (groups order after it)
@@ -1120,7 +1122,7 @@ int do_ystats(mrgp_handle *h) {
         rr = d.ident_run;
         part = h->xchg;
     }
-    k_reduce_ystats<<<lp.R, 64, 0, h->stream>>>(rr, part, h->part_stride, lp.R, M, padded_basis(M), DY, d.yc, d.ysum);
+    k_reduce_ystats<<<lp.R, 1024, 0, h->stream>>>(rr, part, h->part_stride, lp.R, M, padded_basis(M), DY, d.yc, d.ysum);
     CK(cudaGetLastError());
     count(h);
     h->ystats_valid = true;
@@ -2214,14 +2216,22 @@ int mrgp_elbo(mrgp_handle *h, double *out_host) {
     if (rc) return rc;
     if (!out_host) return fail(h, MRGP_EINVAL, "null argument");
     if (h->cfg.mode != MRGP_MODE_CI) return fail(h, MRGP_EINVAL, "the lower bound is defined for ci mode only (MRGP.py:378-401)");
-    std::vector<RegionArgs> args(h->cfg.n_layers);
-    for (int j = 0; j < h->cfg.n_layers; ++j) {
-        args[j] = region_args(h, j);
-        // adaptive intervals: the data sums with the re-learnt basis (MRGP.py:535-569 reads phi_x after MRGP.py:640)
-        if (h->dev[j].adaptive && h->sweeps_done > 0) args[j].sumsB = h->dev[j].sumsE;
+    // the argument blocks of the layers live on the device; they change only with what drop_graph() tracks (pointers,
+    // intervals, adaptive switches) and with the first sweep of an adaptive model
+    const uint64_t key = h->generation * 2 + (h->sweeps_done > 0 ? 1 : 0);
+    if (!h->elbo_args_valid || h->elbo_args_key != key) {
+        std::vector<RegionArgs> args(h->cfg.n_layers);
+        for (int j = 0; j < h->cfg.n_layers; ++j) {
+            args[j] = region_args(h, j);
+            args[j].ts = nullptr;
+            // adaptive intervals: the data sums with the re-learnt basis (MRGP.py:535-569 reads phi_x after MRGP.py:640)
+            if (h->dev[j].adaptive && h->sweeps_done > 0) args[j].sumsB = h->dev[j].sumsE;
+        }
+        CK(cudaMemcpyAsync(h->elbo_args, args.data(), args.size() * sizeof(RegionArgs), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));   // args is a local
+        h->elbo_args_valid = true;
+        h->elbo_args_key = key;
     }
-    CK(cudaMemcpyAsync(h->elbo_args, args.data(), args.size() * sizeof(RegionArgs), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));   // args is a local
     k_elbo<2><<<h->cfg.n_layers, 256, 0, h->stream>>>(h->elbo_args, h->elbo_out);
     CK(cudaGetLastError());
     count(h);

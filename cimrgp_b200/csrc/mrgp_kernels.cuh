@@ -640,17 +640,36 @@ __global__ void __launch_bounds__(kThreads, 1) k_ystats(StreamArgs p) {
 }
 
 // yc[r][i][d], ysum[r][0..DY] = sums over the region's runs of the k_ystats partials (fixed order).
-// (MP: the padded number of basis functions the partials were written for.)
-__global__ void k_reduce_ystats(const int32_t *region_run, const double *part, int part_stride, int R, int M, int MP, int DY, double *yc, double *ysum) {
-    const int r = blockIdx.x, nv = MP * DY + DY + 1;
-    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
-        if (v >= M * DY && v < MP * DY) continue;
+// (MP: the padded number of basis functions the partials were written for.)  1024 threads: value = tid % 64 (chunks of
+// 64 values), 16 slices over the runs with their loads in flight together, combined in slice order.
+__global__ void __launch_bounds__(1024) k_reduce_ystats(const int32_t *region_run, const double *part, int part_stride, int R, int M, int MP, int DY,
+                                                        double *yc, double *ysum) {
+    __shared__ double sm[16][64];
+    const int r = blockIdx.x, nv = MP * DY + DY + 1, lane64 = threadIdx.x & 63, slice = threadIdx.x >> 6;
+    const int q_end = region_run[r + 1];
+    for (int v0 = 0; v0 < nv; v0 += 64) {
+        const int v = v0 + lane64;
         double s = 0.0;
-        for (int q = region_run[r]; q < region_run[r + 1]; ++q) s += part[(size_t)q * part_stride + v];
-        if (v < M * DY)
-            yc[(size_t)r * M * DY + v] = s;
-        else
-            ysum[(size_t)r * 4 + (v - MP * DY)] = s;
+        if (v < nv)
+            for (int q = region_run[r] + slice; q < q_end; q += 16 * 4) {
+                double t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t[u] = q + 16 * u < q_end ? part[(size_t)(q + 16 * u) * part_stride + v] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) s += t[u];
+            }
+        sm[slice][lane64] = s;
+        __syncthreads();
+        if (slice == 0 && v < nv && !(v >= M * DY && v < MP * DY)) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) t += sm[k][lane64];
+            if (v < M * DY)
+                yc[(size_t)r * M * DY + v] = t;
+            else
+                ysum[(size_t)r * 4 + (v - MP * DY)] = t;
+        }
+        __syncthreads();
     }
 }
 

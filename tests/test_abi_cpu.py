@@ -129,7 +129,7 @@ def test_create_rejects_what_the_reference_rejects():
     bad[1][1] = 0
     lib, rc, h = _create(64, bad)
     assert rc == _lib.EINVAL
-    for kw in (dict(dy=3), dict(dx=2), dict(m=31)):
+    for kw in (dict(dy=3), dict(dx=2), dict(m=49), dict(m=0)):
         lib, rc, h = _create(64, off, **kw)
         assert rc == _lib.EINVAL, kw
     for kw in (dict(noise=0), dict(bias=0), dict(noise=0, bias=0)):      # shared noise / bias variants are accepted

@@ -42,6 +42,21 @@ def _worker(rank, world, port, ret):
         T_all = np.stack([(ly.Phi[off[r]:off[r + 1]].T @ y[off[r]:off[r + 1]]).T for r in range(ly.R)])
         want = np.concatenate([T_all.ravel(), ly.d.ravel()])
         ok = ok and np.allclose(got, want, rtol=1e-12, atol=1e-12 * np.abs(want).max())
+    # the one exchange of the fused ci sweep: layer-0 sufficient statistics of the observations, summed over the ranks
+    ly = full.layers[0]
+    rows = np.arange(lo, hi)
+    loc = np.concatenate([(ly.Phi[rows].T @ y[rows]).ravel(), y[rows].sum(0), [np.sum(y[rows] ** 2)]])
+    t = torch.from_numpy(loc)
+    dist.all_reduce(t)
+    want = np.concatenate([(ly.Phi.T @ y).ravel(), y.sum(0), [np.sum(y ** 2)]])
+    ok = ok and np.allclose(t.numpy(), want, rtol=1e-12, atol=1e-12 * np.abs(want).max())
+    # series of a batch split by rank: a partition, no collective
+    from cimrgp_b200.batch import series_range
+    mine = torch.zeros(4097, dtype=torch.int64)
+    a, b = series_range(4097, rank, world)
+    mine[a:b] = 1
+    dist.all_reduce(mine)
+    ok = ok and bool(torch.all(mine == 1))
     bounds = [chunk_bounds(n, world, r) for r in range(world)]
     ok = ok and bounds[0][0] == 0 and bounds[-1][1] == n and all(b[0] % 32 == 0 for b in bounds) \
         and all(bounds[k][1] == bounds[k + 1][0] for k in range(world - 1))
