@@ -160,24 +160,44 @@ def port_sweeps(n, layers, warmup, steps):
     return times, threads, t_ctor
 
 
+class _BytecodeFinder(object):
+    """Imports the reference's modules from their compiled bytecode under oracle/_ref/<name>.bytecode."""
+
+    def __init__(self, path):
+        self.path = path
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        f = os.path.join(self.path, name + '.bytecode')
+        if '.' in name or not os.path.exists(f):
+            return None
+        return importlib.util.spec_from_file_location(name, f, loader=importlib.machinery.SourcelessFileLoader(name, f))
+
+
 def load_reference():
     """The UNMODIFIED reference: /root/reference/src in the build container, its bytecode under oracle/_ref (compiled by
     __graft_entry__.build(), git-ignored, travels with the snapshot) on the GPU box.  None when neither is there."""
     import types
     import warnings
-    for path in ('/root/reference/src', os.path.join(ROOT, 'oracle', '_ref')):
-        if os.path.isdir(path) and (os.path.exists(os.path.join(path, 'MRGP.py')) or os.path.exists(os.path.join(path, 'MRGP.pyc'))):
-            import scipy.misc
-            import scipy.special
-            scipy.misc.logsumexp = scipy.special.logsumexp          # Stats.py:4
-            for name in ('GPy', 'gpflow'):                           # RegressionInput.py:4-5 (only used with adaptive_inputs)
-                sys.modules.setdefault(name, types.ModuleType(name))
-            if path not in sys.path:
-                sys.path.insert(0, path)
-            warnings.filterwarnings('ignore')
-            mods = {name: __import__(name) for name in ('IndexSetGenerator', 'KernelClass', 'MRGP')}
-            return types.SimpleNamespace(path=path, **mods)
-    return None
+    src, byt = '/root/reference/src', os.path.join(ROOT, 'oracle', '_ref')
+    if os.path.exists(os.path.join(src, 'MRGP.py')):
+        path = src
+        if path not in sys.path:
+            sys.path.insert(0, path)
+    elif os.path.exists(os.path.join(byt, 'MRGP.bytecode')):
+        path = byt
+        sys.meta_path.insert(0, _BytecodeFinder(byt))
+    else:
+        return None
+    import scipy.misc
+    import scipy.special
+    scipy.misc.logsumexp = scipy.special.logsumexp          # Stats.py:4
+    for name in ('GPy', 'gpflow'):                           # RegressionInput.py:4-5 (only used with adaptive_inputs)
+        sys.modules.setdefault(name, types.ModuleType(name))
+    warnings.filterwarnings('ignore')
+    mods = {name: __import__(name) for name in ('IndexSetGenerator', 'KernelClass', 'MRGP')}
+    return types.SimpleNamespace(path=path, **mods)
 
 
 def reference_calibration(n=100000, layers=8):
