@@ -21,6 +21,7 @@ F_FBAR, F_FVAR, F_YVAR, F_PHASE_B_SUMS, F_A_PREV, F_BIAS_PREV = 27, 28, 29, 30, 
 F_AXIS_B, F_AXIS_KAPPA, F_AXIS_RHO, F_AXIS_LOGC, F_AXIS_COV = 40, 41, 42, 43, 44
 F_ARD_SHAPE, F_ARD_SCALE, F_ARD_MEAN, F_ARD_LOG_MEAN, F_OMEGA, F_LOG_OMEGA_HAT = 45, 46, 47, 48, 49, 50
 F_OMEGA_ITERS = 51
+F_FUSED_GUARD = 55
 
 
 class Config(C.Structure):

@@ -246,7 +246,10 @@ __device__ __forceinline__ void mid2_stats_layer0(const ChainModel &m, const Cha
         if (l == 0) {
             const double ratio = y2 > 0.0 ? sums[2] / y2 : 1.0;
             m.guard[0] = ratio;
-            if (!(ratio >= kChainGuard)) atomicOr(m.status, 1u);
+            if (!(ratio >= m.guard_threshold)) {
+                atomicOr(m.status, 1u);
+                m.guard[1] = 1.0;
+            }
         }
         bias_noise_update(ly, l, false, sums, rc, 1.0, b0, b1);
     }
@@ -978,6 +981,67 @@ __global__ void __launch_bounds__(256) k_ystats_small(const ChainModel *const *m
     }
 }
 
+// Streamed fallback for layer 0 of the fused sweep, one CTA per (model, region): runs only for models whose guard
+// tripped (ChainModel::status, see kChainGuard): the P4 / P5 statistics of the region by a pass over its samples with
+// the NEW coefficients (r = y - Phi A^T; Posteriors.py:81-148) and the bias / noise update again from those sums.
+template <int MP>
+__global__ void __launch_bounds__(256) k_l0_fix_small(const ChainModel *const *models, int r0_max) {
+    __shared__ double red[8][4];
+    __shared__ double sA[MP * 2], sC[MP];
+    const ChainModel &m = *models[blockIdx.x / r0_max];
+    if (m.status[0] == 0u) return;
+    const int r = blockIdx.x % r0_max;
+    const ChainLayer &ly = m.layer[0];
+    if (r >= ly.R) return;
+    const int M = m.M, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = tid; t < MP * 2; t += 256) sA[t] = t < M * 2 ? ly.A[(size_t)r * M * 2 + t] : 0.0;
+    for (int t = tid; t < MP; t += 256) sC[t] = t < M ? ly.cm2[(size_t)r * M + t] : 0.0;
+    __syncthreads();
+    const int64_t lo = ly.offsets[r], hi = ly.offsets[r + 1];
+    const double inv2L = ly.inv2L[r], rs = ly.rsqrtL[r];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};      // sum r_0, sum r_1, sum |r|^2, sum phi^2 cm2
+    for (int64_t n = lo + tid; n < hi; n += 256) {
+        double f, c2, fm = 0.0, e0 = 0.0, e1 = 0.0, v = 0.0;
+        basis_seed(m.x[n], inv2L, rs, f, c2);
+#pragma unroll 6
+        for (int i = 0; i < MP; ++i) {
+            e0 = fma(f, sA[i * 2], e0);
+            e1 = fma(f, sA[i * 2 + 1], e1);
+            v = fma(f * sC[i], f, v);
+            const double fn = fma(c2, f, -fm);
+            fm = f;
+            f = fn;
+        }
+        const double r0 = m.y[n * 2] - e0, r1 = m.y[n * 2 + 1] - e1;
+        acc[0] += r0;
+        acc[1] += r1;
+        acc[2] += fma(r1, r1, r0 * r0);
+        acc[3] += v;
+    }
+    wsum_n<4>(acc);
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[warp][k] = acc[k];
+    __syncthreads();
+    if (tid == 0) {
+        double sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, rc[7];
+        for (int w = 0; w < 8; ++w) {
+            sums[0] += red[w][0];
+            sums[1] += red[w][1];
+            sums[2] += red[w][2];
+            sums[4] += red[w][3];
+        }
+        for (int k = 0; k < 7; ++k) rc[k] = ly.rconst[(size_t)r * 8 + k];
+        bias_noise_update(ly, r, false, sums, rc, 1.0, ly.bias_prev[(size_t)r * 2], ly.bias_prev[(size_t)r * 2 + 1]);
+    }
+}
+
+template <int MP>
+int launch_l0_fix_impl(const ChainModel *const *models_dev, int n_models, int r0_max, cudaStream_t stream) {
+    k_l0_fix_small<MP><<<(unsigned)(n_models * r0_max), 256, 0, stream>>>(models_dev, r0_max);
+    return (int)cudaGetLastError();
+}
+
 template <int MP>
 int launch_ystats_impl(const ChainModel *const *models_dev, int n_models, int r0_max, cudaStream_t stream) {
     k_ystats_small<MP><<<(unsigned)(n_models * r0_max), 256, 0, stream>>>(models_dev, r0_max);
@@ -1025,6 +1089,19 @@ int launch_ystats_small(int solver_size, const ChainModel *const *models_dev, in
         case 24: return launch_ystats_impl<24>(models_dev, n_models, r0_max, st);
         case 30: return launch_ystats_impl<30>(models_dev, n_models, r0_max, st);
         case 32: return launch_ystats_impl<32>(models_dev, n_models, r0_max, st);
+        default: return (int)cudaErrorInvalidValue;
+    }
+}
+
+int launch_l0_fix_small(int solver_size, const ChainModel *const *models_dev, int n_models, int r0_max, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_models < 1 || r0_max < 1) return (int)cudaErrorInvalidValue;
+    switch (solver_size) {
+        case 8: return launch_l0_fix_impl<8>(models_dev, n_models, r0_max, st);
+        case 16: return launch_l0_fix_impl<16>(models_dev, n_models, r0_max, st);
+        case 24: return launch_l0_fix_impl<24>(models_dev, n_models, r0_max, st);
+        case 30: return launch_l0_fix_impl<30>(models_dev, n_models, r0_max, st);
+        case 32: return launch_l0_fix_impl<32>(models_dev, n_models, r0_max, st);
         default: return (int)cudaErrorInvalidValue;
     }
 }

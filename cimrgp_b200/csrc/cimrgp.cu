@@ -130,7 +130,9 @@ struct mrgp_handle {
     ChainModel chain_host{};
     unsigned int *chain_status = nullptr;
     double *chain_guard = nullptr, *chain_prof = nullptr;
+    double chain_guard_threshold = kChainGuard;   // MRGP_CHAIN_GUARD overrides (tests of the streamed fallback)
     bool chain_prof_on = false;      // MRGP_CHAIN_PROF=1: SM-clock stamps of the fused sweep (field 54)
+    const unsigned int *gate_next = nullptr;   // gate of the next phase-B launch (streamed fallback of the fused sweep)
     bool elbo_args_valid = false;    // the per-layer argument blocks of k_elbo on the device match generation / sweeps_done
     uint64_t elbo_args_key = 0;
     bool chain_uploaded = false;     // the device descriptor matches the current pointers (reset by drop_graph)
@@ -454,6 +456,7 @@ StreamArgs stream_args(mrgp_handle *h, int j) {
     a.region_run = d.region_run;
     a.offsets = d.offsets;
     a.R = h->plan[j].R;
+    a.gate = h->gate_next;
     a.n_basis = h->cfg.n_basis;
     a.infer = (h->cfg.mode == MRGP_MODE_CI && j > 0) ? 1 : 0;
     a.fuse_tail = 0;
@@ -1157,6 +1160,7 @@ int upload_chain_model(mrgp_handle *h) {
     m.chol_count = h->chol_count;
     m.status = h->chain_status;
     m.guard = h->chain_guard;
+    m.guard_threshold = h->chain_guard_threshold;
     m.ts = h->timeline ? h->ts : nullptr;
     m.prof = h->chain_prof_on ? h->chain_prof : nullptr;
     for (int j = 0; j < m.J; ++j) {
@@ -1186,11 +1190,27 @@ int upload_chain_model(mrgp_handle *h) {
     return MRGP_OK;
 }
 
+int do_phase_b(mrgp_handle *h, int j, bool fuse_tail, int prop_override);
+
 int do_fused_sweep(mrgp_handle *h) {
     const int rc = launch_ci_sweep(chain_solver_size(h->cfg.n_basis), h->chain_ptr_dev, 1, chain_cluster_size(h), h->stream);
     if (rc != 0) return fail(h, MRGP_ECUDA, "fused sweep launch: %s", cudaGetErrorString((cudaError_t)rc));
     count(h);
-    return MRGP_OK;
+    // Guarded fallback for layer 0: its sum |r|^2 is formed from the sufficient statistics of y as a difference of large
+    // terms; when the residual is tiny against sum |y|^2 (ratio below kChainGuard: high-SNR data) the sweep sets the
+    // model's status word and the kernel below - a no-op otherwise - takes the statistics of layer 0 by a pass over the
+    // samples and repeats its bias / noise update (nothing else of the sweep depends on them).
+    if (h->sharded) return MRGP_OK;   // (the sharded handle reports the status; its fallback would need an exchange)
+    if (ystats_small(h)) {
+        const int e = launch_l0_fix_small(chain_solver_size(h->cfg.n_basis), h->chain_ptr_dev, 1, h->plan[0].R, h->stream);
+        if (e != 0) return fail(h, MRGP_ECUDA, "layer-0 fallback launch: %s", cudaGetErrorString((cudaError_t)e));
+        count(h);
+        return MRGP_OK;
+    }
+    h->gate_next = h->chain_status;
+    const int r2 = do_phase_b(h, 0, true, 0);
+    h->gate_next = nullptr;
+    return r2;
 }
 
 int sweep_once(mrgp_handle *h, bool fork_omega) {
@@ -1293,7 +1313,8 @@ FieldRef field_ref(mrgp_handle *h, int layer, int field) {
         if (layer != -1) return f;
         SharedDev &s = h->sh;
         switch (field) {
-            case 54: f = {h->chain_prof, (int64_t)h->cfg.n_layers * 16}; break;   // MRGP_CHAIN_PROF=1: clock stamps of the fused sweep
+            case 54: f = {h->chain_prof, (int64_t)h->cfg.n_layers * 16}; break;
+            case MRGP_F_FUSED_GUARD: f = {h->chain_guard, 2}; break;   // MRGP_CHAIN_PROF=1: clock stamps of the fused sweep
             case 52: f = {s.omegaK + 64 * 64 + 32, 3}; break;
             case 53: f = {s.omegaK + 64 * 64 + 40, 5}; break;   // MRGP_OMEGA_PROF builds: cycles of the k_ard phases   // MRGP_OMEGA_PROF builds: cycles of the Newton stages
             case MRGP_F_AXIS_B: f = {s.axB, (int64_t)M * DY * DY}; break;
@@ -1419,6 +1440,7 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     if (const char *e = getenv("MRGP_STREAM_ALL")) h->inferred_shortcut = !(e[0] == '1');
     if (const char *e = getenv("MRGP_FUSED")) h->fused = !(e[0] == '0');
     if (const char *e = getenv("MRGP_CHAIN_PROF")) h->chain_prof_on = e[0] == '1';
+    if (const char *e = getenv("MRGP_CHAIN_GUARD")) h->chain_guard_threshold = atof(e);
     if (const char *e = getenv("MRGP_CHAIN_CLUSTER")) h->chain_cluster = atoi(e);
     h->sharded = cfg->sample_end > cfg->sample_begin;   // an explicit range selects the exchange-buffer path
     h->lo = h->sharded ? cfg->sample_begin : 0;
@@ -1787,6 +1809,10 @@ int mrgp_init_state(mrgp_handle *h, double noise_var0, double ard_prior_influenc
     CK(cudaMemsetAsync(h->g, 0, (size_t)(h->hi - h->lo) * h->cfg.dy * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->hvar, 0, (size_t)(h->hi - h->lo) * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->sh.omegaWarm, 0, kMaxLayers * sizeof(double), h->stream));
+    if (h->chain_status) {
+        CK(cudaMemsetAsync(h->chain_status, 0, 4 * sizeof(unsigned int), h->stream));
+        CK(cudaMemsetAsync(h->chain_guard, 0, 2 * sizeof(double), h->stream));
+    }
     drop_graph(h);
     h->sweeps_done = 0;
     h->state_init = true;
@@ -2158,10 +2184,12 @@ int mrgp_group_sweep(mrgp_group *g, int32_t n_iter) {
             g->launches += 1;
         }
         for (int it = 0; it < n_iter; ++it) {
-            const int e = launch_ci_sweep(g->solver, g->ptrs_dev, n, g->cluster, g->stream);
+            int e = launch_ci_sweep(g->solver, g->ptrs_dev, n, g->cluster, g->stream);
             if (e != 0) return gfail(g, MRGP_ECUDA, "fused sweep launch", (cudaError_t)e);
+            e = launch_l0_fix_small(g->solver, g->ptrs_dev, n, g->r0_max, g->stream);   // no-op for models whose guard did not trip
+            if (e != 0) return gfail(g, MRGP_ECUDA, "layer-0 fallback launch", (cudaError_t)e);
         }
-        g->launches += n_iter;
+        g->launches += 2 * n_iter;
         for (int i = 0; i < n; ++i) g->handles[i]->sweeps_done += n_iter;
         return MRGP_OK;
     }

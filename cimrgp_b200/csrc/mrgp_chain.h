@@ -57,7 +57,8 @@ struct ChainModel {
     const double *priorB, *priorLogC, *priorShape, *priorScale, *priorSk;
     unsigned long long *chol_count;
     unsigned int *status;          // [0]: layer-0 closed-form guard tripped (sum |r|^2 / sum |y|^2 below kChainGuard)
-    double *guard;                 // [0]: last ratio sum |r|^2 / sum |y|^2 of layer 0
+    double guard_threshold;        // kChainGuard unless overridden (MRGP_CHAIN_GUARD, tests of the fallback)
+    double *guard;                 // [0]: last ratio sum |r|^2 / sum |y|^2 of layer 0; [1]: 1.0 once the guard tripped
     unsigned long long *ts;        // timeline stamps or null
     double *prof;                  // (J, 16) SM-clock stamps inside CTA 0 (MRGP_CHAIN_PROF=1) or null
     ChainLayer layer[kChainMaxLayers];
@@ -84,6 +85,9 @@ int launch_ci_sweep(int solver_size, const ChainModel *const *models_dev, int n_
 // layer 0): the form for models whose layer-0 regions are small (a batch of short series: one launch for all of them).
 // r0_max: largest number of layer-0 regions among the models.
 int launch_ystats_small(int solver_size, const ChainModel *const *models_dev, int n_models, int r0_max, void *stream);
+// Streamed fallback of layer 0 for the models whose guard tripped (status != 0), same geometry as launch_ystats_small:
+// exact P4 / P5 statistics by a pass over the samples and the bias / noise update of layer 0 again.
+int launch_l0_fix_small(int solver_size, const ChainModel *const *models_dev, int n_models, int r0_max, void *stream);
 constexpr int64_t kYstatsSmallMaxRegion = 32768;   // longest layer-0 region this form is used for
 size_t ci_sweep_smem_bytes(int solver_size);
 

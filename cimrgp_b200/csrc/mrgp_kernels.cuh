@@ -81,6 +81,7 @@ struct StreamArgs {
     const int32_t *region_run;   // (R + 1)
     const int64_t *offsets;      // (R + 1)
     int32_t R, infer, fuse_tail, layer;
+    const unsigned int *gate;    // phase B only: when non-null the kernel runs only if *gate != 0 (streamed fallback of the fused sweep)
     int32_t n_basis;             // basis functions of the model; the kernels are instantiated for a padded M >= n_basis and
                                  // treat the extra functions as zero-weight (their sums are never read)
     unsigned long long *ts;
@@ -759,6 +760,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) k_phase_b(StreamArgs p) {
     __shared__ __align__(8) uint64_t full_bar[kStages];
     __shared__ __align__(8) uint64_t empty_bar[kStages];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (p.gate && *p.gate == 0u) return;   // uniform over the grid: the statistics of the fused sweep were good enough
     const int64_t c0 = p.sample_begin + (int64_t)blockIdx.x * p.cta_quantum;
     const int64_t c1 = (c0 + p.cta_quantum < p.n_samples) ? c0 + p.cta_quantum : p.n_samples;
     const int n_tiles = (c1 > c0) ? (int)((c1 - c0 + kTile - 1) / kTile) : 0;

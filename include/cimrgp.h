@@ -90,7 +90,9 @@ enum {
     MRGP_F_ARD_LOG_MEAN = 48,   /* ([R,] M)                                                          */
     MRGP_F_OMEGA = 49,          /* (M, M)    ci only, Stats.py:369, 390-420                          */
     MRGP_F_LOG_OMEGA_HAT = 50,  /* (M, M)    ci only, Stats.py:405-412 (last evaluation)             */
-    MRGP_F_OMEGA_ITERS = 51     /* (J,)      ci only: scaling iterations of the last omega solve per layer */
+    MRGP_F_OMEGA_ITERS = 51,    /* (J,)      ci only: scaling iterations of the last omega solve per layer */
+    MRGP_F_FUSED_GUARD = 55     /* (2,)      ci, fused sweep: [sum |r|^2 / sum |y|^2 of layer 0 in the last sweep, 1.0 once the
+                                 * ratio fell below 1e-5 and the streamed fallback took over the statistics of layer 0] */
 };
 
 typedef struct mrgp_handle mrgp_handle;
