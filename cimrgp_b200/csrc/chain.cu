@@ -80,7 +80,9 @@ struct ChainSmem {
                               // the copy of layer j + 1 is being written)
     double rowmax[32], colmax[32];
     double dg[32], sh[32], sc[32];              // shared step: digamma(shape), mixed prior shape / scale
+    alignas(16) double sv[32], su[32];          // solver: column and row scalings of the current iterate (broadcast reads)
     double eta[kChainMaxLayers][32];            // warm start of the solver: log column scalings of the previous sweep
+    double vout[kChainMaxLayers][32], cshift[kChainMaxLayers][32];   // column scalings and shifts of this sweep's solves
     double warm[kChainMaxLayers];
     int nchol;
     // the model's descriptor: every pointer of the sweep comes from here (a descriptor left in global memory costs an L2
@@ -385,45 +387,51 @@ __device__ __forceinline__ void mid2_stats_upper(const ChainModel &m, const Chai
 // while it contracts fast, Newton on the log column scalings otherwise, cold restart on a non-finite residual, plain
 // Sinkhorn sweeps as the last resort; tolerance kOmegaTol.  MP rows / columns live in the registers of MP lanes; for
 // M < MP the table is padded with an identity block (its scalings stay at 1 and do not couple to the model's block).
+// One evaluation of the scaling iteration: u = 1 / (K v) (rows normalised exactly), s = K^T u, c = v s (column sums of
+// P = diag(u) K diag(v)).  Lane i keeps BOTH row i (Kr) and column i (Kc) of the table in registers, v and u travel
+// through two 32-entry arrays in shared memory (broadcast loads): no transposes and no shuffles inside the loop.
+// Returns max |c - 1| (reduced in single precision: one REDUX instead of a five-step butterfly; it only steers the
+// iteration) - NaN if any entry is NaN - and the Sinkhorn column step v / c = 1 / s.
 template <int MP>
-__device__ __forceinline__ double omega_eval(const double (&K)[MP], double (&P)[MP], double (&Q)[MP], double v, double &c, double *T,
-                                             bool row, int lane) {
-    double s0 = 0.0, s1 = 0.0;
+__device__ __forceinline__ float omega_eval(const double (&Kr)[MP], const double (&Kc)[MP], double *sv, double *su, double v, double &u,
+                                            double &c, double &v_sinkhorn, bool row, int lane) {
+    sv[lane] = v;
+    __syncwarp();
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+    const double2 *pv = reinterpret_cast<const double2 *>(sv);
 #pragma unroll
     for (int k = 0; k < MP; k += 2) {
-        P[k] = K[k] * __shfl_sync(kFull, v, k);
-        P[k + 1] = K[k + 1] * __shfl_sync(kFull, v, k + 1);
-        s0 += P[k];
-        s1 += P[k + 1];
-    }
-    const double u = row ? 1.0 / (s0 + s1) : 0.0;
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < MP; ++k) {
-        P[k] *= u;
-        T[k * LD + lane] = P[k];
-    }
-    __syncwarp();
-    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
-    const double2 *col = reinterpret_cast<const double2 *>(T + (row ? lane : 0) * LD);
-#pragma unroll
-    for (int i = 0; i < MP; i += 2) {
-        const double2 t = col[i >> 1];
-        Q[i] = t.x;
-        Q[i + 1] = t.y;
-        if (i & 2) {
-            c2 += t.x;
-            c3 += t.y;
+        const double2 t = pv[k >> 1];
+        if (k & 2) {
+            r2 = fma(Kr[k], t.x, r2);
+            r3 = fma(Kr[k + 1], t.y, r3);
         } else {
-            c0 += t.x;
-            c1 += t.y;
+            r0 = fma(Kr[k], t.x, r0);
+            r1 = fma(Kr[k + 1], t.y, r1);
         }
     }
-    c = (c0 + c1) + (c2 + c3);
-    double e = row ? fabs(c - 1.0) : 0.0;
-    const bool bad = !(e == e);
-    e = wmax(e);
-    return __any_sync(kFull, bad) ? NAN : e;
+    u = row ? 1.0 / ((r0 + r1) + (r2 + r3)) : 0.0;
+    su[lane] = u;
+    __syncwarp();
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    const double2 *pu = reinterpret_cast<const double2 *>(su);
+#pragma unroll
+    for (int i = 0; i < MP; i += 2) {
+        const double2 t = pu[i >> 1];
+        if (i & 2) {
+            c2 = fma(Kc[i], t.x, c2);
+            c3 = fma(Kc[i + 1], t.y, c3);
+        } else {
+            c0 = fma(Kc[i], t.x, c0);
+            c1 = fma(Kc[i + 1], t.y, c1);
+        }
+    }
+    const double s = (c0 + c1) + (c2 + c3);
+    c = row ? v * s : 1.0;
+    v_sinkhorn = row ? 1.0 / s : 1.0;
+    const float e = row ? fabsf((float)(c - 1.0)) : 0.0f;      // NaN stays NaN; |.| >= 0: floats order like their bit patterns
+    const unsigned bits = __reduce_max_sync(kFull, __float_as_uint(e));
+    return __uint_as_float(bits);
 }
 
 template <int MP>
@@ -432,10 +440,20 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
     const int M = m.M, j = layer;
     if (lane == 0) PROF(6);
     const bool row = lane < MP, real = lane < M;
-    double *T = sm.T;
-    double K[MP], P[MP], Q[MP];
+    double *T = sm.T, *sv = sm.sv, *su = sm.su;
+    double Kr[MP], Kc[MP];
+    // padding (M <= index < MP): an identity block, its scalings stay at 1 and do not couple to the model's block
 #pragma unroll
-    for (int k = 0; k < MP; ++k) K[k] = (real && k < M) ? sm.Kt[k * LD + lane] : ((row && !real && k == lane) ? 1.0 : 0.0);
+    for (int k = 0; k < MP; ++k) Kr[k] = (real && k < M) ? sm.Kt[k * LD + lane] : ((row && !real && k == lane) ? 1.0 : 0.0);
+    {
+        const double2 *col = reinterpret_cast<const double2 *>(sm.Kt + (real ? lane : 0) * LD);
+#pragma unroll
+        for (int i = 0; i < MP; i += 2) {
+            const double2 t = col[i >> 1];
+            Kc[i] = (real && i < M) ? t.x : ((row && !real && i == lane) ? 1.0 : 0.0);
+            Kc[i + 1] = (real && i + 1 < M) ? t.y : ((row && !real && i + 1 == lane) ? 1.0 : 0.0);
+        }
+    }
     const double cshift = real ? sm.colmax[lane] : 0.0;
     const bool warm = sm.warm[layer] > 0.5;
     double v = 1.0;
@@ -444,14 +462,14 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
         v = (warm && isfinite(eta)) ? exp(fmax(-600.0, fmin(600.0, eta))) : 1.0;
     }
     int iters = 0;
-    double err_prev = INFINITY, c = 1.0;
+    double err_prev = INFINITY, c = 1.0, u = 0.0, vs = 1.0;
     int last = kOmegaNone;
     bool converged = false;
     const double inv_m = 1.0 / (double)M;
     if (lane == 0) PROF(7);
     for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
         ++iters;
-        const double err = omega_eval<MP>(K, P, Q, v, c, T, row, lane);
+        const double err = (double)omega_eval<MP>(Kr, Kc, sv, su, v, u, c, vs, row, lane);
         if (err < kOmegaTol) {
             converged = true;
             break;
@@ -463,13 +481,33 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
             continue;
         }
         if (!omega_take_newton(err, err_prev, last)) {
-            if (real) v = fmax(1e-280, fmin(1e280, v / c));   // Sinkhorn column step
+            if (real) v = fmax(1e-280, fmin(1e280, vs));      // Sinkhorn column step v / c
             err_prev = err;
             last = kOmegaSinkhorn;
             continue;
         }
         err_prev = err;
         last = kOmegaNewton;
+        // ---- Newton on the log column scalings.  The table P = diag(u) K diag(v), transposed, goes to shared memory
+        //      (T[k][i] = P_ik); lane j holds column j of P in Q.
+        double Q[MP];
+        {
+            const double2 *pv = reinterpret_cast<const double2 *>(sv);
+#pragma unroll
+            for (int k = 0; k < MP; k += 2) {
+                const double2 t = pv[k >> 1];
+                T[k * LD + lane] = Kr[k] * u * t.x;
+                T[(k + 1) * LD + lane] = Kr[k + 1] * u * t.y;
+            }
+            const double2 *pu = reinterpret_cast<const double2 *>(su);
+#pragma unroll
+            for (int i = 0; i < MP; i += 2) {
+                const double2 t = pu[i >> 1];
+                Q[i] = Kc[i] * t.x * v;
+                Q[i + 1] = Kc[i + 1] * t.y * v;
+            }
+        }
+        __syncwarp();
         // ---- Newton matrix: lane j builds row j of diag(c) - P^T P + e e^T / M (e: the model's columns; the padding
         //      columns get a unit diagonal) from its column Q and the transposed table
         double H[MP];
@@ -538,20 +576,35 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
         }
         if (real) v = fmax(1e-280, fmin(1e280, v * exp(fmax(-30.0, fmin(30.0, x)))));
         __syncwarp();
+        // the column registers made room for the Newton step: reload them
+        {
+            const double2 *col = reinterpret_cast<const double2 *>(sm.Kt + (real ? lane : 0) * LD);
+#pragma unroll
+            for (int i = 0; i < MP; i += 2) {
+                const double2 t = col[i >> 1];
+                Kc[i] = (real && i < M) ? t.x : ((row && !real && i == lane) ? 1.0 : 0.0);
+                Kc[i + 1] = (real && i + 1 < M) ? t.y : ((row && !real && i + 1 == lane) ? 1.0 : 0.0);
+            }
+        }
     }
     if (lane == 0) PROF(8);
-    // last resort: plain Sinkhorn sweeps (see omega_solve_serial); on model tables the loop exits at its first test
+    // last resort: plain Sinkhorn sweeps (see omega_solve_serial); on model tables the loop is not entered
     for (int it = 0; it < kOmegaFallbackSweeps && !converged; ++it) {
-        const double err = omega_eval<MP>(K, P, Q, v, c, T, row, lane);
+        const double err = (double)omega_eval<MP>(Kr, Kc, sv, su, v, u, c, vs, row, lane);
         if (err < kOmegaTol || !isfinite(err)) break;
         ++iters;
-        if (real) v = fmax(1e-280, fmin(1e280, v / c));
+        if (real) v = fmax(1e-280, fmin(1e280, vs));
     }
-    if (real) {
+    if (real) {   // omega = diag(u) K diag(v), kept transposed for the mixing step of the next layer
+        const double2 *pv = reinterpret_cast<const double2 *>(sv);
 #pragma unroll
-        for (int k = 0; k < MP; ++k)
-            if (k < M) sm.omT[k * LD + lane] = P[k];
-        m.omegaEta[layer * 64 + lane] = log(v) - cshift;
+        for (int k = 0; k < MP; k += 2) {
+            const double2 t = pv[k >> 1];
+            if (k < M) sm.omT[k * LD + lane] = Kr[k] * u * t.x;
+            if (k + 1 < M) sm.omT[(k + 1) * LD + lane] = Kr[k + 1] * u * t.y;
+        }
+        sm.vout[layer][lane] = v;           // log(v) - column shift (next sweep's warm start): taken at the end of the kernel
+        sm.cshift[layer][lane] = cshift;
     }
     if (lane == 0) {
         m.omegaIters[layer] = (double)iters;
@@ -605,6 +658,24 @@ __device__ __forceinline__ void bingham2_chain(double a, double b, double c, Bin
     out.cov[1] = out.rho[0] * p01 - out.rho[1] * p01;
     out.cov[2] = out.rho[0] * p11 + out.rho[1] * (1.0 - p11);
     out.n_chol = 1;
+}
+
+// psi(x) as digamma() of mrgp_math.cuh with the recurrence below 10 summed as ONE fraction (a chain of multiplications
+// and a single division instead of up to ten divisions in a row: the coarse layers have shapes of 0.5 .. 8).
+__device__ __forceinline__ double digamma_chain(double x) {
+    double num = 0.0, den = 1.0;
+    while (x < 10.0) {
+        num = fma(num, x, den);
+        den *= x;
+        x += 1.0;
+    }
+    const double inv = 1.0 / x;
+    const double i2 = inv * inv;
+    const double series =
+        i2 * (1.0 / 12.0 -
+              i2 * (1.0 / 120.0 -
+                    i2 * (1.0 / 252.0 - i2 * (1.0 / 240.0 - i2 * (1.0 / 132.0 - i2 * (691.0 / 32760.0 - i2 * (1.0 / 12.0)))))));
+    return (log(x) - 0.5 * inv - series) - num / den;
 }
 
 // ---- the shared step of a layer on CTA 0 (256 threads) ------------------------------------------------------------
@@ -688,7 +759,7 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
         const double shape = sh + 0.5 * (double)ly.R;
         sm.sh[i] = shape;
         sm.sc[i] = sc;
-        sm.dg[i] = digamma(shape);
+        sm.dg[i] = digamma_chain(shape);
     }
     __syncthreads();
     if (tid == 0) PROF(2);
@@ -823,9 +894,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
 
     // ---- prologue: the small-matrix state into L2 (the sweep is a chain of dependent loads), omega (transposed) and the
     //      warm starts on CTA 0, the ARD mean of the previous sweep everywhere ---------------------------------------
-    {
-        const unsigned long long lines = m.pf_lines, nthr = (unsigned long long)C * kChainThreads;
-        for (unsigned long long l = (unsigned long long)rank * kChainThreads + tid; l < lines; l += nthr)
+    if (C >= 4 && rank >= 2) {   // CTAs that are neither on the chain (0) nor own layer 0's region (1) pull the state into L2
+        const unsigned long long lines = m.pf_lines, nthr = (unsigned long long)(C - 2) * kChainThreads;
+        for (unsigned long long l = (unsigned long long)(rank - 2) * kChainThreads + tid; l < lines; l += nthr)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(m.pf_base + l * 128));
     }
     if (rank == 0) {
@@ -927,6 +998,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
             m.ardMean[t] = sm.mean[t];
             m.ardLogMean[t] = sm.lmean[t];
         }
+        for (int t = tid; t < J * 32; t += kChainThreads)
+            if ((t & 31) < M) m.omegaEta[(t >> 5) * 64 + (t & 31)] = log(sm.vout[t >> 5][t & 31]) - sm.cshift[t >> 5][t & 31];
         if (tid == 0) atomicAdd(m.chol_count, (unsigned long long)sm.nchol);
         if (ts && tid == 0) atomicMax(&ts[((J - 1) * 4 + 1) * 2 + 1], gtimer());
     }
