@@ -833,6 +833,7 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
 }
 
 // Worker steps of one warp for a whole layer, NB regions at a time (NB by the regions per worker warp).
+// (Inlined at their three call sites: as separate functions they cost 4 % - the calls spill around the 255-register solver.)
 __device__ __forceinline__ void layer_mid1(const ChainModel &m, int j, int ww, int n_workers, int lane, const double *ardMean, double (&acc)[7]) {
     const ChainLayer &ly = m.layer[j];
     if (j == 0) {
