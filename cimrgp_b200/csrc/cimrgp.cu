@@ -138,6 +138,7 @@ struct mrgp_handle {
     bool chain_uploaded = false;     // the device descriptor matches the current pointers (reset by drop_graph)
     uint64_t generation = 0;         // bumped whenever a captured sweep / descriptor becomes stale (groups re-capture)
     uint64_t stream_ops = 0;         // asynchronous work queued on the handle's stream from outside a sweep (groups order after it)
+    bool split_kernels = false;      // MRGP_SPLIT=1: lane-split statistics kernel (experiment, 30 % slower: profiles/r02_ncu_summary.md)
     bool fused = true;               // MRGP_FUSED=0: the multi-kernel sweep of round 1
     int chain_cluster = 0;           // CTAs per model of the fused sweep (0: by the number of regions)
     bool inferred_shortcut = true;   // skip phase A where Phi^T r == 0 identically (MRGP_STREAM_ALL=1: stream everything)
@@ -1082,6 +1083,13 @@ int do_exchange(mrgp_handle *h, int j, int slot, int nv, bool is_max);
 template <int M>
 cudaError_t launch_ystats(mrgp_handle *h, const StreamArgs &a) {
     constexpr int DY = 2;
+    if (h->split_kernels) {   // lane-split form: 512 threads, DY lanes per sample
+        const size_t smem2 = (size_t)(kStages * TileLayout<DY, true, false, false>::kDoubles) * sizeof(double);
+        cudaError_t e2 = set_smem(k_ystats_split<DY, M>, smem2);
+        if (e2 != cudaSuccess) return e2;
+        k_ystats_split<DY, M><<<h->n_ctas, kThreadsS, smem2, h->stream>>>(a);
+        return cudaGetLastError();
+    }
     const size_t smem = (size_t)(kStages * TileLayout<DY, true, false, false>::kDoubles + kRedSmemDoubles) * sizeof(double);
     cudaError_t e = set_smem(k_ystats<DY, M>, smem);
     if (e != cudaSuccess) return e;
@@ -1439,6 +1447,7 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     if (const char *e = getenv("MRGP_OMEGA_BLOCK")) h->omega_warp = !(e[0] == '1');
     if (const char *e = getenv("MRGP_STREAM_ALL")) h->inferred_shortcut = !(e[0] == '1');
     if (const char *e = getenv("MRGP_FUSED")) h->fused = !(e[0] == '0');
+    if (const char *e = getenv("MRGP_SPLIT")) h->split_kernels = !(e[0] == '0');
     if (const char *e = getenv("MRGP_CHAIN_PROF")) h->chain_prof_on = e[0] == '1';
     if (const char *e = getenv("MRGP_CHAIN_GUARD")) h->chain_guard_threshold = atof(e);
     if (const char *e = getenv("MRGP_CHAIN_CLUSTER")) h->chain_cluster = atoi(e);

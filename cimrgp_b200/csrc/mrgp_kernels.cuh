@@ -640,6 +640,161 @@ __global__ void __launch_bounds__(kThreads, 1) k_ystats(StreamArgs p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Lane-split form of the streaming kernels: DY lanes per sample, every lane owns ONE output dimension of the sample
+// (its column of Phi^T y / Phi^T r, its residual) and repeats the basis recurrence.  A thread then carries M + 2
+// accumulators instead of DY M + 3: half the registers, 512-thread CTAs (16 warps per SM instead of 8), and the
+// dependent FMAs of an accumulator are far enough apart for the FP64 pipe.  Price: the seed and the recurrence are
+// computed DY times per sample.
+// ------------------------------------------------------------------------------------------------
+constexpr int kThreadsS = 512;
+
+// Sums over the threads of the block that own the same output dimension, fixed order: out index by (value, dim).
+template <int NV, int DY>
+__device__ __forceinline__ void block_reduce_split(const double (&v)[NV], double *sm /* [16][NV][DY] */, double (&res)[1], int &res_index) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = v[k];
+#pragma unroll
+        for (int o = 16; o >= DY; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane < DY) sm[(warp * NV + k) * DY + lane] = t;
+    }
+    __syncthreads();
+    res_index = -1;
+    if (tid < NV * DY) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreadsS / 32; ++w) t += sm[w * NV * DY + tid];
+        res[0] = t;
+        res_index = tid;      // = value * DY + dim
+    }
+}
+
+template <int DY, int M, int SB>
+__device__ __forceinline__ void ystats_split_block(double (&T)[M + 2], const double *st, int k0, int lo_rel, int hi_rel, double inv2L,
+                                                   double rs) {
+    using L = TileLayout<DY, true, false, false>;
+    const int pair = threadIdx.x / DY, d = threadIdx.x % DY;
+    double c2[SB], f[SB], fm[SB], yv[SB];
+#pragma unroll
+    for (int q = 0; q < SB; ++q) {
+        const int idx = (k0 + q) * kThreads + pair;
+        const bool act = idx >= lo_rel && idx < hi_rel;
+        const double x = act ? st[L::kX + idx] : 0.0;
+        basis_seed(x, inv2L, act ? rs : 0.0, f[q], c2[q]);
+        fm[q] = 0.0;
+        yv[q] = act ? st[L::kY + idx * DY + d] : 0.0;
+        T[M] += yv[q];
+        T[M + 1] = fma(yv[q], yv[q], T[M + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+#pragma unroll
+        for (int q = 0; q < SB; ++q) {
+            T[i] = fma(f[q], yv[q], T[i]);
+            const double fn = fma(c2[q], f[q], -fm[q]);
+            fm[q] = f[q];
+            f[q] = fn;
+        }
+    }
+}
+
+template <int DY, int M>
+__global__ void __launch_bounds__(kThreadsS, 1) k_ystats_split(StreamArgs p) {
+    using L = TileLayout<DY, true, false, false>;
+    static_assert(kThreadsS / DY == kThreads, "a sub-block of the tile is kThreads samples");
+    constexpr int NCW = kThreadsS / 32, NV = M + 2;
+    extern __shared__ __align__(128) double dsm[];
+    double *stages = dsm;
+    __shared__ double red[NCW * NV * DY];
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t c0 = p.sample_begin + (int64_t)blockIdx.x * p.cta_quantum;
+    const int64_t c1 = (c0 + p.cta_quantum < p.n_samples) ? c0 + p.cta_quantum : p.n_samples;
+    const int n_tiles = (c1 > c0) ? (int)((c1 - c0 + kTile - 1) / kTile) : 0;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NCW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    int next_issue = 0;
+    double T[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) T[i] = 0.0;
+    int s = p.cta_seg[blockIdx.x];
+    const int s_end = p.cta_seg[blockIdx.x + 1];
+    int loaded = -1;
+    double inv2L = 0.0, rs = 0.0;
+    Segment sg;
+    if (s < s_end) sg = p.segs[s];
+    for (int t = 0; t < n_tiles; ++t) {
+        const int stage = t % kStages;
+        const double *st = stages + stage * L::kDoubles;
+        if (tid == 0) refill<DY, true, false, false>(p, stages, full_bar, empty_bar, next_issue, t, n_tiles, c0, c1);
+        mbar_wait(&full_bar[stage], (uint32_t)((t / kStages) & 1));
+        const int64_t tile_lo = c0 + (int64_t)t * kTile;
+        const int64_t tile_hi = (tile_lo + kTile < c1) ? tile_lo + kTile : c1;
+        int64_t pos = tile_lo;
+        while (pos < tile_hi) {
+            if (loaded != s) {
+                inv2L = p.inv2L[sg.region];
+                rs = p.rsqrtL[sg.region];
+                loaded = s;
+            }
+            const int64_t seg_end = sg.start + sg.len;
+            const int64_t hi = (seg_end < tile_hi) ? seg_end : tile_hi;
+            int ka = (int)((pos - tile_lo) / kThreads);
+            const int kb = (int)((hi - 1 - tile_lo) / kThreads);
+            while (ka <= kb) {
+                const int left = kb - ka + 1;
+                if (left >= 4) {
+                    ystats_split_block<DY, M, 4>(T, st, ka, (int)(pos - tile_lo), (int)(hi - tile_lo), inv2L, rs);
+                    ka += 4;
+                } else if (left >= 2) {
+                    ystats_split_block<DY, M, 2>(T, st, ka, (int)(pos - tile_lo), (int)(hi - tile_lo), inv2L, rs);
+                    ka += 2;
+                } else {
+                    ystats_split_block<DY, M, 1>(T, st, ka, (int)(pos - tile_lo), (int)(hi - tile_lo), inv2L, rs);
+                    ka += 1;
+                }
+            }
+            pos = hi;
+            if (hi == seg_end) {
+                if (sg.flush) {
+                    // partial layout of k_ystats: [c (M*DY) | sum y (DY) | sum |y|^2]
+                    double res[1];
+                    int idx;
+                    block_reduce_split<NV, DY>(T, red, res, idx);
+                    double *out = p.part + (size_t)sg.run * p.part_stride;
+                    if (idx >= 0 && idx < (M + 1) * DY) out[idx] = res[0];          // c and sum y: index = value * DY + dim
+                    if (idx >= (M + 1) * DY) red[idx - (M + 1) * DY] = res[0];      // sum y_d^2 per dimension
+                    __syncthreads();
+                    if (tid == 0) {
+                        double t2 = 0.0;
+#pragma unroll
+                        for (int dd = 0; dd < DY; ++dd) t2 += red[dd];
+                        out[M * DY + DY] = t2;
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) T[i] = 0.0;
+                }
+                ++s;
+                if (s < s_end) sg = p.segs[s];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+}
+
 // yc[r][i][d], ysum[r][0..DY] = sums over the region's runs of the k_ystats partials (fixed order).
 // (MP: the padded number of basis functions the partials were written for.)  1024 threads: value = tid % 64 (chunks of
 // 64 values), 16 slices over the runs with their loads in flight together, combined in slice order.
