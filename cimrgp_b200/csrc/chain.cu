@@ -19,6 +19,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <cstddef>
+#include <cstdlib>
 
 #include "mrgp_math.cuh"
 
@@ -128,12 +129,13 @@ __device__ __forceinline__ void mid1_layer0(const ChainModel &m, const ChainLaye
     const double s = on ? __ldg(ly.sumPhi + ri) : 0.0;
     double t0 = on ? fma(-s, b0, ly.yc[ri * 2]) : 0.0, t1 = on ? fma(-s, b1, ly.yc[ri * 2 + 1]) : 0.0;
     const double *G = ly.gram + (size_t)l * M * M;
-#pragma unroll 6
-    for (int k = 0; k < M; ++k) {
-        const double ak0 = __shfl_sync(kFull, a.x, k), ak1 = __shfl_sync(kFull, a.y, k);
-        const double g = (on && k != lane) ? __ldg(G + (size_t)k * M + lane) : 0.0;
-        t0 = fma(-g, ak0, t0);
-        t1 = fma(-g, ak1, t1);
+    double g[32];      // column `lane` of G without its diagonal entry, all loads in flight at once
+#pragma unroll
+    for (int k = 0; k < 32; ++k) g[k] = (on && k < M && k != lane) ? __ldg(G + (size_t)k * M + lane) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        t0 = fma(-g[k], __shfl_sync(kFull, a.x, k), t0);
+        t1 = fma(-g[k], __shfl_sync(kFull, a.y, k), t1);
     }
     if (on) p1_finish(ly, ri, t0, t1, dsum, S, noise, ardMean[lane], acc);
 }
@@ -225,12 +227,14 @@ __device__ __forceinline__ void mid2_stats_layer0(const ChainModel &m, const Cha
     double cm2;
     s2_region(ly, ri, on, cov[lane], cov[32 + lane], cov[64 + lane], yt, zeta, prec, ao, an, cm2);
     const double *G = ly.gram + (size_t)l * M * M;
+    double g[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) g[k] = (on && k < M) ? __ldg(G + (size_t)k * M + lane) : 0.0;
     double t0 = 0.0, t1 = 0.0;
-#pragma unroll 6
-    for (int k = 0; k < M; ++k) {
-        const double g = on ? __ldg(G + (size_t)k * M + lane) : 0.0;
-        t0 = fma(g, __shfl_sync(kFull, an.x, k), t0);
-        t1 = fma(g, __shfl_sync(kFull, an.y, k), t1);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        t0 = fma(g[k], __shfl_sync(kFull, an.x, k), t0);
+        t1 = fma(g[k], __shfl_sync(kFull, an.y, k), t1);
     }
     const double sa0 = wsum(si * an.x), sa1 = wsum(si * an.y);
     const double cross = wsum(an.x * yc.x + an.y * yc.y);
@@ -312,7 +316,8 @@ __device__ __forceinline__ void mid2_stats_upper(const ChainModel &m, const Chai
     int e_pass = 0;      // the slots of a region are filled from the front: the longest list of the batch
 #pragma unroll
     for (int q = 0; q < NB; ++q) e_pass = max(e_pass, __popc(__ballot_sync(kFull, en[q].len >= 0)));
-#pragma unroll 4
+    constexpr int UE = NB >= 4 ? 4 : (NB == 2 ? 8 : 16);   // 2 NB UE loads in flight per round trip
+#pragma unroll UE
     for (int e = 0; e < e_pass; ++e) {
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
@@ -357,12 +362,14 @@ __device__ __forceinline__ void mid2_stats_upper(const ChainModel &m, const Chai
         for (int q = 0; q < NB; ++q) {
             const double dA0 = ao[q].x - an[q].x, dA1 = ao[q].y - an[q].y;
             const double *G = ly.gram + (size_t)(live[q] ? l0 + q * stride : 0) * M * M;
+            double g[32];      // column `lane` of G: all its loads in flight at once (one L2 round trip per region)
+#pragma unroll
+            for (int k = 0; k < 32; ++k) g[k] = (on && live[q] && k < M) ? __ldg(G + (size_t)k * M + lane) : 0.0;
             double t0 = 0.0, t1 = 0.0;
-#pragma unroll 6
-            for (int k = 0; k < M; ++k) {
-                const double g = (on && live[q]) ? __ldg(G + (size_t)k * M + lane) : 0.0;
-                t0 = fma(g, __shfl_sync(kFull, dA0, k), t0);
-                t1 = fma(g, __shfl_sync(kFull, dA1, k), t1);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                t0 = fma(g[k], __shfl_sync(kFull, dA0, k), t0);
+                t1 = fma(g[k], __shfl_sync(kFull, dA1, k), t1);
             }
             quad[q] = dA0 * t0 + dA1 * t1;
         }
@@ -680,7 +687,7 @@ __device__ __forceinline__ double digamma_chain(double x) {
 
 // ---- the shared step of a layer on CTA 0 (256 threads) ------------------------------------------------------------
 __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, cg::cluster_group &cluster, int j, int tid, unsigned C) {
-    const int M = m.M, lane = tid & 31, warp = tid >> 5;
+    const int M = m.M, lane = tid & 31, warp = __shfl_sync(kFull, tid >> 5, 0);   // (warp-uniform for the compiler)
     const ChainLayer &ly = m.layer[j];
     if (tid == 0) PROF(0);
     // region sums of the cluster, in rank order (all DSMEM loads of a thread in flight at once)
@@ -842,8 +849,10 @@ __device__ __forceinline__ void layer_mid1(const ChainModel &m, int j, int ww, i
         if (ww < ly.R) mid1_upper<1>(m, ly, ww, n_workers, lane, ardMean, acc);
     } else if (ly.R <= 2 * n_workers) {
         mid1_upper<2>(m, ly, ww, n_workers, lane, ardMean, acc);
+    } else if (ly.R <= 4 * n_workers) {
+        mid1_upper<4>(m, ly, ww, n_workers, lane, ardMean, acc);
     } else {
-        for (int l = ww; l < ly.R; l += 4 * n_workers) mid1_upper<4>(m, ly, l, n_workers, lane, ardMean, acc);
+        for (int l = ww; l < ly.R; l += 8 * n_workers) mid1_upper<8>(m, ly, l, n_workers, lane, ardMean, acc);
     }
 }
 
@@ -864,13 +873,25 @@ __device__ __forceinline__ void layer_finish(const ChainModel &m, int j, int ww,
 // workers and finish layer j (S2, P4 / P5) in the BACKGROUND: they arrive at the cluster barrier as soon as the region
 // sums of layer j + 1 are published and do that work before they wait, so the chain on CTA 0 never waits for it.
 // C == 1 (a batch of small models, one CTA each): warp 0 solves while warps 1-7 do the worker steps of the layer.
+__device__ unsigned int g_pad_epoch;   // experiment (MRGP_CHAIN_PAD): last launch whose model clusters have finished
+
 template <int MP>
-__global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel *const *models) {
+__global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel *const *models, int n_models, unsigned int pad_epoch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ChainSmem &sm = *reinterpret_cast<ChainSmem *>(smem_raw);
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the warp index as a broadcast: the compiler then knows that every branch on it is warp-uniform and emits plain
+    // shuffles inside the solver / worker roles (otherwise each one is bracketed by a WARPSYNC and serialised)
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(kFull, tid >> 5, 0);
+    const long long t_begin = clock64();
+    if ((int)(blockIdx.x / C) >= n_models) {   // padding clusters of the occupancy experiment: no model
+        if (pad_epoch != 0u && tid == 0) {     // stay resident until the model clusters are done (bounded: 2 ms)
+            const unsigned long long t0 = gtimer();
+            while (*reinterpret_cast<volatile unsigned int *>(&g_pad_epoch) != pad_epoch && gtimer() - t0 < 2000000ull) __nanosleep(500);
+        }
+        return;
+    }
     {
         const ChainModel *gm = models[blockIdx.x / C];
         const int J0 = gm->J;
@@ -895,10 +916,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
 
     // ---- prologue: the small-matrix state into L2 (the sweep is a chain of dependent loads), omega (transposed) and the
     //      warm starts on CTA 0, the ARD mean of the previous sweep everywhere ---------------------------------------
-    if (C >= 4 && rank >= 2) {   // CTAs that are neither on the chain (0) nor own layer 0's region (1) pull the state into L2
+    if (C >= 4 && rank >= 2 && m.pf_mode != 0) {   // CTAs that are neither on the chain (0) nor own layer 0's region (1) pull the state into L2
         const unsigned long long lines = m.pf_lines, nthr = (unsigned long long)(C - 2) * kChainThreads;
-        for (unsigned long long l = (unsigned long long)(rank - 2) * kChainThreads + tid; l < lines; l += nthr)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(m.pf_base + l * 128));
+        const unsigned long long first = (unsigned long long)(rank - 2) * kChainThreads + tid;
+        if (m.pf_mode == 2) {    // bulk prefetches (the TMA unit walks the lines): 4 KB per instruction
+            constexpr unsigned long long kChunk = 4096;
+            const unsigned long long bytes = lines * 128;
+            for (unsigned long long off = first * kChunk; off < bytes; off += nthr * kChunk) {
+                const unsigned sz = (unsigned)(bytes - off < kChunk ? bytes - off : kChunk);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(m.pf_base + off), "r"(sz) : "memory");
+            }
+        } else {
+            for (unsigned long long l = first; l < lines; l += nthr) asm volatile("prefetch.global.L2 [%0];" ::"l"(m.pf_base + l * 128));
+        }
     }
     if (rank == 0) {
         for (int t = tid; t < M * M; t += kChainThreads) {
@@ -932,10 +962,22 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
         }
     }
 
-    for (int j = 0; j < J; ++j) {
+    if (m.prof && J >= 4 && rank == 0 && tid == 0) {   // whole-kernel stamps of CTA 0 in slot 15 of rows 0 .. 3 (needs J >= 4)
+        m.prof[0 * 16 + 15] = (double)t_begin;
+        m.prof[1 * 16 + 15] = (double)clock64();
+    }
+    // Iteration j = J only finishes the last layer (the one call site of layer_finish: the sweep's code is mostly the
+    // unrolled worker steps and has to stay in the instruction caches).
+    for (int j = 0; j <= J; ++j) {
+        if (j == J && m.prof && J >= 4 && rank == 0 && tid == 0) m.prof[2 * 16 + 15] = (double)clock64();
         cl_arrive();                                       // A_j: this thread's share of the region sums of layer j is published
-        if (worker && early && j > 0) layer_finish(m, j - 1, ww, n_workers, lane, sm.loc[(j - 1) & 1]);   // background
+        if (worker && j > 0) {   // S2 and P4 / P5 of layer j - 1 in the background of the chain (C >= 2) / of the solve (C == 1)
+            const long long tf = clock64();
+            layer_finish(m, j - 1, ww, n_workers, lane, sm.loc[(j - 1) & 1]);
+            if (m.prof && j > 4 && ww == 0 && lane == 0) m.prof[(j - 1) * 16 + 15] = (double)(clock64() - tf);   // rows >= 4: its cycles
+        }
         cl_wait();
+        if (j == J) break;
         if (rank == 0) {
             if (ts && tid == 0) atomicMin(&ts[(j * 4 + 3) * 2], gtimer());
             shared_step(m, sm, cluster, j, tid, C);
@@ -970,14 +1012,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
                 sm.ctaPart[v] = s;
             }
             if (stamp) PROF(13);
-            if (!early) layer_finish(m, j, ww, n_workers, lane, loc);
             if (ts && stamp) atomicMax(&ts[(j * 4 + 1) * 2 + 1], gtimer());
             if (stamp) PROF(14);
         }
     }
-    if (worker && early) layer_finish(m, J - 1, ww, n_workers, lane, sm.loc[(J - 1) & 1]);
-    cl_arrive();
-    cl_wait();
+    if (m.prof && J >= 4 && rank == 0 && tid == 0) m.prof[3 * 16 + 15] = (double)clock64();
     // ---- the shared posterior / stats left by the last layer (Posteriors.py:482-541, Stats.py:354-420) ----------
     if (rank == 0) {
         for (int t = tid; t < M * M; t += kChainThreads) {
@@ -1003,6 +1042,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
             if ((t & 31) < M) m.omegaEta[(t >> 5) * 64 + (t & 31)] = log(sm.vout[t >> 5][t & 31]) - sm.cshift[t >> 5][t & 31];
         if (tid == 0) atomicAdd(m.chol_count, (unsigned long long)sm.nchol);
         if (ts && tid == 0) atomicMax(&ts[((J - 1) * 4 + 1) * 2 + 1], gtimer());
+        if (pad_epoch != 0u && tid == 0) *reinterpret_cast<volatile unsigned int *>(&g_pad_epoch) = pad_epoch;
     }
 }
 
@@ -1016,7 +1056,7 @@ __global__ void __launch_bounds__(256) k_ystats_small(const ChainModel *const *m
     const int r = blockIdx.x % r0_max;
     const ChainLayer &ly = m.layer[0];
     if (r >= ly.R) return;
-    const int M = m.M, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = m.M, tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(kFull, tid >> 5, 0);
     const int64_t lo = ly.offsets[r], hi = ly.offsets[r + 1];
     const double inv2L = ly.inv2L[r], rs = ly.rsqrtL[r];
     double T[NV];
@@ -1067,7 +1107,7 @@ __global__ void __launch_bounds__(256) k_l0_fix_small(const ChainModel *const *m
     const int r = blockIdx.x % r0_max;
     const ChainLayer &ly = m.layer[0];
     if (r >= ly.R) return;
-    const int M = m.M, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = m.M, tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(kFull, tid >> 5, 0);
     for (int t = tid; t < MP * 2; t += 256) sA[t] = t < M * 2 ? ly.A[(size_t)r * M * 2 + t] : 0.0;
     for (int t = tid; t < MP; t += 256) sC[t] = t < M ? ly.cm2[(size_t)r * M + t] : 0.0;
     __syncthreads();
@@ -1135,8 +1175,14 @@ int launch_impl(const ChainModel *const *models_dev, int n_models, int cluster, 
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
+    // Occupancy experiment (profiles/r02_chain_cycles.md): MRGP_CHAIN_PAD=k adds k clusters without a model, which exit
+    // at once (MRGP_CHAIN_PAD_SPIN unset) or stay resident until the model clusters are done (=1; direct launches only).
+    static const int pad = getenv("MRGP_CHAIN_PAD") ? atoi(getenv("MRGP_CHAIN_PAD")) : 0;
+    static const bool pad_spin = getenv("MRGP_CHAIN_PAD_SPIN") && getenv("MRGP_CHAIN_PAD_SPIN")[0] == '1';
+    static unsigned int epoch = 0;
+    const unsigned int pad_epoch = (pad > 0 && pad_spin) ? ++epoch : 0u;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_models * cluster));
+    cfg.gridDim = dim3((unsigned)((n_models + (pad > 0 ? pad : 0)) * cluster));
     cfg.blockDim = dim3(kChainThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -1147,7 +1193,7 @@ int launch_impl(const ChainModel *const *models_dev, int n_models, int cluster, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, k_ci_sweep<MP>, models_dev);
+    return (int)cudaLaunchKernelEx(&cfg, k_ci_sweep<MP>, models_dev, n_models, pad_epoch);
 }
 
 }  // namespace

@@ -140,6 +140,9 @@ struct mrgp_handle {
     uint64_t stream_ops = 0;         // asynchronous work queued on the handle's stream from outside a sweep (groups order after it)
     bool split_kernels = false;      // MRGP_SPLIT=1: lane-split statistics kernel (experiment, 30 % slower: profiles/r02_ncu_summary.md)
     bool fused = true;               // MRGP_FUSED=0: the multi-kernel sweep of round 1
+    int chain_pf_mode = 1;           // MRGP_CHAIN_PF: L2 prefetch of the state by the fused sweep (0 off, 1 per line, 2 bulk)
+    bool direct_launch = false;      // MRGP_DIRECT=1: the fused sweep is launched on the stream, not through a graph (experiment)
+    bool skip_l0_fallback = false;   // MRGP_NO_L0_FALLBACK=1: timing experiment only (the guard still reports)
     int chain_cluster = 0;           // CTAs per model of the fused sweep (0: by the number of regions)
     bool inferred_shortcut = true;   // skip phase A where Phi^T r == 0 identically (MRGP_STREAM_ALL=1: stream everything)
     bool omega_warp = true;   // single-warp register-resident omega solve for M <= 32 (MRGP_OMEGA_BLOCK=1: block version)
@@ -1155,6 +1158,7 @@ int upload_chain_model(mrgp_handle *h) {
     m.J = h->cfg.n_layers;
     m.M = h->cfg.n_basis;
     m.DY = h->cfg.dy;
+    m.pf_mode = h->chain_pf_mode;
     m.sbase = reinterpret_cast<double *>(h->ws + h->state_begin);
     m.pf_base = h->ws + h->state_begin;
     m.pf_lines = (h->state_end - h->state_begin + 127) / 128;
@@ -1208,7 +1212,7 @@ int do_fused_sweep(mrgp_handle *h) {
     // terms; when the residual is tiny against sum |y|^2 (ratio below kChainGuard: high-SNR data) the sweep sets the
     // model's status word and the kernel below - a no-op otherwise - takes the statistics of layer 0 by a pass over the
     // samples and repeats its bias / noise update (nothing else of the sweep depends on them).
-    if (h->sharded) return MRGP_OK;   // (the sharded handle reports the status; its fallback would need an exchange)
+    if (h->sharded || h->skip_l0_fallback) return MRGP_OK;   // (the sharded handle reports the status; its fallback would need an exchange)
     if (ystats_small(h)) {
         const int e = launch_l0_fix_small(chain_solver_size(h->cfg.n_basis), h->chain_ptr_dev, 1, h->plan[0].R, h->stream);
         if (e != 0) return fail(h, MRGP_ECUDA, "layer-0 fallback launch: %s", cudaGetErrorString((cudaError_t)e));
@@ -1447,6 +1451,9 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     if (const char *e = getenv("MRGP_OMEGA_BLOCK")) h->omega_warp = !(e[0] == '1');
     if (const char *e = getenv("MRGP_STREAM_ALL")) h->inferred_shortcut = !(e[0] == '1');
     if (const char *e = getenv("MRGP_FUSED")) h->fused = !(e[0] == '0');
+    if (const char *e = getenv("MRGP_CHAIN_PF")) h->chain_pf_mode = atoi(e);
+    if (const char *e = getenv("MRGP_DIRECT")) h->direct_launch = e[0] == '1';
+    if (const char *e = getenv("MRGP_NO_L0_FALLBACK")) h->skip_l0_fallback = e[0] == '1';
     if (const char *e = getenv("MRGP_SPLIT")) h->split_kernels = !(e[0] == '0');
     if (const char *e = getenv("MRGP_CHAIN_PROF")) h->chain_prof_on = e[0] == '1';
     if (const char *e = getenv("MRGP_CHAIN_GUARD")) h->chain_guard_threshold = atof(e);
@@ -1969,6 +1976,12 @@ int mrgp_sweep(mrgp_handle *h, int32_t n_iter) {
         if ((rc = build_invariants(h))) return rc;
         if (!h->chain_uploaded && (rc = upload_chain_model(h))) return rc;
         if (!h->ystats_valid && (rc = do_ystats(h))) return rc;
+    }
+    if (fused && h->direct_launch) {
+        for (int it = 0; it < n_iter; ++it)
+            if ((rc = sweep_once(h, true))) return rc;   // count() adds the launches (not capturing)
+        h->sweeps_done += n_iter;
+        return MRGP_OK;
     }
     if (!h->graph_exec) {
         if ((rc = build_invariants(h))) return rc;

@@ -28,3 +28,6 @@ for j in range(res + 1):
     nxt = (p[j + 1][0] - r[9]) if j < res else 0
     print('L%d shared[%s] sync2=%d | solve[%s] ->next=%d | worker(other SM clock)[%s] | layer=%d' % (
         j, sh, r[6] - r[5], so, nxt, wo, (p[j + 1][0] - r[0]) if j < res else r[9] - r[0]))
+k = p[:4, 15]
+print('kernel (CTA 0 clock): prologue=%d loop=%d last finish + barrier=%d total=%d cycles' % (k[1] - k[0], k[2] - k[1], k[3] - k[2], k[3] - k[0]))
+print('background finish of layers 4.. (worker warp 0, cycles):', [int(v) for v in p[4:res, 15]])
