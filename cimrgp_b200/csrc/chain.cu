@@ -11,9 +11,20 @@
 //   * CTA 0 as a whole does the shared step of a layer (P2, P2a-c, S1, P3, S3 and the log omega_hat table:
 //     Posteriors.py:497-541, Stats.py:375-412) from the region sums that the CTAs leave in their shared memory
 //     (read over DSMEM).
-// Per layer: cluster barrier, shared step on CTA 0, cluster barrier, then the solver works on omega(j) WHILE the
-// workers finish layer j (S2, P4/P5) and prepare the region sums of layer j + 1 (which need the ARD moments of layer
-// j but not omega(j)).  Sums are formed in a fixed order: results are bit-reproducible for a cluster size.
+// Per layer: the region sums reach CTA 0, shared step on CTA 0, its results reach the workers, then the solver works
+// on omega(j) WHILE the workers finish layer j (S2, P4/P5) and prepare the region sums of layer j + 1 (which need the
+// ARD moments of layer j but not omega(j)).  Sums are formed in a fixed order: results are bit-reproducible for a
+// cluster size.
+//
+// Hand-offs inside a cluster of C >= 2 CTAs are PUSHES over DSMEM, signalled through mbarriers (a hardware cluster
+// barrier costs ~1.2k cycles with 16 CTAs and waits for every thread; a remote store + remote mbarrier arrive costs one
+// DSMEM hop and only the consumer waits):
+//   A(j): every worker CTA stores its region sums into its slot of CTA 0 and arrives (release.cluster) on CTA 0's barA;
+//   B(j): CTA 0 stores the axis covariances / ARD means of layer j into loc[j & 1] of every worker CTA and arrives on
+//         its barB - and goes on to the solve without waiting for anybody;
+//   F(j): S2 / P4 / P5 of layer j + 1 read moments that OTHER worker CTAs wrote for layer j (global memory): every worker
+//         CTA arrives on every worker's barF when its share of layer j is done and waits for phase j before layer j + 1.
+// A cluster of one CTA (batch of small models) keeps the two barriers per layer (its "cluster" barrier is a CTA barrier).
 #include "mrgp_chain.h"
 
 #include <cooperative_groups.h>
@@ -58,6 +69,37 @@ __device__ __forceinline__ void wsum_n(double (&v)[N]) {
         for (int k = 0; k < N; ++k) v[k] += __shfl_xor_sync(kFull, v[k], o);
     }
 }
+// ---- DSMEM pushes and mbarriers at cluster scope ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// address of the same shared-memory variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t remote_addr(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_remote(uint32_t addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+// one arrival on the mbarrier at cluster address `addr`; publishes the writes that happen before it (cumulative over
+// __syncwarp / CTA barriers) to the CTA that owns the barrier
+__device__ __forceinline__ void bar_arrive_remote(uint32_t addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+// wait for the phase of parity `parity` of a barrier of this CTA; acquires what the arriving CTAs published
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
 // split cluster barrier: arrive publishes this thread's writes, wait makes the others' visible
 __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -74,7 +116,9 @@ struct ChainSmem {
     double primeB[32 * 4], primeLogC[32], primeShape[32], primeScale[32], sk[32], skNext[32];
     double B[32 * 4], kappa[32 * 2], rho[32 * 2], logC[32], cov[32 * 4], shape[32], scale[32], mean[32], lmean[32];
     double part[8][7][32];    // per-warp region sums of the P1-finish step
-    double ctaPart[7 * 32];   // per-CTA sums, read by CTA 0 over DSMEM
+    double ctaPart[7 * 32];   // per-CTA sums (cluster of one CTA; a cluster of several pushes them into `slots` of CTA 0)
+    double slots[kChainMaxCluster][7 * 32];   // CTA 0: the per-CTA sums of the worker CTAs, written by them over DSMEM
+    uint64_t barA, barB, barF;                // mbarriers of the hand-offs (see the head of the file)
     double data[7 * 32];      // cluster sums (CTA 0)
     double pub[4 * 32];       // CTA 0: axis covariance (c00, c01, c11) and ARD mean of the layer, read by every CTA
     double loc[2][4 * 32];    // local copies of pub, by layer parity (the background step of layer j reads its copy while
@@ -686,24 +730,26 @@ __device__ __forceinline__ double digamma_chain(double x) {
 }
 
 // ---- the shared step of a layer on CTA 0 (256 threads) ------------------------------------------------------------
-__device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, cg::cluster_group &cluster, int j, int tid, unsigned C) {
+__device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, int j, int tid, unsigned C) {
     const int M = m.M, lane = tid & 31, warp = __shfl_sync(kFull, tid >> 5, 0);   // (warp-uniform for the compiler)
     const ChainLayer &ly = m.layer[j];
     if (tid == 0) PROF(0);
     // region sums of the cluster, in rank order (all DSMEM loads of a thread in flight at once)
     if (tid < 7 * 32) {
-        double pv[kChainMaxCluster];
-#pragma unroll
-        for (unsigned r = 0; r < kChainMaxCluster; ++r) pv[r] = r < C ? cluster.map_shared_rank(sm.ctaPart, r)[tid] : 0.0;
-        double s = pv[0];
-#pragma unroll
-        for (unsigned r = 1; r < kChainMaxCluster; ++r) s += pv[r];
-        sm.data[tid] = s;
+        if (C >= 2) {    // the slots of the worker CTAs (local shared memory: they pushed), in rank order
+            double s = 0.0;
+            for (unsigned r = 1; r < C; ++r) s += sm.slots[r][tid];
+            sm.data[tid] = s;
+        } else {
+            sm.data[tid] = sm.ctaPart[tid];
+        }
     }
     // snapshot of the previous posterior: the pristine prior for layer 0, the posterior of layer j - 1 otherwise
-    // (MRGP.py:575 / :581); its k-only terms of the table were prepared beside the previous solve
-    if (tid >= 224 && tid - 224 < M) {
-        const int t = tid - 224;
+    // (MRGP.py:575 / :581); its k-only terms of the table were prepared beside the previous solve BY THIS WARP (the
+    // warps of CTA 0 other than the solver arrive here while the solve of layer j - 1 is still running: nothing that
+    // the solver reads or writes may be touched before the barrier below)
+    if (warp == 1 && lane < M) {
+        const int t = lane;
         if (j == 0) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) sm.primeB[t * 4 + q] = m.priorB[t * 4 + q];
@@ -786,6 +832,14 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
     }
     __syncthreads();
     if (tid == 0) PROF(3);
+    if (C >= 2 && warp >= 4) {   // B(j): warps 4-7 push the 4 x 32 values to every worker CTA, lane r - 1 then arrives on CTA r
+        const int t = tid - 128;
+        const double v = sm.pub[t];
+        const uint32_t dst = smem_addr(&sm.loc[j & 1][t]);
+        for (unsigned r = 1; r < C; ++r) st_remote(remote_addr(dst, r), v);
+        __syncwarp();
+        if (lane + 1 < (int)C) bar_arrive_remote(remote_addr(smem_addr(&sm.barB), lane + 1));
+    }
     // S4, the table (Stats.py:405-412; a true matrix product inside the trace): a warp per row, the row maxima on the
     // way; the (at most 4) rows of a warp are independent instruction streams
     const bool last_layer = j == m.J - 1;
@@ -869,14 +923,34 @@ __device__ __forceinline__ void layer_finish(const ChainModel &m, int j, int ww,
     }
 }
 
+// Region sums of a worker CTA for the shared step: the warps' partial sums (registers) are added in warp order; a
+// cluster of several CTAs pushes the result into this CTA's slot of CTA 0 and arrives on its barA (7 warps per CTA).
+__device__ __forceinline__ void publish_sums(ChainSmem &sm, const double (&acc)[7], bool early, unsigned rank, int warp, int lane, int w0, int wt,
+                                             int wthreads) {
+#pragma unroll
+    for (int q = 0; q < 7; ++q) sm.part[warp][q][lane] = acc[q];
+    worker_bar(wthreads);
+    const uint32_t slot = early ? remote_addr(smem_addr(&sm.slots[rank][0]), 0) : 0u;
+    for (int v = wt; v < 7 * 32; v += wthreads) {
+        double s = 0.0;
+        for (int w = w0; w < 8; ++w) s += sm.part[w][v >> 5][v & 31];
+        if (early)
+            st_remote(slot + (uint32_t)v * 8u, s);
+        else
+            sm.ctaPart[v] = s;
+    }
+    if (early && warp < 7) {
+        __syncwarp();
+        if (lane == 0) bar_arrive_remote(remote_addr(smem_addr(&sm.barA), 0));
+    }
+}
+
 // Cluster of C CTAs per model.  C >= 2: CTA 0 runs the shared step and the solver, the warps of CTAs 1 .. C-1 are the
 // workers and finish layer j (S2, P4 / P5) in the BACKGROUND: they arrive at the cluster barrier as soon as the region
 // sums of layer j + 1 are published and do that work before they wait, so the chain on CTA 0 never waits for it.
 // C == 1 (a batch of small models, one CTA each): warp 0 solves while warps 1-7 do the worker steps of the layer.
-__device__ unsigned int g_pad_epoch;   // experiment (MRGP_CHAIN_PAD): last launch whose model clusters have finished
-
 template <int MP>
-__global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel *const *models, int n_models, unsigned int pad_epoch) {
+__global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel *const *models) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ChainSmem &sm = *reinterpret_cast<ChainSmem *>(smem_raw);
     cg::cluster_group cluster = cg::this_cluster();
@@ -885,12 +959,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
     // shuffles inside the solver / worker roles (otherwise each one is bracketed by a WARPSYNC and serialised)
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(kFull, tid >> 5, 0);
     const long long t_begin = clock64();
-    if ((int)(blockIdx.x / C) >= n_models) {   // padding clusters of the occupancy experiment: no model
-        if (pad_epoch != 0u && tid == 0) {     // stay resident until the model clusters are done (bounded: 2 ms)
-            const unsigned long long t0 = gtimer();
-            while (*reinterpret_cast<volatile unsigned int *>(&g_pad_epoch) != pad_epoch && gtimer() - t0 < 2000000ull) __nanosleep(500);
+    if (C >= 2) {    // the hand-off barriers; their initialisation is cluster-visible after the (one) cluster barrier of the prologue
+        if (tid == 0) {
+            bar_init(&sm.barA, 7u * (C - 1u));   // 7 warps of every worker CTA push a slice of its region sums
+            bar_init(&sm.barB, 4u);              // 4 warps of CTA 0 push the covariances / ARD means
+            bar_init(&sm.barF, C - 1u);          // every worker CTA, once its share of a layer is finished
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        return;
+        cl_arrive();
     }
     {
         const ChainModel *gm = models[blockIdx.x / C];
@@ -945,21 +1021,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
         sm.loc[0][tid] = am;
         sm.loc[1][tid] = am;
     }
-    if (tid < 7 * 32) sm.ctaPart[tid] = 0.0;   // a CTA without worker warps (CTA 0 of a cluster of several) contributes zeros
+    if (tid < 7 * 32) sm.ctaPart[tid] = 0.0;
     __syncthreads();
+    if (early) cl_wait();
     double acc[7];
 #pragma unroll
     for (int q = 0; q < 7; ++q) acc[q] = 0.0;
     if (worker) {
         layer_mid1(m, 0, ww, n_workers, lane, sm.loc[0] + 96, acc);
-#pragma unroll
-        for (int q = 0; q < 7; ++q) sm.part[warp][q][lane] = acc[q];
-        worker_bar(wthreads);
-        for (int v = wt; v < 7 * 32; v += wthreads) {
-            double s = 0.0;
-            for (int w = w0; w < 8; ++w) s += sm.part[w][v >> 5][v & 31];
-            sm.ctaPart[v] = s;
-        }
+        publish_sums(sm, acc, early, rank, warp, lane, w0, wt, wthreads);
     }
 
     if (m.prof && J >= 4 && rank == 0 && tid == 0) {   // whole-kernel stamps of CTA 0 in slot 15 of rows 0 .. 3 (needs J >= 4)
@@ -970,20 +1040,30 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
     // unrolled worker steps and has to stay in the instruction caches).
     for (int j = 0; j <= J; ++j) {
         if (j == J && m.prof && J >= 4 && rank == 0 && tid == 0) m.prof[2 * 16 + 15] = (double)clock64();
-        cl_arrive();                                       // A_j: this thread's share of the region sums of layer j is published
+        if (!early) cl_arrive();                           // A_j: this thread's share of the region sums of layer j is published
         if (worker && j > 0) {   // S2 and P4 / P5 of layer j - 1 in the background of the chain (C >= 2) / of the solve (C == 1)
             const long long tf = clock64();
+            if (early && j > 1) bar_wait(&sm.barF, (unsigned)(j - 2) & 1u);   // F(j - 2): the moments of the coarser layers are complete
             layer_finish(m, j - 1, ww, n_workers, lane, sm.loc[(j - 1) & 1]);
+            if (early && j < J) {                                             // F(j - 1) to every worker CTA
+                worker_bar(wthreads);
+                if (warp == 0 && lane + 1 < (int)C) bar_arrive_remote(remote_addr(smem_addr(&sm.barF), lane + 1));
+            }
             if (m.prof && j > 4 && ww == 0 && lane == 0) m.prof[(j - 1) * 16 + 15] = (double)(clock64() - tf);   // rows >= 4: its cycles
         }
-        cl_wait();
+        if (!early) cl_wait();
         if (j == J) break;
         if (rank == 0) {
+            if (early) bar_wait(&sm.barA, (unsigned)j & 1u);                  // A(j): the region sums of every worker CTA are in `slots`
             if (ts && tid == 0) atomicMin(&ts[(j * 4 + 3) * 2], gtimer());
-            shared_step(m, sm, cluster, j, tid, C);
+            shared_step(m, sm, j, tid, C);
         }
-        cl_arrive();                                       // B_j: axis covariance, ARD moments and the table of layer j
-        cl_wait();
+        if (!early) {
+            cl_arrive();                                   // B_j: axis covariance, ARD moments and the table of layer j
+            cl_wait();
+        } else if (rank == 0) {
+            __syncthreads();                               // the table of layer j is complete (the solver reads all of it)
+        }
         if (solver) {
             omega_solve_warp<MP>(m, sm, j, lane);
             if (ts && lane == 0) atomicMax(&ts[(j * 4 + 3) * 2 + 1], gtimer());
@@ -995,21 +1075,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
             if (ts && stamp) atomicMin(&ts[(j * 4 + 1) * 2], gtimer());
             if (stamp) PROF(10);
             double *loc = sm.loc[j & 1];
-            const double *pub = cluster.map_shared_rank(sm.pub, 0);
-            for (int v = wt; v < 4 * 32; v += wthreads) loc[v] = pub[v];
-            worker_bar(wthreads);
+            if (early) {
+                bar_wait(&sm.barB, (unsigned)j & 1u);      // B(j): CTA 0 has pushed the layer's covariances / ARD means into loc
+            } else {
+                for (int v = wt; v < 4 * 32; v += wthreads) loc[v] = sm.pub[v];
+                worker_bar(wthreads);
+            }
             if (stamp) PROF(11);
 #pragma unroll
             for (int q = 0; q < 7; ++q) acc[q] = 0.0;
-            if (j + 1 < J) layer_mid1(m, j + 1, ww, n_workers, lane, loc + 96, acc);
-#pragma unroll
-            for (int q = 0; q < 7; ++q) sm.part[warp][q][lane] = acc[q];
-            if (stamp) PROF(12);
-            worker_bar(wthreads);
-            for (int v = wt; v < 7 * 32; v += wthreads) {
-                double s = 0.0;
-                for (int w = w0; w < 8; ++w) s += sm.part[w][v >> 5][v & 31];
-                sm.ctaPart[v] = s;
+            if (j + 1 < J) {
+                layer_mid1(m, j + 1, ww, n_workers, lane, loc + 96, acc);
+                if (stamp) PROF(12);
+                publish_sums(sm, acc, early, rank, warp, lane, w0, wt, wthreads);
             }
             if (stamp) PROF(13);
             if (ts && stamp) atomicMax(&ts[(j * 4 + 1) * 2 + 1], gtimer());
@@ -1019,6 +1097,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
     if (m.prof && J >= 4 && rank == 0 && tid == 0) m.prof[3 * 16 + 15] = (double)clock64();
     // ---- the shared posterior / stats left by the last layer (Posteriors.py:482-541, Stats.py:354-420) ----------
     if (rank == 0) {
+        __syncthreads();   // the last solve (warp 0) is complete
         for (int t = tid; t < M * M; t += kChainThreads) {
             const int i = t / M, k = t - i * M;
             m.omega[t] = sm.omT[k * LD + i];
@@ -1042,7 +1121,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
             if ((t & 31) < M) m.omegaEta[(t >> 5) * 64 + (t & 31)] = log(sm.vout[t >> 5][t & 31]) - sm.cshift[t >> 5][t & 31];
         if (tid == 0) atomicAdd(m.chol_count, (unsigned long long)sm.nchol);
         if (ts && tid == 0) atomicMax(&ts[((J - 1) * 4 + 1) * 2 + 1], gtimer());
-        if (pad_epoch != 0u && tid == 0) *reinterpret_cast<volatile unsigned int *>(&g_pad_epoch) = pad_epoch;
     }
 }
 
@@ -1175,14 +1253,8 @@ int launch_impl(const ChainModel *const *models_dev, int n_models, int cluster, 
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    // Occupancy experiment (profiles/r02_chain_cycles.md): MRGP_CHAIN_PAD=k adds k clusters without a model, which exit
-    // at once (MRGP_CHAIN_PAD_SPIN unset) or stay resident until the model clusters are done (=1; direct launches only).
-    static const int pad = getenv("MRGP_CHAIN_PAD") ? atoi(getenv("MRGP_CHAIN_PAD")) : 0;
-    static const bool pad_spin = getenv("MRGP_CHAIN_PAD_SPIN") && getenv("MRGP_CHAIN_PAD_SPIN")[0] == '1';
-    static unsigned int epoch = 0;
-    const unsigned int pad_epoch = (pad > 0 && pad_spin) ? ++epoch : 0u;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((n_models + (pad > 0 ? pad : 0)) * cluster));
+    cfg.gridDim = dim3((unsigned)(n_models * cluster));
     cfg.blockDim = dim3(kChainThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -1193,7 +1265,7 @@ int launch_impl(const ChainModel *const *models_dev, int n_models, int cluster, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, k_ci_sweep<MP>, models_dev, n_models, pad_epoch);
+    return (int)cudaLaunchKernelEx(&cfg, k_ci_sweep<MP>, models_dev);
 }
 
 }  // namespace
