@@ -19,9 +19,10 @@
 // Hand-offs inside a cluster of C >= 2 CTAs are PUSHES over DSMEM, signalled through mbarriers (a hardware cluster
 // barrier costs ~1.2k cycles with 16 CTAs and waits for every thread; a remote store + remote mbarrier arrive costs one
 // DSMEM hop and only the consumer waits):
-//   A(j): every worker CTA stores its region sums into its slot of CTA 0 and arrives (release.cluster) on CTA 0's barA;
-//   B(j): CTA 0 stores the axis covariances / ARD means of layer j into loc[j & 1] of every worker CTA and arrives on
-//         its barB - and goes on to the solve without waiting for anybody;
+//   A(j): every worker CTA stores its region sums into its slot of CTA 0 with st.async, counted on CTA 0's barA;
+//   B(j): CTA 0 stores the axis covariances / ARD means of layer j into loc[j & 1] of every worker CTA with st.async,
+//         counted on its barB - and goes on to the solve without waiting for anybody;
+//         (st.async: data and completion travel together - a release.cluster arrive costs a MEMBAR.GPU instead)
 //   F(j): S2 / P4 / P5 of layer j + 1 read moments that OTHER worker CTAs wrote for layer j (global memory): every worker
 //         CTA arrives on every worker's barF when its share of layer j is done and waits for phase j before layer j + 1.
 // A cluster of one CTA (batch of small models) keeps the two barriers per layer (its "cluster" barrier is a CTA barrier).
@@ -77,7 +78,16 @@ __device__ __forceinline__ uint32_t remote_addr(uint32_t local, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_remote(uint32_t addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+// asynchronous store of one double into the shared memory of another CTA of the cluster; its completion is counted (8
+// bytes) on the mbarrier `bar` of that CTA: data and signal travel together, no fence on either side
+__device__ __forceinline__ void st_async_remote(uint32_t addr, double v, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(addr), "d"(v), "r"(bar) : "memory");
+}
+// arm the current phase of a barrier of this CTA: one arrival (the barriers of the pushes are initialised with count 1)
+// and `bytes` of asynchronous stores to come
+__device__ __forceinline__ void bar_expect(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
 }
@@ -86,7 +96,21 @@ __device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void bar_arrive_remote(uint32_t addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
-// wait for the phase of parity `parity` of a barrier of this CTA; acquires what the arriving CTAs published
+// wait for the phase of parity `parity` of a barrier that counts asynchronous stores (their data is visible with it)
+__device__ __forceinline__ void bar_wait_tx(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+// wait for the phase of parity `parity` of a barrier of this CTA; acquires what the arriving CTAs published (global memory)
 __device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -105,6 +129,7 @@ __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arri
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void worker_bar(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 
+constexpr unsigned kSumBytes = 7 * 32 * 8, kPubBytes = 4 * 32 * 8;   // region sums of a CTA, covariances + ARD means of a layer
 constexpr int LD = 34;    // row stride of the transposed tables: conflict-free columns, 16-byte aligned rows
 constexpr int LW = 33;    // row stride of the log omega_hat table
 
@@ -832,13 +857,11 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
     }
     __syncthreads();
     if (tid == 0) PROF(3);
-    if (C >= 2 && warp >= 4) {   // B(j): warps 4-7 push the 4 x 32 values to every worker CTA, lane r - 1 then arrives on CTA r
+    if (C >= 2 && warp >= 4) {   // B(j): warps 4-7 push the 4 x 32 values to every worker CTA
         const int t = tid - 128;
         const double v = sm.pub[t];
-        const uint32_t dst = smem_addr(&sm.loc[j & 1][t]);
-        for (unsigned r = 1; r < C; ++r) st_remote(remote_addr(dst, r), v);
-        __syncwarp();
-        if (lane + 1 < (int)C) bar_arrive_remote(remote_addr(smem_addr(&sm.barB), lane + 1));
+        const uint32_t dst = smem_addr(&sm.loc[j & 1][t]), bar = smem_addr(&sm.barB);
+        for (unsigned r = 1; r < C; ++r) st_async_remote(remote_addr(dst, r), v, remote_addr(bar, r));
     }
     // S4, the table (Stats.py:405-412; a true matrix product inside the trace): a warp per row, the row maxima on the
     // way; the (at most 4) rows of a warp are independent instruction streams
@@ -924,24 +947,21 @@ __device__ __forceinline__ void layer_finish(const ChainModel &m, int j, int ww,
 }
 
 // Region sums of a worker CTA for the shared step: the warps' partial sums (registers) are added in warp order; a
-// cluster of several CTAs pushes the result into this CTA's slot of CTA 0 and arrives on its barA (7 warps per CTA).
+// cluster of several CTAs pushes the result into this CTA's slot of CTA 0 (counted on its barA).
 __device__ __forceinline__ void publish_sums(ChainSmem &sm, const double (&acc)[7], bool early, unsigned rank, int warp, int lane, int w0, int wt,
                                              int wthreads) {
 #pragma unroll
     for (int q = 0; q < 7; ++q) sm.part[warp][q][lane] = acc[q];
     worker_bar(wthreads);
     const uint32_t slot = early ? remote_addr(smem_addr(&sm.slots[rank][0]), 0) : 0u;
+    const uint32_t bar = early ? remote_addr(smem_addr(&sm.barA), 0) : 0u;
     for (int v = wt; v < 7 * 32; v += wthreads) {
         double s = 0.0;
         for (int w = w0; w < 8; ++w) s += sm.part[w][v >> 5][v & 31];
         if (early)
-            st_remote(slot + (uint32_t)v * 8u, s);
+            st_async_remote(slot + (uint32_t)v * 8u, s, bar);
         else
             sm.ctaPart[v] = s;
-    }
-    if (early && warp < 7) {
-        __syncwarp();
-        if (lane == 0) bar_arrive_remote(remote_addr(smem_addr(&sm.barA), 0));
     }
 }
 
@@ -961,10 +981,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
     const long long t_begin = clock64();
     if (C >= 2) {    // the hand-off barriers; their initialisation is cluster-visible after the (one) cluster barrier of the prologue
         if (tid == 0) {
-            bar_init(&sm.barA, 7u * (C - 1u));   // 7 warps of every worker CTA push a slice of its region sums
-            bar_init(&sm.barB, 4u);              // 4 warps of CTA 0 push the covariances / ARD means
+            bar_init(&sm.barA, 1u);              // armed by this CTA per layer; counts the bytes of the pushed region sums
+            bar_init(&sm.barB, 1u);              // likewise, the bytes of the pushed covariances / ARD means
             bar_init(&sm.barF, C - 1u);          // every worker CTA, once its share of a layer is finished
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if (rank == 0)
+                bar_expect(&sm.barA, (C - 1u) * kSumBytes);
+            else
+                bar_expect(&sm.barB, kPubBytes);
         }
         cl_arrive();
     }
@@ -1054,7 +1078,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
         if (!early) cl_wait();
         if (j == J) break;
         if (rank == 0) {
-            if (early) bar_wait(&sm.barA, (unsigned)j & 1u);                  // A(j): the region sums of every worker CTA are in `slots`
+            if (early) {                                                     // A(j): the region sums of every worker CTA are in `slots`
+                bar_wait_tx(&sm.barA, (unsigned)j & 1u);
+                if (tid == 0 && j + 1 < J) bar_expect(&sm.barA, (C - 1u) * kSumBytes);   // (phase j + 1 cannot complete before B(j) is out)
+            }
             if (ts && tid == 0) atomicMin(&ts[(j * 4 + 3) * 2], gtimer());
             shared_step(m, sm, j, tid, C);
         }
@@ -1076,7 +1103,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
             if (stamp) PROF(10);
             double *loc = sm.loc[j & 1];
             if (early) {
-                bar_wait(&sm.barB, (unsigned)j & 1u);      // B(j): CTA 0 has pushed the layer's covariances / ARD means into loc
+                bar_wait_tx(&sm.barB, (unsigned)j & 1u);   // B(j): CTA 0 has pushed the layer's covariances / ARD means into loc
+                if (tid == 0 && j + 1 < J) bar_expect(&sm.barB, kPubBytes);
             } else {
                 for (int v = wt; v < 4 * 32; v += wthreads) loc[v] = sm.pub[v];
                 worker_bar(wthreads);
