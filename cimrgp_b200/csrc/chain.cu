@@ -129,13 +129,13 @@ __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arri
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void worker_bar(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 
+constexpr int kChainAndersonIters = 48;   // accelerated evaluations before the plain Sinkhorn sweeps take over
 constexpr unsigned kSumBytes = 7 * 32 * 8, kPubBytes = 4 * 32 * 8;   // region sums of a CTA, covariances + ARD means of a layer
 constexpr int LD = 34;    // row stride of the transposed tables: conflict-free columns, 16-byte aligned rows
 constexpr int LW = 33;    // row stride of the log omega_hat table
 
 struct ChainSmem {
     double omT[32 * LD];      // omega transposed: omT[k * LD + i] = omega_ik
-    double T[32 * LD];        // solver scratch (transposes, Cholesky columns)
     double Kt[32 * LD];       // shifted, exponentiated table, column-major: Kt[k * LD + i] = K_ik
     double lw[32 * LW];       // log omega_hat, row-major
     double primeB[32 * 4], primeLogC[32], primeShape[32], primeScale[32], sk[32], skNext[32];
@@ -459,10 +459,16 @@ __device__ __forceinline__ void mid2_stats_upper(const ChainModel &m, const Chai
 }
 
 // ---- the solver (one warp) ---------------------------------------------------------------------------------------
-// Same iteration as k_scale_warp / omega_solve_serial: warm start from the previous sweep's column scalings, Sinkhorn
-// while it contracts fast, Newton on the log column scalings otherwise, cold restart on a non-finite residual, plain
-// Sinkhorn sweeps as the last resort; tolerance kOmegaTol.  MP rows / columns live in the registers of MP lanes; for
-// M < MP the table is padded with an identity block (its scalings stay at 1 and do not couple to the model's block).
+// The fixed point of omega_solve_serial (mrgp_math.cuh; tolerance kOmegaTol on the column sums, rows exact), reached by
+// Anderson-accelerated Sinkhorn instead of Sinkhorn / Newton steps: on x = log v the Sinkhorn map is g(x) = -log(K^T u),
+// u = 1 / (K e^x); with the residual f = g(x) - x (its mean removed: g(x + a) = g(x) + a) and the last three differences
+// dX, dF of the iterates and residuals, the next iterate is x + f - sum_a gamma_a (dX_a + dF_a), gamma the least-squares
+// solution of dF gamma = f (3 x 3 normal equations, columns scaled, ridge).  On the tables of the model this takes 2-15
+// evaluations where Sinkhorn needs up to 160 and where a Newton step (Cholesky of the 30 x 30 dual Hessian by one warp)
+// costs as much as 16 evaluations (profiles/r02_chain_cycles.md).  Warm start from the previous sweep's column
+// scalings, history dropped when the residual grows, cold restart on a non-finite residual, plain Sinkhorn sweeps as the
+// last resort.  MP rows / columns live in the registers of MP lanes; for M < MP the table is padded with an identity
+// block (its scalings stay at 1 and do not couple to the model's block).
 // One evaluation of the scaling iteration: u = 1 / (K v) (rows normalised exactly), s = K^T u, c = v s (column sums of
 // P = diag(u) K diag(v)).  Lane i keeps BOTH row i (Kr) and column i (Kc) of the table in registers, v and u travel
 // through two 32-entry arrays in shared memory (broadcast loads): no transposes and no shuffles inside the loop.
@@ -516,7 +522,7 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
     const int M = m.M, j = layer;
     if (lane == 0) PROF(6);
     const bool row = lane < MP, real = lane < M;
-    double *T = sm.T, *sv = sm.sv, *su = sm.su;
+    double *sv = sm.sv, *su = sm.su;
     double Kr[MP], Kc[MP];
     // padding (M <= index < MP): an identity block, its scalings stay at 1 and do not couple to the model's block
 #pragma unroll
@@ -532,137 +538,97 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
     }
     const double cshift = real ? sm.colmax[lane] : 0.0;
     const bool warm = sm.warm[layer] > 0.5;
-    double v = 1.0;
+    double x = 0.0;                                     // log v of this lane's column (0 on the padding)
     if (real) {
         const double eta = sm.eta[layer][lane] + cshift;
-        v = (warm && isfinite(eta)) ? exp(fmax(-600.0, fmin(600.0, eta))) : 1.0;
+        x = (warm && isfinite(eta)) ? fmax(-600.0, fmin(600.0, eta)) : 0.0;
     }
     int iters = 0;
-    double err_prev = INFINITY, c = 1.0, u = 0.0, vs = 1.0;
-    int last = kOmegaNone;
+    double err_prev = INFINITY, c = 1.0, u = 0.0, vs = 1.0, v = 1.0;
     bool converged = false;
-    const double inv_m = 1.0 / (double)M;
+    const double dm = (double)M, inv_m = 1.0 / dm;
+    // Anderson history, newest first: differences of the iterates / centred residuals (per lane) and their Gram matrix
+    double xp = 0.0, fp = 0.0, dX0 = 0.0, dX1 = 0.0, dX2 = 0.0, dF0 = 0.0, dF1 = 0.0, dF2 = 0.0;
+    double g00 = 0.0, g01 = 0.0, g02 = 0.0, g11 = 0.0, g12 = 0.0, g22 = 0.0;
+    int nh = 0;
+    bool have_prev = false;
     if (lane == 0) PROF(7);
-    for (int it = 0; it < kOmegaWarmup + kOmegaMaxNewton; ++it) {
+    for (int it = 0; it < kChainAndersonIters; ++it) {
         ++iters;
+        v = real ? exp(x) : 1.0;
         const double err = (double)omega_eval<MP>(Kr, Kc, sv, su, v, u, c, vs, row, lane);
         if (err < kOmegaTol) {
             converged = true;
             break;
         }
-        if (!isfinite(err)) {   // a bad (warm) start or an overshooting Newton step: start again from the shifts alone
-            v = 1.0;
+        if (!isfinite(err)) {   // a bad (warm) start: start again from the shifts alone
+            x = 0.0;
+            nh = 0;
+            have_prev = false;
             err_prev = INFINITY;
-            last = kOmegaNone;
             continue;
         }
-        if (!omega_take_newton(err, err_prev, last)) {
-            if (real) v = fmax(1e-280, fmin(1e280, vs));      // Sinkhorn column step v / c
-            err_prev = err;
-            last = kOmegaSinkhorn;
-            continue;
+        const double fr = real ? log(vs) - x : 0.0;       // g(x) - x, not centred yet
+        if (!(err <= err_prev)) {                         // the residual grew: drop the history, plain step from here
+            nh = 0;
+            have_prev = false;
         }
+        double fc, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+        if (have_prev) {
+            dX2 = dX1;
+            dX1 = dX0;
+            dF2 = dF1;
+            dF1 = dF0;
+            g22 = g11;
+            g12 = g01;
+            g11 = g00;
+            const double w = real ? fr - fp : 0.0;        // newest residual difference before centring (sum fp = 0)
+            dX0 = x - xp;
+            double sums[7] = {w, w * w, w * dF1, w * dF2, fr * w, fr * dF1, fr * dF2};
+            wsum_n<7>(sums);
+            const double mu = sums[0] * inv_m, mm = dm * mu * mu;
+            g00 = sums[1] - mm;
+            g01 = sums[2];
+            g02 = sums[3];
+            b0 = sums[4] - mm;
+            b1 = sums[5];
+            b2 = sums[6];
+            dF0 = real ? w - mu : 0.0;
+            fc = real ? fr - mu : 0.0;
+            nh = min(nh + 1, 3);
+        } else {
+            const double mu = wsum(fr) * inv_m;
+            fc = real ? fr - mu : 0.0;
+        }
+        xp = x;
+        fp = fc;
+        have_prev = true;
+        double xn = x + fc;                               // the Sinkhorn step (up to the scale of v)
+        if (nh > 0 && g00 > 0.0) {
+            // normal equations of the nh newest differences, columns scaled to unit length, ridge; Cholesky 3 x 3
+            const bool h1 = nh > 1 && g11 > 0.0, h2 = nh > 2 && h1 && g22 > 0.0;
+            const double d0 = rsqrt(g00), d1 = h1 ? rsqrt(g11) : 0.0, d2 = h2 ? rsqrt(g22) : 0.0;
+            const double a01 = g01 * d0 * d1, a02 = g02 * d0 * d2, a12 = g12 * d1 * d2;
+            const double r0 = b0 * d0, r1 = b1 * d1, r2 = b2 * d2;
+            constexpr double kDiag = 1.0 + 1e-8;
+            const double l00 = sqrt(kDiag), il00 = 1.0 / l00;
+            const double l10 = a01 * il00, l20 = a02 * il00;
+            const double t1 = kDiag - l10 * l10;
+            const double il11 = rsqrt(fmax(t1, 1e-300));
+            const double l21 = (a12 - l20 * l10) * il11;
+            const double t2 = kDiag - l20 * l20 - l21 * l21;
+            const double il22 = rsqrt(fmax(t2, 1e-300));
+            const double y0 = r0 * il00, y1 = (r1 - l10 * y0) * il11, y2 = (r2 - l20 * y0 - l21 * y1) * il22;
+            const double q2 = y2 * il22, q1 = (y1 - l21 * q2) * il11, q0 = (y0 - l10 * q1 - l20 * q2) * il00;
+            if (t1 > 0.0 && t2 > 0.0) {
+                const double c0 = q0 * d0, c1 = q1 * d1, c2 = q2 * d2;     // gamma
+                xn -= c0 * (dX0 + dF0) + c1 * (dX1 + dF1) + c2 * (dX2 + dF2);
+            }
+        }
+        x = real ? fmax(-640.0, fmin(640.0, xn)) : 0.0;
         err_prev = err;
-        last = kOmegaNewton;
-        // ---- Newton on the log column scalings.  The table P = diag(u) K diag(v), transposed, goes to shared memory
-        //      (T[k][i] = P_ik); lane j holds column j of P in Q.
-        double Q[MP];
-        {
-            const double2 *pv = reinterpret_cast<const double2 *>(sv);
-#pragma unroll
-            for (int k = 0; k < MP; k += 2) {
-                const double2 t = pv[k >> 1];
-                T[k * LD + lane] = Kr[k] * u * t.x;
-                T[(k + 1) * LD + lane] = Kr[k + 1] * u * t.y;
-            }
-            const double2 *pu = reinterpret_cast<const double2 *>(su);
-#pragma unroll
-            for (int i = 0; i < MP; i += 2) {
-                const double2 t = pu[i >> 1];
-                Q[i] = Kc[i] * t.x * v;
-                Q[i + 1] = Kc[i + 1] * t.y * v;
-            }
-        }
-        __syncwarp();
-        // ---- Newton matrix: lane j builds row j of diag(c) - P^T P + e e^T / M (e: the model's columns; the padding
-        //      columns get a unit diagonal) from its column Q and the transposed table
-        double H[MP];
-#pragma unroll
-        for (int k = 0; k < MP; k += 2) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            const double2 *r0 = reinterpret_cast<const double2 *>(T + k * LD);
-            const double2 *r1 = reinterpret_cast<const double2 *>(T + (k + 1) * LD);
-#pragma unroll
-            for (int i = 0; i < MP; i += 2) {
-                const double2 t0 = r0[i >> 1], t1 = r1[i >> 1];
-                a0 = fma(Q[i], t0.x, a0);
-                a1 = fma(Q[i + 1], t0.y, a1);
-                a2 = fma(Q[i], t1.x, a2);
-                a3 = fma(Q[i + 1], t1.y, a3);
-            }
-            const double add0 = (real && k < M) ? inv_m : ((lane == k && k >= M) ? 1.0 : 0.0);
-            const double add1 = (real && k + 1 < M) ? inv_m : ((lane == k + 1 && k + 1 >= M) ? 1.0 : 0.0);
-            H[k] = ((lane == k) ? c : 0.0) - (a0 + a1) + add0;
-            H[k + 1] = ((lane == k + 1) ? c : 0.0) - (a2 + a3) + add1;
-        }
-        // ---- Cholesky (right-looking, lane = row) fused with the forward substitution; the next pivot is formed
-        //      first in every step (one shuffle) so that its reciprocal square root overlaps the rank-1 update
-        double rhs = 1.0 - c, y = 0.0, dinv = 0.0;
-        double piv = __shfl_sync(kFull, H[0], 0);
-        double *colbuf = T;                                           // the transposed table is no longer needed
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < MP; ++k) {
-            const double di = rsqrt(piv);
-            H[k] *= di;                                               // l_ik for lanes i >= k (l_kk on lane k)
-            double *cb = colbuf + (k & 1) * 32;                       // two buffers: no barrier between the steps
-            cb[lane] = H[k];
-            if (k + 1 < MP)   // the next pivot only needs its own row: h_jj - l_jk^2 on lane j = k + 1
-                piv = __shfl_sync(kFull, fma(-H[k], H[k], H[k + 1]), k + 1);
-            const double yk = __shfl_sync(kFull, rhs, k) * di;
-            if (lane == k) {
-                dinv = di;
-                y = yk;
-            }
-            if (lane > k) rhs = fma(-H[k], yk, rhs);
-            __syncwarp();
-#pragma unroll
-            for (int jj = k + 1; jj < MP; ++jj) H[jj] = fma(-H[k], cb[jj], H[jj]);   // broadcast loads of l_jk
-        }
-        // ---- L^T x = y with the transposed factor: lane i reads l_ki, k > i, from shared memory -------------------
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < MP; ++k) T[k * LD + lane] = H[k];          // T[k][i] = l_ik (valid for i >= k)
-        __syncwarp();
-        {
-            const double2 *lt = reinterpret_cast<const double2 *>(T + (row ? lane : 0) * LD);
-#pragma unroll
-            for (int k = 0; k < MP; k += 2) {
-                const double2 t = lt[k >> 1];
-                Q[k] = t.x;                                           // l_k,lane
-                Q[k + 1] = t.y;
-            }
-        }
-        double x = 0.0;
-#pragma unroll
-        for (int k = MP - 1; k >= 0; --k) {
-            const double xk = __shfl_sync(kFull, y, k) * __shfl_sync(kFull, dinv, k);
-            if (lane == k) x = xk;
-            if (lane < k) y = fma(-Q[k], xk, y);
-        }
-        if (real) v = fmax(1e-280, fmin(1e280, v * exp(fmax(-30.0, fmin(30.0, x)))));
-        __syncwarp();
-        // the column registers made room for the Newton step: reload them
-        {
-            const double2 *col = reinterpret_cast<const double2 *>(sm.Kt + (real ? lane : 0) * LD);
-#pragma unroll
-            for (int i = 0; i < MP; i += 2) {
-                const double2 t = col[i >> 1];
-                Kc[i] = (real && i < M) ? t.x : ((row && !real && i == lane) ? 1.0 : 0.0);
-                Kc[i + 1] = (real && i + 1 < M) ? t.y : ((row && !real && i + 1 == lane) ? 1.0 : 0.0);
-            }
-        }
     }
+    if (!converged) v = real ? exp(x) : 1.0;
     if (lane == 0) PROF(8);
     // last resort: plain Sinkhorn sweeps (see omega_solve_serial); on model tables the loop is not entered
     for (int it = 0; it < kOmegaFallbackSweeps && !converged; ++it) {
@@ -879,6 +845,7 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
                 lwv[u] = tr + sm.sk[k] + (sm.primeShape[k] - 1.0) * sm.lmean[i] - sm.primeScale[k] * sm.mean[i];
                 sm.lw[i * LW + k] = lwv[u];
                 if (last_layer) m.logOmegaHat[i * M + k] = lwv[u];
+                if (m.tables) m.tables[((size_t)j * M + i) * M + k] = lwv[u];
             }
         }
 #pragma unroll

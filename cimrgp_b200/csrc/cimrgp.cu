@@ -129,7 +129,7 @@ struct mrgp_handle {
     const ChainModel **chain_ptr_dev = nullptr;
     ChainModel chain_host{};
     unsigned int *chain_status = nullptr;
-    double *chain_guard = nullptr, *chain_prof = nullptr;
+    double *chain_guard = nullptr, *chain_prof = nullptr, *chain_tables = nullptr;
     double chain_guard_threshold = kChainGuard;   // MRGP_CHAIN_GUARD overrides (tests of the streamed fallback)
     bool chain_prof_on = false;      // MRGP_CHAIN_PROF=1: SM-clock stamps of the fused sweep (field 54)
     const unsigned int *gate_next = nullptr;   // gate of the next phase-B launch (streamed fallback of the fused sweep)
@@ -428,6 +428,7 @@ size_t carve(mrgp_handle *h, char *base) {
         h->chain_status = c.take<unsigned int>(4);
         h->chain_guard = c.take<double>(2);
         h->chain_prof = c.take<double>((size_t)kMaxLayers * 16);
+        h->chain_tables = c.take<double>((size_t)kMaxLayers * 32 * 32);   // MRGP_CHAIN_PROF=1: log omega_hat of every layer (field 56)
     }
     return (c.off + 255) & ~(size_t)255;
 }
@@ -1175,6 +1176,7 @@ int upload_chain_model(mrgp_handle *h) {
     m.guard_threshold = h->chain_guard_threshold;
     m.ts = h->timeline ? h->ts : nullptr;
     m.prof = h->chain_prof_on ? h->chain_prof : nullptr;
+    m.tables = (h->chain_prof_on && h->cfg.n_basis <= 32) ? h->chain_tables : nullptr;
     for (int j = 0; j < m.J; ++j) {
         const LayerDev &d = h->dev[j];
         ChainLayer &l = m.layer[j];
@@ -1326,6 +1328,7 @@ FieldRef field_ref(mrgp_handle *h, int layer, int field) {
         SharedDev &s = h->sh;
         switch (field) {
             case 54: f = {h->chain_prof, (int64_t)h->cfg.n_layers * 16}; break;
+            case 56: f = {h->chain_tables, (int64_t)h->cfg.n_layers * h->cfg.n_basis * h->cfg.n_basis}; break;   // (J, M, M) tables of the last sweep
             case MRGP_F_FUSED_GUARD: f = {h->chain_guard, 2}; break;   // MRGP_CHAIN_PROF=1: clock stamps of the fused sweep
             case 52: f = {s.omegaK + 64 * 64 + 32, 3}; break;
             case 53: f = {s.omegaK + 64 * 64 + 40, 5}; break;   // MRGP_OMEGA_PROF builds: cycles of the k_ard phases   // MRGP_OMEGA_PROF builds: cycles of the Newton stages

@@ -61,6 +61,7 @@ struct ChainModel {
     double *guard;                 // [0]: last ratio sum |r|^2 / sum |y|^2 of layer 0; [1]: 1.0 once the guard tripped
     unsigned long long *ts;        // timeline stamps or null
     double *prof;                  // (J, 16) SM-clock stamps inside CTA 0 (MRGP_CHAIN_PROF=1) or null
+    double *tables;                // (J, M, M) log omega_hat of every layer of the sweep (MRGP_CHAIN_PROF=1) or null
     ChainLayer layer[kChainMaxLayers];
 };
 
