@@ -549,7 +549,7 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
     const double dm = (double)M, inv_m = 1.0 / dm;
     // Anderson history, newest first: differences of the iterates / centred residuals (per lane) and their Gram matrix
     double xp = 0.0, fp = 0.0, dX0 = 0.0, dX1 = 0.0, dX2 = 0.0, dF0 = 0.0, dF1 = 0.0, dF2 = 0.0;
-    double g00 = 0.0, g01 = 0.0, g02 = 0.0, g11 = 0.0, g12 = 0.0, g22 = 0.0;
+    double g00 = 0.0, g01 = 0.0, g02 = 0.0, g11 = 0.0, g12 = 0.0, g22 = 0.0, d1 = 0.0, d2 = 0.0;   // d: 1 / length of dF1, dF2
     int nh = 0;
     bool have_prev = false;
     if (lane == 0) PROF(7);
@@ -605,25 +605,31 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
         have_prev = true;
         double xn = x + fc;                               // the Sinkhorn step (up to the scale of v)
         if (nh > 0 && g00 > 0.0) {
-            // normal equations of the nh newest differences, columns scaled to unit length, ridge; Cholesky 3 x 3
+            // normal equations of the nh newest differences, columns scaled to unit length (the matrix holds the cosines
+            // between the differences), ridge on the diagonal; 3 x 3 by Cramer's rule: one division, no chain of square
+            // roots (gamma only steers the iteration - the fixed point is judged by the column sums)
             const bool h1 = nh > 1 && g11 > 0.0, h2 = nh > 2 && h1 && g22 > 0.0;
-            const double d0 = rsqrt(g00), d1 = h1 ? rsqrt(g11) : 0.0, d2 = h2 ? rsqrt(g22) : 0.0;
+            const double d0 = rsqrt(g00);
+            if (!h1) d1 = 0.0;
+            if (!h2) d2 = 0.0;
             const double a01 = g01 * d0 * d1, a02 = g02 * d0 * d2, a12 = g12 * d1 * d2;
             const double r0 = b0 * d0, r1 = b1 * d1, r2 = b2 * d2;
-            constexpr double kDiag = 1.0 + 1e-8;
-            const double l00 = sqrt(kDiag), il00 = 1.0 / l00;
-            const double l10 = a01 * il00, l20 = a02 * il00;
-            const double t1 = kDiag - l10 * l10;
-            const double il11 = rsqrt(fmax(t1, 1e-300));
-            const double l21 = (a12 - l20 * l10) * il11;
-            const double t2 = kDiag - l20 * l20 - l21 * l21;
-            const double il22 = rsqrt(fmax(t2, 1e-300));
-            const double y0 = r0 * il00, y1 = (r1 - l10 * y0) * il11, y2 = (r2 - l20 * y0 - l21 * y1) * il22;
-            const double q2 = y2 * il22, q1 = (y1 - l21 * q2) * il11, q0 = (y0 - l10 * q1 - l20 * q2) * il00;
-            if (t1 > 0.0 && t2 > 0.0) {
-                const double c0 = q0 * d0, c1 = q1 * d1, c2 = q2 * d2;     // gamma
+            constexpr double kD = 1.0 + 1e-7;
+            const double m00 = kD * kD - a12 * a12, m01 = a02 * a12 - kD * a01, m02 = a01 * a12 - kD * a02;
+            const double m11 = kD * kD - a02 * a02, m12 = a01 * a02 - kD * a12, m22 = kD * kD - a01 * a01;
+            const double det = kD * m00 + a01 * m01 + a02 * m02;
+            if (det > 1e-12) {
+                const double idet = 1.0 / det;
+                const double c0 = (m00 * r0 + m01 * r1 + m02 * r2) * idet * d0;     // gamma
+                const double c1 = (m01 * r0 + m11 * r1 + m12 * r2) * idet * d1;
+                const double c2 = (m02 * r0 + m12 * r1 + m22 * r2) * idet * d2;
                 xn -= c0 * (dX0 + dF0) + c1 * (dX1 + dF1) + c2 * (dX2 + dF2);
             }
+            d2 = d1;      // scalings of the differences, shifted with them
+            d1 = d0;
+        } else {
+            d2 = d1;
+            d1 = 0.0;
         }
         x = real ? fmax(-640.0, fmin(640.0, xn)) : 0.0;
         err_prev = err;
