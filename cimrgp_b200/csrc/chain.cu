@@ -829,12 +829,6 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
     }
     __syncthreads();
     if (tid == 0) PROF(3);
-    if (C >= 2 && warp >= 4) {   // B(j): warps 4-7 push the 4 x 32 values to every worker CTA
-        const int t = tid - 128;
-        const double v = sm.pub[t];
-        const uint32_t dst = smem_addr(&sm.loc[j & 1][t]), bar = smem_addr(&sm.barB);
-        for (unsigned r = 1; r < C; ++r) st_async_remote(remote_addr(dst, r), v, remote_addr(bar, r));
-    }
     // S4, the table (Stats.py:405-412; a true matrix product inside the trace): a warp per row, the row maxima on the
     // way; the (at most 4) rows of a warp are independent instruction streams
     const bool last_layer = j == m.J - 1;
@@ -1063,6 +1057,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_ci_sweep(const ChainModel 
             cl_wait();
         } else if (rank == 0) {
             __syncthreads();                               // the table of layer j is complete (the solver reads all of it)
+            if (warp >= 4) {   // B(j): warps 4-7 push the 4 x 32 values to every worker CTA while warp 0 starts the solve
+                const int t = tid - 128;
+                const double v = sm.pub[t];
+                const uint32_t dst = smem_addr(&sm.loc[j & 1][t]), bar = smem_addr(&sm.barB);
+                for (unsigned r = 1; r < C; ++r) st_async_remote(remote_addr(dst, r), v, remote_addr(bar, r));
+            }
         }
         if (solver) {
             omega_solve_warp<MP>(m, sm, j, lane);
