@@ -1125,21 +1125,29 @@ int do_ystats(mrgp_handle *h) {
         return MRGP_OK;
     }
     StreamArgs a = stream_args(h, 0);
+    // one handle: the last CTA of the pass sums the run partials itself (no second launch); sharded: the partials of
+    // the ranks' chunks are exchanged first
+    const bool fuse = !h->sharded && !h->split_kernels && lp.R <= 64;
+    a.fuse_tail = fuse ? 1 : 0;
+    a.yc_out = d.yc;
+    a.ysum_out = d.ysum;
     cudaError_t e = cudaErrorInvalidValue;
     DISPATCH_M(M, e = launch_ystats<MM>(h, a));
     CK(e);
     count(h);
-    const int32_t *rr = d.region_run;
-    const double *part = h->part;
-    if (h->sharded) {   // sum the statistics of the ranks' chunks
-        int rc = do_exchange(h, 0, 0, padded_basis(M) * DY + DY + 1, false);
-        if (rc) return rc;
-        rr = d.ident_run;
-        part = h->xchg;
+    if (!fuse) {
+        const int32_t *rr = d.region_run;
+        const double *part = h->part;
+        if (h->sharded) {   // sum the statistics of the ranks' chunks
+            int rc = do_exchange(h, 0, 0, padded_basis(M) * DY + DY + 1, false);
+            if (rc) return rc;
+            rr = d.ident_run;
+            part = h->xchg;
+        }
+        k_reduce_ystats<<<lp.R, 1024, 0, h->stream>>>(rr, part, h->part_stride, lp.R, M, padded_basis(M), DY, d.yc, d.ysum);
+        CK(cudaGetLastError());
+        count(h);
     }
-    k_reduce_ystats<<<lp.R, 1024, 0, h->stream>>>(rr, part, h->part_stride, lp.R, M, padded_basis(M), DY, d.yc, d.ysum);
-    CK(cudaGetLastError());
-    count(h);
     h->ystats_valid = true;
     return MRGP_OK;
 }

@@ -89,6 +89,7 @@ struct StreamArgs {
     int32_t sums_only;               // bias_noise_*: only store the per-region sums in sumsB
     int32_t noise_rs, bias_rs, ci;   // noise / bias region specific (MRGP.py:27-28); ci or fi (Posteriors.py:113-211 vs 377-475)
     double *bias_mean_out, *bias_prev_out, *bias_prec, *bias_var, *noise_shape, *noise_scale, *noise_mean, *noise_log_mean, *yvar, *sumsB;
+    double *yc_out, *ysum_out;       // k_ystats with fuse_tail: the last CTA to finish sums the run partials into the region statistics
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -561,6 +562,10 @@ __device__ __forceinline__ void ystats_block(double (&T)[M * DY + DY + 1], const
     }
 }
 
+template <int NS, int NU>
+__device__ __forceinline__ void reduce_ystats_region(double (*sm)[64], int r, const int32_t *region_run, const double *part, int part_stride, int M,
+                                                     int MP, int DY, double *yc, double *ysum);
+
 template <int DY, int M>
 __global__ void __launch_bounds__(kThreads, 1) k_ystats(StreamArgs p) {
     using L = TileLayout<DY, true, false, false>;
@@ -637,6 +642,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_ystats(StreamArgs p) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+    // ---- tail: the last CTA to finish sums the run partials into the statistics of the regions (fixed order) ----
+    if (!p.fuse_tail) return;
+    __shared__ int sLast;
+    __shared__ double sred[kThreads / 64][64];
+    __syncthreads();
+    if (tid == 0) sLast = (atom_add_acq_rel_gpu(p.done_counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (sLast) {
+        for (int r = 0; r < p.R; ++r)
+            reduce_ystats_region<kThreads / 64, 40>(sred, r, p.region_run, p.part, p.part_stride, p.n_basis, M, DY, p.yc_out, p.ysum_out);
+        if (tid == 0) *p.done_counter = 0u;
     }
 }
 
@@ -798,28 +815,28 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_ystats_split(StreamArgs p) {
 // yc[r][i][d], ysum[r][0..DY] = sums over the region's runs of the k_ystats partials (fixed order).
 // (MP: the padded number of basis functions the partials were written for.)  1024 threads: value = tid % 64 (chunks of
 // 64 values), 16 slices over the runs with their loads in flight together, combined in slice order.
-__global__ void __launch_bounds__(1024) k_reduce_ystats(const int32_t *region_run, const double *part, int part_stride, int R, int M, int MP, int DY,
-                                                        double *yc, double *ysum) {
-    __shared__ double sm[16][64];
-    const int r = blockIdx.x, nv = MP * DY + DY + 1, lane64 = threadIdx.x & 63, slice = threadIdx.x >> 6;
+template <int NS, int NU>
+__device__ __forceinline__ void reduce_ystats_region(double (*sm)[64], int r, const int32_t *region_run, const double *part, int part_stride, int M,
+                                                     int MP, int DY, double *yc, double *ysum) {
+    const int nv = MP * DY + DY + 1, lane64 = threadIdx.x & 63, slice = threadIdx.x >> 6;
     const int q_end = region_run[r + 1];
     for (int v0 = 0; v0 < nv; v0 += 64) {
         const int v = v0 + lane64;
         double s = 0.0;
         if (v < nv)
-            for (int q = region_run[r] + slice; q < q_end; q += 16 * 4) {
-                double t[4];
+            for (int q = region_run[r] + slice; q < q_end; q += NS * NU) {
+                double t[NU];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) t[u] = q + 16 * u < q_end ? part[(size_t)(q + 16 * u) * part_stride + v] : 0.0;
+                for (int u = 0; u < NU; ++u) t[u] = q + NS * u < q_end ? __ldcg(part + (size_t)(q + NS * u) * part_stride + v) : 0.0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) s += t[u];
+                for (int u = 0; u < NU; ++u) s += t[u];
             }
         sm[slice][lane64] = s;
         __syncthreads();
         if (slice == 0 && v < nv && !(v >= M * DY && v < MP * DY)) {
             double t = 0.0;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) t += sm[k][lane64];
+            for (int k = 0; k < NS; ++k) t += sm[k][lane64];
             if (v < M * DY)
                 yc[(size_t)r * M * DY + v] = t;
             else
@@ -827,6 +844,12 @@ __global__ void __launch_bounds__(1024) k_reduce_ystats(const int32_t *region_ru
         }
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(1024) k_reduce_ystats(const int32_t *region_run, const double *part, int part_stride, int R, int M, int MP, int DY,
+                                                        double *yc, double *ysum) {
+    __shared__ double sm[16][64];
+    reduce_ystats_region<16, 4>(sm, blockIdx.x, region_run, part, part_stride, M, MP, DY, yc, ysum);
 }
 
 // ------------------------------------------------------------------------------------------------
