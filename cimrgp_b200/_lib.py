@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcimrgp.so')
 
 COMM_BLOB_BYTES = 128
-ABI_VERSION = 3
+ABI_VERSION = 4
 MODE_CI, MODE_FI = 0, 1
 OK, EINVAL, ENODEVICE, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4, -5
 
@@ -54,6 +54,8 @@ SIGNATURES = {
     'mrgp_set_data_host': (C.c_int, [_P, _P, _P]),
     'mrgp_set_observations': (C.c_int, [_P, _P]),
     'mrgp_set_observations_host': (C.c_int, [_P, _P]),
+    'mrgp_prefetch_observations_host': (C.c_int, [_P, _P]),
+    'mrgp_prefetch_sync': (C.c_int, [_P]),
     'mrgp_set_spectral': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double]),
     'mrgp_build_basis': (C.c_int, [_P, C.c_int32, C.c_double, _D]),
     'mrgp_init_state': (C.c_int, [_P, C.c_double, C.c_double]),

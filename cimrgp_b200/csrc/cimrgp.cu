@@ -100,7 +100,7 @@ struct mrgp_handle {
     int64_t lo = 0, hi = 0;   // owned samples [lo, hi)
     double *xchg = nullptr;   // dense exchange buffer (max R) x part_stride
     const double *x = nullptr, *y = nullptr;
-    double *x_ws = nullptr, *y_ws = nullptr, *g = nullptr, *hvar = nullptr, *tmp_mean = nullptr, *tmp_var = nullptr;
+    double *x_ws = nullptr, *y_ws = nullptr, *y_ws2 = nullptr, *g = nullptr, *hvar = nullptr, *tmp_mean = nullptr, *tmp_var = nullptr;
     double *part = nullptr, *elbo_out = nullptr;
     RegionArgs *elbo_args = nullptr;
     int64_t *off_staging = nullptr;
@@ -112,6 +112,9 @@ struct mrgp_handle {
     bool own_stream = false;
     std::vector<cudaEvent_t> ev_fork, ev_join, ev_ard, ev_mid2;
     cudaEvent_t ev_prefetch = nullptr, ev_b0_fork = nullptr, ev_b0_done = nullptr;
+    cudaStream_t copy_stream = nullptr;   // mrgp_prefetch_observations_host: uploads beside the handle's stream
+    cudaEvent_t ev_copy_done = nullptr, ev_y_free = nullptr;
+    bool prefetch_pending = false, y_free_recorded = false;
     cudaStream_t side2 = nullptr;    // layer 0's phase B beside the chain of layer 1 (closed-form ci sweeps)
     bool b0_pending = false;
     cudaGraph_t graph = nullptr;
@@ -281,6 +284,7 @@ size_t carve(mrgp_handle *h, char *base) {
     const bool fi = h->cfg.mode == MRGP_MODE_FI;
     h->x_ws = c.take<double>(N * h->cfg.dx);
     h->y_ws = c.take<double>(N * DY);
+    h->y_ws2 = c.take<double>(N * DY);   // spare buffer of mrgp_prefetch_observations_host
     h->g = c.take<double>(N * DY);
     h->hvar = c.take<double>(N);
     h->tmp_mean = c.take<double>(N * DY);
@@ -1554,6 +1558,9 @@ void mrgp_destroy(mrgp_handle *h) {
     if (h->ev_b0_fork) cudaEventDestroy(h->ev_b0_fork);
     if (h->ev_b0_done) cudaEventDestroy(h->ev_b0_done);
     if (h->side2) cudaStreamDestroy(h->side2);
+    if (h->ev_copy_done) cudaEventDestroy(h->ev_copy_done);
+    if (h->ev_y_free) cudaEventDestroy(h->ev_y_free);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int q = 0; q < kMaxRanks; ++q)
         if (h->comm.opened[q]) cudaIpcCloseMemHandle(h->comm.peer_base[q]);
     if (h->comm.mem) cudaFree(h->comm.mem);
@@ -1720,6 +1727,7 @@ int mrgp_set_observations_host(mrgp_handle *h, const double *y_host) {
     if (h) h->stream_ops += 1;
     if (!h || !y_host) return fail(h, MRGP_EINVAL, "null argument");
     if (!h->have_data) return fail(h, MRGP_ESTATE, "no inputs yet: mrgp_set_data / mrgp_set_data_host first");
+    if (h->prefetch_pending) return fail(h, MRGP_ESTATE, "prefetched observations are waiting to be taken over");
     const size_t N = (size_t)(h->hi - h->lo);
     CK(cudaMemcpyAsync(h->y_ws, y_host, N * h->cfg.dy * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if (h->y != h->y_ws) drop_graph(h);
@@ -1727,6 +1735,61 @@ int mrgp_set_observations_host(mrgp_handle *h, const double *y_host) {
     h->ystats_valid = false;
     return MRGP_OK;
 }
+
+// Double-buffered upload: the copy of the NEXT observations runs on the handle's own copy stream into the spare buffer
+// while the handle's stream works on the current ones (a fused ci sweep reads no sample at all).
+int mrgp_prefetch_observations_host(mrgp_handle *h, const double *y_host) {
+    if (h) h->stream_ops += 1;
+    if (!h || !y_host) return fail(h, MRGP_EINVAL, "null argument");
+    if (!h->have_data) return fail(h, MRGP_ESTATE, "no inputs yet: mrgp_set_data / mrgp_set_data_host first");
+    if (h->prefetch_pending)
+        return fail(h, MRGP_ESTATE, "prefetched observations are waiting to be taken over (mrgp_refresh_statistics)");
+    if (!h->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_copy_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_y_free, cudaEventDisableTiming));
+    }
+    // the spare buffer held the observations before the current ones: its last readers were enqueued before the marker
+    if (h->y_free_recorded) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_y_free, 0));
+    const size_t N = (size_t)(h->hi - h->lo);
+    CK(cudaMemcpyAsync(h->y_ws2, y_host, N * h->cfg.dy * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->ev_copy_done, h->copy_stream));
+    h->prefetch_pending = true;
+    return MRGP_OK;
+}
+
+// Blocks the caller until the last mrgp_prefetch_observations_host() has read its host buffer (which may then be reused).
+int mrgp_prefetch_sync(mrgp_handle *h) {
+    if (!h) return MRGP_EINVAL;
+    if (h->ev_copy_done) CK(cudaEventSynchronize(h->ev_copy_done));
+    return MRGP_OK;
+}
+
+namespace {
+// Take over prefetched observations: swap the buffers, make the stream wait for the copy, invalidate what depends on y.
+int adopt_prefetched(mrgp_handle *h) {
+    if (!h->prefetch_pending) return MRGP_OK;
+    CK(cudaEventRecord(h->ev_y_free, h->stream));   // everything enqueued so far may read the buffer that becomes the spare
+    h->y_free_recorded = true;
+    CK(cudaStreamWaitEvent(h->stream, h->ev_copy_done, 0));
+    std::swap(h->y_ws, h->y_ws2);
+    h->y = h->y_ws;
+    h->ystats_valid = false;
+    h->prefetch_pending = false;
+    if (use_fused(h) && !ystats_small(h)) {
+        // the sweep kernel reads no sample and the guarded fallback takes y from its launch arguments: launch on the
+        // stream from now on (a captured graph would hold the old pointer; two launches per sweep either way)
+        h->direct_launch = true;
+        if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+        if (h->graph) cudaGraphDestroy(h->graph);
+        h->graph_exec = nullptr;
+        h->graph = nullptr;
+    } else {
+        drop_graph(h);
+    }
+    return MRGP_OK;
+}
+}  // namespace
 
 int mrgp_set_all_inputs_host(mrgp_handle *h, const double *x_all_host) {
     if (!h || !x_all_host) return fail(h, MRGP_EINVAL, "null argument");
@@ -1969,6 +2032,7 @@ int mrgp_refresh_statistics(mrgp_handle *h) {
     int rc = check_ready(h, 0, true);
     if (rc) return rc;
     h->stream_ops += 1;
+    if ((rc = adopt_prefetched(h))) return rc;
     if (!use_fused(h)) return MRGP_OK;   // the multi-kernel sweep streams layer 0: nothing to prepare
     if ((rc = build_invariants(h))) return rc;
     if (!h->chain_uploaded && (rc = upload_chain_model(h))) return rc;

@@ -163,6 +163,19 @@ class Engine(object):
         """Asynchronous H2D of the pinned y staging buffer on the engine's stream (16 B per sample)."""
         self._ck(self.lib.mrgp_set_observations_host(self.handle, C.c_void_p(self._pinned[1].data_ptr())))
 
+    def prefetch_observations(self, y=None):
+        """Double-buffered upload (mrgp_prefetch_observations_host): starts the H2D copy of the NEXT observations on the
+        engine's copy stream and returns; they take effect at the next refresh_statistics().  y: NumPy array
+        staged in the pinned buffer first, or None to send the pinned buffer as it is (the caller filled it - and must not
+        touch it again before the data set has been taken over).  Loop of a pipelined consumer:
+            eng.refresh_statistics(); eng.prefetch_observations(y_next); eng.sweep(1); ... read results ..."""
+        if self._pinned is None:
+            raise ValueError('this engine borrows device tensors: nothing to stage')
+        if y is not None:
+            self._ck(self.lib.mrgp_prefetch_sync(self.handle))     # the previous copy has left the staging buffer
+            self._pinned[1].numpy()[...] = np.ascontiguousarray(y, dtype=np.float64).reshape(self.N, self.dy)
+        self._ck(self.lib.mrgp_prefetch_observations_host(self.handle, C.c_void_p(self._pinned[1].data_ptr())))
+
     def build_basis(self, layer, interval_factor=1.0, intervals=None):
         if intervals is None:
             self._ck(self.lib.mrgp_build_basis(self.handle, layer, float(interval_factor), None))

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MRGP_ABI_VERSION 3
+#define MRGP_ABI_VERSION 4
 
 enum {
     MRGP_OK = 0,
@@ -147,6 +147,17 @@ int mrgp_set_data_host(mrgp_handle *h, const double *x_host, const double *y_hos
  * mrgp_set_observations_host is the entry the end-to-end benchmark times (16 B per sample and step).           */
 int mrgp_set_observations(mrgp_handle *h, const double *y_dev);
 int mrgp_set_observations_host(mrgp_handle *h, const double *y_host);
+/* Double-buffered form of mrgp_set_observations_host for a stream of data sets at unchanged inputs: starts the copy of
+ * the NEXT observations (pinned host memory) into the handle's spare buffer on a copy stream of its own and returns. The
+ * copy runs beside whatever the handle's stream is doing - the fused ci sweep reads no sample. The observations take
+ * effect at the next mrgp_refresh_statistics() (and only there: sweeps in between keep working on the current set): the
+ * buffers are swapped and the statistics pass waits for the copy. One set can be pending (MRGP_ESTATE otherwise). Loop
+ * of a pipelined consumer:
+ *     mrgp_refresh_statistics(h);  mrgp_prefetch_observations_host(h, y_next);  mrgp_sweep(h, 1);  ... read results ...
+ * (reference counterpart: a new MultiResolutionGaussianProcess([x, y_next], ...) per data set, MRGP.py:16-66).          */
+int mrgp_prefetch_observations_host(mrgp_handle *h, const double *y_host);
+/* Blocks until the last mrgp_prefetch_observations_host() has read its host buffer (the buffer may then be rewritten). */
+int mrgp_prefetch_sync(mrgp_handle *h);
 
 /* ---- K1-K3: basis intervals, eigenvalues, spectral density, sum phi^2 ---------------------------- */
 

@@ -746,3 +746,31 @@ def test_fused_sweep_guard_falls_back_to_streamed_statistics(n, monkeypatch):
     compare(states[0], states[2], rtol=1e-9)       # streamed fallback == multi-kernel sweep
     compare(states[1], states[2], rtol=1e-9)       # closed form == multi-kernel sweep
     assert any(not np.array_equal(states[0][k], states[1][k]) for k in states[0])   # the fallback did run (other summation order)
+
+
+def test_prefetched_observations_match_synchronous_uploads():
+    """mrgp_prefetch_observations_host: a stream of data sets through the double-buffered upload (copy of the next set beside
+    the sweep of the current one) gives the state of the synchronous uploads, bit for bit; one set can be pending."""
+    from cimrgp_b200 import _lib
+    n = 60000                                   # layer 0 is one region of 60000 samples: the streaming statistics pass
+    x, y = workloads.workload1(n)
+    rng = np.random.default_rng(5)
+    ys = [y + 0.05 * rng.standard_normal(y.shape) for _ in range(3)]
+    a, b = build(x, y, 30, 5, False), build(x, y, 30, 5, False)
+    a.fit(2, None)
+    b.fit(2, None)
+    ea, eb = a._engine, b._engine
+    eb.prefetch_observations(ys[0])
+    with pytest.raises(_lib.MrgpError):
+        eb.prefetch_observations(ys[1])         # the first set has not been taken over yet
+    for k in range(3):
+        ea.set_observations(ys[k])
+        ea.sweep(2)
+        eb.refresh_statistics()                 # takes over set k (waits for its copy) ...
+        if k + 1 < 3:
+            eb.prefetch_observations(ys[k + 1])  # ... and the copy of set k + 1 runs beside the sweeps of set k
+        eb.sweep(2)
+        sa, sb = ea.state(), eb.state()
+        for key in sa:
+            assert np.array_equal(sa[key], sb[key]), (k, key)
+    assert np.array_equal(ea.elbo(), eb.elbo())
