@@ -372,6 +372,51 @@ def config5(n_series, device, torch, rank=0, world=1, n_iter=6):
     return res
 
 
+def measure_e2e(m, eng, steps, flush, barrier, max_over_ranks, torch, scale=1):
+    """End to end through the public API: new observations from pinned host memory every step, statistics pass, sweep, ELBO
+    terms back.  Two loops over the same work: (serial) upload, then compute, then read - the latency of one data set;
+    (pipelined) the double-buffered upload of the API: the copy of step k + 1 is started before the sweep of step k, which
+    reads no sample - the throughput of a stream of data sets, which is what `value` counts.  scale: models working in
+    parallel (replicas, one per GPU)."""
+    e2e_ms = []
+    for k in range(steps):
+        barrier()
+        flush_l2(eng, flush, torch)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(eng.stream)
+        eng.upload_observations()                      # H2D of this rank's rows of y (n, 2) from pinned memory
+        m.fit(n_iter=1, tol=1e-300, min_iter=1)        # statistics pass + one sweep + the six ELBO terms per layer, read back
+        b.record(eng.stream)
+        b.synchronize()
+        e2e_ms.append(max_over_ranks(a.elapsed_time(b)))
+    # pipelined: ONE timed region around all K steps (L2 flushes included - nothing is subtracted); every step's copy,
+    # statistics pass, sweep and read-back happen inside it
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.synchronize()
+    a.record(eng.stream)
+    eng.prefetch_observations()                        # observations of step 0
+    for k in range(steps):
+        flush_l2(eng, flush, torch)
+        eng.refresh_statistics()                       # takes over set k: waits for its copy, statistics pass
+        if k + 1 < steps:
+            eng.prefetch_observations()                # copy of set k + 1 on the copy stream, beside the sweep of set k
+        m.fit(n_iter=1, tol=1e-300, min_iter=1)        # one sweep + ELBO terms, read back
+    b.record(eng.stream)
+    b.synchronize()
+    pipe_ms = max_over_ranks(a.elapsed_time(b)) / steps
+    return {'value': scale * 1e3 / pipe_ms, 'unit': 'it/s', 'h2d_bytes_per_step': scale * eng.N * DY * 8,
+            'd2h_bytes_per_step': scale * N_LAYERS * 6 * 8, 'ms_per_step': pipe_ms,
+            'serial': {'value': scale * steps / (sum(e2e_ms) / 1e3), 'ms_per_step': float(np.mean(e2e_ms)),
+                       'what': 'upload, statistics pass, sweep, read-back one after the other (L2 flush before each step, not timed)'},
+            'what': 'new observations y every step at UNCHANGED inputs x (x-derived tables are reused; new inputs need the '
+                    'basis rebuilt, include/cimrgp.h): y from pinned host memory through the double-buffered upload of the API '
+                    '(mrgp_prefetch_observations_host: the copy of step k + 1 overlaps the sweep of step k, which reads no '
+                    'sample), layer-0 statistics pass over x and y, one sweep, ELBO terms back; one timed region around all '
+                    'steps, the L2 flush of every step included',
+            'lower_bound_layer0': m.lower_bound_layer[0][-1]}
+
+
 def run_gpu(args, rank, world, local_rank):
     import ctypes as C
     import torch
@@ -380,9 +425,12 @@ def run_gpu(args, rank, world, local_rank):
     multi = world > 1
     if multi:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    # strong scaling: the samples of the N = 1e6 problem are split into contiguous chunks, one per GPU; the small-matrix
-    # state is replicated.  In the fused ci sweep no sample-parallel work is left in the steady state.
-    m = make_model(N_SAMPLES, N_LAYERS, local_rank, distributed=multi)
+    # N > 1: one model per GPU (a series of its own per rank, same configuration): the steady-state ci sweep reads no sample,
+    # so nothing of one model is left to shard and independent series are the natural shard of the workload
+    # (BASELINE config 5).  No data-path collective; barrier + max over ranks around the timed regions.  The SAMPLE-sharded
+    # single model (statistics pass and uploads split over the GPUs, the sweep replicated) is measured after it and goes
+    # into extras.sample_sharded.
+    m = make_model(N_SAMPLES, N_LAYERS, local_rank, seed=10 + rank)
     eng = m._engine
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
     peak, peak_src = peaks()
@@ -411,51 +459,9 @@ def run_gpu(args, rank, world, local_rank):
     step_ms = timed_sweeps(eng, args.steps, flush, barrier, max_over_ranks, torch)
     launches = eng.launch_count() - l0
     total_s = sum(step_ms) / 1e3
-    value = args.steps / total_s
+    value = (world if multi else 1) * args.steps / total_s
 
-    # ---- end to end through the public API: new observations from pinned host memory every step, statistics pass, sweep,
-    #      ELBO terms back.  Two loops over the same work: (serial) upload, then compute, then read - the latency of one data
-    #      set; (pipelined) the double-buffered upload of the API: the copy of step k + 1 is started before the sweep of step
-    #      k, which reads no sample - the throughput of a stream of data sets, which is what `value` counts.
-    e2e = None
-    if not args.no_e2e:
-        e2e_ms = []
-        for k in range(args.steps):
-            barrier()
-            flush_l2(eng, flush, torch)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(eng.stream)
-            eng.upload_observations()                      # H2D of this rank's rows of y (n, 2) from pinned memory
-            m.fit(n_iter=1, tol=1e-300, min_iter=1)        # statistics pass + one sweep + the six ELBO terms per layer, read back
-            b.record(eng.stream)
-            b.synchronize()
-            e2e_ms.append(max_over_ranks(a.elapsed_time(b)))
-        # pipelined: ONE timed region around all K steps (L2 flushes included - nothing is subtracted); every step's copy,
-        # statistics pass, sweep and read-back happen inside it
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        eng.synchronize()
-        a.record(eng.stream)
-        eng.prefetch_observations()                        # observations of step 0
-        for k in range(args.steps):
-            flush_l2(eng, flush, torch)
-            eng.refresh_statistics()                       # takes over set k: waits for its copy, statistics pass
-            if k + 1 < args.steps:
-                eng.prefetch_observations()                # copy of set k + 1 on the copy stream, beside the sweep of set k
-            m.fit(n_iter=1, tol=1e-300, min_iter=1)        # one sweep + ELBO terms, read back
-        b.record(eng.stream)
-        b.synchronize()
-        pipe_ms = max_over_ranks(a.elapsed_time(b)) / args.steps
-        e2e = {'value': 1e3 / pipe_ms, 'unit': 'it/s', 'h2d_bytes_per_step': eng.N * DY * 8,
-               'd2h_bytes_per_step': N_LAYERS * 6 * 8, 'ms_per_step': pipe_ms,
-               'serial': {'value': args.steps / (sum(e2e_ms) / 1e3), 'ms_per_step': float(np.mean(e2e_ms)),
-                          'what': 'upload, statistics pass, sweep, read-back one after the other (L2 flush before each step, not timed)'},
-               'what': 'new observations y every step at UNCHANGED inputs x (x-derived tables are reused; new inputs need the '
-                       'basis rebuilt, include/cimrgp.h): y from pinned host memory through the double-buffered upload of the API '
-                       '(mrgp_prefetch_observations_host: the copy of step k + 1 overlaps the sweep of step k, which reads no '
-                       'sample), layer-0 statistics pass over x and y, one sweep, ELBO terms back; one timed region around all '
-                       'steps, the L2 flush of every step included',
-               'lower_bound_layer0': m.lower_bound_layer[0][-1]}
+    e2e = None if args.no_e2e else measure_e2e(m, eng, args.steps, flush, barrier, max_over_ranks, torch, scale=world if multi else 1)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- kernels -------------------------------------------------------------------------------------------------
@@ -491,21 +497,37 @@ def run_gpu(args, rank, world, local_rank):
     if multi:
         line = None
         if rank == 0:
-            serial_us, shard_us = 1e3 * float(np.median(warm_ms)), 1e3 * ys_med * world
             line = {
                 'metric': METRIC, 'value': value, 'unit': 'it/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warm,
                 'ms_per_step': 1e3 * total_s / args.steps, 'ms_per_step_median': float(np.median(step_ms)),
                 'step_ms': [round(v, 4) for v in step_ms],
-                'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-                'config': dict(CONFIG, parallelism='samples sharded in %d contiguous chunks (x, y never leave their GPU); the '
-                               'small-matrix sweep is replicated; one exchange of 63 doubles per data set (layer-0 statistics) over '
-                               'NVLink peer memory, none per sweep' % world),
-                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': None,
-                'amdahl': {'serial_us': serial_us, 'shardable_us_one_gpu': shard_us,
-                           'note': 'steady-state ci sweep: only the replicated chain is left (serial_us); the sharded work is the '
-                                   'statistics pass per data set (e2e). Strong scaling of `value` is therefore flat by construction; '
-                                   'e2e and the series batch (extras) are where more GPUs pay'},
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': dict(CONFIG, parallelism='replicas only: %d independent series of the stated configuration, one model per '
+                               'GPU, no data-path collective (value = models x sweeps / slowest rank). One model cannot use more '
+                               'GPUs in the steady state: its sweep reads no sample; extras.sample_sharded has that arm' % world),
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches * world, 'roofline': roofline, 'cpu_baseline': None,
             }
+        # ---- the sample-sharded single model (strong scaling of ONE N = 1e6 problem) ---------------------------------
+        sharded = None
+        if not args.no_extras:
+            eng.close()
+            del m
+            ms_ = make_model(N_SAMPLES, N_LAYERS, local_rank, distributed=True)
+            es = ms_._engine
+            es.sweep(warm)
+            es.synchronize()
+            st = timed_sweeps(es, 10, flush, barrier, max_over_ranks, torch)
+            e2 = measure_e2e(ms_, es, 10, flush, barrier, max_over_ranks, torch)
+            wm = [max_over_ranks(v) for v in time_call(es, lambda: es.sweep(1), None, torch, 9)]
+            ysm = [max_over_ranks(v) for v in time_call(es, es.refresh_statistics, flush, torch, 7)]
+            sharded = {'value': 10 / (sum(st) / 1e3), 'ms_per_step': float(np.mean(st)), 'e2e': {k: e2[k] for k in ('value', 'ms_per_step', 'serial')},
+                       'h2d_bytes_per_step_per_gpu': es.N * DY * 8,
+                       'amdahl': {'serial_us': 1e3 * float(np.median(wm)), 'statistics_pass_us': 1e3 * float(np.median(ysm)),
+                                  'note': 'samples split into %d contiguous chunks (x, y never leave their GPU); the small-matrix sweep '
+                                          'is replicated (serial_us); the sharded work is the statistics pass per data set with one '
+                                          'exchange of 63 doubles over NVLink peer memory. Strong scaling of the sweep rate is flat by '
+                                          'construction' % world}}
+            eng = es
         extras = None
         if args.config5_series > 0 and not args.no_extras:
             torch.cuda.synchronize()
@@ -517,6 +539,8 @@ def run_gpu(args, rank, world, local_rank):
                                                  'ci_ms_per_batch_iteration': float(t[0]), 'ci_series_sweeps_per_s': args.config5_series / (float(t[0]) * 1e-3),
                                                  'fi_ms_per_batch_iteration': float(t[1]), 'fi_series_sweeps_per_s': args.config5_series / (float(t[1]) * 1e-3)}}
         if rank == 0:
+            if extras is not None or sharded is not None:
+                extras = dict(extras or {}, sample_sharded=sharded)
             line['extras'] = extras
             print(json.dumps(_finite(line)))
             sys.stdout.flush()
