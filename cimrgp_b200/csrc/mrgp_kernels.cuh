@@ -42,8 +42,7 @@ __device__ __forceinline__ void ts_dbg(unsigned long long *ts, int layer, int k,
 }
 constexpr int kThreads = 256;      // streaming CTA size (8 warps)
 constexpr int kPartBStride = 8;    // doubles per phase-B partial (dy + 3 <= 8)
-constexpr int kRedChunk = 32;      // values reduced per block_reduce round
-constexpr int kRedSmemDoubles = kRedChunk * kThreads + 8 * 32;
+constexpr int kRedSmemDoubles = (kThreads / 32) * 128;   // block_reduce_store: one row of (padded) sums per warp
 
 struct Segment {
     int64_t start;
@@ -96,35 +95,45 @@ struct StreamArgs {
 // block reductions
 // ------------------------------------------------------------------------------------------------
 
-// Sum NV per-thread values over the 256 threads of the block, fixed order; out[v] written by warp 0.
+// Sum NV per-thread values over the 256 threads of the block, fixed order.  Inside a warp a halving butterfly: at every
+// level a lane sends one half of its values to its partner and adds the partner's other half, so NP values cost NP - NP/32
+// exchanges (not 5 NP) and lane l ends with the warp's sums of values l NP/32 .. ; the 8 warps then meet in shared memory
+// (red: 8 x NP doubles) and are added in warp order.  (Round 1 staged all values through 66 KB of shared memory with three
+// block barriers per 32 values: a quarter of the time of k_ystats and more on layers with several regions per CTA.)
+
 template <int NV, bool NAMED = false>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *red, double *out) {
+    static_assert(NV <= 128, "block_reduce_store: at most 128 values");
+    constexpr int NP = NV <= 32 ? 32 : (NV <= 64 ? 64 : 128), PER = NP / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *part = red + kRedChunk * kThreads;
     auto sync = [] {
         if (NAMED)
             compute_sync<kThreads>();
         else
             __syncthreads();
     };
+    double a[NP];
 #pragma unroll
-    for (int c = 0; c < (NV + kRedChunk - 1) / kRedChunk; ++c) {
-        sync();
+    for (int k = 0; k < NP; ++k) a[k] = k < NV ? v[k] : 0.0;
 #pragma unroll
-        for (int k = 0; k < kRedChunk; ++k)
-            if (c * kRedChunk + k < NV) red[k * kThreads + tid] = v[c * kRedChunk + k];
-        sync();
-        double s = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) s += red[lane * kThreads + warp * 32 + ((k + lane) & 31)];
-        part[warp * 32 + lane] = s;
-        sync();
-        if (tid < 32 && c * kRedChunk + tid < NV) {
-            double t = 0.0;
+    for (int o = 16, half = NP / 2; o > 0; o >>= 1, half >>= 1) {
+        const bool up = (lane & o) != 0;
 #pragma unroll
-            for (int q = 0; q < kThreads / 32; ++q) t += part[q * 32 + tid];
-            out[c * kRedChunk + tid] = t;
+        for (int k = 0; k < half; ++k) {
+            const double send = up ? a[k] : a[k + half];
+            const double keep = up ? a[k + half] : a[k];
+            a[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
+    }
+    sync();                                       // the previous call's readers are done with `red`
+#pragma unroll
+    for (int k = 0; k < PER; ++k) red[warp * NP + lane * PER + k] = a[k];
+    sync();
+    if (tid < NV) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) t += red[w * NP + tid];
+        out[tid] = t;
     }
 }
 
