@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_phase_a(StreamArgs p) {
             const int kb = (int)((hi - 1 - tile_lo) / kThreads);
             while (ka <= kb) {
                 const int left = kb - ka + 1;
-                if (left >= 4) {
+                if (left >= 3) {   // (three sub-blocks run as four with the last one masked: the small blocks are latency-bound)
                     phase_a_block<DY, M, 4, INFER, LATENT>(T, st, ka, (int)(pos - tile_lo), (int)(hi - tile_lo), sA, inv2L, rs, b, pb);
                     ka += 4;
                 } else if (left >= 2) {
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_ystats(StreamArgs p) {
             const int kb = (int)((hi - 1 - tile_lo) / kThreads);
             while (ka <= kb) {
                 const int left = kb - ka + 1;
-                if (left >= 4) {
+                if (left >= 3) {
                     ystats_block<DY, M, 4>(T, st, ka, (int)(pos - tile_lo), (int)(hi - tile_lo), inv2L, rs);
                     ka += 4;
                 } else if (left >= 2) {
@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_ystats_split(StreamArgs p) {
             const int kb = (int)((hi - 1 - tile_lo) / kThreads);
             while (ka <= kb) {
                 const int left = kb - ka + 1;
-                if (left >= 4) {
+                if (left >= 3) {
                     ystats_split_block<DY, M, 4>(T, st, ka, (int)(pos - tile_lo), (int)(hi - tile_lo), inv2L, rs);
                     ka += 4;
                 } else if (left >= 2) {
@@ -1010,7 +1010,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) k_phase_b(StreamArgs p) {
             const int kb = (int)((hi - 1 - tile_lo) / NT);
             while (ka <= kb) {
                 const int left = kb - ka + 1;
-                if (kSB >= 4 && left >= 4) {
+                if (kSB >= 4 && left >= 3) {
                     phase_b_block<DY, M, 4, NT, INFER, LATENT, PROPAGATE>(acc, p, st, ka, tile_lo, (int)(pos - tile_lo), (int)(hi - tile_lo), sAn, sAo, sC, inv2L, rs, pbv, b, pb);
                     ka += 4;
                 } else if (left >= 2) {
