@@ -101,7 +101,9 @@ struct mrgp_handle {
     double *xchg = nullptr;   // dense exchange buffer (max R) x part_stride
     const double *x = nullptr, *y = nullptr;
     double *x_ws = nullptr, *y_ws = nullptr, *y_ws2 = nullptr, *g = nullptr, *hvar = nullptr, *tmp_mean = nullptr, *tmp_var = nullptr;
-    double *part = nullptr, *elbo_out = nullptr;
+    double *part = nullptr, *elbo_out = nullptr, *elbo_part = nullptr;
+    unsigned int *elbo_counter = nullptr;
+    int elbo_chunks = 1;             // region chunks of the finest layer (grid.y of k_elbo)
     RegionArgs *elbo_args = nullptr;
     int64_t *off_staging = nullptr;
     size_t off_total = 0;
@@ -311,6 +313,13 @@ size_t carve(mrgp_handle *h, char *base) {
         h->build_part = c.take<double>(need);
     }
     h->elbo_out = c.take<double>((size_t)J * 6);
+    {
+        int r_max = 1;
+        for (int j = 0; j < J; ++j) r_max = std::max(r_max, h->plan[j].R);
+        h->elbo_chunks = (r_max + kElboRegions - 1) / kElboRegions;
+        h->elbo_part = c.take<double>((size_t)J * h->elbo_chunks * 6);
+        h->elbo_counter = c.take<unsigned int>(J);
+    }
     h->elbo_args = c.take<RegionArgs>(J);
     h->off_total = 0;
     for (int j = 0; j < J; ++j) h->off_total += h->plan[j].R + 1;
@@ -1654,6 +1663,7 @@ int mrgp_bind_workspace(mrgp_handle *h, void *dev_ptr, size_t bytes) {
     }
     CK(cudaMemsetAsync(h->chol_count, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->done_counter, 0, sizeof(unsigned int), h->stream));
+    CK(cudaMemsetAsync(h->elbo_counter, 0, (size_t)h->cfg.n_layers * sizeof(unsigned int), h->stream));
     CK(cudaMemsetAsync(h->brent_fail, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->mid_sync, 0, 2 * kMaxLayers * sizeof(unsigned int), h->stream));
     if (h->chain_status) {
@@ -1723,13 +1733,29 @@ int mrgp_set_observations(mrgp_handle *h, const double *y_dev) {
     return MRGP_OK;
 }
 
+// Host-to-device copy in chunks: on the B200 boxes of this project one 16 MB cudaMemcpyAsync from pinned memory takes 0.47 ms,
+// the same bytes as 4 MB pieces 0.31 ms (scratch/h2d_bw.py); MRGP_H2D_CHUNK_MB overrides the piece size (0: one copy).
+static cudaError_t copy_h2d_chunked(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    static const size_t chunk = [] {
+        const char *e = getenv("MRGP_H2D_CHUNK_MB");
+        return (size_t)(e ? atoi(e) : 4) << 20;
+    }();
+    if (chunk == 0 || bytes <= chunk) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    for (size_t off = 0; off < bytes; off += chunk) {
+        const size_t n = bytes - off < chunk ? bytes - off : chunk;
+        cudaError_t e = cudaMemcpyAsync(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, n, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 int mrgp_set_observations_host(mrgp_handle *h, const double *y_host) {
     if (h) h->stream_ops += 1;
     if (!h || !y_host) return fail(h, MRGP_EINVAL, "null argument");
     if (!h->have_data) return fail(h, MRGP_ESTATE, "no inputs yet: mrgp_set_data / mrgp_set_data_host first");
     if (h->prefetch_pending) return fail(h, MRGP_ESTATE, "prefetched observations are waiting to be taken over");
     const size_t N = (size_t)(h->hi - h->lo);
-    CK(cudaMemcpyAsync(h->y_ws, y_host, N * h->cfg.dy * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(copy_h2d_chunked(h->y_ws, y_host, N * h->cfg.dy * sizeof(double), h->stream));
     if (h->y != h->y_ws) drop_graph(h);
     h->y = h->y_ws;
     h->ystats_valid = false;
@@ -1752,7 +1778,7 @@ int mrgp_prefetch_observations_host(mrgp_handle *h, const double *y_host) {
     // the spare buffer held the observations before the current ones: its last readers were enqueued before the marker
     if (h->y_free_recorded) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_y_free, 0));
     const size_t N = (size_t)(h->hi - h->lo);
-    CK(cudaMemcpyAsync(h->y_ws2, y_host, N * h->cfg.dy * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    CK(copy_h2d_chunked(h->y_ws2, y_host, N * h->cfg.dy * sizeof(double), h->copy_stream));
     CK(cudaEventRecord(h->ev_copy_done, h->copy_stream));
     h->prefetch_pending = true;
     return MRGP_OK;
@@ -2357,7 +2383,7 @@ int mrgp_elbo(mrgp_handle *h, double *out_host) {
         h->elbo_args_valid = true;
         h->elbo_args_key = key;
     }
-    k_elbo<2><<<h->cfg.n_layers, 256, 0, h->stream>>>(h->elbo_args, h->elbo_out);
+    k_elbo<2><<<dim3((unsigned)h->cfg.n_layers, (unsigned)h->elbo_chunks), 256, 0, h->stream>>>(h->elbo_args, h->elbo_out, h->elbo_part, h->elbo_counter);
     CK(cudaGetLastError());
     count(h);
     CK(cudaMemcpyAsync(out_host, h->elbo_out, (size_t)h->cfg.n_layers * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

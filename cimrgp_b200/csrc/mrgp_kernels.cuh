@@ -2995,19 +2995,29 @@ __device__ __forceinline__ double block_sum_1024(double v, double *sm) {
     return t;   // valid in warp 0
 }
 
+// Grid (J, C): CTA (j, c) takes the regions [c kElboRegions, (c + 1) kElboRegions) of layer j (CTA (j, 0) also the terms
+// of the shared posterior) and leaves six partial sums; the last CTA of a layer to finish adds the partials in chunk
+// order (a fixed order: the bound is bit-reproducible).  One CTA per layer, as in round 1, walked the 512 regions x 30
+// basis functions of the finest layer with 256 threads in a chain of dependent loads: 85 us after an L2 flush.
+constexpr int kElboRegions = 32;
 template <int DY>
-__global__ void __launch_bounds__(256) k_elbo(const RegionArgs *layers, double *out /* (J, 6) */) {
+__global__ void __launch_bounds__(256) k_elbo(const RegionArgs *layers, double *out /* (J, 6) */, double *part /* (J, C, 6) */,
+                                              unsigned int *counter /* (J) */) {
     static_assert(DY == 2, "dy == 2 only");
     __shared__ double sm[32];
-    const RegionArgs a = layers[blockIdx.x];
-    const int j = blockIdx.x, M = a.M, R = a.R;
+    __shared__ int sLast;
+    const RegionArgs &a = layers[blockIdx.x];
+    const int j = blockIdx.x, c = blockIdx.y, C = gridDim.y, M = a.M, R = a.R;
+    const int r_lo = c * kElboRegions, r_hi = min(R, r_lo + kElboRegions);
+    if (r_lo >= R) return;                                    // (not counted: the layer has ceil(R / kElboRegions) chunks)
+    const int n_chunks = (R + kElboRegions - 1) / kElboRegions;
     const bool first = (j == 0);
     const double *pB = first ? a.priorB : a.axB;
     const double *pLogC = first ? a.priorLogC : a.axLogC;
     const double *pShape = first ? a.priorShape : a.ardShape;
     const double *pScale = first ? a.priorScale : a.ardScale;
     double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0;
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    for (int r = r_lo + threadIdx.x; r < r_hi; r += blockDim.x) {
         const double n = (double)(a.offsets[r + 1] - a.offsets[r]);
         const double *sb = a.sumsB + (size_t)r * (DY + 3);
         double bb = 0.0, bs = 0.0, w0w0 = 0.0, ww0 = 0.0;
@@ -3027,29 +3037,48 @@ __global__ void __launch_bounds__(256) k_elbo(const RegionArgs *layers, double *
         const double term1 = 1.0 / (tau * nm) + bb - 2.0 * ww0 + w0w0;
         t4 += (0.5 * DY * (log(tau0) + nlm - kLog2Pi) + 0.5 * tau0 * nm * term1) - (0.5 * DY * (log(tau) + nlm - kLog2Pi) - 0.5);
         // :426-447
-        const double c0 = a.noise_shape0[r], d0 = a.noise_scale0[r], c = a.noise_shape[r], d = a.noise_scale[r];
-        t5 += (c0 * log(d0) - lgamma(c0) + (c0 - 1.0) * nlm - d0 * nm) - (c * log(d) - lgamma(c) + (c - 1.0) * nlm - d * nm);
+        const double c0 = a.noise_shape0[r], d0 = a.noise_scale0[r], cc = a.noise_shape[r], d = a.noise_scale[r];
+        t5 += (c0 * log(d0) - lgamma(c0) + (c0 - 1.0) * nlm - d0 * nm) - (cc * log(d) - lgamma(cc) + (cc - 1.0) * nlm - d * nm);
     }
     // :520-533
-    for (int t = threadIdx.x; t < R * M; t += blockDim.x) {
+#pragma unroll 4
+    for (int t = r_lo * M + threadIdx.x; t < r_hi * M; t += blockDim.x) {
         const int i = t % M;
         t1 += (0.5 * a.ardLogMean[i] / a.S[t] - 0.5 * a.ardMean[i] * a.m2[t] / a.S[t]) - (0.5 * log(a.prec[t]) - 0.5);
     }
-    // :499-518 (element-wise product inside the trace -> diagonal entries only), :477-497
-    for (int t = threadIdx.x; t < M * M; t += blockDim.x) {
-        const int i = t / M, k = t % M;
-        const double w = a.omega[t];
-        t2 += w * (-pLogC[k] + a.axCov[i * 4 + 0] * pB[k * 4 + 0] + a.axCov[i * 4 + 3] * pB[k * 4 + 3]);
-        t3 += w * (pShape[k] * log(pScale[k]) - lgamma(pShape[k]) + (pShape[k] - 1.0) * a.ardLogMean[i] - pScale[k] * a.ardMean[i]);
-    }
-    for (int i = threadIdx.x; i < M; i += blockDim.x) {
-        t2 -= -a.axLogC[i] + a.axCov[i * 4 + 0] * a.axB[i * 4 + 0] + a.axCov[i * 4 + 3] * a.axB[i * 4 + 3];
-        t3 -= a.ardShape[i] * log(a.ardScale[i]) - lgamma(a.ardShape[i]) + (a.ardShape[i] - 1.0) * a.ardLogMean[i] - a.ardScale[i] * a.ardMean[i];
+    if (c == 0) {
+        // :499-518 (element-wise product inside the trace -> diagonal entries only), :477-497
+        for (int t = threadIdx.x; t < M * M; t += blockDim.x) {
+            const int i = t / M, k = t % M;
+            const double w = a.omega[t];
+            t2 += w * (-pLogC[k] + a.axCov[i * 4 + 0] * pB[k * 4 + 0] + a.axCov[i * 4 + 3] * pB[k * 4 + 3]);
+            t3 += w * (pShape[k] * log(pScale[k]) - lgamma(pShape[k]) + (pShape[k] - 1.0) * a.ardLogMean[i] - pScale[k] * a.ardMean[i]);
+        }
+        for (int i = threadIdx.x; i < M; i += blockDim.x) {
+            t2 -= -a.axLogC[i] + a.axCov[i * 4 + 0] * a.axB[i * 4 + 0] + a.axCov[i * 4 + 3] * a.axB[i * 4 + 3];
+            t3 -= a.ardShape[i] * log(a.ardScale[i]) - lgamma(a.ardShape[i]) + (a.ardShape[i] - 1.0) * a.ardLogMean[i] - a.ardScale[i] * a.ardMean[i];
+        }
     }
     double vals[6] = {t0, t1, t2, t3, t4, t5};
+    double *mine = part + ((size_t)j * C + c) * 6;
     for (int q = 0; q < 6; ++q) {
         const double s = block_sum_1024(vals[q], sm);
-        if (threadIdx.x == 0) out[j * 6 + q] = s;
+        if (threadIdx.x == 0) {
+            mine[q] = s;
+            if (n_chunks == 1) out[j * 6 + q] = s;
+        }
+    }
+    if (n_chunks == 1) return;
+    __syncthreads();
+    if (threadIdx.x == 0) sLast = (atom_add_acq_rel_gpu(counter + j, 1u) == (unsigned)n_chunks - 1u);
+    __syncthreads();
+    if (sLast) {
+        if (threadIdx.x < 6) {
+            double s = 0.0;
+            for (int k = 0; k < n_chunks; ++k) s += __ldcg(part + ((size_t)j * C + k) * 6 + threadIdx.x);
+            out[j * 6 + threadIdx.x] = s;
+        }
+        if (threadIdx.x == 0) counter[j] = 0u;
     }
 }
 
