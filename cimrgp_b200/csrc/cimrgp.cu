@@ -1521,9 +1521,6 @@ int mrgp_create(const mrgp_config *cfg, const int64_t *const *region_offsets, co
     want = (int)std::min<int64_t>(want, cap);
     int64_t q = (n_local + want - 1) / want;
     q = ((q + 31) / 32) * 32;
-    // whole tiles per CTA when a CTA has several: the ragged last tile of a range runs in the latency-bound 2- and 1-sample
-    // blocks of the streaming kernels (a quarter of the time of k_ystats at config 4); fewer, equally loaded CTAs are faster
-    if (getenv("MRGP_QUANTUM_TILE") && getenv("MRGP_QUANTUM_TILE")[0] == '1' && q >= 4 * kTile) q = ((q + kTile - 1) / kTile) * kTile;
     h->cta_quantum = q;
     h->n_ctas = (int)((n_local + q - 1) / q);
     build_plan(h);
