@@ -774,3 +774,21 @@ def test_prefetched_observations_match_synchronous_uploads():
         for key in sa:
             assert np.array_equal(sa[key], sb[key]), (k, key)
     assert np.array_equal(ea.elbo(), eb.elbo())
+
+
+@pytest.mark.parametrize('n,res', [(20000, 7), (150000, 9)])
+def test_fused_sweep_is_bit_reproducible(n, res):
+    """Two identical models swept 25 times (cluster of 4 / of 16 CTAs: DSMEM pushes, mbarrier hand-offs, background worker
+    steps): every state array and the ELBO agree bit for bit - a race in the hand-offs would show as a difference."""
+    x, y = workloads.workload1(n)
+    states = []
+    for rep in range(3):
+        m = build(x, y, 30, res, False)
+        m.fit(25, None)
+        st = m._engine.state()
+        st['elbo'] = m._engine.elbo()
+        states.append(st)
+        del m
+    for st in states[1:]:
+        for key in states[0]:
+            assert np.array_equal(states[0][key], st[key], equal_nan=True), key
