@@ -2,9 +2,9 @@
 public state) with the variational-inference sweep running on one B200 through libcimrgp.so.
 
 Same constructor arguments, same exceptions for the same misuse (MRGP.py:37-126), same meaning of every
-method.  What is NOT carried over (raises NotImplementedError with the reason): the GPy input-warp model
-(`adaptive_inputs=True` without an `input_model`; third-party GP),
-dx > 1 and dy > 2 on the device.
+method.  `adaptive_inputs=True` without an `input_model` fits the input-warp GP of cimrgp_b200/RegressionInput.py (a
+restatement of the reference's GPy call, Inputs.py:20-47; parity unpinned: GPy is absent).  What is NOT carried over
+(raises NotImplementedError with the reason): dx > 1 and dy > 2 on the device.
 """
 import numpy as np
 
@@ -113,13 +113,12 @@ class MultiResolutionGaussianProcess(object):
                 raise TypeError('the device path implements the Laplacian eigenfunction basis only')
         # Inputs.py:8-55
         if self.adaptive_inputs is True:
-            if input_model is None:
-                raise NotImplementedError('adaptive_inputs=True needs an input_model: the GPy warp model of the '
-                                          'reference (Inputs.py:22-49) is a third-party GP and out of scope')
             z = np.atleast_2d(np.linspace(start=np.min(x_train), stop=np.max(x_train), num=x_train.shape[0])).T
-            self.input_model = input_model
             self.input_z = z if self.full_x is None else np.atleast_2d(
                 np.linspace(start=np.min(self.full_x), stop=np.max(self.full_x), num=self.full_x.shape[0])).T
+            if input_model is None:      # Inputs.py:20-47: the warp x -> z as an exact RBF GP on at most 3000 points
+                input_model = self._learn_input_model(x_train if self.full_x is None else self.full_x, self.input_z, device)
+            self.input_model = input_model
             x_used = z
         else:
             self.input_model = None
@@ -186,6 +185,40 @@ class MultiResolutionGaussianProcess(object):
         self._sweeps = 0
 
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _learn_input_model(x, z, device):
+        """Inputs.py:20-47 with the reference's calls on the global RNGs in the reference's order (random.uniform, then one
+        numpy permutation per region, then one for the rest): one GP_RBF on all points up to 3000 of them, otherwise on a
+        subsample of 3000 that holds one random point of every region of a uniform split."""
+        import random
+        from .IndexSetGenerator import IndexSetUniform
+        from .RegressionInput import GP_RBF
+        train_data = [np.asarray(x, dtype=np.float64), np.asarray(z, dtype=np.float64)]
+        n_samps = train_data[0].shape[0]
+        if n_samps < 3001:
+            model = GP_RBF(device=device)
+            model.fit(train_data)
+            return model
+        n_repeats, min_length = 1, 3000
+        rate = random.uniform(.1, .2)
+        factor = (1.0 if n_samps < 10000 else 1e-1 if n_samps < 100000 else 1e-2 if n_samps < 1000000 else 1e-3) * rate
+        n_divide = int(np.floor(factor * n_samps))                     # Inputs.py:62-72
+        index_set = IndexSetUniform(sample_length=n_samps, resolution=1, divider=n_divide).index_set[-1]
+        ids_all = list(range(n_samps))
+        models = []
+        for _ in range(n_repeats):
+            ids_l = [np.random.permutation(index_set[l])[0] for l in range(len(index_set))]
+            rem_ids = np.delete(ids_all, ids_l)
+            if min_length > len(ids_l):
+                ids_rep = list(np.random.permutation(rem_ids)[0:min_length - len(ids_l)]) + ids_l
+            else:
+                ids_rep = ids_l
+            ids = list(np.sort(np.unique(ids_rep)))
+            model = GP_RBF(device=device)
+            model.fit([train_data[0][ids, :], train_data[1][ids, :]])
+            models.append(model)
+        return models
+
     def _normalize_inputs(self, x_train, full_x):
         # MRGP.py:278-295
         x = x_train if full_x is None else np.asarray(full_x, dtype=np.float64)
