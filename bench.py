@@ -394,29 +394,34 @@ def measure_e2e(m, eng, steps, flush, barrier, max_over_ranks, torch, scale=1):
         e2e_ms.append(max_over_ranks(a.elapsed_time(b)))
     # pipelined: ONE timed region around all K steps (L2 flushes included - nothing is subtracted); every step's copy,
     # statistics pass, sweep and read-back happen inside it
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.synchronize()
-    a.record(eng.stream)
-    eng.prefetch_observations()                        # observations of step 0
-    for k in range(steps):
-        flush_l2(eng, flush, torch)
-        eng.refresh_statistics()                       # takes over set k: waits for its copy, statistics pass
-        if k + 1 < steps:
-            eng.prefetch_observations()                # copy of set k + 1 on the copy stream, beside the sweep of set k
-        m.fit(n_iter=1, tol=1e-300, min_iter=1)        # one sweep + ELBO terms, read back
-    b.record(eng.stream)
-    b.synchronize()
-    pipe_ms = max_over_ranks(a.elapsed_time(b)) / steps
+    # (three runs of K steps, the median run is reported and all three are listed: one timed region per run has no per-step
+    # median to absorb a stall of the host - a 4-GPU run showed one run of 1.65 ms per step between two of 0.42 / 0.47)
+    runs = []
+    for rep in range(3):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.synchronize()
+        a.record(eng.stream)
+        eng.prefetch_observations()                        # observations of step 0
+        for k in range(steps):
+            flush_l2(eng, flush, torch)
+            eng.refresh_statistics()                       # takes over set k: waits for its copy, statistics pass
+            if k + 1 < steps:
+                eng.prefetch_observations()                # copy of set k + 1 on the copy stream, beside the sweep of set k
+            m.fit(n_iter=1, tol=1e-300, min_iter=1)        # one sweep + ELBO terms, read back
+        b.record(eng.stream)
+        b.synchronize()
+        runs.append(max_over_ranks(a.elapsed_time(b)) / steps)
+    pipe_ms = float(np.median(runs))
     return {'value': scale * 1e3 / pipe_ms, 'unit': 'it/s', 'h2d_bytes_per_step': scale * eng.N * DY * 8,
-            'd2h_bytes_per_step': scale * N_LAYERS * 6 * 8, 'ms_per_step': pipe_ms,
+            'd2h_bytes_per_step': scale * N_LAYERS * 6 * 8, 'ms_per_step': pipe_ms, 'ms_per_step_runs': [round(v, 4) for v in runs],
             'serial': {'value': scale * steps / (sum(e2e_ms) / 1e3), 'ms_per_step': float(np.mean(e2e_ms)),
                        'what': 'upload, statistics pass, sweep, read-back one after the other (L2 flush before each step, not timed)'},
             'what': 'new observations y every step at UNCHANGED inputs x (x-derived tables are reused; new inputs need the '
                     'basis rebuilt, include/cimrgp.h): y from pinned host memory through the double-buffered upload of the API '
                     '(mrgp_prefetch_observations_host: the copy of step k + 1 overlaps the sweep of step k, which reads no '
                     'sample), layer-0 statistics pass over x and y, one sweep, ELBO terms back; one timed region around all '
-                    'steps, the L2 flush of every step included',
+                    'steps of a run, the L2 flush of every step included; median of three runs',
             'lower_bound_layer0': m.lower_bound_layer[0][-1]}
 
 
