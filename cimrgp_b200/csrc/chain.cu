@@ -525,9 +525,19 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
     double *sv = sm.sv, *su = sm.su;
     double Kr[MP], Kc[MP];
     // padding (M <= index < MP): an identity block, its scalings stay at 1 and do not couple to the model's block
+    if (M == MP) {   // no padding (the headline M = 30): plain loads - the per-element selects of the general form cost 1.2 k cycles
 #pragma unroll
-    for (int k = 0; k < MP; ++k) Kr[k] = (real && k < M) ? sm.Kt[k * LD + lane] : ((row && !real && k == lane) ? 1.0 : 0.0);
-    {
+        for (int k = 0; k < MP; ++k) Kr[k] = row ? sm.Kt[k * LD + lane] : 0.0;
+        const double2 *col = reinterpret_cast<const double2 *>(sm.Kt + (row ? lane : 0) * LD);
+#pragma unroll
+        for (int i = 0; i < MP; i += 2) {
+            const double2 t = col[i >> 1];
+            Kc[i] = row ? t.x : 0.0;
+            Kc[i + 1] = row ? t.y : 0.0;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < MP; ++k) Kr[k] = (real && k < M) ? sm.Kt[k * LD + lane] : ((row && !real && k == lane) ? 1.0 : 0.0);
         const double2 *col = reinterpret_cast<const double2 *>(sm.Kt + (real ? lane : 0) * LD);
 #pragma unroll
         for (int i = 0; i < MP; i += 2) {
@@ -645,11 +655,22 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
     }
     if (real) {   // omega = diag(u) K diag(v), kept transposed for the mixing step of the next layer
         const double2 *pv = reinterpret_cast<const double2 *>(sv);
+        if (M == MP) {
+            double2 tv[MP / 2];      // all column scalings first (the column registers are free now): the loads overlap
 #pragma unroll
-        for (int k = 0; k < MP; k += 2) {
-            const double2 t = pv[k >> 1];
-            if (k < M) sm.omT[k * LD + lane] = Kr[k] * u * t.x;
-            if (k + 1 < M) sm.omT[(k + 1) * LD + lane] = Kr[k + 1] * u * t.y;
+            for (int k = 0; k < MP / 2; ++k) tv[k] = pv[k];
+#pragma unroll
+            for (int k = 0; k < MP; k += 2) {
+                sm.omT[k * LD + lane] = (Kr[k] * u) * tv[k >> 1].x;
+                sm.omT[(k + 1) * LD + lane] = (Kr[k + 1] * u) * tv[k >> 1].y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < MP; k += 2) {
+                const double2 t = pv[k >> 1];
+                if (k < M) sm.omT[k * LD + lane] = Kr[k] * u * t.x;
+                if (k + 1 < M) sm.omT[(k + 1) * LD + lane] = Kr[k + 1] * u * t.y;
+            }
         }
         sm.vout[layer][lane] = v;           // log(v) - column shift (next sweep's warm start): taken at the end of the kernel
         sm.cshift[layer][lane] = cshift;
