@@ -61,6 +61,16 @@ __device__ __forceinline__ unsigned long long gtimer() {
     do {                                                                     \
         if (m.prof) m.prof[j * 16 + (k)] = (double)clock64();                \
     } while (0)
+// Maximum over the warp for a stabilising shift: rounded UP to single precision (the shift only has to bound the largest
+// entry; any common shift of a row or column leaves omega unchanged) and reduced with one REDUX on an order-preserving
+// integer image instead of a five-step butterfly of 64-bit shuffles and compares.
+__device__ __forceinline__ double wmax_shift(double v) {
+    unsigned b = __float_as_uint(__double2float_ru(v));
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    b = __reduce_max_sync(kFull, b);
+    b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
+    return (double)__uint_as_float(b);
+}
 // N sums over the warp in lock-step: the butterflies of the N values overlap instead of running one after the other
 template <int N>
 __device__ __forceinline__ void wsum_n(double (&v)[N]) {
@@ -870,10 +880,7 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) lwv[u] = fmax(lwv[u], __shfl_xor_sync(kFull, lwv[u], o));
-        }
+        for (int u = 0; u < 4; ++u) lwv[u] = wmax_shift(lwv[u]);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
             if (lane == 0 && warp + u * 8 < M) sm.rowmax[warp + u * 8] = lwv[u];
@@ -890,10 +897,7 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
             mx[u] = v[u];
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) mx[u] = fmax(mx[u], __shfl_xor_sync(kFull, mx[u], o));
-        }
+        for (int u = 0; u < 4; ++u) mx[u] = wmax_shift(mx[u]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int k = warp + u * 8;
