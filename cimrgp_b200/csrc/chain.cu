@@ -61,6 +61,17 @@ __device__ __forceinline__ unsigned long long gtimer() {
     do {                                                                     \
         if (m.prof) m.prof[j * 16 + (k)] = (double)clock64();                \
     } while (0)
+// 1 / x for normal positive x to the last bit or two: the hardware's reciprocal estimate (20 bits) and two Newton steps.  The
+// IEEE division of the compiler is a subroutine of ~30 instructions with its special-case paths; the chain has five of them
+// in a row per layer (Bingham constants, digamma, ARD mean), the solver two per evaluation and the workers three per region.
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 // Maximum over the warp for a stabilising shift: rounded UP to single precision (the shift only has to bound the largest
 // entry; any common shift of a row or column leaves omega unchanged) and reduced with one REDUX on an order-preserving
 // integer image instead of a five-step butterfly of 64-bit shuffles and compares.
@@ -177,9 +188,9 @@ struct ChainSmem {
 // covariance (ARD, Posteriors.py:533-541; see k_mid1).
 __device__ __forceinline__ void p1_finish(const ChainLayer &ly, size_t ri, double y0, double y1, double dsum, double S, double noise,
                                           double ard, double (&acc)[7]) {
-    const double is = 1.0 / S;
+    const double is = rcp_fast(S);
     const double prec = fma(ard, is, noise * dsum);      // Posteriors.py:40-42: ard / S + noise sum phi^2
-    const double ip = 1.0 / prec;
+    const double ip = rcp_fast(prec);
     const double zeta = noise * ip;
     *reinterpret_cast<double2 *>(ly.ytil + ri * 2) = make_double2(y0, y1);
     ly.prec[ri] = prec;
@@ -251,10 +262,10 @@ __device__ __forceinline__ void mid1_upper(const ChainModel &m, const ChainLayer
 // rc: the region's constants [n, bias_prec0, bias_mean0 (2), noise_shape0, noise_scale0, digamma(noise shape), -].
 __device__ __forceinline__ void bias_noise_update(const ChainLayer &ly, int l, bool infer, const double (&sums)[5], const double (&rc)[7],
                                                   double noise_old, double b0, double b1) {
-    const double n = rc[0], bp0 = rc[1], bp = bp0 + n, ibp = 1.0 / bp;
+    const double n = rc[0], bp0 = rc[1], bp = bp0 + n, ibp = rcp_fast(bp);
     const double mn0 = ibp * (rc[2] * bp0 + sums[0]), mn1 = ibp * (rc[3] * bp0 + sums[1]);
     const double t3 = bp0 * (rc[2] * rc[2] + rc[3] * rc[3]), t4 = bp * (mn0 * mn0 + mn1 * mn1);
-    const double yvar = infer ? 1.0 / noise_old : 0.0;
+    const double yvar = infer ? rcp_fast(noise_old) : 0.0;
     const double shape = rc[4] + 0.5 * 2.0 * n;
     const double scale = rc[5] + 0.5 * (t3 - t4 + sums[2] + sums[3] + sums[4] + yvar);
     *reinterpret_cast<double2 *>(ly.bias_prev + (size_t)l * 2) = make_double2(b0, b1);
@@ -264,7 +275,7 @@ __device__ __forceinline__ void bias_noise_update(const ChainLayer &ly, int l, b
     ly.bias_var[l] = ibp;
     ly.noise_shape[l] = shape;
     ly.noise_scale[l] = scale;
-    ly.noise_mean[l] = shape / scale;
+    ly.noise_mean[l] = shape * rcp_fast(scale);
     ly.noise_log_mean[l] = rc[6] - log(scale);
 #pragma unroll
     for (int d = 0; d < 5; ++d) ly.sumsB[(size_t)l * 5 + d] = sums[d];
@@ -277,7 +288,7 @@ __device__ __forceinline__ void s2_region(const ChainLayer &ly, size_t ri, bool 
     an = make_double2(zeta * cy0, zeta * cy1);
     const double z2 = zeta * zeta;
     const double ccy0 = c00 * cy0 + c01 * cy1, ccy1 = c01 * cy0 + c11 * cy1;
-    const double ip = 1.0 / prec;
+    const double ip = rcp_fast(prec);
     const double m2 = ip + z2 * (yt.x * cy0 + yt.y * cy1);
     cm2 = ip + z2 * (yt.x * (cy0 - ccy0) + yt.y * (cy1 - ccy1));
     if (on) {
@@ -502,7 +513,7 @@ __device__ __forceinline__ float omega_eval(const double (&Kr)[MP], const double
             r1 = fma(Kr[k + 1], t.y, r1);
         }
     }
-    u = row ? 1.0 / ((r0 + r1) + (r2 + r3)) : 0.0;
+    u = row ? rcp_fast((r0 + r1) + (r2 + r3)) : 0.0;
     su[lane] = u;
     __syncwarp();
     double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
@@ -520,7 +531,7 @@ __device__ __forceinline__ float omega_eval(const double (&Kr)[MP], const double
     }
     const double s = (c0 + c1) + (c2 + c3);
     c = row ? v * s : 1.0;
-    v_sinkhorn = row ? 1.0 / s : 1.0;
+    v_sinkhorn = row ? rcp_fast(s) : 1.0;
     const float e = row ? fabsf((float)(c - 1.0)) : 0.0f;      // NaN stays NaN; |.| >= 0: floats order like their bit patterns
     const unsigned bits = __reduce_max_sync(kFull, __float_as_uint(e));
     return __uint_as_float(bits);
@@ -639,7 +650,7 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
             const double m11 = kD * kD - a02 * a02, m12 = a01 * a02 - kD * a12, m22 = kD * kD - a01 * a01;
             const double det = kD * m00 + a01 * m01 + a02 * m02;
             if (det > 1e-12) {
-                const double idet = 1.0 / det;
+                const double idet = rcp_fast(det);
                 const double c0 = (m00 * r0 + m01 * r1 + m02 * r2) * idet * d0;     // gamma
                 const double c1 = (m01 * r0 + m11 * r1 + m12 * r2) * idet * d1;
                 const double c2 = (m02 * r0 + m12 * r1 + m22 * r2) * idet * d2;
@@ -714,13 +725,13 @@ __device__ __forceinline__ void bingham2_chain(double a, double b, double c, Bin
         p01 = b * ih;
     }
     const double l1 = mid + h, l2 = mid - h, gap = l1 - l2;
-    const double u = 0.5 * (1.0 + 1.0 / (sqrt(fma(gap, gap, 1.0)) + gap));
+    const double u = 0.5 * (1.0 + rcp_fast(sqrt(fma(gap, gap, 1.0)) + gap));
     const double ug = u + gap;
-    const double r0 = 1.0 / u, r1 = 1.0 / ug;
+    const double r0 = rcp_fast(u), r1 = rcp_fast(ug);
     const double k2 = 0.5 * (r0 * r0 + r1 * r1), k3 = r0 * r0 * r0 + r1 * r1 * r1;
     const double q = ug * r0;
     out.logc = 0.5 * (kLog2Pi - log(0.5 * (q + u * r1))) + u + l1;
-    const double ik2 = 1.0 / k2, dsumlogdt = -(r0 + r1);
+    const double ik2 = rcp_fast(k2), dsumlogdt = -(r0 + r1);
     const double rr[2] = {r0, r1};
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -748,13 +759,13 @@ __device__ __forceinline__ double digamma_chain(double x) {
         den *= x;
         x += 1.0;
     }
-    const double inv = 1.0 / x;
+    const double inv = rcp_fast(x);
     const double i2 = inv * inv;
     const double series =
         i2 * (1.0 / 12.0 -
               i2 * (1.0 / 120.0 -
                     i2 * (1.0 / 252.0 - i2 * (1.0 / 240.0 - i2 * (1.0 / 132.0 - i2 * (691.0 / 32760.0 - i2 * (1.0 / 12.0)))))));
-    return (log(x) - 0.5 * inv - series) - num / den;
+    return (log(x) - 0.5 * inv - series) - num * rcp_fast(den);
 }
 
 // ---- the shared step of a layer on CTA 0 (256 threads) ------------------------------------------------------------
@@ -851,7 +862,7 @@ __device__ __forceinline__ void shared_step(const ChainModel &m, ChainSmem &sm, 
                              (sm.data[4 * 32 + i] * sm.cov[i * 4 + 0] + 2.0 * sm.data[5 * 32 + i] * sm.cov[i * 4 + 1] + sm.data[6 * 32 + i] * sm.cov[i * 4 + 3]);
         const double shape = sm.sh[i];
         const double scale = sm.sc[i] + 0.5 * beta2;
-        const double mean = shape / scale, lmean = sm.dg[i] - log(scale);
+        const double mean = shape * rcp_fast(scale), lmean = sm.dg[i] - log(scale);
         sm.shape[i] = shape;
         sm.scale[i] = scale;
         sm.mean[i] = mean;
