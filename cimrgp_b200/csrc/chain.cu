@@ -494,7 +494,7 @@ __device__ __forceinline__ void mid2_stats_upper(const ChainModel &m, const Chai
 // P = diag(u) K diag(v)).  Lane i keeps BOTH row i (Kr) and column i (Kc) of the table in registers, v and u travel
 // through two 32-entry arrays in shared memory (broadcast loads): no transposes and no shuffles inside the loop.
 // Returns max |c - 1| (reduced in single precision: one REDUX instead of a five-step butterfly; it only steers the
-// iteration) - NaN if any entry is NaN - and the Sinkhorn column step v / c = 1 / s.
+// iteration) - NaN if any entry is NaN - and the column sums s (the Sinkhorn column step is v / c = 1 / s).
 template <int MP>
 __device__ __forceinline__ float omega_eval(const double (&Kr)[MP], const double (&Kc)[MP], double *sv, double *su, double v, double &u,
                                             double &c, double &v_sinkhorn, bool row, int lane) {
@@ -531,7 +531,7 @@ __device__ __forceinline__ float omega_eval(const double (&Kr)[MP], const double
     }
     const double s = (c0 + c1) + (c2 + c3);
     c = row ? v * s : 1.0;
-    v_sinkhorn = row ? rcp_fast(s) : 1.0;
+    v_sinkhorn = row ? s : 1.0;                                 // (the column sum itself: the Sinkhorn step is v / c = 1 / s)
     const float e = row ? fabsf((float)(c - 1.0)) : 0.0f;      // NaN stays NaN; |.| >= 0: floats order like their bit patterns
     const unsigned bits = __reduce_max_sync(kFull, __float_as_uint(e));
     return __uint_as_float(bits);
@@ -599,7 +599,7 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
             err_prev = INFINITY;
             continue;
         }
-        const double fr = real ? log(vs) - x : 0.0;       // g(x) - x, not centred yet
+        const double fr = real ? -log(vs) - x : 0.0;      // g(x) - x = -log(K^T u) - x, not centred yet
         if (!(err <= err_prev)) {                         // the residual grew: drop the history, plain step from here
             nh = 0;
             have_prev = false;
@@ -672,7 +672,7 @@ __device__ __noinline__ void omega_solve_warp(const ChainModel &m, ChainSmem &sm
         const double err = (double)omega_eval<MP>(Kr, Kc, sv, su, v, u, c, vs, row, lane);
         if (err < kOmegaTol || !isfinite(err)) break;
         ++iters;
-        if (real) v = fmax(1e-280, fmin(1e280, vs));
+        if (real) v = fmax(1e-280, fmin(1e280, rcp_fast(vs)));
     }
     if (real) {   // omega = diag(u) K diag(v), kept transposed for the mixing step of the next layer
         const double2 *pv = reinterpret_cast<const double2 *>(sv);
@@ -725,7 +725,8 @@ __device__ __forceinline__ void bingham2_chain(double a, double b, double c, Bin
         p01 = b * ih;
     }
     const double l1 = mid + h, l2 = mid - h, gap = l1 - l2;
-    const double u = 0.5 * (1.0 + rcp_fast(sqrt(fma(gap, gap, 1.0)) + gap));
+    const double g1 = fma(gap, gap, 1.0);
+    const double u = 0.5 * (1.0 + rcp_fast(g1 * rsqrt(g1) + gap));       // sqrt(1 + gap^2) as x rsqrt(x), x >= 1
     const double ug = u + gap;
     const double r0 = rcp_fast(u), r1 = rcp_fast(ug);
     const double k2 = 0.5 * (r0 * r0 + r1 * r1), k3 = r0 * r0 * r0 + r1 * r1 * r1;
