@@ -236,7 +236,7 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'it/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps, 'step_ms': [round(1e3 * t, 2) for t in times],
         'steps_timed': args.steps, 'extrapolated': False,
-        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'higher_is_better': True, 'scaling': 'weak' if world > 1 else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': CONFIG,
         'cpu_baseline': {'value': value, 'unit': 'it/s', 'cores': threads, 'kind': 'port', 'host_cores': os.cpu_count(),
                          'sample': '%d full sweeps at the stated config (N=1e6, 10 layers, every layer streams its samples twice, as '
@@ -245,7 +245,9 @@ def run_reference(args, rank, world):
         'e2e': {'value': value, 'unit': 'it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'reference_unmodified': calib,
         'note': 'kind "port": the reference is single-threaded Python (295 s per sweep at this config in the survey container); '
-                'its own speed is calibrated under reference_unmodified',
+                'its own speed is calibrated under reference_unmodified'
+                + ('' if world == 1 else '; --gpus %d: the GPU arm runs %d independent models (one per GPU) - on the host they share the '
+                   'same cores, so the aggregate CPU rate of %d models is the rate of one model on all cores, which is what is timed' % (world, world, world)),
     }
     print(json.dumps(_finite(line)))
 
