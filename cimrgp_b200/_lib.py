@@ -79,6 +79,8 @@ SIGNATURES = {
     'mrgp_group_destroy': (None, [_P]),
     'mrgp_synchronize': (C.c_int, [_P]),
     'mrgp_elbo': (C.c_int, [_P, _D]),
+    'mrgp_elbo_async': (C.c_int, [_P, _P, C.c_int32]),
+    'mrgp_elbo_wait': (C.c_int, [_P, C.c_int32]),
     'mrgp_predict_mean': (C.c_int, [_P, _P, C.c_int64, _I64PP, C.c_int32, _P]),
     'mrgp_predict_var_indexed': (C.c_int, [_P, _P, C.c_int64, _I64PP, C.c_int32, _P]),
     'mrgp_predict_var': (C.c_int, [_P, _P, C.c_int64, _P]),

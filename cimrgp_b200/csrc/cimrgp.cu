@@ -115,7 +115,8 @@ struct mrgp_handle {
     std::vector<cudaEvent_t> ev_fork, ev_join, ev_ard, ev_mid2;
     cudaEvent_t ev_prefetch = nullptr, ev_b0_fork = nullptr, ev_b0_done = nullptr;
     cudaStream_t copy_stream = nullptr;   // mrgp_prefetch_observations_host: uploads beside the handle's stream
-    cudaEvent_t ev_copy_done = nullptr, ev_y_free = nullptr;
+    cudaEvent_t ev_copy_done = nullptr, ev_y_free = nullptr, ev_elbo[2] = {nullptr, nullptr};
+    bool elbo_no_sync = false;
     bool prefetch_pending = false, y_free_recorded = false;
     cudaStream_t side2 = nullptr;    // layer 0's phase B beside the chain of layer 1 (closed-form ci sweeps)
     bool b0_pending = false;
@@ -1568,6 +1569,8 @@ void mrgp_destroy(mrgp_handle *h) {
     if (h->ev_b0_done) cudaEventDestroy(h->ev_b0_done);
     if (h->side2) cudaStreamDestroy(h->side2);
     if (h->ev_copy_done) cudaEventDestroy(h->ev_copy_done);
+    for (int q = 0; q < 2; ++q)
+        if (h->ev_elbo[q]) cudaEventDestroy(h->ev_elbo[q]);
     if (h->ev_y_free) cudaEventDestroy(h->ev_y_free);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int q = 0; q < kMaxRanks; ++q)
@@ -2387,7 +2390,29 @@ int mrgp_elbo(mrgp_handle *h, double *out_host) {
     CK(cudaGetLastError());
     count(h);
     CK(cudaMemcpyAsync(out_host, h->elbo_out, (size_t)h->cfg.n_layers * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->elbo_no_sync) return MRGP_OK;
     CK(cudaStreamSynchronize(h->stream));
+    return MRGP_OK;
+}
+
+// The lower bound without the host round trip on the chain of a step: the terms are copied into pinned host memory behind the
+// kernel and an event marks the copy; mrgp_elbo_wait(h, slot) blocks until the terms of that slot have arrived.  Two slots:
+// a consumer that reads the result of step k while step k + 1 is already queued never idles the GPU.
+int mrgp_elbo_async(mrgp_handle *h, double *out_pinned_host, int32_t slot) {
+    if (!h || slot < 0 || slot > 1) return fail(h, MRGP_EINVAL, "slot must be 0 or 1");
+    if (!h->ev_elbo[slot]) CK(cudaEventCreateWithFlags(&h->ev_elbo[slot], cudaEventDisableTiming));
+    h->elbo_no_sync = true;
+    const int rc = mrgp_elbo(h, out_pinned_host);
+    h->elbo_no_sync = false;
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_elbo[slot], h->stream));
+    return MRGP_OK;
+}
+
+int mrgp_elbo_wait(mrgp_handle *h, int32_t slot) {
+    if (!h || slot < 0 || slot > 1) return fail(h, MRGP_EINVAL, "slot must be 0 or 1");
+    if (!h->ev_elbo[slot]) return fail(h, MRGP_ESTATE, "no mrgp_elbo_async on this slot yet");
+    CK(cudaEventSynchronize(h->ev_elbo[slot]));
     return MRGP_OK;
 }
 

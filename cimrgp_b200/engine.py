@@ -233,6 +233,17 @@ class Engine(object):
         self._ck(self.lib.mrgp_elbo(self.handle, _dptr(out)))
         return out
 
+    def elbo_async(self, slot):
+        """Queue the lower bound (six terms per layer) and its copy into pinned host memory; elbo_result(slot) returns it.
+        Two slots (0, 1): read the bound of step k after queueing step k + 1."""
+        if getattr(self, '_elbo_pinned', None) is None:
+            self._elbo_pinned = [self.torch.zeros((self.J, 6), dtype=self.torch.float64).pin_memory() for _ in range(2)]
+        self._ck(self.lib.mrgp_elbo_async(self.handle, C.c_void_p(self._elbo_pinned[slot].data_ptr()), int(slot)))
+
+    def elbo_result(self, slot):
+        self._ck(self.lib.mrgp_elbo_wait(self.handle, int(slot)))
+        return self._elbo_pinned[slot].numpy().copy()
+
     def launch_count(self):
         return int(self.lib.mrgp_launch_count(self.handle))
 

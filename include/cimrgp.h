@@ -220,6 +220,11 @@ int mrgp_synchronize(mrgp_handle *h);
  * noise (MRGP.py:414-569; ci only).  Under adaptive intervals the data term uses the re-learnt basis of every
  * layer against the targets inferred with the previous one, as the reference does (MRGP.py:535-569 after :640). */
 int mrgp_elbo(mrgp_handle *h, double *out_host);
+/* The same without blocking: the terms are copied into PINNED host memory behind the kernel on the handle's stream and
+ * mrgp_elbo_wait(h, slot) blocks until the copy of that slot (0 or 1) has arrived.  A consumer that reads the bound of step k
+ * after queueing step k + 1 keeps the host round trip off the chain of a step (bench.py, e2e).                          */
+int mrgp_elbo_async(mrgp_handle *h, double *out_pinned_host, int32_t slot);
+int mrgp_elbo_wait(mrgp_handle *h, int32_t slot);
 
 /* ---- O1: prediction (MRGP.py:726-861) --------------------------------------------------------- */
 

@@ -792,3 +792,16 @@ def test_fused_sweep_is_bit_reproducible(n, res):
     for st in states[1:]:
         for key in states[0]:
             assert np.array_equal(states[0][key], st[key], equal_nan=True), key
+
+
+def test_elbo_async_matches_blocking_call():
+    x, y = workloads.workload1(20000)
+    m = build(x, y, 30, 6, False)
+    m.fit(3, None)
+    e = m._engine
+    ref = e.elbo()
+    e.elbo_async(0)
+    e.sweep(1)
+    e.elbo_async(1)
+    assert np.array_equal(e.elbo_result(0), ref)
+    assert np.array_equal(e.elbo_result(1), e.elbo())
