@@ -62,3 +62,36 @@ def test_gp_rbf_has_no_cpu_path():
     x, z = _warp(20)
     with pytest.raises(RuntimeError):
         GP_RBF().fit([x, z])
+
+
+def test_subsample_draws_follow_the_reference_order(monkeypatch):
+    """Inputs.py:24-47 on the global RNGs (random.uniform once, one numpy permutation per region, one for the rest), with the
+    GP fit itself stubbed out: 3000 distinct, sorted indices that hold one point of every region."""
+    import random
+    from cimrgp_b200 import IndexSetUniform
+    from cimrgp_b200 import RegressionInput
+    from cimrgp_b200.MRGP import MultiResolutionGaussianProcess as M
+    seen = {}
+
+    def fake_fit(self, train_data):
+        seen['x'] = train_data[0]
+        return True
+
+    monkeypatch.setattr(RegressionInput.GP_RBF, 'fit', fake_fit)
+    n = 5000
+    x, z = _warp(n, 4)
+    x = x + np.arange(n)[:, None] * 1e-9            # distinct values: the rows identify the indices
+    random.seed(11)
+    np.random.seed(11)
+    models = M._learn_input_model(x, z, 0)
+    after = (random.random(), np.random.rand())
+    assert isinstance(models, list) and len(models) == 1 and seen['x'].shape == (3000, 1)
+    random.seed(11)
+    np.random.seed(11)
+    rate = random.uniform(.1, .2)
+    sets = IndexSetUniform(sample_length=n, resolution=1, divider=int(np.floor(rate * n))).index_set[-1]
+    ids_l = [np.random.permutation(s)[0] for s in sets]
+    rest = np.random.permutation(np.delete(list(range(n)), ids_l))[0:3000 - len(ids_l)]
+    ids = np.sort(np.unique(list(rest) + ids_l))
+    assert after == (random.random(), np.random.rand())
+    assert np.array_equal(seen['x'], x[ids, :])
