@@ -242,8 +242,37 @@ class MultiResolutionGaussianProcess(object):
         return y_var / snr_ratio
 
     # ------------------------------------------------------------------------------------------
+    def omega_solve_report(self):
+        """Evaluations of the permutation-weight solve (Stats.py:413-420) per layer in the last sweep (ci mode).  Warns when a
+        layer used up its budget (the accelerated iteration and the 2000 plain Sinkhorn sweeps behind it) without reaching
+        the tolerance 1e-10 on the column sums: the weights of that layer are then the last iterate, rows exact.  Tables of
+        the model converge in 2-15 evaluations.  Such a model is switched to the multi-kernel sweep (Sinkhorn / Newton solver,
+        Engine.set_fused(False)) for the sweeps that follow."""
+        if self.forced_independence or self._sweeps == 0:
+            return None
+        try:
+            iters = np.asarray(self._engine.get(-1, 51, (self.n_layers,)), dtype=np.float64)
+        except (AttributeError, _lib.MrgpError):      # (an engine without the per-layer counters)
+            return None
+        bad = [j for j in range(self.n_layers) if iters[j] >= 2040]
+        if bad:
+            import warnings
+            warnings.warn('the omega solve of layer(s) %s did not reach its tolerance in the last sweep (%s evaluations); '
+                          'this model takes the multi-kernel sweep with the Sinkhorn / Newton solver from now on'
+                          % (bad, [int(iters[j]) for j in bad]), RuntimeWarning)
+            if hasattr(self._engine, 'set_fused'):
+                self._engine.set_fused(False)
+        return iters
+
     def fit(self, n_iter=1, tol=1e-3, min_iter=10):
         # MRGP.py:367-412
+        try:
+            return self._fit_loop(n_iter, tol, min_iter)
+        finally:
+            if n_iter > 0:
+                self.omega_solve_report()
+
+    def _fit_loop(self, n_iter, tol, min_iter):
         if tol is None:
             self._engine.sweep(n_iter)
             self._engine.synchronize()

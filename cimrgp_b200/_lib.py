@@ -56,6 +56,7 @@ SIGNATURES = {
     'mrgp_set_observations_host': (C.c_int, [_P, _P]),
     'mrgp_prefetch_observations_host': (C.c_int, [_P, _P]),
     'mrgp_prefetch_sync': (C.c_int, [_P]),
+    'mrgp_set_fused': (C.c_int, [_P, C.c_int32]),
     'mrgp_set_spectral': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double]),
     'mrgp_build_basis': (C.c_int, [_P, C.c_int32, C.c_double, _D]),
     'mrgp_init_state': (C.c_int, [_P, C.c_double, C.c_double]),

@@ -1787,6 +1787,18 @@ int mrgp_prefetch_observations_host(mrgp_handle *h, const double *y_host) {
     return MRGP_OK;
 }
 
+// Switch between the fused ci sweep and the multi-kernel sweep (the environment variable MRGP_FUSED sets the start value).
+// Both keep the same state arrays; the captured graph is dropped.
+int mrgp_set_fused(mrgp_handle *h, int32_t on) {
+    if (!h) return MRGP_EINVAL;
+    if (h->fused != (on != 0)) {
+        h->fused = on != 0;
+        h->direct_launch = false;
+        drop_graph(h);
+    }
+    return MRGP_OK;
+}
+
 // Blocks the caller until the last mrgp_prefetch_observations_host() has read its host buffer (which may then be reused).
 int mrgp_prefetch_sync(mrgp_handle *h) {
     if (!h) return MRGP_EINVAL;

@@ -233,6 +233,10 @@ class Engine(object):
         self._ck(self.lib.mrgp_elbo(self.handle, _dptr(out)))
         return out
 
+    def set_fused(self, on):
+        """False: the multi-kernel sweep (Sinkhorn / Newton omega solve) from now on; True: the fused sweep where it applies."""
+        self._ck(self.lib.mrgp_set_fused(self.handle, 1 if on else 0))
+
     def elbo_async(self, slot):
         """Queue the lower bound (six terms per layer) and its copy into pinned host memory; elbo_result(slot) returns it.
         Two slots (0, 1): read the bound of step k after queueing step k + 1."""

@@ -214,6 +214,10 @@ int mrgp_sweep(mrgp_handle *h, int32_t n_iter);
  * mrgp_sweep refreshes them on demand; this entry does it now (asynchronously on the handle's stream), e.g. right after
  * mrgp_set_observations_host.  A no-op for models that take the multi-kernel sweep.                             */
 int mrgp_refresh_statistics(mrgp_handle *h);
+/* on = 0: this handle takes the multi-kernel sweep (Sinkhorn / Newton omega solve) from now on; on = 1: the fused sweep
+ * again where it applies.  Same state either way (results agree to summation order).  The host mirror switches a model
+ * over when the accelerated omega solve of the fused sweep used up its budget on a layer (MRGP.omega_solve_report). */
+int mrgp_set_fused(mrgp_handle *h, int32_t on);
 int mrgp_synchronize(mrgp_handle *h);
 
 /* E1-E6: the six ELBO terms per layer, out_host (J, 6) in the order data, scale|axis, axis, ard, bias,

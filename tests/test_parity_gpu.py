@@ -805,3 +805,18 @@ def test_elbo_async_matches_blocking_call():
     e.elbo_async(1)
     assert np.array_equal(e.elbo_result(0), ref)
     assert np.array_equal(e.elbo_result(1), e.elbo())
+
+
+def test_switch_from_the_fused_to_the_multi_kernel_sweep(monkeypatch):
+    """Engine.set_fused(False) in the middle of a fit (what the host does when the accelerated omega solve of the fused sweep
+    runs out of budget): same state arrays, results equal to a model that took the multi-kernel sweep throughout."""
+    x, y = workloads.workload1(20000)
+    a = build(x, y, 30, 6, False)
+    a.fit(2, None)
+    assert a.omega_solve_report().max() < 100
+    a._engine.set_fused(False)
+    a.fit(2, None)
+    monkeypatch.setenv('MRGP_FUSED', '0')
+    b = build(x, y, 30, 6, False)
+    b.fit(4, None)
+    compare(a._engine.state(latent=False), b._engine.state(latent=False), rtol=1e-9)
