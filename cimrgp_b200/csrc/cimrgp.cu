@@ -1730,14 +1730,16 @@ int mrgp_set_observations(mrgp_handle *h, const double *y_dev) {
     if (!h || !y_dev) return fail(h, MRGP_EINVAL, "null argument");
     if (!h->have_data) return fail(h, MRGP_ESTATE, "no inputs yet: mrgp_set_data / mrgp_set_data_host first");
     if (((uintptr_t)y_dev & 15) != 0) return fail(h, MRGP_EINVAL, "y must be 16-byte aligned (bulk copies)");
+    if (h->prefetch_pending) return fail(h, MRGP_ESTATE, "prefetched observations are waiting to be taken over");
     if (h->y != y_dev) drop_graph(h);   // the captured kernels hold the pointer
     h->y = y_dev;
     h->ystats_valid = false;
     return MRGP_OK;
 }
 
-// Host-to-device copy in chunks: on the B200 boxes of this project one 16 MB cudaMemcpyAsync from pinned memory takes 0.47 ms,
-// the same bytes as 4 MB pieces 0.31 ms (scratch/h2d_bw.py); MRGP_H2D_CHUNK_MB overrides the piece size (0: one copy).
+// Host-to-device copy in pieces of MRGP_H2D_CHUNK_MB (default 4, 0: one copy).  In isolation 16 MB from pinned memory took
+// 0.47 ms as one cudaMemcpyAsync and 0.31 ms as 4 MB pieces on the boxes of this project (scratch/h2d_bw.py, noisy); inside
+// bench.py the piece size made no difference (the copy is hidden behind the sweep).
 static cudaError_t copy_h2d_chunked(void *dst, const void *src, size_t bytes, cudaStream_t st) {
     static const size_t chunk = [] {
         const char *e = getenv("MRGP_H2D_CHUNK_MB");
