@@ -156,7 +156,8 @@ int mrgp_set_observations_host(mrgp_handle *h, const double *y_host);
  *     mrgp_refresh_statistics(h);  mrgp_prefetch_observations_host(h, y_next);  mrgp_sweep(h, 1);  ... read results ...
  * (reference counterpart: a new MultiResolutionGaussianProcess([x, y_next], ...) per data set, MRGP.py:16-66).          */
 int mrgp_prefetch_observations_host(mrgp_handle *h, const double *y_host);
-/* Blocks until the last mrgp_prefetch_observations_host() has read its host buffer (the buffer may then be rewritten). */
+/* Blocks until the last mrgp_prefetch_observations_host() has read its host buffer (the buffer may then be rewritten).
+ * (No counterpart in the reference, which is synchronous NumPy.)                                                     */
 int mrgp_prefetch_sync(mrgp_handle *h);
 
 /* ---- K1-K3: basis intervals, eigenvalues, spectral density, sum phi^2 ---------------------------- */
@@ -216,7 +217,8 @@ int mrgp_sweep(mrgp_handle *h, int32_t n_iter);
 int mrgp_refresh_statistics(mrgp_handle *h);
 /* on = 0: this handle takes the multi-kernel sweep (Sinkhorn / Newton omega solve) from now on; on = 1: the fused sweep
  * again where it applies.  Same state either way (results agree to summation order).  The host mirror switches a model
- * over when the accelerated omega solve of the fused sweep used up its budget on a layer (MRGP.omega_solve_report). */
+ * over when the accelerated omega solve of the fused sweep used up its budget on a layer (MRGP.omega_solve_report).
+ * Both are the sweep of MRGP.py:571-652; the permutation weights are Stats.py:390-445 either way.                    */
 int mrgp_set_fused(mrgp_handle *h, int32_t on);
 int mrgp_synchronize(mrgp_handle *h);
 
@@ -224,7 +226,7 @@ int mrgp_synchronize(mrgp_handle *h);
  * noise (MRGP.py:414-569; ci only).  Under adaptive intervals the data term uses the re-learnt basis of every
  * layer against the targets inferred with the previous one, as the reference does (MRGP.py:535-569 after :640). */
 int mrgp_elbo(mrgp_handle *h, double *out_host);
-/* The same without blocking: the terms are copied into PINNED host memory behind the kernel on the handle's stream and
+/* The same (MRGP.py:414-569) without blocking: the terms are copied into PINNED host memory behind the kernel on the handle's stream and
  * mrgp_elbo_wait(h, slot) blocks until the copy of that slot (0 or 1) has arrived.  A consumer that reads the bound of step k
  * after queueing step k + 1 keeps the host round trip off the chain of a step (bench.py, e2e).                          */
 int mrgp_elbo_async(mrgp_handle *h, double *out_pinned_host, int32_t slot);
